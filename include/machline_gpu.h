@@ -1,0 +1,190 @@
+/*
+ * machline_gpu.h -- C ABI of the B200 (sm_100a) replacement for MachLine's two hot paths:
+ *   (1) AIC assembly  (reference: src/panel_solver.f90:651-775 DoD pre-pass,
+ *                                  src/panel_solver.f90:1290-1501 calc_body_influences,
+ *                                  src/panel_solver.f90:1504-1706 calc_wake_influences,
+ *                                  src/panel_solver.f90:1203-1287 update_system_row,
+ *                                  src/panel.f90:1732-2971 check_dod .. calc_potential_influences)
+ *   (2) dense solve   (reference: src/panel_solver.f90:1802-2027 solve_system,
+ *                                  common/linalg.f90:118-342 lu_solve, :1235-1334 GMRES,
+ *                                  :1337-1453 restarted_GMRES, :601-728 block_jacobi_solve,
+ *                                  :1798-1831 diagonal_preconditioner)
+ *
+ * The reference has no FFI; the two seams are the Fortran call sites
+ *   call this%calc_body_influences(body) / call this%calc_wake_influences(body)   (panel_solver.f90:1072,1075)
+ *   select case(this%matrix_solver) ... end select                                (panel_solver.f90:1915-1975)
+ * A Fortran bind(C) shim flattens type(panel)/type(control_point) into the
+ * plain arrays below and calls these entry points.  Everything is 0-based on this side of the ABI.
+ *
+ * All pointers are HOST pointers owned by the caller for the duration of the call only.
+ * Every entry point returns ml_status; none of them aborts the process (the reference `stop`s).
+ * A context is bound to one CUDA device and is not thread-safe.
+ */
+#ifndef MACHLINE_GPU_H
+#define MACHLINE_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ml_ctx ml_ctx;
+
+/* Status codes: 0..4 follow the reference's solver_stat (panel_solver.f90:1722-1761, 2006-2010). */
+typedef enum ml_status {
+    ML_OK = 0,
+    ML_NAN_IN_SYSTEM = 1,      /* NaN in A or b          (check_system, panel_solver.f90:1723-1730) */
+    ML_UNINFLUENCED = 2,       /* zero row / column      (panel_solver.f90:1735-1761)               */
+    ML_SINGULAR = 3,           /* lu_decomp code 1       (linalg.f90:138-140, 205-208)              */
+    ML_NAN_RESIDUAL = 4,       /* NaN residual           (panel_solver.f90:2006-2010)               */
+    ML_BAD_ARGUMENT = 10,
+    ML_NOT_READY = 11,         /* e.g. ml_solve before ml_assemble                                  */
+    ML_UNSUPPORTED = 12,       /* feature outside the hot-path scope                    */
+    ML_CUDA_ERROR = 100,
+    ML_NCCL_ERROR = 101
+} ml_status;
+
+/* Boundary-condition codes, identical to base_geom.f90:14-20. */
+enum { ML_BC_ZERO_POTENTIAL = 1, ML_BC_SF_POTENTIAL = 2, ML_BC_ZERO_NORMAL_MF = 3,
+       ML_BC_STRENGTH_MATCHING = 4, ML_BC_ZERO_NORMAL_VEL = 5, ML_BC_ZERO_X_VEL = 6,
+       ML_BC_MF_INNER_FLOW = 7 };
+
+/* Freestream constants (type flow, src/flow.f90:11-29).  3x3 matrices are row-major. */
+typedef struct ml_flow {
+    double M_inf;
+    double B;            /* sqrt|1-M^2|                       flow.f90:100-108 */
+    double s;            /* sign(1-M^2): +1 elliptic, -1 hyperbolic            */
+    double K_inv;        /* 1/(4 pi) subsonic, 1/(2 pi) supersonic             */
+    double c_hat_g[3];   /* compressibility axis = freestream direction        */
+    double B_mat_g[9];   /* dual metric matrix   flow.f90:158-163              */
+    double C_mat_g[9];   /* metric matrix        flow.f90:174-179              */
+    int supersonic;
+    int mirror_plane;    /* 0 = none, else 1..3 = index of the normal to the mirror plane (mesh.f90:16) */
+} ml_flow;
+
+/*
+ * Panel table (type panel members used at evaluation time, src/panel.f90:38-70).
+ * n_rec = n_panels * n_images records; record r < n_panels is the panel itself, record
+ * r + n_panels its mirrored twin (the *_mir members).  Arrays are record-major (AoS inside a
+ * record, e.g. centr[3*r + c]); 3x3 matrices are row-major.
+ */
+typedef struct ml_panel_soa {
+    int n_panels;
+    int n_images;              /* 1, or 2 when mirrored twins are present                              */
+    int n_cols;                /* entries of i_vert_d per panel: M_dim (3) for body, 2*M_dim (6) wake  */
+    int in_wake;               /* 1: wake table (doublet only, bottom = -top, panel.f90:2909-2912)     */
+    const double *centr;       /* [n_rec][3]      centr / centr_mir                                    */
+    const double *A_g_to_ls;   /* [n_rec][3][3]   A_g_to_ls / A_g_to_ls_mir                            */
+    const double *vertices_ls; /* [n_rec][3][2]   vertex k -> (xi, eta) = Fortran vertices_ls(:,k)     */
+    const double *n_hat_ls;    /* [n_rec][3][2]   edge k   -> (n_xi, n_eta) = n_hat_ls(:,k)            */
+    const double *b;           /* [n_rec][3]      edge parameter (panel.f90:525-539)                   */
+    const double *sqrt_b;      /* [n_rec][3]                                                           */
+    const double *J;           /* [n_rec]         area Jacobian  (panel.f90:469)                       */
+    const int    *r;           /* [n_rec]         inclination indicator; must be +1 (panel.f90:439)    */
+    const double *area;        /* [n_panels]      A > 0 test (panel.f90:2933)                          */
+    const double *vert_g;      /* [n_rec][3][3]   global vertex locations (mirrored for the twin)      */
+    const double *T_mu;        /* [n_rec][3][3]   T_mu / T_mu_mir, row-major (mu_dim x M_dim)          */
+    const int    *i_vert_d;    /* [n_panels][n_cols] 0-based doublet unknown ids (panel.f90:618-638)   */
+    const int    *i_panel_s;   /* [n_panels]      0-based source panel id (panel.f90:680); body only   */
+    const unsigned char *has_sources;   /* [n_panels]; body only                                       */
+    const unsigned char *image_present; /* [n_panels] or NULL (= all): whether record r+n_panels is
+                                           evaluated (wake_strip%mirrored, wake_strip.f90:49)          */
+} ml_panel_soa;
+
+/* Unknown / index bookkeeping used by update_system_row (panel_solver.f90:1203-1287). */
+typedef struct ml_system_map {
+    int n_cp;                  /* rows of A                                                            */
+    int n_unknown;             /* columns of A                                                         */
+    int n_verts;               /* body%N_verts (after cloning)                                         */
+    int n_body_panels;         /* body%N_panels                                                        */
+    int n_sigma;               /* N_panels or 2*N_panels                                               */
+    int mirrored;              /* body%mirrored                                                        */
+    int asym_flow;             /* body%asym_flow                                                       */
+    const int *P;              /* [n_unknown] permutation, 0-based (panel_solver.f90:778-1030)         */
+    const unsigned char *sigma_known; /* [n_sigma]                                                     */
+    const int *i_sigma_in_sys; /* [n_sigma] 0-based unknown id (before P) or -1                        */
+    const double *sigma;       /* [n_sigma] known source strengths (panel_solver.f90:1162-1200)        */
+} ml_system_map;
+
+typedef enum ml_matrix_solver {     /* solver.matrix_solver values, panel_solver.f90:1915-1975 */
+    ML_SOLVER_LU = 0, ML_SOLVER_QRUP = 1, ML_SOLVER_FQRUP = 2, ML_SOLVER_GMRES = 3,
+    ML_SOLVER_RGMRES = 4, ML_SOLVER_PURC = 5, ML_SOLVER_BSSOR = 6, ML_SOLVER_BJAC = 7
+} ml_matrix_solver;
+
+typedef enum ml_preconditioner { ML_PREC_NONE = 0, ML_PREC_DIAG = 1 } ml_preconditioner;
+
+typedef struct ml_solver_opts {     /* defaults: panel_solver.f90:173-209 */
+    int matrix_solver;         /* ml_matrix_solver                                                      */
+    int preconditioner;        /* ml_preconditioner; DIAG reproduces linalg.f90:1813-1816 (1/A(N,N))    */
+    double tol;                /* 1e-12                                                                 */
+    double rel;                /* 0.8                                                                   */
+    int max_iterations;        /* 1000                                                                  */
+    int restart_iterations;    /* 20                                                                    */
+    int block_size;            /* <= 0 -> N/5 (panel_solver.f90:1910-1912)                              */
+    const char *iteration_file;/* NULL or "none": no iteration history                                  */
+} ml_solver_opts;
+
+typedef struct ml_solve_info {
+    int iterations;            /* -1 for direct solvers (panel_solver.f90:189)                          */
+    double res_max;            /* max |A x - b|         (panel_solver.f90:1997)                         */
+    double res_norm;           /* ||A x - b||_2         (panel_solver.f90:1998)                         */
+    double assemble_ms;        /* device time of the last ml_assemble                                   */
+    double solve_ms;           /* device time of the last ml_solve                                      */
+} ml_solve_info;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int  ml_abi_version(void);
+ml_status ml_ctx_create(ml_ctx **out, int device_id);
+void ml_ctx_destroy(ml_ctx *ctx);
+const char *ml_last_error(const ml_ctx *ctx);
+
+/* ---- inputs (host -> device) ---------------------------------------------------------------- */
+ml_status ml_set_flow(ml_ctx *ctx, const ml_flow *flow);
+/* body is required; wake may be NULL or have n_panels == 0 (panel_solver.f90:1075). */
+ml_status ml_set_panels(ml_ctx *ctx, const ml_panel_soa *body, const ml_panel_soa *wake);
+/* loc[n_cp][3], bc[n_cp] (ML_BC_*), n_g[n_cp][3] or NULL, row_perm[n_cp] = row of A that control
+   point i owns (P(i) when use_sort_for_cp, else i; panel_solver.f90:1484-1490). */
+ml_status ml_set_control_points(ml_ctx *ctx, int n_cp, const double *loc, const int *bc,
+                                const double *n_g, const int *row_perm);
+ml_status ml_set_system_map(ml_ctx *ctx, const ml_system_map *map);
+/* Multi-GPU: this context builds and owns rows [row0, row0+nrows) of the permuted system.
+   Default: all rows. */
+ml_status ml_set_row_shard(ml_ctx *ctx, int row0, int nrows);
+/* Multi-GPU: join an NCCL communicator (id = the 128-byte ncclUniqueId made by rank 0). */
+ml_status ml_set_communicator(ml_ctx *ctx, const void *nccl_unique_id, int rank, int world_size);
+
+/* ---- hot path 1: AIC assembly ---------------------------------------------------------------- */
+/* Builds A (device resident, column-major, ld = local rows) and I_known.  I_known_out (host,
+   length = local rows, indexed by local row) may be NULL. */
+ml_status ml_assemble(ml_ctx *ctx, double *I_known_out);
+/* Copy rows [row0,row0+nrows) (global row ids inside this context's shard) of A to a host
+   column-major array with leading dimension ld (parity channel = write_A_and_b). */
+ml_status ml_get_A(ml_ctx *ctx, int row0, int nrows, double *dst_colmajor, int ld);
+/* Pair count of the last ml_assemble on this context: local rows x (body records + wake records). */
+long long ml_pair_count(const ml_ctx *ctx);
+
+/* ---- hot path 2: dense solve ------------------------------------------------------------------ */
+/* BC[n_cp] is the boundary-condition vector in row order (panel_solver.f90:1104-1159); the library
+   forms b = BC - I_known (:1818), applies the reference's "preconditioner", dispatches on
+   matrix_solver, and returns x[n_unknown] (in permuted order; mu(i) = x(P(i)), :2018-2020).
+   With a communicator every rank passes the full BC and receives the full x. */
+ml_status ml_solve(ml_ctx *ctx, const ml_solver_opts *opts, const double *BC, double *x_out,
+                   ml_solve_info *info);
+
+/* Stand-alone dense solve of a host system (the lu_solve / GMRES / block_jacobi_solve signatures,
+   linalg.f90:118, 1235, 601): A is column-major N x N and is not modified. */
+ml_status ml_solve_dense(ml_ctx *ctx, int N, const double *A_colmajor, const double *b,
+                         const ml_solver_opts *opts, double *x_out, ml_solve_info *info);
+
+/* ---- introspection for tests / benches --------------------------------------------------------- */
+/* Number of kernel launches issued by this context since creation (bench.py "gpu_launches"). */
+long long ml_launch_count(const ml_ctx *ctx);
+/* Device pointers of the resident system (NULL before ml_assemble): for benches that time kernels
+   with inputs already resident. */
+ml_status ml_device_system(ml_ctx *ctx, double **A_dev, int *ld, int *nrows_local, int *ncols);
+/* Re-run the assembly kernels only (inputs resident, no host transfers); returns device ms. */
+ml_status ml_assemble_resident(ml_ctx *ctx, double *device_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MACHLINE_GPU_H */

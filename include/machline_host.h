@@ -1,0 +1,75 @@
+/*
+ * machline_host.h -- C ABI of the host-side setup library (libmachline_host.so).
+ *
+ * It restates what MachLine's `main` does around the two hot paths (src/main.f90:102-160):
+ * read the JSON input, load and analyse the mesh, build the wake, place control points, compute
+ * the per-panel tables, and -- after the solve -- turn x into mu/sigma, cell velocities, pressure
+ * coefficients, forces and moments.  It contains NO influence-coefficient or linear-solver code:
+ * those are only reachable through include/machline_gpu.h (CUDA).  The tables it hands out are
+ * exactly the arguments of ml_set_flow / ml_set_panels / ml_set_control_points / ml_set_system_map.
+ */
+#ifndef MACHLINE_HOST_H
+#define MACHLINE_HOST_H
+
+#include "machline_gpu.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mlh_case mlh_case;
+
+typedef struct mlh_cp_table {
+    int n_cp;
+    const double *loc;      /* [n_cp][3]  control_point%loc                                         */
+    const int *bc;          /* [n_cp]     control_point%bc (ML_BC_*)                                */
+    const double *n_g;      /* [n_cp][3]  normal for Neumann conditions (zeros for Dirichlet)       */
+    const int *row_perm;    /* [n_cp]     row of A owned by control point i                         */
+    const double *BC;       /* [n_cp]     boundary-condition vector in row order (:1104-1159)       */
+} mlh_cp_table;
+
+typedef struct mlh_solver_settings {   /* solver.* keys after defaults (panel_solver.f90:173-209) */
+    ml_solver_opts opts;
+    char matrix_solver_name[16];
+    char formulation[48];
+    int sort_system;
+    int write_A_and_b;
+} mlh_solver_settings;
+
+typedef struct mlh_results {
+    double C_p_max, C_p_min;  /* of the rule test/test_machline.py:62-66 reads                      */
+    double C_F[3], C_M[3];
+    int n_cells, n_mu;
+    const double *mu;         /* [n_mu]                                                             */
+    const double *C_p;        /* [n_cells] same rule as C_p_max/min                                 */
+    const double *V_cells;    /* [n_cells][3]                                                       */
+} mlh_results;
+
+typedef struct mlh_mesh_info {
+    int n_body_panels, n_body_verts, n_wake_panels, n_wake_strips, n_edges, n_cp, n_unknown;
+    int mirrored, asym_flow, mirror_plane, supersonic;
+    double sort_seconds;
+} mlh_mesh_info;
+
+/* Returns 0 on success; on failure returns nonzero and mlh_last_error() describes it (the
+   reference would have printed "!!! ..." and stopped). */
+int mlh_case_create(const char *json_text, const char *base_dir, mlh_case **out);
+void mlh_case_destroy(mlh_case *c);
+const char *mlh_last_error(void);
+
+int mlh_case_info(const mlh_case *c, mlh_mesh_info *out);
+/* Pointers stay valid until mlh_case_destroy. wake->n_panels == 0 when no wake is appended. */
+int mlh_case_tables(mlh_case *c, ml_flow *flow, ml_panel_soa *body, ml_panel_soa *wake,
+                    ml_system_map *map, mlh_cp_table *cps);
+int mlh_case_solver_settings(const mlh_case *c, mlh_solver_settings *out);
+/* x[n_unknown] in permuted order, as returned by ml_solve. Result pointers valid until the next
+   mlh_case_post or destroy. */
+int mlh_case_post(mlh_case *c, const double *x, mlh_results *out);
+/* Write report.json in the reference's layout (panel_solver.f90:2618-2746) */
+int mlh_case_write_report(mlh_case *c, const char *path, const ml_solve_info *info, int solver_stat,
+                          double total_runtime);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,357 @@
+// C ABI of the host setup library (include/machline_host.h): flattens the Case object into the
+// plain tables that the GPU library takes (ml_flow / ml_panel_soa / ml_system_map), mirroring what
+// a Fortran bind(C) shim would do with type(panel) (src/panel.f90:38-70).
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+
+#include "../../../include/machline_host.h"
+#include "model.hpp"
+
+using namespace mlh;
+
+namespace {
+
+struct PanelTableStore {
+    std::vector<double> centr, A_g_to_ls, vertices_ls, n_hat_ls, b, sqrt_b, J, area, vert_g, T_mu;
+    std::vector<int> r, i_vert_d, i_panel_s;
+    std::vector<unsigned char> has_sources, image_present;
+    int n_panels = 0, n_images = 1, n_cols = 3, in_wake = 0;
+
+    void reserve_for(int np, int ni, int ncols, int wake) {
+        n_panels = np;
+        n_images = ni;
+        n_cols = ncols;
+        in_wake = wake;
+        size_t n_rec = (size_t)np * ni;
+        centr.assign(n_rec * 3, 0.);
+        A_g_to_ls.assign(n_rec * 9, 0.);
+        vertices_ls.assign(n_rec * 6, 0.);
+        n_hat_ls.assign(n_rec * 6, 0.);
+        b.assign(n_rec * 3, 0.);
+        sqrt_b.assign(n_rec * 3, 0.);
+        J.assign(n_rec, 0.);
+        r.assign(n_rec, 1);
+        area.assign(np, 0.);
+        vert_g.assign(n_rec * 9, 0.);
+        T_mu.assign(n_rec * 9, 0.);
+        i_vert_d.assign((size_t)np * ncols, -1);
+        i_panel_s.assign(np, -1);
+        has_sources.assign(np, 0);
+        image_present.assign(np, ni > 1 ? 1 : 0);
+    }
+    void put(int j, const Panel& p, const std::vector<Vertex>& verts, bool with_mirror, int mirror_plane) {
+        for (int img = 0; img < (with_mirror ? 2 : 1); ++img) {
+            size_t rec = (size_t)j + (size_t)img * n_panels;
+            const bool m = img == 1;
+            const V3& c = m ? p.centr_mir : p.centr;
+            const M33& A = m ? p.A_g_to_ls_mir : p.A_g_to_ls;
+            for (int k = 0; k < 3; ++k) centr[rec * 3 + k] = c[k];
+            for (int a = 0; a < 3; ++a)
+                for (int bb = 0; bb < 3; ++bb) A_g_to_ls[rec * 9 + 3 * a + bb] = A[a][bb];
+            for (int k = 0; k < 3; ++k) {
+                vertices_ls[rec * 6 + 2 * k + 0] = m ? p.vertices_ls_mir[k][0] : p.vertices_ls[k][0];
+                vertices_ls[rec * 6 + 2 * k + 1] = m ? p.vertices_ls_mir[k][1] : p.vertices_ls[k][1];
+                n_hat_ls[rec * 6 + 2 * k + 0] = m ? p.n_hat_ls_mir[k][0] : p.n_hat_ls[k][0];
+                n_hat_ls[rec * 6 + 2 * k + 1] = m ? p.n_hat_ls_mir[k][1] : p.n_hat_ls[k][1];
+                b[rec * 3 + k] = m ? p.b_mir[k] : p.b[k];
+                sqrt_b[rec * 3 + k] = m ? p.sqrt_b_mir[k] : p.sqrt_b[k];
+                V3 loc = verts[p.iv[k]].loc;
+                if (m) loc = mirror_across_plane(loc, mirror_plane);
+                for (int cc = 0; cc < 3; ++cc) vert_g[rec * 9 + 3 * k + cc] = loc[cc];
+            }
+            J[rec] = m ? p.J_mir : p.J;
+            r[rec] = m ? p.r_mir : p.r;
+            const std::vector<double>& T = m ? p.T_mu_mir : p.T_mu;
+            for (int k = 0; k < 9 && k < (int)T.size(); ++k) T_mu[rec * 9 + k] = T[k];
+        }
+        area[j] = p.A;
+        for (int k = 0; k < n_cols && k < (int)p.i_vert_d.size(); ++k) i_vert_d[(size_t)j * n_cols + k] = p.i_vert_d[k];
+        i_panel_s[j] = p.i_panel_s.empty() ? -1 : p.i_panel_s[0];
+        has_sources[j] = p.has_sources ? 1 : 0;
+    }
+    void view(ml_panel_soa* out) const {
+        std::memset(out, 0, sizeof *out);
+        out->n_panels = n_panels;
+        out->n_images = n_images;
+        out->n_cols = n_cols;
+        out->in_wake = in_wake;
+        out->centr = centr.data();
+        out->A_g_to_ls = A_g_to_ls.data();
+        out->vertices_ls = vertices_ls.data();
+        out->n_hat_ls = n_hat_ls.data();
+        out->b = b.data();
+        out->sqrt_b = sqrt_b.data();
+        out->J = J.data();
+        out->r = r.data();
+        out->area = area.data();
+        out->vert_g = vert_g.data();
+        out->T_mu = T_mu.data();
+        out->i_vert_d = i_vert_d.data();
+        out->i_panel_s = i_panel_s.data();
+        out->has_sources = has_sources.data();
+        out->image_present = image_present.data();
+    }
+};
+
+}  // namespace
+
+struct mlh_case {
+    Case c;
+    PanelTableStore body, wake;
+    std::vector<double> cp_loc, cp_n_g;
+    std::vector<int> cp_bc, cp_row;
+    bool tables_built = false;
+    Results last;
+    std::vector<double> res_cp, res_v;
+};
+
+static thread_local std::string g_err;
+
+extern "C" const char* mlh_last_error(void) { return g_err.c_str(); }
+
+extern "C" int mlh_case_create(const char* json_text, const char* base_dir, mlh_case** out) {
+    if (!json_text || !out) {
+        g_err = "null argument";
+        return 1;
+    }
+    try {
+        std::unique_ptr<mlh_case> h(new mlh_case());
+        h->c.load(json_text, base_dir ? base_dir : "");
+        h->c.setup();
+        *out = h.release();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+extern "C" void mlh_case_destroy(mlh_case* c) { delete c; }
+
+extern "C" int mlh_case_info(const mlh_case* h, mlh_mesh_info* o) {
+    if (!h || !o) return 1;
+    const Case& c = h->c;
+    o->n_body_panels = c.N_panels;
+    o->n_body_verts = c.N_verts;
+    o->n_wake_panels = c.wake.N_panels;
+    o->n_wake_strips = c.wake.N_strips;
+    o->n_edges = c.N_edges;
+    o->n_cp = c.N_cp;
+    o->n_unknown = c.N_unknown;
+    o->mirrored = c.mirrored;
+    o->asym_flow = c.asym_flow;
+    o->mirror_plane = c.mirror_plane;
+    o->supersonic = c.freestream.supersonic;
+    o->sort_seconds = c.sort_time;
+    return 0;
+}
+
+static void build_tables(mlh_case* h) {
+    Case& c = h->c;
+    h->body.reserve_for(c.N_panels, c.mirrored ? 2 : 1, 3, 0);
+    for (int j = 0; j < c.N_panels; ++j) h->body.put(j, c.panels[j], c.vertices, c.mirrored, c.mirror_plane);
+    // wake: strips flattened in (strip, panel) order, the order of panel_solver.f90:1656-1657
+    int nw = c.wake.N_panels;
+    bool any_mir = false;
+    for (auto& st : c.wake.strips) any_mir = any_mir || st.mirrored;
+    h->wake.reserve_for(nw, any_mir ? 2 : 1, 6, 1);
+    int j = 0;
+    for (auto& st : c.wake.strips)
+        for (auto& p : st.panels) {
+            h->wake.put(j, p, st.vertices, st.mirrored, c.mirror_plane);
+            h->wake.image_present[j] = st.mirrored ? 1 : 0;
+            ++j;
+        }
+    h->cp_loc.assign((size_t)c.N_cp * 3, 0.);
+    h->cp_n_g.assign((size_t)c.N_cp * 3, 0.);
+    h->cp_bc.assign(c.N_cp, 0);
+    h->cp_row.assign(c.N_cp, 0);
+    for (int i = 0; i < c.N_cp; ++i) {
+        for (int k = 0; k < 3; ++k) {
+            h->cp_loc[3 * (size_t)i + k] = c.cp[i].loc[k];
+            h->cp_n_g[3 * (size_t)i + k] = c.cp[i].n_g[k];
+        }
+        h->cp_bc[i] = c.cp[i].bc;
+        h->cp_row[i] = c.solver.use_sort_for_cp ? c.P[i] : i;
+    }
+    h->tables_built = true;
+}
+
+extern "C" int mlh_case_tables(mlh_case* h, ml_flow* flow, ml_panel_soa* body, ml_panel_soa* wake, ml_system_map* map,
+                               mlh_cp_table* cps) {
+    if (!h) return 1;
+    try {
+        if (!h->tables_built) build_tables(h);
+        const Case& c = h->c;
+        if (flow) {
+            const Flow& f = c.freestream;
+            flow->M_inf = f.M_inf;
+            flow->B = f.B;
+            flow->s = f.s;
+            flow->K_inv = f.K_inv;
+            for (int i = 0; i < 3; ++i) flow->c_hat_g[i] = f.c_hat_g[i];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    flow->B_mat_g[3 * i + j] = f.B_mat_g[i][j];
+                    flow->C_mat_g[3 * i + j] = f.C_mat_g[i][j];
+                }
+            flow->supersonic = f.supersonic ? 1 : 0;
+            flow->mirror_plane = c.mirrored ? c.mirror_plane : 0;
+        }
+        if (body) h->body.view(body);
+        if (wake) h->wake.view(wake);
+        if (map) {
+            map->n_cp = c.N_cp;
+            map->n_unknown = c.N_unknown;
+            map->n_verts = c.N_verts;
+            map->n_body_panels = c.N_panels;
+            map->n_sigma = c.N_sigma;
+            map->mirrored = c.mirrored;
+            map->asym_flow = c.asym_flow;
+            map->P = c.P.data();
+            map->sigma_known = c.sigma_known.data();
+            map->i_sigma_in_sys = c.i_sigma_in_sys.data();
+            map->sigma = c.sigma.data();
+        }
+        if (cps) {
+            cps->n_cp = c.N_cp;
+            cps->loc = h->cp_loc.data();
+            cps->bc = h->cp_bc.data();
+            cps->n_g = h->cp_n_g.data();
+            cps->row_perm = h->cp_row.data();
+            cps->BC = c.BC.data();
+        }
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+static int solver_code(const std::string& name) {
+    if (name == "LU") return ML_SOLVER_LU;
+    if (name == "QRUP") return ML_SOLVER_QRUP;
+    if (name == "FQRUP") return ML_SOLVER_FQRUP;
+    if (name == "GMRES") return ML_SOLVER_GMRES;
+    if (name == "RGMRES") return ML_SOLVER_RGMRES;
+    if (name == "PURC") return ML_SOLVER_PURC;
+    if (name == "BSSOR") return ML_SOLVER_BSSOR;
+    if (name == "BJAC") return ML_SOLVER_BJAC;
+    return ML_SOLVER_GMRES;  // invalid name -> GMRES (panel_solver.f90:1969-1973)
+}
+
+extern "C" int mlh_case_solver_settings(const mlh_case* h, mlh_solver_settings* o) {
+    if (!h || !o) return 1;
+    const SolverSettings& s = h->c.solver;
+    std::memset(o, 0, sizeof *o);
+    o->opts.matrix_solver = solver_code(s.matrix_solver);
+    o->opts.preconditioner = (s.preconditioner == "DIAG") ? ML_PREC_DIAG : ML_PREC_NONE;
+    o->opts.tol = s.tol;
+    o->opts.rel = s.rel;
+    o->opts.max_iterations = s.max_iterations;
+    o->opts.restart_iterations = s.restart_iterations;
+    o->opts.block_size = s.block_size;
+    o->opts.iteration_file = nullptr;
+    std::snprintf(o->matrix_solver_name, sizeof o->matrix_solver_name, "%s", s.matrix_solver.c_str());
+    std::snprintf(o->formulation, sizeof o->formulation, "%s", s.formulation.c_str());
+    o->sort_system = s.sort_system;
+    o->write_A_and_b = s.write_A_and_b;
+    return 0;
+}
+
+extern "C" int mlh_case_post(mlh_case* h, const double* x, mlh_results* out) {
+    if (!h || !x || !out) return 1;
+    try {
+        const Case& c = h->c;
+        std::vector<double> xv(x, x + c.N_unknown);
+        h->last = c.post(xv);
+        const Results& R = h->last;
+        const std::vector<double>& rep = c.solver.incompressible_rule ? R.C_p_inc : R.C_p_ise;
+        h->res_cp = rep;
+        h->res_v.assign((size_t)R.N_cells * 3, 0.);
+        for (int i = 0; i < R.N_cells; ++i)
+            for (int k = 0; k < 3; ++k) h->res_v[3 * (size_t)i + k] = R.V_cells[i][k];
+        out->C_p_max = R.C_p_max;
+        out->C_p_min = R.C_p_min;
+        for (int k = 0; k < 3; ++k) {
+            out->C_F[k] = R.C_F[k];
+            out->C_M[k] = R.C_M[k];
+        }
+        out->n_cells = R.N_cells;
+        out->n_mu = (int)R.mu.size();
+        out->mu = R.mu.data();
+        out->C_p = h->res_cp.data();
+        out->V_cells = h->res_v.data();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+static void add_minmax(FILE* f, const char* label, const std::vector<double>& v, bool& first) {
+    if (v.empty()) return;
+    double mx = v[0], mn = v[0];
+    for (double x : v) {
+        if (x > mx) mx = x;
+        if (x < mn) mn = x;
+    }
+    std::fprintf(f, "%s\n        \"%s\": {\n            \"max\": %.16E,\n            \"min\": %.16E\n        }", first ? "" : ",",
+                 label, mx, mn);
+    first = false;
+}
+
+// panel_solver.f90:2618-2746 + main.f90:92-101,140-176
+extern "C" int mlh_case_write_report(mlh_case* h, const char* path, const ml_solve_info* info, int solver_stat,
+                                     double total_runtime) {
+    if (!h || !path) return 1;
+    const Case& c = h->c;
+    const Results& R = h->last;
+    FILE* f = std::fopen(path, "w");
+    if (!f) {
+        g_err = std::string("cannot write ") + path;
+        return 1;
+    }
+    double l_avg = 0.;
+    for (auto& p : c.panels) l_avg = l_avg + std::sqrt(p.A);
+    l_avg = l_avg / c.N_panels;
+    const double PI = 3.14159265358979323846264338327950288419716939937510;
+    std::fprintf(f, "{\n    \"info\": {\n        \"generated_by\": \"machline-b200 (MachLine-compatible report)\"\n    },\n");
+    std::fprintf(f,
+                 "    \"mesh_info\": {\n        \"N_body_panels\": %d,\n        \"N_body_vertices\": %d,\n        "
+                 "\"N_wake_panels\": %d,\n        \"average_characteristic_length\": %.16E,\n        "
+                 "\"max_flow_turning_angle\": %.16E\n    },\n",
+                 c.N_panels, c.N_verts, c.wake.N_panels, l_avg, std::acos(c.C_min_panel_angle) * 180. / PI);
+    std::fprintf(f,
+                 "    \"solver_results\": {\n        \"solver_status_code\": %d,\n        \"system_dimension\": %d,\n        "
+                 "\"timing\": {\n            \"system_sorting\": %.16E,\n            \"preconditioner\": %.16E,\n            "
+                 "\"matrix_solver\": %.16E\n        }",
+                 solver_stat, c.N_unknown, c.sort_time, 0.0, info ? info->solve_ms * 1e-3 : 0.0);
+    if (solver_stat == 0 && info) {
+        if (info->iterations > -1) std::fprintf(f, ",\n        \"iterations\": %d", info->iterations);
+        std::fprintf(f, ",\n        \"residual\": {\n            \"max\": %.16E,\n            \"norm\": %.16E\n        }\n    },\n",
+                     info->res_max, info->res_norm);
+        std::fprintf(f, "    \"pressure_calculations\": {");
+        bool first = true;
+        add_minmax(f, "incompressible_rule", R.C_p_inc, first);
+        add_minmax(f, "isentropic_rule", R.C_p_ise, first);
+        add_minmax(f, "second_order_rule", R.C_p_2nd, first);
+        add_minmax(f, "slender_body_rule", R.C_p_sln, first);
+        add_minmax(f, "linear_rule", R.C_p_lin, first);
+        add_minmax(f, "prandtl_glauert", R.C_p_pg, first);
+        add_minmax(f, "karman_tsien", R.C_p_kt, first);
+        add_minmax(f, "laitone", R.C_p_lai, first);
+        std::fprintf(f, "\n    },\n");
+        std::fprintf(f, "    \"total_forces\": {\n        \"Cx\": %.16E,\n        \"Cy\": %.16E,\n        \"Cz\": %.16E\n    },\n",
+                     R.C_F[0], R.C_F[1], R.C_F[2]);
+        std::fprintf(f, "    \"total_moments\": {\n        \"CMx\": %.16E,\n        \"CMy\": %.16E,\n        \"CMz\": %.16E\n    },\n",
+                     R.C_M[0], R.C_M[1], R.C_M[2]);
+    } else {
+        std::fprintf(f, "\n    },\n");
+    }
+    std::fprintf(f, "    \"total_runtime\": %.16E\n}\n", total_runtime);
+    std::fclose(f);
+    return 0;
+}

@@ -1,0 +1,515 @@
+// Solver-side setup and post-processing on the host: restatement of the non-hot-path halves of
+// src/panel_solver.f90 -- settings (:164-310), Dirichlet init (:313-364, :423-512), control-point
+// boundary conditions (:601-648), system permutation (:778-1030), source strengths and BC vector
+// (:1104-1200), and after the solve: strengths, cell velocities, pressures, forces, moments
+// (:2012-2615) -- plus control-point placement from src/surface_mesh.f90:1473-1892.
+// The two hot paths (DoD + influences -> A; the dense solve) are NOT here: they are behind
+// include/machline_gpu.h.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <numeric>
+#include <stdexcept>
+
+#include "model.hpp"
+
+namespace mlh {
+
+static bool contains(const std::vector<int>& v, int x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+
+// panel_solver.f90:164-310
+static void parse_settings(Case& c) {
+    static const Json empty_obj = [] {
+        Json j;
+        j.type = Json::Object;
+        return j;
+    }();
+    const Json* sj = c.input.find("solver");
+    const Json* pj = c.input.find("post_processing");
+    const Json& s = sj ? *sj : empty_obj;
+    const Json& p = pj ? *pj : empty_obj;
+    SolverSettings& o = c.solver;
+    const Flow& fs = c.freestream;
+    o.formulation = s.get("formulation", "dirichlet-morino");
+    o.matrix_solver = s.get("matrix_solver", "GMRES");
+    o.block_size = s.get("block_size", -1);
+    o.tol = s.get("tolerance", 1.e-12);
+    o.rel = s.get("relaxation", 0.8);
+    o.max_iterations = s.get("max_iterations", 1000);
+    o.restart_iterations = s.get("restart_iterations", 20);
+    o.preconditioner = s.get("preconditioner", "DIAG");
+    o.iteration_file = s.get("iterative_solver_output", "none");
+    o.sort_system = s.get("sort_system", fs.supersonic);
+    if (o.formulation == "neumann-mass-flux" || o.formulation == "neumann-velocity") {
+        o.sort_system = false;
+        o.use_sort_for_cp = false;
+        o.overdetermined_ls = true;
+        o.underdetermined_ls = false;
+    } else if (o.formulation == "neumann-doublet-source-mass-flux-ls") {
+        o.sort_system = false;
+        o.use_sort_for_cp = false;
+        o.underdetermined_ls = true;
+        o.overdetermined_ls = false;
+    } else {
+        o.use_sort_for_cp = true;
+        o.overdetermined_ls = false;
+        o.underdetermined_ls = false;
+    }
+    o.write_A_and_b = s.get("write_A_and_b", false);
+    o.control_point_offset = s.get("control_point_offset", 1.e-7);
+    o.control_point_offset_type = s.get("control_point_offset_type", "direct");
+    if (o.control_point_offset <= 0.) o.control_point_offset = 1.e-7;
+
+    // parse_processing_settings
+    if (fs.M_inf > 0.) {
+        o.isentropic_rule = p.get("pressure_rules.isentropic", true);
+        o.incompressible_rule = p.get("pressure_rules.incompressible", false);
+        if (o.incompressible_rule) {
+            o.incompressible_rule = false;
+            o.isentropic_rule = true;
+        }
+    } else {
+        o.incompressible_rule = p.get("pressure_rules.incompressible", true);
+        o.isentropic_rule = p.get("pressure_rules.isentropic", false);
+        if (o.isentropic_rule) {
+            o.isentropic_rule = false;
+            o.incompressible_rule = true;
+        }
+    }
+    o.second_order_rule = p.get("pressure_rules.second-order", false);
+    o.slender_rule = p.get("pressure_rules.slender-body", false);
+    o.linear_rule = p.get("pressure_rules.linear", false);
+    o.M_inf_corr = p.get("subsonic_pressure_correction.correction_mach_number", 0.0);
+    o.prandtl_glauert = p.get("subsonic_pressure_correction.prandtl-glauert", false);
+    o.karman_tsien = p.get("subsonic_pressure_correction.karman-tsien", false);
+    o.laitone = p.get("subsonic_pressure_correction.laitone", false);
+    if (o.M_inf_corr < 0.0 || o.M_inf_corr >= 1.0)
+        throw std::runtime_error("The pressure correction Mach number must be between zero and one.");
+    bool any_corr = o.prandtl_glauert || o.karman_tsien || o.laitone;
+    if (any_corr && fs.M_inf != 0.0)
+        throw std::runtime_error("Subsonic pressure corrections require freestream_mach_number = 0.");
+    if (any_corr && !o.incompressible_rule) o.incompressible_rule = true;
+    const char* dflt = nullptr;
+    if (o.incompressible_rule) dflt = "incompressible";
+    else if (o.isentropic_rule) dflt = "isentropic";
+    else if (o.second_order_rule) dflt = "second-order";
+    else if (o.linear_rule) dflt = "linear";
+    else if (o.slender_rule) dflt = "slender-body";
+    else if (o.prandtl_glauert) dflt = "prandtl-glauert";
+    else if (o.karman_tsien) dflt = "karman-tsien";
+    else if (o.laitone) dflt = "laitone";
+    if (dflt) o.pressure_for_forces = p.get("pressure_for_forces", dflt);
+}
+
+// surface_mesh.f90:1473-1680
+V3 Case::get_clone_control_point_dir(int i_vert) const {
+    const Vertex& v = vertices[i_vert];
+    bool found_first = false;
+    int i_edge_1 = -1, i_edge_2 = -1;
+    for (int i_edge : v.adjacent_edges) {
+        const Edge& e = edges[i_edge];
+        if (e.sheds_wake) {
+            int panel1 = e.panels[0], panel2 = e.panels[1];
+            bool in1 = contains(v.panels_not_across_wake_edge, panel1);
+            bool in2 = contains(v.panels_not_across_wake_edge, panel2);
+            if ((in1 && !in2) || (in2 && !in1)) {
+                if (found_first) i_edge_2 = i_edge;
+                else {
+                    i_edge_1 = i_edge;
+                    found_first = true;
+                }
+            }
+        }
+    }
+    auto opposite_endpoint = [&](const Edge& e) {  // base_geom.f90:481-498
+        if (dist(v.loc, vertices[e.top_verts[0]].loc) < 1.e-12) return e.top_verts[1];
+        return e.top_verts[0];
+    };
+    V3 t_avg;
+    if (i_edge_2 != -1) {
+        V3 t1 = v.loc - vertices[opposite_endpoint(edges[i_edge_1])].loc;
+        t1 = t1 / norm2(t1);
+        V3 t2 = vertices[opposite_endpoint(edges[i_edge_2])].loc - v.loc;
+        t2 = t2 / norm2(t2);
+        t_avg = t1 + t2;
+        t_avg = t_avg / norm2(t_avg);
+    } else {
+        t_avg = {0., 0., 0.};
+        t_avg[mirror_plane - 1] = 1.;
+    }
+    bool tp_found = false;
+    V3 tp{0., 0., 0.};
+    for (int i_panel : v.panels_not_across_wake_edge) {
+        const Panel& p = panels[i_panel];
+        double l_to_cent = norm2(p.centr - v.loc);
+        tp = cross(t_avg, p.n_g);
+        tp = tp / norm2(tp);
+        if (panel_projection_inside(p, vertices, (0.01 * l_to_cent) * tp + v.loc, false, 0)) {
+            tp_found = true;
+            break;
+        } else if (panel_projection_inside(p, vertices, (-0.01 * l_to_cent) * tp + v.loc, false, 0)) {
+            tp_found = true;
+            tp = -tp;
+            break;
+        }
+    }
+    if (!tp_found) throw std::runtime_error("Failed to find t_p for placing a cloned control point.");
+    tp = tp / norm2(tp);
+    double C_min = 1.;
+    for (size_t j = 0; j < v.panels.size(); ++j) {
+        int panel1 = v.panels[j];
+        for (size_t k = j + 1; k < v.panels.size(); ++k) {
+            double x = inner(panels[panel1].n_g, panels[v.panels[k]].n_g);
+            C_min = std::min(C_min, x);
+        }
+        if (mirrored && v.on_mirror_plane) {
+            double x = -panels[panel1].n_g[mirror_plane - 1];
+            C_min = std::min(C_min, x);
+        }
+    }
+    V3 n_avg{0., 0., 0.};
+    for (int i_panel : v.panels_not_across_wake_edge) {
+        quad w[3];
+        panel_weighted_normal_at_corner(panels[i_panel], vertices, v.loc, w);
+        for (int k = 0; k < 3; ++k) n_avg[k] = (double)((quad)n_avg[k] + w[k]);
+    }
+    n_avg = n_avg / norm2(n_avg);
+    double offset_ratio = 0.5 * std::sqrt(0.5 * (1. + C_min));
+    V3 dir = tp - offset_ratio * n_avg;
+    if (v.on_mirror_plane) dir[mirror_plane - 1] = 0.;
+    dir = dir / norm2(dir);
+    return dir;
+}
+
+// surface_mesh.f90:1796-1841
+bool Case::control_point_outside_mesh(const V3& cp_loc, int i_vert) const {
+    const Vertex& v = vertices[i_vert];
+    const Panel& p0 = panels[v.panels[0]];
+    V3 start = std::sqrt(p0.A) * p0.n_g + p0.centr;
+    V3 dir = cp_loc - start;
+    int N_crosses = 0;
+    for (int i_panel : v.panels) {
+        double s_star = 0.;
+        if (panel_line_passes_through(panels[i_panel], vertices, start, dir, false, 0, s_star))
+            if (s_star <= 1. && s_star >= 0.) ++N_crosses;
+        if (v.on_mirror_plane) {
+            if (panel_line_passes_through(panels[i_panel], vertices, start, dir, true, mirror_plane, s_star))
+                if (s_star <= 1. && s_star >= 0.) ++N_crosses;
+        }
+    }
+    return N_crosses % 2 == 0;
+}
+
+// surface_mesh.f90:1683-1769, 1844-1892
+void Case::place_internal_vertex_control_points(double offset, const std::string& offset_type) {
+    N_cp = asym_flow ? N_verts * 2 : N_verts;
+    cp.assign(N_cp, ControlPoint());
+    for (int i = 0; i < N_verts; ++i) {
+        const Vertex& v = vertices[i];
+        V3 dir = v.clone ? get_clone_control_point_dir(i) : -v.n_g;
+        double this_offset = (offset_type == "local") ? offset * v.l_avg : offset;
+        V3 loc = v.loc + this_offset * dir;
+        while (control_point_outside_mesh(loc, i)) {
+            V3 n_avg{0., 0., 0.};
+            for (int i_panel : v.panels) {
+                if (panel_point_above(panels[i_panel], loc, false)) {
+                    quad w[3];
+                    panel_weighted_normal_at_corner(panels[i_panel], vertices, v.loc, w);
+                    for (int k = 0; k < 3; ++k) n_avg[k] = (double)((quad)n_avg[k] + w[k]);
+                }
+            }
+            if (v.on_mirror_plane) n_avg[mirror_plane - 1] = 0.;
+            if (norm2(n_avg) < 1.e-16) break;
+            n_avg = n_avg / norm2(n_avg);
+            V3 disp = loc - v.loc;
+            V3 new_dir = disp - (1.1 * n_avg) * inner(disp, n_avg);
+            new_dir = new_dir / norm2(new_dir);
+            loc = v.loc + this_offset * new_dir;
+        }
+        cp[i].loc = loc;
+        cp[i].cp_type = 1;
+        cp[i].tied_to_type = TT_VERTEX;
+        cp[i].tied_to_index = i;
+        cp[i].is_mirror = false;
+    }
+    if (asym_flow) {
+        for (int i = 0; i < N_cp / 2; ++i) {
+            ControlPoint& m = cp[i + N_cp / 2];
+            m.loc = mirror_across_plane(cp[i].loc, mirror_plane);
+            m.cp_type = cp[i].cp_type;
+            m.tied_to_type = cp[i].tied_to_type;
+            m.tied_to_index = cp[i].tied_to_index;
+            m.is_mirror = true;
+        }
+    }
+}
+
+// panel_solver.f90:778-1030
+void Case::set_permutation() {
+    auto t0 = std::chrono::steady_clock::now();
+    if (solver.sort_system) {
+        std::vector<double> x(N_unknown);
+        for (int i = 0; i < N_cp; ++i) {
+            V3 loc;
+            if (cp[i].is_mirror) {
+                if (cp[i].tied_to_type == 1) loc = mirror_across_plane(vertices[cp[i].tied_to_index].loc, mirror_plane);
+                else loc = panels[cp[i].tied_to_index].centr_mir;
+            } else {
+                if (cp[i].tied_to_type == 1) loc = vertices[cp[i].tied_to_index].loc;
+                else loc = panels[cp[i].tied_to_index].centr;
+            }
+            x[i] = -inner(freestream.c_hat_g, loc);
+        }
+        // insertion_arg_sort (sort.f90:359-388) is a stable ascending sort
+        std::vector<int> P_inv_1(N_unknown);
+        std::iota(P_inv_1.begin(), P_inv_1.end(), 0);
+        std::stable_sort(P_inv_1.begin(), P_inv_1.end(), [&](int a, int b) { return x[a] < x[b]; });
+
+        const double huge = std::numeric_limits<double>::max();
+        for (int i = 0; i < (int)P_inv_1.size(); ++i) {
+            int i_cp = P_inv_1[i];
+            const ControlPoint& q = cp[i_cp];
+            const bool mir = q.is_mirror;
+            auto key = [&](const V3& l) {
+                return -inner(freestream.c_hat_g, mir ? mirror_across_plane(l, mirror_plane) : l);
+            };
+            if (q.tied_to_type == 1) {
+                int i_vert = q.tied_to_index;
+                x[i] = huge;
+                for (int i_neighbor : vertices[i_vert].adjacent_vertices) x[i] = std::min(x[i], key(vertices[i_neighbor].loc));
+                // (higher-order abutting-panel extension, panel_solver.f90:859-894/931-966, applies to
+                //  order-2 panels only)
+            } else {
+                int i_panel = q.tied_to_index;
+                x[i] = huge;
+                for (int j = 0; j < 3; ++j) x[i] = std::min(x[i], key(vertices[panels[i_panel].iv[j]].loc));
+            }
+        }
+        std::vector<int> P_inv_2(N_unknown);
+        std::iota(P_inv_2.begin(), P_inv_2.end(), 0);
+        std::stable_sort(P_inv_2.begin(), P_inv_2.end(), [&](int a, int b) { return x[a] < x[b]; });
+        P.assign(N_cp, -1);
+        for (int i = 0; i < N_cp; ++i) P[P_inv_1[P_inv_2[i]]] = i;
+    } else {
+        P.assign(N_unknown, -1);
+        for (int i = 0; i < N_verts; ++i) P[i] = vertex_ordering[i];
+        int source_start = N_verts;
+        if (asym_flow) {
+            for (int i = 0; i < N_verts; ++i) P[N_verts + i] = vertex_ordering[i] + N_verts;
+            source_start = 2 * N_verts;
+        }
+        for (int i = 0; i < N_s_unknown; ++i) P[source_start + i] = source_start + i;
+    }
+    sort_time = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// panel_solver.f90:115-161 without calc_domains_of_dependence (fused into the GPU assembly)
+void Case::init_solver() {
+    parse_settings(*this);
+    const std::string& f = solver.formulation;
+    if (f == "dirichlet-morino" || f == "dirichlet-source-free") {
+        solver.dirichlet = true;
+    } else if (f == "neumann-mass-flux" || f == "neumann-velocity" || f == "neumann-doublet-source-mass-flux-ls" ||
+               f == "neumann-mass-flux-inner-flow" || f == "neumann-doublet-only-mass-flux") {
+        throw std::runtime_error("Neumann formulations are outside the round-1 hot-path scope (SURVEY 8f rank 3)");
+    } else {
+        throw std::runtime_error("'" + f + "' is not a valid formulation.");
+    }
+    // init_dirichlet, panel_solver.f90:313-364
+    place_internal_vertex_control_points(solver.control_point_offset, solver.control_point_offset_type);
+    // set_panel_sources :423-444
+    for (auto& p : panels) p.has_sources = (f == "dirichlet-morino") ? true : (p.r < 0);
+    // determine_dirichlet_unknowns :447-512
+    N_sigma = asym_flow ? N_panels * 2 : N_panels;
+    N_d_unknown = asym_flow ? N_verts * 2 : N_verts;
+    sigma_known.assign(N_sigma, 1);
+    N_s_unknown = N_supinc;
+    i_sigma_in_sys.assign(N_sigma, -1);
+    i_sys_sigma_in_body.assign(N_s_unknown, -1);
+    int j = N_d_unknown;
+    for (int i = 0; i < N_panels; ++i) {
+        if (panels[i].r < 0) {
+            i_sigma_in_sys[i] = j;
+            i_sys_sigma_in_body[j - N_d_unknown] = i;
+            sigma_known[i] = 0;
+            ++j;
+        }
+    }
+    if (asym_flow) {
+        for (int i = 0; i < N_panels; ++i) {
+            if (panels[i].r_mir < 0) {
+                i_sigma_in_sys[i + N_panels] = j;
+                i_sys_sigma_in_body[j - N_d_unknown] = i + N_panels;
+                sigma_known[i + N_panels] = 0;
+                ++j;
+            }
+        }
+    }
+    N_unknown = N_d_unknown + N_s_unknown;
+    if (N_unknown != N_cp)
+        throw std::runtime_error("The number of unknowns is not the same as the number of control points.");
+    inner_flow = freestream.c_hat_g;
+    if (f == "dirichlet-source-free") inner_flow = inner_flow - matvec(freestream.B_mat_g_inv, freestream.c_hat_g);
+
+    // init_control_point_boundary_conditions :601-648
+    for (int i = 0; i < N_cp; ++i) {
+        if (cp[i].bc == BC_STRENGTH_MATCHING) continue;
+        if (cp[i].is_mirror && cp[i].tied_to_type == TT_VERTEX) {
+            if (!vertices[cp[i].tied_to_index].mirrored_is_unique) {
+                cp[i].bc = BC_STRENGTH_MATCHING;
+                continue;
+            }
+        }
+        cp[i].bc = (f == "dirichlet-morino") ? BC_ZERO_POTENTIAL : BC_SF_POTENTIAL;
+    }
+    set_permutation();
+}
+
+// calc_source_strengths (panel_solver.f90:1162-1200) + assemble_BC_vector (:1104-1159)
+void Case::pre_solve() {
+    sigma.assign(N_sigma, 0.);
+    if (solver.formulation == "dirichlet-morino") {
+        for (int i = 0; i < N_panels; ++i) {
+            if (sigma_known[i]) sigma[i] = -inner(panels[i].n_g, freestream.c_hat_g);
+            if (asym_flow && sigma_known[i + N_panels]) sigma[i + N_panels] = -inner(panels[i].n_g_mir, freestream.c_hat_g);
+        }
+    }
+    BC.assign(N_cp, 0.);
+    V3 x = matvec(freestream.B_mat_g_inv, freestream.c_hat_g);
+    for (int i = 0; i < N_cp; ++i) {
+        int ind = solver.use_sort_for_cp ? P[i] : i;
+        switch (cp[i].bc) {
+            case BC_SF_POTENTIAL: BC[ind] = -inner(x, cp[i].loc); break;
+            case BC_ZERO_NORMAL_MF: BC[ind] = -inner(cp[i].n_g, freestream.c_hat_g); break;
+            case BC_MF_INNER_FLOW: BC[ind] = -inner(x, cp[i].loc); break;
+            case BC_ZERO_NORMAL_VEL: BC[ind] = -inner(freestream.c_hat_g, cp[i].n_g); break;
+            default: BC[ind] = 0.;
+        }
+    }
+}
+
+// panel.f90:3351-3512 (lower-order): velocity jump across a panel at its centroid
+V3 panel_get_velocity_jump(const Panel& p, const Case& c, const std::vector<double>& mu, const std::vector<double>& sigma,
+                           bool mirrored) {
+    // get_doublet_strengths, panel.f90:3351-3412 (body panels)
+    double mu_verts[3];
+    for (int i = 0; i < 3; ++i) {
+        int iv = p.i_vert_d[i];
+        int idx;
+        if (c.asym_flow) {
+            if (mirrored) idx = (iv >= c.N_verts) ? iv - c.N_verts : iv + c.N_verts;
+            else idx = iv;
+        } else {
+            idx = (iv >= c.N_verts) ? iv - c.N_verts : iv;
+        }
+        mu_verts[i] = mu[idx];
+    }
+    const std::vector<double>& T = mirrored ? p.T_mu_mir : p.T_mu;
+    double mu_params[3];
+    for (int i = 0; i < 3; ++i) mu_params[i] = T[3 * i + 0] * mu_verts[0] + T[3 * i + 1] * mu_verts[1] + T[3 * i + 2] * mu_verts[2];
+    V3 dv{mu_params[1], mu_params[2], 0.};
+    const M33& A = mirrored ? p.A_g_to_ls_mir : p.A_g_to_ls;
+    dv = matvec(transpose(A), dv);
+    if (p.has_sources) {
+        V3 s_dir = mirrored ? p.n_g_mir / inner(p.nu_g_mir, p.n_g_mir) : p.n_g / inner(p.nu_g, p.n_g);
+        // get_source_strengths, panel.f90:3268-3313
+        int ip = p.i_panel_s[0];
+        int idx;
+        if (c.asym_flow) {
+            if (mirrored) idx = (ip >= c.N_panels) ? ip - c.N_panels : ip + c.N_panels;
+            else idx = ip;
+        } else {
+            idx = (ip >= c.N_panels) ? ip - c.N_panels : ip;
+        }
+        double s = sigma[idx];
+        dv = dv + s * s_dir;
+    }
+    return dv;
+}
+
+// panel_solver.f90:2012-2615 (lower-order path)
+Results Case::post(const std::vector<double>& x) const {
+    Results R;
+    R.mu.assign(asym_flow ? N_verts * 2 : N_verts, 0.);
+    for (int i = 0; i < N_d_unknown; ++i) R.mu[i] = x[P[i]];
+    R.sigma = sigma;
+    for (int i = 0; i < N_s_unknown; ++i) R.sigma[i_sys_sigma_in_body[i]] = x[P[N_d_unknown + i]];
+
+    const Flow& fs = freestream;
+    R.N_cells = asym_flow ? 2 * N_panels : N_panels;
+    R.V_cells.assign(R.N_cells, V3{});
+    R.V_cells_inner.assign(R.N_cells, V3{});
+    for (int i = 0; i < N_panels; ++i) {  // calc_cell_velocities :2030-2095
+        R.V_cells_inner[i] = inner_flow * fs.U;
+        V3 dv = panel_get_velocity_jump(panels[i], *this, R.mu, R.sigma, false);
+        R.V_cells[i] = fs.U * ((R.V_cells_inner[i] / fs.U) + dv);
+        if (asym_flow) {
+            R.V_cells_inner[i + N_panels] = inner_flow * fs.U;
+            V3 dvm = panel_get_velocity_jump(panels[i], *this, R.mu, R.sigma, true);
+            R.V_cells[i + N_panels] = fs.U * ((R.V_cells_inner[i + N_panels] / fs.U) + dvm);
+        }
+    }
+    // calc_pressures :2218-2321; the lower-order average pressure is the rule applied to the
+    // centroid velocity (panel.f90:3638-3649), i.e. to V_cells.
+    auto fill = [&](std::vector<double>& dst, const char* rule) {
+        dst.assign(R.N_cells, 0.);
+        for (int i = 0; i < R.N_cells; ++i) dst[i] = fs.get_C_P(R.V_cells[i], rule, solver.M_inf_corr);
+    };
+    if (solver.incompressible_rule) fill(R.C_p_inc, "incompressible");
+    if (solver.isentropic_rule) fill(R.C_p_ise, "isentropic");
+    if (solver.second_order_rule) fill(R.C_p_2nd, "second-order");
+    if (solver.slender_rule) fill(R.C_p_sln, "slender-body");
+    if (solver.linear_rule) fill(R.C_p_lin, "linear");
+    if (solver.prandtl_glauert) fill(R.C_p_pg, "prandtl-glauert");
+    if (solver.karman_tsien) fill(R.C_p_kt, "karman-tsien");
+    if (solver.laitone) fill(R.C_p_lai, "laitone");
+
+    // calc_forces :2440-2528
+    const std::vector<double>* pr = nullptr;
+    const std::string& pf = solver.pressure_for_forces;
+    if (pf == "incompressible") pr = &R.C_p_inc;
+    else if (pf == "isentropic") pr = &R.C_p_ise;
+    else if (pf == "second-order") pr = &R.C_p_2nd;
+    else if (pf == "slender-body") pr = &R.C_p_sln;
+    else if (pf == "linear") pr = &R.C_p_lin;
+    else if (pf == "prandtl-glauert") pr = &R.C_p_pg;
+    else if (pf == "karman-tsien") pr = &R.C_p_kt;
+    else if (pf == "laitone") pr = &R.C_p_lai;
+    if (!pr || pr->empty()) throw std::runtime_error(pf + " pressure for forces is not available.");
+    R.dC_f.assign(R.N_cells, V3{});
+    for (int i = 0; i < N_panels; ++i) {
+        R.dC_f[i] = (-(*pr)[i] * panels[i].A) * panels[i].n_g;
+        if (asym_flow) R.dC_f[i + N_panels] = (-(*pr)[i + N_panels] * panels[i].A) * panels[i].n_g_mir;
+    }
+    V3 sum{0., 0., 0.};
+    for (int i = 0; i < R.N_cells; ++i) sum = sum + R.dC_f[i];
+    R.C_F = sum / S_ref;
+    if (mirrored && !asym_flow) {
+        R.C_F = 2. * R.C_F;
+        R.C_F[mirror_plane - 1] = 0.;
+    }
+    // calc_moments :2551-2615 (order 1: no pressure-variation term)
+    V3 msum{0., 0., 0.};
+    std::vector<V3> dC_m(R.N_cells, V3{});
+    for (int i = 0; i < N_panels; ++i) {
+        dC_m[i] = cross(panels[i].centr - CG, R.dC_f[i]);
+        if (asym_flow) dC_m[i + N_panels] = cross(panels[i].centr_mir - CG, R.dC_f[i]);  // sic (:2583)
+    }
+    for (int i = 0; i < R.N_cells; ++i) msum = msum + dC_m[i];
+    R.C_M = msum / l_ref;
+    if (mirrored && !asym_flow) {
+        for (int i = 0; i < 3; ++i) {
+            if (i == mirror_plane - 1) R.C_M[i] = 2. * R.C_M[i];
+            else R.C_M[i] = 0.;
+        }
+    }
+    // what test/test_machline.py:62-66 reads: incompressible rule if present, else isentropic
+    const std::vector<double>& rep = solver.incompressible_rule ? R.C_p_inc : R.C_p_ise;
+    if (!rep.empty()) {
+        R.C_p_max = *std::max_element(rep.begin(), rep.end());
+        R.C_p_min = *std::min_element(rep.begin(), rep.end());
+    }
+    return R;
+}
+
+}  // namespace mlh

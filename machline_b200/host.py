@@ -1,0 +1,155 @@
+"""Host-side case setup (mesh, wake, control points, panel tables, post-processing).
+
+Thin ctypes wrapper over libmachline_host.so (csrc/host/), which restates what MachLine's
+``main`` does around the two hot paths (src/main.f90:102-160).  No influence or solver code lives
+here; the tables produced are the arguments of the GPU library's ``ml_set_*`` calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from dataclasses import dataclass
+from pathlib import Path
+
+import numpy as np
+
+from . import _abi, build
+
+
+class MachLineError(RuntimeError):
+    """Raised where the reference prints '!!! ...' and stops."""
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = build.HOST_LIB
+        if not path.exists():
+            build.build_host()
+        L = C.CDLL(str(path))
+        L.mlh_last_error.restype = C.c_char_p
+        L.mlh_case_create.argtypes = [C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+        L.mlh_case_destroy.argtypes = [C.c_void_p]
+        L.mlh_case_info.argtypes = [C.c_void_p, C.POINTER(_abi.MlhMeshInfo)]
+        L.mlh_case_tables.argtypes = [C.c_void_p, C.POINTER(_abi.MlFlow), C.POINTER(_abi.MlPanelSoa),
+                                      C.POINTER(_abi.MlPanelSoa), C.POINTER(_abi.MlSystemMap),
+                                      C.POINTER(_abi.MlhCpTable)]
+        L.mlh_case_solver_settings.argtypes = [C.c_void_p, C.POINTER(_abi.MlhSolverSettings)]
+        L.mlh_case_post.argtypes = [C.c_void_p, _abi.c_double_p, C.POINTER(_abi.MlhResults)]
+        L.mlh_case_write_report.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_abi.MlSolveInfo), C.c_int,
+                                            C.c_double]
+        _lib = L
+    return _lib
+
+
+@dataclass
+class Results:
+    C_p_max: float
+    C_p_min: float
+    C_F: np.ndarray
+    C_M: np.ndarray
+    mu: np.ndarray
+    C_p: np.ndarray
+    V_cells: np.ndarray
+
+
+class Case:
+    """One MachLine input (dict / JSON text / path) after mesh + flow + solver initialisation."""
+
+    def __init__(self, inp, base_dir: str | os.PathLike | None = None):
+        if isinstance(inp, (str, os.PathLike)) and os.path.exists(str(inp)):
+            text = Path(inp).read_text()
+            if base_dir is None:
+                base_dir = "."
+        elif isinstance(inp, dict):
+            text = json.dumps(inp)
+        else:
+            text = str(inp)
+        self.input = json.loads(text)
+        self._h = C.c_void_p()
+        rc = lib().mlh_case_create(text.encode(), str(base_dir or "").encode(), C.byref(self._h))
+        if rc != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+        self.flow = _abi.MlFlow()
+        self.body = _abi.MlPanelSoa()
+        self.wake = _abi.MlPanelSoa()
+        self.map = _abi.MlSystemMap()
+        self.cps = _abi.MlhCpTable()
+        rc = lib().mlh_case_tables(self._h, C.byref(self.flow), C.byref(self.body), C.byref(self.wake),
+                                   C.byref(self.map), C.byref(self.cps))
+        if rc != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+        self.info = _abi.MlhMeshInfo()
+        lib().mlh_case_info(self._h, C.byref(self.info))
+        self.settings = _abi.MlhSolverSettings()
+        lib().mlh_case_solver_settings(self._h, C.byref(self.settings))
+
+    # -- convenience views (numpy, no copies) ---------------------------------------------------
+    @property
+    def n_cp(self) -> int:
+        return self.map.n_cp
+
+    @property
+    def n_unknown(self) -> int:
+        return self.map.n_unknown
+
+    @property
+    def BC(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self.cps.BC, shape=(self.n_cp,))
+
+    @property
+    def cp_loc(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self.cps.loc, shape=(self.n_cp, 3))
+
+    @property
+    def P(self) -> np.ndarray:
+        return np.ctypeslib.as_array(self.map.P, shape=(self.n_unknown,))
+
+    @property
+    def n_pairs(self) -> int:
+        """Pair count of SURVEY 8(d): N_cp x (body records + evaluated wake records)."""
+        nb = self.body.n_panels * self.body.n_images
+        nw = self.wake.n_panels
+        if self.wake.n_panels and self.wake.n_images == 2:
+            pres = np.ctypeslib.as_array(self.wake.image_present, shape=(self.wake.n_panels,))
+            nw += int(pres.sum())
+        return self.n_cp * (nb + nw)
+
+    def solver_opts(self) -> _abi.MlSolverOpts:
+        o = _abi.MlSolverOpts()
+        C.memmove(C.byref(o), C.byref(self.settings.opts), C.sizeof(o))
+        return o
+
+    def post(self, x: np.ndarray) -> Results:
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        assert x.shape == (self.n_unknown,)
+        r = _abi.MlhResults()
+        rc = lib().mlh_case_post(self._h, x.ctypes.data_as(_abi.c_double_p), C.byref(r))
+        if rc != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+        return Results(
+            C_p_max=r.C_p_max, C_p_min=r.C_p_min, C_F=np.array(r.C_F[:]), C_M=np.array(r.C_M[:]),
+            mu=np.ctypeslib.as_array(r.mu, shape=(r.n_mu,)).copy(),
+            C_p=np.ctypeslib.as_array(r.C_p, shape=(r.n_cells,)).copy(),
+            V_cells=np.ctypeslib.as_array(r.V_cells, shape=(r.n_cells, 3)).copy())
+
+    def write_report(self, path, info: _abi.MlSolveInfo, solver_stat: int = 0, runtime: float = 0.0):
+        Path(path).parent.mkdir(parents=True, exist_ok=True)
+        rc = lib().mlh_case_write_report(self._h, str(path).encode(), C.byref(info), solver_stat, runtime)
+        if rc != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+
+    def close(self):
+        if self._h:
+            lib().mlh_case_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,48 @@
+/* ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle_aic.cpp header).  C ABI of the CPU restatement. */
+#ifndef MACHLINE_ORACLE_H
+#define MACHLINE_ORACLE_H
+#include "../include/machline_gpu.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct orc_pair_out {
+    int in_dod;
+    int edges_in_dod[3];
+    double F111[3];
+    double hH113, H111, H213, H123, h;
+    double phi_s;      /* source influence (S space, S_dim = 1)      */
+    double phi_d[3];   /* doublet influences (M space, M_dim = 3)    */
+} orc_pair_out;
+
+void orc_pair_influence(const ml_flow *fs, const ml_panel_soa *t, int j, int img, const double *P, orc_pair_out *out);
+
+int orc_assemble(const ml_flow *fs, const ml_panel_soa *body, const ml_panel_soa *wake, const ml_system_map *map,
+                 int n_cp, const double *cp_loc, const int *cp_bc, const int *row_perm, int row0, int nrows,
+                 double *A_colmajor, int ld, double *I_known, int n_threads);
+
+/* common/linalg.f90 solvers on a host system; A is column-major N x N and is overwritten the way
+   the reference overwrites A_p.  Returns ml_status. */
+int orc_lu_solve(int N, double *A, const double *b, double *x);
+int orc_gmres(int N, const double *A, const double *b, double tol, int max_iter, int *total_iter, double *x,
+              double *err_history /* NULL or [max_iter] */);
+int orc_restarted_gmres(int N, const double *A, const double *b, double tol, int max_iter, int restart_iter,
+                        int *total_iter, double *x);
+int orc_block_jacobi(int N, double *A, const double *b, int block_size, double tol, double rel, int max_iter,
+                     int *total_iter, double *x);
+int orc_block_ssor(int N, double *A, const double *b, int block_size, double tol, double rel, int max_iter,
+                   int *total_iter, double *x);
+int orc_qr_givens_up(int N, double *A, double *b, double *x);
+int orc_qr_fast_givens_up(int N, double *A, double *b, double *x);
+int orc_purcell(int N, const double *A, const double *b, double *x);
+int orc_lower_bandwidth(int N, const double *A);
+
+/* panel_solver.f90:1802-2027: b = BC - I_known, preconditioner, dispatch, residual.  A (n x n,
+   column-major) is not modified. */
+int orc_solve_system(int N, const double *A, const double *I_known, const double *BC, const ml_solver_opts *opts,
+                     double *x, ml_solve_info *info);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

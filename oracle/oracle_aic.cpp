@@ -1,0 +1,443 @@
+// ORACLE -- TEST INFRASTRUCTURE ONLY.  Never linked, imported or executed by the product path
+// (machline_b200/, include/): only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs may use it, and only as the checker.
+//
+// CPU restatement of MachLine's AIC assembly for lower-order (linear doublet / constant source)
+// Dirichlet formulations, following the reference statement by statement:
+//   flow_point_in_dod                         src/flow.f90:282-310
+//   panel_check_dod                           src/panel.f90:1732-1901
+//   panel_calc_basic_geom                     src/panel.f90:1904-1938
+//   panel_calc_subsonic_geom                  src/panel.f90:1941-1997
+//   panel_calc_supersonic_subinc_geom         src/panel.f90:2000-2091
+//   panel_calc_basic_F_integrals_subsonic     src/panel.f90:2232-2283
+//   panel_calc_basic_F_integrals_supersonic_subinc  src/panel.f90:2286-2407
+//   panel_calc_hH113_subsonic                 src/panel.f90:2472-2509
+//   panel_calc_hH113_supersonic_subinc        src/panel.f90:2512-2573   (binary128 F1,F2,b)
+//   panel_calc_remaining_integrals            src/panel.f90:2631-2683   (order 1 part)
+//   panel_assemble_phi_s_S_space / phi_d_M_space   src/panel.f90:2815-2914
+//   panel_calc_potential_influences           src/panel.f90:2917-2971
+//   panel_solver_update_system_row            src/panel_solver.f90:1203-1287
+//   panel_solver_calc_body_influences         src/panel_solver.f90:1290-1501 (Dirichlet + strength matching)
+//   panel_solver_calc_wake_influences         src/panel_solver.f90:1504-1706 (Dirichlet)
+// Compiled with -O2 -ffp-contract=off (gfortran -O2 on x86-64 does not contract), real(16) ->
+// __float128.  Superinclined panels are rejected by the reference at init (panel.f90:439-443), so
+// the *_supinc branches are not restated.
+//
+// Parity pinning: through the golden tuples of test/test_machline.py (tests/test_golden_cpu.py) and
+// through known-answer integrals generated from dev/unit_tests/panel.py (tests/golden/).
+#include <cmath>
+#include <cstring>
+#include <vector>
+#include <quadmath.h>
+#include <omp.h>
+
+#include "../include/machline_gpu.h"
+#include "oracle.h"
+
+namespace {
+
+typedef __float128 quad;
+const double pi = 3.14159265358979323846264338327950288419716939937510;
+
+inline double inner3(const double* a, const double* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+inline void cross3(const double* a, const double* b, double* c) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }
+
+struct Rec {  // one panel image
+    const double *centr, *A, *vls, *nh, *b, *sb, *vg, *T;
+    double J;
+    int r;
+};
+inline Rec get_rec(const ml_panel_soa* t, int j, int img) {
+    size_t rec = (size_t)j + (size_t)img * t->n_panels;
+    Rec R;
+    R.centr = t->centr + 3 * rec;
+    R.A = t->A_g_to_ls + 9 * rec;
+    R.vls = t->vertices_ls + 6 * rec;
+    R.nh = t->n_hat_ls + 6 * rec;
+    R.b = t->b + 3 * rec;
+    R.sb = t->sqrt_b + 3 * rec;
+    R.vg = t->vert_g + 9 * rec;
+    R.T = t->T_mu + 9 * rec;
+    R.J = t->J[rec];
+    R.r = t->r[rec];
+    return R;
+}
+
+// flow.f90:282-310
+inline bool point_in_dod(const ml_flow* fs, const double* Q, const double* P) {
+    double d[3] = {P[0] - Q[0], P[1] - Q[1], P[2] - Q[2]};
+    if (inner3(d, fs->c_hat_g) >= 0.) {
+        double Cd[3];
+        for (int i = 0; i < 3; ++i) Cd[i] = fs->C_mat_g[3 * i] * d[0] + fs->C_mat_g[3 * i + 1] * d[1] + fs->C_mat_g[3 * i + 2] * d[2];
+        if (inner3(d, Cd) >= 0.) return true;
+    }
+    return false;
+}
+
+struct Dod {
+    bool in_dod = true;
+    bool e[3] = {true, true, true};
+};
+
+// panel.f90:1732-1901
+Dod check_dod(const Rec& p, const double* P, const ml_flow* fs) {
+    Dod dod;
+    if (!fs->supersonic) return dod;
+    bool vin[3];
+    for (int i = 0; i < 3; ++i) vin[i] = point_in_dod(fs, p.vg + 3 * i, P);
+    if (vin[0] && vin[1] && vin[2]) return dod;
+    double dfv[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 3; ++k) dfv[i][k] = P[k] - p.vg[3 * i + k];
+    bool downstream = false;
+    for (int i = 0; i < 3; ++i) {
+        double x = inner3(dfv[i], fs->c_hat_g);
+        downstream = x > 0. || downstream;
+    }
+    if (downstream) {
+        for (int i = 0; i < 3; ++i) {
+            int i_next = (i + 1) % 3;
+            if (vin[i] || vin[i_next]) {
+                dod.e[i] = true;
+            } else if (p.b[i] <= 0.) {
+                dod.e[i] = false;
+            } else {
+                const double* Q_end = p.vg + 3 * i_next;
+                double d[3] = {Q_end[0] - p.vg[3 * i], Q_end[1] - p.vg[3 * i + 1], Q_end[2] - p.vg[3 * i + 2]};
+                double a[3], b[3], nd[3] = {-dfv[i_next][0], -dfv[i_next][1], -dfv[i_next][2]};
+                cross3(fs->c_hat_g, d, a);
+                cross3(fs->c_hat_g, nd, b);
+                double s_star = inner3(a, b) / std::fabs(inner3(a, a));
+                double R_star[3] = {Q_end[0] - s_star * d[0], Q_end[1] - s_star * d[1], Q_end[2] - s_star * d[2]};
+                if (s_star > 0. && s_star < 1.) dod.e[i] = point_in_dod(fs, R_star, P);
+                else dod.e[i] = false;
+            }
+        }
+        if (vin[0] || vin[1] || vin[2] || dod.e[0] || dod.e[1] || dod.e[2]) dod.in_dod = true;
+        else dod.in_dod = false;  // (superinclined fallback, panel.f90:1859-1877, is dead: r > 0)
+    } else {
+        dod.e[0] = dod.e[1] = dod.e[2] = false;
+        dod.in_dod = false;
+    }
+    return dod;
+}
+
+struct Geom {  // eval_point_geom, base_geom.f90:97-112
+    double P_ls[2], h, h2, d_ls[3][2], a[3], l1[3], l2[3], R1[3], R2[3], dR[3], g2[3], v_xi[3], v_eta[3];
+};
+
+// panel.f90:1904-1938 + base_geom.f90:501-521
+void basic_geom(const Rec& p, const double* P, Geom& g) {
+    double d[3] = {P[0] - p.centr[0], P[1] - p.centr[1], P[2] - p.centr[2]};
+    double Pls[3];
+    for (int i = 0; i < 3; ++i) Pls[i] = p.A[3 * i] * d[0] + p.A[3 * i + 1] * d[1] + p.A[3 * i + 2] * d[2];
+    g.P_ls[0] = Pls[0];
+    g.P_ls[1] = Pls[1];
+    g.h = Pls[2];
+    g.h2 = g.h * g.h;
+    for (int i = 0; i < 3; ++i) {
+        g.R1[i] = g.R2[i] = g.a[i] = 0.;
+        g.l1[i] = g.l2[i] = g.g2[i] = g.dR[i] = 0.;  // garbage in the reference; multiplied by zeros
+        g.v_xi[i] = p.nh[2 * i];
+        g.v_eta[i] = p.nh[2 * i + 1];
+        g.d_ls[i][0] = p.vls[2 * i] - g.P_ls[0];
+        g.d_ls[i][1] = p.vls[2 * i + 1] - g.P_ls[1];
+    }
+}
+
+// panel.f90:1941-1997
+void subsonic_geom(const Rec& p, const double* P, bool mirror, Geom& g) {
+    basic_geom(p, P, g);
+    for (int i = 0; i < 3; ++i) {
+        int n = (i + 1) % 3;
+        g.l1[i] = -g.d_ls[i][0] * g.v_eta[i] + g.d_ls[i][1] * g.v_xi[i];
+        g.l2[i] = -g.d_ls[n][0] * g.v_eta[i] + g.d_ls[n][1] * g.v_xi[i];
+    }
+    for (int i = 0; i < 3; ++i) {
+        g.a[i] = g.d_ls[i][0] * g.v_xi[i] + g.d_ls[i][1] * g.v_eta[i];
+        g.g2[i] = g.a[i] * g.a[i] + g.h2;
+        g.R1[i] = std::sqrt(g.d_ls[i][0] * g.d_ls[i][0] + g.d_ls[i][1] * g.d_ls[i][1] + g.h2);
+    }
+    for (int i = 0; i < 3; ++i) g.R2[i] = g.R1[(i + 1) % 3];  // cshift(R1, 1)
+    if (mirror) {
+        for (int i = 0; i < 3; ++i) {
+            double t = g.l1[i];
+            g.l1[i] = g.l2[i];
+            g.l2[i] = t;
+        }
+        double R1o[3] = {g.R1[0], g.R1[1], g.R1[2]};
+        for (int i = 0; i < 3; ++i) {
+            g.R1[i] = g.R2[i];
+            g.R2[i] = R1o[i];
+        }
+    }
+    for (int i = 0; i < 3; ++i) g.dR[i] = g.R2[i] - g.R1[i];
+}
+
+// panel.f90:2000-2091
+void supersonic_subinc_geom(const Rec& p, const double* P, bool mirror, const Dod& dod, Geom& g) {
+    basic_geom(p, P, g);
+    for (int i = 0; i < 3; ++i) {
+        if (!dod.e[i]) continue;
+        int n = (i + 1) % 3;
+        g.l1[i] = g.v_eta[i] * g.d_ls[i][0] + g.v_xi[i] * g.d_ls[i][1];
+        g.l2[i] = g.v_eta[i] * g.d_ls[n][0] + g.v_xi[i] * g.d_ls[n][1];
+        g.a[i] = g.v_xi[i] * g.d_ls[i][0] + g.v_eta[i] * g.d_ls[i][1];
+        g.g2[i] = g.a[i] * g.a[i] - p.b[i] * g.h2;
+        double x = g.d_ls[i][0] * g.d_ls[i][0] - g.d_ls[i][1] * g.d_ls[i][1] - g.h2;
+        if (x > 0. && g.d_ls[i][0] < 0.) {
+            g.R1[i] = std::sqrt(x);
+        } else {
+            g.l1[i] = -std::sqrt(std::fabs(g.g2[i]));
+            g.R1[i] = 0.;
+        }
+        x = g.d_ls[n][0] * g.d_ls[n][0] - g.d_ls[n][1] * g.d_ls[n][1] - g.h2;
+        if (x > 0. && g.d_ls[n][0] < 0.) {
+            g.R2[i] = std::sqrt(x);
+        } else {
+            g.l2[i] = std::sqrt(std::fabs(g.g2[i]));
+            g.R2[i] = 0.;
+        }
+        if (mirror) {
+            double dummy = g.l1[i];
+            if (g.R2[i] == 0.) g.l1[i] = -g.l2[i];
+            else g.l1[i] = g.l2[i];
+            if (g.R1[i] == 0.) g.l2[i] = -dummy;
+            else g.l2[i] = dummy;
+            dummy = g.R1[i];
+            g.R1[i] = g.R2[i];
+            g.R2[i] = dummy;
+        }
+    }
+    for (int i = 0; i < 3; ++i) g.dR[i] = g.R2[i] - g.R1[i];
+}
+
+struct Integrals {
+    int r, s, rs;
+    double H111, hH113, H213, H123;
+    double F111[3];
+};
+
+// panel.f90:2232-2283 (F121/F211 feed only the order-2 recursions and are not restated)
+void F_subsonic(const Geom& g, Integrals& I) {
+    for (int i = 0; i < 3; ++i) {
+        if (fsign(1., g.l1[i]) != fsign(1., g.l2[i])) {
+            I.F111[i] = std::log(((g.R1[i] - g.l1[i]) * (g.R2[i] + g.l2[i])) / g.g2[i]);
+        } else {
+            I.F111[i] = fsign(1., g.l1[i]) * std::log((g.R2[i] + std::fabs(g.l2[i])) / (g.R1[i] + std::fabs(g.l1[i])));
+        }
+    }
+}
+
+// panel.f90:2286-2407
+void F_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integrals& I) {
+    for (int i = 0; i < 3; ++i) {
+        if (!dod.e[i]) continue;
+        double b = p.b[i], s_b = p.sb[i];
+        if (g.R1[i] == 0. && g.R2[i] == 0.) {
+            I.F111[i] = pi / s_b;
+        } else {
+            double F1, F2;
+            if (b > 0.) {
+                F1 = (g.l1[i] * g.R2[i] - g.l2[i] * g.R1[i]) / g.g2[i];
+                F2 = (b * g.R1[i] * g.R2[i] + g.l1[i] * g.l2[i]) / g.g2[i];
+            } else {
+                F1 = (g.R2[i] - g.R1[i]) * (g.R2[i] + g.R1[i]) / (g.l1[i] * g.R2[i] + g.l2[i] * g.R1[i]);
+                F2 = (g.g2[i] - g.l1[i] * g.l1[i] - g.l2[i] * g.l2[i]) / (b * g.R1[i] * g.R2[i] - g.l1[i] * g.l2[i]);
+            }
+            if (std::fabs(F2) > 125.0 * std::fabs(s_b * F1)) {
+                double eps = F1 / F2;
+                double eps2 = eps * eps;
+                double series = eps * eps2 * (1. / 3. - b * eps2 / 5. + (b * eps2) * (b * eps2) / 7.);
+                I.F111[i] = -eps + b * series;
+            } else if (b > 0.) {
+                I.F111[i] = -std::atan2(s_b * F1, F2) / s_b;
+            } else {
+                F1 = s_b * g.R1[i] + std::fabs(g.l1[i]);
+                F2 = s_b * g.R2[i] + std::fabs(g.l2[i]);
+                if (F1 != 0. && F2 != 0.) I.F111[i] = -fsign(1., g.v_eta[i]) * std::log(F1 / F2) / s_b;
+            }
+        }
+    }
+}
+
+// panel.f90:2472-2509
+void hH113_subsonic(const Geom& g, Integrals& I) {
+    I.hH113 = 0.;
+    for (int i = 0; i < 3; ++i) {
+        double c1 = g.g2[i] + std::fabs(g.h) * g.R1[i];
+        double c2 = g.g2[i] + std::fabs(g.h) * g.R2[i];
+        double S = g.a[i] * (g.l2[i] * c1 - g.l1[i] * c2);
+        double C = c1 * c2 + g.a[i] * g.a[i] * g.l1[i] * g.l2[i];
+        double x = std::atan2(S, C);
+        I.hH113 = I.hH113 + x;
+    }
+    I.hH113 = fsign(I.hH113, g.h);
+}
+
+// panel.f90:2512-2573 -- F1, F2, b are real(16); operands of pure-binary64 subexpressions are
+// evaluated in binary64 first and then widened, as Fortran's mixed-mode rules prescribe.
+void hH113_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integrals& I) {
+    I.hH113 = 0.;
+    for (int i = 0; i < 3; ++i) {
+        if (!dod.e[i]) continue;
+        quad b = (quad)p.b[i];
+        if (std::fabs(g.h) > 1.e-12) {
+            if (g.R1[i] == 0. && g.R2[i] == 0.) {
+                I.hH113 = I.hH113 + pi * fsign(1., g.h * g.v_xi[i]);
+            } else {
+                quad F1, F2;
+                if (b > 0) {
+                    F1 = (quad)((g.l1[i] * g.R2[i] - g.l2[i] * g.R1[i]) / g.g2[i]);
+                    F2 = (b * (quad)g.R1[i] * (quad)g.R2[i] + (quad)(g.l1[i] * g.l2[i])) / (quad)g.g2[i];
+                } else {
+                    F1 = (quad)(g.dR[i] * (g.R2[i] + g.R1[i]) / (g.l1[i] * g.R2[i] + g.l2[i] * g.R1[i]));
+                    F2 = (quad)(g.g2[i] - g.l1[i] * g.l1[i] - g.l2[i] * g.l2[i]) /
+                         (b * (quad)g.R1[i] * (quad)g.R2[i] - (quad)(g.l1[i] * g.l2[i]));
+                }
+                quad y = (quad)(g.h * g.a[i]) * F1;
+                quad x = (quad)(g.R1[i] * g.R2[i]) + (quad)g.h2 * F2;
+                I.hH113 = (double)((quad)I.hH113 + atan2q(y, x));
+            }
+        }
+    }
+}
+
+// panel.f90:2766-2812 + 2631-2647
+void calc_integrals(const Rec& p, const Geom& g, const ml_flow* fs, const Dod& dod, Integrals& I) {
+    I.F111[0] = I.F111[1] = I.F111[2] = 0.;
+    I.r = p.r;
+    I.s = (int)fs->s;
+    I.rs = I.r * I.s;
+    if (fs->supersonic) {
+        F_supersonic_subinc(p, g, dod, I);
+        hH113_supersonic_subinc(p, g, dod, I);
+    } else {
+        F_subsonic(g, I);
+        hH113_subsonic(g, I);
+    }
+    double s1 = 0., s2 = 0., s3 = 0.;
+    for (int i = 0; i < 3; ++i) s1 = s1 + g.a[i] * I.F111[i];
+    for (int i = 0; i < 3; ++i) s2 = s2 + g.v_xi[i] * I.F111[i];
+    for (int i = 0; i < 3; ++i) s3 = s3 + g.v_eta[i] * I.F111[i];
+    I.H111 = s1 - I.rs * g.h * I.hH113;
+    I.H213 = -I.r * s2;
+    I.H123 = -I.s * s3;
+}
+
+}  // namespace
+
+// panel.f90:2917-2971.  phi_d has 3 entries (the wake's negated copy, :2909-2912, is applied by the caller).
+extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int j, int img, const double* P,
+                                   orc_pair_out* out) {
+    std::memset(out, 0, sizeof *out);
+    Rec p = get_rec(t, j, img);
+    bool mirror = img == 1;
+    Dod dod = check_dod(p, P, fs);
+    out->in_dod = dod.in_dod;
+    for (int i = 0; i < 3; ++i) out->edges_in_dod[i] = dod.e[i];
+    if (!(dod.in_dod && t->area[j] > 0.)) return;
+    Geom g;
+    if (fs->supersonic) supersonic_subinc_geom(p, P, mirror, dod, g);
+    else subsonic_geom(p, P, mirror, g);
+    Integrals I;
+    calc_integrals(p, g, fs, dod, I);
+    for (int i = 0; i < 3; ++i) out->F111[i] = I.F111[i];
+    out->hH113 = I.hH113;
+    out->H111 = I.H111;
+    out->H213 = I.H213;
+    out->H123 = I.H123;
+    out->h = g.h;
+    // assemble_phi_s_S_space (order 1), panel.f90:2852-2859
+    bool has_src = !t->in_wake && t->has_sources && t->has_sources[j];
+    out->phi_s = has_src ? -p.J * fs->K_inv * I.H111 : 0.;
+    // assemble_phi_d_M_space, panel.f90:2888-2907
+    double m[3];
+    m[0] = I.hH113;
+    m[1] = I.hH113 * g.P_ls[0] + g.h * I.H213;
+    m[2] = I.hH113 * g.P_ls[1] + g.h * I.H123;
+    for (int c = 0; c < 3; ++c) {
+        double acc = 0.;
+        for (int k = 0; k < 3; ++k) acc = acc + m[k] * p.T[3 * k + c];
+        out->phi_d[c] = I.s * fs->K_inv * acc;
+    }
+}
+
+// panel_solver.f90:1290-1501 + :1504-1706, Dirichlet / strength-matching rows.
+// A is column-major n_cp x n_unknown (A[row + col*n_cp]); rows row0..row0+nrows-1 only are filled
+// when a sub-range is requested (rows outside are left untouched).
+extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const ml_panel_soa* wake,
+                            const ml_system_map* map, int n_cp, const double* cp_loc, const int* cp_bc,
+                            const int* row_perm, int row0, int nrows, double* A, int ld, double* I_known,
+                            int n_threads) {
+    const int N_unknown = map->n_unknown, N_panels = map->n_body_panels, N_verts = map->n_verts;
+    const int* P = map->P;
+    if (n_threads <= 0) n_threads = omp_get_max_threads();
+    int status = 0;
+#pragma omp parallel for schedule(dynamic) num_threads(n_threads)
+    for (int i = 0; i < n_cp; ++i) {
+        int row = row_perm[i];
+        if (row < row0 || row >= row0 + nrows) continue;
+        std::vector<double> A_i(N_unknown, 0.);
+        double I_known_i = 0.;
+        const double* Pt = cp_loc + 3 * (size_t)i;
+        if (cp_bc[i] == ML_BC_STRENGTH_MATCHING) {
+            A_i[P[i]] = 1.;
+            A_i[P[i - n_cp / 2]] = -1.;
+        } else if (cp_bc[i] == ML_BC_ZERO_POTENTIAL || cp_bc[i] == ML_BC_SF_POTENTIAL) {
+            for (int j = 0; j < N_panels; ++j) {
+                for (int img = 0; img < body->n_images; ++img) {
+                    orc_pair_out o;
+                    orc_pair_influence(fs, body, j, img, Pt, &o);
+                    if (!o.in_dod) continue;  // panel_solver.f90:1448 / 1462
+                    bool mirrored_panel = (img == 1) && map->asym_flow;  // :1470-1471
+                    // update_system_row, panel_solver.f90:1203-1287 (S_dim = 1, M_dim = 3)
+                    if (body->has_sources[j]) {
+                        int ips = body->i_panel_s[j];
+                        int index;
+                        if (mirrored_panel) index = (ips >= N_panels) ? ips - N_panels : ips + N_panels;
+                        else index = (ips >= N_panels) ? ips - N_panels : ips;
+                        if (map->sigma_known[index]) I_known_i = I_known_i + o.phi_s * map->sigma[index];
+                        else A_i[P[map->i_sigma_in_sys[index]]] += o.phi_s;
+                    }
+                    for (int k = 0; k < 3; ++k) {
+                        int iv = body->i_vert_d[(size_t)j * body->n_cols + k];
+                        int index;
+                        if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
+                        else index = (iv >= N_verts) ? iv - N_verts : iv;
+                        A_i[P[index]] = A_i[P[index]] + o.phi_d[k];
+                    }
+                }
+            }
+        } else {
+#pragma omp critical
+            status = ML_UNSUPPORTED;
+        }
+        // wake pass (panel_solver.f90:1650-1697): a separate row accumulated from zero, then added
+        if (wake && wake->n_panels > 0 && cp_bc[i] != ML_BC_STRENGTH_MATCHING) {
+            std::vector<double> W_i(N_unknown, 0.);
+            for (int l = 0; l < wake->n_panels; ++l) {
+                for (int img = 0; img < wake->n_images; ++img) {
+                    if (img == 1 && !(wake->image_present && wake->image_present[l])) continue;
+                    orc_pair_out o;
+                    orc_pair_influence(fs, wake, l, img, Pt, &o);
+                    // in_dod = false leaves zeros (panel.f90:2959-2967), which are still "added"
+                    for (int k = 0; k < 6; ++k) {
+                        int iv = wake->i_vert_d[(size_t)l * wake->n_cols + k];
+                        double v = (k < 3) ? o.phi_d[k] : -o.phi_d[k - 3];
+                        W_i[P[iv]] = W_i[P[iv]] + v;
+                    }
+                }
+            }
+            for (int c = 0; c < N_unknown; ++c) A_i[c] = A_i[c] + W_i[c];
+        }
+        for (int c = 0; c < N_unknown; ++c) A[(size_t)row + (size_t)c * ld] = A_i[c];
+        if (I_known) I_known[row] = I_known_i;
+    }
+    return status;
+}

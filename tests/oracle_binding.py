@@ -1,0 +1,107 @@
+"""ctypes binding of oracle/liboracle.so -- TEST INFRASTRUCTURE ONLY.
+
+The oracle is the CPU restatement of the reference's hot paths (oracle/oracle_aic.cpp,
+oracle/oracle_linalg.cpp).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs may import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+from machline_b200 import _abi  # noqa: E402  (struct layouts only)
+
+ORACLE_DIR = ROOT / "oracle"
+ORACLE_LIB = ORACLE_DIR / "liboracle.so"
+
+
+class OrcPairOut(C.Structure):
+    _fields_ = [("in_dod", C.c_int), ("edges_in_dod", C.c_int * 3), ("F111", C.c_double * 3),
+                ("hH113", C.c_double), ("H111", C.c_double), ("H213", C.c_double), ("H123", C.c_double),
+                ("h", C.c_double), ("phi_s", C.c_double), ("phi_d", C.c_double * 3)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        srcs = list(ORACLE_DIR.glob("*.cpp")) + list(ORACLE_DIR.glob("*.h")) + [ROOT / "include" / "machline_gpu.h"]
+        if not ORACLE_LIB.exists() or any(s.stat().st_mtime > ORACLE_LIB.stat().st_mtime for s in srcs):
+            subprocess.run(["make", "-C", str(ORACLE_DIR), "-s"], check=True)
+        L = C.CDLL(str(ORACLE_LIB))
+        dp, ip = _abi.c_double_p, _abi.c_int_p
+        L.orc_pair_influence.argtypes = [C.POINTER(_abi.MlFlow), C.POINTER(_abi.MlPanelSoa), C.c_int, C.c_int, dp,
+                                         C.POINTER(OrcPairOut)]
+        L.orc_pair_influence.restype = None
+        L.orc_assemble.argtypes = [C.POINTER(_abi.MlFlow), C.POINTER(_abi.MlPanelSoa), C.POINTER(_abi.MlPanelSoa),
+                                   C.POINTER(_abi.MlSystemMap), C.c_int, dp, ip, ip, C.c_int, C.c_int, dp, C.c_int,
+                                   dp, C.c_int]
+        L.orc_lu_solve.argtypes = [C.c_int, dp, dp, dp]
+        L.orc_gmres.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, ip, dp, dp]
+        L.orc_restarted_gmres.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, C.c_int, ip, dp]
+        L.orc_block_jacobi.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, ip, dp]
+        L.orc_block_ssor.argtypes = [C.c_int, dp, dp, C.c_int, C.c_double, C.c_double, C.c_int, ip, dp]
+        L.orc_qr_givens_up.argtypes = [C.c_int, dp, dp, dp]
+        L.orc_qr_fast_givens_up.argtypes = [C.c_int, dp, dp, dp]
+        L.orc_purcell.argtypes = [C.c_int, dp, dp, dp]
+        L.orc_lower_bandwidth.argtypes = [C.c_int, dp]
+        L.orc_solve_system.argtypes = [C.c_int, dp, dp, dp, C.POINTER(_abi.MlSolverOpts), dp,
+                                       C.POINTER(_abi.MlSolveInfo)]
+        _lib = L
+    return _lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(_abi.c_double_p)
+
+
+def assemble(case, row0: int = 0, nrows: int | None = None, n_threads: int = 0):
+    """Oracle AIC for a machline_b200.host.Case.  Returns (A [n_cp x n_unknown, Fortran order], I_known)."""
+    n_cp, n_u = case.n_cp, case.n_unknown
+    if nrows is None:
+        nrows = n_cp - row0
+    A = np.zeros((n_cp, n_u), dtype=np.float64, order="F")
+    I_known = np.zeros(n_cp, dtype=np.float64)
+    wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
+    st = lib().orc_assemble(C.byref(case.flow), C.byref(case.body), wake, C.byref(case.map), n_cp, case.cps.loc,
+                            case.cps.bc, case.cps.row_perm, row0, nrows, _dp(A), n_cp, _dp(I_known), n_threads)
+    if st != 0:
+        raise RuntimeError(f"orc_assemble status {st}")
+    return A, I_known
+
+
+def pair(case, table, j: int, img: int, P) -> OrcPairOut:
+    out = OrcPairOut()
+    Pa = np.ascontiguousarray(P, dtype=np.float64)
+    lib().orc_pair_influence(C.byref(case.flow), C.byref(table), j, img, _dp(Pa), C.byref(out))
+    return out
+
+
+def solve_system(A, I_known, BC, opts):
+    """panel_solver_solve_system on the CPU.  Returns (x, MlSolveInfo)."""
+    N = A.shape[0]
+    A = np.asfortranarray(A, dtype=np.float64)
+    x = np.zeros(N)
+    info = _abi.MlSolveInfo()
+    I_known = np.ascontiguousarray(I_known, dtype=np.float64)
+    BC = np.ascontiguousarray(BC, dtype=np.float64)
+    st = lib().orc_solve_system(N, _dp(A), _dp(I_known), _dp(BC), C.byref(opts), _dp(x), C.byref(info))
+    if st != 0:
+        raise RuntimeError(f"orc_solve_system status {st}")
+    return x, info
+
+
+def run_case(case):
+    """Full CPU pipeline: host setup (already done in `case`) -> oracle assemble -> oracle solve -> host post."""
+    A, I_known = assemble(case)
+    x, info = solve_system(A, I_known, case.BC, case.solver_opts())
+    return case.post(x), info, A
