@@ -183,6 +183,11 @@ long long ml_launch_count(const ml_ctx *ctx);
 ml_status ml_device_system(ml_ctx *ctx, double **A_dev, int *ld, int *nrows_local, int *ncols);
 /* Re-run the assembly kernels only (inputs resident, no host transfers); returns device ms. */
 ml_status ml_assemble_resident(ml_ctx *ctx, double *device_ms);
+/* Roofline denominators measured on this device: FP64 vector pipe (register-resident DFMA loop,
+   TFLOP/s) and a streaming copy (read+write GB/s).  Either pointer may be NULL. */
+ml_status ml_measure_peaks(ml_ctx *ctx, double *fp64_tflops, double *hbm_gbs);
+/* Rank 0 makes the 128-byte NCCL unique id that every rank passes to ml_set_communicator. */
+ml_status ml_nccl_unique_id(void *out128);
 
 #ifdef __cplusplus
 }

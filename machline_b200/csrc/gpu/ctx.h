@@ -1,0 +1,128 @@
+// Internal context of libmachline_gpu.so (one per device).  See include/machline_gpu.h for the ABI.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <string>
+#include <vector>
+
+#include "../../../include/machline_gpu.h"
+#include "pair_influence.cuh"
+
+#ifdef ML_HAVE_NCCL
+#include <nccl.h>
+#endif
+
+namespace mlgpu {
+
+struct HostPanelTable {  // deep copy of an ml_panel_soa
+    int n_panels = 0, n_images = 1, n_cols = 3, in_wake = 0;
+    std::vector<double> centr, A_g_to_ls, vertices_ls, n_hat_ls, b, sqrt_b, J, area, vert_g, T_mu;
+    std::vector<int> r, i_vert_d, i_panel_s;
+    std::vector<unsigned char> has_sources, image_present;
+    void copy_from(const ml_panel_soa* t);
+};
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        if (count <= n && p) return cudaSuccess;
+        release();
+        if (count == 0) return cudaSuccess;
+        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        else p = nullptr;
+        return e;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+};
+
+struct AicLaunch {            // arguments of the assembly kernel
+    const double* recs;       // packed records, [n_rec][rec_doubles]
+    int n_rec;
+    int rec_doubles;
+    const double* cp_xyz;     // [3][n_rows_pad] control-point coordinates by local row
+    const unsigned char* row_active;  // [n_rows_pad] 1: row evaluates influences
+    int n_rows;               // local rows
+    double* A;                // column-major, ld rows
+    int ld;
+    double* I_known;          // [n_rows]
+    int n_cp_tiles, n_tiles, tiles_per_seg, n_segments;
+    int* work_counter;
+};
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    int num_sms = 148;
+    long long launches = 0;
+
+    // ---- host copies of the inputs ----
+    bool have_flow = false, have_panels = false, have_cps = false, have_map = false;
+    ml_flow flow{};
+    HostPanelTable body, wake;
+    int n_cp = 0;
+    std::vector<double> cp_loc;
+    std::vector<int> cp_bc, cp_row;
+    ml_system_map map{};
+    std::vector<int> P, i_sigma_in_sys;
+    std::vector<unsigned char> sigma_known;
+    std::vector<double> sigma;
+    int row0 = 0, nrows = -1;   // shard (global permuted rows)
+    bool dirty = true;          // device tables need rebuilding
+
+    // ---- device tables ----
+    DevBuf<double> d_recs, d_cp_xyz, d_A, d_I_known, d_work;
+    DevBuf<unsigned char> d_row_active;
+    DevBuf<int> d_counter, d_sm_rows, d_sm_colp, d_sm_colm;
+    int n_rec = 0, rec_doubles = 0, n_sm_rows = 0;
+    int n_rows = 0, n_rows_pad = 0, ld = 0, n_cols = 0;
+    bool assembled = false;
+    std::vector<double> h_I_known;  // local rows
+    long long pair_count = 0;
+    double assemble_ms = 0, solve_ms = 0;
+
+    // ---- multi-GPU ----
+    int rank = 0, world = 1;
+#ifdef ML_HAVE_NCCL
+    ncclComm_t comm = nullptr;
+#endif
+    std::vector<int> shard_row0, shard_nrows;  // per rank (equal split)
+
+    ml_status fail(ml_status st, const std::string& msg) {
+        err = msg;
+        return st;
+    }
+    ml_status cuda_fail(cudaError_t e, const char* where) {
+        err = std::string(where) + ": " + cudaGetErrorString(e);
+        return ML_CUDA_ERROR;
+    }
+};
+
+#define ML_CUDA(ctx, call)                                            \
+    do {                                                              \
+        cudaError_t e__ = (call);                                     \
+        if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call);  \
+    } while (0)
+
+// aic_kernels.cu
+cudaError_t upload_flow_constants(const ml_flow& f, cudaStream_t s);
+cudaError_t launch_aic(Ctx* c, const AicLaunch& L, bool supersonic);
+cudaError_t launch_strength_rows(Ctx* c, double* A, int ld, const int* rows, const int* colp, const int* colm, int n);
+int aic_tile_records();
+
+// solve_kernels.cu / lu_kernels.cu
+ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info);
+ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_b, const ml_solver_opts* opts,
+                             double* x_out, ml_solve_info* info, bool A_is_scratch);
+
+}  // namespace mlgpu
+
+struct ml_ctx : public mlgpu::Ctx {};

@@ -1,0 +1,621 @@
+// Dense solve on sm_100a: replaces the select-case of panel_solver_solve_system
+// (src/panel_solver.f90:1802-2027) and the iterative solvers of common/linalg.f90:
+//   diagonal_preconditioner  :1798-1831  (reproduced as the uniform scale 1/A(N,N) it really is, folded
+//                                          into the matvec instead of copying A into A_p)
+//   arnoldi_update / GMRES   :1208-1334
+//   restarted_GMRES          :1337-1453
+//   block_jacobi_solve       :601-728    (uses lu_kernels.cu for the diagonal blocks)
+// The matrix stays where the assembly kernel built it: column-major, rows sharded across ranks.
+// Per iteration the only HBM-heavy kernel is gemv_n (one pass over the local rows of A);
+// with several ranks the slices of w are all-gathered over NCCL (8 N bytes) and the
+// orthogonalisation is replicated, so no reduction collective is needed.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "ctx.h"
+
+namespace mlgpu {
+
+// ---------------------------------------------------------------------------------------------------
+// y_part[ks][row] = sum over the ks-th column range of A[row, col] * x[col]      (HBM-bound)
+// CTA = 8 warps over the same 64 rows (lane owns 2 rows -> 128-bit loads), warps stride the columns.
+// ---------------------------------------------------------------------------------------------------
+constexpr int GEMV_THREADS = 256;
+constexpr int GEMV_ROWS = 64;
+constexpr int GEMV_UNROLL = 8;
+
+__device__ __forceinline__ double2 ld_stream_d2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+__global__ void __launch_bounds__(GEMV_THREADS) gemv_n_partial_kernel(const double* __restrict__ A, int ld, int n_rows_pad,
+                                                                       int n_cols, int cols_per_split,
+                                                                       const double* __restrict__ x,
+                                                                       double* __restrict__ y_part) {
+    __shared__ double2 s_acc[GEMV_THREADS / 32][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * GEMV_ROWS + 2 * lane;
+    const int c0 = blockIdx.y * cols_per_split;
+    const int c1 = min(c0 + cols_per_split, n_cols);
+    constexpr int NW = GEMV_THREADS / 32;
+    double2 acc = make_double2(0., 0.);
+    const double* Ap = A + row;
+    int c = c0 + warp;
+    // main loop: GEMV_UNROLL independent 16-byte loads in flight per thread
+    for (; c + (GEMV_UNROLL - 1) * NW < c1; c += GEMV_UNROLL * NW) {
+        double2 v[GEMV_UNROLL];
+        double xv[GEMV_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GEMV_UNROLL; ++u) v[u] = ld_stream_d2(Ap + (size_t)(c + u * NW) * ld);
+#pragma unroll
+        for (int u = 0; u < GEMV_UNROLL; ++u) xv[u] = __ldg(x + c + u * NW);
+#pragma unroll
+        for (int u = 0; u < GEMV_UNROLL; ++u) {
+            acc.x = fma(v[u].x, xv[u], acc.x);
+            acc.y = fma(v[u].y, xv[u], acc.y);
+        }
+    }
+    for (; c < c1; c += NW) {
+        double2 v = ld_stream_d2(Ap + (size_t)c * ld);
+        double xv = __ldg(x + c);
+        acc.x = fma(v.x, xv, acc.x);
+        acc.y = fma(v.y, xv, acc.y);
+    }
+    s_acc[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0) {
+        double2 s = s_acc[0][lane];
+#pragma unroll
+        for (int w = 1; w < NW; ++w) {
+            s.x += s_acc[w][lane].x;
+            s.y += s_acc[w][lane].y;
+        }
+        double2* out = reinterpret_cast<double2*>(y_part + (size_t)blockIdx.y * n_rows_pad + row);
+        *out = s;
+    }
+}
+
+// y[row] = alpha * sum_ks y_part[ks][row] (+ beta_vec[row]*beta)   -- fixed order, deterministic
+__global__ void gemv_n_finish_kernel(const double* __restrict__ y_part, int n_rows_pad, int n_rows, int n_split,
+                                     const double* __restrict__ alpha_dev, double alpha, double* __restrict__ y) {
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double s = 0.;
+    for (int k = 0; k < n_split; ++k) s += y_part[(size_t)k * n_rows_pad + row];
+    double a = alpha_dev ? (*alpha_dev) * alpha : alpha;
+    y[row] = a * s;
+}
+
+// h[j] (+)= Q[:, j] . w   for j = 0..ncol-1; one CTA per column, fixed-order block reduction
+__global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ Q, int ldq, int n, const double* __restrict__ w,
+                                                      double* __restrict__ h, int accumulate) {
+    __shared__ double s_part[8];
+    const int j = blockIdx.x;
+    const double* q = Q + (size_t)j * ldq;
+    double acc = 0.;
+    for (int i = threadIdx.x; i < n; i += 256) acc = fma(q[i], w[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_part[k];
+        h[j] = accumulate ? h[j] + s : s;
+    }
+}
+
+// w[i] -= sum_j Q[i, j] * h[j]
+__global__ void __launch_bounds__(256) gemv_n_sub_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
+                                                          const double* __restrict__ h, double* __restrict__ w) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.;
+    for (int j = 0; j < ncol; ++j) acc = fma(Q[i + (size_t)j * ldq], __ldg(h + j), acc);
+    w[i] -= acc;
+}
+
+// x[i] (+)= sum_j Q[i, j] * y[j]
+__global__ void __launch_bounds__(256) gemv_n_small_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
+                                                            const double* __restrict__ y, double* __restrict__ x, int accumulate) {
+    int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.;
+    for (int j = 0; j < ncol; ++j) acc = fma(Q[i + (size_t)j * ldq], __ldg(y + j), acc);
+    x[i] = accumulate ? x[i] + acc : acc;
+}
+
+// out[0] = sqrt(sum w^2) (single CTA, fixed order); optionally q = w / norm
+__global__ void __launch_bounds__(1024) norm_scale_kernel(const double* __restrict__ w, int n, double* __restrict__ norm_out,
+                                                           double* __restrict__ q) {
+    __shared__ double s_part[32];
+    __shared__ double s_norm;
+    double acc = 0.;
+    for (int i = threadIdx.x; i < n; i += 1024) acc = fma(w[i], w[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.;
+        for (int k = 0; k < 32; ++k) s += s_part[k];
+        s_norm = sqrt(s);
+        *norm_out = s_norm;
+    }
+    __syncthreads();
+    if (q) {
+        const double nrm = s_norm;
+        for (int i = threadIdx.x; i < n; i += 1024) q[i] = w[i] / nrm;
+    }
+}
+
+// Modified Gram-Schmidt in the reference's order (linalg.f90:1222-1226): one CTA walks the basis.
+__global__ void __launch_bounds__(1024) mgs_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
+                                                    double* __restrict__ w, double* __restrict__ h) {
+    __shared__ double s_part[32];
+    __shared__ double s_h;
+    for (int j = 0; j < ncol; ++j) {
+        const double* q = Q + (size_t)j * ldq;
+        double acc = 0.;
+        for (int i = threadIdx.x; i < n; i += 1024) acc = fma(w[i], q[i], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double s = 0.;
+            for (int k = 0; k < 32; ++k) s += s_part[k];
+            s_h = s;
+            h[j] = s;
+        }
+        __syncthreads();
+        const double hj = s_h;
+        for (int i = threadIdx.x; i < n; i += 1024) w[i] = w[i] - hj * q[i];
+        __syncthreads();
+    }
+}
+
+__global__ void scale_copy_kernel(const double* __restrict__ src, double alpha, const double* alpha_dev, double* __restrict__ dst,
+                                  int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (alpha_dev ? *alpha_dev * alpha : alpha) * src[i];
+}
+
+__global__ void axpby_kernel(double a, const double* __restrict__ x, double b, const double* __restrict__ y,
+                             double* __restrict__ out, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a * x[i] + b * y[i];
+}
+
+__global__ void recip_kernel(const double* src, double* dst) { *dst = 1. / *src; }
+
+// ---------------------------------------------------------------------------------------------------
+// Host-side drivers
+// ---------------------------------------------------------------------------------------------------
+struct Sys {            // the (possibly row-sharded) system seen by the solvers
+    Ctx* c;
+    const double* A;    // local rows, column-major
+    int ld, n_rows, n_rows_pad, N;
+    int row0;           // first global row of this shard
+    int shard_pad;      // rows per rank in the all-gather layout
+    DevBuf<double> y_part, gather;
+    int n_split = 1, cols_per_split = 0;
+
+    ml_status init() {
+        // enough CTAs for >= 4 per SM; splits of at least 256 columns
+        int row_blocks = n_rows_pad / GEMV_ROWS;
+        if (row_blocks < 1) row_blocks = 1;
+        int want = c->num_sms * 4;
+        n_split = std::max(1, std::min((want + row_blocks - 1) / row_blocks, std::max(1, N / 256)));
+        cols_per_split = (N + n_split - 1) / n_split;
+        n_split = (N + cols_per_split - 1) / cols_per_split;
+        ML_CUDA(c, y_part.alloc((size_t)n_split * n_rows_pad));
+        if (c->world > 1) ML_CUDA(c, gather.alloc((size_t)shard_pad * c->world));
+        return ML_OK;
+    }
+    // y_full[N] = alpha * (alpha_dev ? *alpha_dev : 1) * A x      (x, y_full replicated full-length vectors)
+    ml_status matvec(const double* x, double* y_full, double alpha, const double* alpha_dev) {
+        dim3 grid(n_rows_pad / GEMV_ROWS, n_split);
+        gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p);
+        double* dst = (c->world > 1) ? gather.p + (size_t)c->rank * shard_pad : y_full;
+        gemv_n_finish_kernel<<<(n_rows + 255) / 256, 256, 0, c->stream>>>(y_part.p, n_rows_pad, n_rows, n_split, alpha_dev, alpha, dst);
+        c->launches += 2;
+        ML_CUDA(c, cudaGetLastError());
+#ifdef ML_HAVE_NCCL
+        if (c->world > 1) {
+            ncclResult_t r = ncclAllGather(gather.p + (size_t)c->rank * shard_pad, gather.p, shard_pad, ncclDouble, c->comm, c->stream);
+            if (r != ncclSuccess) return c->fail(ML_NCCL_ERROR, ncclGetErrorString(r));
+            // compact the padded shards into the contiguous full vector
+            for (int rk = 0; rk < c->world; ++rk) {
+                int r0 = c->shard_row0[rk], nr = c->shard_nrows[rk];
+                if (nr > 0)
+                    ML_CUDA(c, cudaMemcpyAsync(y_full + r0, gather.p + (size_t)rk * shard_pad, (size_t)nr * sizeof(double),
+                                               cudaMemcpyDeviceToDevice, c->stream));
+            }
+        }
+#endif
+        return ML_OK;
+    }
+    void release() {
+        y_part.release();
+        gather.release();
+    }
+};
+
+static inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }
+
+// GMRES / restarted GMRES (linalg.f90:1235-1453) on the scaled system (scale*A) x = scale*b.
+static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, double tol, int max_iter, int restart_iter,
+                              bool restarted, bool use_mgs, double* d_x, int* total_iter_out) {
+    Ctx* c = S.c;
+    const int N = S.N;
+    const int k_max = restarted ? std::min(restart_iter, N) : std::min(N, max_iter);
+    if (k_max < 1) return c->fail(ML_BAD_ARGUMENT, "max_iterations < 1");
+    DevBuf<double> Q, w, hdev, nrm, r0, ydev;
+    ML_CUDA(c, Q.alloc((size_t)N * (k_max + 1)));
+    ML_CUDA(c, w.alloc(N));
+    ML_CUDA(c, hdev.alloc(2 * (size_t)(k_max + 2)));
+    ML_CUDA(c, nrm.alloc(2));
+    ML_CUDA(c, r0.alloc(N));
+    ML_CUDA(c, ydev.alloc(k_max + 1));
+    const int ldh = k_max + 1;
+    std::vector<double> H((size_t)ldh * k_max, 0.), cs(k_max, 0.), sn(k_max, 0.), E(std::max(N, k_max + 1) + 1, 0.), hcol(k_max + 2);
+    ML_CUDA(c, cudaMemsetAsync(d_x, 0, (size_t)N * sizeof(double), c->stream));
+    int total_iter = 0;
+    double err = tol + 1;
+    const int nb = (N + 255) / 256;
+    ml_status st = ML_OK;
+    auto cleanup = [&]() {
+        Q.release(); w.release(); hdev.release(); nrm.release(); r0.release(); ydev.release();
+    };
+    bool first_cycle = true;
+    while (err > tol && (restarted ? total_iter <= max_iter : first_cycle)) {
+        first_cycle = false;
+        std::fill(H.begin(), H.end(), 0.);
+        std::fill(cs.begin(), cs.end(), 0.);
+        std::fill(sn.begin(), sn.end(), 0.);
+        std::fill(E.begin(), E.end(), 0.);
+        E[0] = 1.;
+        // r0 = scale*b - (scale*A) x   (x = 0 in the first cycle: r0 = scale*b exactly as linalg.f90:1268)
+        if (restarted && total_iter > 0) {
+            st = S.matvec(d_x, w.p, 1.0, d_scale);
+            if (st != ML_OK) { cleanup(); return st; }
+            scale_copy_kernel<<<nb, 256, 0, c->stream>>>(d_b, 1.0, d_scale, r0.p, N);
+            axpby_kernel<<<nb, 256, 0, c->stream>>>(1.0, r0.p, -1.0, w.p, r0.p, N);
+            c->launches += 2;
+        } else {
+            scale_copy_kernel<<<nb, 256, 0, c->stream>>>(d_b, 1.0, d_scale, r0.p, N);
+            c->launches += 1;
+        }
+        norm_scale_kernel<<<1, 1024, 0, c->stream>>>(r0.p, N, nrm.p, Q.p);  // beta, Q(:,1) = r0/beta
+        c->launches += 1;
+        double beta = 0.;
+        ML_CUDA(c, cudaMemcpyAsync(&beta, nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        ML_CUDA(c, cudaStreamSynchronize(c->stream));
+        if (!(beta == beta)) { cleanup(); return ML_NAN_IN_SYSTEM; }
+        int k = 0;
+        while (err > tol && k < k_max - 1) {
+            k += 1;
+            total_iter += 1;
+            const int kk = k - 1;
+            // arnoldi_update (linalg.f90:1208-1232)
+            st = S.matvec(Q.p + (size_t)kk * N, w.p, 1.0, d_scale);
+            if (st != ML_OK) { cleanup(); return st; }
+            if (use_mgs) {
+                mgs_kernel<<<1, 1024, 0, c->stream>>>(Q.p, N, N, k, w.p, hdev.p);
+                c->launches += 1;
+            } else {
+                // classical Gram-Schmidt with one re-orthogonalisation pass (same subspace, device-parallel)
+                gemv_t_kernel<<<k, 256, 0, c->stream>>>(Q.p, N, N, w.p, hdev.p, 0);
+                gemv_n_sub_kernel<<<nb, 256, 0, c->stream>>>(Q.p, N, N, k, hdev.p, w.p);
+                gemv_t_kernel<<<k, 256, 0, c->stream>>>(Q.p, N, N, w.p, hdev.p + (k_max + 2), 0);
+                gemv_n_sub_kernel<<<nb, 256, 0, c->stream>>>(Q.p, N, N, k, hdev.p + (k_max + 2), w.p);
+                c->launches += 4;
+            }
+            norm_scale_kernel<<<1, 1024, 0, c->stream>>>(w.p, N, hdev.p + k, Q.p + (size_t)k * N);
+            c->launches += 1;
+            ML_CUDA(c, cudaMemcpyAsync(hcol.data(), hdev.p, (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            std::vector<double> h2;
+            if (!use_mgs) {
+                h2.resize(k);
+                ML_CUDA(c, cudaMemcpyAsync(h2.data(), hdev.p + (k_max + 2), (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+            }
+            ML_CUDA(c, cudaStreamSynchronize(c->stream));
+            for (int i = 0; i < k; ++i) H[i + (size_t)kk * ldh] = hcol[i] + (use_mgs ? 0. : h2[i]);
+            H[k + (size_t)kk * ldh] = hcol[k];
+            // Givens updates (linalg.f90:1293-1313), on the host: k+1 numbers per iteration
+            for (int i = 0; i < kk; ++i) {
+                double temp = cs[i] * H[i + (size_t)kk * ldh] + sn[i] * H[(i + 1) + (size_t)kk * ldh];
+                H[(i + 1) + (size_t)kk * ldh] = -sn[i] * H[i + (size_t)kk * ldh] + cs[i] * H[(i + 1) + (size_t)kk * ldh];
+                H[i + (size_t)kk * ldh] = temp;
+            }
+            const double hkk = H[kk + (size_t)kk * ldh], hk1 = H[(kk + 1) + (size_t)kk * ldh];
+            const double d = std::sqrt(hkk * hkk + hk1 * hk1);
+            cs[kk] = std::fabs(hkk) / d;
+            sn[kk] = fsign(1., hkk) * hk1 / d;
+            H[kk + (size_t)kk * ldh] = cs[kk] * hkk + sn[kk] * hk1;
+            H[(kk + 1) + (size_t)kk * ldh] = 0.;
+            E[kk + 1] = -sn[kk] * E[kk];
+            E[kk] = cs[kk] * E[kk];
+            err = beta * std::fabs(E[kk + 1]);
+            if (!restarted && err < tol) break;
+        }
+        if (k == 0) break;
+        // back substitution (linalg.f90:930-965) and x (+)= Q(:,1:k) y
+        std::vector<double> y(k);
+        for (int i = k - 1; i >= 0; --i) {
+            double v = beta * E[i];
+            for (int j = i + 1; j < k; ++j) v = v - H[i + (size_t)j * ldh] * y[j];
+            if (H[i + (size_t)i * ldh] == 0.) { cleanup(); return ML_SINGULAR; }
+            y[i] = v / H[i + (size_t)i * ldh];
+        }
+        ML_CUDA(c, cudaMemcpyAsync(ydev.p, y.data(), (size_t)k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        gemv_n_small_kernel<<<nb, 256, 0, c->stream>>>(Q.p, N, N, k, ydev.p, d_x, restarted ? 1 : 0);
+        c->launches += 1;
+        ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    }
+    *total_iter_out = total_iter;
+    cleanup();
+    return ML_OK;
+}
+
+ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, double* d_x);  // lu_kernels.cu
+ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
+                              int max_iter, int* iters, double* d_x);                        // lu_kernels.cu
+
+// Common tail: dispatch + residual.  d_scale points at 1/A(N,N) on the device when the "DIAG"
+// preconditioner is selected, else nullptr.
+static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_b, const double* d_scale, double* d_x,
+                            ml_solve_info* info, double* lu_matrix /* full square copy or nullptr */, int lu_ld) {
+    Ctx* c = S.c;
+    int iters = -1;
+    ml_status st = ML_OK;
+    const bool use_mgs = std::getenv("MACHLINE_GMRES_MGS") != nullptr;
+    int block_size = opts->block_size;
+    if (block_size <= 0) block_size = S.N / 5;  // panel_solver.f90:1910-1912
+    switch (opts->matrix_solver) {
+        case ML_SOLVER_LU:
+            if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "LU needs the full matrix on one device");
+            st = lu_solve_device(c, S.N, lu_matrix, lu_ld, d_b, d_x);
+            break;
+        case ML_SOLVER_BJAC:
+            if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "BJAC needs the full matrix on one device");
+            st = block_jacobi_device(c, S.N, lu_matrix, lu_ld, d_b, block_size, opts->tol, opts->rel, opts->max_iterations, &iters, d_x);
+            break;
+        case ML_SOLVER_RGMRES:
+            st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, true, use_mgs, d_x, &iters);
+            break;
+        case ML_SOLVER_QRUP:
+        case ML_SOLVER_FQRUP:
+        case ML_SOLVER_PURC:
+        case ML_SOLVER_BSSOR:
+            return c->fail(ML_UNSUPPORTED, "QRUP/FQRUP/PURC/BSSOR are sequential solvers outside the GPU hot-path scope (DESIGN.md)");
+        case ML_SOLVER_GMRES:
+        default:  // invalid names fall back to GMRES (panel_solver.f90:1969-1973)
+            st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, false, use_mgs, d_x, &iters);
+            break;
+    }
+    if (st != ML_OK) return st;
+    if (info) info->iterations = iters;
+    return ML_OK;
+}
+
+// R = A x - b: max and 2-norm (panel_solver.f90:1992-1998), with the unscaled A
+static ml_status residual(Sys& S, const double* d_x, const double* d_b, ml_solve_info* info) {
+    Ctx* c = S.c;
+    DevBuf<double> Ax;
+    ML_CUDA(c, Ax.alloc(S.N));
+    ml_status st = S.matvec(d_x, Ax.p, 1.0, nullptr);
+    if (st != ML_OK) { Ax.release(); return st; }
+    std::vector<double> hAx(S.N), hb(S.N);
+    ML_CUDA(c, cudaMemcpyAsync(hAx.data(), Ax.p, (size_t)S.N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaMemcpyAsync(hb.data(), d_b, (size_t)S.N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    Ax.release();
+    double mx = 0., ss = 0.;
+    for (int i = 0; i < S.N; ++i) {
+        double r = hAx[i] - hb[i];
+        mx = std::max(mx, std::fabs(r));
+        ss += r * r;
+    }
+    if (info) {
+        info->res_max = mx;
+        info->res_norm = std::sqrt(ss);
+    }
+    if (!(ss == ss)) return ML_NAN_RESIDUAL;
+    return ML_OK;
+}
+
+// Solve with the matrix the assembly left resident (possibly row-sharded).
+ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info) {
+    const int N = c->n_cols;
+    if (c->n_cp != N) return c->fail(ML_UNSUPPORTED, "only square systems are supported (least-squares formulations are out of scope)");
+    ML_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    Sys S{};
+    S.c = c;
+    S.A = c->d_A.p;
+    S.ld = c->ld;
+    S.n_rows = c->n_rows;
+    S.n_rows_pad = c->n_rows_pad;
+    S.N = N;
+    S.row0 = c->row0;
+    // all-gather layout: every rank contributes shard_pad entries
+    if (c->world > 1) {
+#ifdef ML_HAVE_NCCL
+        // exchange (row0, nrows) of every rank
+        std::vector<int> mine = {c->row0, c->n_rows}, all(2 * c->world);
+        DevBuf<int> dm, da;
+        ML_CUDA(c, dm.alloc(2));
+        ML_CUDA(c, da.alloc(2 * c->world));
+        ML_CUDA(c, cudaMemcpyAsync(dm.p, mine.data(), 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        if (ncclAllGather(dm.p, da.p, 2, ncclInt, c->comm, c->stream) != ncclSuccess) return c->fail(ML_NCCL_ERROR, "allgather shards");
+        ML_CUDA(c, cudaMemcpyAsync(all.data(), da.p, 2 * c->world * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ML_CUDA(c, cudaStreamSynchronize(c->stream));
+        dm.release();
+        da.release();
+        c->shard_row0.resize(c->world);
+        c->shard_nrows.resize(c->world);
+        int mxr = 0;
+        for (int r = 0; r < c->world; ++r) {
+            c->shard_row0[r] = all[2 * r];
+            c->shard_nrows[r] = all[2 * r + 1];
+            mxr = std::max(mxr, all[2 * r + 1]);
+        }
+        S.shard_pad = ((mxr + 63) / 64) * 64;
+#else
+        return c->fail(ML_UNSUPPORTED, "library built without NCCL");
+#endif
+    } else {
+        if (c->n_rows != N) return c->fail(ML_BAD_ARGUMENT, "row shard set but no communicator joined");
+        S.shard_pad = c->n_rows_pad;
+    }
+    ml_status st = S.init();
+    if (st != ML_OK) return st;
+
+    // b = BC - I_known (panel_solver.f90:1818); I_known lives sharded -> build the full b on the host
+    std::vector<double> b(N);
+    std::vector<double> Ik_full(N, 0.);
+    if (c->world > 1) {
+#ifdef ML_HAVE_NCCL
+        DevBuf<double> g;
+        ML_CUDA(c, g.alloc((size_t)S.shard_pad * c->world));
+        ML_CUDA(c, cudaMemcpyAsync(g.p + (size_t)c->rank * S.shard_pad, c->d_I_known.p, (size_t)c->n_rows * sizeof(double),
+                                   cudaMemcpyDeviceToDevice, c->stream));
+        if (ncclAllGather(g.p + (size_t)c->rank * S.shard_pad, g.p, S.shard_pad, ncclDouble, c->comm, c->stream) != ncclSuccess)
+            return c->fail(ML_NCCL_ERROR, "allgather I_known");
+        std::vector<double> tmp((size_t)S.shard_pad * c->world);
+        ML_CUDA(c, cudaMemcpyAsync(tmp.data(), g.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        ML_CUDA(c, cudaStreamSynchronize(c->stream));
+        g.release();
+        for (int r = 0; r < c->world; ++r)
+            for (int i = 0; i < c->shard_nrows[r]; ++i) Ik_full[c->shard_row0[r] + i] = tmp[(size_t)r * S.shard_pad + i];
+#endif
+    } else {
+        for (int i = 0; i < N; ++i) Ik_full[i] = c->h_I_known[i];
+    }
+    for (int i = 0; i < N; ++i) b[i] = BC[i] - Ik_full[i];
+    for (int i = 0; i < N; ++i)
+        if (!(b[i] == b[i])) return c->fail(ML_NAN_IN_SYSTEM, "NaN in b");
+
+    DevBuf<double> d_b, d_x, d_scale;
+    ML_CUDA(c, d_b.alloc(N));
+    ML_CUDA(c, d_x.alloc(N));
+    ML_CUDA(c, d_scale.alloc(2));
+    ML_CUDA(c, cudaMemcpyAsync(d_b.p, b.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const double* scale_ptr = nullptr;
+    if (opts->preconditioner == ML_PREC_DIAG) {
+        // linalg.f90:1813-1816: A_ii_inv(:) = 1/A(N,N).  Row N-1 lives on the rank that owns it.
+        const int last = N - 1;
+        const bool mine = last >= c->row0 && last < c->row0 + c->n_rows;
+        if (mine) {
+            recip_kernel<<<1, 1, 0, c->stream>>>(c->d_A.p + (last - c->row0) + (size_t)last * c->ld, d_scale.p);
+            c->launches += 1;
+        }
+#ifdef ML_HAVE_NCCL
+        if (c->world > 1) {
+            int owner = 0;
+            for (int r = 0; r < c->world; ++r)
+                if (last >= c->shard_row0[r] && last < c->shard_row0[r] + c->shard_nrows[r]) owner = r;
+            if (ncclBroadcast(d_scale.p, d_scale.p, 1, ncclDouble, owner, c->comm, c->stream) != ncclSuccess)
+                return c->fail(ML_NCCL_ERROR, "broadcast scale");
+        }
+#endif
+        scale_ptr = d_scale.p;
+    }
+
+    // Direct / block solvers work on a private full copy (the reference's A_p), single device only.
+    DevBuf<double> Acopy;
+    double* lu_matrix = nullptr;
+    if (opts->matrix_solver == ML_SOLVER_LU || opts->matrix_solver == ML_SOLVER_BJAC) {
+        if (c->world > 1) return c->fail(ML_UNSUPPORTED, "LU/BJAC on a row-sharded system are not built yet");
+        ML_CUDA(c, Acopy.alloc((size_t)c->ld * N));
+        ML_CUDA(c, cudaMemcpyAsync(Acopy.p, c->d_A.p, (size_t)c->ld * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        lu_matrix = Acopy.p;
+    }
+    st = run_solver(S, opts, d_b.p, scale_ptr, d_x.p, info, lu_matrix, c->ld);
+    Acopy.release();
+    if (st == ML_OK) st = residual(S, d_x.p, d_b.p, info);
+    if (st == ML_OK || st == ML_NAN_RESIDUAL) {
+        ML_CUDA(c, cudaMemcpyAsync(x_out, d_x.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    ML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->solve_ms = ms;
+    if (info) {
+        info->assemble_ms = c->assemble_ms;
+        info->solve_ms = ms;
+    }
+    d_b.release();
+    d_x.release();
+    d_scale.release();
+    S.release();
+    return st;
+}
+
+// Stand-alone dense solve of a device matrix (column-major, ld); A may be overwritten if A_is_scratch.
+ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_b, const ml_solver_opts* opts, double* x_out,
+                             ml_solve_info* info, bool A_is_scratch) {
+    ML_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    Sys S{};
+    S.c = c;
+    S.A = dA;
+    S.ld = ld;
+    S.n_rows = N;
+    S.n_rows_pad = ld;
+    S.N = N;
+    S.row0 = 0;
+    S.shard_pad = ld;
+    int saved_world = c->world;
+    c->world = 1;  // a host-supplied dense system is never sharded
+    ml_status st = S.init();
+    if (st != ML_OK) { c->world = saved_world; return st; }
+    DevBuf<double> d_b, d_x, d_scale, Acopy;
+    ML_CUDA(c, d_b.alloc(N));
+    ML_CUDA(c, d_x.alloc(N));
+    ML_CUDA(c, d_scale.alloc(2));
+    ML_CUDA(c, cudaMemcpyAsync(d_b.p, h_b, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    const double* scale_ptr = nullptr;
+    if (opts->preconditioner == ML_PREC_DIAG) {
+        recip_kernel<<<1, 1, 0, c->stream>>>(dA + (N - 1) + (size_t)(N - 1) * ld, d_scale.p);
+        c->launches += 1;
+        scale_ptr = d_scale.p;
+    }
+    double* lu_matrix = nullptr;
+    if (opts->matrix_solver == ML_SOLVER_LU || opts->matrix_solver == ML_SOLVER_BJAC) {
+        (void)A_is_scratch;  // the residual below needs the original matrix: always factor a copy
+        ML_CUDA(c, Acopy.alloc((size_t)ld * N));
+        ML_CUDA(c, cudaMemcpyAsync(Acopy.p, dA, (size_t)ld * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        lu_matrix = Acopy.p;
+    }
+    st = run_solver(S, opts, d_b.p, scale_ptr, d_x.p, info, lu_matrix, ld);
+    Acopy.release();
+    if (st == ML_OK) st = residual(S, d_x.p, d_b.p, info);
+    if (st == ML_OK || st == ML_NAN_RESIDUAL)
+        ML_CUDA(c, cudaMemcpyAsync(x_out, d_x.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->solve_ms = ms;
+    if (info) {
+        info->assemble_ms = 0.;
+        info->solve_ms = ms;
+    }
+    d_b.release();
+    d_x.release();
+    d_scale.release();
+    S.release();
+    c->world = saved_world;
+    return st;
+}
+
+}  // namespace mlgpu

@@ -1,0 +1,174 @@
+"""ctypes wrapper over libmachline_gpu.so (include/machline_gpu.h).
+
+The library is the product's only compute path: there is no CPU fallback.  Loading it on a box
+without the built extension, or creating a context without a CUDA device, raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _abi, build
+
+
+class GpuError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"{_abi.ML_STATUS_NAMES.get(status, status)}: {msg}")
+        self.status = status
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        path = build.GPU_LIB
+        if not path.exists():
+            raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(the CUDA extension is the only compute path; there is no fallback)")
+        L = C.CDLL(str(path))
+        vp, dp, ip = C.c_void_p, _abi.c_double_p, _abi.c_int_p
+        L.ml_abi_version.restype = C.c_int
+        L.ml_ctx_create.argtypes = [C.POINTER(vp), C.c_int]
+        L.ml_ctx_destroy.argtypes = [vp]
+        L.ml_ctx_destroy.restype = None
+        L.ml_last_error.argtypes = [vp]
+        L.ml_last_error.restype = C.c_char_p
+        L.ml_set_flow.argtypes = [vp, C.POINTER(_abi.MlFlow)]
+        L.ml_set_panels.argtypes = [vp, C.POINTER(_abi.MlPanelSoa), C.POINTER(_abi.MlPanelSoa)]
+        L.ml_set_control_points.argtypes = [vp, C.c_int, dp, ip, dp, ip]
+        L.ml_set_system_map.argtypes = [vp, C.POINTER(_abi.MlSystemMap)]
+        L.ml_set_row_shard.argtypes = [vp, C.c_int, C.c_int]
+        L.ml_set_communicator.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
+        L.ml_assemble.argtypes = [vp, dp]
+        L.ml_assemble_resident.argtypes = [vp, dp]
+        L.ml_get_A.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int]
+        L.ml_pair_count.argtypes = [vp]
+        L.ml_pair_count.restype = C.c_longlong
+        L.ml_launch_count.argtypes = [vp]
+        L.ml_launch_count.restype = C.c_longlong
+        L.ml_solve.argtypes = [vp, C.POINTER(_abi.MlSolverOpts), dp, dp, C.POINTER(_abi.MlSolveInfo)]
+        L.ml_solve_dense.argtypes = [vp, C.c_int, dp, dp, C.POINTER(_abi.MlSolverOpts), dp,
+                                     C.POINTER(_abi.MlSolveInfo)]
+        L.ml_device_system.argtypes = [vp, C.POINTER(dp), ip, ip, ip]
+        L.ml_measure_peaks.argtypes = [vp, dp, dp]
+        L.ml_nccl_unique_id.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _dp(a: np.ndarray):
+    return a.ctypes.data_as(_abi.c_double_p)
+
+
+class Context:
+    """One ml_ctx bound to one CUDA device."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        st = lib().ml_ctx_create(C.byref(self._h), device)
+        if st != 0:
+            raise GpuError(st, "ml_ctx_create failed (no CUDA device visible?)")
+        self.device = device
+        self.row0 = 0
+        self.nrows = None
+        self.n_unknown = 0
+
+    def _check(self, st: int):
+        if st != 0:
+            raise GpuError(st, lib().ml_last_error(self._h).decode())
+
+    # ---- inputs ----------------------------------------------------------------------------------
+    def set_case(self, case, row0: int = 0, nrows: int | None = None):
+        """Stage the tables of a machline_b200.host.Case (host -> device happens in assemble())."""
+        L = lib()
+        self._check(L.ml_set_flow(self._h, C.byref(case.flow)))
+        wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
+        self._check(L.ml_set_panels(self._h, C.byref(case.body), wake))
+        self._check(L.ml_set_control_points(self._h, case.cps.n_cp, case.cps.loc, case.cps.bc, case.cps.n_g,
+                                            case.cps.row_perm))
+        self._check(L.ml_set_system_map(self._h, C.byref(case.map)))
+        self.n_unknown = case.n_unknown
+        self.n_cp = case.n_cp
+        if nrows is None:
+            nrows = case.n_cp - row0
+        self._check(L.ml_set_row_shard(self._h, row0, nrows))
+        self.row0, self.nrows = row0, nrows
+
+    def set_communicator(self, unique_id: bytes, rank: int, world: int):
+        buf = C.create_string_buffer(unique_id, len(unique_id))
+        self._check(lib().ml_set_communicator(self._h, buf, rank, world))
+
+    # ---- hot path 1 --------------------------------------------------------------------------------
+    def assemble(self) -> np.ndarray:
+        """ml_assemble: builds A on the device, returns I_known for the local rows."""
+        I_known = np.zeros(self.nrows, dtype=np.float64)
+        self._check(lib().ml_assemble(self._h, _dp(I_known)))
+        return I_known
+
+    def assemble_resident(self) -> float:
+        """Re-run the assembly kernels with inputs resident; returns device milliseconds."""
+        ms = C.c_double()
+        self._check(lib().ml_assemble_resident(self._h, C.byref(ms)))
+        return ms.value
+
+    def get_A(self, row0: int | None = None, nrows: int | None = None) -> np.ndarray:
+        row0 = self.row0 if row0 is None else row0
+        nrows = self.nrows if nrows is None else nrows
+        A = np.zeros((nrows, self.n_unknown), dtype=np.float64, order="F")
+        self._check(lib().ml_get_A(self._h, row0, nrows, _dp(A), nrows))
+        return A
+
+    @property
+    def pair_count(self) -> int:
+        return int(lib().ml_pair_count(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().ml_launch_count(self._h))
+
+    # ---- hot path 2 --------------------------------------------------------------------------------
+    def solve(self, opts: _abi.MlSolverOpts, BC: np.ndarray):
+        BC = np.ascontiguousarray(BC, dtype=np.float64)
+        x = np.zeros(self.n_unknown, dtype=np.float64)
+        info = _abi.MlSolveInfo()
+        st = lib().ml_solve(self._h, C.byref(opts), _dp(BC), _dp(x), C.byref(info))
+        self._check(st)
+        return x, info
+
+    def solve_dense(self, A: np.ndarray, b: np.ndarray, opts: _abi.MlSolverOpts):
+        A = np.asfortranarray(A, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        N = A.shape[0]
+        assert A.shape == (N, N) and b.shape == (N,)
+        x = np.zeros(N, dtype=np.float64)
+        info = _abi.MlSolveInfo()
+        self._check(lib().ml_solve_dense(self._h, N, _dp(A), _dp(b), C.byref(opts), _dp(x), C.byref(info)))
+        return x, info
+
+    def measure_peaks(self, hbm: bool = True):
+        """(FP64 DFMA TFLOP/s, copy GB/s) measured on this device."""
+        f, h = C.c_double(), C.c_double()
+        self._check(lib().ml_measure_peaks(self._h, C.byref(f), C.byref(h) if hbm else None))
+        return f.value, h.value
+
+    def close(self):
+        if self._h:
+            lib().ml_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    st = lib().ml_nccl_unique_id(buf)
+    if st != 0:
+        raise GpuError(st, "ml_nccl_unique_id")
+    return buf.raw

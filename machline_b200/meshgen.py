@@ -1,0 +1,143 @@
+"""Deterministic synthetic surface meshes for benchmarks and scale tests (no RNG, no network).
+
+The reference's benchmark inputs live in its `studies/` tree, which does not travel to the GPU box;
+these generators produce meshes of the same families and sizes:
+
+* ``icosphere(level)``       -- unit sphere, 20*4**level panels (config 1 / config 5 family)
+* ``swept_wing_half(...)``   -- ONERA-M6-like tapered swept half wing with a sharp trailing edge, root
+                                on the xz mirror plane, closed tip (config 2 family: mirrored, wake)
+* ``write_vtk(path, ...)``   -- ASCII VTK v3 POLYDATA, the format src/vtk.f90:480-553 reads
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import numpy as np
+
+
+def write_vtk(path, points: np.ndarray, triangles: np.ndarray) -> str:
+    path = Path(path)
+    path.parent.mkdir(parents=True, exist_ok=True)
+    with open(path, "w") as f:
+        f.write("# vtk DataFile Version 3.0\nmachline_b200 synthetic mesh\nASCII\nDATASET POLYDATA\n")
+        f.write(f"POINTS {len(points)} float\n")
+        np.savetxt(f, points, fmt="%.17g")
+        f.write(f"POLYGONS {len(triangles)} {4 * len(triangles)}\n")
+        np.savetxt(f, np.column_stack([np.full(len(triangles), 3), triangles]), fmt="%d")
+    return str(path)
+
+
+def icosphere(level: int, radius: float = 1.0):
+    """Icosahedron subdivided `level` times and projected on the sphere; outward-oriented triangles."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = np.array([[-1, t, 0], [1, t, 0], [-1, -t, 0], [1, -t, 0], [0, -1, t], [0, 1, t], [0, -1, -t], [0, 1, -t],
+                  [t, 0, -1], [t, 0, 1], [-t, 0, -1], [-t, 0, 1]], dtype=np.float64)
+    v /= np.linalg.norm(v, axis=1)[:, None]
+    f = np.array([[0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4], [11, 10, 2],
+                  [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8], [3, 8, 9], [4, 9, 5], [2, 4, 11],
+                  [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.int64)
+    verts = [tuple(p) for p in v]
+    for _ in range(level):
+        cache = {}
+        new_f = []
+
+        def mid(a, b):
+            key = (a, b) if a < b else (b, a)
+            if key not in cache:
+                m = (np.array(verts[a]) + np.array(verts[b])) * 0.5
+                m /= np.linalg.norm(m)
+                cache[key] = len(verts)
+                verts.append(tuple(m))
+            return cache[key]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            new_f += [[a, ab, ca], [b, bc, ab], [c, ca, bc], [ab, bc, ca]]
+        f = np.array(new_f, dtype=np.int64)
+    return np.array(verts, dtype=np.float64) * radius, f.astype(np.int32)
+
+
+def _naca4_thickness(x: np.ndarray, t: float) -> np.ndarray:
+    """NACA 00xx half-thickness with the closed-trailing-edge coefficient (-0.1036)."""
+    return 5.0 * t * (0.2969 * np.sqrt(x) - 0.1260 * x - 0.3516 * x ** 2 + 0.2843 * x ** 3 - 0.1036 * x ** 4)
+
+
+def swept_wing_half(n_chord: int = 80, n_span: int = 45, root_chord: float = 0.8059, tip_chord: float = 0.4535,
+                    semi_span: float = 1.1963, le_sweep_deg: float = 30.0, thickness: float = 0.10):
+    """Right half (y >= 0) of a swept tapered wing; root ring lies on y = 0 (mirror about xz).
+    Panels: 4*n_chord*n_span on the surface + 2*n_chord - 2 on the flat tip cap."""
+    nc, ns = n_chord, n_span
+    beta = np.linspace(0.0, np.pi, nc + 1)
+    xc = 0.5 * (1.0 - np.cos(beta))            # 0 (LE) .. 1 (TE), cosine spacing
+    zt = _naca4_thickness(xc, thickness)
+    zt[-1] = 0.0                                # sharp trailing edge
+    # ring: TE -> upper surface -> LE -> lower surface -> (back to TE, not repeated): 2*nc points
+    ring_x = np.concatenate([xc[::-1], xc[1:-1]])
+    ring_z = np.concatenate([zt[::-1], -zt[1:-1]])
+    nr = 2 * nc
+    eta = 0.5 * (1.0 - np.cos(np.linspace(0.0, np.pi, ns + 1)))  # cosine spacing root..tip
+    tan_le = np.tan(np.radians(le_sweep_deg))
+    pts = []
+    for e in eta:
+        y = e * semi_span
+        c = root_chord + (tip_chord - root_chord) * e
+        x_le = y * tan_le
+        pts.append(np.column_stack([x_le + c * ring_x, np.full(nr, y), c * ring_z]))
+    pts = np.concatenate(pts)
+    tris = []
+    for k in range(ns):
+        a0, b0 = k * nr, (k + 1) * nr
+        for i in range(nr):
+            i1 = (i + 1) % nr
+            p00, p01, p10, p11 = a0 + i, a0 + i1, b0 + i, b0 + i1
+            # ring runs TE->upper->LE->lower (clockwise seen from +y), span index grows with y:
+            # (p00, p10, p11) and (p00, p11, p01) have outward normals
+            tris.append([p00, p10, p11])
+            tris.append([p00, p11, p01])
+    # flat tip cap at y = semi_span: connect upper point j with the lower point at the same chord station
+    t0 = ns * nr
+    up = [t0 + j for j in range(0, nc + 1)]                 # TE (j=0) .. LE (j=nc) along the upper surface
+    lo = [t0] + [t0 + nr - j for j in range(1, nc)] + [t0 + nc]  # same chord stations on the lower surface
+    for j in range(nc):
+        u0, u1, l0, l1 = up[j], up[j + 1], lo[j], lo[j + 1]
+        if j == 0:
+            tris.append([u0, l1, u1])           # TE triangle (u0 == l0)
+        elif j == nc - 1:
+            tris.append([u0, l0, u1])           # LE triangle (u1 == l1)
+        else:
+            tris.append([u0, l0, l1])
+            tris.append([u0, l1, u1])
+    return pts, np.array(tris, dtype=np.int32)
+
+
+def check_outward(points: np.ndarray, triangles: np.ndarray, closed_by_mirror_axis: int | None = None) -> float:
+    """Signed volume by the divergence theorem (positive for outward-oriented closed surfaces)."""
+    a, b, c = points[triangles[:, 0]], points[triangles[:, 1]], points[triangles[:, 2]]
+    return float(np.einsum("ij,ij->i", a, np.cross(b, c)).sum() / 6.0)
+
+
+def wing_input(mesh_file: str, mach: float = 0.5, alpha_deg: float = 3.06, matrix_solver: str = "GMRES",
+               formulation: str = "dirichlet-morino") -> dict:
+    """MachLine input of the config-2 family: mirrored half wing, automatic wake, Prandtl-Glauert M."""
+    a = np.radians(alpha_deg)
+    return {
+        "flow": {"freestream_velocity": [float(np.cos(a)), 0.0, float(np.sin(a))], "freestream_mach_number": mach},
+        "geometry": {"file": mesh_file, "mirror_about": "xz", "spanwise_axis": "+y",
+                     # 90 deg (the default) would also flag the square tip-cap edges; only the sharp trailing edge sheds
+                     "wake_model": {"wake_present": True, "append_wake": True, "wake_shedding_angle": 120.0},
+                     "reference": {"area": 1.0}},
+        "solver": {"formulation": formulation, "matrix_solver": matrix_solver, "control_point_offset": 1.1e-5},
+        "post_processing": {},
+        "output": {"verbose": False},
+    }
+
+
+def sphere_input(mesh_file: str, matrix_solver: str = "GMRES") -> dict:
+    """The reference's sphere case (test/input_files/sphere_input.json) on a synthetic icosphere."""
+    return {
+        "flow": {"freestream_velocity": [0.0, 0.0, 10.0]},
+        "geometry": {"file": mesh_file, "wake_model": {"wake_present": False}},
+        "solver": {"formulation": "dirichlet-morino", "matrix_solver": matrix_solver, "control_point_offset": 1.1e-5},
+        "post_processing": {},
+        "output": {"verbose": False},
+    }

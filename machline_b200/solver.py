@@ -1,0 +1,60 @@
+"""Public entry point: run one MachLine input end to end.
+
+Mirrors ``program main`` / ``panel_solver%solve`` of the reference (src/main.f90:102-176,
+src/panel_solver.f90:1033-1101): host setup -> AIC assembly on the GPU -> dense solve on the GPU
+-> host post-processing -> report.json.  The two hot paths only exist as CUDA kernels
+(libmachline_gpu.so); without a GPU this raises.
+"""
+from __future__ import annotations
+
+import time
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _abi, gpu, host
+
+
+@dataclass
+class RunResult:
+    C_p_max: float
+    C_p_min: float
+    C_F: np.ndarray
+    C_M: np.ndarray
+    mu: np.ndarray
+    C_p: np.ndarray
+    iterations: int
+    res_max: float
+    res_norm: float
+    assemble_ms: float
+    solve_ms: float
+    n_pairs: int
+    gpu_launches: int
+    total_s: float
+
+
+def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None,
+             matrix_solver: str | None = None) -> RunResult:
+    """`inp`: dict, JSON text or path of a MachLine input file."""
+    t0 = time.perf_counter()
+    case = host.Case(inp, base_dir=base_dir)
+    ctx = gpu.Context(device)
+    try:
+        ctx.set_case(case)
+        ctx.assemble()
+        opts = case.solver_opts()
+        if matrix_solver is not None:
+            opts.matrix_solver = _abi.SOLVERS.get(matrix_solver, _abi.SOLVERS["GMRES"])
+        x, info = ctx.solve(opts, case.BC)
+        res = case.post(x)
+        total = time.perf_counter() - t0
+        if report_file is None:
+            report_file = case.input.get("output", {}).get("report_file")
+        if report_file and report_file != "none":
+            case.write_report(report_file, info, 0, total)
+        return RunResult(res.C_p_max, res.C_p_min, res.C_F, res.C_M, res.mu, res.C_p, info.iterations,
+                         info.res_max, info.res_norm, info.assemble_ms, info.solve_ms, ctx.pair_count,
+                         ctx.launch_count, total)
+    finally:
+        ctx.close()
+        case.close()

@@ -1,0 +1,168 @@
+"""Generates the committed golden fixtures from the read-only reference tree.
+
+Run in the BUILD container only (`python tests/golden/make_fixtures.py`): /root/reference does not
+exist on the GPU box, and nothing under tests/ reads it at test time.
+
+Outputs (all under tests/golden/):
+  meshes.npz                -- the raw point / triangle arrays of the reference's test meshes
+                               (test/meshes/*.vtk, *.stl), pre-duplicate-collapse, so that the host
+                               loader sees exactly the same vertex list and ordering.
+  reference_goldens.json    -- the (C_p_max, C_p_min, Cx, Cy, Cz) tuples and tolerances asserted by
+                               test/test_machline.py, with the input each test builds.
+  prototype_integrals.json  -- known-answer H(1,1,1) / hH(1,1,3) / F(1,1,1) values computed by
+                               IMPORTING the reference's Python prototype dev/unit_tests/panel.py
+                               (quadrilateral panels in local coordinates) at fixed points.
+"""
+from __future__ import annotations
+
+import json
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+
+REF = Path("/root/reference")
+OUT = Path(__file__).resolve().parent
+
+
+def read_vtk_v3(path: Path):
+    lines = path.read_text().split("\n")
+    assert "Version 3" in lines[0], lines[0]
+    toks = " ".join(lines[4:]).split()
+    assert lines[4].split()[0] == "POINTS"
+    n = int(lines[4].split()[1])
+    body = " ".join(lines[5:]).split()
+    pts = np.array(body[: 3 * n], dtype=np.float64).reshape(n, 3)
+    rest = body[3 * n:]
+    assert rest[0] == "POLYGONS"
+    m = int(rest[1])
+    vals = np.array(rest[3: 3 + 4 * m], dtype=np.int64).reshape(m, 4)
+    assert (vals[:, 0] == 3).all()
+    # keep the decimal strings: they are the ground truth the Fortran reader parses
+    pts_txt = np.array(body[: 3 * n]).reshape(n, 3)
+    return pts, vals[:, 1:4].astype(np.int32), pts_txt
+
+
+def read_stl(path: Path):
+    pts, txt = [], []
+    for line in path.read_text().split("\n"):
+        w = line.split()
+        if len(w) == 4 and w[0] == "vertex":
+            pts.append([float(w[1]), float(w[2]), float(w[3])])
+            txt.append(w[1:4])
+    return np.array(pts, dtype=np.float64), np.array(txt)
+
+
+def make_meshes():
+    out = {}
+    for name in ["sphere", "diamond_half_wing", "half_wing_right", "commercial_fuselage", "full_wing"]:
+        pts, tris, txt = read_vtk_v3(REF / "test" / "meshes" / f"{name}.vtk")
+        # round-trip check: repr() of the parsed double parses back to the same double
+        assert all(float(repr(float(v))) == float(v) for v in pts.ravel()[:100])
+        out[f"{name}.vtk:points"] = pts
+        out[f"{name}.vtk:triangles"] = tris
+    pts, txt = read_stl(REF / "test" / "meshes" / "diamond_full_wing.stl")
+    out["diamond_full_wing.stl:facet_vertices"] = pts
+    np.savez_compressed(OUT / "meshes.npz", **out)
+    print("meshes.npz:", {k: v.shape for k, v in out.items()})
+
+
+# (C_p_max, C_p_min, Cx, Cy, Cz) and tolerances, transcribed from test/test_machline.py (line numbers
+# of the asserts).  "alter" is the list of (dotted key, value) edits the test applies to the base input.
+GOLDENS = [
+    dict(name="test_01", lines="73-89", input="half_wing_input.json", alter=[],
+         expect=[0.749340997284039, -1.280587303416, -0.393828202123999, -0.0468973172312513, 20.6476349003493],
+         tol=[1e-10, 1e-9, 1e-9, 1e-9, 1e-8]),
+    dict(name="test_03", lines="124-153", input="half_wing_input.json",
+         alter=[["solver.formulation", "dirichlet-morino"]],
+         expect=[0.749339435828545, -1.28056616763669, -0.393823334747539, -0.0468966684057296, 20.6473533100845],
+         tol=[1e-10, 1e-9, 1e-9, 1e-9, 1e-8]),
+    dict(name="test_05", lines="189-218", input="half_wing_input.json",
+         alter=[["flow.freestream_velocity", [100.0, 0.0, 0.0]], ["solver.formulation", "dirichlet-morino"]],
+         expect=[0.221628441564136, -0.427625486100214, 0.301682907690379, 0.0, 3.22319026937329e-12],
+         tol=[1e-12, 1e-12, 1e-12, 1e-12, 1e-12]),
+    dict(name="test_07", lines="254-283", input="sphere_input.json",
+         alter=[["solver.matrix_solver", "BJAC"], ["solver.relaxation", 0.9]],
+         expect=[0.99114275830853, -1.23782791839695, 0.0, 0.0, 0.0], tol=[1e-12, 1e-12, 2e-5, 2e-5, 2e-5]),
+    dict(name="test_08", lines="286-297", input="sphere_input.json", alter=[],
+         expect=[0.991142758308531, -1.23782791839695, 0.0, 0.0, 0.0], tol=[1e-12, 1e-12, 1e-4, 1e-4, 1e-4]),
+    dict(name="test_12", lines="416-429", input="compressible_half_wing_input.json", alter=[],
+         expect=[0.817285785213847, -1.09376107707523, -0.508549885785561, 0.0102005794126269, 26.2795099006351],
+         tol=[1e-9, 1e-9, 1e-9, 1e-9, 1e-8]),
+    dict(name="test_13", lines="432-445", input="supersonic_half_wing_input.json", alter=[],
+         expect=[0.121697468024553, -0.116094421618336, 0.1424008894449, 0.0, 0.0],
+         tol=[1e-12, 1e-12, 1e-12, 1e-12, 1e-12]),
+    dict(name="test_14", lines="448-477", input="supersonic_half_wing_input.json",
+         alter=[["solver.formulation", "dirichlet-source-free"]],
+         expect=[0.121697468024034, -0.116094421600922, 0.142400889444425, 0.0, 0.0],
+         tol=[1e-12, 1e-12, 1e-12, 1e-12, 1e-12]),
+    dict(name="test_15", lines="480-510", input="supersonic_half_wing_input.json",
+         alter=[["flow.freestream_velocity", [100.0, 5.0, 5.0]], ["geometry.wake_model.append_wake", True]],
+         expect=[0.194725933694785, -0.298780589679282, 0.142781624853592, 0.000852303050093563, 0.892593299837566],
+         tol=[1e-12, 1e-12, 1e-12, 1e-12, 1e-9]),
+    dict(name="test_18", lines="578-609", input="supersonic_half_wing_input.json",
+         alter=[["flow.freestream_velocity", [100.0, 0.0, 5.0]], ["geometry.wake_model.append_wake", True],
+                ["solver.formulation", "dirichlet-source-free"]],
+         expect=[0.194950373758414, -0.291642542743292, 0.142905077607286, 0.0, 0.893492282700425],
+         tol=[1e-12, 1e-12, 1e-12, 1e-12, 1e-10]),
+    dict(name="test_19", lines="612-625", input="fuselage_input.json", alter=[],
+         expect=[0.955084903205978, -0.574040916470699, 0.0, 0.0, 0.0], tol=[1e-12, 1e-12, 2.1e-3, 2.1e-3, 2.1e-3]),
+    dict(name="test_20", lines="628-641", input="supersonic_full_wing_input.json", alter=[],
+         expect=[0.194950351346633, -0.324945660429385, 0.0718540012154408, 0.0, 0.429236847680447],
+         tol=[1e-12, 1e-12, 1e-12, 1e-11, 1e-12]),
+]
+
+
+def make_goldens():
+    inputs = {}
+    for g in GOLDENS:
+        if g["input"] not in inputs:
+            inputs[g["input"]] = json.loads((REF / "test" / "input_files" / g["input"]).read_text())
+    doc = dict(source="usuaero/MachLine test/test_machline.py (golden tuples C_p_max, C_p_min, Cx, Cy, Cz)",
+               inputs=inputs, cases=GOLDENS)
+    (OUT / "reference_goldens.json").write_text(json.dumps(doc, indent=1))
+    print("reference_goldens.json:", len(GOLDENS), "cases")
+
+
+def make_prototype_integrals():
+    """Import dev/unit_tests/panel.py (matplotlib stubbed) and tabulate its integrals."""
+    stub = types.ModuleType("matplotlib")
+    stub.pyplot = types.ModuleType("matplotlib.pyplot")
+    sys.modules.setdefault("matplotlib", stub)
+    sys.modules.setdefault("matplotlib.pyplot", stub.pyplot)
+    sys.path.insert(0, str(REF / "dev" / "unit_tests"))
+    import panel as proto  # type: ignore
+
+    cases = []
+    # subsonic: rectangular panel centred at the origin, z = 0
+    sub = proto.SubsonicPanel(2.0, 1.0)
+    for P in ([0.3, 0.2, 0.7], [1.7, -0.4, 0.25], [-2.5, 1.5, -1.1], [0.1, 0.05, 1e-3], [0.9, 0.49, -0.3]):
+        P = np.array(P)
+        geom = sub.calc_geom(P)
+        ints = sub.calc_F_integrals(geom)
+        sub.calc_H_integrals(geom, ints)
+        cases.append(dict(kind="subsonic", verts=sub.verts.T.tolist(), P=P.tolist(), H111=float(ints.H111),
+                          hH113=float(ints.hH113), F111=[float(v) for v in ints.F111]))
+    # supersonic subinclined (local-scaled coordinates, freestream along +x)
+    verts = np.array([[0.5, -0.5, -0.5, 0.5], [0.5, 0.5, -0.5, -0.5]])
+    sup = proto.SupersonicSubinclinedPanel(verts)
+    for P in ([5.0, 1.0, 1.0], [3.0, 0.2, 0.4], [2.0, -0.3, -0.6], [1.2, 0.1, 0.2], [4.0, 2.5, 0.5], [0.8, 0.0, 0.1]):
+        P = np.array(P)
+        geom = sup.calc_geom(P)
+        ints = sup.calc_F_integrals(geom)
+        sup.calc_H_integrals(geom, ints)
+        cases.append(dict(kind="supersonic_subinclined", verts=verts.T.tolist(), P=P.tolist(), H111=float(ints.H111),
+                          hH113=float(ints.hH113), F111=[float(v) for v in ints.F111]))
+    (OUT / "prototype_integrals.json").write_text(json.dumps(dict(
+        source="dev/unit_tests/panel.py (SubsonicPanel, SupersonicSubinclinedPanel): quadrilateral panels",
+        note="hH113 of the supersonic prototype carries the opposite sign convention (it subtracts the atan2 "
+             "terms, panel.py:703-716, where src/panel.f90:2549,2565 adds them); H111 is convention-free.",
+        cases=cases), indent=1))
+    print("prototype_integrals.json:", len(cases), "cases")
+
+
+if __name__ == "__main__":
+    make_meshes()
+    make_goldens()
+    make_prototype_integrals()
