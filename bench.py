@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the two hot paths (AIC assembly + dense solve).
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+A "step" is one pass of the hot path over one synthetic case: ml_assemble (DoD + body + wake
+influences -> A resident in HBM) followed by ml_solve (the input's matrix_solver, GMRES by default
+as in the reference).  Workload at N=1: BASELINE.json configs[1] -- a mirrored, swept, tapered
+ONERA-M6-like half wing at M = 0.5 with an automatic wake, ~20k panels -- generated
+deterministically by machline_b200.meshgen (the reference's own mesh lives in its studies/ tree,
+which does not travel).  At N GPUs the mesh is refined so that pairs/GPU stays ~constant (weak
+scaling) and the permuted system's rows are dealt to the ranks in contiguous blocks.
+
+One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+ALG_FLOPS_PER_PAIR_SUBSONIC = 187.0   # lower-order Dirichlet, subsonic evaluated pair
+METRIC = "aic_pair_influences_per_s"
+UNIT = "pair-influences/s"
+
+
+def wing_dims(n_gpus: int):
+    """(n_chord, n_span) of the config-2 family; pairs scale ~ N_panels^2, so panels ~ sqrt(n_gpus)."""
+    f = n_gpus ** 0.25
+    return int(round(96 * f)), int(round(52 * f))
+
+
+def build_case(n_gpus: int, tmpdir: str, matrix_solver: str):
+    from machline_b200 import host, meshgen
+    nc, ns = wing_dims(n_gpus)
+    pts, tris = meshgen.swept_wing_half(nc, ns)
+    name = f"wing_{nc}x{ns}.vtk"
+    meshgen.write_vtk(Path(tmpdir) / name, pts, tris)
+    inp = meshgen.wing_input(name, mach=0.5, alpha_deg=3.06, matrix_solver=matrix_solver)
+    t0 = time.perf_counter()
+    case = host.Case(inp, base_dir=tmpdir)
+    return case, dict(n_chord=nc, n_span=ns, host_setup_s=time.perf_counter() - t0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.dev = device_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.dev), "-lms", "100"], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in Path(self.path).read_text().splitlines():
+            w = [x.strip() for x in line.split(",")]
+            if len(w) < 9:
+                continue
+            try:
+                sm.append(float(w[1])); mx.append(float(w[2])); power.append(float(w[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, w[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(n_gpus: int):
+    if n_gpus <= 1 and "RANK" not in os.environ:
+        return None, 0, 1, 0
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return (dist if world > 1 else None), rank, world, local
+
+
+def cpu_baseline(case, seconds: float = 10.0):
+    """The oracle (CPU restatement of the reference, OpenMP over control points as src/panel_solver.f90:1307)
+    timed on a bounded row sample of the same workload."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_binding as ob
+    cores = os.cpu_count() or 1
+    per_row = case.n_pairs // case.n_cp
+    t0 = time.perf_counter()
+    n0 = min(case.n_cp, 4 * cores)
+    ob.assemble(case, row0=0, nrows=n0)
+    rate = n0 * per_row / (time.perf_counter() - t0)
+    rows = int(max(n0, min(case.n_cp, seconds * rate / per_row)))
+    mid = max(0, (case.n_cp - rows) // 2)
+    t0 = time.perf_counter()
+    ob.assemble(case, row0=mid, nrows=rows)
+    dt = time.perf_counter() - t0
+    return {"value": rows * per_row / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"AIC rows {mid}..{mid + rows} of {case.n_cp} ({rows * per_row:.3g} pairs, {dt:.1f} s), "
+                      "oracle/ C++ restatement with OpenMP; the reference is Fortran and cannot be built here"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU algorithm (oracle port) on this box's host cores."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_binding as ob
+    tmp = tempfile.mkdtemp(prefix="machline_bench_ref_")
+    case, dims = build_case(args.gpus, tmp, args.matrix_solver)
+    cores = os.cpu_count() or 1
+    per_row = case.n_pairs // case.n_cp
+    # bound each step to ~ (120 s / (steps+warmup)) of CPU time
+    t0 = time.perf_counter()
+    n0 = min(case.n_cp, 2 * cores)
+    ob.assemble(case, row0=0, nrows=n0)
+    rate = n0 * per_row / (time.perf_counter() - t0)
+    budget = min(8.0, 120.0 / max(1, args.steps + args.warmup))
+    rows = int(max(cores, min(case.n_cp, budget * rate / per_row)))
+    starts = np.linspace(0, case.n_cp - rows, args.steps + args.warmup).astype(int)
+    times = []
+    for i, s in enumerate(starts):
+        t0 = time.perf_counter()
+        ob.assemble(case, row0=int(s), nrows=rows)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.mean(times))
+    value = rows * per_row / dt
+    sample = (f"per step: AIC rows of a {rows}-row window of {case.n_cp} ({rows * per_row:.3g} pairs) assembled by the oracle "
+              f"port with OpenMP on {cores} threads; dense solve not included (needs the full matrix: ~{case.n_pairs / rate:.0f} s of CPU)")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(case, dims), "n_panels": case.info.n_body_panels, "n_unknown": case.n_unknown,
+                       "pairs_full_case": case.n_pairs},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_name(case, dims):
+    i = case.info
+    return (f"BASELINE configs[1] family: mirrored swept tapered half wing (ONERA-M6 planform, NACA0010-type section), "
+            f"M=0.5, alpha=3.06deg, automatic wake, dirichlet-morino lower-order; {i.n_body_panels} body panels x 2 images + "
+            f"{i.n_wake_panels} wake panels x 2, {case.n_unknown} unknowns (synthetic mesh {dims['n_chord']}x{dims['n_span']})")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--matrix-solver", default="GMRES")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    from machline_b200 import gpu
+
+    dist, rank, world, local = dist_setup(args.gpus)
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    tmp = tempfile.mkdtemp(prefix=f"machline_bench_r{rank}_")
+    case, dims = build_case(world, tmp, args.matrix_solver)
+    N = case.n_cp
+    # contiguous row blocks of the permuted system, multiples of 64 rows
+    per = ((N + world - 1) // world + 63) // 64 * 64
+    row0 = min(N, rank * per)
+    nrows = max(0, min(N, row0 + per) - row0)
+    ctx = gpu.Context(local)
+    if world > 1:
+        uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(gpu.nccl_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, src=0)
+        ctx.set_communicator(bytes(uid.cpu().numpy().tobytes()), rank, world)
+    opts = case.solver_opts()
+    BC = np.array(case.BC)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident-input steps (value): tables already on the device --------------------------------
+    ctx.set_case(case, row0=row0, nrows=nrows)
+    ctx.assemble()                      # H2D of the tables + first assembly (untimed)
+    x = None
+    for _ in range(args.warmup):
+        ctx.assemble_resident()
+        x, info = ctx.solve(opts, BC)
+    launches0 = ctx.launch_count
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    asm_ms, sol_ms = [], []
+    for _ in range(args.steps):
+        asm_ms.append(ctx.assemble_resident())
+        x, info = ctx.solve(opts, BC)
+        sol_ms.append(info.solve_ms)
+    barrier()
+    wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    launches = ctx.launch_count - launches0
+    step_ms_local = wall * 1e3 / args.steps
+    local_pairs = ctx.pair_count
+
+    # ---- end-to-end steps: host tables in, x out, every step ---------------------------------------
+    ctx.profile(reset=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ctx.set_case(case, row0=row0, nrows=nrows)   # marks the device tables dirty -> H2D again in assemble()
+        ctx.assemble()
+        x, info_e = ctx.solve(opts, BC)
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    prof = ctx.profile()
+    e2e_ms_local = e2e_wall * 1e3 / args.steps
+
+    # ---- one profiled step: CUDA-event time of the HBM-bound gemv kernel ------------------------------
+    ctx.set_profiling(True)
+    ctx.profile(reset=True)
+    ctx.assemble_resident()
+    ctx.solve(opts, BC)
+    gp = ctx.profile()
+    ctx.set_profiling(False)
+
+    # ---- reduce over ranks: max time, sum of pairs ---------------------------------------------------
+    vals = torch.tensor([step_ms_local, e2e_ms_local, float(np.mean(asm_ms)), float(np.mean(sol_ms))], dtype=torch.float64,
+                        device=f"cuda:{local}")
+    pairs_t = torch.tensor([float(local_pairs)], dtype=torch.float64, device=f"cuda:{local}")
+    if dist is not None:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+        dist.all_reduce(pairs_t, op=dist.ReduceOp.SUM)
+    step_ms, e2e_ms, a_ms, s_ms = [float(v) for v in vals.cpu()]
+    pairs = float(pairs_t.cpu()[0])
+
+    if rank == 0:
+        res = case.post(x)
+        fp64_peak, copy_peak = ctx.measure_peaks()
+        peaks_file = ROOT / "MEASURED_PEAKS.json"
+        hbm_peak, hbm_src = copy_peak, "measured live (ml_measure_peaks copy kernel); MEASURED_PEAKS.json absent"
+        if peaks_file.exists():
+            try:
+                hbm_peak = float(json.loads(peaks_file.read_text())["hbm_gbs"])
+                hbm_src = "MEASURED_PEAKS.json hbm_gbs (driver-measured copy)"
+            except Exception:
+                pass
+        traffic = {}
+        tf = ROOT / "profiles" / "roofline_traffic.json"
+        if tf.exists():
+            try:
+                traffic = json.loads(tf.read_text())
+            except Exception:
+                traffic = {}
+        gemv_avg_ms = gp.gemv_ms / max(1, gp.gemv_launches)
+        gemv_bytes = gp.gemv_bytes / max(1, gp.gemv_launches)
+        gemv_gbs = gemv_bytes / (gemv_avg_ms * 1e-3) / 1e9 if gemv_avg_ms > 0 else 0.0
+        gemv_share = gp.gemv_ms / max(1e-9, (a_ms + s_ms))
+        asm_tflops = ALG_FLOPS_PER_PAIR_SUBSONIC * local_pairs / (a_ms * 1e-3) / 1e12
+        roof_gemv = {"kernel": "gemv_n_partial_kernel (GMRES matvec w = A q)", "bound": "hbm", "achieved": gemv_gbs,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": gemv_gbs / hbm_peak if hbm_peak else None,
+                     "traffic": traffic.get("gemv_n_partial_kernel"), "peak_source": hbm_src,
+                     "algorithmic_bytes_per_launch": gemv_bytes, "avg_launch_ms": gemv_avg_ms,
+                     "launches_per_step": int(gp.gemv_launches), "share_of_step": gemv_share}
+        roof_asm = {"kernel": "aic_assemble_kernel<false>", "bound": "fp64", "achieved": asm_tflops, "peak": fp64_peak,
+                    "unit": "TFLOP/s", "frac": asm_tflops / fp64_peak if fp64_peak else None,
+                    "traffic": traffic.get("aic_assemble_kernel"),
+                    "peak_source": "measured live: register-resident DFMA loop on all SMs (ml_measure_peaks); "
+                                   "MEASURED_PEAKS.json carries no FP64 figure",
+                    "algorithmic_flops_per_pair": ALG_FLOPS_PER_PAIR_SUBSONIC, "avg_launch_ms": a_ms,
+                    "share_of_step": a_ms / max(1e-9, (a_ms + s_ms))}
+        dominant, other = (roof_gemv, roof_asm) if gemv_share >= roof_asm["share_of_step"] else (roof_asm, roof_gemv)
+        line = {
+            "metric": METRIC, "value": pairs / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(case, dims), "n_panels": case.info.n_body_panels, "n_unknown": case.n_unknown,
+                       "pairs_per_step": pairs, "matrix_solver": args.matrix_solver, "parallelism": f"row-sharded x{world}",
+                       "l2": "inputs larger than L2: A (8*N^2 bytes) is rewritten by every assembly and streamed by every matvec"},
+            "assemble": {"ms": a_ms, "pairs_per_s": pairs / (a_ms * 1e-3)},
+            "solve": {"ms": s_ms, "iterations": int(info.iterations), "res_norm": info.res_norm, "res_max": info.res_max},
+            "end_to_end_solve_ms": step_ms,
+            "result_check": {"C_p_max": res.C_p_max, "C_p_min": res.C_p_min, "Cx": float(res.C_F[0]), "Cz": float(res.C_F[2])},
+            "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": prof.h2d_bytes / args.steps, "d2h_bytes_per_step": prof.d2h_bytes / args.steps,
+                    "path": "host tables -> ml_set_* -> ml_assemble -> ml_solve -> x on host (C ABI, pageable host buffers)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": dominant,
+            "roofline_other": [other],
+            "host_setup_s": dims["host_setup_s"],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(case)
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

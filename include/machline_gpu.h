@@ -186,6 +186,19 @@ ml_status ml_assemble_resident(ml_ctx *ctx, double *device_ms);
 /* Roofline denominators measured on this device: FP64 vector pipe (register-resident DFMA loop,
    TFLOP/s) and a streaming copy (read+write GB/s).  Either pointer may be NULL. */
 ml_status ml_measure_peaks(ml_ctx *ctx, double *fp64_tflops, double *hbm_gbs);
+/* Accounting since context creation (or the last ml_reset_profile): host<->device bytes moved by the
+   entry points, and -- when profiling is on -- CUDA-event time of the HBM-bound gemv kernel of the
+   Krylov solvers (one event pair per launch, on the launching stream). */
+typedef struct ml_profile {
+    long long h2d_bytes, d2h_bytes;
+    long long gemv_launches;   /* profiled launches of gemv_n_partial_kernel                       */
+    long long gemv_bytes;      /* algorithmic bytes of those launches: 8*rows*cols each             */
+    double gemv_ms;            /* summed device time of those launches                               */
+    double assemble_ms;        /* device time of the last assembly                                   */
+} ml_profile;
+ml_status ml_set_profiling(ml_ctx *ctx, int on);
+ml_status ml_get_profile(ml_ctx *ctx, ml_profile *out);
+ml_status ml_reset_profile(ml_ctx *ctx);
 /* Rank 0 makes the 128-byte NCCL unique id that every rank passes to ml_set_communicator. */
 ml_status ml_nccl_unique_id(void *out128);
 

@@ -85,3 +85,8 @@ def solver_opts(matrix_solver="GMRES", preconditioner="DIAG", tol=1e-12, rel=0.8
     o.max_iterations, o.restart_iterations, o.block_size = max_iterations, restart_iterations, block_size
     o.iteration_file = None
     return o
+
+
+class MlProfile(C.Structure):
+    _fields_ = [("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("gemv_launches", C.c_longlong),
+                ("gemv_bytes", C.c_longlong), ("gemv_ms", C.c_double), ("assemble_ms", C.c_double)]

@@ -88,6 +88,47 @@ extern "C" const char* ml_last_error(const ml_ctx* c) { return c ? c->err.c_str(
 extern "C" long long ml_launch_count(const ml_ctx* c) { return c ? c->launches : 0; }
 extern "C" long long ml_pair_count(const ml_ctx* c) { return c ? c->pair_count : 0; }
 
+extern "C" ml_status ml_set_profiling(ml_ctx* c, int on) {
+    if (!c) return ML_BAD_ARGUMENT;
+    c->profile = on != 0;
+    return ML_OK;
+}
+
+static void drain_gemv_events(ml_ctx* c) {
+    for (size_t i = 0; i + 1 < c->gemv_ev.size(); i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->gemv_ev[i], c->gemv_ev[i + 1]) == cudaSuccess) c->gemv_ms += ms;
+        cudaEventDestroy(c->gemv_ev[i]);
+        cudaEventDestroy(c->gemv_ev[i + 1]);
+    }
+    c->gemv_ev.clear();
+}
+
+extern "C" ml_status ml_get_profile(ml_ctx* c, ml_profile* out) {
+    if (!c || !out) return ML_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    drain_gemv_events(c);
+    out->h2d_bytes = c->h2d_bytes;
+    out->d2h_bytes = c->d2h_bytes;
+    out->gemv_launches = c->gemv_launches;
+    out->gemv_bytes = c->gemv_bytes;
+    out->gemv_ms = c->gemv_ms;
+    out->assemble_ms = c->assemble_ms;
+    return ML_OK;
+}
+
+extern "C" ml_status ml_reset_profile(ml_ctx* c) {
+    if (!c) return ML_BAD_ARGUMENT;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    drain_gemv_events(c);
+    c->h2d_bytes = c->d2h_bytes = 0;
+    c->gemv_launches = c->gemv_bytes = 0;
+    c->gemv_ms = 0;
+    return ML_OK;
+}
+
 extern "C" ml_status ml_set_flow(ml_ctx* c, const ml_flow* f) {
     if (!c || !f) return ML_BAD_ARGUMENT;
     c->flow = *f;
@@ -310,6 +351,8 @@ static ml_status prepare(ml_ctx* c) {
         ML_CUDA(c, cudaMemcpyAsync(c->d_sm_colp.p, sm_colp.data(), sm_rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
         ML_CUDA(c, cudaMemcpyAsync(c->d_sm_colm.p, sm_colm.data(), sm_rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     }
+    c->h2d_bytes += (long long)(recs.size() * sizeof(double) + xyz.size() * sizeof(double) + active.size() +
+                                3 * sm_rows.size() * sizeof(int) + sizeof(FlowConst));
     ML_CUDA(c, upload_flow_constants(c->flow, c->stream));
     // A: local rows x all columns, column-major
     ML_CUDA(c, c->d_A.alloc((size_t)c->ld * c->n_cols));
@@ -366,6 +409,7 @@ extern "C" ml_status ml_assemble(ml_ctx* c, double* I_known_out) {
     c->h_I_known.assign(c->n_rows, 0.);
     ML_CUDA(c, cudaMemcpyAsync(c->h_I_known.data(), c->d_I_known.p, (size_t)c->n_rows * sizeof(double), cudaMemcpyDeviceToHost,
                                c->stream));
+    c->d2h_bytes += (long long)c->n_rows * sizeof(double);
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
     float ms = 0.f;
     ML_CUDA(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));

@@ -63,6 +63,12 @@ struct Ctx {
     std::string err;
     int num_sms = 148;
     long long launches = 0;
+    // accounting for bench.py (ml_get_profile)
+    long long h2d_bytes = 0, d2h_bytes = 0;
+    bool profile = false;
+    std::vector<cudaEvent_t> gemv_ev;   // start/stop pairs around gemv_n_partial launches (profiling only)
+    long long gemv_launches = 0, gemv_bytes = 0;
+    double gemv_ms = 0;
 
     // ---- host copies of the inputs ----
     bool have_flow = false, have_panels = false, have_cps = false, have_map = false;

@@ -4,11 +4,16 @@
 //                                          into the matvec instead of copying A into A_p)
 //   arnoldi_update / GMRES   :1208-1334
 //   restarted_GMRES          :1337-1453
-//   block_jacobi_solve       :601-728    (uses lu_kernels.cu for the diagonal blocks)
+//   block_jacobi_solve       :601-728    (lu_kernels.cu)
 // The matrix stays where the assembly kernel built it: column-major, rows sharded across ranks.
-// Per iteration the only HBM-heavy kernel is gemv_n (one pass over the local rows of A);
+// Per iteration the only HBM-heavy kernel is gemv_n_partial (one pass over the local rows of A);
 // with several ranks the slices of w are all-gathered over NCCL (8 N bytes) and the
 // orthogonalisation is replicated, so no reduction collective is needed.
+//
+// The Krylov loop is software-pipelined against the host: the Hessenberg column of iteration k is
+// copied to pinned host memory asynchronously and iteration k+1 is already enqueued while the host
+// applies the Givens rotations of iteration k (linalg.f90:1293-1319), so the device never waits for
+// the convergence test; at most one speculative iteration is discarded at the end.
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -81,7 +86,7 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_n_partial_kernel(const doub
     }
 }
 
-// y[row] = alpha * sum_ks y_part[ks][row] (+ beta_vec[row]*beta)   -- fixed order, deterministic
+// y[row] = alpha * sum_ks y_part[ks][row]   -- fixed order, deterministic
 __global__ void gemv_n_finish_kernel(const double* __restrict__ y_part, int n_rows_pad, int n_rows, int n_split,
                                      const double* __restrict__ alpha_dev, double alpha, double* __restrict__ y) {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -92,14 +97,22 @@ __global__ void gemv_n_finish_kernel(const double* __restrict__ y_part, int n_ro
     y[row] = a * s;
 }
 
-// h[j] (+)= Q[:, j] . w   for j = 0..ncol-1; one CTA per column, fixed-order block reduction
+// h[j] = Q[:, j] . w   for j = 0..ncol-1; one CTA per column, fixed-order block reduction
 __global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ Q, int ldq, int n, const double* __restrict__ w,
-                                                      double* __restrict__ h, int accumulate) {
+                                                      double* __restrict__ h) {
     __shared__ double s_part[8];
     const int j = blockIdx.x;
     const double* q = Q + (size_t)j * ldq;
-    double acc = 0.;
-    for (int i = threadIdx.x; i < n; i += 256) acc = fma(q[i], w[i], acc);
+    double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+    int i = threadIdx.x;
+    for (; i + 768 < n; i += 1024) {
+        a0 = fma(q[i], w[i], a0);
+        a1 = fma(q[i + 256], w[i + 256], a1);
+        a2 = fma(q[i + 512], w[i + 512], a2);
+        a3 = fma(q[i + 768], w[i + 768], a3);
+    }
+    for (; i < n; i += 256) a0 = fma(q[i], w[i], a0);
+    double acc = (a0 + a1) + (a2 + a3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
@@ -108,24 +121,34 @@ __global__ void __launch_bounds__(256) gemv_t_kernel(const double* __restrict__ 
         double s = 0.;
 #pragma unroll
         for (int k = 0; k < 8; ++k) s += s_part[k];
-        h[j] = accumulate ? h[j] + s : s;
+        h[j] = s;
     }
 }
 
-// w[i] -= sum_j Q[i, j] * h[j]
-__global__ void __launch_bounds__(256) gemv_n_sub_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
-                                                          const double* __restrict__ h, double* __restrict__ w) {
-    int i = blockIdx.x * 256 + threadIdx.x;
+// w[i] -= sum_j Q[i, j] * h[j]; optionally hsum[j] = h[j] + hprev[j] (second Gram-Schmidt pass)
+__global__ void __launch_bounds__(64) gemv_n_sub_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
+                                                         const double* __restrict__ h, double* __restrict__ w,
+                                                         const double* __restrict__ hprev, double* __restrict__ hsum) {
+    const int i = blockIdx.x * 64 + threadIdx.x;
+    if (hsum && blockIdx.x == 0)
+        for (int j = threadIdx.x; j < ncol; j += 64) hsum[j] = hprev[j] + h[j];
     if (i >= n) return;
-    double acc = 0.;
-    for (int j = 0; j < ncol; ++j) acc = fma(Q[i + (size_t)j * ldq], __ldg(h + j), acc);
-    w[i] -= acc;
+    double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+    int j = 0;
+    for (; j + 3 < ncol; j += 4) {
+        a0 = fma(Q[i + (size_t)j * ldq], __ldg(h + j), a0);
+        a1 = fma(Q[i + (size_t)(j + 1) * ldq], __ldg(h + j + 1), a1);
+        a2 = fma(Q[i + (size_t)(j + 2) * ldq], __ldg(h + j + 2), a2);
+        a3 = fma(Q[i + (size_t)(j + 3) * ldq], __ldg(h + j + 3), a3);
+    }
+    for (; j < ncol; ++j) a0 = fma(Q[i + (size_t)j * ldq], __ldg(h + j), a0);
+    w[i] -= (a0 + a1) + (a2 + a3);
 }
 
 // x[i] (+)= sum_j Q[i, j] * y[j]
-__global__ void __launch_bounds__(256) gemv_n_small_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
-                                                            const double* __restrict__ y, double* __restrict__ x, int accumulate) {
-    int i = blockIdx.x * 256 + threadIdx.x;
+__global__ void __launch_bounds__(64) gemv_n_small_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
+                                                           const double* __restrict__ y, double* __restrict__ x, int accumulate) {
+    int i = blockIdx.x * 64 + threadIdx.x;
     if (i >= n) return;
     double acc = 0.;
     for (int j = 0; j < ncol; ++j) acc = fma(Q[i + (size_t)j * ldq], __ldg(y + j), acc);
@@ -223,7 +246,20 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
     // y_full[N] = alpha * (alpha_dev ? *alpha_dev : 1) * A x      (x, y_full replicated full-length vectors)
     ml_status matvec(const double* x, double* y_full, double alpha, const double* alpha_dev) {
         dim3 grid(n_rows_pad / GEMV_ROWS, n_split);
-        gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p);
+        if (c->profile) {
+            cudaEvent_t e0, e1;
+            ML_CUDA(c, cudaEventCreate(&e0));
+            ML_CUDA(c, cudaEventCreate(&e1));
+            ML_CUDA(c, cudaEventRecord(e0, c->stream));
+            gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p);
+            ML_CUDA(c, cudaEventRecord(e1, c->stream));
+            c->gemv_ev.push_back(e0);
+            c->gemv_ev.push_back(e1);
+            c->gemv_launches += 1;
+            c->gemv_bytes += (long long)8 * n_rows * N;
+        } else {
+            gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p);
+        }
         double* dst = (c->world > 1) ? gather.p + (size_t)c->rank * shard_pad : y_full;
         gemv_n_finish_kernel<<<(n_rows + 255) / 256, 256, 0, c->stream>>>(y_part.p, n_rows_pad, n_rows, n_split, alpha_dev, alpha, dst);
         c->launches += 2;
@@ -251,6 +287,23 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
 
 static inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }
 
+namespace {
+struct GmresWork {  // device + pinned host buffers of one gmres_device call
+    DevBuf<double> Q, w, r0, ydev, hdev, nrm;
+    double* h_pinned = nullptr;   // 2 slots x (k_max + 2)
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    void release() {
+        Q.release(); w.release(); r0.release(); ydev.release(); hdev.release(); nrm.release();
+        if (h_pinned) cudaFreeHost(h_pinned);
+        h_pinned = nullptr;
+        for (auto& e : ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+    }
+};
+}  // namespace
+
 // GMRES / restarted GMRES (linalg.f90:1235-1453) on the scaled system (scale*A) x = scale*b.
 static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, double tol, int max_iter, int restart_iter,
                               bool restarted, bool use_mgs, double* d_x, int* total_iter_out) {
@@ -258,23 +311,65 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     const int N = S.N;
     const int k_max = restarted ? std::min(restart_iter, N) : std::min(N, max_iter);
     if (k_max < 1) return c->fail(ML_BAD_ARGUMENT, "max_iterations < 1");
-    DevBuf<double> Q, w, hdev, nrm, r0, ydev;
-    ML_CUDA(c, Q.alloc((size_t)N * (k_max + 1)));
-    ML_CUDA(c, w.alloc(N));
-    ML_CUDA(c, hdev.alloc(2 * (size_t)(k_max + 2)));
-    ML_CUDA(c, nrm.alloc(2));
-    ML_CUDA(c, r0.alloc(N));
-    ML_CUDA(c, ydev.alloc(k_max + 1));
+    const int hs = k_max + 2;  // stride of one Hessenberg-column slot
+    GmresWork W;
+    auto fail_cuda = [&](cudaError_t e, const char* where) {
+        cudaStreamSynchronize(c->stream);
+        W.release();
+        return c->cuda_fail(e, where);
+    };
+#define GM_CUDA(call)                                        \
+    do {                                                     \
+        cudaError_t e__ = (call);                            \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
+    } while (0)
+    GM_CUDA(W.Q.alloc((size_t)N * (k_max + 1)));
+    GM_CUDA(W.w.alloc(N));
+    GM_CUDA(W.r0.alloc(N));
+    GM_CUDA(W.ydev.alloc(k_max + 1));
+    GM_CUDA(W.hdev.alloc((size_t)4 * hs));  // per slot: h (final column) and h1 (first-pass scratch)
+    GM_CUDA(W.nrm.alloc(2));
+    GM_CUDA(cudaHostAlloc((void**)&W.h_pinned, (size_t)2 * hs * sizeof(double), cudaHostAllocDefault));
+    GM_CUDA(cudaEventCreateWithFlags(&W.ev[0], cudaEventDisableTiming));
+    GM_CUDA(cudaEventCreateWithFlags(&W.ev[1], cudaEventDisableTiming));
+
     const int ldh = k_max + 1;
-    std::vector<double> H((size_t)ldh * k_max, 0.), cs(k_max, 0.), sn(k_max, 0.), E(std::max(N, k_max + 1) + 1, 0.), hcol(k_max + 2);
-    ML_CUDA(c, cudaMemsetAsync(d_x, 0, (size_t)N * sizeof(double), c->stream));
+    std::vector<double> H((size_t)ldh * k_max, 0.), cs(k_max, 0.), sn(k_max, 0.), E(std::max(N, k_max + 1) + 1, 0.);
+    GM_CUDA(cudaMemsetAsync(d_x, 0, (size_t)N * sizeof(double), c->stream));
     int total_iter = 0;
     double err = tol + 1;
-    const int nb = (N + 255) / 256;
+    const int nb256 = (N + 255) / 256, nb64 = (N + 63) / 64;
     ml_status st = ML_OK;
-    auto cleanup = [&]() {
-        Q.release(); w.release(); hdev.release(); nrm.release(); r0.release(); ydev.release();
+
+    // enqueue Arnoldi step kk (0-based): Q(:,kk+1), Hessenberg column -> pinned slot, event
+    auto enqueue = [&](int kk) -> ml_status {
+        const int k = kk + 1, slot = kk & 1;
+        double* hfin = W.hdev.p + (size_t)slot * 2 * hs;  // final column h[0..k]
+        double* h1 = hfin + hs;                            // first-pass coefficients
+        ml_status s = S.matvec(W.Q.p + (size_t)kk * N, W.w.p, 1.0, d_scale);
+        if (s != ML_OK) return s;
+        if (use_mgs) {
+            mgs_kernel<<<1, 1024, 0, c->stream>>>(W.Q.p, N, N, k, W.w.p, hfin);
+            c->launches += 1;
+        } else {
+            // classical Gram-Schmidt with one re-orthogonalisation pass: same Krylov subspace and Hessenberg
+            // matrix as the reference's modified Gram-Schmidt up to rounding, but every pass is device-parallel
+            gemv_t_kernel<<<k, 256, 0, c->stream>>>(W.Q.p, N, N, W.w.p, h1);
+            gemv_n_sub_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, h1, W.w.p, nullptr, nullptr);
+            gemv_t_kernel<<<k, 256, 0, c->stream>>>(W.Q.p, N, N, W.w.p, hfin);
+            gemv_n_sub_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, hfin, W.w.p, h1, hfin);
+            c->launches += 4;
+        }
+        norm_scale_kernel<<<1, 1024, 0, c->stream>>>(W.w.p, N, hfin + k, W.Q.p + (size_t)k * N);
+        c->launches += 1;
+        cudaError_t e = cudaMemcpyAsync(W.h_pinned + (size_t)slot * hs, hfin, (size_t)(k + 1) * sizeof(double),
+                                        cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(W.ev[slot], c->stream);
+        if (e != cudaSuccess) return c->cuda_fail(e, "gmres enqueue");
+        c->d2h_bytes += (long long)(k + 1) * sizeof(double);
+        return ML_OK;
     };
+
     bool first_cycle = true;
     while (err > tol && (restarted ? total_iter <= max_iter : first_cycle)) {
         first_cycle = false;
@@ -284,53 +379,46 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         std::fill(E.begin(), E.end(), 0.);
         E[0] = 1.;
         // r0 = scale*b - (scale*A) x   (x = 0 in the first cycle: r0 = scale*b exactly as linalg.f90:1268)
+        scale_copy_kernel<<<nb256, 256, 0, c->stream>>>(d_b, 1.0, d_scale, W.r0.p, N);
+        c->launches += 1;
         if (restarted && total_iter > 0) {
-            st = S.matvec(d_x, w.p, 1.0, d_scale);
-            if (st != ML_OK) { cleanup(); return st; }
-            scale_copy_kernel<<<nb, 256, 0, c->stream>>>(d_b, 1.0, d_scale, r0.p, N);
-            axpby_kernel<<<nb, 256, 0, c->stream>>>(1.0, r0.p, -1.0, w.p, r0.p, N);
-            c->launches += 2;
-        } else {
-            scale_copy_kernel<<<nb, 256, 0, c->stream>>>(d_b, 1.0, d_scale, r0.p, N);
+            st = S.matvec(d_x, W.w.p, 1.0, d_scale);
+            if (st != ML_OK) break;
+            axpby_kernel<<<nb256, 256, 0, c->stream>>>(1.0, W.r0.p, -1.0, W.w.p, W.r0.p, N);
             c->launches += 1;
         }
-        norm_scale_kernel<<<1, 1024, 0, c->stream>>>(r0.p, N, nrm.p, Q.p);  // beta, Q(:,1) = r0/beta
+        norm_scale_kernel<<<1, 1024, 0, c->stream>>>(W.r0.p, N, W.nrm.p, W.Q.p);  // beta, Q(:,1) = r0/beta
         c->launches += 1;
         double beta = 0.;
-        ML_CUDA(c, cudaMemcpyAsync(&beta, nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-        ML_CUDA(c, cudaStreamSynchronize(c->stream));
-        if (!(beta == beta)) { cleanup(); return ML_NAN_IN_SYSTEM; }
+        GM_CUDA(cudaMemcpyAsync(&beta, W.nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        GM_CUDA(cudaStreamSynchronize(c->stream));
+        if (!(beta == beta)) {
+            st = ML_NAN_IN_SYSTEM;
+            break;
+        }
         int k = 0;
-        while (err > tol && k < k_max - 1) {
+        const int k_last = k_max - 1;  // the loop condition k < k_max-1 allows steps k = 1..k_max-1
+        bool have_next = false;
+        if (err > tol && k < k_last) {
+            st = enqueue(0);
+            if (st != ML_OK) break;
+            have_next = true;
+        }
+        while (err > tol && k < k_last && have_next) {
             k += 1;
             total_iter += 1;
-            const int kk = k - 1;
-            // arnoldi_update (linalg.f90:1208-1232)
-            st = S.matvec(Q.p + (size_t)kk * N, w.p, 1.0, d_scale);
-            if (st != ML_OK) { cleanup(); return st; }
-            if (use_mgs) {
-                mgs_kernel<<<1, 1024, 0, c->stream>>>(Q.p, N, N, k, w.p, hdev.p);
-                c->launches += 1;
-            } else {
-                // classical Gram-Schmidt with one re-orthogonalisation pass (same subspace, device-parallel)
-                gemv_t_kernel<<<k, 256, 0, c->stream>>>(Q.p, N, N, w.p, hdev.p, 0);
-                gemv_n_sub_kernel<<<nb, 256, 0, c->stream>>>(Q.p, N, N, k, hdev.p, w.p);
-                gemv_t_kernel<<<k, 256, 0, c->stream>>>(Q.p, N, N, w.p, hdev.p + (k_max + 2), 0);
-                gemv_n_sub_kernel<<<nb, 256, 0, c->stream>>>(Q.p, N, N, k, hdev.p + (k_max + 2), w.p);
-                c->launches += 4;
+            const int kk = k - 1, slot = kk & 1;
+            // speculatively enqueue the next Arnoldi step before looking at this one's numbers
+            have_next = false;
+            if (k < k_last) {
+                st = enqueue(kk + 1);
+                if (st != ML_OK) break;
+                have_next = true;
             }
-            norm_scale_kernel<<<1, 1024, 0, c->stream>>>(w.p, N, hdev.p + k, Q.p + (size_t)k * N);
-            c->launches += 1;
-            ML_CUDA(c, cudaMemcpyAsync(hcol.data(), hdev.p, (size_t)(k + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            std::vector<double> h2;
-            if (!use_mgs) {
-                h2.resize(k);
-                ML_CUDA(c, cudaMemcpyAsync(h2.data(), hdev.p + (k_max + 2), (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-            }
-            ML_CUDA(c, cudaStreamSynchronize(c->stream));
-            for (int i = 0; i < k; ++i) H[i + (size_t)kk * ldh] = hcol[i] + (use_mgs ? 0. : h2[i]);
-            H[k + (size_t)kk * ldh] = hcol[k];
-            // Givens updates (linalg.f90:1293-1313), on the host: k+1 numbers per iteration
+            GM_CUDA(cudaEventSynchronize(W.ev[slot]));
+            const double* hcol = W.h_pinned + (size_t)slot * hs;
+            for (int i = 0; i <= k; ++i) H[i + (size_t)kk * ldh] = hcol[i];
+            // Givens updates (linalg.f90:1293-1313) on the host: k+1 numbers per iteration
             for (int i = 0; i < kk; ++i) {
                 double temp = cs[i] * H[i + (size_t)kk * ldh] + sn[i] * H[(i + 1) + (size_t)kk * ldh];
                 H[(i + 1) + (size_t)kk * ldh] = -sn[i] * H[i + (size_t)kk * ldh] + cs[i] * H[(i + 1) + (size_t)kk * ldh];
@@ -347,31 +435,44 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
             err = beta * std::fabs(E[kk + 1]);
             if (!restarted && err < tol) break;
         }
+        if (st != ML_OK) break;
+        GM_CUDA(cudaStreamSynchronize(c->stream));  // drain the speculative step, if any
         if (k == 0) break;
         // back substitution (linalg.f90:930-965) and x (+)= Q(:,1:k) y
         std::vector<double> y(k);
+        bool singular = false;
         for (int i = k - 1; i >= 0; --i) {
             double v = beta * E[i];
             for (int j = i + 1; j < k; ++j) v = v - H[i + (size_t)j * ldh] * y[j];
-            if (H[i + (size_t)i * ldh] == 0.) { cleanup(); return ML_SINGULAR; }
+            if (H[i + (size_t)i * ldh] == 0.) {
+                singular = true;
+                break;
+            }
             y[i] = v / H[i + (size_t)i * ldh];
         }
-        ML_CUDA(c, cudaMemcpyAsync(ydev.p, y.data(), (size_t)k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        gemv_n_small_kernel<<<nb, 256, 0, c->stream>>>(Q.p, N, N, k, ydev.p, d_x, restarted ? 1 : 0);
+        if (singular) {
+            st = c->fail(ML_SINGULAR, "Zero found on the diagonal of R (linalg.f90:956-961)");
+            break;
+        }
+        GM_CUDA(cudaMemcpyAsync(W.ydev.p, y.data(), (size_t)k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        gemv_n_small_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, W.ydev.p, d_x, restarted ? 1 : 0);
         c->launches += 1;
-        ML_CUDA(c, cudaStreamSynchronize(c->stream));
+        GM_CUDA(cudaStreamSynchronize(c->stream));
     }
+    cudaStreamSynchronize(c->stream);
     *total_iter_out = total_iter;
-    cleanup();
-    return ML_OK;
+    W.release();
+#undef GM_CUDA
+    return st;
 }
 
 ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, double* d_x);  // lu_kernels.cu
 ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
                               int max_iter, int* iters, double* d_x);                        // lu_kernels.cu
 
-// Common tail: dispatch + residual.  d_scale points at 1/A(N,N) on the device when the "DIAG"
-// preconditioner is selected, else nullptr.
+// Common tail: dispatch.  d_scale points at 1/A(N,N) on the device when the "DIAG" preconditioner is
+// selected, else nullptr.  The direct and block solvers are scale-invariant (implicit row scaling), so
+// they ignore it.
 static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_b, const double* d_scale, double* d_x,
                             ml_solve_info* info, double* lu_matrix /* full square copy or nullptr */, int lu_ld) {
     Ctx* c = S.c;
@@ -418,6 +519,7 @@ static ml_status residual(Sys& S, const double* d_x, const double* d_b, ml_solve
     ML_CUDA(c, cudaMemcpyAsync(hAx.data(), Ax.p, (size_t)S.N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ML_CUDA(c, cudaMemcpyAsync(hb.data(), d_b, (size_t)S.N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += (long long)2 * S.N * sizeof(double);
     Ax.release();
     double mx = 0., ss = 0.;
     for (int i = 0; i < S.N; ++i) {
@@ -509,6 +611,7 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     ML_CUDA(c, d_x.alloc(N));
     ML_CUDA(c, d_scale.alloc(2));
     ML_CUDA(c, cudaMemcpyAsync(d_b.p, b.data(), (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (long long)N * sizeof(double);
     const double* scale_ptr = nullptr;
     if (opts->preconditioner == ML_PREC_DIAG) {
         // linalg.f90:1813-1816: A_ii_inv(:) = 1/A(N,N).  Row N-1 lives on the rank that owns it.
@@ -544,6 +647,7 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     if (st == ML_OK) st = residual(S, d_x.p, d_b.p, info);
     if (st == ML_OK || st == ML_NAN_RESIDUAL) {
         ML_CUDA(c, cudaMemcpyAsync(x_out, d_x.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        c->d2h_bytes += (long long)N * sizeof(double);
     }
     ML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -561,7 +665,7 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     return st;
 }
 
-// Stand-alone dense solve of a device matrix (column-major, ld); A may be overwritten if A_is_scratch.
+// Stand-alone dense solve of a device matrix (column-major, ld); the matrix itself is left intact.
 ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_b, const ml_solver_opts* opts, double* x_out,
                              ml_solve_info* info, bool A_is_scratch) {
     ML_CUDA(c, cudaEventRecord(c->ev0, c->stream));
@@ -583,6 +687,7 @@ ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_
     ML_CUDA(c, d_x.alloc(N));
     ML_CUDA(c, d_scale.alloc(2));
     ML_CUDA(c, cudaMemcpyAsync(d_b.p, h_b, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (long long)N * sizeof(double) + (long long)N * N * sizeof(double);
     const double* scale_ptr = nullptr;
     if (opts->preconditioner == ML_PREC_DIAG) {
         recip_kernel<<<1, 1, 0, c->stream>>>(dA + (N - 1) + (size_t)(N - 1) * ld, d_scale.p);
@@ -599,8 +704,10 @@ ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_
     st = run_solver(S, opts, d_b.p, scale_ptr, d_x.p, info, lu_matrix, ld);
     Acopy.release();
     if (st == ML_OK) st = residual(S, d_x.p, d_b.p, info);
-    if (st == ML_OK || st == ML_NAN_RESIDUAL)
+    if (st == ML_OK || st == ML_NAN_RESIDUAL) {
         ML_CUDA(c, cudaMemcpyAsync(x_out, d_x.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        c->d2h_bytes += (long long)N * sizeof(double);
+    }
     ML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
     float ms = 0.f;

@@ -55,6 +55,9 @@ def lib() -> C.CDLL:
         L.ml_device_system.argtypes = [vp, C.POINTER(dp), ip, ip, ip]
         L.ml_measure_peaks.argtypes = [vp, dp, dp]
         L.ml_nccl_unique_id.argtypes = [C.c_void_p]
+        L.ml_set_profiling.argtypes = [vp, C.c_int]
+        L.ml_get_profile.argtypes = [vp, C.POINTER(_abi.MlProfile)]
+        L.ml_reset_profile.argtypes = [vp]
         _lib = L
     return _lib
 
@@ -147,6 +150,16 @@ class Context:
         info = _abi.MlSolveInfo()
         self._check(lib().ml_solve_dense(self._h, N, _dp(A), _dp(b), C.byref(opts), _dp(x), C.byref(info)))
         return x, info
+
+    def set_profiling(self, on: bool):
+        self._check(lib().ml_set_profiling(self._h, int(on)))
+
+    def profile(self, reset: bool = False) -> _abi.MlProfile:
+        p = _abi.MlProfile()
+        self._check(lib().ml_get_profile(self._h, C.byref(p)))
+        if reset:
+            self._check(lib().ml_reset_profile(self._h))
+        return p
 
     def measure_peaks(self, hbm: bool = True):
         """(FP64 DFMA TFLOP/s, copy GB/s) measured on this device."""

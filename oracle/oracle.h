@@ -19,7 +19,8 @@ void orc_pair_influence(const ml_flow *fs, const ml_panel_soa *t, int j, int img
 
 int orc_assemble(const ml_flow *fs, const ml_panel_soa *body, const ml_panel_soa *wake, const ml_system_map *map,
                  int n_cp, const double *cp_loc, const int *cp_bc, const int *row_perm, int row0, int nrows,
-                 double *A_colmajor, int ld, double *I_known, int n_threads);
+                 double *A_colmajor, int ld, double *I_known, int n_threads,
+                 double *A_abs /* NULL or same layout: per entry, the sum of |panel contributions| */);
 
 /* common/linalg.f90 solvers on a host system; A is column-major N x N and is overwritten the way
    the reference overwrites A_p.  Returns ml_status. */

@@ -25,6 +25,7 @@
 //
 // Parity pinning: through the golden tuples of test/test_machline.py (tests/test_golden_cpu.py) and
 // through known-answer integrals generated from dev/unit_tests/panel.py (tests/golden/).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -369,12 +370,12 @@ extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int
 }
 
 // panel_solver.f90:1290-1501 + :1504-1706, Dirichlet / strength-matching rows.
-// A is column-major n_cp x n_unknown (A[row + col*n_cp]); rows row0..row0+nrows-1 only are filled
-// when a sub-range is requested (rows outside are left untouched).
+// Rows row0..row0+nrows-1 of the permuted system are computed; A is column-major nrows x n_unknown with
+// leading dimension ld, output row index = row - row0 (likewise I_known and A_abs).
 extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const ml_panel_soa* wake,
                             const ml_system_map* map, int n_cp, const double* cp_loc, const int* cp_bc,
                             const int* row_perm, int row0, int nrows, double* A, int ld, double* I_known,
-                            int n_threads) {
+                            int n_threads, double* A_abs) {
     const int N_unknown = map->n_unknown, N_panels = map->n_body_panels, N_verts = map->n_verts;
     const int* P = map->P;
     if (n_threads <= 0) n_threads = omp_get_max_threads();
@@ -384,6 +385,8 @@ extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const m
         int row = row_perm[i];
         if (row < row0 || row >= row0 + nrows) continue;
         std::vector<double> A_i(N_unknown, 0.);
+        // sum of |contributions| per entry: the scale rounding differences must be judged against
+        std::vector<double> S_i(A_abs ? N_unknown : 0, 0.);
         double I_known_i = 0.;
         const double* Pt = cp_loc + 3 * (size_t)i;
         if (cp_bc[i] == ML_BC_STRENGTH_MATCHING) {
@@ -411,6 +414,7 @@ extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const m
                         if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
                         else index = (iv >= N_verts) ? iv - N_verts : iv;
                         A_i[P[index]] = A_i[P[index]] + o.phi_d[k];
+                        if (A_abs) S_i[P[index]] += std::fabs(o.phi_d[k]);
                     }
                 }
             }
@@ -431,13 +435,17 @@ extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const m
                         int iv = wake->i_vert_d[(size_t)l * wake->n_cols + k];
                         double v = (k < 3) ? o.phi_d[k] : -o.phi_d[k - 3];
                         W_i[P[iv]] = W_i[P[iv]] + v;
+                        if (A_abs) S_i[P[iv]] += std::fabs(v);
                     }
                 }
             }
             for (int c = 0; c < N_unknown; ++c) A_i[c] = A_i[c] + W_i[c];
         }
-        for (int c = 0; c < N_unknown; ++c) A[(size_t)row + (size_t)c * ld] = A_i[c];
-        if (I_known) I_known[row] = I_known_i;
+        const size_t orow = (size_t)(row - row0);
+        for (int c = 0; c < N_unknown; ++c) A[orow + (size_t)c * ld] = A_i[c];
+        if (A_abs)
+            for (int c = 0; c < N_unknown; ++c) A_abs[orow + (size_t)c * ld] = std::max(S_i[c], std::fabs(A_i[c]));
+        if (I_known) I_known[orow] = I_known_i;
     }
     return status;
 }

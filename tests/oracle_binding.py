@@ -44,7 +44,7 @@ def lib() -> C.CDLL:
         L.orc_pair_influence.restype = None
         L.orc_assemble.argtypes = [C.POINTER(_abi.MlFlow), C.POINTER(_abi.MlPanelSoa), C.POINTER(_abi.MlPanelSoa),
                                    C.POINTER(_abi.MlSystemMap), C.c_int, dp, ip, ip, C.c_int, C.c_int, dp, C.c_int,
-                                   dp, C.c_int]
+                                   dp, C.c_int, dp]
         L.orc_lu_solve.argtypes = [C.c_int, dp, dp, dp]
         L.orc_gmres.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, ip, dp, dp]
         L.orc_restarted_gmres.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, C.c_int, ip, dp]
@@ -64,18 +64,23 @@ def _dp(a):
     return a.ctypes.data_as(_abi.c_double_p)
 
 
-def assemble(case, row0: int = 0, nrows: int | None = None, n_threads: int = 0):
-    """Oracle AIC for a machline_b200.host.Case.  Returns (A [n_cp x n_unknown, Fortran order], I_known)."""
+def assemble(case, row0: int = 0, nrows: int | None = None, n_threads: int = 0, with_scale: bool = False):
+    """Oracle AIC for a machline_b200.host.Case.  Returns (A [n_cp x n_unknown, Fortran order], I_known) and,
+    with_scale, also S with S_ij = sum over panels of |contribution to A_ij| (>= |A_ij|)."""
     n_cp, n_u = case.n_cp, case.n_unknown
     if nrows is None:
         nrows = n_cp - row0
-    A = np.zeros((n_cp, n_u), dtype=np.float64, order="F")
-    I_known = np.zeros(n_cp, dtype=np.float64)
+    A = np.zeros((nrows, n_u), dtype=np.float64, order="F")   # rows row0..row0+nrows of the permuted system
+    I_known = np.zeros(nrows, dtype=np.float64)
     wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
+    S = np.zeros((nrows, n_u), dtype=np.float64, order="F") if with_scale else None
     st = lib().orc_assemble(C.byref(case.flow), C.byref(case.body), wake, C.byref(case.map), n_cp, case.cps.loc,
-                            case.cps.bc, case.cps.row_perm, row0, nrows, _dp(A), n_cp, _dp(I_known), n_threads)
+                            case.cps.bc, case.cps.row_perm, row0, nrows, _dp(A), max(1, nrows), _dp(I_known), n_threads,
+                            _dp(S) if with_scale else None)
     if st != 0:
         raise RuntimeError(f"orc_assemble status {st}")
+    if with_scale:
+        return A, I_known, S
     return A, I_known
 
 
