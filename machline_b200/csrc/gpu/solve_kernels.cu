@@ -327,7 +327,7 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     GM_CUDA(W.w.alloc(N));
     GM_CUDA(W.r0.alloc(N));
     GM_CUDA(W.ydev.alloc(k_max + 1));
-    GM_CUDA(W.hdev.alloc((size_t)4 * hs));  // per slot: h (final column) and h1 (first-pass scratch)
+    GM_CUDA(W.hdev.alloc((size_t)6 * hs));  // per slot: hfin (final column), h1 and h2 (the two Gram-Schmidt passes)
     GM_CUDA(W.nrm.alloc(2));
     GM_CUDA(cudaHostAlloc((void**)&W.h_pinned, (size_t)2 * hs * sizeof(double), cudaHostAllocDefault));
     GM_CUDA(cudaEventCreateWithFlags(&W.ev[0], cudaEventDisableTiming));
@@ -344,8 +344,9 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     // enqueue Arnoldi step kk (0-based): Q(:,kk+1), Hessenberg column -> pinned slot, event
     auto enqueue = [&](int kk) -> ml_status {
         const int k = kk + 1, slot = kk & 1;
-        double* hfin = W.hdev.p + (size_t)slot * 2 * hs;  // final column h[0..k]
+        double* hfin = W.hdev.p + (size_t)slot * 3 * hs;  // final column h[0..k]
         double* h1 = hfin + hs;                            // first-pass coefficients
+        double* h2 = h1 + hs;                              // second-pass corrections (hfin = h1 + h2)
         ml_status s = S.matvec(W.Q.p + (size_t)kk * N, W.w.p, 1.0, d_scale);
         if (s != ML_OK) return s;
         if (use_mgs) {
@@ -356,8 +357,9 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
             // matrix as the reference's modified Gram-Schmidt up to rounding, but every pass is device-parallel
             gemv_t_kernel<<<k, 256, 0, c->stream>>>(W.Q.p, N, N, W.w.p, h1);
             gemv_n_sub_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, h1, W.w.p, nullptr, nullptr);
-            gemv_t_kernel<<<k, 256, 0, c->stream>>>(W.Q.p, N, N, W.w.p, hfin);
-            gemv_n_sub_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, hfin, W.w.p, h1, hfin);
+            gemv_t_kernel<<<k, 256, 0, c->stream>>>(W.Q.p, N, N, W.w.p, h2);
+            // hfin must not alias h2: block 0 writes hfin while the other blocks still read the coefficients
+            gemv_n_sub_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, h2, W.w.p, h1, hfin);
             c->launches += 4;
         }
         norm_scale_kernel<<<1, 1024, 0, c->stream>>>(W.w.p, N, hfin + k, W.Q.p + (size_t)k * N);

@@ -5,7 +5,7 @@ these generators produce meshes of the same families and sizes:
 
 * ``icosphere(level)``       -- unit sphere, 20*4**level panels (config 1 / config 5 family)
 * ``swept_wing_half(...)``   -- ONERA-M6-like tapered swept half wing with a sharp trailing edge, root
-                                on the xz mirror plane, closed tip (config 2 family: mirrored, wake)
+                                on the xz mirror plane, rounded tip (config 2 family: mirrored, wake)
 * ``write_vtk(path, ...)``   -- ASCII VTK v3 POLYDATA, the format src/vtk.f90:480-553 reads
 """
 from __future__ import annotations
@@ -63,27 +63,35 @@ def _naca4_thickness(x: np.ndarray, t: float) -> np.ndarray:
 
 
 def swept_wing_half(n_chord: int = 80, n_span: int = 45, root_chord: float = 0.8059, tip_chord: float = 0.4535,
-                    semi_span: float = 1.1963, le_sweep_deg: float = 30.0, thickness: float = 0.10):
-    """Right half (y >= 0) of a swept tapered wing; root ring lies on y = 0 (mirror about xz).
-    Panels: 4*n_chord*n_span on the surface + 2*n_chord - 2 on the flat tip cap."""
+                    semi_span: float = 1.1963, le_sweep_deg: float = 30.0, thickness: float = 0.10, n_cap: int = 4,
+                    te_cluster: float = 0.5):
+    """Right half (y >= 0) of a swept tapered wing (ONERA-M6 planform); root ring lies on y = 0 (mirror about xz).
+    The tip is closed by half a body of revolution (as on the M6): at chord station i the upper and lower surface
+    points are joined by a semicircle of radius = local half-thickness in the y-z plane, `n_cap` arcs each.
+    Panels: 4*n_chord*n_span on the surface + 2*n_cap*(n_chord-2) + 2*n_cap on the tip cap.
+    Chordwise spacing: cosine clustering at the leading edge blended (te_cluster in [0,1]) towards uniform at
+    the trailing edge, so trailing-edge panels stay thicker than the control-point offset."""
     nc, ns = n_chord, n_span
-    beta = np.linspace(0.0, np.pi, nc + 1)
-    xc = 0.5 * (1.0 - np.cos(beta))            # 0 (LE) .. 1 (TE), cosine spacing
+    u = np.linspace(0.0, 1.0, nc + 1)
+    x_cos = 0.5 * (1.0 - np.cos(np.pi * u))       # clusters at both ends
+    x_le = 1.0 - np.cos(0.5 * np.pi * u)            # clusters at the leading edge only
+    xc = te_cluster * x_cos + (1.0 - te_cluster) * x_le
+    xc[0], xc[-1] = 0.0, 1.0                        # 0 (LE) .. 1 (TE)
     zt = _naca4_thickness(xc, thickness)
-    zt[-1] = 0.0                                # sharp trailing edge
+    zt[-1] = 0.0                                    # sharp trailing edge
     # ring: TE -> upper surface -> LE -> lower surface -> (back to TE, not repeated): 2*nc points
     ring_x = np.concatenate([xc[::-1], xc[1:-1]])
     ring_z = np.concatenate([zt[::-1], -zt[1:-1]])
     nr = 2 * nc
-    eta = 0.5 * (1.0 - np.cos(np.linspace(0.0, np.pi, ns + 1)))  # cosine spacing root..tip
+    eta = np.sin(0.5 * np.pi * np.linspace(0.0, 1.0, ns + 1))   # clusters towards the tip
     tan_le = np.tan(np.radians(le_sweep_deg))
     pts = []
     for e in eta:
         y = e * semi_span
         c = root_chord + (tip_chord - root_chord) * e
-        x_le = y * tan_le
-        pts.append(np.column_stack([x_le + c * ring_x, np.full(nr, y), c * ring_z]))
-    pts = np.concatenate(pts)
+        x0 = y * tan_le
+        pts.append(np.column_stack([x0 + c * ring_x, np.full(nr, y), c * ring_z]))
+    pts = list(np.concatenate(pts))
     tris = []
     for k in range(ns):
         a0, b0 = k * nr, (k + 1) * nr
@@ -94,20 +102,34 @@ def swept_wing_half(n_chord: int = 80, n_span: int = 45, root_chord: float = 0.8
             # (p00, p10, p11) and (p00, p11, p01) have outward normals
             tris.append([p00, p10, p11])
             tris.append([p00, p11, p01])
-    # flat tip cap at y = semi_span: connect upper point j with the lower point at the same chord station
+    # rounded tip cap.  Chord station j = 0 (TE) .. nc (LE); upper point index t0 + j, lower point t0 + (nr - j) % nr.
     t0 = ns * nr
-    up = [t0 + j for j in range(0, nc + 1)]                 # TE (j=0) .. LE (j=nc) along the upper surface
-    lo = [t0] + [t0 + nr - j for j in range(1, nc)] + [t0 + nc]  # same chord stations on the lower surface
+    c_tip = tip_chord
+    x_tip0 = semi_span * tan_le
+    m = max(2, n_cap)
+    cap = {}   # (j, a) -> point index, a = 0 (upper) .. m (lower)
+    for j in range(nc + 1):
+        up, lo = t0 + j, t0 + (nr - j) % nr
+        cap[(j, 0)], cap[(j, m)] = up, lo
+        if j == 0 or j == nc:
+            for a in range(1, m):
+                cap[(j, a)] = up            # zero radius: TE and LE points
+            continue
+        xs = xc[::-1][j]                    # chord fraction of station j (TE -> LE)
+        r = c_tip * zt[::-1][j]
+        for a in range(1, m):
+            th = np.pi * a / m
+            cap[(j, a)] = len(pts)
+            pts.append(np.array([x_tip0 + c_tip * xs, semi_span + r * np.sin(th), r * np.cos(th)]))
     for j in range(nc):
-        u0, u1, l0, l1 = up[j], up[j + 1], lo[j], lo[j + 1]
-        if j == 0:
-            tris.append([u0, l1, u1])           # TE triangle (u0 == l0)
-        elif j == nc - 1:
-            tris.append([u0, l0, u1])           # LE triangle (u1 == l1)
-        else:
-            tris.append([u0, l0, l1])
-            tris.append([u0, l1, u1])
-    return pts, np.array(tris, dtype=np.int32)
+        for a in range(m):
+            q00, q01, q10, q11 = cap[(j, a)], cap[(j, a + 1)], cap[(j + 1, a)], cap[(j + 1, a + 1)]
+            # upper surface runs TE->LE with +z normals as (p00, p10, p11) above; continuing over the tip, the
+            # outward orientation is (q00, q01, q11), (q00, q11, q10)
+            for tri in ([q00, q01, q11], [q00, q11, q10]):
+                if len(set(tri)) == 3:
+                    tris.append(tri)
+    return np.array(pts), np.array(tris, dtype=np.int32)
 
 
 def check_outward(points: np.ndarray, triangles: np.ndarray, closed_by_mirror_axis: int | None = None) -> float:

@@ -13,7 +13,11 @@ typedef struct orc_pair_out {
     double hH113, H111, H213, H123, h;
     double phi_s;      /* source influence (S space, S_dim = 1)      */
     double phi_d[3];   /* doublet influences (M space, M_dim = 3)    */
+    double phi_d_abs[3]; /* sum of |terms| behind phi_d[c]: the scale of its rounding noise (tests only) */
 } orc_pair_out;
+
+/* tests only: log/atan2 through binary128, rounded once (noise-floor calibration) */
+void orc_set_exact_libm(int on);
 
 void orc_pair_influence(const ml_flow *fs, const ml_panel_soa *t, int j, int img, const double *P, orc_pair_out *out);
 

@@ -48,6 +48,13 @@ inline void cross3(const double* a, const double* b, double* c) {
 }
 inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }
 
+// Calibration switch (tests only): evaluate log / atan2 in binary128 and round once, i.e. a libm that is
+// correctly rounded.  The difference between the two modes is the noise floor that ANY two conforming
+// libms (glibc vs CUDA, or two glibc versions under the reference itself) put on an AIC entry.
+int g_exact_libm = 0;
+inline double o_log(double x) { return g_exact_libm ? (double)logq((quad)x) : std::log(x); }
+inline double o_atan2(double y, double x) { return g_exact_libm ? (double)atan2q((quad)y, (quad)x) : std::atan2(y, x); }
+
 struct Rec {  // one panel image
     const double *centr, *A, *vls, *nh, *b, *sb, *vg, *T;
     double J;
@@ -222,15 +229,16 @@ struct Integrals {
     int r, s, rs;
     double H111, hH113, H213, H123;
     double F111[3];
+    double hH113_abs = 0.;  // sum of |edge terms| of hH113 (scale of its rounding noise; not a reference quantity)
 };
 
 // panel.f90:2232-2283 (F121/F211 feed only the order-2 recursions and are not restated)
 void F_subsonic(const Geom& g, Integrals& I) {
     for (int i = 0; i < 3; ++i) {
         if (fsign(1., g.l1[i]) != fsign(1., g.l2[i])) {
-            I.F111[i] = std::log(((g.R1[i] - g.l1[i]) * (g.R2[i] + g.l2[i])) / g.g2[i]);
+            I.F111[i] = o_log(((g.R1[i] - g.l1[i]) * (g.R2[i] + g.l2[i])) / g.g2[i]);
         } else {
-            I.F111[i] = fsign(1., g.l1[i]) * std::log((g.R2[i] + std::fabs(g.l2[i])) / (g.R1[i] + std::fabs(g.l1[i])));
+            I.F111[i] = fsign(1., g.l1[i]) * o_log((g.R2[i] + std::fabs(g.l2[i])) / (g.R1[i] + std::fabs(g.l1[i])));
         }
     }
 }
@@ -257,11 +265,11 @@ void F_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integrals&
                 double series = eps * eps2 * (1. / 3. - b * eps2 / 5. + (b * eps2) * (b * eps2) / 7.);
                 I.F111[i] = -eps + b * series;
             } else if (b > 0.) {
-                I.F111[i] = -std::atan2(s_b * F1, F2) / s_b;
+                I.F111[i] = -o_atan2(s_b * F1, F2) / s_b;
             } else {
                 F1 = s_b * g.R1[i] + std::fabs(g.l1[i]);
                 F2 = s_b * g.R2[i] + std::fabs(g.l2[i]);
-                if (F1 != 0. && F2 != 0.) I.F111[i] = -fsign(1., g.v_eta[i]) * std::log(F1 / F2) / s_b;
+                if (F1 != 0. && F2 != 0.) I.F111[i] = -fsign(1., g.v_eta[i]) * o_log(F1 / F2) / s_b;
             }
         }
     }
@@ -275,8 +283,9 @@ void hH113_subsonic(const Geom& g, Integrals& I) {
         double c2 = g.g2[i] + std::fabs(g.h) * g.R2[i];
         double S = g.a[i] * (g.l2[i] * c1 - g.l1[i] * c2);
         double C = c1 * c2 + g.a[i] * g.a[i] * g.l1[i] * g.l2[i];
-        double x = std::atan2(S, C);
+        double x = o_atan2(S, C);
         I.hH113 = I.hH113 + x;
+        I.hH113_abs += std::fabs(x);
     }
     I.hH113 = fsign(I.hH113, g.h);
 }
@@ -291,6 +300,7 @@ void hH113_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integr
         if (std::fabs(g.h) > 1.e-12) {
             if (g.R1[i] == 0. && g.R2[i] == 0.) {
                 I.hH113 = I.hH113 + pi * fsign(1., g.h * g.v_xi[i]);
+                I.hH113_abs += pi;
             } else {
                 quad F1, F2;
                 if (b > 0) {
@@ -303,7 +313,9 @@ void hH113_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integr
                 }
                 quad y = (quad)(g.h * g.a[i]) * F1;
                 quad x = (quad)(g.R1[i] * g.R2[i]) + (quad)g.h2 * F2;
-                I.hH113 = (double)((quad)I.hH113 + atan2q(y, x));
+                quad t = atan2q(y, x);
+                I.hH113 = (double)((quad)I.hH113 + t);
+                I.hH113_abs += std::fabs((double)t);
             }
         }
     }
@@ -334,6 +346,8 @@ void calc_integrals(const Rec& p, const Geom& g, const ml_flow* fs, const Dod& d
 }  // namespace
 
 // panel.f90:2917-2971.  phi_d has 3 entries (the wake's negated copy, :2909-2912, is applied by the caller).
+extern "C" void orc_set_exact_libm(int on) { g_exact_libm = on; }
+
 extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int j, int img, const double* P,
                                    orc_pair_out* out) {
     std::memset(out, 0, sizeof *out);
@@ -366,6 +380,19 @@ extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int
         double acc = 0.;
         for (int k = 0; k < 3; ++k) acc = acc + m[k] * p.T[3 * k + c];
         out->phi_d[c] = I.s * fs->K_inv * acc;
+    }
+    // magnitude of the terms that were summed into phi_d[c] (forward-error scale, tests only)
+    double ma[3];
+    double s2a = 0., s3a = 0.;
+    for (int i = 0; i < 3; ++i) s2a += std::fabs(g.v_xi[i] * I.F111[i]);
+    for (int i = 0; i < 3; ++i) s3a += std::fabs(g.v_eta[i] * I.F111[i]);
+    ma[0] = I.hH113_abs;
+    ma[1] = I.hH113_abs * std::fabs(g.P_ls[0]) + std::fabs(g.h) * s2a;
+    ma[2] = I.hH113_abs * std::fabs(g.P_ls[1]) + std::fabs(g.h) * s3a;
+    for (int c = 0; c < 3; ++c) {
+        double acc = 0.;
+        for (int k = 0; k < 3; ++k) acc += ma[k] * std::fabs(p.T[3 * k + c]);
+        out->phi_d_abs[c] = fs->K_inv * acc;
     }
 }
 
@@ -414,7 +441,7 @@ extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const m
                         if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
                         else index = (iv >= N_verts) ? iv - N_verts : iv;
                         A_i[P[index]] = A_i[P[index]] + o.phi_d[k];
-                        if (A_abs) S_i[P[index]] += std::fabs(o.phi_d[k]);
+                        if (A_abs) S_i[P[index]] += o.phi_d_abs[k];
                     }
                 }
             }
@@ -435,7 +462,7 @@ extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const m
                         int iv = wake->i_vert_d[(size_t)l * wake->n_cols + k];
                         double v = (k < 3) ? o.phi_d[k] : -o.phi_d[k - 3];
                         W_i[P[iv]] = W_i[P[iv]] + v;
-                        if (A_abs) S_i[P[iv]] += std::fabs(v);
+                        if (A_abs) S_i[P[iv]] += o.phi_d_abs[k % 3];
                     }
                 }
             }

@@ -25,7 +25,8 @@ ORACLE_LIB = ORACLE_DIR / "liboracle.so"
 class OrcPairOut(C.Structure):
     _fields_ = [("in_dod", C.c_int), ("edges_in_dod", C.c_int * 3), ("F111", C.c_double * 3),
                 ("hH113", C.c_double), ("H111", C.c_double), ("H213", C.c_double), ("H123", C.c_double),
-                ("h", C.c_double), ("phi_s", C.c_double), ("phi_d", C.c_double * 3)]
+                ("h", C.c_double), ("phi_s", C.c_double), ("phi_d", C.c_double * 3),
+                ("phi_d_abs", C.c_double * 3)]
 
 
 _lib = None

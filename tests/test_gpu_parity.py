@@ -13,10 +13,13 @@ AIC_CASES = ["test_08", "test_13", "test_01", "test_15", "test_05", "test_20"]
 
 
 def _rel_err(A, A_ref, S):
-    """|dA_ij| / S_ij with S_ij = sum of |panel contributions| to the entry (>= |A_ij|).  An entry is a sum of
-    ~6-12 panel terms; where they cancel (far field of a vertex's doublet hat function) the entry is orders of
-    magnitude below its terms and 1-ulp differences in log/atan2 between CUDA libm and glibc cannot be smaller
-    than ~1e-16 of the TERMS.  For entries without cancellation S_ij = |A_ij| and this is the plain relative error."""
+    """|dA_ij| / S_ij, S_ij = sum of |terms| that were added up into the entry (oracle_aic.cpp phi_d_abs: the three
+    edge atan2 terms of hH113, the F111 edge terms, times |T_mu|, over all panels feeding the column).
+    Why not plain |dA|/|A|: an entry is a sum of O(1) atan2 values that cancel to the panel's small solid angle and of
+    6-12 panel terms that cancel in a vertex's far field, so a 1-ulp difference between two libms moves it by far more
+    than 1e-12 of ITSELF.  tests/test_oracle_noise_floor.py shows the reference algorithm does this to itself: glibc's
+    log/atan2 vs correctly rounded ones differ by up to 7e-12 (sphere) .. 1e-8 (half wing) in plain relative terms and
+    by 2e-16 relative to S.  For entries without cancellation S_ij ~ |A_ij| and this IS the plain relative error."""
     den = np.where(S > 0, S, 1.0)
     return np.abs(A - A_ref) / den
 
@@ -39,10 +42,18 @@ def test_aic_entries_match_oracle(ctx, name):
     # structural zeros must be exact zeros on both sides
     assert ((A == 0) == (A_ref == 0)).all()
     err = _rel_err(A, A_ref, S)
-    assert err.max() < 1e-12, f"max relative AIC error {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
-    # entries whose terms do not cancel (|A_ij| > S_ij / 2) carry 1e-12 relative to themselves
-    plain = np.abs(A - A_ref)[np.abs(A_ref) > 0.5 * S] / np.abs(A_ref)[np.abs(A_ref) > 0.5 * S]
+    # 1e-13 of the summed terms (10x inside the north star's 1e-12; the libm noise floor is ~2e-16)
+    assert err.max() < 1e-13, f"max AIC error relative to its terms {err.max():.3e} at {np.unravel_index(err.argmax(), err.shape)}"
+    # and 1e-13 of the row's largest entry
+    assert (np.abs(A - A_ref) / np.abs(A_ref).max(axis=1, keepdims=True)).max() < 1e-13
+    # entries whose terms do not cancel (|A_ij| > S_ij / 4) carry 1e-12 relative to themselves
+    sel = np.abs(A_ref) > 0.25 * S
+    assert sel.any()
+    plain = np.abs(A - A_ref)[sel] / np.abs(A_ref)[sel]
     assert plain.max() < 1e-12
+    # plain relative error everywhere: no worse than what two CPU libms do to the reference itself (see above)
+    nz = A_ref != 0
+    assert (np.abs(A - A_ref)[nz] / np.abs(A_ref[nz]) > 1e-12).mean() < 2e-2
     scale = max(1e-300, np.abs(I_ref).max())
     assert np.abs(I_known - I_ref).max() / scale < 1e-13
     case.close()

@@ -91,6 +91,22 @@ def test_gmres_mgs_mode_matches_oracle_iteration_history(ctx, monkeypatch):
     case.close()
 
 
+def test_gmres_many_iterations_many_blocks(ctx):
+    """Hundreds of Arnoldi steps on a system wide enough for every kernel to run many CTAs (the config-2 bench
+    case needs ~500 iterations at N ~ 10k): iteration count and solution must follow the oracle."""
+    n = 3000
+    rng = np.random.default_rng(11)
+    A = rng.standard_normal((n, n)) / np.sqrt(n) * 0.9 + np.eye(n)   # spectrum fills a disc of radius ~0.9 around 1
+    b = rng.standard_normal(n)
+    opts = _abi.solver_opts("GMRES", max_iterations=1000)
+    x, info = ctx.solve_dense(A, b, opts)
+    x_or, info_or = ob.solve_system(np.asfortranarray(A), np.zeros(n), b, opts)
+    assert info_or.iterations > 150
+    assert abs(info.iterations - info_or.iterations) <= 2, (info.iterations, info_or.iterations)
+    assert np.abs(x - x_or).max() <= 1e-9 * np.abs(x_or).max()
+    assert info.res_norm < 1e-9
+
+
 def test_invalid_solver_name_falls_back_to_gmres(ctx):
     A, b = _system(120, seed=5)
     o = _abi.solver_opts("NOT_A_SOLVER")
