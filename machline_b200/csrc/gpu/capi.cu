@@ -6,9 +6,11 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ctx.h"
+#include "record_pack.h"
 
 using namespace mlgpu;
 
@@ -73,6 +75,10 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     c->d_A.release();
     c->d_I_known.release();
     c->d_work.release();
+    c->d_W.release();
+    c->d_lists.release();
+    c->d_wcol.release();
+    c->d_zero_cols.release();
     c->d_row_active.release();
     c->d_counter.release();
     c->d_sm_rows.release();
@@ -220,29 +226,19 @@ extern "C" ml_status ml_set_communicator(ml_ctx* c, const void* id, int rank, in
 #endif
 }
 
-// Pack one record (see panel_record.h).  cols[] are the final permuted columns.
-static void pack_record(double* rec, int rec_doubles, const HostPanelTable& t, int j, int img, const int cols[6],
-                        double sigma_val, int flags) {
-    const size_t r = (size_t)j + (size_t)img * t.n_panels;
-    std::memset(rec, 0, sizeof(double) * rec_doubles);
-    for (int k = 0; k < 3; ++k) rec[R_CENTR + k] = t.centr[3 * r + k];
-    for (int k = 0; k < 9; ++k) rec[R_A + k] = t.A_g_to_ls[9 * r + k];
-    for (int k = 0; k < 6; ++k) rec[R_VLS + k] = t.vertices_ls[6 * r + k];
-    for (int k = 0; k < 6; ++k) rec[R_NH + k] = t.n_hat_ls[6 * r + k];
-    for (int k = 0; k < 9; ++k) rec[R_T + k] = t.T_mu[9 * r + k];
-    rec[R_J] = t.J[r];
-    rec[R_SIGMA] = sigma_val;
-    int* ci = reinterpret_cast<int*>(rec + R_COLS);
-    for (int k = 0; k < 6; ++k) ci[k] = cols[k];
-    int* fl = reinterpret_cast<int*>(rec + R_FLAGS);
-    fl[0] = flags;
-    fl[1] = 0;
-    if (rec_doubles >= R_SUP_DOUBLES) {
-        for (int k = 0; k < 3; ++k) rec[R_B + k] = t.b[3 * r + k];
-        for (int k = 0; k < 3; ++k) rec[R_SB + k] = t.sqrt_b[3 * r + k];
-        for (int k = 0; k < 9; ++k) rec[R_VG + k] = t.vert_g[9 * r + k];
-    }
+static PanelView view_of(const HostPanelTable& t) {
+    return PanelView{t.n_panels, t.centr.data(), t.A_g_to_ls.data(), t.vertices_ls.data(), t.n_hat_ls.data(), t.b.data(),
+                     t.sqrt_b.data(), t.J.data(), t.vert_g.data(), t.T_mu.data()};
 }
+
+namespace {
+struct HostRecord {   // one evaluated (panel, image) in stream order, with its final scatter targets
+    const HostPanelTable* table;
+    int j, img, flags, n_slots;
+    double sigma_val;
+    int cols[6];      // body: permuted columns of slots 0..2; wake: permuted columns of slots 0..5 (3..5 subtract)
+};
+}  // namespace
 
 // Builds the device tables from the staged inputs.
 static ml_status prepare(ml_ctx* c) {
@@ -253,58 +249,8 @@ static ml_status prepare(ml_ctx* c) {
     const int N_verts = m.n_verts, N_panels = m.n_body_panels;
     if (N_panels != c->body.n_panels) return c->fail(ML_BAD_ARGUMENT, "n_body_panels mismatch");
     const bool sup = c->flow.supersonic != 0;
-    const int REC = sup ? R_SUP_DOUBLES : R_SUB_DOUBLES;
+    const int STRIDE = aic_record_stride(sup);
     const std::vector<int>& P = c->P;
-
-    // ---- records in the reference's evaluation order (panel_solver.f90:1445-1476, 1656-1686) ----
-    std::vector<double> recs;
-    recs.reserve(((size_t)c->body.n_panels * c->body.n_images + (size_t)c->wake.n_panels * c->wake.n_images) * REC);
-    std::vector<double> rec(REC);
-    int n_rec = 0;
-    for (int j = 0; j < c->body.n_panels; ++j) {
-        for (int img = 0; img < c->body.n_images; ++img) {
-            if (!(c->body.area[j] > 0.)) continue;  // panel.f90:2933
-            const bool mirrored_panel = (img == 1) && m.asym_flow;  // panel_solver.f90:1470-1471
-            int cols[6] = {-1, -1, -1, -1, -1, -1};
-            for (int k = 0; k < 3; ++k) {
-                int iv = c->body.i_vert_d[(size_t)j * 3 + k], index;
-                if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
-                else index = (iv >= N_verts) ? iv - N_verts : iv;
-                if (index < 0 || index >= m.n_unknown) return c->fail(ML_BAD_ARGUMENT, "doublet index out of range");
-                cols[k] = P[index];
-            }
-            int flags = RF_EVAL | (img == 1 ? RF_MIRROR : 0);
-            double sigma_val = 0.;
-            if (c->body.has_sources[j]) {
-                int ips = c->body.i_panel_s[j], index;
-                if (mirrored_panel) index = (ips >= N_panels) ? ips - N_panels : ips + N_panels;
-                else index = (ips >= N_panels) ? ips - N_panels : ips;
-                if (index < 0 || index >= m.n_sigma) return c->fail(ML_BAD_ARGUMENT, "source index out of range");
-                sigma_val = c->sigma[index];
-                flags |= RF_SOURCE;
-            }
-            pack_record(rec.data(), REC, c->body, j, img, cols, sigma_val, flags);
-            recs.insert(recs.end(), rec.begin(), rec.end());
-            ++n_rec;
-        }
-    }
-    for (int l = 0; l < c->wake.n_panels; ++l) {
-        for (int img = 0; img < c->wake.n_images; ++img) {
-            if (img == 1 && !c->wake.image_present[l]) continue;
-            if (!(c->wake.area[l] > 0.)) continue;
-            int cols[6];
-            for (int k = 0; k < 6; ++k) {
-                int iv = c->wake.i_vert_d[(size_t)l * 6 + k];
-                if (iv < 0 || iv >= m.n_unknown) return c->fail(ML_BAD_ARGUMENT, "wake doublet index out of range");
-                cols[k] = P[iv];  // panel_solver.f90:1665-1668: no mirror shifting for wake panels
-            }
-            pack_record(rec.data(), REC, c->wake, l, img, cols, 0., RF_EVAL | (img == 1 ? RF_MIRROR : 0));
-            recs.insert(recs.end(), rec.begin(), rec.end());
-            ++n_rec;
-        }
-    }
-    c->n_rec = n_rec;
-    c->rec_doubles = REC;
 
     // ---- rows: this context's shard of the permuted system ----
     const int nrows = (c->nrows < 0) ? c->n_cp - c->row0 : c->nrows;
@@ -314,6 +260,143 @@ static ml_status prepare(ml_ctx* c) {
     if (c->n_rows_pad == 0) c->n_rows_pad = 64;
     c->ld = c->n_rows_pad;
     c->n_cols = m.n_unknown;
+    // Tile height: a CTA owns R rows for the whole record stream, so R trades per-chunk overhead against the
+    // number of tiles available to the 2 x num_sms resident CTAs (dynamic scheduling wants several per CTA).
+    {
+        const long long slots = 2LL * c->num_sms;
+        int R = 8;
+        if (c->n_rows_pad / 32 >= 8 * slots) R = 32;
+        else if (c->n_rows_pad / 16 >= 6 * slots) R = 16;
+        if (const char* e = std::getenv("MACHLINE_AIC_TILE_ROWS")) {
+            int v = std::atoi(e);
+            if (v == 8 || v == 16 || v == 32) R = v;
+        }
+        c->tile_rows = R;
+        c->chunk_records = aic_chunk_records(R);
+    }
+    const int C = c->chunk_records;
+
+    // ---- records in the reference's evaluation order (panel_solver.f90:1445-1476, 1656-1686) ----
+    std::vector<HostRecord> body_recs, wake_recs;
+    body_recs.reserve((size_t)c->body.n_panels * c->body.n_images);
+    for (int j = 0; j < c->body.n_panels; ++j) {
+        for (int img = 0; img < c->body.n_images; ++img) {
+            if (!(c->body.area[j] > 0.)) continue;  // panel.f90:2933
+            const bool mirrored_panel = (img == 1) && m.asym_flow;  // panel_solver.f90:1470-1471
+            HostRecord hr{};
+            hr.table = &c->body;
+            hr.j = j;
+            hr.img = img;
+            hr.n_slots = 3;
+            for (int k = 0; k < 3; ++k) {
+                int iv = c->body.i_vert_d[(size_t)j * 3 + k], index;
+                if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
+                else index = (iv >= N_verts) ? iv - N_verts : iv;
+                if (index < 0 || index >= m.n_unknown) return c->fail(ML_BAD_ARGUMENT, "doublet index out of range");
+                hr.cols[k] = P[index];
+            }
+            hr.flags = RF_EVAL | (img == 1 ? RF_MIRROR : 0);
+            if (c->body.has_sources[j]) {
+                int ips = c->body.i_panel_s[j], index;
+                if (mirrored_panel) index = (ips >= N_panels) ? ips - N_panels : ips + N_panels;
+                else index = (ips >= N_panels) ? ips - N_panels : ips;
+                if (index < 0 || index >= m.n_sigma) return c->fail(ML_BAD_ARGUMENT, "source index out of range");
+                hr.sigma_val = c->sigma[index];
+                hr.flags |= RF_SOURCE;
+            }
+            body_recs.push_back(hr);
+        }
+    }
+    for (int l = 0; l < c->wake.n_panels; ++l) {
+        for (int img = 0; img < c->wake.n_images; ++img) {
+            if (img == 1 && !c->wake.image_present[l]) continue;
+            if (!(c->wake.area[l] > 0.)) continue;
+            HostRecord hr{};
+            hr.table = &c->wake;
+            hr.j = l;
+            hr.img = img;
+            hr.n_slots = 6;
+            for (int k = 0; k < 6; ++k) {
+                int iv = c->wake.i_vert_d[(size_t)l * 6 + k];
+                if (iv < 0 || iv >= m.n_unknown) return c->fail(ML_BAD_ARGUMENT, "wake doublet index out of range");
+                hr.cols[k] = P[iv];  // panel_solver.f90:1665-1668: no mirror shifting for wake panels
+            }
+            hr.flags = RF_EVAL | (img == 1 ? RF_MIRROR : 0);
+            wake_recs.push_back(hr);
+        }
+    }
+    c->n_rec = (int)(body_recs.size() + wake_recs.size());
+
+    // ---- chunks: packed records + ordered scatter lists (panel_record.h) ----
+    const int n_body_chunks = (int)((body_recs.size() + C - 1) / C), n_wake_chunks = (int)((wake_recs.size() + C - 1) / C);
+    const int n_chunks = n_body_chunks + n_wake_chunks;
+    const int LB = aic_list_bytes(C), MAXI = 6 * C;
+    std::vector<double> recs((size_t)std::max(1, n_chunks) * C * STRIDE, 0.);
+    std::vector<unsigned char> lists((size_t)std::max(1, n_chunks) * LB, 0);
+    std::vector<unsigned char> col_seen(m.n_unknown, 0);
+    std::vector<int> wcol_of(m.n_unknown, -1), wcols;      // compact wake column ids
+    std::vector<unsigned char> wseen;
+    std::vector<int> slot_of_col(m.n_unknown, -1);           // scratch: column -> position in the current chunk's list
+    auto build_chunk = [&](int chunk, const std::vector<HostRecord>& src, size_t first, bool wake) {
+        const size_t n_here = std::min((size_t)C, src.size() - first);
+        int* head = reinterpret_cast<int*>(lists.data() + (size_t)chunk * LB);
+        unsigned* cols = reinterpret_cast<unsigned*>(head + 4);
+        unsigned short* beg = reinterpret_cast<unsigned short*>(head + 4 + MAXI);
+        unsigned short* item = beg + MAXI + 2;
+        std::vector<int> order;                       // columns in order of first appearance
+        std::vector<std::vector<unsigned short>> per; // items per column, in (record, slot) order
+        for (size_t r = 0; r < n_here; ++r) {
+            const HostRecord& hr = src[first + r];
+            pack_record(recs.data() + ((size_t)chunk * C + r) * STRIDE, STRIDE, sup, view_of(*hr.table), hr.j, hr.img, hr.sigma_val, hr.flags);
+            for (int k = 0; k < hr.n_slots; ++k) {
+                const int col = hr.cols[k];
+                if (slot_of_col[col] < 0) {
+                    slot_of_col[col] = (int)order.size();
+                    order.push_back(col);
+                    per.emplace_back();
+                }
+                per[slot_of_col[col]].push_back((unsigned short)((r * 3 + (k % 3)) | (k >= 3 ? 0x8000u : 0u)));
+            }
+        }
+        int n_items = 0;
+        for (size_t i = 0; i < order.size(); ++i) {
+            const int col = order[i];
+            unsigned target;
+            bool first_touch;
+            if (wake) {
+                if (wcol_of[col] < 0) {
+                    wcol_of[col] = (int)wcols.size();
+                    wcols.push_back(col);
+                    wseen.push_back(0);
+                }
+                target = (unsigned)wcol_of[col];
+                first_touch = !wseen[target];
+                wseen[target] = 1;
+            } else {
+                target = (unsigned)col;
+                first_touch = !col_seen[col];
+                col_seen[col] = 1;
+            }
+            cols[i] = target | (first_touch ? COL_FIRST : 0u);
+            beg[i] = (unsigned short)n_items;
+            for (unsigned short u : per[i]) item[n_items++] = u;
+            slot_of_col[col] = -1;
+        }
+        beg[order.size()] = (unsigned short)n_items;
+        head[0] = (int)order.size();
+        head[1] = n_items;
+        head[2] = wake ? LF_WAKE : 0;
+        head[3] = (int)n_here;
+    };
+    for (int ch = 0; ch < n_body_chunks; ++ch) build_chunk(ch, body_recs, (size_t)ch * C, false);
+    for (int ch = 0; ch < n_wake_chunks; ++ch) build_chunk(n_body_chunks + ch, wake_recs, (size_t)ch * C, true);
+    c->n_chunks = n_chunks;
+    c->n_wcols = (int)wcols.size();
+    std::vector<int> zero_cols;
+    for (int col = 0; col < m.n_unknown; ++col)
+        if (!col_seen[col]) zero_cols.push_back(col);
+    c->n_zero_cols = (int)zero_cols.size();
+
     std::vector<double> xyz((size_t)3 * c->n_rows_pad, 0.);
     std::vector<unsigned char> active(c->n_rows_pad, 0);
     std::vector<int> sm_rows, sm_colp, sm_colm;
@@ -335,7 +418,8 @@ static ml_status prepare(ml_ctx* c) {
     }
     c->n_sm_rows = (int)sm_rows.size();
 
-    ML_CUDA(c, c->d_recs.alloc(recs.size() + 2));
+    ML_CUDA(c, c->d_recs.alloc(recs.size()));
+    ML_CUDA(c, c->d_lists.alloc(lists.size()));
     ML_CUDA(c, c->d_cp_xyz.alloc(xyz.size()));
     ML_CUDA(c, c->d_row_active.alloc(active.size()));
     ML_CUDA(c, c->d_counter.alloc(4));
@@ -343,54 +427,70 @@ static ml_status prepare(ml_ctx* c) {
     ML_CUDA(c, c->d_sm_rows.alloc(sm_rows.size() + 1));
     ML_CUDA(c, c->d_sm_colp.alloc(sm_rows.size() + 1));
     ML_CUDA(c, c->d_sm_colm.alloc(sm_rows.size() + 1));
-    ML_CUDA(c, cudaMemcpyAsync(c->d_recs.p, recs.data(), recs.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    ML_CUDA(c, cudaMemcpyAsync(c->d_cp_xyz.p, xyz.data(), xyz.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    ML_CUDA(c, cudaMemcpyAsync(c->d_row_active.p, active.data(), active.size(), cudaMemcpyHostToDevice, c->stream));
-    if (!sm_rows.empty()) {
-        ML_CUDA(c, cudaMemcpyAsync(c->d_sm_rows.p, sm_rows.data(), sm_rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        ML_CUDA(c, cudaMemcpyAsync(c->d_sm_colp.p, sm_colp.data(), sm_rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        ML_CUDA(c, cudaMemcpyAsync(c->d_sm_colm.p, sm_colm.data(), sm_rows.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-    }
-    c->h2d_bytes += (long long)(recs.size() * sizeof(double) + xyz.size() * sizeof(double) + active.size() +
-                                3 * sm_rows.size() * sizeof(int) + sizeof(FlowConst));
-    ML_CUDA(c, upload_flow_constants(c->flow, c->stream));
+    ML_CUDA(c, c->d_wcol.alloc(wcols.size() + 1));
+    ML_CUDA(c, c->d_zero_cols.alloc(zero_cols.size() + 1));
+    ML_CUDA(c, c->d_W.alloc((size_t)c->ld * std::max<size_t>(1, wcols.size())));
+    auto h2d = [&](void* dst, const void* src, size_t bytes) -> cudaError_t {
+        c->h2d_bytes += (long long)bytes;
+        return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream) : cudaSuccess;
+    };
+    ML_CUDA(c, h2d(c->d_recs.p, recs.data(), recs.size() * sizeof(double)));
+    ML_CUDA(c, h2d(c->d_lists.p, lists.data(), lists.size()));
+    ML_CUDA(c, h2d(c->d_cp_xyz.p, xyz.data(), xyz.size() * sizeof(double)));
+    ML_CUDA(c, h2d(c->d_row_active.p, active.data(), active.size()));
+    ML_CUDA(c, h2d(c->d_sm_rows.p, sm_rows.data(), sm_rows.size() * sizeof(int)));
+    ML_CUDA(c, h2d(c->d_sm_colp.p, sm_colp.data(), sm_rows.size() * sizeof(int)));
+    ML_CUDA(c, h2d(c->d_sm_colm.p, sm_colm.data(), sm_rows.size() * sizeof(int)));
+    ML_CUDA(c, h2d(c->d_wcol.p, wcols.data(), wcols.size() * sizeof(int)));
+    ML_CUDA(c, h2d(c->d_zero_cols.p, zero_cols.data(), zero_cols.size() * sizeof(int)));
     // A: local rows x all columns, column-major
     ML_CUDA(c, c->d_A.alloc((size_t)c->ld * c->n_cols));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));  // host staging vectors go out of scope
     long long active_rows = 0;
     for (int r = 0; r < nrows; ++r) active_rows += active[r];
-    c->pair_count = active_rows * n_rec;
+    c->pair_count = active_rows * c->n_rec;
     c->dirty = false;
     c->assembled = false;
     return ML_OK;
 }
 
 static ml_status run_assembly_kernels(ml_ctx* c) {
-    ML_CUDA(c, cudaMemsetAsync(c->d_A.p, 0, (size_t)c->ld * c->n_cols * sizeof(double), c->stream));
-    ML_CUDA(c, cudaMemsetAsync(c->d_I_known.p, 0, (size_t)c->n_rows_pad * sizeof(double), c->stream));
+    const bool sup = c->flow.supersonic != 0;
     ML_CUDA(c, cudaMemsetAsync(c->d_counter.p, 0, 4 * sizeof(int), c->stream));
-    c->launches += 3;
+    c->launches += 1;
+    if (sup) {
+        // the supersonic kernel skips chunks that lie outside every row's domain of dependence, so the sums cannot
+        // rely on "first chunk starts from zero": zero-fill instead
+        ML_CUDA(c, cudaMemsetAsync(c->d_A.p, 0, (size_t)c->ld * c->n_cols * sizeof(double), c->stream));
+        ML_CUDA(c, cudaMemsetAsync(c->d_W.p, 0, (size_t)c->ld * std::max(1, c->n_wcols) * sizeof(double), c->stream));
+        c->launches += 2;
+    } else {
+        ML_CUDA(c, launch_zero_columns(c, c->d_A.p, c->ld, c->d_zero_cols.p, c->n_zero_cols));
+    }
     AicLaunch L{};
     L.recs = c->d_recs.p;
-    L.n_rec = c->n_rec;
-    L.rec_doubles = c->rec_doubles;
+    L.lists = c->d_lists.p;
+    L.n_chunks = c->n_chunks;
+    L.tile_rows = c->tile_rows;
     L.cp_xyz = c->d_cp_xyz.p;
     L.row_active = c->d_row_active.p;
     L.n_rows = c->n_rows;
+    L.n_rows_pad = c->n_rows_pad;
     L.A = c->d_A.p;
     L.ld = c->ld;
     L.I_known = c->d_I_known.p;
-    L.n_cp_tiles = c->n_rows_pad / 32;
-    const int TILE = aic_tile_records();
-    L.n_tiles = (c->n_rec + TILE - 1) / TILE;
-    // enough units for ~8 per resident CTA (2 CTAs/SM), never more segments than tiles
-    long long want_units = (long long)c->num_sms * 2 * 8;
-    int n_seg = (int)((want_units + L.n_cp_tiles - 1) / L.n_cp_tiles);
-    n_seg = std::max(1, std::min(n_seg, L.n_tiles));
-    L.tiles_per_seg = (L.n_tiles + n_seg - 1) / n_seg;
-    L.n_segments = (L.n_tiles + L.tiles_per_seg - 1) / L.tiles_per_seg;
+    L.W = c->d_W.p;
+    L.wcol = c->d_wcol.p;
+    L.n_wcols = c->n_wcols;
+    L.n_tiles = c->n_rows_pad / c->tile_rows;
     L.work_counter = c->d_counter.p;
-    if (L.n_tiles > 0) ML_CUDA(c, launch_aic(c, L, c->flow.supersonic != 0));
+    L.fc = make_flow_const(c->flow);
+    if (c->n_chunks > 0) {
+        ML_CUDA(c, launch_aic(c, L, sup));
+    } else {
+        ML_CUDA(c, cudaMemsetAsync(c->d_A.p, 0, (size_t)c->ld * c->n_cols * sizeof(double), c->stream));
+        ML_CUDA(c, cudaMemsetAsync(c->d_I_known.p, 0, (size_t)c->n_rows_pad * sizeof(double), c->stream));
+    }
     ML_CUDA(c, launch_strength_rows(c, c->d_A.p, c->ld, c->d_sm_rows.p, c->d_sm_colp.p, c->d_sm_colm.p, c->n_sm_rows));
     return ML_OK;
 }

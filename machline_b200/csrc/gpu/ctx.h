@@ -42,18 +42,23 @@ struct DevBuf {
     }
 };
 
-struct AicLaunch {            // arguments of the assembly kernel
-    const double* recs;       // packed records, [n_rec][rec_doubles]
-    int n_rec;
-    int rec_doubles;
+struct AicLaunch {            // arguments of the assembly kernel (aic_kernels.cu)
+    const double* recs;       // packed records, n_chunks * C records of `stride` doubles (panel_record.h)
+    const unsigned char* lists;  // per-chunk scatter lists, n_chunks blocks of list_bytes(C)
+    int n_chunks;             // body chunks, then wake chunks
+    int tile_rows;            // R: rows owned by one CTA (32, 16 or 8)
     const double* cp_xyz;     // [3][n_rows_pad] control-point coordinates by local row
     const unsigned char* row_active;  // [n_rows_pad] 1: row evaluates influences
-    int n_rows;               // local rows
+    int n_rows, n_rows_pad;   // local rows, padded to 64
     double* A;                // column-major, ld rows
     int ld;
     double* I_known;          // [n_rows]
-    int n_cp_tiles, n_tiles, tiles_per_seg, n_segments;
+    double* W;                // wake side matrix, column-major [n_wcols][ld]
+    const int* wcol;          // [n_wcols] column of A each wake column is added to
+    int n_wcols;
+    int n_tiles;              // n_rows_pad / R
     int* work_counter;
+    FlowConst fc;             // freestream constants (kernel-parameter constant bank)
 };
 
 struct Ctx {
@@ -85,10 +90,11 @@ struct Ctx {
     bool dirty = true;          // device tables need rebuilding
 
     // ---- device tables ----
-    DevBuf<double> d_recs, d_cp_xyz, d_A, d_I_known, d_work;
-    DevBuf<unsigned char> d_row_active;
-    DevBuf<int> d_counter, d_sm_rows, d_sm_colp, d_sm_colm;
-    int n_rec = 0, rec_doubles = 0, n_sm_rows = 0;
+    DevBuf<double> d_recs, d_cp_xyz, d_A, d_I_known, d_work, d_W;
+    DevBuf<unsigned char> d_row_active, d_lists;
+    DevBuf<int> d_counter, d_sm_rows, d_sm_colp, d_sm_colm, d_wcol, d_zero_cols;
+    int n_rec = 0, n_sm_rows = 0;
+    int tile_rows = 32, chunk_records = 64, n_chunks = 0, n_wcols = 0, n_zero_cols = 0;
     int n_rows = 0, n_rows_pad = 0, ld = 0, n_cols = 0;
     bool assembled = false;
     std::vector<double> h_I_known;  // local rows
@@ -119,10 +125,13 @@ struct Ctx {
     } while (0)
 
 // aic_kernels.cu
-cudaError_t upload_flow_constants(const ml_flow& f, cudaStream_t s);
+FlowConst make_flow_const(const ml_flow& f);
 cudaError_t launch_aic(Ctx* c, const AicLaunch& L, bool supersonic);
 cudaError_t launch_strength_rows(Ctx* c, double* A, int ld, const int* rows, const int* colp, const int* colm, int n);
-int aic_tile_records();
+cudaError_t launch_zero_columns(Ctx* c, double* A, int ld, const int* cols, int n_cols);
+int aic_chunk_records(int tile_rows);
+int aic_record_stride(bool supersonic);
+int aic_list_bytes(int chunk_records);
 
 // solve_kernels.cu / lu_kernels.cu
 ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info);

@@ -1,7 +1,8 @@
 // Packed per-image panel record, the unit the assembly kernel stages in shared memory with a bulk
-// (TMA) copy.  One record per (panel, image); doubles first, then an int tail, 16-byte multiple.
-// Source of every field: type(panel) members used at evaluation time (src/panel.f90:38-70) after
-// the index resolution of panel_solver_update_system_row (src/panel_solver.f90:1203-1287).
+// (TMA) copy.  One record per (panel, image); doubles first, then an int tail.
+// Source of every field: type(panel) members used at evaluation time (src/panel.f90:38-70).
+// The record stride is an ODD number of doubles (37 / 51): when the lanes of a warp read the same field of
+// 2, 4 or 8 different records (row tiles narrower than a warp) the 8-byte accesses fall in distinct banks.
 #pragma once
 
 namespace mlgpu {
@@ -15,15 +16,31 @@ enum : int {
     R_T = 24,       // [9]   T_mu (row-major, mu_dim x M_dim)
     R_J = 33,       // [1]   J
     R_SIGMA = 34,   // [1]   known source strength of the panel this record's source feeds (0 if none)
-    R_COLS = 35,    // 6 ints (3 doubles): permuted column of doublet slot k (0..2 add, 3..5 subtract), -1 unused
-    R_FLAGS = 38,   // 2 ints: [0] flags (bit0 evaluate, bit1 mirror image, bit2 has known source), [1] spare
-    R_SUB_DOUBLES = 40,  // subsonic record length (320 B)
-    R_B = 40,       // [3]   edge parameter b            (supersonic only from here on)
-    R_SB = 43,      // [3]   sqrt|b|
-    R_VG = 46,      // [9]   global vertex locations of this image (DoD tests)
-    R_SUP_DOUBLES = 56   // supersonic record length (448 B)
+    R_FLAGS = 35,   // 2 ints: [0] flags (bit0 evaluate, bit1 mirror image, bit2 has known source),
+                    //         [1] subsonic: float bits of the near-edge threshold (0.05 * longest edge)^2
+    R_AREA2 = 36,   // [1]   |(v2-v1) x (v3-v1)| in local scaled coordinates = twice the panel area there (subsonic only)
+    R_SUB_DOUBLES = 37,  // subsonic payload
+    R_SUB_STRIDE = 37,   // subsonic record stride (296 B)
+    R_B = 36,       // [3]   edge parameter b            (supersonic only from here on)
+    R_SB = 39,      // [3]   sqrt|b|
+    R_VG = 42,      // [9]   global vertex locations of this image (DoD tests)
+    R_SUP_DOUBLES = 51,  // supersonic payload
+    R_SUP_STRIDE = 51    // supersonic record stride (408 B)
 };
 
 enum : int { RF_EVAL = 1, RF_MIRROR = 2, RF_SOURCE = 4 };
+
+// ---- per-chunk scatter list (built on the host, staged next to the records) -------------------------------
+// A chunk is C consecutive records of the stream.  Its list names every column of A that the chunk's
+// records feed and, per column, the (record, slot) items in the reference's order of addition
+// (panel_solver.f90:1445-1476 / 1656-1686: record order, slot order inside a record).
+//   int  head[4]      : n_cols, n_items, flags (bit0: wake pass), spare
+//   int  col[6C]      : target column; bit 31 set = first chunk of the pass that touches it (start from 0)
+//   u16  beg[6C + 2]  : item range of column i = [beg[i], beg[i+1])
+//   u16  item[6C]     : (record_in_chunk * 3 + slot % 3) | (slot >= 3 ? 0x8000 : 0)   (0x8000 = subtract)
+constexpr int list_max_items(int C) { return 6 * C; }
+constexpr int list_bytes(int C) { return ((16 + 4 * list_max_items(C) + 2 * (list_max_items(C) + 2) + 2 * list_max_items(C)) + 15) / 16 * 16; }
+enum : int { LF_WAKE = 1 };
+constexpr unsigned COL_FIRST = 0x80000000u;
 
 }  // namespace mlgpu

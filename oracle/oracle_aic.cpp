@@ -51,9 +51,20 @@ inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a)
 // Calibration switch (tests only): evaluate log / atan2 in binary128 and round once, i.e. a libm that is
 // correctly rounded.  The difference between the two modes is the noise floor that ANY two conforming
 // libms (glibc vs CUDA, or two glibc versions under the reference itself) put on an AIC entry.
+// mode 2: the correctly rounded value moved by one ulp in a pseudo-random ~1/3 of the calls, i.e. a libm whose
+// results are "faithfully" but not correctly rounded (what CUDA's 1-2 ulp log/atan2 look like from outside).
 int g_exact_libm = 0;
-inline double o_log(double x) { return g_exact_libm ? (double)logq((quad)x) : std::log(x); }
-inline double o_atan2(double y, double x) { return g_exact_libm ? (double)atan2q((quad)y, (quad)x) : std::atan2(y, x); }
+inline double o_jitter(double v) {
+    if (g_exact_libm != 2) return v;
+    unsigned long long u;
+    std::memcpy(&u, &v, 8);
+    unsigned h = (unsigned)((u * 0x9E3779B97F4A7C15ull) >> 61);   // 0..7 from the value's own bits
+    if (h == 0 || h == 1) return std::nextafter(v, 1e300);
+    if (h == 2) return std::nextafter(v, -1e300);
+    return v;
+}
+inline double o_log(double x) { return g_exact_libm ? o_jitter((double)logq((quad)x)) : std::log(x); }
+inline double o_atan2(double y, double x) { return g_exact_libm ? o_jitter((double)atan2q((quad)y, (quad)x)) : std::atan2(y, x); }
 
 struct Rec {  // one panel image
     const double *centr, *A, *vls, *nh, *b, *sb, *vg, *T;
@@ -229,7 +240,8 @@ struct Integrals {
     int r, s, rs;
     double H111, hH113, H213, H123;
     double F111[3];
-    double hH113_abs = 0.;  // sum of |edge terms| of hH113 (scale of its rounding noise; not a reference quantity)
+    double hH113_abs = 0.;  // running-error scale of hH113: sum over edges of |term| + |cancelled products behind it|
+                            // (not a reference quantity; tests only)
 };
 
 // panel.f90:2232-2283 (F121/F211 feed only the order-2 recursions and are not restated)
@@ -285,7 +297,12 @@ void hH113_subsonic(const Geom& g, Integrals& I) {
         double C = c1 * c2 + g.a[i] * g.a[i] * g.l1[i] * g.l2[i];
         double x = o_atan2(S, C);
         I.hH113 = I.hH113 + x;
-        I.hH113_abs += std::fabs(x);
+        // scale of the term's rounding noise: |x| plus what the cancellations inside S and C feed into the angle,
+        // d(theta) = (C dS - S dC) / (S^2 + C^2) with dS, dC ~ the summed |products| of S and C
+        const double S_abs = std::fabs(g.a[i]) * (std::fabs(g.l2[i] * c1) + std::fabs(g.l1[i] * c2));
+        const double C_abs = std::fabs(c1 * c2) + std::fabs(g.a[i] * g.a[i] * g.l1[i] * g.l2[i]);
+        const double den = S * S + C * C;
+        I.hH113_abs += std::fabs(x) + (den > 0. ? (std::fabs(C) * S_abs + std::fabs(S) * C_abs) / den : 0.);
     }
     I.hH113 = fsign(I.hH113, g.h);
 }
@@ -393,6 +410,28 @@ extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int
         double acc = 0.;
         for (int k = 0; k < 3; ++k) acc += ma[k] * std::fabs(p.T[3 * k + c]);
         out->phi_d_abs[c] = fs->K_inv * acc;
+    }
+}
+
+// Batch of pair evaluations (tests only): records are (panel j, image img) with index r = j + img * n_panels.
+// phi_d[n_pts][n_rec][3], phi_d_abs likewise, phi_s[n_pts][n_rec], in_dod[n_pts][n_rec].
+extern "C" void orc_pair_batch(const ml_flow* fs, const ml_panel_soa* t, int n_pts, const double* pts, double* phi_d,
+                               double* phi_d_abs, double* phi_s, unsigned char* in_dod) {
+    const int n_rec = t->n_panels * t->n_images;
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < n_pts; ++p) {
+        for (int r = 0; r < n_rec; ++r) {
+            orc_pair_out o;
+            orc_pair_influence(fs, t, r % t->n_panels, r / t->n_panels, pts + 3 * (size_t)p, &o);
+            const size_t k = (size_t)p * n_rec + r;
+            const bool on = o.in_dod && t->area[r % t->n_panels] > 0.;
+            in_dod[k] = on;
+            phi_s[k] = on ? o.phi_s : 0.;
+            for (int c = 0; c < 3; ++c) {
+                phi_d[3 * k + c] = on ? o.phi_d[c] : 0.;
+                phi_d_abs[3 * k + c] = on ? o.phi_d_abs[c] : 0.;
+            }
+        }
     }
 }
 
