@@ -145,6 +145,135 @@ __global__ void __launch_bounds__(64) gemv_n_sub_kernel(const double* __restrict
     w[i] -= (a0 + a1) + (a2 + a3);
 }
 
+// ---- device-parallel Gram-Schmidt pass (classical, applied twice) -------------------------------------------------
+// K1: partial[rb][j] = sum over the rb-th block of ORTH_RB rows of Q[i, j] * w[i].  Grid (row blocks, column groups of
+//     32): every CTA reads its slice of w once into registers and streams 32 columns of Q (L2 resident: N x k doubles).
+// K2: h[j] = sum_rb partial[rb][j] (fixed order, every CTA recomputes it into shared memory), w -= Q h for 64 rows per
+//     CTA with the 8 warps splitting the columns, and -- optionally -- the per-CTA partial of ||w||^2.
+constexpr int ORTH_RB = 512;      // rows per K1 CTA
+constexpr int ORTH_CG = 32;       // columns per K1 CTA (4 per warp)
+
+__global__ void __launch_bounds__(256) orth_dot_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
+                                                        const double* __restrict__ w, double* __restrict__ partial, int kpad) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row0 = blockIdx.x * ORTH_RB;
+    const int col0 = blockIdx.y * ORTH_CG + warp * 4;
+    if (col0 >= ncol) return;
+    double wv[ORTH_RB / 32];
+#pragma unroll
+    for (int j = 0; j < ORTH_RB / 32; ++j) {
+        const int r = row0 + lane + 32 * j;
+        wv[j] = (r < n) ? w[r] : 0.;
+    }
+    double acc[4] = {0., 0., 0., 0.};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        if (col0 + c < ncol) {
+            const double* q = Q + (size_t)(col0 + c) * ldq + row0 + lane;
+            double a0 = 0., a1 = 0.;
+#pragma unroll
+            for (int j = 0; j < ORTH_RB / 32; j += 2) {
+                const int r = row0 + lane + 32 * j;
+                const double q0 = (r < n) ? q[32 * j] : 0.;
+                const double q1 = (r + 32 < n) ? q[32 * j + 32] : 0.;
+                a0 = fma(q0, wv[j], a0);
+                a1 = fma(q1, wv[j + 1], a1);
+            }
+            acc[c] = a0 + a1;
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    if (lane < 4 && col0 + lane < ncol) {
+        const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+        partial[(size_t)blockIdx.x * kpad + col0 + lane] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) orth_sub_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
+                                                        const double* __restrict__ partial, int kpad, int n_rb,
+                                                        double* __restrict__ w, const double* __restrict__ hprev,
+                                                        double* __restrict__ hout, double* __restrict__ norm_partial) {
+    extern __shared__ double s_h[];                 // [ncol] coefficients, then [8][64] warp partials, then 2 norm partials
+    double* s_acc = s_h + ((ncol + 1) & ~1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < ncol; j += 256) {
+        double s = 0.;
+        for (int rb = 0; rb < n_rb; ++rb) s += partial[(size_t)rb * kpad + j];
+        s_h[j] = s;
+        if (blockIdx.x == 0 && hout) hout[j] = hprev ? hprev[j] + s : s;
+    }
+    __syncthreads();
+    const int row = blockIdx.x * 64 + 2 * lane;     // ldq is a multiple of 64 and Q, w are padded: no row guard needed
+    double2 acc = make_double2(0., 0.);
+    int j = warp;
+    for (; j + 24 < ncol; j += 32) {
+        const double2 q0 = *reinterpret_cast<const double2*>(Q + (size_t)j * ldq + row);
+        const double2 q1 = *reinterpret_cast<const double2*>(Q + (size_t)(j + 8) * ldq + row);
+        const double2 q2 = *reinterpret_cast<const double2*>(Q + (size_t)(j + 16) * ldq + row);
+        const double2 q3 = *reinterpret_cast<const double2*>(Q + (size_t)(j + 24) * ldq + row);
+        const double h0 = s_h[j], h1 = s_h[j + 8], h2 = s_h[j + 16], h3 = s_h[j + 24];
+        acc.x = fma(q0.x, h0, acc.x); acc.y = fma(q0.y, h0, acc.y);
+        acc.x = fma(q1.x, h1, acc.x); acc.y = fma(q1.y, h1, acc.y);
+        acc.x = fma(q2.x, h2, acc.x); acc.y = fma(q2.y, h2, acc.y);
+        acc.x = fma(q3.x, h3, acc.x); acc.y = fma(q3.y, h3, acc.y);
+    }
+    for (; j < ncol; j += 8) {
+        const double2 q0 = *reinterpret_cast<const double2*>(Q + (size_t)j * ldq + row);
+        const double h0 = s_h[j];
+        acc.x = fma(q0.x, h0, acc.x); acc.y = fma(q0.y, h0, acc.y);
+    }
+    s_acc[warp * 64 + 2 * lane] = acc.x;
+    s_acc[warp * 64 + 2 * lane + 1] = acc.y;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        double s = 0.;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += s_acc[k * 64 + threadIdx.x];
+        const int r = blockIdx.x * 64 + threadIdx.x;
+        double v = 0.;
+        if (r < n) {
+            v = w[r] - s;
+            w[r] = v;
+        }
+        if (norm_partial) {
+            double sq = v * v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) s_acc[8 * 64 + warp] = sq;   // warps 0 and 1; a slot of its own (other warps may still read s_acc)
+        }
+    }
+    if (norm_partial) {
+        __syncthreads();
+        if (threadIdx.x == 0) norm_partial[blockIdx.x] = s_acc[8 * 64] + s_acc[8 * 64 + 1];
+    }
+}
+
+// norm = sqrt(sum of the per-CTA partials) (fixed order); q = w / norm; CTA 0 also stores the norm
+__global__ void __launch_bounds__(1024) norm_scale2_kernel(const double* __restrict__ w, int n, const double* __restrict__ norm_partial,
+                                                            int n_part, double* __restrict__ norm_out, double* __restrict__ q) {
+    __shared__ double s_part[32];
+    __shared__ double s_norm;
+    double acc = 0.;
+    for (int i = threadIdx.x; i < n_part; i += 1024) acc += norm_partial[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.;
+        for (int k = 0; k < 32; ++k) s += s_part[k];
+        s_norm = sqrt(s);
+        if (blockIdx.x == 0) *norm_out = s_norm;
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 1024 + threadIdx.x;
+    if (i < n) q[i] = w[i] / s_norm;
+}
+
 // x[i] (+)= sum_j Q[i, j] * y[j]
 __global__ void __launch_bounds__(64) gemv_n_small_kernel(const double* __restrict__ Q, int ldq, int n, int ncol,
                                                            const double* __restrict__ y, double* __restrict__ x, int accumulate) {
@@ -289,11 +418,11 @@ static inline double fsign(double a, double b) { return std::signbit(b) ? -std::
 
 namespace {
 struct GmresWork {  // device + pinned host buffers of one gmres_device call
-    DevBuf<double> Q, w, r0, ydev, hdev, nrm;
+    DevBuf<double> Q, w, r0, ydev, hdev, nrm, opart, npart;
     double* h_pinned = nullptr;   // 2 slots x (k_max + 2)
     cudaEvent_t ev[2] = {nullptr, nullptr};
     void release() {
-        Q.release(); w.release(); r0.release(); ydev.release(); hdev.release(); nrm.release();
+        Q.release(); w.release(); r0.release(); ydev.release(); hdev.release(); nrm.release(); opart.release(); npart.release();
         if (h_pinned) cudaFreeHost(h_pinned);
         h_pinned = nullptr;
         for (auto& e : ev) {
@@ -323,9 +452,22 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         cudaError_t e__ = (call);                            \
         if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
     } while (0)
-    GM_CUDA(W.Q.alloc((size_t)N * (k_max + 1)));
-    GM_CUDA(W.w.alloc(N));
-    GM_CUDA(W.r0.alloc(N));
+    const int ldq = ((N + 63) / 64) * 64;                    // padded so that 64-row CTAs can use 16-byte loads unguarded
+    const int n_rb = (N + ORTH_RB - 1) / ORTH_RB, kpad = k_max + 4, n_row64 = ldq / 64;
+    GM_CUDA(W.Q.alloc((size_t)ldq * (k_max + 1)));
+    GM_CUDA(W.w.alloc(ldq));
+    GM_CUDA(W.r0.alloc(ldq));
+    GM_CUDA(W.opart.alloc((size_t)n_rb * kpad));
+    GM_CUDA(W.npart.alloc(n_row64));
+    GM_CUDA(cudaMemsetAsync(W.Q.p, 0, (size_t)ldq * (k_max + 1) * sizeof(double), c->stream));
+    GM_CUDA(cudaMemsetAsync(W.w.p, 0, (size_t)ldq * sizeof(double), c->stream));
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            GM_CUDA(cudaFuncSetAttribute(orth_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            attr_set = true;
+        }
+    }
     GM_CUDA(W.ydev.alloc(k_max + 1));
     GM_CUDA(W.hdev.alloc((size_t)6 * hs));  // per slot: hfin (final column), h1 and h2 (the two Gram-Schmidt passes)
     GM_CUDA(W.nrm.alloc(2));
@@ -347,23 +489,24 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         double* hfin = W.hdev.p + (size_t)slot * 3 * hs;  // final column h[0..k]
         double* h1 = hfin + hs;                            // first-pass coefficients
         double* h2 = h1 + hs;                              // second-pass corrections (hfin = h1 + h2)
-        ml_status s = S.matvec(W.Q.p + (size_t)kk * N, W.w.p, 1.0, d_scale);
+        ml_status s = S.matvec(W.Q.p + (size_t)kk * ldq, W.w.p, 1.0, d_scale);
         if (s != ML_OK) return s;
         if (use_mgs) {
-            mgs_kernel<<<1, 1024, 0, c->stream>>>(W.Q.p, N, N, k, W.w.p, hfin);
-            c->launches += 1;
+            mgs_kernel<<<1, 1024, 0, c->stream>>>(W.Q.p, ldq, N, k, W.w.p, hfin);
+            norm_scale_kernel<<<1, 1024, 0, c->stream>>>(W.w.p, N, hfin + k, W.Q.p + (size_t)k * ldq);
+            c->launches += 2;
         } else {
             // classical Gram-Schmidt with one re-orthogonalisation pass: same Krylov subspace and Hessenberg
             // matrix as the reference's modified Gram-Schmidt up to rounding, but every pass is device-parallel
-            gemv_t_kernel<<<k, 256, 0, c->stream>>>(W.Q.p, N, N, W.w.p, h1);
-            gemv_n_sub_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, h1, W.w.p, nullptr, nullptr);
-            gemv_t_kernel<<<k, 256, 0, c->stream>>>(W.Q.p, N, N, W.w.p, h2);
-            // hfin must not alias h2: block 0 writes hfin while the other blocks still read the coefficients
-            gemv_n_sub_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, h2, W.w.p, h1, hfin);
-            c->launches += 4;
+            const dim3 gdot(n_rb, (k + ORTH_CG - 1) / ORTH_CG);
+            const size_t sub_smem = (size_t)(((k + 1) & ~1) + 8 * 64 + 2) * sizeof(double);
+            orth_dot_kernel<<<gdot, 256, 0, c->stream>>>(W.Q.p, ldq, N, k, W.w.p, W.opart.p, kpad);
+            orth_sub_kernel<<<n_row64, 256, sub_smem, c->stream>>>(W.Q.p, ldq, N, k, W.opart.p, kpad, n_rb, W.w.p, nullptr, h1, nullptr);
+            orth_dot_kernel<<<gdot, 256, 0, c->stream>>>(W.Q.p, ldq, N, k, W.w.p, W.opart.p, kpad);
+            orth_sub_kernel<<<n_row64, 256, sub_smem, c->stream>>>(W.Q.p, ldq, N, k, W.opart.p, kpad, n_rb, W.w.p, h1, hfin, W.npart.p);
+            norm_scale2_kernel<<<(N + 1023) / 1024, 1024, 0, c->stream>>>(W.w.p, N, W.npart.p, n_row64, hfin + k, W.Q.p + (size_t)k * ldq);
+            c->launches += 5;
         }
-        norm_scale_kernel<<<1, 1024, 0, c->stream>>>(W.w.p, N, hfin + k, W.Q.p + (size_t)k * N);
-        c->launches += 1;
         cudaError_t e = cudaMemcpyAsync(W.h_pinned + (size_t)slot * hs, hfin, (size_t)(k + 1) * sizeof(double),
                                         cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaEventRecord(W.ev[slot], c->stream);
@@ -457,7 +600,7 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
             break;
         }
         GM_CUDA(cudaMemcpyAsync(W.ydev.p, y.data(), (size_t)k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        gemv_n_small_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, N, N, k, W.ydev.p, d_x, restarted ? 1 : 0);
+        gemv_n_small_kernel<<<nb64, 64, 0, c->stream>>>(W.Q.p, ldq, N, k, W.ydev.p, d_x, restarted ? 1 : 0);
         c->launches += 1;
         GM_CUDA(cudaStreamSynchronize(c->stream));
     }
