@@ -7,9 +7,9 @@
 A "step" is one pass of the hot path over one synthetic case: ml_assemble (DoD + body + wake
 influences -> A resident in HBM) followed by ml_solve (the input's matrix_solver, GMRES by default
 as in the reference).  Workload at N=1: BASELINE.json configs[1] -- a mirrored, swept, tapered
-ONERA-M6-like half wing at M = 0.5 with an automatic wake, ~20k panels -- generated
-deterministically by machline_b200.meshgen (the reference's own mesh lives in its studies/ tree,
-which does not travel).  At N GPUs the mesh is refined so that pairs/GPU stays ~constant (weak
+ONERA-M6-planform half wing with a rounded tip at M = 0.5 with an automatic wake, ~20k panels --
+generated deterministically by machline_b200.meshgen (the reference's own mesh lives in its
+studies/ tree, which does not travel).  At N GPUs the mesh is refined so that pairs/GPU stays ~constant (weak
 scaling) and the permuted system's rows are dealt to the ranks in contiguous blocks.
 
 One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
@@ -117,62 +117,107 @@ def dist_setup(n_gpus: int):
     return (dist if world > 1 else None), rank, world, local
 
 
-def cpu_baseline(case, seconds: float = 10.0):
-    """The oracle (CPU restatement of the reference, OpenMP over control points as src/panel_solver.f90:1307)
-    timed on a bounded row sample of the same workload."""
+def _oracle():
     sys.path.insert(0, str(ROOT / "tests"))
     import oracle_binding as ob
-    cores = os.cpu_count() or 1
-    per_row = case.n_pairs // case.n_cp
-    t0 = time.perf_counter()
-    n0 = min(case.n_cp, 4 * cores)
-    ob.assemble(case, row0=0, nrows=n0)
-    rate = n0 * per_row / (time.perf_counter() - t0)
-    rows = int(max(n0, min(case.n_cp, seconds * rate / per_row)))
-    mid = max(0, (case.n_cp - rows) // 2)
-    t0 = time.perf_counter()
-    ob.assemble(case, row0=mid, nrows=rows)
-    dt = time.perf_counter() - t0
-    return {"value": rows * per_row / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"AIC rows {mid}..{mid + rows} of {case.n_cp} ({rows * per_row:.3g} pairs, {dt:.1f} s), "
-                      "oracle/ C++ restatement with OpenMP; the reference is Fortran and cannot be built here"}
+    return ob
+
+
+class ReferenceRunner:
+    """The reference's own CPU algorithm for the step (oracle port: AIC assembly with OpenMP over control points as
+    src/panel_solver.f90:1307, then panel_solver_solve_system with the input's matrix_solver), on all host threads.
+
+    A step is the WHOLE hot path when that fits the time budget; otherwise a bounded sample of it: the same fraction f
+    of both phases -- a window of f*N rows of the assembly and the first f*iterations Arnoldi steps of the solve (the
+    iteration count comes from one untimed run to convergence) -- and the pair count is scaled by f."""
+
+    def __init__(self, case, budget_s: float, n_steps: int):
+        self.ob = _oracle()
+        self.case = case
+        self.cores = os.cpu_count() or 1
+        self.per_row = case.n_pairs // case.n_cp
+        self.ob.assemble(case, row0=0, nrows=min(case.n_cp, self.cores))   # thread pool / page-in warm-up, untimed
+        t0 = time.perf_counter()
+        self.A, self.I = self.ob.assemble(case)
+        self.t_asm = time.perf_counter() - t0
+        self.opts = case.solver_opts()
+        t0 = time.perf_counter()
+        self.x, info = self.ob.solve_system(self.A, self.I, case.BC, self.opts)
+        self.t_sol = time.perf_counter() - t0
+        self.iters = int(info.iterations)
+        self.res_norm = float(info.res_norm)
+        full = self.t_asm + self.t_sol
+        self.f = 1.0 if full * n_steps <= budget_s else max(0.02, budget_s / (full * n_steps))
+        if self.iters <= 0:   # direct solver: only the assembly can be sampled
+            self.f = 1.0 if full * n_steps <= budget_s else self.f
+
+    def step(self, k: int):
+        """Returns (pairs processed, seconds)."""
+        case, ob = self.case, self.ob
+        if self.f >= 1.0:
+            t0 = time.perf_counter()
+            A, I = ob.assemble(case)
+            ob.solve_system(A, I, case.BC, self.opts)
+            return case.n_pairs, time.perf_counter() - t0
+        rows = max(self.cores, int(self.f * case.n_cp))
+        row0 = (k * 7919) % max(1, case.n_cp - rows)
+        o = case.solver_opts()
+        o.max_iterations = max(2, int(round(self.f * self.iters)) + 1)   # GMRES runs max_iterations - 1 Arnoldi steps
+        t0 = time.perf_counter()
+        ob.assemble(case, row0=row0, nrows=rows)
+        if self.iters > 0:
+            ob.solve_system(self.A, self.I, case.BC, o)
+        return rows * self.per_row, time.perf_counter() - t0
+
+    def sample_text(self):
+        if self.f >= 1.0:
+            what = "the whole step (full AIC assembly + full solve)"
+        else:
+            what = (f"a {self.f:.3f} fraction of the step: {max(self.cores, int(self.f * self.case.n_cp))} of {self.case.n_cp} rows "
+                    f"assembled + {int(round(self.f * self.iters))} of {self.iters} Arnoldi steps on the full matrix")
+        return (f"{what}; oracle/ C++ restatement of the reference (the Fortran cannot be built: no compiler), OpenMP on "
+                f"{self.cores} threads incl. the GMRES matvec (the reference's matmul is single-threaded); one full run: "
+                f"assembly {self.t_asm:.2f} s, solve {self.t_sol:.2f} s, {self.iters} iterations, residual {self.res_norm:.1e}")
+
+
+def cpu_baseline(case):
+    """bench.py's cpu_baseline leg: one reference step on the box's host cores (bounded to ~30 s of CPU work)."""
+    r = ReferenceRunner(case, budget_s=30.0, n_steps=1)
+    if r.f >= 1.0:
+        pairs, dt = case.n_pairs, r.t_asm + r.t_sol      # the constructor's own full run is the sample
+    else:
+        pairs, dt = r.step(0)
+    return {"value": pairs / dt, "unit": UNIT, "cores": r.cores, "kind": "port", "sample": r.sample_text(),
+            "assemble_only_pairs_per_s": case.n_pairs / r.t_asm}
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port) on this box's host cores."""
+    """--impl reference: the reference's CPU algorithm (oracle port) on this box's host cores, same metric and config."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    sys.path.insert(0, str(ROOT / "tests"))
-    import oracle_binding as ob
     tmp = tempfile.mkdtemp(prefix="machline_bench_ref_")
     case, dims = build_case(args.gpus, tmp, args.matrix_solver)
-    cores = os.cpu_count() or 1
-    per_row = case.n_pairs // case.n_cp
-    # bound each step to ~ (120 s / (steps+warmup)) of CPU time
-    t0 = time.perf_counter()
-    n0 = min(case.n_cp, 2 * cores)
-    ob.assemble(case, row0=0, nrows=n0)
-    rate = n0 * per_row / (time.perf_counter() - t0)
-    budget = min(8.0, 120.0 / max(1, args.steps + args.warmup))
-    rows = int(max(cores, min(case.n_cp, budget * rate / per_row)))
-    starts = np.linspace(0, case.n_cp - rows, args.steps + args.warmup).astype(int)
-    times = []
-    for i, s in enumerate(starts):
-        t0 = time.perf_counter()
-        ob.assemble(case, row0=int(s), nrows=rows)
+    n_steps = args.steps + args.warmup
+    r = ReferenceRunner(case, budget_s=200.0, n_steps=n_steps)
+    times, pairs = [], []
+    for i in range(n_steps):
+        if r.f >= 1.0 and i == 0:
+            p, dt = case.n_pairs, r.t_asm + r.t_sol       # the constructor's full run is the first warm-up step
+        else:
+            p, dt = r.step(i)
         if i >= args.warmup:
-            times.append(time.perf_counter() - t0)
+            times.append(dt)
+            pairs.append(p)
     dt = float(np.mean(times))
-    value = rows * per_row / dt
-    sample = (f"per step: AIC rows of a {rows}-row window of {case.n_cp} ({rows * per_row:.3g} pairs) assembled by the oracle "
-              f"port with OpenMP on {cores} threads; dense solve not included (needs the full matrix: ~{case.n_pairs / rate:.0f} s of CPU)")
+    value = float(np.sum(pairs) / np.sum(times))
+    cores = r.cores
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(case, dims), "n_panels": case.info.n_body_panels, "n_unknown": case.n_unknown,
-                       "pairs_full_case": case.n_pairs},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                       "pairs_per_step": float(np.mean(pairs)), "pairs_full_case": case.n_pairs, "matrix_solver": args.matrix_solver},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": r.sample_text()},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -311,9 +356,10 @@ def main():
                      "traffic": traffic.get("gemv_n_partial_kernel"), "peak_source": hbm_src,
                      "algorithmic_bytes_per_launch": gemv_bytes, "avg_launch_ms": gemv_avg_ms,
                      "launches_per_step": int(gp.gemv_launches), "share_of_step": gemv_share}
-        roof_asm = {"kernel": "aic_assemble_kernel<false>", "bound": "fp64", "achieved": asm_tflops, "peak": fp64_peak,
+        roof_asm = {"kernel": "aic_assemble_kernel<subsonic>", "bound": "fp64", "achieved": asm_tflops, "peak": fp64_peak,
                     "unit": "TFLOP/s", "frac": asm_tflops / fp64_peak if fp64_peak else None,
                     "traffic": traffic.get("aic_assemble_kernel"),
+                    "ncu": traffic.get("_aic_ncu"),
                     "peak_source": "measured live: register-resident DFMA loop on all SMs (ml_measure_peaks); "
                                    "MEASURED_PEAKS.json carries no FP64 figure",
                     "algorithmic_flops_per_pair": ALG_FLOPS_PER_PAIR_SUBSONIC, "avg_launch_ms": a_ms,

@@ -419,8 +419,9 @@ static inline double fsign(double a, double b) { return std::signbit(b) ? -std::
 namespace {
 struct GmresWork {  // device + pinned host buffers of one gmres_device call
     DevBuf<double> Q, w, r0, ydev, hdev, nrm, opart, npart;
-    double* h_pinned = nullptr;   // 2 slots x (k_max + 2)
-    cudaEvent_t ev[2] = {nullptr, nullptr};
+    static constexpr int MAX_SLOTS = 9;
+    double* h_pinned = nullptr;   // n_slots x (k_max + 2)
+    cudaEvent_t ev[MAX_SLOTS] = {};
     void release() {
         Q.release(); w.release(); r0.release(); ydev.release(); hdev.release(); nrm.release(); opart.release(); npart.release();
         if (h_pinned) cudaFreeHost(h_pinned);
@@ -469,11 +470,16 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         }
     }
     GM_CUDA(W.ydev.alloc(k_max + 1));
-    GM_CUDA(W.hdev.alloc((size_t)6 * hs));  // per slot: hfin (final column), h1 and h2 (the two Gram-Schmidt passes)
+    // Look-ahead: Arnoldi steps kept in flight beyond the one whose Hessenberg column the host is examining.  One is
+    // enough on a quiet host; a few more make the device immune to host scheduling hiccups (an iteration is ~0.2 ms)
+    // at the price of that many discarded steps at convergence.
+    int depth = 4;
+    if (const char* e = std::getenv("MACHLINE_GMRES_LOOKAHEAD")) depth = std::max(1, std::min(GmresWork::MAX_SLOTS - 1, std::atoi(e)));
+    const int n_slots = depth + 1;
+    GM_CUDA(W.hdev.alloc((size_t)3 * n_slots * hs));  // per slot: hfin (final column), h1 and h2 (the two Gram-Schmidt passes)
     GM_CUDA(W.nrm.alloc(2));
-    GM_CUDA(cudaHostAlloc((void**)&W.h_pinned, (size_t)2 * hs * sizeof(double), cudaHostAllocDefault));
-    GM_CUDA(cudaEventCreateWithFlags(&W.ev[0], cudaEventDisableTiming));
-    GM_CUDA(cudaEventCreateWithFlags(&W.ev[1], cudaEventDisableTiming));
+    GM_CUDA(cudaHostAlloc((void**)&W.h_pinned, (size_t)n_slots * hs * sizeof(double), cudaHostAllocDefault));
+    for (int i = 0; i < n_slots; ++i) GM_CUDA(cudaEventCreateWithFlags(&W.ev[i], cudaEventDisableTiming));
 
     const int ldh = k_max + 1;
     std::vector<double> H((size_t)ldh * k_max, 0.), cs(k_max, 0.), sn(k_max, 0.), E(std::max(N, k_max + 1) + 1, 0.);
@@ -485,7 +491,7 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
 
     // enqueue Arnoldi step kk (0-based): Q(:,kk+1), Hessenberg column -> pinned slot, event
     auto enqueue = [&](int kk) -> ml_status {
-        const int k = kk + 1, slot = kk & 1;
+        const int k = kk + 1, slot = kk % n_slots;
         double* hfin = W.hdev.p + (size_t)slot * 3 * hs;  // final column h[0..k]
         double* h1 = hfin + hs;                            // first-pass coefficients
         double* h2 = h1 + hs;                              // second-pass corrections (hfin = h1 + h2)
@@ -543,23 +549,24 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         }
         int k = 0;
         const int k_last = k_max - 1;  // the loop condition k < k_max-1 allows steps k = 1..k_max-1
-        bool have_next = false;
-        if (err > tol && k < k_last) {
-            st = enqueue(0);
-            if (st != ML_OK) break;
-            have_next = true;
-        }
-        while (err > tol && k < k_last && have_next) {
+        int next_enq = 0;   // Arnoldi steps enqueued so far in this cycle
+        auto fill = [&](int upto) -> ml_status {   // speculatively enqueue steps up to index `upto`
+            while (next_enq <= upto && next_enq < k_last) {
+                ml_status s = enqueue(next_enq);
+                if (s != ML_OK) return s;
+                ++next_enq;
+            }
+            return ML_OK;
+        };
+        if (err > tol) st = fill(depth - 1);
+        if (st != ML_OK) break;
+        while (err > tol && k < k_last && k < next_enq) {
             k += 1;
             total_iter += 1;
-            const int kk = k - 1, slot = kk & 1;
-            // speculatively enqueue the next Arnoldi step before looking at this one's numbers
-            have_next = false;
-            if (k < k_last) {
-                st = enqueue(kk + 1);
-                if (st != ML_OK) break;
-                have_next = true;
-            }
+            const int kk = k - 1, slot = kk % n_slots;
+            // keep `depth` steps in flight beyond the one examined now
+            st = fill(kk + depth);
+            if (st != ML_OK) break;
             GM_CUDA(cudaEventSynchronize(W.ev[slot]));
             const double* hcol = W.h_pinned + (size_t)slot * hs;
             for (int i = 0; i <= k; ++i) H[i + (size_t)kk * ldh] = hcol[i];
