@@ -42,9 +42,11 @@ def wing_dims(n_gpus: int):
     return int(round(96 * f)), int(round(52 * f))
 
 
-def build_case(n_gpus: int, tmpdir: str, matrix_solver: str):
+def build_case(n_gpus: int, tmpdir: str, matrix_solver: str, dims: str | None = None):
     from machline_b200 import host, meshgen
     nc, ns = wing_dims(n_gpus)
+    if dims:   # tests only: a small mesh, e.g. "16x8"
+        nc, ns = (int(v) for v in dims.lower().split("x"))
     pts, tris = meshgen.swept_wing_half(nc, ns)
     name = f"wing_{nc}x{ns}.vtk"
     meshgen.write_vtk(Path(tmpdir) / name, pts, tris)
@@ -134,7 +136,8 @@ class ReferenceRunner:
     def __init__(self, case, budget_s: float, n_steps: int):
         self.ob = _oracle()
         self.case = case
-        self.cores = os.cpu_count() or 1
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.ob.set_threads(self.cores)   # torchrun exports OMP_NUM_THREADS=1; the reference arm uses every host core
         self.per_row = case.n_pairs // case.n_cp
         self.ob.assemble(case, row0=0, nrows=min(case.n_cp, self.cores))   # thread pool / page-in warm-up, untimed
         t0 = time.perf_counter()
@@ -197,9 +200,9 @@ def run_reference(args):
     if rank != 0:
         return
     tmp = tempfile.mkdtemp(prefix="machline_bench_ref_")
-    case, dims = build_case(args.gpus, tmp, args.matrix_solver)
+    case, dims = build_case(args.gpus, tmp, args.matrix_solver, args.dims)
     n_steps = args.steps + args.warmup
-    r = ReferenceRunner(case, budget_s=200.0, n_steps=n_steps)
+    r = ReferenceRunner(case, budget_s=120.0, n_steps=n_steps)
     times, pairs = [], []
     for i in range(n_steps):
         if r.f >= 1.0 and i == 0:
@@ -237,6 +240,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--matrix-solver", default="GMRES")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dims", default=None, help="tests only: NCxNS mesh instead of the BASELINE-sized one")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -245,18 +249,15 @@ def main():
         return
 
     import torch
-    from machline_b200 import gpu
+    from machline_b200 import gpu, shard
 
     dist, rank, world, local = dist_setup(args.gpus)
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     tmp = tempfile.mkdtemp(prefix=f"machline_bench_r{rank}_")
-    case, dims = build_case(world, tmp, args.matrix_solver)
+    case, dims = build_case(world, tmp, args.matrix_solver, args.dims)
     N = case.n_cp
-    # contiguous row blocks of the permuted system, multiples of 64 rows
-    per = ((N + world - 1) // world + 63) // 64 * 64
-    row0 = min(N, rank * per)
-    nrows = max(0, min(N, row0 + per) - row0)
+    row0, nrows = shard.row_shard(N, rank, world)   # contiguous row blocks of the permuted system
     ctx = gpu.Context(local)
     if world > 1:
         uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
@@ -282,33 +283,46 @@ def main():
         x, info = ctx.solve(opts, BC)
     launches0 = ctx.launch_count
     sampler = ClockSampler(local)
+    # device timing: CUDA events recorded on the context's own stream (torch.cuda.Event sees only the stream it is
+    # recorded on); the host-side Givens/convergence test of GMRES runs while that stream is busy, so the event
+    # interval is the whole step.  Wall clock is kept as a cross-check.
+    ext = torch.cuda.ExternalStream(ctx.stream_handle, device=torch.device("cuda", local))
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     barrier()
     sampler.start()
     t0 = time.perf_counter()
+    ev[0].record(ext)
     asm_ms, sol_ms = [], []
     for _ in range(args.steps):
         asm_ms.append(ctx.assemble_resident())
         x, info = ctx.solve(opts, BC)
         sol_ms.append(info.solve_ms)
+    ev[1].record(ext)
     barrier()
     wall = time.perf_counter() - t0
     clocks = sampler.stop()
     launches = ctx.launch_count - launches0
-    step_ms_local = wall * 1e3 / args.steps
+    step_ms_local = ev[0].elapsed_time(ev[1]) / args.steps
+    step_wall_ms_local = wall * 1e3 / args.steps
     local_pairs = ctx.pair_count
 
     # ---- end-to-end steps: host tables in, x out, every step ---------------------------------------
     ctx.profile(reset=True)
     barrier()
     t0 = time.perf_counter()
+    ev[2].record(ext)
     for _ in range(args.steps):
         ctx.set_case(case, row0=row0, nrows=nrows)   # marks the device tables dirty -> H2D again in assemble()
         ctx.assemble()
         x, info_e = ctx.solve(opts, BC)
+    ev[3].record(ext)
     barrier()
     e2e_wall = time.perf_counter() - t0
     prof = ctx.profile()
+    # the end-to-end figure includes the host-side packing of the tables (ml_set_*), which no device event sees:
+    # wall clock between the two barriers, cross-checked by the event interval
     e2e_ms_local = e2e_wall * 1e3 / args.steps
+    e2e_dev_ms_local = ev[2].elapsed_time(ev[3]) / args.steps
 
     # ---- one profiled step: CUDA-event time of the HBM-bound gemv kernel ------------------------------
     ctx.set_profiling(True)
@@ -319,13 +333,13 @@ def main():
     ctx.set_profiling(False)
 
     # ---- reduce over ranks: max time, sum of pairs ---------------------------------------------------
-    vals = torch.tensor([step_ms_local, e2e_ms_local, float(np.mean(asm_ms)), float(np.mean(sol_ms))], dtype=torch.float64,
-                        device=f"cuda:{local}")
+    vals = torch.tensor([step_ms_local, e2e_ms_local, float(np.mean(asm_ms)), float(np.mean(sol_ms)), step_wall_ms_local,
+                         e2e_dev_ms_local], dtype=torch.float64, device=f"cuda:{local}")
     pairs_t = torch.tensor([float(local_pairs)], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(pairs_t, op=dist.ReduceOp.SUM)
-    step_ms, e2e_ms, a_ms, s_ms = [float(v) for v in vals.cpu()]
+    step_ms, e2e_ms, a_ms, s_ms, step_wall_ms, e2e_dev_ms = [float(v) for v in vals.cpu()]
     pairs = float(pairs_t.cpu()[0])
 
     if rank == 0:
@@ -375,6 +389,9 @@ def main():
             "assemble": {"ms": a_ms, "pairs_per_s": pairs / (a_ms * 1e-3)},
             "solve": {"ms": s_ms, "iterations": int(info.iterations), "res_norm": info.res_norm, "res_max": info.res_max},
             "end_to_end_solve_ms": step_ms,
+            "timing": {"ms_per_step": "CUDA events on the context's stream, max over ranks", "wall_ms_per_step": step_wall_ms,
+                       "e2e": "wall clock between barriers (includes host-side table packing), max over ranks",
+                       "e2e_device_event_ms_per_step": e2e_dev_ms},
             "result_check": {"C_p_max": res.C_p_max, "C_p_min": res.C_p_min, "Cx": float(res.C_F[0]), "Cz": float(res.C_F[2])},
             "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": prof.h2d_bytes / args.steps, "d2h_bytes_per_step": prof.d2h_bytes / args.steps,

@@ -181,6 +181,9 @@ long long ml_launch_count(const ml_ctx *ctx);
 /* Device pointers of the resident system (NULL before ml_assemble): for benches that time kernels
    with inputs already resident. */
 ml_status ml_device_system(ml_ctx *ctx, double **A_dev, int *ld, int *nrows_local, int *ncols);
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is enqueued on: lets a caller bracket a
+   sequence of entry-point calls with its own CUDA events (bench.py times steps on the device this way). */
+ml_status ml_device_stream(ml_ctx *ctx, void **stream_out);
 /* Re-run the assembly kernels only (inputs resident, no host transfers); returns device ms. */
 ml_status ml_assemble_resident(ml_ctx *ctx, double *device_ms);
 /* Roofline denominators measured on this device: FP64 vector pipe (register-resident DFMA loop,

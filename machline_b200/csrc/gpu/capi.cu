@@ -561,6 +561,12 @@ extern "C" ml_status ml_device_system(ml_ctx* c, double** A_dev, int* ld, int* n
     return ML_OK;
 }
 
+extern "C" ml_status ml_device_stream(ml_ctx* c, void** stream_out) {
+    if (!c || !stream_out) return ML_BAD_ARGUMENT;
+    *stream_out = (void*)c->stream;
+    return ML_OK;
+}
+
 extern "C" ml_status ml_solve(ml_ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info) {
     if (!c || !opts || !BC || !x_out) return ML_BAD_ARGUMENT;
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_solve before ml_assemble");

@@ -403,8 +403,10 @@ __global__ void __launch_bounds__(1024) vec_norm_kernel(const double* __restrict
     }
 }
 
+// err_scale = |1/A(N,N)| when the reference's DIAG "preconditioner" scaled the system (the stopping test is on the
+// scaled residual, linalg.f90:712-716), else 1.
 ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
-                              int max_iter, int* iters, double* d_x) {
+                              int max_iter, int* iters, double* d_x, double err_scale) {
     if (block_size <= 0 || block_size > N) return c->fail(ML_BAD_ARGUMENT, "block_size out of range");
     int N_blocks = N / block_size;
     if (N % block_size > 0) N_blocks += 1;
@@ -465,6 +467,87 @@ ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const dou
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { st = c->cuda_fail(e, "block_jacobi iteration"); break; }
         if (!(err == err)) { st = ML_NAN_RESIDUAL; break; }
+        err *= err_scale;
+    }
+    *iters = iteration;
+    cleanup();
+    return st;
+}
+
+// ---- block SSOR (linalg.f90:459-598) ------------------------------------------------------------------------
+// x_new(block) = (1-rel) x(block) + rel * D_block^{-1} (b - A(block, left) x_left - A(block, right) x_right), blocks visited
+// first..last and last..first in alternation.  In the forward sweep the left part comes from x_new and the right part
+// from x (:533-546), in the backward sweep the other way round; because x = x_new at the end of every iteration (:590)
+// both are simply the current content of x_new outside the block, so one vector is kept.
+__global__ void bssor_relax_kernel(double rel, const double* __restrict__ xi, double* __restrict__ x_new, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x_new[i] = (1. - rel) * x_new[i] + rel * xi[i];  // linalg.f90:577
+}
+
+ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
+                            int max_iter, int* iters, double* d_x, double err_scale) {
+    if (block_size <= 0 || block_size > N) return c->fail(ML_BAD_ARGUMENT, "block_size out of range");
+    int N_blocks = N / block_size;
+    if (N % block_size > 0) N_blocks += 1;
+    std::vector<DevBuf<double>> blocks(N_blocks);
+    std::vector<DevBuf<int>> pivs(N_blocks);
+    std::vector<int> bs(N_blocks), be(N_blocks), bld(N_blocks);
+    DevBuf<double> vv, xi, bi, nrm;
+    DevBuf<int> flag;
+    auto cleanup = [&]() {
+        for (auto& b : blocks) b.release();
+        for (auto& p : pivs) p.release();
+        vv.release(); flag.release(); xi.release(); bi.release(); nrm.release();
+    };
+    if (vv.alloc(block_size + 64) != cudaSuccess || flag.alloc(1) != cudaSuccess || xi.alloc(N) != cudaSuccess ||
+        bi.alloc(N) != cudaSuccess || nrm.alloc(1) != cudaSuccess) {
+        cleanup();
+        return c->fail(ML_CUDA_ERROR, "block SSOR: out of device memory");
+    }
+    ml_status st = ML_OK;
+    for (int i = 0; i < N_blocks && st == ML_OK; ++i) {
+        bs[i] = i * block_size;
+        be[i] = (i == N_blocks - 1) ? N : (i + 1) * block_size;
+        const int nb = be[i] - bs[i];
+        bld[i] = ((nb + 63) / 64) * 64;
+        if (blocks[i].alloc((size_t)bld[i] * nb) != cudaSuccess || pivs[i].alloc(nb) != cudaSuccess || vv.alloc(nb) != cudaSuccess) {
+            cleanup();
+            return c->fail(ML_CUDA_ERROR, "block SSOR: out of device memory");
+        }
+        dim3 grid((nb + 255) / 256, nb);
+        bj_copy_block_kernel<<<grid, 256, 0, c->stream>>>(dA, ld, bs[i], nb, blocks[i].p, bld[i]);
+        c->launches += 1;
+        st = lu_factor(c, blocks[i].p, bld[i], nb, pivs[i].p, vv.p, flag.p);
+    }
+    // x = 0 (linalg.f90:493); d_x plays x_new
+    if (st == ML_OK) {
+        cudaError_t e = cudaMemsetAsync(d_x, 0, (size_t)N * sizeof(double), c->stream);
+        if (e != cudaSuccess) st = c->cuda_fail(e, "block_ssor init");
+    }
+    int iteration = 0, step = -1;
+    double err = tol + 1.;
+    while (st == ML_OK && err >= tol && iteration < max_iter) {
+        iteration += 1;
+        step = -step;   // first sweep runs forward (linalg.f90:516-527)
+        for (int n = 0; n < N_blocks && st == ML_OK; ++n) {
+            const int i = (step == 1) ? n : N_blocks - 1 - n;
+            const int nb = be[i] - bs[i];
+            bj_rhs_kernel<<<(nb + 31) / 32, 256, 0, c->stream>>>(dA, ld, N, bs[i], be[i], bs[i], be[i], d_b, d_x, bi.p);
+            c->launches += 1;
+            st = lu_substitute(c, blocks[i].p, bld[i], nb, pivs[i].p, bi.p + bs[i], xi.p + bs[i]);
+            if (st != ML_OK) break;
+            bssor_relax_kernel<<<(nb + 255) / 256, 256, 0, c->stream>>>(rel, xi.p + bs[i], d_x + bs[i], nb);
+            c->launches += 1;
+        }
+        if (st != ML_OK) break;
+        bj_rhs_kernel<<<(N + 31) / 32, 256, 0, c->stream>>>(dA, ld, N, 0, N, 0, 0, d_b, d_x, bi.p);
+        vec_norm_kernel<<<1, 1024, 0, c->stream>>>(bi.p, N, nrm.p);
+        c->launches += 2;
+        cudaError_t e = cudaMemcpyAsync(&err, nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { st = c->cuda_fail(e, "block_ssor iteration"); break; }
+        if (!(err == err)) { st = ML_NAN_RESIDUAL; break; }
+        err *= err_scale;
     }
     *iters = iteration;
     cleanup();

@@ -620,7 +620,21 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
 
 ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, double* d_x);  // lu_kernels.cu
 ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
-                              int max_iter, int* iters, double* d_x);                        // lu_kernels.cu
+                              int max_iter, int* iters, double* d_x, double err_scale);      // lu_kernels.cu
+ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
+                            int max_iter, int* iters, double* d_x, double err_scale);        // lu_kernels.cu
+ml_status qrup_solve_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, const double* d_scale, bool fast,
+                            double* d_x);                                                    // seq_solvers.cu
+ml_status purcell_solve_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, const double* d_scale,
+                               double* d_x);                                                 // seq_solvers.cu
+
+static bool needs_whole_matrix(int matrix_solver) {   // everything but the Krylov solvers (invalid names are GMRES)
+    switch (matrix_solver) {
+        case ML_SOLVER_LU: case ML_SOLVER_BJAC: case ML_SOLVER_BSSOR: case ML_SOLVER_QRUP: case ML_SOLVER_FQRUP: case ML_SOLVER_PURC:
+            return true;
+        default: return false;
+    }
+}
 
 // Common tail: dispatch.  d_scale points at 1/A(N,N) on the device when the "DIAG" preconditioner is
 // selected, else nullptr.  The direct and block solvers are scale-invariant (implicit row scaling), so
@@ -633,6 +647,14 @@ static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_
     const bool use_mgs = std::getenv("MACHLINE_GMRES_MGS") != nullptr;
     int block_size = opts->block_size;
     if (block_size <= 0) block_size = S.N / 5;  // panel_solver.f90:1910-1912
+    double err_scale = 1.;
+    const int ms = opts->matrix_solver;
+    if (d_scale && (ms == ML_SOLVER_BJAC || ms == ML_SOLVER_BSSOR)) {
+        cudaError_t e = cudaMemcpyAsync(&err_scale, d_scale, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) return c->cuda_fail(e, "read 1/A(N,N)");
+        err_scale = std::fabs(err_scale);
+    }
     switch (opts->matrix_solver) {
         case ML_SOLVER_LU:
             if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "LU needs the full matrix on one device");
@@ -640,16 +662,26 @@ static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_
             break;
         case ML_SOLVER_BJAC:
             if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "BJAC needs the full matrix on one device");
-            st = block_jacobi_device(c, S.N, lu_matrix, lu_ld, d_b, block_size, opts->tol, opts->rel, opts->max_iterations, &iters, d_x);
+            st = block_jacobi_device(c, S.N, lu_matrix, lu_ld, d_b, block_size, opts->tol, opts->rel, opts->max_iterations, &iters, d_x,
+                                     err_scale);
+            break;
+        case ML_SOLVER_BSSOR:
+            if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "BSSOR needs the full matrix on one device");
+            st = block_ssor_device(c, S.N, lu_matrix, lu_ld, d_b, block_size, opts->tol, opts->rel, opts->max_iterations, &iters, d_x,
+                                   err_scale);
+            break;
+        case ML_SOLVER_QRUP:
+        case ML_SOLVER_FQRUP:
+            if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "QRUP/FQRUP need the full matrix on one device");
+            st = qrup_solve_device(c, S.N, lu_matrix, lu_ld, d_b, d_scale, ms == ML_SOLVER_FQRUP, d_x);
+            break;
+        case ML_SOLVER_PURC:
+            if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "PURC needs the full matrix on one device");
+            st = purcell_solve_device(c, S.N, lu_matrix, lu_ld, d_b, d_scale, d_x);
             break;
         case ML_SOLVER_RGMRES:
             st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, true, use_mgs, d_x, &iters);
             break;
-        case ML_SOLVER_QRUP:
-        case ML_SOLVER_FQRUP:
-        case ML_SOLVER_PURC:
-        case ML_SOLVER_BSSOR:
-            return c->fail(ML_UNSUPPORTED, "QRUP/FQRUP/PURC/BSSOR are sequential solvers outside the GPU hot-path scope (DESIGN.md)");
         case ML_SOLVER_GMRES:
         default:  // invalid names fall back to GMRES (panel_solver.f90:1969-1973)
             st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, false, use_mgs, d_x, &iters);
@@ -788,11 +820,15 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     // Direct / block solvers work on a private full copy (the reference's A_p), single device only.
     DevBuf<double> Acopy;
     double* lu_matrix = nullptr;
-    if (opts->matrix_solver == ML_SOLVER_LU || opts->matrix_solver == ML_SOLVER_BJAC) {
-        if (c->world > 1) return c->fail(ML_UNSUPPORTED, "LU/BJAC on a row-sharded system are not built yet");
-        ML_CUDA(c, Acopy.alloc((size_t)c->ld * N));
-        ML_CUDA(c, cudaMemcpyAsync(Acopy.p, c->d_A.p, (size_t)c->ld * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        lu_matrix = Acopy.p;
+    if (needs_whole_matrix(opts->matrix_solver)) {
+        if (c->world > 1)
+            return c->fail(ML_UNSUPPORTED, "LU/BJAC/BSSOR/QRUP/FQRUP/PURC on a row-sharded system are not built (SURVEY 8(e)): use GMRES/RGMRES");
+        lu_matrix = c->d_A.p;
+        if (opts->matrix_solver == ML_SOLVER_LU) {   // factored in place: work on the reference's A_p copy
+            ML_CUDA(c, Acopy.alloc((size_t)c->ld * N));
+            ML_CUDA(c, cudaMemcpyAsync(Acopy.p, c->d_A.p, (size_t)c->ld * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            lu_matrix = Acopy.p;
+        }
     }
     st = run_solver(S, opts, d_b.p, scale_ptr, d_x.p, info, lu_matrix, c->ld);
     Acopy.release();
@@ -847,11 +883,14 @@ ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_
         scale_ptr = d_scale.p;
     }
     double* lu_matrix = nullptr;
-    if (opts->matrix_solver == ML_SOLVER_LU || opts->matrix_solver == ML_SOLVER_BJAC) {
-        (void)A_is_scratch;  // the residual below needs the original matrix: always factor a copy
-        ML_CUDA(c, Acopy.alloc((size_t)ld * N));
-        ML_CUDA(c, cudaMemcpyAsync(Acopy.p, dA, (size_t)ld * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-        lu_matrix = Acopy.p;
+    if (needs_whole_matrix(opts->matrix_solver)) {
+        (void)A_is_scratch;  // the residual below needs the original matrix: LU factors a copy, the others only read it
+        lu_matrix = dA;
+        if (opts->matrix_solver == ML_SOLVER_LU) {
+            ML_CUDA(c, Acopy.alloc((size_t)ld * N));
+            ML_CUDA(c, cudaMemcpyAsync(Acopy.p, dA, (size_t)ld * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            lu_matrix = Acopy.p;
+        }
     }
     st = run_solver(S, opts, d_b.p, scale_ptr, d_x.p, info, lu_matrix, ld);
     Acopy.release();

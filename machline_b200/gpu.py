@@ -54,6 +54,7 @@ def lib() -> C.CDLL:
                                      C.POINTER(_abi.MlSolveInfo)]
         L.ml_device_system.argtypes = [vp, C.POINTER(dp), ip, ip, ip]
         L.ml_measure_peaks.argtypes = [vp, dp, dp]
+        L.ml_device_stream.argtypes = [vp, C.POINTER(vp)]
         L.ml_nccl_unique_id.argtypes = [C.c_void_p]
         L.ml_set_profiling.argtypes = [vp, C.c_int]
         L.ml_get_profile.argtypes = [vp, C.POINTER(_abi.MlProfile)]
@@ -160,6 +161,13 @@ class Context:
         if reset:
             self._check(lib().ml_reset_profile(self._h))
         return p
+
+    @property
+    def stream_handle(self) -> int:
+        """cudaStream_t of this context (for CUDA-event timing by the caller)."""
+        h = C.c_void_p()
+        self._check(lib().ml_device_stream(self._h, C.byref(h)))
+        return int(h.value or 0)
 
     def measure_peaks(self, hbm: bool = True):
         """(FP64 DFMA TFLOP/s, copy GB/s) measured on this device."""

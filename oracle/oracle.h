@@ -44,6 +44,8 @@ int orc_qr_givens_up(int N, double *A, double *b, double *x);
 int orc_qr_fast_givens_up(int N, double *A, double *b, double *x);
 int orc_purcell(int N, const double *A, const double *b, double *x);
 int orc_lower_bandwidth(int N, const double *A);
+/* number of OpenMP threads used by orc_assemble (n_threads <= 0) and the matvecs of the solvers */
+void orc_set_threads(int n);
 
 /* panel_solver.f90:1802-2027: b = BC - I_known, preconditioner, dispatch, residual.  A (n x n,
    column-major) is not modified. */

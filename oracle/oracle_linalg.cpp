@@ -195,6 +195,11 @@ void arnoldi_update(int N, const double* A, int k, double* Q, double* H, int ldh
 
 }  // namespace
 
+// bench.py --impl reference under torchrun: the launcher exports OMP_NUM_THREADS=1, the reference run uses every core
+extern "C" void orc_set_threads(int n) {
+    if (n > 0) omp_set_num_threads(n);
+}
+
 extern "C" int orc_lower_bandwidth(int N, const double* A) {  // linalg.f90:797-835
     int B_l = 0;
     for (int i = N - 1; i >= 0; --i) {

@@ -57,8 +57,14 @@ def lib() -> C.CDLL:
         L.orc_lower_bandwidth.argtypes = [C.c_int, dp]
         L.orc_solve_system.argtypes = [C.c_int, dp, dp, dp, C.POINTER(_abi.MlSolverOpts), dp,
                                        C.POINTER(_abi.MlSolveInfo)]
+        L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_threads.restype = None
         _lib = L
     return _lib
+
+
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(int(n))
 
 
 def _dp(a):

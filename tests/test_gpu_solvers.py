@@ -1,5 +1,5 @@
 """GPU: the dense solvers behind ml_solve / ml_solve_dense against the oracle restatement of
-common/linalg.f90 on the same systems (LU, GMRES, RGMRES, BJAC), including the reference's quirks:
+common/linalg.f90 on the same systems (LU, GMRES, RGMRES, BJAC, BSSOR, QRUP, FQRUP, PURC), including the reference's quirks:
 the uniform 1/A(N,N) "DIAG" scale, the N/5 default block size and the invalid-name -> GMRES fallback."""
 import numpy as np
 import pytest
@@ -115,10 +115,78 @@ def test_invalid_solver_name_falls_back_to_gmres(ctx):
     assert info.iterations > 0 and np.abs(A @ x - b).max() < 1e-9
 
 
-def test_sequential_solvers_are_declared_unsupported(ctx):
+def _pentagonal(n, band, seed):
+    """Upper-pentagonal system like the reference's sorted AIC (panel_solver.f90:778-1030): zero below the band."""
+    rng = np.random.default_rng(seed)
+    A = rng.standard_normal((n, n)) + 3.0 * np.sqrt(n) * np.eye(n)
+    i, j = np.indices((n, n))
+    A[i - j > band] = 0.0
+    A[(i - j > 0) & ((i + 2 * j) % 5 == 0)] = 0.0          # exact zeros inside the band are skipped (linalg.f90:908, 1145)
+    A[(i - j == band) & (i % 3 == 0)] = 3e-13               # below the 1e-12 bandwidth threshold, yet still rotated
+    return np.asfortranarray(A), rng.standard_normal(n)
+
+
+@pytest.mark.parametrize("solver", ["QRUP", "FQRUP"])
+@pytest.mark.parametrize("n,band", [(1, 0), (2, 1), (3, 2), (65, 7), (300, 299), (700, 90), (1500, 400)])
+@pytest.mark.parametrize("prec", ["none", "DIAG"])
+def test_givens_solvers_are_bit_identical_to_oracle(ctx, solver, n, band, prec):
+    """Every rotation is generated and applied in the reference's order with unfused IEEE operations, so the
+    solution equals the oracle's bit for bit (including the never-rotated last column, linalg.f90:914)."""
+    if n == 1500 and prec == "DIAG":
+        pytest.skip("covered by the unscaled case")
+    A, b = _pentagonal(n, band, seed=n + band)
+    opts = _abi.solver_opts(solver, preconditioner=prec)
+    x, info = ctx.solve_dense(A, b, opts)
+    x_or, info_or = ob.solve_system(A, np.zeros(n), b, opts)
+    assert np.array_equal(x, x_or), np.abs(x - x_or).max()
+    assert info.iterations == -1
+
+
+def test_givens_zero_diagonal_reports_status_3(ctx):
     from machline_b200 import gpu
-    A, b = _system(40, seed=6)
-    for name in ("QRUP", "FQRUP", "PURC", "BSSOR"):
-        with pytest.raises(gpu.GpuError) as e:
-            ctx.solve_dense(A, b, _abi.solver_opts(name))
-        assert e.value.status == 12  # ML_UNSUPPORTED, documented in DESIGN.md
+    n = 20
+    A = np.triu(np.ones((n, n)))
+    A[7, 7] = 0.0
+    with pytest.raises(gpu.GpuError) as e:
+        ctx.solve_dense(np.asfortranarray(A), np.ones(n), _abi.solver_opts("QRUP"))
+    assert e.value.status == 3   # "Zero found on the diagonal of R" (linalg.f90:956-961)
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 257, 600])
+@pytest.mark.parametrize("prec", ["none", "DIAG"])
+def test_purcell_is_bit_identical_to_oracle(ctx, n, prec):
+    A, b = _system(n, seed=100 + n)
+    opts = _abi.solver_opts("PURC", preconditioner=prec)
+    x, info = ctx.solve_dense(A, b, opts)
+    x_or, _ = ob.solve_system(A, np.zeros(n), b, opts)
+    assert np.array_equal(x, x_or), np.abs(x - x_or).max()
+    assert np.abs(A @ x - b).max() < 1e-8
+
+
+@pytest.mark.parametrize("n,bsz", [(200, 40), (777, 0), (1000, 333)])
+@pytest.mark.parametrize("prec", ["none", "DIAG"])
+def test_block_ssor_matches_oracle(ctx, n, bsz, prec):
+    A, b = _system(n, seed=7 * n)
+    opts = _abi.solver_opts("BSSOR", preconditioner=prec, block_size=bsz, rel=0.9, tol=1e-11)
+    x, info = ctx.solve_dense(A, b, opts)
+    x_or, info_or = ob.solve_system(A, np.zeros(n), b, opts)
+    assert info_or.iterations > 2
+    assert abs(info.iterations - info_or.iterations) <= 1, (info.iterations, info_or.iterations)
+    assert np.abs(x - x_or).max() <= 1e-9 * np.abs(x_or).max()
+
+
+@pytest.mark.parametrize("solver", ["QRUP", "FQRUP", "BSSOR", "PURC"])
+def test_sequential_solvers_on_assembled_system(ctx, solver):
+    """The sorted supersonic half-wing system of test 13 through ml_solve with each of the reference's other solvers."""
+    case, _, _ = fixtures.make_case("test_13")
+    ctx.set_case(case)
+    ctx.assemble()
+    opts = case.solver_opts()
+    opts.matrix_solver = _abi.SOLVERS[solver]
+    opts.rel = 0.9
+    x, info = ctx.solve(opts, case.BC)
+    A_ref, I_ref = ob.assemble(case)
+    x_or, info_or = ob.solve_system(A_ref, I_ref, case.BC, opts)
+    assert np.abs(x - x_or).max() <= 2e-9 * np.abs(x_or).max()
+    assert info.res_norm < 1e-9
+    case.close()

@@ -1,0 +1,170 @@
+"""CPU, world_size 2 (gloo): the host-side logic of the N > 1 path.
+
+The GPU path shards the permuted system by control-point rows (no data-path collective in the assembly) and the
+Krylov solvers all-gather one padded vector per matvec (machline_b200/shard.py is the host statement of that layout,
+csrc/gpu/solve_kernels.cu Sys::matvec the device one).  Here two gloo ranks play the two GPUs with the ORACLE as the
+per-rank compute (test infrastructure standing in for the CUDA kernels, which cannot run on this box):
+  * each rank assembles only its own rows; stacked, they are the full matrix, bit for bit;
+  * the sharded matvec + padded all-gather + compaction reproduces the full matvec, and a GMRES driven by it
+    reaches the oracle's solution;
+  * bench.py's reference arm under torchrun: rank 0 alone prints one JSON line, the other rank exits 0."""
+import json
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def test_row_shards_cover_every_row_once():
+    from machline_b200 import shard
+    for n in [1, 63, 64, 65, 1202, 10513, 100000]:
+        for world in [1, 2, 3, 4, 8]:
+            sh = shard.all_shards(n, world)
+            assert sh[0][0] == 0 and sum(nr for _, nr in sh) == n
+            for (a0, an), (b0, _) in zip(sh, sh[1:]):
+                assert a0 + an == b0
+            assert all(r0 % 64 == 0 or nr == 0 for r0, nr in sh)          # aligned shard starts
+            assert max(nr for _, nr in sh) - min(nr for _, nr in sh if nr) <= 64 * world or n < 64 * world
+            pad = shard.shard_pad(sh)
+            assert pad % 64 == 0 and pad >= max(nr for _, nr in sh)
+    with pytest.raises(ValueError):
+        shard.row_shard(10, 2, 2)
+
+
+def _worker(rank: int, world: int, port: int, out_dir: str):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    sys.path.insert(0, str(ROOT / "tests"))
+    import fixtures
+    import oracle_binding as ob
+    from machline_b200 import shard
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        case, _, _ = fixtures.make_case("test_08")      # sphere, 1202 unknowns
+        N = case.n_cp
+        shards = shard.all_shards(N, world)
+        row0, nrows = shards[rank]
+        pad = shard.shard_pad(shards)
+        A_loc, I_loc = ob.assemble(case, row0=row0, nrows=nrows)           # this rank's rows only
+
+        def gather_vec(v_loc):
+            buf = torch.zeros(pad, dtype=torch.float64)
+            buf[:nrows] = torch.from_numpy(np.ascontiguousarray(v_loc))
+            allb = [torch.zeros(pad, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(allb, buf)
+            return shard.compact_gathered(torch.cat(allb).numpy(), shards, pad)
+
+        I_full = gather_vec(I_loc)
+        b = np.asarray(case.BC) - I_full
+
+        def matvec(q):                                                     # Sys::matvec: local rows, all-gather, compact
+            return gather_vec(A_loc @ q)
+
+        # GMRES (x0 = 0, MGS, Givens; linalg.f90:1235-1334) on the unscaled system, replicated small problem per rank
+        tol, kmax = 1e-12, 200
+        beta = np.linalg.norm(b)
+        Q = [b / beta]
+        H = np.zeros((kmax + 1, kmax))
+        cs, sn, e = np.zeros(kmax), np.zeros(kmax), np.zeros(kmax + 1)
+        e[0] = beta
+        k_done = 0
+        for k in range(kmax):
+            w = matvec(Q[k])
+            for i in range(k + 1):
+                H[i, k] = w @ Q[i]
+                w = w - H[i, k] * Q[i]
+            H[k + 1, k] = np.linalg.norm(w)
+            Q.append(w / H[k + 1, k])
+            for i in range(k):
+                t = cs[i] * H[i, k] + sn[i] * H[i + 1, k]
+                H[i + 1, k] = -sn[i] * H[i, k] + cs[i] * H[i + 1, k]
+                H[i, k] = t
+            d = np.hypot(H[k, k], H[k + 1, k])
+            cs[k], sn[k] = H[k, k] / d, H[k + 1, k] / d
+            H[k, k], H[k + 1, k] = d, 0.0
+            e[k + 1] = -sn[k] * e[k]
+            e[k] = cs[k] * e[k]
+            k_done = k + 1
+            if abs(e[k + 1]) < tol:
+                break
+        y = np.linalg.solve(np.triu(H[:k_done, :k_done]), e[:k_done])
+        x = sum(yi * qi for yi, qi in zip(y, Q))
+        res = np.linalg.norm(matvec(x) - b)
+
+        # every rank must hold the same replicated vectors
+        chk = torch.tensor([float(x.sum()), float(res)], dtype=torch.float64)
+        allc = [torch.zeros(2, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        same = all(torch.equal(allc[0], c) for c in allc)
+        np.savez(Path(out_dir) / f"rank{rank}.npz", A_loc=A_loc, row0=row0, nrows=nrows, x=x, res=res, iters=k_done, same=same,
+                 I_full=I_full)
+        case.close()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_row_sharded_assembly_and_gmres(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    sys.path.insert(0, str(ROOT / "tests"))
+    import fixtures
+    import oracle_binding as ob
+    case, _, _ = fixtures.make_case("test_08")
+    A_ref, I_ref = ob.assemble(case)
+    opts = case.solver_opts()
+    opts.preconditioner = 0
+    x_ref, info_ref = ob.solve_system(A_ref, I_ref, case.BC, opts)
+    r = [np.load(tmp_path / f"rank{k}.npz") for k in range(2)]
+    assert int(r[0]["row0"]) == 0 and int(r[0]["nrows"]) + int(r[1]["nrows"]) == case.n_cp
+    assert int(r[1]["row0"]) == int(r[0]["nrows"])
+    assert np.array_equal(np.vstack([r[0]["A_loc"], r[1]["A_loc"]]), A_ref)     # rows do not depend on who builds them
+    for k in range(2):
+        assert bool(r[k]["same"])
+        assert np.array_equal(r[k]["I_full"], I_ref)
+        assert float(r[k]["res"]) < 1e-10
+        assert abs(int(r[k]["iters"]) - info_ref.iterations) <= 1
+        assert np.abs(r[k]["x"] - x_ref).max() <= 1e-9 * np.abs(x_ref).max()
+    case.close()
+
+
+def test_bench_reference_arm_under_torchrun_two_ranks():
+    """Driver contract for --impl reference at N > 1: launched through torch.distributed.run, rank 0 alone runs and
+    prints ONE JSON line; the other rank exits 0 without work.  (torchrun exports OMP_NUM_THREADS=1; the arm resets it.)"""
+    port = _free_port()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), str(ROOT / "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1",
+           "--dims", "16x8"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=str(ROOT))
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1, res.stdout
+    doc = json.loads(lines[0])
+    assert doc["impl"] == "reference" and doc["n_gpus"] == 2 and doc["value"] > 0
+    assert doc["metric"] == "aic_pair_influences_per_s" and doc["higher_is_better"] is True
+    assert doc["cpu_baseline"]["kind"] == "port" and doc["cpu_baseline"]["cores"] >= 1
+    assert doc["e2e"]["h2d_bytes_per_step"] == 0 and doc["e2e"]["value"] == doc["value"]
+
+
+def test_bench_b200_arm_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible")
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--steps", "1", "--dims", "16x8"], capture_output=True, text=True,
+                         timeout=600, cwd=str(ROOT))
+    assert res.returncode != 0
+    assert not any(ln.startswith("{") for ln in res.stdout.splitlines())      # no number without the CUDA path
