@@ -60,6 +60,12 @@ extern "C" ml_status ml_ctx_create(ml_ctx** out, int device_id) {
         delete c;
         return ML_CUDA_ERROR;
     }
+    // solver temporaries come from the default stream-ordered pool and stay cached between solves (ctx.h: PoolScope)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
+        unsigned long long thr = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
     *out = c;
     return ML_OK;
 }
@@ -67,6 +73,10 @@ extern "C" ml_status ml_ctx_create(ml_ctx** out, int device_id) {
 extern "C" void ml_ctx_destroy(ml_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    for (auto& e : c->slot_ev)
+        if (e) cudaEventDestroy(e);
 #ifdef ML_HAVE_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
@@ -87,6 +97,7 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
+    trim_default_pool();
     delete c;
 }
 
@@ -571,6 +582,7 @@ extern "C" ml_status ml_solve(ml_ctx* c, const ml_solver_opts* opts, const doubl
     if (!c || !opts || !BC || !x_out) return ML_BAD_ARGUMENT;
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_solve before ml_assemble");
     ML_CUDA(c, cudaSetDevice(c->device));
+    PoolScope pool(c->stream);
     return solve_resident(c, opts, BC, x_out, info);
 }
 
@@ -578,6 +590,7 @@ extern "C" ml_status ml_solve_dense(ml_ctx* c, int N, const double* A, const dou
                                     double* x_out, ml_solve_info* info) {
     if (!c || N <= 0 || !A || !b || !opts || !x_out) return ML_BAD_ARGUMENT;
     ML_CUDA(c, cudaSetDevice(c->device));
+    PoolScope pool(c->stream);
     DevBuf<double> dA;
     const int ld = ((N + 63) / 64) * 64;
     ML_CUDA(c, dA.alloc((size_t)ld * N));

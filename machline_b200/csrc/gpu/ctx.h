@@ -22,23 +22,60 @@ struct HostPanelTable {  // deep copy of an ml_panel_soa
     void copy_from(const ml_panel_soa* t);
 };
 
+// Stream-ordered allocation for solver temporaries.  ml_solve / ml_solve_dense set this for the duration of the call
+// (PoolScope); DevBuf then allocates from the device's default memory pool on the context's stream, whose release
+// threshold ml_ctx_create raises so that freed blocks stay cached: a solve in steady state performs no cudaMalloc /
+// cudaFree (both synchronise the device and cost up to milliseconds each; a GMRES solve needs ~10 buffers).
+inline thread_local cudaStream_t tl_pool_stream = nullptr;
+
+struct PoolScope {
+    cudaStream_t prev;
+    explicit PoolScope(cudaStream_t s) : prev(tl_pool_stream) { tl_pool_stream = s; }
+    ~PoolScope() { tl_pool_stream = prev; }
+};
+
+inline void trim_default_pool() {
+    int dev = 0;
+    cudaMemPool_t pool;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        cudaDeviceSynchronize();
+        cudaMemPoolTrimTo(pool, 0);
+    }
+}
+
 template <typename T>
 struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
+    cudaStream_t pool_stream = nullptr;   // non-null: allocated with cudaMallocAsync on this stream
     cudaError_t alloc(size_t count) {
         if (count <= n && p) return cudaSuccess;
         release();
         if (count == 0) return cudaSuccess;
-        cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+        cudaError_t e;
+        if (tl_pool_stream) {
+            e = cudaMallocAsync((void**)&p, count * sizeof(T), tl_pool_stream);
+            if (e == cudaSuccess) pool_stream = tl_pool_stream;
+        } else {
+            e = cudaMalloc((void**)&p, count * sizeof(T));
+            if (e == cudaErrorMemoryAllocation) {   // cached pool blocks may be holding the memory
+                cudaGetLastError();
+                trim_default_pool();
+                e = cudaMalloc((void**)&p, count * sizeof(T));
+            }
+        }
         if (e == cudaSuccess) n = count;
         else p = nullptr;
         return e;
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pool_stream) cudaFreeAsync(p, pool_stream);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
+        pool_stream = nullptr;
     }
 };
 
@@ -72,6 +109,10 @@ struct Ctx {
     long long h2d_bytes = 0, d2h_bytes = 0;
     bool profile = false;
     std::vector<cudaEvent_t> gemv_ev;   // start/stop pairs around gemv_n_partial launches (profiling only)
+    // GMRES host pipeline: pinned Hessenberg-column slots and their events, kept across solves
+    double* h_pinned = nullptr;
+    size_t h_pinned_n = 0;
+    cudaEvent_t slot_ev[9] = {};
     long long gemv_launches = 0, gemv_bytes = 0;
     double gemv_ms = 0;
 

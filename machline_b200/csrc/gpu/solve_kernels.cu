@@ -39,10 +39,14 @@ __device__ __forceinline__ double2 ld_stream_d2(const double* p) {
     return v;
 }
 
+// The CTA that finishes a 64-row block last (ticket counter per row block) adds the split partials in split order and
+// writes y = alpha * sum: the result does not depend on which CTA that is, and no second kernel is needed.
 __global__ void __launch_bounds__(GEMV_THREADS) gemv_n_partial_kernel(const double* __restrict__ A, int ld, int n_rows_pad,
                                                                        int n_cols, int cols_per_split,
                                                                        const double* __restrict__ x,
-                                                                       double* __restrict__ y_part) {
+                                                                       double* __restrict__ y_part, unsigned* __restrict__ tickets,
+                                                                       int n_rows, const double* __restrict__ alpha_dev,
+                                                                       double alpha, double* __restrict__ y) {
     __shared__ double2 s_acc[GEMV_THREADS / 32][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * GEMV_ROWS + 2 * lane;
@@ -82,7 +86,26 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_n_partial_kernel(const doub
             s.y += s_acc[w][lane].y;
         }
         double2* out = reinterpret_cast<double2*>(y_part + (size_t)blockIdx.y * n_rows_pad + row);
-        *out = s;
+        __stcg(out, s);
+        if (tickets) {
+            __threadfence();
+            unsigned t = 0;
+            if (lane == 0) t = atomicAdd(tickets + blockIdx.x, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t == gridDim.y - 1) {
+                __threadfence();
+                double2 sum = make_double2(0., 0.);
+                for (unsigned k = 0; k < gridDim.y; ++k) {
+                    const double2 p = __ldcg(reinterpret_cast<const double2*>(y_part + (size_t)k * n_rows_pad + row));
+                    sum.x += p.x;
+                    sum.y += p.y;
+                }
+                const double a = alpha_dev ? (*alpha_dev) * alpha : alpha;
+                if (row < n_rows) y[row] = a * sum.x;
+                if (row + 1 < n_rows) y[row + 1] = a * sum.y;
+                if (lane == 0) tickets[blockIdx.x] = 0;   // ready for the next launch
+            }
+        }
     }
 }
 
@@ -252,6 +275,186 @@ __global__ void __launch_bounds__(256) orth_sub_kernel(const double* __restrict_
     }
 }
 
+
+// ---- fused Arnoldi tail: both Gram-Schmidt passes, the norm and the new basis vector in ONE cooperative launch ----------
+// One CTA per SM (1024 threads), four grid barriers:
+//   dot(w) | B | h1 = sum partials, w -= Q h1 | B | dot(w) | B | h2, w -= Q h2, ||w||^2 partials | B | q_next = w / ||w||
+// Between kernels the per-iteration latency was launch gaps + one wave ramp per kernel (6 launches ~ 80 us at N = 10k
+// for ~10 us of L2-resident traffic); inside one launch a barrier costs ~2 us.  Data other CTAs wrote earlier in the
+// launch (w, partials) is read with ld.global.cg: L1 is not coherent across SMs.
+constexpr int TAIL_THREADS = 1024;
+constexpr int TAIL_WARPS = TAIL_THREADS / 32;
+constexpr int TAIL_RB = 256;       // rows per dot item (8 per lane)
+
+struct TailArgs {
+    const double* Q;
+    int ldq, n, k;          // k = number of basis vectors to orthogonalise against
+    double* w;              // in: A q (length ldq, pad rows zero); out: orthogonalised, not normalised
+    double* partial;        // [n_rb][kpad]
+    int kpad, n_rb;
+    double* h1;             // first-pass coefficients
+    double* hfin;           // hfin[0..k-1] = h1 + h2, hfin[k] = ||w||
+    double* npart;          // [gridDim.x]
+    double* qnext;          // Q(:, k)
+    unsigned* bar;          // monotonic barrier counter (zeroed at the start of a solve)
+    unsigned bar_base;      // its value when this launch begins
+    int rows_per_cta;       // multiple of 32
+};
+
+__device__ __forceinline__ void tail_grid_sync(unsigned* bar, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void tail_dot_phase(const TailArgs& a) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ncg = (a.k + 3) >> 2;
+    const int items = a.n_rb * ncg;
+    for (int item = blockIdx.x * TAIL_WARPS + warp; item < items; item += gridDim.x * TAIL_WARPS) {
+        const int rb = item % a.n_rb, col0 = (item / a.n_rb) * 4;
+        const int row0 = rb * TAIL_RB + lane;
+        double wv[TAIL_RB / 32];
+#pragma unroll
+        for (int j = 0; j < TAIL_RB / 32; ++j) {
+            const int r = row0 + 32 * j;
+            wv[j] = (r < a.n) ? __ldcg(a.w + r) : 0.;
+        }
+        double acc[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int col = min(col0 + c, a.k - 1);
+            const double* q = a.Q + (size_t)col * a.ldq + row0;
+            double a0 = 0., a1 = 0.;
+#pragma unroll
+            for (int j = 0; j < TAIL_RB / 32; j += 2) {
+                const int r = row0 + 32 * j;
+                const double q0 = (r < a.n) ? q[32 * j] : 0.;
+                const double q1 = (r + 32 < a.n) ? q[32 * j + 32] : 0.;
+                a0 = fma(q0, wv[j], a0);
+                a1 = fma(q1, wv[j + 1], a1);
+            }
+            acc[c] = a0 + a1;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        }
+        if (lane < 4 && col0 + lane < a.k) {
+            const double v = lane == 0 ? acc[0] : lane == 1 ? acc[1] : lane == 2 ? acc[2] : acc[3];
+            __stcg(a.partial + (size_t)rb * a.kpad + col0 + lane, v);
+        }
+    }
+}
+
+// s_h[j] = sum_rb partial[rb][j]; w -= Q s_h over this CTA's rows; returns the CTA's sum of squares of the new w (thread 0)
+__device__ __forceinline__ double tail_sub_phase(const TailArgs& a, double* s_h, double* s_acc, bool second) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < a.k; j += TAIL_THREADS) {
+        double s = 0.;
+        for (int rb = 0; rb < a.n_rb; ++rb) s += __ldcg(a.partial + (size_t)rb * a.kpad + j);
+        s_h[j] = s;
+        if (blockIdx.x == 0) {
+            if (second) a.hfin[j] = a.h1[j] + s;
+            else a.h1[j] = s;
+        }
+    }
+    __syncthreads();
+    const int n_rg = a.rows_per_cta >> 5;                 // 32-row groups of this CTA
+    const int n_cs = TAIL_WARPS / n_rg > 0 ? TAIL_WARPS / n_rg : 1;   // column splits
+    const int cta_row0 = blockIdx.x * a.rows_per_cta;
+    double sq_total = 0.;
+    for (int rg0 = 0; rg0 < n_rg; rg0 += TAIL_WARPS) {     // one trip unless a CTA owns more than 1024 rows
+        const int rg = rg0 + (n_cs > 1 ? warp % n_rg : warp), cs = (n_cs > 1) ? warp / n_rg : 0;
+        const bool busy = rg < n_rg && cs < n_cs;
+        const int row = cta_row0 + rg * 32 + lane;
+        double a0 = 0., a1 = 0., a2 = 0., a3 = 0.;
+        if (busy && row < a.n) {
+            const double* q = a.Q + row;
+            int j = cs;
+            for (; j + 3 * n_cs < a.k; j += 4 * n_cs) {
+                const double q0 = q[(size_t)j * a.ldq], q1 = q[(size_t)(j + n_cs) * a.ldq];
+                const double q2 = q[(size_t)(j + 2 * n_cs) * a.ldq], q3 = q[(size_t)(j + 3 * n_cs) * a.ldq];
+                a0 = fma(q0, s_h[j], a0);
+                a1 = fma(q1, s_h[j + n_cs], a1);
+                a2 = fma(q2, s_h[j + 2 * n_cs], a2);
+                a3 = fma(q3, s_h[j + 3 * n_cs], a3);
+            }
+            for (; j < a.k; j += n_cs) a0 = fma(q[(size_t)j * a.ldq], s_h[j], a0);
+        }
+        if (busy) s_acc[cs * a.rows_per_cta + (rg - rg0) * 32 + lane] = (a0 + a1) + (a2 + a3);
+        __syncthreads();
+        const int rows_here = min(TAIL_WARPS, n_rg - rg0) * 32;
+        double sq = 0.;
+        if ((int)threadIdx.x < rows_here) {
+            double s = 0.;
+            for (int c = 0; c < n_cs; ++c) s += s_acc[c * a.rows_per_cta + threadIdx.x];
+            const int r = cta_row0 + rg0 * 32 + threadIdx.x;
+            if (r < a.n) {
+                const double v = __ldcg(a.w + r) - s;
+                __stcg(a.w + r, v);
+                sq = v * v;
+            }
+        }
+        if (second) {
+            // fixed-order block sum of sq (a fixed shuffle tree per warp, then warp order)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            __syncthreads();
+            if (lane == 0) s_acc[warp] = sq;
+            __syncthreads();
+            if (threadIdx.x == 0)
+                for (int k2 = 0; k2 < TAIL_WARPS; ++k2) sq_total += s_acc[k2];
+        }
+        __syncthreads();
+    }
+    return sq_total;   // meaningful in thread 0
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) arnoldi_tail_kernel(const TailArgs a) {
+    extern __shared__ double s_mem[];
+    double* s_h = s_mem;                                   // [k rounded up to even]
+    double* s_acc = s_mem + ((a.k + 1) & ~1);              // [1024]: column splits x rows per trip <= 32 x 32
+    __shared__ double s_norm;
+    const unsigned G = gridDim.x;
+    tail_dot_phase(a);
+    tail_grid_sync(a.bar, a.bar_base + G);
+    tail_sub_phase(a, s_h, s_acc, false);
+    tail_grid_sync(a.bar, a.bar_base + 2 * G);
+    tail_dot_phase(a);
+    tail_grid_sync(a.bar, a.bar_base + 3 * G);
+    const double sq = tail_sub_phase(a, s_h, s_acc, true);
+    if (threadIdx.x == 0) __stcg(a.npart + blockIdx.x, sq);
+    tail_grid_sync(a.bar, a.bar_base + 4 * G);
+    // ||w|| from the per-CTA partials in CTA order (every CTA computes the same value), q_next = w / ||w||
+    if (threadIdx.x < 32) {
+        double t = 0.;
+        for (unsigned c = threadIdx.x; c < G; c += 32) t += __ldcg(a.npart + c);
+        // fixed tree over the 32 lane sums
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) {
+            s_norm = sqrt(t);
+            if (blockIdx.x == 0) a.hfin[a.k] = s_norm;
+        }
+    }
+    __syncthreads();
+    const double nrm = s_norm;
+    const int cta_row0 = blockIdx.x * a.rows_per_cta;
+    for (int t = threadIdx.x; t < a.rows_per_cta; t += TAIL_THREADS) {
+        const int r = cta_row0 + t;
+        if (r < a.n) a.qnext[r] = __ldcg(a.w + r) / nrm;
+    }
+}
+
 // norm = sqrt(sum of the per-CTA partials) (fixed order); q = w / norm; CTA 0 also stores the norm
 __global__ void __launch_bounds__(1024) norm_scale2_kernel(const double* __restrict__ w, int n, const double* __restrict__ norm_partial,
                                                             int n_part, double* __restrict__ norm_out, double* __restrict__ q) {
@@ -358,6 +561,7 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
     int row0;           // first global row of this shard
     int shard_pad;      // rows per rank in the all-gather layout
     DevBuf<double> y_part, gather;
+    DevBuf<unsigned> tickets;   // per 64-row block: splits finished (gemv_n_partial_kernel)
     int n_split = 1, cols_per_split = 0;
 
     ml_status init() {
@@ -369,29 +573,31 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
         cols_per_split = (N + n_split - 1) / n_split;
         n_split = (N + cols_per_split - 1) / cols_per_split;
         ML_CUDA(c, y_part.alloc((size_t)n_split * n_rows_pad));
+        ML_CUDA(c, tickets.alloc(row_blocks));
+        ML_CUDA(c, cudaMemsetAsync(tickets.p, 0, (size_t)row_blocks * sizeof(unsigned), c->stream));
         if (c->world > 1) ML_CUDA(c, gather.alloc((size_t)shard_pad * c->world));
         return ML_OK;
     }
     // y_full[N] = alpha * (alpha_dev ? *alpha_dev : 1) * A x      (x, y_full replicated full-length vectors)
     ml_status matvec(const double* x, double* y_full, double alpha, const double* alpha_dev) {
         dim3 grid(n_rows_pad / GEMV_ROWS, n_split);
+        double* dst = (c->world > 1) ? gather.p + (size_t)c->rank * shard_pad : y_full;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (c->profile) {
-            cudaEvent_t e0, e1;
             ML_CUDA(c, cudaEventCreate(&e0));
             ML_CUDA(c, cudaEventCreate(&e1));
             ML_CUDA(c, cudaEventRecord(e0, c->stream));
-            gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p);
+        }
+        gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p, tickets.p,
+                                                                     n_rows, alpha_dev, alpha, dst);
+        if (c->profile) {
             ML_CUDA(c, cudaEventRecord(e1, c->stream));
             c->gemv_ev.push_back(e0);
             c->gemv_ev.push_back(e1);
             c->gemv_launches += 1;
             c->gemv_bytes += (long long)8 * n_rows * N;
-        } else {
-            gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p);
         }
-        double* dst = (c->world > 1) ? gather.p + (size_t)c->rank * shard_pad : y_full;
-        gemv_n_finish_kernel<<<(n_rows + 255) / 256, 256, 0, c->stream>>>(y_part.p, n_rows_pad, n_rows, n_split, alpha_dev, alpha, dst);
-        c->launches += 2;
+        c->launches += 1;
         ML_CUDA(c, cudaGetLastError());
 #ifdef ML_HAVE_NCCL
         if (c->world > 1) {
@@ -411,25 +617,22 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
     void release() {
         y_part.release();
         gather.release();
+        tickets.release();
     }
 };
 
 static inline double fsign(double a, double b) { return std::signbit(b) ? -std::fabs(a) : std::fabs(a); }
 
 namespace {
-struct GmresWork {  // device + pinned host buffers of one gmres_device call
+struct GmresWork {  // device buffers of one gmres_device call (pool-allocated); the pinned slots and events live in Ctx
     DevBuf<double> Q, w, r0, ydev, hdev, nrm, opart, npart;
+    DevBuf<unsigned> bar;         // grid-barrier counter of the fused Arnoldi tail
     static constexpr int MAX_SLOTS = 9;
-    double* h_pinned = nullptr;   // n_slots x (k_max + 2)
-    cudaEvent_t ev[MAX_SLOTS] = {};
+    double* h_pinned = nullptr;   // n_slots x (k_max + 2), borrowed from Ctx
+    cudaEvent_t* ev = nullptr;    // borrowed from Ctx
     void release() {
         Q.release(); w.release(); r0.release(); ydev.release(); hdev.release(); nrm.release(); opart.release(); npart.release();
-        if (h_pinned) cudaFreeHost(h_pinned);
-        h_pinned = nullptr;
-        for (auto& e : ev) {
-            if (e) cudaEventDestroy(e);
-            e = nullptr;
-        }
+        bar.release();
     }
 };
 }  // namespace
@@ -454,18 +657,28 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         if (e__ != cudaSuccess) return fail_cuda(e__, #call); \
     } while (0)
     const int ldq = ((N + 63) / 64) * 64;                    // padded so that 64-row CTAs can use 16-byte loads unguarded
-    const int n_rb = (N + ORTH_RB - 1) / ORTH_RB, kpad = k_max + 4, n_row64 = ldq / 64;
+    const int n_row64 = ldq / 64, kpad = k_max + 4;
+    // fused Arnoldi tail (one cooperative launch per iteration); MACHLINE_GMRES_TAIL=0 selects the five-kernel sequence
+    bool fused_tail = !use_mgs;
+    if (const char* e = std::getenv("MACHLINE_GMRES_TAIL")) fused_tail = fused_tail && std::atoi(e) != 0;
+    const int tail_grid = c->num_sms;
+    const int tail_rows = 32 * ((N + 32 * tail_grid - 1) / (32 * tail_grid));
+    const int n_rb = fused_tail ? (N + TAIL_RB - 1) / TAIL_RB : (N + ORTH_RB - 1) / ORTH_RB;
+    unsigned bar_base = 0;
     GM_CUDA(W.Q.alloc((size_t)ldq * (k_max + 1)));
     GM_CUDA(W.w.alloc(ldq));
     GM_CUDA(W.r0.alloc(ldq));
     GM_CUDA(W.opart.alloc((size_t)n_rb * kpad));
-    GM_CUDA(W.npart.alloc(n_row64));
+    GM_CUDA(W.npart.alloc(std::max(n_row64, tail_grid)));
+    GM_CUDA(W.bar.alloc(1));
+    GM_CUDA(cudaMemsetAsync(W.bar.p, 0, sizeof(unsigned), c->stream));
     GM_CUDA(cudaMemsetAsync(W.Q.p, 0, (size_t)ldq * (k_max + 1) * sizeof(double), c->stream));
     GM_CUDA(cudaMemsetAsync(W.w.p, 0, (size_t)ldq * sizeof(double), c->stream));
     {
         static bool attr_set = false;
         if (!attr_set) {
             GM_CUDA(cudaFuncSetAttribute(orth_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            GM_CUDA(cudaFuncSetAttribute(arnoldi_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
             attr_set = true;
         }
     }
@@ -478,8 +691,17 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     const int n_slots = depth + 1;
     GM_CUDA(W.hdev.alloc((size_t)3 * n_slots * hs));  // per slot: hfin (final column), h1 and h2 (the two Gram-Schmidt passes)
     GM_CUDA(W.nrm.alloc(2));
-    GM_CUDA(cudaHostAlloc((void**)&W.h_pinned, (size_t)n_slots * hs * sizeof(double), cudaHostAllocDefault));
-    for (int i = 0; i < n_slots; ++i) GM_CUDA(cudaEventCreateWithFlags(&W.ev[i], cudaEventDisableTiming));
+    if (c->h_pinned_n < (size_t)n_slots * hs) {
+        if (c->h_pinned) cudaFreeHost(c->h_pinned);
+        c->h_pinned = nullptr;
+        c->h_pinned_n = 0;
+        GM_CUDA(cudaHostAlloc((void**)&c->h_pinned, (size_t)n_slots * hs * sizeof(double), cudaHostAllocDefault));
+        c->h_pinned_n = (size_t)n_slots * hs;
+    }
+    W.h_pinned = c->h_pinned;
+    for (int i = 0; i < n_slots; ++i)
+        if (!c->slot_ev[i]) GM_CUDA(cudaEventCreateWithFlags(&c->slot_ev[i], cudaEventDisableTiming));
+    W.ev = c->slot_ev;
 
     const int ldh = k_max + 1;
     std::vector<double> H((size_t)ldh * k_max, 0.), cs(k_max, 0.), sn(k_max, 0.), E(std::max(N, k_max + 1) + 1, 0.);
@@ -501,9 +723,22 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
             mgs_kernel<<<1, 1024, 0, c->stream>>>(W.Q.p, ldq, N, k, W.w.p, hfin);
             norm_scale_kernel<<<1, 1024, 0, c->stream>>>(W.w.p, N, hfin + k, W.Q.p + (size_t)k * ldq);
             c->launches += 2;
+        } else if (fused_tail) {
+            // classical Gram-Schmidt with one re-orthogonalisation pass (same Krylov subspace and Hessenberg matrix as
+            // the reference's modified Gram-Schmidt up to rounding), norm and normalisation: one cooperative launch
+            TailArgs ta;
+            ta.Q = W.Q.p; ta.ldq = ldq; ta.n = N; ta.k = k;
+            ta.w = W.w.p; ta.partial = W.opart.p; ta.kpad = kpad; ta.n_rb = n_rb;
+            ta.h1 = h1; ta.hfin = hfin; ta.npart = W.npart.p; ta.qnext = W.Q.p + (size_t)k * ldq;
+            ta.bar = W.bar.p; ta.bar_base = bar_base; ta.rows_per_cta = tail_rows;
+            bar_base += 4u * (unsigned)tail_grid;
+            void* kargs[] = {(void*)&ta};
+            const size_t smem = (size_t)(((k + 1) & ~1) + 1024) * sizeof(double);
+            cudaError_t e = cudaLaunchCooperativeKernel((const void*)arnoldi_tail_kernel, dim3(tail_grid), dim3(TAIL_THREADS), kargs, smem,
+                                                        c->stream);
+            if (e != cudaSuccess) return c->cuda_fail(e, "arnoldi_tail_kernel");
+            c->launches += 1;
         } else {
-            // classical Gram-Schmidt with one re-orthogonalisation pass: same Krylov subspace and Hessenberg
-            // matrix as the reference's modified Gram-Schmidt up to rounding, but every pass is device-parallel
             const dim3 gdot(n_rb, (k + ORTH_CG - 1) / ORTH_CG);
             const size_t sub_smem = (size_t)(((k + 1) & ~1) + 8 * 64 + 2) * sizeof(double);
             orth_dot_kernel<<<gdot, 256, 0, c->stream>>>(W.Q.p, ldq, N, k, W.w.p, W.opart.p, kpad);

@@ -1,5 +1,5 @@
-"""Repeat the solve on the resident bench system (development aid: timing spread)."""
-import sys, tempfile
+"""Repeat the solve on the resident bench system (development aid: timing spread, wall vs device)."""
+import sys, tempfile, time
 from pathlib import Path
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
@@ -15,9 +15,12 @@ ctx = gpu.Context(0)
 ctx.set_case(case)
 ctx.assemble()
 opts = case.solver_opts()
-ms = []
+ms, wall = [], []
 for i in range(reps):
+    t0 = time.perf_counter()
     x, info = ctx.solve(opts, case.BC)
+    wall.append(1e3 * (time.perf_counter() - t0))
     ms.append(info.solve_ms)
 print(solver, "N", case.n_unknown, "iters", info.iterations, "res %.2e" % info.res_norm, "solve ms:", " ".join(f"{m:.1f}" for m in ms))
+print("   wall ms:", " ".join(f"{m:.1f}" for m in wall))
 ctx.close()
