@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "ctx.h"
@@ -102,6 +103,192 @@ __global__ void __launch_bounds__(256) lu_panel_update_kernel(double* __restrict
     for (int c = 0; c < nc; ++c) A[i + (size_t)(j + 1 + c) * ld] = fma(-l, s_row[c], A[i + (size_t)(j + 1 + c) * ld]);
 }
 
+// ---- whole panel in ONE cooperative launch --------------------------------------------------------------
+// The per-column kernels above cost two launches and two passes over L2 per column (2 N launches per
+// factorisation).  Here the panel (rows k0..n, columns k0..k1) is dealt to the CTAs in blocks of `rpc` row
+// positions, each CTA keeps its block in shared memory for the whole panel, and a column costs one grid barrier:
+//   before the barrier  every CTA publishes its best candidate (value, position) and that row's panel entries;
+//                       the CTA holding position j publishes row j (it moves to the pivot's position);
+//   after the barrier   every CTA reduces the G candidates with the reference's rule (largest vv*|a|, ties ->
+//                       LAST position, linalg.f90:242), takes the pivot row from the winner's slot, the two
+//                       CTAs involved exchange rows j <-> p (all panel columns, as the reference swaps whole
+//                       rows, :254-262, and vv(p) = vv(j), :263), and all update their rows below j.
+// Candidate slots are double-buffered by column parity: a slot written for column j is next written for
+// column j+2, after barrier j+1, i.e. after every CTA finished reading it.  Arithmetic per element is
+// a(i,c) = fma(-l, a(j,c), a(i,c)) with l = a(i,j) * (1/a(j,j)), identical to the per-column kernels.
+constexpr int LUP_THREADS = 256;
+constexpr int LUP_CAP = 384;   // rows a CTA can hold: 64 columns x 384 rows x 8 B = 192 KB
+
+struct LuPanelArgs {
+    double* A;
+    int ld, n, k0, k1, rpc;
+    double* vv;
+    int* piv;
+    double* cand_v;     // [2][G]
+    int* cand_i;        // [2][G]
+    double* cand_row;   // [2][G][LU_NB]
+    double* rowj;       // [2][LU_NB + 1]   (last entry: vv of row j)
+    unsigned* bar;
+    unsigned bar_base;
+};
+
+__device__ __forceinline__ void lup_grid_sync(unsigned* bar, unsigned target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1u);
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory");
+        } while ((int)(v - target) < 0);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool lup_better(double v, int i, double best, int bi) { return v > best || (v == best && i > bi); }
+
+__global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuPanelArgs a) {
+    extern __shared__ __align__(16) double lup_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int nb = a.k1 - a.k0;
+    const int r0 = a.k0 + bid * a.rpc;                 // first row position of this CTA
+    const int nr = min(a.rpc, a.n - r0);               // > 0 by grid sizing
+    const int S = a.rpc | 1;                           // odd column stride: row gathers are conflict-free
+    double* sP = lup_smem;                             // [LU_NB][S]
+    double* s_piv = sP + LU_NB * S;                    // [LU_NB]  pivot row, panel columns
+    double* s_oldj = s_piv + LU_NB;                    // [LU_NB + 1] old row j (+ its vv)
+    double* s_l = s_oldj + LU_NB + 1;                  // [rpc]
+    double* s_vv = s_l + a.rpc;                        // [rpc]
+    double* s_rv = s_vv + a.rpc;                       // [8]
+    int* s_ri = reinterpret_cast<int*>(s_rv + 8);      // [8] + s_ri[8] = winner
+    const int nrb = (nr + 31) >> 5;
+
+    for (int item = warp; item < nb * nrb; item += LUP_THREADS / 32) {
+        const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
+        if (r < nr) sP[c * S + r] = __ldcg(a.A + (size_t)(a.k0 + c) * a.ld + r0 + r);
+    }
+    for (int r = tid; r < nr; r += LUP_THREADS) s_vv[r] = __ldcg(a.vv + r0 + r);
+    __syncthreads();
+
+    for (int jj = 0; jj < nb; ++jj) {
+        const int j = a.k0 + jj, par = jj & 1;
+        // ---- this CTA's candidate for column j ------------------------------------------------------------
+        double best = -1.;
+        int bi = -1;
+        for (int r = tid; r < nr; r += LUP_THREADS) {
+            const int gp = r0 + r;
+            if (gp >= j) {
+                const double v = s_vv[r] * fabs(sP[jj * S + r]);
+                if (lup_better(v, gp, best, bi)) { best = v; bi = gp; }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (lup_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+        }
+        if (lane == 0) { s_rv[warp] = best; s_ri[warp] = bi; }
+        __syncthreads();
+        if (warp == 0) {
+            best = lane < LUP_THREADS / 32 ? s_rv[lane] : -1.;
+            bi = lane < LUP_THREADS / 32 ? s_ri[lane] : -1;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) {
+                const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (lup_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+            }
+            if (lane == 0) {
+                s_ri[8] = bi;
+                __stcg(a.cand_v + par * G + bid, best);
+                __stcg(a.cand_i + par * G + bid, bi);
+            }
+        }
+        __syncthreads();
+        bi = s_ri[8];
+        if (bi >= 0 && tid < nb) __stcg(a.cand_row + ((size_t)par * G + bid) * LU_NB + tid, sP[tid * S + (bi - r0)]);
+        const bool own_j = (j >= r0 && j < r0 + nr);
+        if (own_j) {
+            if (tid < nb) __stcg(a.rowj + par * (LU_NB + 1) + tid, sP[tid * S + (j - r0)]);
+            if (tid == nb) __stcg(a.rowj + par * (LU_NB + 1) + LU_NB, s_vv[j - r0]);
+        }
+        lup_grid_sync(a.bar, a.bar_base + (unsigned)(jj + 1) * (unsigned)G);
+        // ---- global pivot: reduce the G candidates (every CTA, redundantly) ---------------------------------
+        best = -1.;
+        bi = -1;
+        for (int g = tid; g < G; g += LUP_THREADS) {
+            const double v = __ldcg(a.cand_v + par * G + g);
+            const int i = __ldcg(a.cand_i + par * G + g);
+            if (i >= 0 && lup_better(v, i, best, bi)) { best = v; bi = i; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (lup_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+        }
+        if (G > 32) {
+            if (lane == 0) { s_rv[warp] = best; s_ri[warp] = bi; }
+            __syncthreads();
+            if (warp == 0) {
+                best = lane < LUP_THREADS / 32 ? s_rv[lane] : -1.;
+                bi = lane < LUP_THREADS / 32 ? s_ri[lane] : -1;
+#pragma unroll
+                for (int o = 4; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                    if (lup_better(ov, oi, best, bi)) { best = ov; bi = oi; }
+                }
+                if (lane == 0) s_ri[8] = bi;
+            }
+        } else if (tid == 0) {
+            s_ri[8] = bi;   // warp 0 saw every candidate
+        }
+        __syncthreads();
+        int p = s_ri[8];
+        if (p < 0) p = j;   // a column of NaNs: keep the diagonal (the reference's imax stays at its previous value)
+        const int w = (p - a.k0) / a.rpc;
+        const bool own_p = (p >= r0 && p < r0 + nr);
+        if (tid < nb) s_piv[tid] = __ldcg(a.cand_row + ((size_t)par * G + w) * LU_NB + tid);
+        if (p != j && own_p && tid <= nb) s_oldj[tid == nb ? LU_NB : tid] = __ldcg(a.rowj + par * (LU_NB + 1) + (tid == nb ? LU_NB : tid));
+        if (bid == 0 && tid == 0) a.piv[j] = p;
+        __syncthreads();
+        if (p != j) {   // whole-row interchange inside the panel (linalg.f90:254-263)
+            if (own_j && tid < nb) sP[tid * S + (j - r0)] = s_piv[tid];
+            if (own_p) {
+                if (tid < nb) sP[tid * S + (p - r0)] = s_oldj[tid];
+                if (tid == nb) s_vv[p - r0] = s_oldj[LU_NB];
+            }
+            __syncthreads();
+        }
+        // ---- eliminate column j from the rows below it ------------------------------------------------------
+        const double inv = 1.0 / s_piv[jj];
+        for (int r = tid; r < nr; r += LUP_THREADS) {
+            double l = 0.;
+            if (r0 + r > j) {
+                l = sP[jj * S + r] * inv;
+                sP[jj * S + r] = l;
+            }
+            s_l[r] = l;
+        }
+        __syncthreads();
+        const int ncr = nb - jj - 1;
+        for (int item = warp; item < ncr * nrb; item += LUP_THREADS / 32) {
+            const int cc = item / nrb, r = ((item - cc * nrb) << 5) + lane;
+            const int c = jj + 1 + cc;
+            if (r < nr && r0 + r > j) sP[c * S + r] = fma(-s_l[r], s_piv[c], sP[c * S + r]);
+        }
+        __syncthreads();
+    }
+    for (int item = warp; item < nb * nrb; item += LUP_THREADS / 32) {
+        const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
+        if (r < nr) a.A[(size_t)(a.k0 + c) * a.ld + r0 + r] = sP[c * S + r];
+    }
+    for (int r = tid; r < nr; r += LUP_THREADS) a.vv[r0 + r] = s_vv[r];
+}
+
 // apply the panel's row interchanges to the columns outside the panel
 __global__ void __launch_bounds__(256) lu_laswp_kernel(double* __restrict__ A, int ld, int n, int k0, int k1,
                                                         const int* __restrict__ piv) {
@@ -119,28 +306,34 @@ __global__ void __launch_bounds__(256) lu_laswp_kernel(double* __restrict__ A, i
     }
 }
 
-// U12 = L11^{-1} A12 : one thread per column right of the panel, L11 (unit lower, nb x nb) in shared memory
-__global__ void __launch_bounds__(128) lu_trsm_kernel(double* __restrict__ A, int ld, int n, int k0, int k1) {
-    __shared__ double sL[LU_NB * (LU_NB + 1)];
-    const int nb = k1 - k0;
-    for (int t = threadIdx.x; t < nb * nb; t += 128) {
-        int r = t % nb, c = t / nb;
-        sL[r * (LU_NB + 1) + c] = A[(k0 + r) + (size_t)(k0 + c) * ld];
+// U12 = L11^{-1} A12 : one thread per column right of the panel, L11 (unit lower, 64 x 64) in shared memory.
+// Only full panels reach this kernel (a short last panel has nothing to its right).  Both loops are unrolled so the
+// column lives in registers; the column-oriented order (x[r] -= L[r][k] x[k] for all r > k) exposes 63..1 independent
+// FMAs per step, and every L[r][k] is a shared-memory broadcast.
+__global__ void __launch_bounds__(64) lu_trsm_kernel(double* __restrict__ A, int ld, int n, int k0, int k1) {
+    __shared__ double sL[LU_NB * LU_NB];   // sL[k * LU_NB + r] = L(r, k): column-major, conflict-free fill
+    for (int t = threadIdx.x; t < LU_NB * LU_NB; t += 64) {
+        const int r = t % LU_NB, k = t / LU_NB;
+        sL[t] = A[(k0 + r) + (size_t)(k0 + k) * ld];
     }
     __syncthreads();
-    int c = k1 + blockIdx.x * 128 + threadIdx.x;
+    const int c = k1 + blockIdx.x * 64 + threadIdx.x;
     if (c >= n) return;
     double* col = A + (size_t)c * ld + k0;
     double x[LU_NB];
-#pragma unroll 8
-    for (int r = 0; r < LU_NB; ++r) x[r] = (r < nb) ? col[r] : 0.;
-#pragma unroll 1
-    for (int r = 1; r < nb; ++r) {
-        double s = x[r];
-        for (int k = 0; k < r; ++k) s = fma(-sL[r * (LU_NB + 1) + k], x[k], s);
-        x[r] = s;
+#pragma unroll
+    for (int r = 0; r < LU_NB; r += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(col + r);
+        x[r] = v.x;
+        x[r + 1] = v.y;
     }
-    for (int r = 0; r < nb; ++r) col[r] = x[r];
+#pragma unroll
+    for (int k = 0; k < LU_NB - 1; ++k) {
+#pragma unroll
+        for (int r = k + 1; r < LU_NB; ++r) x[r] = fma(-sL[k * LU_NB + r], x[k], x[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < LU_NB; r += 2) *reinterpret_cast<double2*>(col + r) = make_double2(x[r], x[r + 1]);
 }
 
 // ---- trailing update on the FP64 tensor cores ---------------------------------------------------------
@@ -209,6 +402,111 @@ __global__ void __launch_bounds__(256) lu_gemm_dmma_kernel(double* __restrict__ 
         }
 }
 
+// Second-generation trailing update.  A CTA owns one block of 128 rows: it stages -L21 (128 x 64) in shared memory
+// ONCE with cp.async and then walks over a run of 64-column tiles; the U12 tile of the next step is fetched with
+// cp.async into the other half of a double buffer and the next C tile is prefetched into registers while the DMMAs of
+// the current tile run, so no global-memory latency is exposed between tiles.  Same fragment layout and the same
+// accumulation order over k as lu_gemm_dmma_kernel (bitwise the same result).
+constexpr int G2_THREADS = 256;
+constexpr size_t G2_SMEM = (size_t)(GM_K * GM_SA + 2 * GM_BN * GM_SB) * sizeof(double);
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    const int sz = pred ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restrict__ A, int ld, int n, int k0, int k1, int n_col_tiles,
+                                                                 int tiles_per_cta) {
+    extern __shared__ __align__(16) double smem[];
+    double* sA = smem;                  // [GM_K][GM_SA]   L21 (negated when the fragments are read)
+    double* sB = smem + GM_K * GM_SA;   // [2][GM_BN][GM_SB] U12 tiles
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int row0 = k1 + blockIdx.x * GM_BM;
+    const int ct0 = blockIdx.y * tiles_per_cta, ct1 = min(ct0 + tiles_per_cta, n_col_tiles);
+    if (ct0 >= ct1) return;
+    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int g = lane >> 2, q = lane & 3;
+
+    for (int t = tid; t < GM_K * (GM_BM / 2); t += G2_THREADS) {
+        const int k = t / (GM_BM / 2), m2 = (t % (GM_BM / 2)) * 2;
+        const int r = row0 + m2;
+        cp_async16(sA + k * GM_SA + m2, A + (size_t)(k0 + k) * ld + min(r, n - 1), r < n);
+    }
+    auto load_u = [&](int buf, int ct) {
+        double* dst = sB + buf * (GM_BN * GM_SB);
+        const int col0 = k1 + ct * GM_BN;
+        for (int t = tid; t < GM_BN * (GM_K / 2); t += G2_THREADS) {
+            const int nn = t / (GM_K / 2), k2 = (t % (GM_K / 2)) * 2;
+            const int c = col0 + nn;
+            cp_async16(dst + nn * GM_SB + k2, A + (size_t)min(c, n - 1) * ld + k0 + k2, c < n);
+        }
+    };
+    double cn[4][4][2];
+    auto load_c = [&](int ct) {
+        const int col0 = k1 + ct * GM_BN;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int r = row0 + wm + mt * 8 + g;
+                const int cc = col0 + wn + nt * 8 + 2 * q;
+                cn[mt][nt][0] = (r < n && cc < n) ? __ldcs(A + r + (size_t)cc * ld) : 0.;
+                cn[mt][nt][1] = (r < n && cc + 1 < n) ? __ldcs(A + r + (size_t)(cc + 1) * ld) : 0.;
+            }
+    };
+    load_u(0, ct0);
+    cp_async_commit();
+    load_c(ct0);
+    for (int ct = ct0; ct < ct1; ++ct) {
+        const int buf = (ct - ct0) & 1;
+        double c[4][4][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                c[mt][nt][0] = cn[mt][nt][0];
+                c[mt][nt][1] = cn[mt][nt][1];
+            }
+        if (ct + 1 < ct1) {
+            load_u(buf ^ 1, ct + 1);
+            cp_async_commit();
+            load_c(ct + 1);
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+        const double* sBb = sB + buf * (GM_BN * GM_SB);
+#pragma unroll 4
+        for (int ks = 0; ks < GM_K; ks += 4) {
+            double a[4], b[4];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt) a[mt] = -sA[(ks + q) * GM_SA + wm + mt * 8 + g];
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) b[nt] = sBb[(wn + nt * 8 + g) * GM_SB + ks + q];
+#pragma unroll
+            for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(c[mt][nt][0], c[mt][nt][1], a[mt], b[nt]);
+        }
+        const int col0 = k1 + ct * GM_BN;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+                const int r = row0 + wm + mt * 8 + g;
+                const int cc = col0 + wn + nt * 8 + 2 * q;
+                if (r < n && cc < n) A[r + (size_t)cc * ld] = c[mt][nt][0];
+                if (r < n && cc + 1 < n) A[r + (size_t)(cc + 1) * ld] = c[mt][nt][1];
+            }
+        __syncthreads();   // every warp is done with sB[buf] before the next iteration refills it
+    }
+}
+
 // ---- triangular solves with the factors (blocked TRSV) --------------------------------------------------
 // diagonal block: x[k0..k1) solved in place by one CTA
 __global__ void __launch_bounds__(64) lu_trsv_diag_kernel(const double* __restrict__ A, int ld, int k0, int k1, double* __restrict__ x,
@@ -262,6 +560,10 @@ __global__ void lu_permute_kernel(const double* __restrict__ b, const int* __res
     }
 }
 
+static size_t lu_panel_smem(int rpc) {
+    return (size_t)(LU_NB * (rpc | 1) + LU_NB + LU_NB + 1 + 2 * rpc + 8) * sizeof(double) + 16 * sizeof(int);
+}
+
 // ---- host drivers ---------------------------------------------------------------------------------------
 // In-place LU of the n x n matrix at dA (leading dimension ld).  piv / vv are device work arrays of length n.
 static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double* d_vv, int* d_flag) {
@@ -269,6 +571,8 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     const size_t gemm_smem = (size_t)(GM_K * GM_SA + GM_BN * GM_SB) * sizeof(double);
     if (!attr_set) {
         ML_CUDA(c, cudaFuncSetAttribute(lu_gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+        ML_CUDA(c, cudaFuncSetAttribute(lu_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
+        ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel_smem(LUP_CAP)));
         attr_set = true;
     }
     ML_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
@@ -278,26 +582,70 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     ML_CUDA(c, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
     if (flag) return c->fail(ML_SINGULAR, "lu_decomp: the matrix is singular (a row is zero; linalg.f90:205-208)");
+    // scratch of the cooperative panel kernel: candidate slots for up to num_sms CTAs, two parities
+    const int gmax = c->num_sms;
+    DevBuf<double> pscr;
+    DevBuf<int> pidx;
+    DevBuf<unsigned> pbar;
+    ML_CUDA(c, pscr.alloc((size_t)2 * gmax * (LU_NB + 1) + 2 * (LU_NB + 1)));
+    ML_CUDA(c, pidx.alloc((size_t)2 * gmax));
+    ML_CUDA(c, pbar.alloc(1));
+    ML_CUDA(c, cudaMemsetAsync(pbar.p, 0, sizeof(unsigned), c->stream));
+    unsigned bar_base = 0;
+    static const bool per_column = getenv("MACHLINE_LU_PER_COLUMN") != nullptr;   // the unfused paths, kept for A/B timing
+    static const bool old_gemm = getenv("MACHLINE_LU_GEMM_V1") != nullptr;
     for (int k0 = 0; k0 < n; k0 += LU_NB) {
         const int k1 = std::min(k0 + LU_NB, n);
-        for (int j = k0; j < k1; ++j) {
-            lu_pivot_kernel<<<1, 1024, 0, c->stream>>>(dA, ld, n, j, k0, k1, d_vv, d_piv);
-            if (j + 1 < n) lu_panel_update_kernel<<<(n - j - 1 + 255) / 256, 256, 0, c->stream>>>(dA, ld, n, j, k1);
-            c->launches += 2;
+        const int m = n - k0;
+        int rpc = 128;
+        if ((long long)rpc * gmax < m) rpc = (((m + gmax - 1) / gmax) + 31) & ~31;
+        if (!per_column && rpc <= LUP_CAP) {
+            LuPanelArgs pa;
+            pa.A = dA; pa.ld = ld; pa.n = n; pa.k0 = k0; pa.k1 = k1; pa.rpc = rpc;
+            pa.vv = d_vv; pa.piv = d_piv;
+            pa.cand_v = pscr.p;
+            pa.cand_row = pscr.p + 2 * gmax;
+            pa.rowj = pa.cand_row + (size_t)2 * gmax * LU_NB;
+            pa.cand_i = pidx.p;
+            pa.bar = pbar.p; pa.bar_base = bar_base;
+            const int G = (m + rpc - 1) / rpc;
+            bar_base += (unsigned)(k1 - k0) * (unsigned)G;
+            const size_t smem = lu_panel_smem(rpc);
+            void* kargs[] = {(void*)&pa};
+            ML_CUDA(c, cudaLaunchCooperativeKernel((const void*)lu_panel_coop_kernel, dim3(G), dim3(LUP_THREADS), kargs, smem, c->stream));
+            c->launches += 1;
+        } else {
+            for (int j = k0; j < k1; ++j) {
+                lu_pivot_kernel<<<1, 1024, 0, c->stream>>>(dA, ld, n, j, k0, k1, d_vv, d_piv);
+                if (j + 1 < n) lu_panel_update_kernel<<<(n - j - 1 + 255) / 256, 256, 0, c->stream>>>(dA, ld, n, j, k1);
+                c->launches += 2;
+            }
         }
         lu_laswp_kernel<<<(n - (k1 - k0) + 255) / 256 + 1, 256, 0, c->stream>>>(dA, ld, n, k0, k1, d_piv);
         c->launches += 1;
         if (k1 < n) {
-            lu_trsm_kernel<<<(n - k1 + 127) / 128, 128, 0, c->stream>>>(dA, ld, n, k0, k1);
+            lu_trsm_kernel<<<(n - k1 + 63) / 64, 64, 0, c->stream>>>(dA, ld, n, k0, k1);
             c->launches += 1;
             if (k1 - k0 == LU_NB) {
-                dim3 grid((n - k1 + GM_BM - 1) / GM_BM, (n - k1 + GM_BN - 1) / GM_BN);
-                lu_gemm_dmma_kernel<<<grid, 256, gemm_smem, c->stream>>>(dA, ld, n, k0, k1);
+                const int rb = (n - k1 + GM_BM - 1) / GM_BM, ctiles = (n - k1 + GM_BN - 1) / GM_BN;
+                if (!old_gemm && (ld & 1) == 0) {
+                    // enough CTAs for ~2 waves of one CTA per SM; each walks over a run of column tiles
+                    const int chunks = std::max(1, std::min(ctiles, (2 * c->num_sms + rb - 1) / rb));
+                    const int per = (ctiles + chunks - 1) / chunks;
+                    dim3 grid(rb, (ctiles + per - 1) / per);
+                    lu_gemm2_kernel<<<grid, G2_THREADS, G2_SMEM, c->stream>>>(dA, ld, n, k0, k1, ctiles, per);
+                } else {
+                    dim3 grid(rb, ctiles);
+                    lu_gemm_dmma_kernel<<<grid, 256, gemm_smem, c->stream>>>(dA, ld, n, k0, k1);
+                }
                 c->launches += 1;
             }
         }
         ML_CUDA(c, cudaGetLastError());
     }
+    pscr.release();
+    pidx.release();
+    pbar.release();
     return ML_OK;
 }
 

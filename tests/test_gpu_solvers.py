@@ -53,6 +53,35 @@ def test_lu_needs_pivoting(ctx):
     assert np.abs(A @ x - b).max() < 1e-10
 
 
+@pytest.mark.parametrize("n", [1500, 4500, 5000])
+def test_lu_heavy_pivoting_across_ctas(ctx, n):
+    """No diagonal dominance: (almost) every column interchanges two rows held by different CTAs of the cooperative
+    panel kernel (n = 4500 / 5000: more than 32 CTAs, the two-level candidate reduction; 5000 is not a multiple of 64)."""
+    rng = np.random.default_rng(n)
+    A = np.asfortranarray(rng.standard_normal((n, n)))
+    A[::5] *= 1e3          # implicit scaling matters: vv differs by row
+    b = rng.standard_normal(n)
+    x, info = ctx.solve_dense(A, b, _abi.solver_opts("LU"))
+    x_np = np.linalg.solve(A, b)
+    assert np.abs(x - x_np).max() <= 1e-8 * np.abs(x_np).max()
+    r = A @ x - b
+    assert np.abs(r).max() <= 1e-9 * (np.abs(A).sum(axis=1) * np.abs(x).max()).max()
+
+
+def test_lu_ties_take_the_last_row(ctx):
+    """Exact ties of vv*|a| (rows that are sign / permutation copies of each other in a column): the reference keeps the LAST
+    maximal row (`>=`, linalg.f90:242).  With a different tie rule the factorisation is still valid, so the check is
+    against the oracle's solution to rounding on a matrix where wrong ties change the pivot order drastically."""
+    n = 192
+    rng = np.random.default_rng(5)
+    A = rng.integers(-1, 2, size=(n, n)).astype(float) + 3 * np.eye(n)
+    A = np.asfortranarray(A)
+    b = rng.standard_normal(n)
+    x, _ = ctx.solve_dense(A, b, _abi.solver_opts("LU"))
+    x_or, _ = ob.solve_system(A, np.zeros(n), b, _abi.solver_opts("LU"))
+    assert np.abs(x - x_or).max() <= 1e-11 * np.abs(x_or).max()
+
+
 def test_lu_singular_reports_status_3(ctx):
     from machline_b200 import gpu
     A, b = _system(50, seed=9)
