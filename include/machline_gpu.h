@@ -189,6 +189,9 @@ ml_status ml_assemble_resident(ml_ctx *ctx, double *device_ms);
 /* Roofline denominators measured on this device: FP64 vector pipe (register-resident DFMA loop,
    TFLOP/s) and a streaming copy (read+write GB/s).  Either pointer may be NULL. */
 ml_status ml_measure_peaks(ml_ctx *ctx, double *fp64_tflops, double *hbm_gbs);
+/* FP64 tensor pipe (DMMA, mma.sync.m8n8k4.f64) peak measured on this device, TFLOP/s: the roofline of the
+   blocked LU's trailing update. */
+ml_status ml_measure_dmma_peak(ml_ctx *ctx, double *tflops);
 /* Accounting since context creation (or the last ml_reset_profile): host<->device bytes moved by the
    entry points, and -- when profiling is on -- CUDA-event time of the HBM-bound gemv kernel of the
    Krylov solvers (one event pair per launch, on the launching stream). */

@@ -20,13 +20,26 @@ namespace mlgpu {
 constexpr int LU_NB = 64;
 
 // ---- implicit row scaling (linalg.f90:193-213) --------------------------------------------------------
-__global__ void lu_row_scale_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ vv, int* __restrict__ flag) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+// amax(i) = max_j |A(i,j)| over a 2-D grid (rows x column chunks); non-negative doubles order like their bit patterns, so
+// the chunks combine with an integer atomicMax.  amax must be zeroed before the launch.
+constexpr int RS_COLS = 128;
+__global__ void __launch_bounds__(128) lu_row_amax_kernel(const double* __restrict__ A, int ld, int n, unsigned long long* __restrict__ amax) {
+    const int i = blockIdx.x * 128 + threadIdx.x;
     if (i >= n) return;
-    double amax = 0.;
-    for (int j = 0; j < n; ++j) amax = fmax(amax, fabs(A[i + (size_t)j * ld]));
+    const int j0 = blockIdx.y * RS_COLS, j1 = min(j0 + RS_COLS, n);
+    double m = 0.;
+#pragma unroll 8
+    for (int j = j0; j < j1; ++j) m = fmax(m, fabs(A[i + (size_t)j * ld]));
+    atomicMax(amax + i, (unsigned long long)__double_as_longlong(m));
+}
+// vv(i) = 1/amax(i) in place; a zero row flags the matrix singular (linalg.f90:205-208); perm = identity
+__global__ void lu_row_scale_finish_kernel(double* __restrict__ vv, int n, int* __restrict__ flag, int* __restrict__ perm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double amax = vv[i];
     if (amax <= 1.5e-20) atomicExch(flag, 1);
     vv[i] = 1.0 / amax;
+    perm[i] = i;
 }
 
 // ---- one column of the panel: pivot search + row swap inside the panel ---------------------------------
@@ -118,16 +131,18 @@ __global__ void __launch_bounds__(256) lu_panel_update_kernel(double* __restrict
 // a(i,c) = fma(-l, a(j,c), a(i,c)) with l = a(i,j) * (1/a(j,j)), identical to the per-column kernels.
 constexpr int LUP_THREADS = 256;
 constexpr int LUP_CAP = 384;   // rows a CTA can hold: 64 columns x 384 rows x 8 B = 192 KB
+constexpr int LUP_ROW = LU_NB + 2;   // a published row: LU_NB panel entries, perm, vv
 
 struct LuPanelArgs {
     double* A;
     int ld, n, k0, k1, rpc;
     double* vv;
     int* piv;
+    int* perm;          // perm[i] = original row now at position i (the composition of the interchanges so far)
     double* cand_v;     // [2][G]
     int* cand_i;        // [2][G]
-    double* cand_row;   // [2][G][LU_NB]
-    double* rowj;       // [2][LU_NB + 1]   (last entry: vv of row j)
+    double* cand_row;   // [2][G][LUP_ROW]  panel entries of the candidate row, then its perm entry
+    double* rowj;       // [2][LUP_ROW]     panel entries of row j, its perm entry, its vv
     unsigned* bar;
     unsigned bar_base;
 };
@@ -157,18 +172,22 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
     const int S = a.rpc | 1;                           // odd column stride: row gathers are conflict-free
     double* sP = lup_smem;                             // [LU_NB][S]
     double* s_piv = sP + LU_NB * S;                    // [LU_NB]  pivot row, panel columns
-    double* s_oldj = s_piv + LU_NB;                    // [LU_NB + 1] old row j (+ its vv)
-    double* s_l = s_oldj + LU_NB + 1;                  // [rpc]
+    double* s_oldj = s_piv + LUP_ROW;                  // [LUP_ROW] old row j (+ perm, vv)
+    double* s_l = s_oldj + LUP_ROW;                    // [rpc]
     double* s_vv = s_l + a.rpc;                        // [rpc]
     double* s_rv = s_vv + a.rpc;                       // [8]
     int* s_ri = reinterpret_cast<int*>(s_rv + 8);      // [8] + s_ri[8] = winner
+    int* s_perm = s_ri + 16;                           // [rpc]
     const int nrb = (nr + 31) >> 5;
 
     for (int item = warp; item < nb * nrb; item += LUP_THREADS / 32) {
         const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
         if (r < nr) sP[c * S + r] = __ldcg(a.A + (size_t)(a.k0 + c) * a.ld + r0 + r);
     }
-    for (int r = tid; r < nr; r += LUP_THREADS) s_vv[r] = __ldcg(a.vv + r0 + r);
+    for (int r = tid; r < nr; r += LUP_THREADS) {
+        s_vv[r] = __ldcg(a.vv + r0 + r);
+        s_perm[r] = __ldcg(a.perm + r0 + r);
+    }
     __syncthreads();
 
     for (int jj = 0; jj < nb; ++jj) {
@@ -208,11 +227,17 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         }
         __syncthreads();
         bi = s_ri[8];
-        if (bi >= 0 && tid < nb) __stcg(a.cand_row + ((size_t)par * G + bid) * LU_NB + tid, sP[tid * S + (bi - r0)]);
+        if (bi >= 0) {
+            double* slot = a.cand_row + ((size_t)par * G + bid) * LUP_ROW;
+            if (tid < nb) __stcg(slot + tid, sP[tid * S + (bi - r0)]);
+            if (tid == LU_NB) __stcg(slot + LU_NB, (double)s_perm[bi - r0]);
+        }
         const bool own_j = (j >= r0 && j < r0 + nr);
         if (own_j) {
-            if (tid < nb) __stcg(a.rowj + par * (LU_NB + 1) + tid, sP[tid * S + (j - r0)]);
-            if (tid == nb) __stcg(a.rowj + par * (LU_NB + 1) + LU_NB, s_vv[j - r0]);
+            double* slot = a.rowj + par * LUP_ROW;
+            if (tid < nb) __stcg(slot + tid, sP[tid * S + (j - r0)]);
+            if (tid == LU_NB) __stcg(slot + LU_NB, (double)s_perm[j - r0]);
+            if (tid == LU_NB + 1) __stcg(slot + LU_NB + 1, s_vv[j - r0]);
         }
         lup_grid_sync(a.bar, a.bar_base + (unsigned)(jj + 1) * (unsigned)G);
         // ---- global pivot: reduce the G candidates (every CTA, redundantly) ---------------------------------
@@ -251,15 +276,19 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         if (p < 0) p = j;   // a column of NaNs: keep the diagonal (the reference's imax stays at its previous value)
         const int w = (p - a.k0) / a.rpc;
         const bool own_p = (p >= r0 && p < r0 + nr);
-        if (tid < nb) s_piv[tid] = __ldcg(a.cand_row + ((size_t)par * G + w) * LU_NB + tid);
-        if (p != j && own_p && tid <= nb) s_oldj[tid == nb ? LU_NB : tid] = __ldcg(a.rowj + par * (LU_NB + 1) + (tid == nb ? LU_NB : tid));
+        if (tid < nb || tid == LU_NB) s_piv[tid] = __ldcg(a.cand_row + ((size_t)par * G + w) * LUP_ROW + tid);
+        if (p != j && own_p && (tid < nb || tid == LU_NB || tid == LU_NB + 1)) s_oldj[tid] = __ldcg(a.rowj + par * LUP_ROW + tid);
         if (bid == 0 && tid == 0) a.piv[j] = p;
         __syncthreads();
         if (p != j) {   // whole-row interchange inside the panel (linalg.f90:254-263)
-            if (own_j && tid < nb) sP[tid * S + (j - r0)] = s_piv[tid];
+            if (own_j) {
+                if (tid < nb) sP[tid * S + (j - r0)] = s_piv[tid];
+                if (tid == LU_NB) s_perm[j - r0] = (int)s_piv[LU_NB];
+            }
             if (own_p) {
                 if (tid < nb) sP[tid * S + (p - r0)] = s_oldj[tid];
-                if (tid == nb) s_vv[p - r0] = s_oldj[LU_NB];
+                if (tid == LU_NB) s_perm[p - r0] = (int)s_oldj[LU_NB];
+                if (tid == LU_NB + 1) s_vv[p - r0] = s_oldj[LU_NB + 1];
             }
             __syncthreads();
         }
@@ -286,7 +315,25 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
         if (r < nr) a.A[(size_t)(a.k0 + c) * a.ld + r0 + r] = sP[c * S + r];
     }
-    for (int r = tid; r < nr; r += LUP_THREADS) a.vv[r0 + r] = s_vv[r];
+    for (int r = tid; r < nr; r += LUP_THREADS) {
+        a.vv[r0 + r] = s_vv[r];
+        a.perm[r0 + r] = s_perm[r];
+    }
+}
+
+// the per-column fallback keeps only the interchanges: compose them (sequentially) into the row permutation
+__global__ void lu_perm_from_piv_kernel(const int* __restrict__ piv, int n, int* __restrict__ perm) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        for (int i = 0; i < n; ++i) perm[i] = i;
+        for (int i = 0; i < n; ++i) {
+            const int p = piv[i];
+            if (p != i) {
+                const int t = perm[p];
+                perm[p] = perm[i];
+                perm[i] = t;
+            }
+        }
+    }
 }
 
 // apply the panel's row interchanges to the columns outside the panel
@@ -402,13 +449,17 @@ __global__ void __launch_bounds__(256) lu_gemm_dmma_kernel(double* __restrict__ 
         }
 }
 
-// Second-generation trailing update.  A CTA owns one block of 128 rows: it stages -L21 (128 x 64) in shared memory
-// ONCE with cp.async and then walks over a run of 64-column tiles; the U12 tile of the next step is fetched with
-// cp.async into the other half of a double buffer and the next C tile is prefetched into registers while the DMMAs of
-// the current tile run, so no global-memory latency is exposed between tiles.  Same fragment layout and the same
-// accumulation order over k as lu_gemm_dmma_kernel (bitwise the same result).
+// Second-generation trailing update.  A CTA owns one block of 128 rows: it stages L21 (128 x 64) in shared memory
+// ONCE with cp.async and then walks over a run of 32-column tiles.  The CTA is split into two groups of four warps
+// that work on alternate tiles with their own double-buffered U12 tiles and their own named barrier, so one group's
+// load / store phase overlaps the other group's DMMA phase (with a single CTA-wide barrier per tile all eight warps
+// issue their stores, address arithmetic and loads in lockstep and the tensor pipe idles meanwhile).  The U12 tile
+// of a group's next step is fetched with cp.async and its next C tile is prefetched into registers while the DMMAs
+// of the current tile run.  Same fragment layout and the same accumulation order over k as lu_gemm_dmma_kernel
+// (bitwise the same result).
 constexpr int G2_THREADS = 256;
-constexpr size_t G2_SMEM = (size_t)(GM_K * GM_SA + 2 * GM_BN * GM_SB) * sizeof(double);
+constexpr int G2_BN = 32;                                   // columns per group tile
+constexpr size_t G2_SMEM = (size_t)(GM_K * GM_SA + 2 * 2 * G2_BN * GM_SB) * sizeof(double);
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -418,17 +469,17 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, boo
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
 __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restrict__ A, int ld, int n, int k0, int k1, int n_col_tiles,
                                                                  int tiles_per_cta) {
     extern __shared__ __align__(16) double smem[];
     double* sA = smem;                  // [GM_K][GM_SA]   L21 (negated when the fragments are read)
-    double* sB = smem + GM_K * GM_SA;   // [2][GM_BN][GM_SB] U12 tiles
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127, warp = gtid >> 5, lane = tid & 31;
+    double* sB = smem + GM_K * GM_SA + grp * (2 * G2_BN * GM_SB);   // this group's [2][G2_BN][GM_SB] U12 tiles
     const int row0 = k1 + blockIdx.x * GM_BM;
-    const int ct0 = blockIdx.y * tiles_per_cta, ct1 = min(ct0 + tiles_per_cta, n_col_tiles);
-    if (ct0 >= ct1) return;
-    const int wm = (warp & 3) * 32, wn = (warp >> 2) * 32;
+    const int ct0 = blockIdx.y * tiles_per_cta + grp, ct1 = min((int)(blockIdx.y + 1) * tiles_per_cta, n_col_tiles);
+    const int wm = warp * 32;
     const int g = lane >> 2, q = lane & 3;
 
     for (int t = tid; t < GM_K * (GM_BM / 2); t += G2_THREADS) {
@@ -436,10 +487,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restr
         const int r = row0 + m2;
         cp_async16(sA + k * GM_SA + m2, A + (size_t)(k0 + k) * ld + min(r, n - 1), r < n);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
+    __syncthreads();
+    if (ct0 >= ct1) return;
     auto load_u = [&](int buf, int ct) {
-        double* dst = sB + buf * (GM_BN * GM_SB);
-        const int col0 = k1 + ct * GM_BN;
-        for (int t = tid; t < GM_BN * (GM_K / 2); t += G2_THREADS) {
+        double* dst = sB + buf * (G2_BN * GM_SB);
+        const int col0 = k1 + ct * G2_BN;
+        for (int t = gtid; t < G2_BN * (GM_K / 2); t += 128) {
             const int nn = t / (GM_K / 2), k2 = (t % (GM_K / 2)) * 2;
             const int c = col0 + nn;
             cp_async16(dst + nn * GM_SB + k2, A + (size_t)min(c, n - 1) * ld + k0 + k2, c < n);
@@ -447,13 +502,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restr
     };
     double cn[4][4][2];
     auto load_c = [&](int ct) {
-        const int col0 = k1 + ct * GM_BN;
+        const int col0 = k1 + ct * G2_BN;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int r = row0 + wm + mt * 8 + g;
-                const int cc = col0 + wn + nt * 8 + 2 * q;
+                const int cc = col0 + nt * 8 + 2 * q;
                 cn[mt][nt][0] = (r < n && cc < n) ? __ldcs(A + r + (size_t)cc * ld) : 0.;
                 cn[mt][nt][1] = (r < n && cc + 1 < n) ? __ldcs(A + r + (size_t)(cc + 1) * ld) : 0.;
             }
@@ -461,8 +516,8 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restr
     load_u(0, ct0);
     cp_async_commit();
     load_c(ct0);
-    for (int ct = ct0; ct < ct1; ++ct) {
-        const int buf = (ct - ct0) & 1;
+    int buf = 0;
+    for (int ct = ct0; ct < ct1; ct += 2, buf ^= 1) {
         double c[4][4][2];
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
@@ -471,40 +526,59 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restr
                 c[mt][nt][0] = cn[mt][nt][0];
                 c[mt][nt][1] = cn[mt][nt][1];
             }
-        if (ct + 1 < ct1) {
-            load_u(buf ^ 1, ct + 1);
+        if (ct + 2 < ct1) {
+            load_u(buf ^ 1, ct + 2);
             cp_async_commit();
-            load_c(ct + 1);
+            load_c(ct + 2);
             cp_async_wait<1>();
         } else {
             cp_async_wait<0>();
         }
-        __syncthreads();
-        const double* sBb = sB + buf * (GM_BN * GM_SB);
+        group_sync(1 + grp);
+        const double* sBb = sB + buf * (G2_BN * GM_SB);
 #pragma unroll 4
         for (int ks = 0; ks < GM_K; ks += 4) {
             double a[4], b[4];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt) a[mt] = -sA[(ks + q) * GM_SA + wm + mt * 8 + g];
 #pragma unroll
-            for (int nt = 0; nt < 4; ++nt) b[nt] = sBb[(wn + nt * 8 + g) * GM_SB + ks + q];
+            for (int nt = 0; nt < 4; ++nt) b[nt] = sBb[(nt * 8 + g) * GM_SB + ks + q];
 #pragma unroll
             for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(c[mt][nt][0], c[mt][nt][1], a[mt], b[nt]);
         }
-        const int col0 = k1 + ct * GM_BN;
+        const int col0 = k1 + ct * G2_BN;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int r = row0 + wm + mt * 8 + g;
-                const int cc = col0 + wn + nt * 8 + 2 * q;
+                const int cc = col0 + nt * 8 + 2 * q;
                 if (r < n && cc < n) A[r + (size_t)cc * ld] = c[mt][nt][0];
                 if (r < n && cc + 1 < n) A[r + (size_t)(cc + 1) * ld] = c[mt][nt][1];
             }
-        __syncthreads();   // every warp is done with sB[buf] before the next iteration refills it
+        group_sync(1 + grp);   // every warp of the group is done with sB[buf] before the next iteration refills it
     }
+}
+
+// Grid shape of the trailing update: rb row blocks x `chunks` runs of 32-column tiles.  Picks the run length that
+// minimises (number of waves over the SMs) x (tiles per run + the cost of staging L21, ~3 tiles), so the last wave
+// is not mostly empty (82 row blocks x 4 runs = 2.2 waves wasted a quarter of the launch).
+static void lu_gemm2_shape(int rb, int ctiles, int num_sms, int* per_out, int* chunks_out) {
+    long long best = -1;
+    int best_per = ctiles, best_chunks = 1;
+    for (int chunks = 1; chunks <= ctiles; ++chunks) {
+        int per = (ctiles + chunks - 1) / chunks;
+        per = (per + 1) & ~1;   // both warp groups get the same number of tiles
+        const int nch = (ctiles + per - 1) / per;
+        const long long waves = ((long long)rb * nch + num_sms - 1) / num_sms;
+        const long long cost = waves * (per + 6);
+        if (best < 0 || cost < best) { best = cost; best_per = per; best_chunks = nch; }
+        if (per <= 8) break;
+    }
+    *per_out = best_per;
+    *chunks_out = best_chunks;
 }
 
 // ---- triangular solves with the factors (blocked TRSV) --------------------------------------------------
@@ -545,23 +619,93 @@ __global__ void __launch_bounds__(256) lu_trsv_update_kernel(const double* __res
     x[r] -= acc;
 }
 
-__global__ void lu_permute_kernel(const double* __restrict__ b, const int* __restrict__ piv, int n, double* __restrict__ x) {
-    // sequential interchanges (linalg.f90:311-316 "untangle pivoting"); n is small next to the factorisation
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        for (int i = 0; i < n; ++i) x[i] = b[i];
-        for (int i = 0; i < n; ++i) {
-            int p = piv[i];
-            if (p != i) {
-                double t = x[p];
-                x[p] = x[i];
-                x[i] = t;
-            }
+// x = P b: the interchanges of the factorisation (linalg.f90:311-316 "untangle pivoting") composed into one gather
+__global__ void lu_permute_kernel(const double* __restrict__ b, const int* __restrict__ perm, int n, double* __restrict__ x) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = b[perm[i]];
+}
+
+// One step of the blocked forward substitution in ONE launch: x[k0..k1) is final; every row below gets
+// x[r] -= L(r, k0..k1) . x[k0..k1), and the CTA that holds the next diagonal block solves it straight away (unit lower
+// triangular, one warp, column order), so a step costs one launch instead of two.  Same operation order per element
+// as lu_trsv_update_kernel followed by lu_trsv_diag_kernel.
+__global__ void __launch_bounds__(256) lu_fwd_step_kernel(const double* __restrict__ A, int ld, int n, int k0, int k1, double* __restrict__ x) {
+    __shared__ double sx[LU_NB];
+    __shared__ double sy[LU_NB];
+    __shared__ double sL[LU_NB * LU_NB];
+    const int nb = k1 - k0, tid = threadIdx.x;
+    if (tid < nb) sx[tid] = x[k0 + tid];
+    __syncthreads();
+    const int r = k1 + blockIdx.x * 256 + tid;
+    double xr = 0.;
+    if (r < n) {
+        double acc = 0.;
+        for (int c = 0; c < nb; ++c) acc = fma(A[r + (size_t)(k0 + c) * ld], sx[c], acc);
+        xr = x[r] - acc;
+        if (blockIdx.x != 0 || tid >= LU_NB) x[r] = xr;
+    }
+    if (blockIdx.x != 0) return;
+    const int nb2 = min(LU_NB, n - k1);
+    if (tid < nb2) sy[tid] = xr;
+    for (int t = tid; t < nb2 * nb2; t += 256) {
+        const int rr = t % nb2, cc = t / nb2;
+        sL[cc * LU_NB + rr] = A[(k1 + rr) + (size_t)(k1 + cc) * ld];
+    }
+    __syncthreads();
+    if (tid < 32) {
+        for (int c = 0; c < nb2; ++c) {
+            const double xc = sy[c];
+            if (tid > c && tid < nb2) sy[tid] = fma(-sL[c * LU_NB + tid], xc, sy[tid]);
+            if (tid + 32 > c && tid + 32 < nb2) sy[tid + 32] = fma(-sL[c * LU_NB + tid + 32], xc, sy[tid + 32]);
+            __syncwarp();
         }
     }
+    __syncthreads();
+    if (tid < nb2) x[k1 + tid] = sy[tid];
+}
+
+// One step of the blocked back substitution: x[k0..k1) is final; rows above get x[r] -= U(r, k0..k1) . x[k0..k1), and the
+// CTA holding the diagonal block just above (rows k0-64..k0) solves it (upper triangular, divisions by the diagonal).
+__global__ void __launch_bounds__(256) lu_bwd_step_kernel(const double* __restrict__ A, int ld, int k0, int k1, double* __restrict__ x) {
+    __shared__ double sx[LU_NB];
+    __shared__ double sy[LU_NB];
+    __shared__ double sU[LU_NB * LU_NB];
+    const int nb = k1 - k0, tid = threadIdx.x;
+    if (tid < nb) sx[tid] = x[k0 + tid];
+    __syncthreads();
+    // CTA 0 covers rows [k0-256, k0) with its first 64 threads on the block just above the solved one
+    const int r = k0 - 1 - (blockIdx.x * 256 + tid);
+    double xr = 0.;
+    if (r >= 0) {
+        double acc = 0.;
+        for (int c = 0; c < nb; ++c) acc = fma(A[r + (size_t)(k0 + c) * ld], sx[c], acc);
+        xr = x[r] - acc;
+        if (blockIdx.x != 0 || tid >= LU_NB) x[r] = xr;
+    }
+    if (blockIdx.x != 0) return;
+    const int b0 = k0 - LU_NB;   // k0 is a multiple of LU_NB and > 0
+    if (tid < LU_NB) sy[LU_NB - 1 - tid] = xr;   // thread t holds row k0-1-t
+    for (int t = tid; t < LU_NB * LU_NB; t += 256) {
+        const int rr = t % LU_NB, cc = t / LU_NB;
+        sU[cc * LU_NB + rr] = A[(b0 + rr) + (size_t)(b0 + cc) * ld];
+    }
+    __syncthreads();
+    if (tid < 32) {
+        for (int c = LU_NB - 1; c >= 0; --c) {
+            if (tid == (c & 31)) sy[c] = sy[c] / sU[c * LU_NB + c];
+            __syncwarp();
+            const double xc = sy[c];
+            if (tid < c) sy[tid] = fma(-sU[c * LU_NB + tid], xc, sy[tid]);
+            if (tid + 32 < c) sy[tid + 32] = fma(-sU[c * LU_NB + tid + 32], xc, sy[tid + 32]);
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    if (tid < LU_NB) x[b0 + tid] = sy[tid];
 }
 
 static size_t lu_panel_smem(int rpc) {
-    return (size_t)(LU_NB * (rpc | 1) + LU_NB + LU_NB + 1 + 2 * rpc + 8) * sizeof(double) + 16 * sizeof(int);
+    return (size_t)(LU_NB * (rpc | 1) + 2 * LUP_ROW + 2 * rpc + 8) * sizeof(double) + (size_t)(16 + rpc) * sizeof(int);
 }
 
 // ---- host drivers ---------------------------------------------------------------------------------------
@@ -576,8 +720,11 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
         attr_set = true;
     }
     ML_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
-    lu_row_scale_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(dA, ld, n, d_vv, d_flag);
-    c->launches += 1;
+    int* d_perm = d_piv + n;   // d_piv holds 2 n ints: the interchanges, then the row permutation they compose to
+    ML_CUDA(c, cudaMemsetAsync(d_vv, 0, (size_t)n * sizeof(double), c->stream));
+    lu_row_amax_kernel<<<dim3((n + 127) / 128, (n + RS_COLS - 1) / RS_COLS), 128, 0, c->stream>>>(dA, ld, n, (unsigned long long*)d_vv);
+    lu_row_scale_finish_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_vv, n, d_flag, d_perm);
+    c->launches += 2;
     int flag = 0;
     ML_CUDA(c, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -587,11 +734,12 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     DevBuf<double> pscr;
     DevBuf<int> pidx;
     DevBuf<unsigned> pbar;
-    ML_CUDA(c, pscr.alloc((size_t)2 * gmax * (LU_NB + 1) + 2 * (LU_NB + 1)));
+    ML_CUDA(c, pscr.alloc((size_t)2 * gmax * (LUP_ROW + 1) + 2 * LUP_ROW));
     ML_CUDA(c, pidx.alloc((size_t)2 * gmax));
     ML_CUDA(c, pbar.alloc(1));
     ML_CUDA(c, cudaMemsetAsync(pbar.p, 0, sizeof(unsigned), c->stream));
     unsigned bar_base = 0;
+    bool all_coop = true;
     static const bool per_column = getenv("MACHLINE_LU_PER_COLUMN") != nullptr;   // the unfused paths, kept for A/B timing
     static const bool old_gemm = getenv("MACHLINE_LU_GEMM_V1") != nullptr;
     for (int k0 = 0; k0 < n; k0 += LU_NB) {
@@ -602,10 +750,10 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
         if (!per_column && rpc <= LUP_CAP) {
             LuPanelArgs pa;
             pa.A = dA; pa.ld = ld; pa.n = n; pa.k0 = k0; pa.k1 = k1; pa.rpc = rpc;
-            pa.vv = d_vv; pa.piv = d_piv;
+            pa.vv = d_vv; pa.piv = d_piv; pa.perm = d_perm;
             pa.cand_v = pscr.p;
             pa.cand_row = pscr.p + 2 * gmax;
-            pa.rowj = pa.cand_row + (size_t)2 * gmax * LU_NB;
+            pa.rowj = pa.cand_row + (size_t)2 * gmax * LUP_ROW;
             pa.cand_i = pidx.p;
             pa.bar = pbar.p; pa.bar_base = bar_base;
             const int G = (m + rpc - 1) / rpc;
@@ -615,6 +763,7 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
             ML_CUDA(c, cudaLaunchCooperativeKernel((const void*)lu_panel_coop_kernel, dim3(G), dim3(LUP_THREADS), kargs, smem, c->stream));
             c->launches += 1;
         } else {
+            all_coop = false;
             for (int j = k0; j < k1; ++j) {
                 lu_pivot_kernel<<<1, 1024, 0, c->stream>>>(dA, ld, n, j, k0, k1, d_vv, d_piv);
                 if (j + 1 < n) lu_panel_update_kernel<<<(n - j - 1 + 255) / 256, 256, 0, c->stream>>>(dA, ld, n, j, k1);
@@ -629,11 +778,11 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
             if (k1 - k0 == LU_NB) {
                 const int rb = (n - k1 + GM_BM - 1) / GM_BM, ctiles = (n - k1 + GM_BN - 1) / GM_BN;
                 if (!old_gemm && (ld & 1) == 0) {
-                    // enough CTAs for ~2 waves of one CTA per SM; each walks over a run of column tiles
-                    const int chunks = std::max(1, std::min(ctiles, (2 * c->num_sms + rb - 1) / rb));
-                    const int per = (ctiles + chunks - 1) / chunks;
-                    dim3 grid(rb, (ctiles + per - 1) / per);
-                    lu_gemm2_kernel<<<grid, G2_THREADS, G2_SMEM, c->stream>>>(dA, ld, n, k0, k1, ctiles, per);
+                    const int ct32 = (n - k1 + G2_BN - 1) / G2_BN;
+                    int per, chunks;
+                    lu_gemm2_shape(rb, ct32, c->num_sms, &per, &chunks);
+                    dim3 grid(rb, chunks);
+                    lu_gemm2_kernel<<<grid, G2_THREADS, G2_SMEM, c->stream>>>(dA, ld, n, k0, k1, ct32, per);
                 } else {
                     dim3 grid(rb, ctiles);
                     lu_gemm_dmma_kernel<<<grid, 256, gemm_smem, c->stream>>>(dA, ld, n, k0, k1);
@@ -643,34 +792,36 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
         }
         ML_CUDA(c, cudaGetLastError());
     }
+    if (!all_coop) {
+        lu_perm_from_piv_kernel<<<1, 32, 0, c->stream>>>(d_piv, n, d_perm);
+        c->launches += 1;
+    }
     pscr.release();
     pidx.release();
     pbar.release();
     return ML_OK;
 }
 
-// x = U^{-1} L^{-1} P b with the factors in dA
+// x = U^{-1} L^{-1} P b with the factors in dA; d_piv holds the interchanges and, after them, the permutation
 static ml_status lu_substitute(Ctx* c, const double* dA, int ld, int n, const int* d_piv, const double* d_b, double* d_x) {
-    lu_permute_kernel<<<1, 32, 0, c->stream>>>(d_b, d_piv, n, d_x);
-    c->launches += 1;
-    for (int k0 = 0; k0 < n; k0 += LU_NB) {
-        const int k1 = std::min(k0 + LU_NB, n);
-        lu_trsv_diag_kernel<<<1, 64, 0, c->stream>>>(dA, ld, k0, k1, d_x, 0);
+    lu_permute_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_b, d_piv + n, n, d_x);
+    lu_trsv_diag_kernel<<<1, 64, 0, c->stream>>>(dA, ld, 0, std::min(LU_NB, n), d_x, 0);
+    c->launches += 2;
+    for (int k0 = 0; k0 + LU_NB < n; k0 += LU_NB) {
+        const int k1 = k0 + LU_NB;
+        lu_fwd_step_kernel<<<(n - k1 + 255) / 256, 256, 0, c->stream>>>(dA, ld, n, k0, k1, d_x);
         c->launches += 1;
-        if (k1 < n) {
-            lu_trsv_update_kernel<<<(n - k1 + 255) / 256, 256, 0, c->stream>>>(dA, ld, k1, n, k0, k1, d_x);
-            c->launches += 1;
-        }
     }
     const int nblk = (n + LU_NB - 1) / LU_NB;
-    for (int b = nblk - 1; b >= 0; --b) {
-        const int k0 = b * LU_NB, k1 = std::min(k0 + LU_NB, n);
-        lu_trsv_diag_kernel<<<1, 64, 0, c->stream>>>(dA, ld, k0, k1, d_x, 1);
+    {
+        const int k0 = (nblk - 1) * LU_NB;
+        lu_trsv_diag_kernel<<<1, 64, 0, c->stream>>>(dA, ld, k0, n, d_x, 1);
         c->launches += 1;
-        if (k0 > 0) {
-            lu_trsv_update_kernel<<<(k0 + 255) / 256, 256, 0, c->stream>>>(dA, ld, 0, k0, k0, k1, d_x);
-            c->launches += 1;
-        }
+    }
+    for (int b = nblk - 1; b >= 1; --b) {
+        const int k0 = b * LU_NB, k1 = std::min(k0 + LU_NB, n);
+        lu_bwd_step_kernel<<<(k0 + 255) / 256, 256, 0, c->stream>>>(dA, ld, k0, k1, d_x);
+        c->launches += 1;
     }
     ML_CUDA(c, cudaGetLastError());
     return ML_OK;
@@ -680,7 +831,7 @@ static ml_status lu_substitute(Ctx* c, const double* dA, int ld, int n, const in
 ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, double* d_x) {
     DevBuf<int> piv, flag;
     DevBuf<double> vv;
-    ML_CUDA(c, piv.alloc(N));
+    ML_CUDA(c, piv.alloc(2 * (size_t)N));
     ML_CUDA(c, flag.alloc(1));
     ML_CUDA(c, vv.alloc(N));
     ml_status st = lu_factor(c, dA, ld, N, piv.p, vv.p, flag.p);
@@ -780,7 +931,7 @@ ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const dou
         be[i] = (i == N_blocks - 1) ? N : (i + 1) * block_size;
         const int nb = be[i] - bs[i];
         bld[i] = ((nb + 63) / 64) * 64;
-        if (blocks[i].alloc((size_t)bld[i] * nb) != cudaSuccess || pivs[i].alloc(nb) != cudaSuccess || vv.alloc(nb) != cudaSuccess) {
+        if (blocks[i].alloc((size_t)bld[i] * nb) != cudaSuccess || pivs[i].alloc(2 * (size_t)nb) != cudaSuccess || vv.alloc(nb) != cudaSuccess) {
             cleanup();
             return c->fail(ML_CUDA_ERROR, "block Jacobi: out of device memory");
         }
@@ -858,7 +1009,7 @@ ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const doubl
         be[i] = (i == N_blocks - 1) ? N : (i + 1) * block_size;
         const int nb = be[i] - bs[i];
         bld[i] = ((nb + 63) / 64) * 64;
-        if (blocks[i].alloc((size_t)bld[i] * nb) != cudaSuccess || pivs[i].alloc(nb) != cudaSuccess || vv.alloc(nb) != cudaSuccess) {
+        if (blocks[i].alloc((size_t)bld[i] * nb) != cudaSuccess || pivs[i].alloc(2 * (size_t)nb) != cudaSuccess || vv.alloc(nb) != cudaSuccess) {
             cleanup();
             return c->fail(ML_CUDA_ERROR, "block SSOR: out of device memory");
         }

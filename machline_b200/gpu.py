@@ -54,6 +54,7 @@ def lib() -> C.CDLL:
                                      C.POINTER(_abi.MlSolveInfo)]
         L.ml_device_system.argtypes = [vp, C.POINTER(dp), ip, ip, ip]
         L.ml_measure_peaks.argtypes = [vp, dp, dp]
+        L.ml_measure_dmma_peak.argtypes = [vp, dp]
         L.ml_device_stream.argtypes = [vp, C.POINTER(vp)]
         L.ml_nccl_unique_id.argtypes = [C.c_void_p]
         L.ml_set_profiling.argtypes = [vp, C.c_int]
@@ -174,6 +175,12 @@ class Context:
         f, h = C.c_double(), C.c_double()
         self._check(lib().ml_measure_peaks(self._h, C.byref(f), C.byref(h) if hbm else None))
         return f.value, h.value
+
+    def measure_dmma_peak(self) -> float:
+        """FP64 tensor-pipe (DMMA) TFLOP/s measured on this device."""
+        f = C.c_double()
+        self._check(lib().ml_measure_dmma_peak(self._h, C.byref(f)))
+        return f.value
 
     def close(self):
         if self._h:
