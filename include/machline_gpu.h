@@ -159,6 +159,9 @@ ml_status ml_assemble(ml_ctx *ctx, double *I_known_out);
 /* Copy rows [row0,row0+nrows) (global row ids inside this context's shard) of A to a host
    column-major array with leading dimension ld (parity channel = write_A_and_b). */
 ml_status ml_get_A(ml_ctx *ctx, int row0, int nrows, double *dst_colmajor, int ld);
+/* The inverse channel: overwrite rows [row0,row0+nrows) of the resident system from a host column-major array (a system
+   assembled elsewhere, or a test matrix, solved through ml_solve on the row shards). */
+ml_status ml_set_A(ml_ctx *ctx, int row0, int nrows, const double *src_colmajor, int ld);
 /* Pair count of the last ml_assemble on this context: local rows x (body records + wake records). */
 long long ml_pair_count(const ml_ctx *ctx);
 

@@ -562,6 +562,18 @@ extern "C" ml_status ml_get_A(ml_ctx* c, int row0, int nrows, double* dst, int l
     return ML_OK;
 }
 
+extern "C" ml_status ml_set_A(ml_ctx* c, int row0, int nrows, const double* src, int ld) {
+    if (!c || !src || nrows < 0 || ld < nrows) return ML_BAD_ARGUMENT;
+    if (!c->assembled) return c->fail(ML_NOT_READY, "ml_set_A before ml_assemble");
+    int lr = row0 - c->row0;
+    if (lr < 0 || lr + nrows > c->n_rows) return c->fail(ML_BAD_ARGUMENT, "rows outside this context's shard");
+    ML_CUDA(c, cudaSetDevice(c->device));
+    ML_CUDA(c, cudaMemcpy2DAsync(c->d_A.p + lr, (size_t)c->ld * sizeof(double), src, (size_t)ld * sizeof(double),
+                                 (size_t)nrows * sizeof(double), c->n_cols, cudaMemcpyHostToDevice, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ML_OK;
+}
+
 extern "C" ml_status ml_device_system(ml_ctx* c, double** A_dev, int* ld, int* nrows_local, int* ncols) {
     if (!c) return ML_BAD_ARGUMENT;
     if (!c->assembled) return c->fail(ML_NOT_READY, "system not assembled");

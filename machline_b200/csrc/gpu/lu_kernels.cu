@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "ctx.h"
@@ -23,10 +24,10 @@ constexpr int LU_NB = 64;
 // amax(i) = max_j |A(i,j)| over a 2-D grid (rows x column chunks); non-negative doubles order like their bit patterns, so
 // the chunks combine with an integer atomicMax.  amax must be zeroed before the launch.
 constexpr int RS_COLS = 128;
-__global__ void __launch_bounds__(128) lu_row_amax_kernel(const double* __restrict__ A, int ld, int n, unsigned long long* __restrict__ amax) {
+__global__ void __launch_bounds__(128) lu_row_amax_kernel(const double* __restrict__ A, int ld, int nr, int nc, unsigned long long* __restrict__ amax) {
     const int i = blockIdx.x * 128 + threadIdx.x;
-    if (i >= n) return;
-    const int j0 = blockIdx.y * RS_COLS, j1 = min(j0 + RS_COLS, n);
+    if (i >= nr) return;
+    const int j0 = blockIdx.y * RS_COLS, j1 = min(j0 + RS_COLS, nc);
     double m = 0.;
 #pragma unroll 8
     for (int j = j0; j < j1; ++j) m = fmax(m, fabs(A[i + (size_t)j * ld]));
@@ -357,16 +358,17 @@ __global__ void __launch_bounds__(256) lu_laswp_kernel(double* __restrict__ A, i
 // Only full panels reach this kernel (a short last panel has nothing to its right).  Both loops are unrolled so the
 // column lives in registers; the column-oriented order (x[r] -= L[r][k] x[k] for all r > k) exposes 63..1 independent
 // FMAs per step, and every L[r][k] is a shared-memory broadcast.
-__global__ void __launch_bounds__(64) lu_trsm_kernel(double* __restrict__ A, int ld, int n, int k0, int k1) {
+__global__ void __launch_bounds__(64) lu_trsm_kernel(const double* __restrict__ L, int ldl, double* __restrict__ X, int ldx, int ncols) {
+    // L: the 64 x 64 diagonal block (unit lower part used); X: 64 x ncols right-hand sides, overwritten by L^{-1} X
     __shared__ double sL[LU_NB * LU_NB];   // sL[k * LU_NB + r] = L(r, k): column-major, conflict-free fill
     for (int t = threadIdx.x; t < LU_NB * LU_NB; t += 64) {
         const int r = t % LU_NB, k = t / LU_NB;
-        sL[t] = A[(k0 + r) + (size_t)(k0 + k) * ld];
+        sL[t] = L[r + (size_t)k * ldl];
     }
     __syncthreads();
-    const int c = k1 + blockIdx.x * 64 + threadIdx.x;
-    if (c >= n) return;
-    double* col = A + (size_t)c * ld + k0;
+    const int c = blockIdx.x * 64 + threadIdx.x;
+    if (c >= ncols) return;
+    double* col = X + (size_t)c * ldx;
     double x[LU_NB];
 #pragma unroll
     for (int r = 0; r < LU_NB; r += 2) {
@@ -471,13 +473,18 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
-__global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restrict__ A, int ld, int n, int k0, int k1, int n_col_tiles,
-                                                                 int tiles_per_cta) {
+__global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(const double* __restrict__ Lp, int ldl, const double* __restrict__ Up, int ldu,
+                                                                 double* __restrict__ Cp, int ldc, int M, int Nc, int n_col_tiles,
+                                                                 int tiles_per_cta, const unsigned char* __restrict__ row_block_active) {
+    // C (M x Nc, ldc) -= L (M x 64, ldl) * U (64 x Nc, ldu).  Single GPU: the three are windows of the same matrix; the
+    // distributed factorisation passes the gathered multipliers of the local rows and the broadcast U12 block row, and
+    // a byte per 128-row block that says whether any of its rows is still below the panel.
     extern __shared__ __align__(16) double smem[];
+    if (row_block_active && !row_block_active[blockIdx.x]) return;
     double* sA = smem;                  // [GM_K][GM_SA]   L21 (negated when the fragments are read)
     const int tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127, warp = gtid >> 5, lane = tid & 31;
     double* sB = smem + GM_K * GM_SA + grp * (2 * G2_BN * GM_SB);   // this group's [2][G2_BN][GM_SB] U12 tiles
-    const int row0 = k1 + blockIdx.x * GM_BM;
+    const int row0 = blockIdx.x * GM_BM;
     const int ct0 = blockIdx.y * tiles_per_cta + grp, ct1 = min((int)(blockIdx.y + 1) * tiles_per_cta, n_col_tiles);
     const int wm = warp * 32;
     const int g = lane >> 2, q = lane & 3;
@@ -485,7 +492,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restr
     for (int t = tid; t < GM_K * (GM_BM / 2); t += G2_THREADS) {
         const int k = t / (GM_BM / 2), m2 = (t % (GM_BM / 2)) * 2;
         const int r = row0 + m2;
-        cp_async16(sA + k * GM_SA + m2, A + (size_t)(k0 + k) * ld + min(r, n - 1), r < n);
+        cp_async16(sA + k * GM_SA + m2, Lp + (size_t)k * ldl + min(r, M - 1), r < M);
     }
     cp_async_commit();
     cp_async_wait<0>();
@@ -493,24 +500,24 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restr
     if (ct0 >= ct1) return;
     auto load_u = [&](int buf, int ct) {
         double* dst = sB + buf * (G2_BN * GM_SB);
-        const int col0 = k1 + ct * G2_BN;
+        const int col0 = ct * G2_BN;
         for (int t = gtid; t < G2_BN * (GM_K / 2); t += 128) {
             const int nn = t / (GM_K / 2), k2 = (t % (GM_K / 2)) * 2;
             const int c = col0 + nn;
-            cp_async16(dst + nn * GM_SB + k2, A + (size_t)min(c, n - 1) * ld + k0 + k2, c < n);
+            cp_async16(dst + nn * GM_SB + k2, Up + (size_t)min(c, Nc - 1) * ldu + k2, c < Nc);
         }
     };
     double cn[4][4][2];
     auto load_c = [&](int ct) {
-        const int col0 = k1 + ct * G2_BN;
+        const int col0 = ct * G2_BN;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int r = row0 + wm + mt * 8 + g;
                 const int cc = col0 + nt * 8 + 2 * q;
-                cn[mt][nt][0] = (r < n && cc < n) ? __ldcs(A + r + (size_t)cc * ld) : 0.;
-                cn[mt][nt][1] = (r < n && cc + 1 < n) ? __ldcs(A + r + (size_t)(cc + 1) * ld) : 0.;
+                cn[mt][nt][0] = (r < M && cc < Nc) ? __ldcs(Cp + r + (size_t)cc * ldc) : 0.;
+                cn[mt][nt][1] = (r < M && cc + 1 < Nc) ? __ldcs(Cp + r + (size_t)(cc + 1) * ldc) : 0.;
             }
     };
     load_u(0, ct0);
@@ -548,15 +555,15 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(double* __restr
 #pragma unroll
                 for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(c[mt][nt][0], c[mt][nt][1], a[mt], b[nt]);
         }
-        const int col0 = k1 + ct * G2_BN;
+        const int col0 = ct * G2_BN;
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt) {
                 const int r = row0 + wm + mt * 8 + g;
                 const int cc = col0 + nt * 8 + 2 * q;
-                if (r < n && cc < n) A[r + (size_t)cc * ld] = c[mt][nt][0];
-                if (r < n && cc + 1 < n) A[r + (size_t)(cc + 1) * ld] = c[mt][nt][1];
+                if (r < M && cc < Nc) Cp[r + (size_t)cc * ldc] = c[mt][nt][0];
+                if (r < M && cc + 1 < Nc) Cp[r + (size_t)(cc + 1) * ldc] = c[mt][nt][1];
             }
         group_sync(1 + grp);   // every warp of the group is done with sB[buf] before the next iteration refills it
     }
@@ -704,8 +711,84 @@ __global__ void __launch_bounds__(256) lu_bwd_step_kernel(const double* __restri
     if (tid < LU_NB) x[b0 + tid] = sy[tid];
 }
 
+// C (M x Nc) -= L (M x 64) * U (64 x Nc) on the FP64 tensor cores; all leading dimensions even, pointers 16-byte aligned
+void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ldu, double* Cp, int ldc, int M, int Nc,
+                     const unsigned char* row_block_active) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(lu_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
+        attr_set = true;
+    }
+    const int rb = (M + GM_BM - 1) / GM_BM, ct32 = (Nc + G2_BN - 1) / G2_BN;
+    int per, chunks;
+    lu_gemm2_shape(rb, ct32, c->num_sms, &per, &chunks);
+    lu_gemm2_kernel<<<dim3(rb, chunks), G2_THREADS, G2_SMEM, c->stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
+    c->launches += 1;
+}
+
 static size_t lu_panel_smem(int rpc) {
     return (size_t)(LU_NB * (rpc | 1) + 2 * LUP_ROW + 2 * rpc + 8) * sizeof(double) + (size_t)(16 + rpc) * sizeof(int);
+}
+
+// Scratch of the cooperative panel kernel (candidate slots for up to num_sms CTAs, two parities) and its barrier.
+struct LuPanelWork {
+    DevBuf<double> pscr;
+    DevBuf<int> pidx;
+    DevBuf<unsigned> pbar;
+    unsigned bar_base = 0;
+    bool all_coop = true;   // every panel so far went through the cooperative kernel (which maintains perm)
+    int gmax = 0;
+    ml_status init(Ctx* c) {
+        static bool attr_set = false;
+        if (!attr_set) {
+            ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel_smem(LUP_CAP)));
+            attr_set = true;
+        }
+        gmax = c->num_sms;
+        ML_CUDA(c, pscr.alloc((size_t)2 * gmax * (LUP_ROW + 1) + 2 * LUP_ROW));
+        ML_CUDA(c, pidx.alloc((size_t)2 * gmax));
+        ML_CUDA(c, pbar.alloc(1));
+        ML_CUDA(c, cudaMemsetAsync(pbar.p, 0, sizeof(unsigned), c->stream));
+        bar_base = 0;
+        return ML_OK;
+    }
+    void release() {
+        pscr.release();
+        pidx.release();
+        pbar.release();
+    }
+};
+
+// Factor the panel (rows k0..n, columns k0..k1 of dA): pivots into d_piv[k0..k1), rows interchanged inside the panel.
+// One cooperative launch when the panel's rows fit the CTAs' shared memory, else two launches per column.
+static ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int n, int k0, int k1, double* d_vv, int* d_piv, int* d_perm) {
+    static const bool per_column = getenv("MACHLINE_LU_PER_COLUMN") != nullptr;   // the unfused path, kept for A/B timing
+    const int m = n - k0;
+    int rpc = 128;
+    if ((long long)rpc * W.gmax < m) rpc = (((m + W.gmax - 1) / W.gmax) + 31) & ~31;
+    if (!per_column && rpc <= LUP_CAP) {
+        LuPanelArgs pa;
+        pa.A = dA; pa.ld = ld; pa.n = n; pa.k0 = k0; pa.k1 = k1; pa.rpc = rpc;
+        pa.vv = d_vv; pa.piv = d_piv; pa.perm = d_perm;
+        pa.cand_v = W.pscr.p;
+        pa.cand_row = W.pscr.p + 2 * W.gmax;
+        pa.rowj = pa.cand_row + (size_t)2 * W.gmax * LUP_ROW;
+        pa.cand_i = W.pidx.p;
+        pa.bar = W.pbar.p; pa.bar_base = W.bar_base;
+        const int G = (m + rpc - 1) / rpc;
+        W.bar_base += (unsigned)(k1 - k0) * (unsigned)G;
+        void* kargs[] = {(void*)&pa};
+        ML_CUDA(c, cudaLaunchCooperativeKernel((const void*)lu_panel_coop_kernel, dim3(G), dim3(LUP_THREADS), kargs, lu_panel_smem(rpc), c->stream));
+        c->launches += 1;
+    } else {
+        W.all_coop = false;
+        for (int j = k0; j < k1; ++j) {
+            lu_pivot_kernel<<<1, 1024, 0, c->stream>>>(dA, ld, n, j, k0, k1, d_vv, d_piv);
+            if (j + 1 < n) lu_panel_update_kernel<<<(n - j - 1 + 255) / 256, 256, 0, c->stream>>>(dA, ld, n, j, k1);
+            c->launches += 2;
+        }
+    }
+    return ML_OK;
 }
 
 // ---- host drivers ---------------------------------------------------------------------------------------
@@ -715,90 +798,50 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     const size_t gemm_smem = (size_t)(GM_K * GM_SA + GM_BN * GM_SB) * sizeof(double);
     if (!attr_set) {
         ML_CUDA(c, cudaFuncSetAttribute(lu_gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-        ML_CUDA(c, cudaFuncSetAttribute(lu_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM));
-        ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel_smem(LUP_CAP)));
         attr_set = true;
     }
     ML_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
     int* d_perm = d_piv + n;   // d_piv holds 2 n ints: the interchanges, then the row permutation they compose to
     ML_CUDA(c, cudaMemsetAsync(d_vv, 0, (size_t)n * sizeof(double), c->stream));
-    lu_row_amax_kernel<<<dim3((n + 127) / 128, (n + RS_COLS - 1) / RS_COLS), 128, 0, c->stream>>>(dA, ld, n, (unsigned long long*)d_vv);
+    lu_row_amax_kernel<<<dim3((n + 127) / 128, (n + RS_COLS - 1) / RS_COLS), 128, 0, c->stream>>>(dA, ld, n, n, (unsigned long long*)d_vv);
     lu_row_scale_finish_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(d_vv, n, d_flag, d_perm);
     c->launches += 2;
     int flag = 0;
     ML_CUDA(c, cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
     if (flag) return c->fail(ML_SINGULAR, "lu_decomp: the matrix is singular (a row is zero; linalg.f90:205-208)");
-    // scratch of the cooperative panel kernel: candidate slots for up to num_sms CTAs, two parities
-    const int gmax = c->num_sms;
-    DevBuf<double> pscr;
-    DevBuf<int> pidx;
-    DevBuf<unsigned> pbar;
-    ML_CUDA(c, pscr.alloc((size_t)2 * gmax * (LUP_ROW + 1) + 2 * LUP_ROW));
-    ML_CUDA(c, pidx.alloc((size_t)2 * gmax));
-    ML_CUDA(c, pbar.alloc(1));
-    ML_CUDA(c, cudaMemsetAsync(pbar.p, 0, sizeof(unsigned), c->stream));
-    unsigned bar_base = 0;
-    bool all_coop = true;
-    static const bool per_column = getenv("MACHLINE_LU_PER_COLUMN") != nullptr;   // the unfused paths, kept for A/B timing
+    LuPanelWork PW;
+    ml_status pst = PW.init(c);
+    if (pst != ML_OK) return pst;
     static const bool old_gemm = getenv("MACHLINE_LU_GEMM_V1") != nullptr;
     for (int k0 = 0; k0 < n; k0 += LU_NB) {
         const int k1 = std::min(k0 + LU_NB, n);
-        const int m = n - k0;
-        int rpc = 128;
-        if ((long long)rpc * gmax < m) rpc = (((m + gmax - 1) / gmax) + 31) & ~31;
-        if (!per_column && rpc <= LUP_CAP) {
-            LuPanelArgs pa;
-            pa.A = dA; pa.ld = ld; pa.n = n; pa.k0 = k0; pa.k1 = k1; pa.rpc = rpc;
-            pa.vv = d_vv; pa.piv = d_piv; pa.perm = d_perm;
-            pa.cand_v = pscr.p;
-            pa.cand_row = pscr.p + 2 * gmax;
-            pa.rowj = pa.cand_row + (size_t)2 * gmax * LUP_ROW;
-            pa.cand_i = pidx.p;
-            pa.bar = pbar.p; pa.bar_base = bar_base;
-            const int G = (m + rpc - 1) / rpc;
-            bar_base += (unsigned)(k1 - k0) * (unsigned)G;
-            const size_t smem = lu_panel_smem(rpc);
-            void* kargs[] = {(void*)&pa};
-            ML_CUDA(c, cudaLaunchCooperativeKernel((const void*)lu_panel_coop_kernel, dim3(G), dim3(LUP_THREADS), kargs, smem, c->stream));
-            c->launches += 1;
-        } else {
-            all_coop = false;
-            for (int j = k0; j < k1; ++j) {
-                lu_pivot_kernel<<<1, 1024, 0, c->stream>>>(dA, ld, n, j, k0, k1, d_vv, d_piv);
-                if (j + 1 < n) lu_panel_update_kernel<<<(n - j - 1 + 255) / 256, 256, 0, c->stream>>>(dA, ld, n, j, k1);
-                c->launches += 2;
-            }
-        }
+        pst = lu_panel_factor(c, PW, dA, ld, n, k0, k1, d_vv, d_piv, d_perm);
+        if (pst != ML_OK) { PW.release(); return pst; }
         lu_laswp_kernel<<<(n - (k1 - k0) + 255) / 256 + 1, 256, 0, c->stream>>>(dA, ld, n, k0, k1, d_piv);
         c->launches += 1;
         if (k1 < n) {
-            lu_trsm_kernel<<<(n - k1 + 63) / 64, 64, 0, c->stream>>>(dA, ld, n, k0, k1);
+            lu_trsm_kernel<<<(n - k1 + 63) / 64, 64, 0, c->stream>>>(dA + k0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)k1 * ld, ld, n - k1);
             c->launches += 1;
             if (k1 - k0 == LU_NB) {
                 const int rb = (n - k1 + GM_BM - 1) / GM_BM, ctiles = (n - k1 + GM_BN - 1) / GM_BN;
                 if (!old_gemm && (ld & 1) == 0) {
-                    const int ct32 = (n - k1 + G2_BN - 1) / G2_BN;
-                    int per, chunks;
-                    lu_gemm2_shape(rb, ct32, c->num_sms, &per, &chunks);
-                    dim3 grid(rb, chunks);
-                    lu_gemm2_kernel<<<grid, G2_THREADS, G2_SMEM, c->stream>>>(dA, ld, n, k0, k1, ct32, per);
+                    lu_gemm2_launch(c, dA + k1 + (size_t)k0 * ld, ld, dA + k0 + (size_t)k1 * ld, ld, dA + k1 + (size_t)k1 * ld, ld, n - k1, n - k1,
+                                    nullptr);
                 } else {
                     dim3 grid(rb, ctiles);
                     lu_gemm_dmma_kernel<<<grid, 256, gemm_smem, c->stream>>>(dA, ld, n, k0, k1);
+                    c->launches += 1;
                 }
-                c->launches += 1;
             }
         }
         ML_CUDA(c, cudaGetLastError());
     }
-    if (!all_coop) {
+    if (!PW.all_coop) {
         lu_perm_from_piv_kernel<<<1, 32, 0, c->stream>>>(d_piv, n, d_perm);
         c->launches += 1;
     }
-    pscr.release();
-    pidx.release();
-    pbar.release();
+    PW.release();
     return ML_OK;
 }
 
@@ -845,6 +888,278 @@ ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, 
     vv.release();
     return st;
 }
+
+// ---- LU of a row-sharded matrix (NCCL over NVLink) ---------------------------------------------------
+// Every rank keeps the rows it assembled (n_rows x N, column-major) for the whole factorisation: rows never move
+// between GPUs.  The reference's row interchanges act on POSITIONS; perm[pos] = slot (rank * S + local row) of the
+// row currently at position pos is replicated on every rank and is the only thing an interchange changes.
+// Per panel of 64 columns:
+//   1. ncclAllGather of the panel's columns (local rows x 64) -> every rank has the whole panel; a gather kernel puts
+//      it into position order;
+//   2. every rank factors the panel redundantly with the same cooperative kernel as the single-GPU path (identical
+//      inputs -> identical pivots and multipliers everywhere; no pivot broadcast, no per-column collective);
+//   3. the 64 pivot rows' trailing entries are packed by their owners into a zero-filled 64 x W block and summed with
+//      ncclAllReduce (each entry has exactly one non-zero contributor) -> U-row block on every rank; TRSM with the
+//      panel's diagonal block, redundantly; owners store their rows back;
+//   4. each rank updates the rows it owns that are still below the panel: C -= L21(local) * U12 on the FP64 tensor
+//      cores (blocks of 128 local rows without such a row are skipped).
+// The right-hand side travels as column N of the local matrix, so forward elimination costs nothing extra and L is
+// never stored.  Back substitution walks the panels backwards: owners contribute their 64 y entries (allreduce), the
+// diagonal block (kept from step 2, replicated) is solved redundantly, and every rank updates its local y.
+__global__ void dist_init_perm_kernel(int* __restrict__ perm, int* __restrict__ pos_of_lr, int N, const int* __restrict__ row0,
+                                      const int* __restrict__ nrows, int world, int S, int rank) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= N) return;
+    for (int r = 0; r < world; ++r)
+        if (pos >= row0[r] && pos < row0[r] + nrows[r]) {
+            perm[pos] = r * S + (pos - row0[r]);
+            if (r == rank) pos_of_lr[pos - row0[r]] = pos;
+        }
+}
+// vv(pos) = 1 / amax(slot at pos); a zero row flags the matrix singular
+__global__ void dist_vv_kernel(const double* __restrict__ amax_all, const int* __restrict__ perm, int N, double* __restrict__ vv,
+                               int* __restrict__ flag) {
+    const int pos = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= N) return;
+    const double a = amax_all[perm[pos]];
+    if (a <= 1.5e-20) atomicExch(flag, 1);
+    vv[pos] = 1.0 / a;
+}
+// Pbuf(pos, c) = gathered panel entry of the row at position pos, for pos >= k0
+__global__ void __launch_bounds__(256) dist_gather_panel_kernel(const double* __restrict__ Gall, int S, int nb, const int* __restrict__ perm,
+                                                                 int k0, int N, double* __restrict__ Pbuf, int NP) {
+    const int pos = k0 + blockIdx.x * 256 + threadIdx.x;
+    const int c = blockIdx.y;
+    if (pos >= N) return;
+    const int s = perm[pos], r = s / S, lr = s - r * S;
+    Pbuf[pos + (size_t)c * NP] = Gall[((size_t)r * nb + c) * S + lr];
+}
+__global__ void dist_pos_of_row_kernel(const int* __restrict__ perm, int k0, int N, int S, int rank, int* __restrict__ pos_of_lr) {
+    const int pos = k0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (pos >= N) return;
+    const int s = perm[pos];
+    if (s / S == rank) pos_of_lr[s - rank * S] = pos;
+}
+// the per-column fallback of the panel factorisation records interchanges only: apply them to perm
+__global__ void dist_apply_piv_kernel(const int* __restrict__ piv, int k0, int k1, int* __restrict__ perm) {
+    if (blockIdx.x == 0 && threadIdx.x == 0)
+        for (int j = k0; j < k1; ++j) {
+            const int p = piv[j];
+            if (p != j) {
+                const int t = perm[p];
+                perm[p] = perm[j];
+                perm[j] = t;
+            }
+        }
+}
+// Usend(j, c') = A_loc(row at position k0+j, c0+c') if this rank owns that row, else 0   (j < 64, c' < W)
+__global__ void __launch_bounds__(256) dist_pack_u_kernel(const double* __restrict__ Aloc, int ld, const int* __restrict__ perm, int k0, int nb,
+                                                           int S, int rank, int c0, int W, double* __restrict__ Usend) {
+    const int j = threadIdx.x & 63;
+    const int cc = blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (cc >= W) return;
+    double v = 0.;
+    if (j < nb) {
+        const int s = perm[k0 + j];
+        if (s / S == rank) v = Aloc[(s - rank * S) + (size_t)(c0 + cc) * ld];
+    }
+    Usend[j + (size_t)cc * LU_NB] = v;
+}
+__global__ void __launch_bounds__(256) dist_unpack_u_kernel(double* __restrict__ Aloc, int ld, const int* __restrict__ perm, int k0, int nb,
+                                                             int S, int rank, int c0, int W, const double* __restrict__ Ubuf) {
+    const int j = threadIdx.x & 63;
+    const int cc = blockIdx.x * 4 + (threadIdx.x >> 6);
+    if (cc >= W || j >= nb) return;
+    const int s = perm[k0 + j];
+    if (s / S == rank) Aloc[(s - rank * S) + (size_t)(c0 + cc) * ld] = Ubuf[j + (size_t)cc * LU_NB];
+}
+// Lloc(lr, c) = multiplier of local row lr in the factored panel (0 for rows at or above the panel's last pivot)
+__global__ void __launch_bounds__(256) dist_gather_l_kernel(const double* __restrict__ Pbuf, int NP, const int* __restrict__ pos_of_lr, int n_rows,
+                                                             int n_rows_pad, int k1, double* __restrict__ Lloc,
+                                                             unsigned char* __restrict__ rb_active) {
+    const int lr = blockIdx.x * 256 + threadIdx.x;
+    const int c = blockIdx.y;
+    if (lr >= n_rows_pad) return;
+    const int pos = lr < n_rows ? pos_of_lr[lr] : -1;
+    const bool active = pos >= k1;
+    Lloc[lr + (size_t)c * n_rows_pad] = active ? Pbuf[pos + (size_t)c * NP] : 0.;
+    if (active && c == 0) rb_active[lr / GM_BM] = 1;
+}
+__global__ void dist_pack_y_kernel(const double* __restrict__ ycol, const int* __restrict__ perm, int k0, int nb, int S, int rank,
+                                   double* __restrict__ ysend) {
+    const int j = threadIdx.x;
+    double v = 0.;
+    if (j < nb) {
+        const int s = perm[k0 + j];
+        if (s / S == rank) v = ycol[s - rank * S];
+    }
+    ysend[j] = v;
+}
+// y_loc -= A_loc(:, k0..k1) x_k  (rows already solved receive garbage that is never read again)
+__global__ void __launch_bounds__(256) dist_y_update_kernel(const double* __restrict__ Aloc, int ld, int n_rows, int k0, int nb,
+                                                             const double* __restrict__ xk, double* __restrict__ ycol, double* __restrict__ x_out) {
+    __shared__ double sx[LU_NB];
+    if (threadIdx.x < nb) {
+        sx[threadIdx.x] = xk[threadIdx.x];
+        if (blockIdx.x == 0) x_out[k0 + threadIdx.x] = xk[threadIdx.x];
+    }
+    __syncthreads();
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= n_rows) return;
+    double acc = 0.;
+    for (int c = 0; c < nb; ++c) acc = fma(Aloc[r + (size_t)(k0 + c) * ld], sx[c], acc);
+    ycol[r] -= acc;
+}
+__global__ void dist_copy_block_kernel(const double* __restrict__ Pbuf, int NP, int k0, int nb, double* __restrict__ D) {
+    // D (64 x 64, zero-initialised) <- the panel's nb x nb diagonal block [L11 \ U11]
+    const int r = threadIdx.x, cc = blockIdx.x;
+    if (r < nb && cc < nb) D[r + cc * LU_NB] = Pbuf[(k0 + r) + (size_t)cc * NP];
+}
+
+#ifdef ML_HAVE_NCCL
+#define DIST_NCCL(call)                                                                        \
+    do {                                                                                       \
+        ncclResult_t r__ = (call);                                                             \
+        if (r__ != ncclSuccess) { st = c->fail(ML_NCCL_ERROR, std::string(#call) + ": " + ncclGetErrorString(r__)); goto done; } \
+    } while (0)
+#endif
+#define DIST_CUDA(call)                                                   \
+    do {                                                                  \
+        cudaError_t e__ = (call);                                         \
+        if (e__ != cudaSuccess) { st = c->cuda_fail(e__, #call); goto done; } \
+    } while (0)
+
+// dAloc: this rank's rows (n_rows x (N+1) columns allocated, leading dimension ld, a scratch copy: overwritten);
+// d_b: the whole right-hand side on every rank; d_x: the whole solution on every rank.
+ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int n_rows_pad, int S, const double* d_b, double* d_x) {
+    const int world = c->world, rank = c->rank;
+    if ((int)c->shard_row0.size() != world) return c->fail(ML_NOT_READY, "row shards unknown");
+    if (ld & 1) return c->fail(ML_BAD_ARGUMENT, "leading dimension must be even");
+    const int NP = ((N + 63) / 64) * 64;
+    const int npan = (N + LU_NB - 1) / LU_NB;
+    const int row0 = c->shard_row0[rank];
+    ml_status st = ML_OK;
+    DevBuf<int> perm, piv, pos_of_lr, d_shards, flag;
+    DevBuf<double> vv, amax_loc, amax_all, Gsend, Gall, Pbuf, Usend, Ubuf, Dall, Lloc, yvec;
+    DevBuf<unsigned char> rb_active;
+    LuPanelWork PW;
+    const int n_rb = (n_rows_pad + GM_BM - 1) / GM_BM;
+    double* ycol = dAloc + (size_t)N * ld;
+    int h_flag = 0;
+    std::vector<int> h_shards(2 * world);
+    for (int r = 0; r < world; ++r) {
+        h_shards[r] = c->shard_row0[r];
+        h_shards[world + r] = c->shard_nrows[r];
+    }
+    auto allgather = [&](const double* send, double* recv, size_t count) -> bool {
+        if (world == 1) return cudaMemcpyAsync(recv, send, count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+#ifdef ML_HAVE_NCCL
+        return ncclAllGather(send, recv, count, ncclDouble, c->comm, c->stream) == ncclSuccess;
+#else
+        return false;
+#endif
+    };
+    auto allreduce = [&](const double* send, double* recv, size_t count) -> bool {
+        if (world == 1) return cudaMemcpyAsync(recv, send, count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
+#ifdef ML_HAVE_NCCL
+        return ncclAllReduce(send, recv, count, ncclDouble, ncclSum, c->comm, c->stream) == ncclSuccess;
+#else
+        return false;
+#endif
+    };
+    DIST_CUDA(perm.alloc(N));
+    DIST_CUDA(piv.alloc(N));
+    DIST_CUDA(pos_of_lr.alloc(std::max(1, S)));
+    DIST_CUDA(d_shards.alloc(2 * world));
+    DIST_CUDA(flag.alloc(1));
+    DIST_CUDA(vv.alloc(N));
+    DIST_CUDA(amax_loc.alloc(S));
+    DIST_CUDA(amax_all.alloc((size_t)S * world));
+    DIST_CUDA(Gsend.alloc((size_t)S * LU_NB));
+    DIST_CUDA(Gall.alloc((size_t)S * LU_NB * world));
+    DIST_CUDA(Pbuf.alloc((size_t)NP * LU_NB));
+    DIST_CUDA(Usend.alloc((size_t)LU_NB * (N + 1)));
+    DIST_CUDA(Ubuf.alloc((size_t)LU_NB * (N + 1)));
+    DIST_CUDA(Dall.alloc((size_t)LU_NB * LU_NB * npan));
+    DIST_CUDA(Lloc.alloc((size_t)n_rows_pad * LU_NB));
+    DIST_CUDA(yvec.alloc(2 * LU_NB));
+    DIST_CUDA(rb_active.alloc(n_rb));
+    st = PW.init(c);
+    if (st != ML_OK) goto done;
+    DIST_CUDA(cudaMemcpyAsync(d_shards.p, h_shards.data(), 2 * world * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    DIST_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), c->stream));
+    DIST_CUDA(cudaMemsetAsync(Dall.p, 0, (size_t)LU_NB * LU_NB * npan * sizeof(double), c->stream));
+    DIST_CUDA(cudaMemsetAsync(amax_loc.p, 0, (size_t)S * sizeof(double), c->stream));
+    // right-hand side as column N of the local rows
+    DIST_CUDA(cudaMemcpyAsync(ycol, d_b + row0, (size_t)n_rows * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    dist_init_perm_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(perm.p, pos_of_lr.p, N, d_shards.p, d_shards.p + world, world, S, rank);
+    if (n_rows > 0)
+        lu_row_amax_kernel<<<dim3((n_rows + 127) / 128, (N + RS_COLS - 1) / RS_COLS), 128, 0, c->stream>>>(dAloc, ld, n_rows, N,
+                                                                                                            (unsigned long long*)amax_loc.p);
+    c->launches += 2;
+    if (!allgather(amax_loc.p, amax_all.p, S)) { st = c->fail(ML_NCCL_ERROR, "allgather row maxima"); goto done; }
+    dist_vv_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(amax_all.p, perm.p, N, vv.p, flag.p);
+    c->launches += 1;
+    DIST_CUDA(cudaMemcpyAsync(&h_flag, flag.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    DIST_CUDA(cudaStreamSynchronize(c->stream));
+    if (h_flag) { st = c->fail(ML_SINGULAR, "lu_decomp: the matrix is singular (a row is zero; linalg.f90:205-208)"); goto done; }
+
+    for (int k = 0; k < npan; ++k) {
+        const int k0 = k * LU_NB, k1 = std::min(k0 + LU_NB, N), nb = k1 - k0;
+        const int W = N + 1 - k1;   // trailing columns + the right-hand side
+        // 1. the whole panel on every rank, in position order
+        if (n_rows > 0)
+            DIST_CUDA(cudaMemcpy2DAsync(Gsend.p, (size_t)S * sizeof(double), dAloc + (size_t)k0 * ld, (size_t)ld * sizeof(double),
+                                        (size_t)n_rows * sizeof(double), nb, cudaMemcpyDeviceToDevice, c->stream));
+        if (!allgather(Gsend.p, Gall.p, (size_t)S * nb)) { st = c->fail(ML_NCCL_ERROR, "allgather panel"); goto done; }
+        dist_gather_panel_kernel<<<dim3((N - k0 + 255) / 256, nb), 256, 0, c->stream>>>(Gall.p, S, nb, perm.p, k0, N, Pbuf.p, NP);
+        c->launches += 1;
+        // 2. factor it (replicated); the kernel addresses column k0 + c at A + (k0 + c) * ld
+        st = lu_panel_factor(c, PW, Pbuf.p - (size_t)k0 * NP, NP, N, k0, k1, vv.p, piv.p, perm.p);
+        if (st != ML_OK) goto done;
+        if (!PW.all_coop) {
+            dist_apply_piv_kernel<<<1, 32, 0, c->stream>>>(piv.p, k0, k1, perm.p);
+            c->launches += 1;
+            PW.all_coop = true;
+        }
+        dist_pos_of_row_kernel<<<(N - k0 + 255) / 256, 256, 0, c->stream>>>(perm.p, k0, N, S, rank, pos_of_lr.p);
+        dist_copy_block_kernel<<<nb, 64, 0, c->stream>>>(Pbuf.p, NP, k0, nb, Dall.p + (size_t)k * LU_NB * LU_NB);
+        // 3. U-row block: owners pack, sum over ranks, solve with L11, owners store back
+        dist_pack_u_kernel<<<(W + 3) / 4, 256, 0, c->stream>>>(dAloc, ld, perm.p, k0, nb, S, rank, k1, W, Usend.p);
+        c->launches += 3;
+        if (!allreduce(Usend.p, Ubuf.p, (size_t)LU_NB * W)) { st = c->fail(ML_NCCL_ERROR, "allreduce U rows"); goto done; }
+        lu_trsm_kernel<<<(W + 63) / 64, 64, 0, c->stream>>>(Dall.p + (size_t)k * LU_NB * LU_NB, LU_NB, Ubuf.p, LU_NB, W);
+        dist_unpack_u_kernel<<<(W + 3) / 4, 256, 0, c->stream>>>(dAloc, ld, perm.p, k0, nb, S, rank, k1, W, Ubuf.p);
+        c->launches += 2;
+        // 4. local trailing update
+        if (k1 < N && n_rows > 0) {
+            DIST_CUDA(cudaMemsetAsync(rb_active.p, 0, n_rb, c->stream));
+            dist_gather_l_kernel<<<dim3((n_rows_pad + 255) / 256, LU_NB), 256, 0, c->stream>>>(Pbuf.p, NP, pos_of_lr.p, n_rows, n_rows_pad, k1,
+                                                                                               Lloc.p, rb_active.p);
+            c->launches += 1;
+            lu_gemm2_launch(c, Lloc.p, n_rows_pad, Ubuf.p, LU_NB, dAloc + (size_t)k1 * ld, ld, n_rows, W, rb_active.p);
+        }
+        DIST_CUDA(cudaGetLastError());
+    }
+    // back substitution, last panel first
+    for (int k = npan - 1; k >= 0; --k) {
+        const int k0 = k * LU_NB, k1 = std::min(k0 + LU_NB, N), nb = k1 - k0;
+        dist_pack_y_kernel<<<1, 64, 0, c->stream>>>(ycol, perm.p, k0, nb, S, rank, yvec.p);
+        if (!allreduce(yvec.p, yvec.p + LU_NB, LU_NB)) { st = c->fail(ML_NCCL_ERROR, "allreduce y block"); goto done; }
+        lu_trsv_diag_kernel<<<1, 64, 0, c->stream>>>(Dall.p + (size_t)k * LU_NB * LU_NB, LU_NB, 0, nb, yvec.p + LU_NB, 1);
+        dist_y_update_kernel<<<std::max(1, (n_rows + 255) / 256), 256, 0, c->stream>>>(dAloc, ld, n_rows, k0, nb, yvec.p + LU_NB, ycol, d_x);
+        c->launches += 3;
+    }
+    DIST_CUDA(cudaGetLastError());
+    DIST_CUDA(cudaStreamSynchronize(c->stream));
+done:
+    PW.release();
+    perm.release(); piv.release(); pos_of_lr.release(); d_shards.release(); flag.release();
+    vv.release(); amax_loc.release(); amax_all.release(); Gsend.release(); Gall.release(); Pbuf.release();
+    Usend.release(); Ubuf.release(); Dall.release(); Lloc.release(); yvec.release(); rb_active.release();
+    return st;
+}
+#undef DIST_CUDA
 
 // ---- block Jacobi (linalg.f90:601-728) --------------------------------------------------------------------
 __global__ void bj_init_kernel(const double* __restrict__ A, int ld, const double* __restrict__ b, int n, double* __restrict__ x) {

@@ -854,6 +854,8 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
 }
 
 ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, double* d_x);  // lu_kernels.cu
+ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int n_rows_pad, int S, const double* d_b,
+                           double* d_x);                                                      // lu_kernels.cu
 ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
                               int max_iter, int* iters, double* d_x, double err_scale);      // lu_kernels.cu
 ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
@@ -1055,9 +1057,21 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     // Direct / block solvers work on a private full copy (the reference's A_p), single device only.
     DevBuf<double> Acopy;
     double* lu_matrix = nullptr;
-    if (needs_whole_matrix(opts->matrix_solver)) {
+    static const bool force_sharded_lu = std::getenv("MACHLINE_LU_SHARDED") != nullptr;   // tests: the NCCL algorithm on one rank
+    if (opts->matrix_solver == ML_SOLVER_LU && (c->world > 1 || force_sharded_lu)) {
+        // row-sharded LU: the local rows (plus the right-hand side as column N) are factored in a scratch copy (A_p)
+        if (c->world == 1) {
+            c->shard_row0.assign(1, 0);
+            c->shard_nrows.assign(1, N);
+        }
+        ML_CUDA(c, Acopy.alloc((size_t)c->ld * (N + 1)));
+        ML_CUDA(c, cudaMemcpyAsync(Acopy.p, c->d_A.p, (size_t)c->ld * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        st = lu_solve_sharded(c, N, Acopy.p, c->ld, c->n_rows, c->n_rows_pad, S.shard_pad, d_b.p, d_x.p);
+        Acopy.release();
+        if (st == ML_OK && info) info->iterations = -1;
+    } else if (needs_whole_matrix(opts->matrix_solver)) {
         if (c->world > 1)
-            return c->fail(ML_UNSUPPORTED, "LU/BJAC/BSSOR/QRUP/FQRUP/PURC on a row-sharded system are not built (SURVEY 8(e)): use GMRES/RGMRES");
+            return c->fail(ML_UNSUPPORTED, "BJAC/BSSOR/QRUP/FQRUP/PURC on a row-sharded system are not built (SURVEY 8(e)): use LU/GMRES/RGMRES");
         lu_matrix = c->d_A.p;
         if (opts->matrix_solver == ML_SOLVER_LU) {   // factored in place: work on the reference's A_p copy
             ML_CUDA(c, Acopy.alloc((size_t)c->ld * N));
@@ -1065,7 +1079,8 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
             lu_matrix = Acopy.p;
         }
     }
-    st = run_solver(S, opts, d_b.p, scale_ptr, d_x.p, info, lu_matrix, c->ld);
+    if (!(opts->matrix_solver == ML_SOLVER_LU && (c->world > 1 || force_sharded_lu)))
+        st = run_solver(S, opts, d_b.p, scale_ptr, d_x.p, info, lu_matrix, c->ld);
     Acopy.release();
     if (st == ML_OK) st = residual(S, d_x.p, d_b.p, info);
     if (st == ML_OK || st == ML_NAN_RESIDUAL) {

@@ -45,6 +45,7 @@ def lib() -> C.CDLL:
         L.ml_assemble.argtypes = [vp, dp]
         L.ml_assemble_resident.argtypes = [vp, dp]
         L.ml_get_A.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int]
+        L.ml_set_A.argtypes = [vp, C.c_int, C.c_int, dp, C.c_int]
         L.ml_pair_count.argtypes = [vp]
         L.ml_pair_count.restype = C.c_longlong
         L.ml_launch_count.argtypes = [vp]
@@ -125,6 +126,12 @@ class Context:
         A = np.zeros((nrows, self.n_unknown), dtype=np.float64, order="F")
         self._check(lib().ml_get_A(self._h, row0, nrows, _dp(A), nrows))
         return A
+
+    def set_A(self, A_rows: np.ndarray, row0: int | None = None):
+        """Overwrite rows [row0, row0 + len(A_rows)) of the resident system (ml_set_A)."""
+        row0 = self.row0 if row0 is None else row0
+        A_rows = np.asfortranarray(A_rows, dtype=np.float64)
+        self._check(lib().ml_set_A(self._h, row0, A_rows.shape[0], _dp(A_rows), A_rows.shape[0]))
 
     @property
     def pair_count(self) -> int:
