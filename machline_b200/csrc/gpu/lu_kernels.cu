@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(256) lu_panel_update_kernel(double* __restrict
 // a(i,c) = fma(-l, a(j,c), a(i,c)) with l = a(i,j) * (1/a(j,j)), identical to the per-column kernels.
 constexpr int LUP_THREADS = 256;
 constexpr int LUP_CAP = 384;   // rows a CTA can hold: 64 columns x 384 rows x 8 B = 192 KB
+constexpr int LUP_CAP_OVF = 320;   // shared-memory rows per CTA when the panel overflows (the rest stay in global memory)
+constexpr int LUP_RPC_MAX = 2048;  // rows per CTA the overflow variant supports (s_l, s_vv, s_perm are per row)
 constexpr int LUP_ROW = LU_NB + 2;   // a published row: LU_NB panel entries, perm, vv
 
 struct LuPanelArgs {
@@ -163,6 +165,7 @@ __device__ __forceinline__ void lup_grid_sync(unsigned* bar, unsigned target) {
 
 __device__ __forceinline__ bool lup_better(double v, int i, double best, int bi) { return v > best || (v == best && i > bi); }
 
+template <bool OVF>
 __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuPanelArgs a) {
     extern __shared__ __align__(16) double lup_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -170,8 +173,16 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
     const int nb = a.k1 - a.k0;
     const int r0 = a.k0 + bid * a.rpc;                 // first row position of this CTA
     const int nr = min(a.rpc, a.n - r0);               // > 0 by grid sizing
-    const int S = a.rpc | 1;                           // odd column stride: row gathers are conflict-free
+    // OVF: the panel has more rows than the CTAs' shared memory holds; the first `cap` rows of a CTA live in shared
+    // memory, the rest stay where they are in global memory (only their owner CTA ever touches them).
+    const int cap = OVF ? LUP_CAP_OVF : a.rpc;
+    const int S = cap | 1;                             // odd column stride: row gathers are conflict-free
     double* sP = lup_smem;                             // [LU_NB][S]
+    double* const gA = a.A + (size_t)a.k0 * a.ld + r0; // this CTA's rows of the panel in global memory
+    auto el = [&](int r, int c) -> double& {
+        if (OVF && r >= cap) return gA[(size_t)c * a.ld + r];
+        return sP[c * S + r];
+    };
     double* s_piv = sP + LU_NB * S;                    // [LU_NB]  pivot row, panel columns
     double* s_oldj = s_piv + LUP_ROW;                  // [LUP_ROW] old row j (+ perm, vv)
     double* s_l = s_oldj + LUP_ROW;                    // [rpc]
@@ -183,7 +194,7 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
 
     for (int item = warp; item < nb * nrb; item += LUP_THREADS / 32) {
         const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
-        if (r < nr) sP[c * S + r] = __ldcg(a.A + (size_t)(a.k0 + c) * a.ld + r0 + r);
+        if (r < nr && r < cap) sP[c * S + r] = __ldcg(a.A + (size_t)(a.k0 + c) * a.ld + r0 + r);
     }
     for (int r = tid; r < nr; r += LUP_THREADS) {
         s_vv[r] = __ldcg(a.vv + r0 + r);
@@ -199,7 +210,7 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         for (int r = tid; r < nr; r += LUP_THREADS) {
             const int gp = r0 + r;
             if (gp >= j) {
-                const double v = s_vv[r] * fabs(sP[jj * S + r]);
+                const double v = s_vv[r] * fabs(el(r, jj));
                 if (lup_better(v, gp, best, bi)) { best = v; bi = gp; }
             }
         }
@@ -230,13 +241,13 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         bi = s_ri[8];
         if (bi >= 0) {
             double* slot = a.cand_row + ((size_t)par * G + bid) * LUP_ROW;
-            if (tid < nb) __stcg(slot + tid, sP[tid * S + (bi - r0)]);
+            if (tid < nb) __stcg(slot + tid, el(bi - r0, tid));
             if (tid == LU_NB) __stcg(slot + LU_NB, (double)s_perm[bi - r0]);
         }
         const bool own_j = (j >= r0 && j < r0 + nr);
         if (own_j) {
             double* slot = a.rowj + par * LUP_ROW;
-            if (tid < nb) __stcg(slot + tid, sP[tid * S + (j - r0)]);
+            if (tid < nb) __stcg(slot + tid, el(j - r0, tid));
             if (tid == LU_NB) __stcg(slot + LU_NB, (double)s_perm[j - r0]);
             if (tid == LU_NB + 1) __stcg(slot + LU_NB + 1, s_vv[j - r0]);
         }
@@ -283,11 +294,11 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         __syncthreads();
         if (p != j) {   // whole-row interchange inside the panel (linalg.f90:254-263)
             if (own_j) {
-                if (tid < nb) sP[tid * S + (j - r0)] = s_piv[tid];
+                if (tid < nb) el(j - r0, tid) = s_piv[tid];
                 if (tid == LU_NB) s_perm[j - r0] = (int)s_piv[LU_NB];
             }
             if (own_p) {
-                if (tid < nb) sP[tid * S + (p - r0)] = s_oldj[tid];
+                if (tid < nb) el(p - r0, tid) = s_oldj[tid];
                 if (tid == LU_NB) s_perm[p - r0] = (int)s_oldj[LU_NB];
                 if (tid == LU_NB + 1) s_vv[p - r0] = s_oldj[LU_NB + 1];
             }
@@ -298,8 +309,8 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         for (int r = tid; r < nr; r += LUP_THREADS) {
             double l = 0.;
             if (r0 + r > j) {
-                l = sP[jj * S + r] * inv;
-                sP[jj * S + r] = l;
+                l = el(r, jj) * inv;
+                el(r, jj) = l;
             }
             s_l[r] = l;
         }
@@ -308,13 +319,13 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         for (int item = warp; item < ncr * nrb; item += LUP_THREADS / 32) {
             const int cc = item / nrb, r = ((item - cc * nrb) << 5) + lane;
             const int c = jj + 1 + cc;
-            if (r < nr && r0 + r > j) sP[c * S + r] = fma(-s_l[r], s_piv[c], sP[c * S + r]);
+            if (r < nr && r0 + r > j) el(r, c) = fma(-s_l[r], s_piv[c], el(r, c));
         }
         __syncthreads();
     }
     for (int item = warp; item < nb * nrb; item += LUP_THREADS / 32) {
         const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
-        if (r < nr) a.A[(size_t)(a.k0 + c) * a.ld + r0 + r] = sP[c * S + r];
+        if (r < nr && r < cap) a.A[(size_t)(a.k0 + c) * a.ld + r0 + r] = sP[c * S + r];
     }
     for (int r = tid; r < nr; r += LUP_THREADS) {
         a.vv[r0 + r] = s_vv[r];
@@ -727,7 +738,8 @@ void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ld
 }
 
 static size_t lu_panel_smem(int rpc) {
-    return (size_t)(LU_NB * (rpc | 1) + 2 * LUP_ROW + 2 * rpc + 8) * sizeof(double) + (size_t)(16 + rpc) * sizeof(int);
+    const int cap = rpc <= LUP_CAP ? rpc : LUP_CAP_OVF;
+    return (size_t)(LU_NB * (cap | 1) + 2 * LUP_ROW + 2 * rpc + 8) * sizeof(double) + (size_t)(16 + rpc) * sizeof(int);
 }
 
 // Scratch of the cooperative panel kernel (candidate slots for up to num_sms CTAs, two parities) and its barrier.
@@ -741,7 +753,9 @@ struct LuPanelWork {
     ml_status init(Ctx* c) {
         static bool attr_set = false;
         if (!attr_set) {
-            ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel_smem(LUP_CAP)));
+            ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel_smem(LUP_CAP)));
+            ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)lu_panel_smem(LUP_RPC_MAX)));
             attr_set = true;
         }
         gmax = c->num_sms;
@@ -766,7 +780,9 @@ static ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int
     const int m = n - k0;
     int rpc = 128;
     if ((long long)rpc * W.gmax < m) rpc = (((m + W.gmax - 1) / W.gmax) + 31) & ~31;
-    if (!per_column && rpc <= LUP_CAP) {
+    static const char* rpc_env = getenv("MACHLINE_LU_PANEL_RPC");   // tests: force a rows-per-CTA value (e.g. the overflow variant)
+    if (rpc_env && atoi(rpc_env) >= 128) rpc = std::max(rpc, (atoi(rpc_env) + 31) & ~31);
+    if (!per_column && rpc <= LUP_RPC_MAX) {
         LuPanelArgs pa;
         pa.A = dA; pa.ld = ld; pa.n = n; pa.k0 = k0; pa.k1 = k1; pa.rpc = rpc;
         pa.vv = d_vv; pa.piv = d_piv; pa.perm = d_perm;
@@ -778,7 +794,8 @@ static ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int
         const int G = (m + rpc - 1) / rpc;
         W.bar_base += (unsigned)(k1 - k0) * (unsigned)G;
         void* kargs[] = {(void*)&pa};
-        ML_CUDA(c, cudaLaunchCooperativeKernel((const void*)lu_panel_coop_kernel, dim3(G), dim3(LUP_THREADS), kargs, lu_panel_smem(rpc), c->stream));
+        const void* kern = rpc <= LUP_CAP ? (const void*)lu_panel_coop_kernel<false> : (const void*)lu_panel_coop_kernel<true>;
+        ML_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(G), dim3(LUP_THREADS), kargs, lu_panel_smem(rpc), c->stream));
         c->launches += 1;
     } else {
         W.all_coop = false;

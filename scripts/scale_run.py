@@ -1,0 +1,94 @@
+"""BASELINE configs[4]-class run: a synthetic refined case (50k-100k+ unknowns) assembled and solved on N GPUs, row-sharded.
+Not the bench (one pass, no warm-up repetitions): it records that the large case runs end to end and what each phase costs.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29544 \
+        scripts/scale_run.py --dims 320x160 --solvers GMRES,LU
+
+Rank 0 prints one JSON line per solver."""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+from machline_b200 import _abi, gpu, host, meshgen, shard  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--dims", default="226x112")
+ap.add_argument("--solvers", default="GMRES,LU")
+ap.add_argument("--mach", type=float, default=0.5)
+args = ap.parse_args()
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", rank))
+if world > 1:
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+nc, ns = (int(v) for v in args.dims.split("x"))
+tmp = tempfile.mkdtemp(prefix=f"machline_scale_r{rank}_")
+t0 = time.perf_counter()
+pts, tris = meshgen.swept_wing_half(nc, ns)
+meshgen.write_vtk(f"{tmp}/w.vtk", pts, tris)
+case = host.Case(meshgen.wing_input("w.vtk", mach=args.mach), base_dir=tmp)
+host_s = time.perf_counter() - t0
+N = case.n_cp
+row0, nrows = shard.row_shard(N, rank, world)
+ctx = gpu.Context(local)
+if world > 1:
+    uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(gpu.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, src=0)
+    ctx.set_communicator(bytes(uid.cpu().numpy().tobytes()), rank, world)
+
+
+def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+
+
+ctx.set_case(case, row0=row0, nrows=nrows)
+barrier()
+t0 = time.perf_counter()
+ctx.assemble()
+barrier()
+asm_wall = time.perf_counter() - t0
+asm_ms = ctx.assemble_resident()
+BC = np.array(case.BC)
+for solver in args.solvers.split(","):
+    opts = case.solver_opts()
+    o = _abi.solver_opts(solver, preconditioner="DIAG" if opts.preconditioner else "none", tol=opts.tol,
+                         max_iterations=opts.max_iterations)
+    barrier()
+    t0 = time.perf_counter()
+    x, info = ctx.solve(o, BC)
+    barrier()
+    wall = time.perf_counter() - t0
+    vals = torch.tensor([asm_ms, info.solve_ms, wall], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        res = case.post(x)
+        a_ms, s_ms, w_s = (float(v) for v in vals.cpu())
+        print(json.dumps({"case": f"half wing {nc}x{ns}, M={args.mach}", "n_gpus": world, "n_panels": case.info.n_body_panels,
+                          "n_unknown": N, "A_bytes": 8.0 * N * N, "pairs": float(case.n_pairs), "matrix_solver": solver,
+                          "host_setup_s": host_s, "assemble_ms": a_ms, "assemble_first_wall_s": asm_wall,
+                          "pairs_per_s": case.n_pairs / (a_ms * 1e-3), "solve_ms": s_ms, "solve_wall_s": w_s,
+                          "iterations": int(info.iterations), "res_norm": info.res_norm, "res_max": info.res_max,
+                          "lu_tflops": (2.0 / 3.0 * N ** 3 / (s_ms * 1e-3) / 1e12) if solver == "LU" else None,
+                          "C_p_max": res.C_p_max, "C_p_min": res.C_p_min, "Cx": float(res.C_F[0]), "Cz": float(res.C_F[2])}),
+              flush=True)
+ctx.close()
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()

@@ -38,3 +38,11 @@ def test_sharded_lu_two_ranks_nccl(dims):
     out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                 "--master-port", "29533", WORKER, dims], {})
     assert out.count("OK") == 2
+
+
+@pytest.mark.parametrize("env", [{"MACHLINE_LU_PANEL_RPC": "512"}, {"MACHLINE_LU_PER_COLUMN": "1"}, {"MACHLINE_LU_GEMM_V1": "1"}])
+def test_lu_kernel_variants(env):
+    """The other code paths of the factorisation on heavy-pivoting systems: panel rows overflowing shared memory (rows 320..511
+    of every CTA stay in global memory), the per-column fallback, the first-generation trailing update."""
+    out = _run([sys.executable, str(ROOT / "tests" / "lu_env_worker.py"), "700", "3000"], env)
+    assert out.count("OK") == 2
