@@ -49,9 +49,10 @@ def launches(tag, path):
     h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
     hdr = rows[h]
     ki, vi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+    mi = hdr.index("Metric Name")
     t, n = collections.defaultdict(float), collections.Counter()
     for r in rows[h + 1:]:
-        if len(r) <= vi:
+        if len(r) <= vi or r[mi] != "gpu__time_duration.sum":
             continue
         v = float(r[vi].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}.get(r[ui], 1.0)
