@@ -240,6 +240,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--matrix-solver", default="GMRES")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-lu-probe", action="store_true")
     ap.add_argument("--dims", default=None, help="tests only: NCxNS mesh instead of the BASELINE-sized one")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -332,6 +333,28 @@ def main():
     gp = ctx.profile()
     ctx.set_profiling(False)
 
+    # ---- LU probe (outside the timed region; N = 1 only): the direct solver on the same resident system, against the
+    # measured FP64 tensor-pipe (DMMA) peak -- the third roofline north_star names ------------------------------------
+    lu_probe = None
+    if world == 1 and not args.no_lu_probe:
+        from machline_b200 import _abi
+        lu_opts = _abi.solver_opts("LU", preconditioner="DIAG" if opts.preconditioner else "none")
+        best = None
+        for _ in range(2):
+            ctx.assemble_resident()
+            x_lu, info_lu = ctx.solve(lu_opts, BC)
+            best = info_lu.solve_ms if best is None else min(best, info_lu.solve_ms)
+        dmma_peak = ctx.measure_dmma_peak()
+        flops = 2.0 / 3.0 * float(N) ** 3
+        lu_probe = {"kernel": "blocked LU (lu_panel_coop_kernel + lu_trsm_kernel + lu_gemm2_kernel DMMA), whole solve",
+                    "bound": "tensor(fp64)", "n": int(N), "solve_ms": best, "achieved": flops / (best * 1e-3) / 1e12,
+                    "peak": dmma_peak, "unit": "TFLOP/s", "frac": flops / (best * 1e-3) / 1e12 / dmma_peak,
+                    "peak_source": "measured live: register-resident mma.sync.m8n8k4.f64 loop (ml_measure_dmma_peak)",
+                    "res_norm": info_lu.res_norm, "max_abs_dx_vs_gmres": float(np.abs(x_lu - x).max()),
+                    "note": "N = 10.5k is latency-bound on the 165 panel launches; profiles/ holds N = 29k (52 %) and the "
+                            "8-GPU N = 104k run"}
+        ctx.assemble_resident()   # leave the resident system as the timed region left it
+
     # ---- reduce over ranks: max time, sum of pairs ---------------------------------------------------
     vals = torch.tensor([step_ms_local, e2e_ms_local, float(np.mean(asm_ms)), float(np.mean(sol_ms)), step_wall_ms_local,
                          e2e_dev_ms_local], dtype=torch.float64, device=f"cuda:{local}")
@@ -399,7 +422,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": dominant,
-            "roofline_other": [other],
+            "roofline_other": [other] + ([lu_probe] if lu_probe else []),
             "host_setup_s": dims["host_setup_s"],
         }
         if world == 1 and not args.no_cpu_baseline:

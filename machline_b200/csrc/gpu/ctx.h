@@ -101,7 +101,9 @@ struct AicLaunch {            // arguments of the assembly kernel (aic_kernels.c
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;               // high priority: LU look-ahead (panel k+1 under the update of panel k)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaEvent_t ev_strip = nullptr, ev_panel = nullptr;   // ordering between stream and stream2
     std::string err;
     int num_sms = 148;
     long long launches = 0;

@@ -130,6 +130,8 @@ __global__ void __launch_bounds__(256) lu_panel_update_kernel(double* __restrict
 // Candidate slots are double-buffered by column parity: a slot written for column j is next written for
 // column j+2, after barrier j+1, i.e. after every CTA finished reading it.  Arithmetic per element is
 // a(i,c) = fma(-l, a(j,c), a(i,c)) with l = a(i,j) * (1/a(j,j)), identical to the per-column kernels.
+// 256 threads per CTA; 128 (<= 96 registers) when a CTA holds 128 rows, so that it fits on an SM next to a CTA of the
+// trailing update: the look-ahead factors panel k+1 under the update of panel k.
 constexpr int LUP_THREADS = 256;
 constexpr int LUP_CAP = 384;   // rows a CTA can hold: 64 columns x 384 rows x 8 B = 192 KB
 constexpr int LUP_CAP_OVF = 320;   // shared-memory rows per CTA when the panel overflows (the rest stay in global memory)
@@ -165,8 +167,8 @@ __device__ __forceinline__ void lup_grid_sync(unsigned* bar, unsigned target) {
 
 __device__ __forceinline__ bool lup_better(double v, int i, double best, int bi) { return v > best || (v == best && i > bi); }
 
-template <bool OVF>
-__global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuPanelArgs a) {
+template <bool OVF, int T>
+__global__ void __launch_bounds__(T, T == 128 ? 5 : 1) lu_panel_coop_kernel(const LuPanelArgs a) {
     extern __shared__ __align__(16) double lup_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, bid = blockIdx.x;
@@ -192,11 +194,11 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
     int* s_perm = s_ri + 16;                           // [rpc]
     const int nrb = (nr + 31) >> 5;
 
-    for (int item = warp; item < nb * nrb; item += LUP_THREADS / 32) {
+    for (int item = warp; item < nb * nrb; item += T / 32) {
         const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
         if (r < nr && r < cap) sP[c * S + r] = __ldcg(a.A + (size_t)(a.k0 + c) * a.ld + r0 + r);
     }
-    for (int r = tid; r < nr; r += LUP_THREADS) {
+    for (int r = tid; r < nr; r += T) {
         s_vv[r] = __ldcg(a.vv + r0 + r);
         s_perm[r] = __ldcg(a.perm + r0 + r);
     }
@@ -207,7 +209,7 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         // ---- this CTA's candidate for column j ------------------------------------------------------------
         double best = -1.;
         int bi = -1;
-        for (int r = tid; r < nr; r += LUP_THREADS) {
+        for (int r = tid; r < nr; r += T) {
             const int gp = r0 + r;
             if (gp >= j) {
                 const double v = s_vv[r] * fabs(el(r, jj));
@@ -223,8 +225,8 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         if (lane == 0) { s_rv[warp] = best; s_ri[warp] = bi; }
         __syncthreads();
         if (warp == 0) {
-            best = lane < LUP_THREADS / 32 ? s_rv[lane] : -1.;
-            bi = lane < LUP_THREADS / 32 ? s_ri[lane] : -1;
+            best = lane < T / 32 ? s_rv[lane] : -1.;
+            bi = lane < T / 32 ? s_ri[lane] : -1;
 #pragma unroll
             for (int o = 4; o > 0; o >>= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -255,7 +257,7 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         // ---- global pivot: reduce the G candidates (every CTA, redundantly) ---------------------------------
         best = -1.;
         bi = -1;
-        for (int g = tid; g < G; g += LUP_THREADS) {
+        for (int g = tid; g < G; g += T) {
             const double v = __ldcg(a.cand_v + par * G + g);
             const int i = __ldcg(a.cand_i + par * G + g);
             if (i >= 0 && lup_better(v, i, best, bi)) { best = v; bi = i; }
@@ -270,8 +272,8 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
             if (lane == 0) { s_rv[warp] = best; s_ri[warp] = bi; }
             __syncthreads();
             if (warp == 0) {
-                best = lane < LUP_THREADS / 32 ? s_rv[lane] : -1.;
-                bi = lane < LUP_THREADS / 32 ? s_ri[lane] : -1;
+                best = lane < T / 32 ? s_rv[lane] : -1.;
+                bi = lane < T / 32 ? s_ri[lane] : -1;
 #pragma unroll
                 for (int o = 4; o > 0; o >>= 1) {
                     const double ov = __shfl_xor_sync(0xffffffffu, best, o);
@@ -306,7 +308,7 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         }
         // ---- eliminate column j from the rows below it ------------------------------------------------------
         const double inv = 1.0 / s_piv[jj];
-        for (int r = tid; r < nr; r += LUP_THREADS) {
+        for (int r = tid; r < nr; r += T) {
             double l = 0.;
             if (r0 + r > j) {
                 l = el(r, jj) * inv;
@@ -316,18 +318,18 @@ __global__ void __launch_bounds__(LUP_THREADS, 1) lu_panel_coop_kernel(const LuP
         }
         __syncthreads();
         const int ncr = nb - jj - 1;
-        for (int item = warp; item < ncr * nrb; item += LUP_THREADS / 32) {
+        for (int item = warp; item < ncr * nrb; item += T / 32) {
             const int cc = item / nrb, r = ((item - cc * nrb) << 5) + lane;
             const int c = jj + 1 + cc;
             if (r < nr && r0 + r > j) el(r, c) = fma(-s_l[r], s_piv[c], el(r, c));
         }
         __syncthreads();
     }
-    for (int item = warp; item < nb * nrb; item += LUP_THREADS / 32) {
+    for (int item = warp; item < nb * nrb; item += T / 32) {
         const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
         if (r < nr && r < cap) a.A[(size_t)(a.k0 + c) * a.ld + r0 + r] = sP[c * S + r];
     }
-    for (int r = tid; r < nr; r += LUP_THREADS) {
+    for (int r = tid; r < nr; r += T) {
         a.vv[r0 + r] = s_vv[r];
         a.perm[r0 + r] = s_perm[r];
     }
@@ -348,12 +350,11 @@ __global__ void lu_perm_from_piv_kernel(const int* __restrict__ piv, int n, int*
     }
 }
 
-// apply the panel's row interchanges to the columns outside the panel
-__global__ void __launch_bounds__(256) lu_laswp_kernel(double* __restrict__ A, int ld, int n, int k0, int k1,
+// apply the panel's row interchanges to columns [c0, c1)
+__global__ void __launch_bounds__(256) lu_laswp_kernel(double* __restrict__ A, int ld, int c0, int c1, int k0, int k1,
                                                         const int* __restrict__ piv) {
-    int c = blockIdx.x * 256 + threadIdx.x;
-    if (c >= n - (k1 - k0)) return;
-    if (c >= k0) c += (k1 - k0);  // skip the panel's own columns
+    const int c = c0 + blockIdx.x * 256 + threadIdx.x;
+    if (c >= c1) return;
     double* col = A + (size_t)c * ld;
     for (int j = k0; j < k1; ++j) {
         int p = piv[j];
@@ -583,12 +584,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(const double* _
 // Grid shape of the trailing update: rb row blocks x `chunks` runs of 32-column tiles.  Picks the run length that
 // minimises (number of waves over the SMs) x (tiles per run + the cost of staging L21, ~3 tiles), so the last wave
 // is not mostly empty (82 row blocks x 4 runs = 2.2 waves wasted a quarter of the launch).
-static void lu_gemm2_shape(int rb, int ctiles, int num_sms, int* per_out, int* chunks_out) {
+static void lu_gemm2_shape(int rb, int ctiles, int num_sms, int max_per, int* per_out, int* chunks_out) {
     long long best = -1;
     int best_per = ctiles, best_chunks = 1;
     for (int chunks = 1; chunks <= ctiles; ++chunks) {
         int per = (ctiles + chunks - 1) / chunks;
         per = (per + 1) & ~1;   // both warp groups get the same number of tiles
+        if (per > max_per && per > 2) continue;   // short runs: CTAs retire often (look-ahead: the panel kernel waits for SMs)
         const int nch = (ctiles + per - 1) / per;
         const long long waves = ((long long)rb * nch + num_sms - 1) / num_sms;
         const long long cost = waves * (per + 6);
@@ -724,7 +726,7 @@ __global__ void __launch_bounds__(256) lu_bwd_step_kernel(const double* __restri
 
 // C (M x Nc) -= L (M x 64) * U (64 x Nc) on the FP64 tensor cores; all leading dimensions even, pointers 16-byte aligned
 void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ldu, double* Cp, int ldc, int M, int Nc,
-                     const unsigned char* row_block_active) {
+                     const unsigned char* row_block_active, int max_per = 1 << 30) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(lu_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
@@ -732,7 +734,7 @@ void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ld
     }
     const int rb = (M + GM_BM - 1) / GM_BM, ct32 = (Nc + G2_BN - 1) / G2_BN;
     int per, chunks;
-    lu_gemm2_shape(rb, ct32, c->num_sms, &per, &chunks);
+    lu_gemm2_shape(rb, ct32, c->num_sms, max_per, &per, &chunks);
     lu_gemm2_kernel<<<dim3(rb, chunks), G2_THREADS, G2_SMEM, c->stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
     c->launches += 1;
 }
@@ -753,8 +755,9 @@ struct LuPanelWork {
     ml_status init(Ctx* c) {
         static bool attr_set = false;
         if (!attr_set) {
-            ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel_smem(LUP_CAP)));
-            ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)lu_panel_smem(LUP_CAP)));
+            ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)lu_panel_smem(LUP_RPC_MAX)));
             attr_set = true;
         }
@@ -775,10 +778,13 @@ struct LuPanelWork {
 
 // Factor the panel (rows k0..n, columns k0..k1 of dA): pivots into d_piv[k0..k1), rows interchanged inside the panel.
 // One cooperative launch when the panel's rows fit the CTAs' shared memory, else two launches per column.
-static ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int n, int k0, int k1, double* d_vv, int* d_piv, int* d_perm) {
+static ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int n, int k0, int k1, double* d_vv, int* d_piv, int* d_perm,
+                                 cudaStream_t stream, bool few_ctas = false) {
     static const bool per_column = getenv("MACHLINE_LU_PER_COLUMN") != nullptr;   // the unfused path, kept for A/B timing
     const int m = n - k0;
-    int rpc = 128;
+    // few_ctas (look-ahead): as many rows per CTA as shared memory holds, so the panel occupies few SMs and the trailing
+    // update of the previous panel keeps the others
+    int rpc = few_ctas ? LUP_CAP : 128;
     if ((long long)rpc * W.gmax < m) rpc = (((m + W.gmax - 1) / W.gmax) + 31) & ~31;
     static const char* rpc_env = getenv("MACHLINE_LU_PANEL_RPC");   // tests: force a rows-per-CTA value (e.g. the overflow variant)
     if (rpc_env && atoi(rpc_env) >= 128) rpc = std::max(rpc, (atoi(rpc_env) + 31) & ~31);
@@ -794,14 +800,14 @@ static ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int
         const int G = (m + rpc - 1) / rpc;
         W.bar_base += (unsigned)(k1 - k0) * (unsigned)G;
         void* kargs[] = {(void*)&pa};
-        const void* kern = rpc <= LUP_CAP ? (const void*)lu_panel_coop_kernel<false> : (const void*)lu_panel_coop_kernel<true>;
-        ML_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(G), dim3(LUP_THREADS), kargs, lu_panel_smem(rpc), c->stream));
+        const void* kern = rpc <= LUP_CAP ? (const void*)lu_panel_coop_kernel<false, 256> : (const void*)lu_panel_coop_kernel<true, 256>;
+        ML_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(G), dim3(LUP_THREADS), kargs, lu_panel_smem(rpc), stream));
         c->launches += 1;
     } else {
         W.all_coop = false;
         for (int j = k0; j < k1; ++j) {
-            lu_pivot_kernel<<<1, 1024, 0, c->stream>>>(dA, ld, n, j, k0, k1, d_vv, d_piv);
-            if (j + 1 < n) lu_panel_update_kernel<<<(n - j - 1 + 255) / 256, 256, 0, c->stream>>>(dA, ld, n, j, k1);
+            lu_pivot_kernel<<<1, 1024, 0, stream>>>(dA, ld, n, j, k0, k1, d_vv, d_piv);
+            if (j + 1 < n) lu_panel_update_kernel<<<(n - j - 1 + 255) / 256, 256, 0, stream>>>(dA, ld, n, j, k1);
             c->launches += 2;
         }
     }
@@ -831,26 +837,64 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     ml_status pst = PW.init(c);
     if (pst != ML_OK) return pst;
     static const bool old_gemm = getenv("MACHLINE_LU_GEMM_V1") != nullptr;
-    for (int k0 = 0; k0 < n; k0 += LU_NB) {
-        const int k1 = std::min(k0 + LU_NB, n);
-        pst = lu_panel_factor(c, PW, dA, ld, n, k0, k1, d_vv, d_piv, d_perm);
-        if (pst != ML_OK) { PW.release(); return pst; }
-        lu_laswp_kernel<<<(n - (k1 - k0) + 255) / 256 + 1, 256, 0, c->stream>>>(dA, ld, n, k0, k1, d_piv);
-        c->launches += 1;
-        if (k1 < n) {
-            lu_trsm_kernel<<<(n - k1 + 63) / 64, 64, 0, c->stream>>>(dA + k0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)k1 * ld, ld, n - k1);
+    static const bool want_lookahead = getenv("MACHLINE_LU_LOOKAHEAD") != nullptr;
+    // Look-ahead (opt-in, MACHLINE_LU_LOOKAHEAD=1): once the update of panel k has reached the columns of panel k+1 (a
+    // 64-column strip, done first), panel k+1 is factored on a second, high-priority stream while the main stream
+    // applies panel k to the rest of the matrix; the two touch disjoint columns.  Measured on B200 (r01e): it does NOT
+    // pay yet - 108.6 vs 103.4 ms at N = 10.5k, 916 vs 841 ms at N = 29k - the cooperative panel grid only starts once
+    // all its CTAs fit, i.e. after the trailing update has drained, so nothing overlaps and the strip launches are pure
+    // overhead.  Kept for the next round (a non-cooperative panel kernel on a reserved set of SMs).
+    const bool lookahead = want_lookahead && !old_gemm && (ld & 1) == 0 && n > 4 * LU_NB && c->stream2 != nullptr;
+    cudaStream_t S0 = c->stream, S1 = lookahead ? c->stream2 : c->stream;
+    static const int la_max_per = getenv("MACHLINE_LU_LA_PER") ? atoi(getenv("MACHLINE_LU_LA_PER")) : 8;
+    auto laswp = [&](int c0, int c1, int k0, int k1) {
+        if (c1 > c0) {
+            lu_laswp_kernel<<<(c1 - c0 + 255) / 256, 256, 0, S0>>>(dA, ld, c0, c1, k0, k1, d_piv);
             c->launches += 1;
-            if (k1 - k0 == LU_NB) {
-                const int rb = (n - k1 + GM_BM - 1) / GM_BM, ctiles = (n - k1 + GM_BN - 1) / GM_BN;
-                if (!old_gemm && (ld & 1) == 0) {
-                    lu_gemm2_launch(c, dA + k1 + (size_t)k0 * ld, ld, dA + k0 + (size_t)k1 * ld, ld, dA + k1 + (size_t)k1 * ld, ld, n - k1, n - k1,
-                                    nullptr);
-                } else {
-                    dim3 grid(rb, ctiles);
-                    lu_gemm_dmma_kernel<<<grid, 256, gemm_smem, c->stream>>>(dA, ld, n, k0, k1);
-                    c->launches += 1;
-                }
+        }
+    };
+    auto update = [&](int c0, int c1, int k0, int k1) {   // columns [c0, c1) right of panel [k0, k1): TRSM + rank-64 update
+        if (c1 <= c0) return;
+        lu_trsm_kernel<<<(c1 - c0 + 63) / 64, 64, 0, S0>>>(dA + k0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, c1 - c0);
+        c->launches += 1;
+        if (k1 >= n) return;
+        if (!old_gemm && (ld & 1) == 0) {
+            lu_gemm2_launch(c, dA + k1 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, dA + k1 + (size_t)c0 * ld, ld, n - k1, c1 - c0, nullptr,
+                            lookahead ? la_max_per : (1 << 30));
+        } else {
+            const size_t gemm_smem1 = (size_t)(GM_K * GM_SA + GM_BN * GM_SB) * sizeof(double);
+            dim3 grid((n - k1 + GM_BM - 1) / GM_BM, (n - k1 + GM_BN - 1) / GM_BN);
+            lu_gemm_dmma_kernel<<<grid, 256, gemm_smem1, S0>>>(dA, ld, n, k0, k1);   // whole trailing matrix (c0 == k1, c1 == n)
+            c->launches += 1;
+        }
+    };
+    pst = lu_panel_factor(c, PW, dA, ld, n, 0, std::min(LU_NB, n), d_vv, d_piv, d_perm, S0);
+    if (pst != ML_OK) { PW.release(); return pst; }
+    for (int k0 = 0; k0 < n; k0 += LU_NB) {
+        const int k1 = std::min(k0 + LU_NB, n), k2 = std::min(k1 + LU_NB, n);
+        if (lookahead && k0 > 0) ML_CUDA(c, cudaStreamWaitEvent(S0, c->ev_panel, 0));   // panel [k0, k1) is factored
+        if (k1 < n) {
+            if (lookahead) {
+                // the strip first, then panel k+1 goes to the second stream
+                laswp(k1, k2, k0, k1);
+                update(k1, k2, k0, k1);
+                ML_CUDA(c, cudaEventRecord(c->ev_strip, S0));
+                ML_CUDA(c, cudaStreamWaitEvent(S1, c->ev_strip, 0));
+                pst = lu_panel_factor(c, PW, dA, ld, n, k1, k2, d_vv, d_piv, d_perm, S1, true);
+                if (pst != ML_OK) { PW.release(); return pst; }
+                ML_CUDA(c, cudaEventRecord(c->ev_panel, S1));
+                laswp(0, k0, k0, k1);
+                laswp(k2, n, k0, k1);
+                update(k2, n, k0, k1);
+            } else {
+                laswp(0, k0, k0, k1);
+                laswp(k1, n, k0, k1);
+                update(k1, n, k0, k1);
+                pst = lu_panel_factor(c, PW, dA, ld, n, k1, k2, d_vv, d_piv, d_perm, S0);
+                if (pst != ML_OK) { PW.release(); return pst; }
             }
+        } else {
+            laswp(0, k0, k0, k1);
         }
         ML_CUDA(c, cudaGetLastError());
     }
@@ -1132,7 +1176,7 @@ ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int
         dist_gather_panel_kernel<<<dim3((N - k0 + 255) / 256, nb), 256, 0, c->stream>>>(Gall.p, S, nb, perm.p, k0, N, Pbuf.p, NP);
         c->launches += 1;
         // 2. factor it (replicated); the kernel addresses column k0 + c at A + (k0 + c) * ld
-        st = lu_panel_factor(c, PW, Pbuf.p - (size_t)k0 * NP, NP, N, k0, k1, vv.p, piv.p, perm.p);
+        st = lu_panel_factor(c, PW, Pbuf.p - (size_t)k0 * NP, NP, N, k0, k1, vv.p, piv.p, perm.p, c->stream);
         if (st != ML_OK) goto done;
         if (!PW.all_coop) {
             dist_apply_piv_kernel<<<1, 32, 0, c->stream>>>(piv.p, k0, k1, perm.p);
