@@ -625,20 +625,6 @@ __global__ void __launch_bounds__(64) lu_trsv_diag_kernel(const double* __restri
     if (t < nb) x[k0 + t] = sx[t];
 }
 
-// x[r0..r1) -= A[r0..r1, k0..k1) * x[k0..k1)
-__global__ void __launch_bounds__(256) lu_trsv_update_kernel(const double* __restrict__ A, int ld, int r0, int r1, int k0, int k1,
-                                                              double* __restrict__ x) {
-    __shared__ double sx[LU_NB];
-    const int nb = k1 - k0;
-    if (threadIdx.x < nb) sx[threadIdx.x] = x[k0 + threadIdx.x];
-    __syncthreads();
-    int r = r0 + blockIdx.x * 256 + threadIdx.x;
-    if (r >= r1) return;
-    double acc = 0.;
-    for (int c = 0; c < nb; ++c) acc = fma(A[r + (size_t)(k0 + c) * ld], sx[c], acc);
-    x[r] -= acc;
-}
-
 // x = P b: the interchanges of the factorisation (linalg.f90:311-316 "untangle pivoting") composed into one gather
 __global__ void lu_permute_kernel(const double* __restrict__ b, const int* __restrict__ perm, int n, double* __restrict__ x) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -648,7 +634,7 @@ __global__ void lu_permute_kernel(const double* __restrict__ b, const int* __res
 // One step of the blocked forward substitution in ONE launch: x[k0..k1) is final; every row below gets
 // x[r] -= L(r, k0..k1) . x[k0..k1), and the CTA that holds the next diagonal block solves it straight away (unit lower
 // triangular, one warp, column order), so a step costs one launch instead of two.  Same operation order per element
-// as lu_trsv_update_kernel followed by lu_trsv_diag_kernel.
+// as a separate update of the rows followed by lu_trsv_diag_kernel on the block.
 __global__ void __launch_bounds__(256) lu_fwd_step_kernel(const double* __restrict__ A, int ld, int n, int k0, int k1, double* __restrict__ x) {
     __shared__ double sx[LU_NB];
     __shared__ double sy[LU_NB];
