@@ -357,12 +357,12 @@ def main():
 
     # ---- reduce over ranks: max time, sum of pairs ---------------------------------------------------
     vals = torch.tensor([step_ms_local, e2e_ms_local, float(np.mean(asm_ms)), float(np.mean(sol_ms)), step_wall_ms_local,
-                         e2e_dev_ms_local], dtype=torch.float64, device=f"cuda:{local}")
+                         e2e_dev_ms_local, gp.gemv_ms, gp.comm_ms], dtype=torch.float64, device=f"cuda:{local}")
     pairs_t = torch.tensor([float(local_pairs)], dtype=torch.float64, device=f"cuda:{local}")
     if dist is not None:
         dist.all_reduce(vals, op=dist.ReduceOp.MAX)
         dist.all_reduce(pairs_t, op=dist.ReduceOp.SUM)
-    step_ms, e2e_ms, a_ms, s_ms, step_wall_ms, e2e_dev_ms = [float(v) for v in vals.cpu()]
+    step_ms, e2e_ms, a_ms, s_ms, step_wall_ms, e2e_dev_ms, gemv_ms_max, comm_ms_max = [float(v) for v in vals.cpu()]
     pairs = float(pairs_t.cpu()[0])
 
     if rank == 0:
@@ -410,7 +410,10 @@ def main():
                        "pairs_per_step": pairs, "matrix_solver": args.matrix_solver, "parallelism": f"row-sharded x{world}",
                        "l2": "inputs larger than L2: A (8*N^2 bytes) is rewritten by every assembly and streamed by every matvec"},
             "assemble": {"ms": a_ms, "pairs_per_s": pairs / (a_ms * 1e-3)},
-            "solve": {"ms": s_ms, "iterations": int(info.iterations), "res_norm": info.res_norm, "res_max": info.res_max},
+            "solve": {"ms": s_ms, "iterations": int(info.iterations), "res_norm": info.res_norm, "res_max": info.res_max,
+                      "breakdown_ms": {"matvec_kernels": gemv_ms_max, "exchange_allgather": comm_ms_max,
+                                       "orthogonalisation_and_host": max(0.0, s_ms - gemv_ms_max - comm_ms_max),
+                                       "how": "CUDA events per launch in one separately profiled step, max over ranks"}},
             "end_to_end_solve_ms": step_ms,
             "timing": {"ms_per_step": "CUDA events on the context's stream, max over ranks", "wall_ms_per_step": step_wall_ms,
                        "e2e": "wall clock between barriers (includes host-side table packing), max over ranks",

@@ -204,6 +204,8 @@ typedef struct ml_profile {
     long long gemv_bytes;      /* algorithmic bytes of those launches: 8*rows*cols each             */
     double gemv_ms;            /* summed device time of those launches                               */
     double assemble_ms;        /* device time of the last assembly                                   */
+    double comm_ms;            /* multi-GPU: summed device time of the exchange step after those launches
+                                  (ncclAllGather of the Krylov vector + compaction)                     */
 } ml_profile;
 ml_status ml_set_profiling(ml_ctx *ctx, int on);
 ml_status ml_get_profile(ml_ctx *ctx, ml_profile *out);

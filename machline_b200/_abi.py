@@ -89,4 +89,4 @@ def solver_opts(matrix_solver="GMRES", preconditioner="DIAG", tol=1e-12, rel=0.8
 
 class MlProfile(C.Structure):
     _fields_ = [("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("gemv_launches", C.c_longlong),
-                ("gemv_bytes", C.c_longlong), ("gemv_ms", C.c_double), ("assemble_ms", C.c_double)]
+                ("gemv_bytes", C.c_longlong), ("gemv_ms", C.c_double), ("assemble_ms", C.c_double), ("comm_ms", C.c_double)]

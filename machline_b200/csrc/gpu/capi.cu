@@ -92,6 +92,7 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     for (auto& e : c->slot_ev)
         if (e) cudaEventDestroy(e);
 #ifdef ML_HAVE_NCCL
+    mlgpu::p2p_release(c);
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
     c->d_recs.release();
@@ -126,6 +127,12 @@ extern "C" ml_status ml_set_profiling(ml_ctx* c, int on) {
 }
 
 static void drain_gemv_events(ml_ctx* c) {
+    for (size_t i = 0; i + 1 < c->comm_ev.size(); i += 2) {   // before the gemv pairs: they own the first event of each pair
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->comm_ev[i], c->comm_ev[i + 1]) == cudaSuccess) c->comm_ms += ms;
+        cudaEventDestroy(c->comm_ev[i + 1]);
+    }
+    c->comm_ev.clear();
     for (size_t i = 0; i + 1 < c->gemv_ev.size(); i += 2) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, c->gemv_ev[i], c->gemv_ev[i + 1]) == cudaSuccess) c->gemv_ms += ms;
@@ -146,6 +153,7 @@ extern "C" ml_status ml_get_profile(ml_ctx* c, ml_profile* out) {
     out->gemv_bytes = c->gemv_bytes;
     out->gemv_ms = c->gemv_ms;
     out->assemble_ms = c->assemble_ms;
+    out->comm_ms = c->comm_ms;
     return ML_OK;
 }
 
@@ -157,6 +165,7 @@ extern "C" ml_status ml_reset_profile(ml_ctx* c) {
     c->h2d_bytes = c->d2h_bytes = 0;
     c->gemv_launches = c->gemv_bytes = 0;
     c->gemv_ms = 0;
+    c->comm_ms = 0;
     return ML_OK;
 }
 
@@ -237,6 +246,7 @@ extern "C" ml_status ml_set_communicator(ml_ctx* c, const void* id, int rank, in
     cudaSetDevice(c->device);
     ncclUniqueId uid;
     std::memcpy(&uid, id, sizeof uid);
+    mlgpu::p2p_release(c);
     if (c->comm) {
         ncclCommDestroy(c->comm);
         c->comm = nullptr;

@@ -111,6 +111,8 @@ struct Ctx {
     long long h2d_bytes = 0, d2h_bytes = 0;
     bool profile = false;
     std::vector<cudaEvent_t> gemv_ev;   // start/stop pairs around gemv_n_partial launches (profiling only)
+    std::vector<cudaEvent_t> comm_ev;   // (end of local matvec, end of all-gather + compaction) pairs; the first is owned by gemv_ev
+    double comm_ms = 0;
     // GMRES host pipeline: pinned Hessenberg-column slots and their events, kept across solves
     double* h_pinned = nullptr;
     size_t h_pinned_n = 0;
@@ -150,6 +152,16 @@ struct Ctx {
     ncclComm_t comm = nullptr;
 #endif
     std::vector<int> shard_row0, shard_nrows;  // per rank (equal split)
+    // Peer-memory exchange of the Krylov vector (solve_kernels.cu: p2p_setup): every rank maps every other rank's window
+    // (CUDA IPC); after the matvec one CTA per peer stores this rank's rows of w straight into that peer's window over NVLink
+    // and raises a flag there.
+    static constexpr int P2P_MAX = 8;
+    double* win = nullptr;              // this rank's window: [2][win_n] doubles, then [2][P2P_MAX] flags
+    size_t win_n = 0;                   // doubles per parity buffer
+    void* peer_base[P2P_MAX] = {};      // mapped windows (peer_base[rank] == win)
+    unsigned* p2p_done = nullptr;       // unused scratch counter (kept zero)
+    unsigned p2p_seq = 0;               // matvecs exchanged so far (identical on every rank)
+    bool p2p_ok = false;
 
     ml_status fail(ml_status st, const std::string& msg) {
         err = msg;
@@ -177,6 +189,7 @@ int aic_record_stride(bool supersonic);
 int aic_list_bytes(int chunk_records);
 
 // solve_kernels.cu / lu_kernels.cu
+void p2p_release(Ctx* c);   // unmap the peer windows (no-op without NCCL)
 ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info);
 ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_b, const ml_solver_opts* opts,
                              double* x_out, ml_solve_info* info, bool A_is_scratch);

@@ -39,6 +39,30 @@ __device__ __forceinline__ double2 ld_stream_d2(const double* p) {
     return v;
 }
 
+// Multi-GPU exchange of the matvec result over peer memory (no collective call): every rank maps every other rank's
+// window (CUDA IPC).  p2p_push_kernel, one CTA per destination rank, stores this rank's rows of w straight into that
+// rank's window at their global row index (NVLink / NVSwitch stores) and then raises this rank's flag there (release,
+// system scope); p2p_wait_copy_kernel on the destination spins on the `world` flags of its own window.
+// A first version issued the peer stores from the matvec kernel itself (the CTA finishing a 64-row block wrote its rows
+// to every window, the last one raised the flags).  Measured on 2 x B200: exchange 19 -> 7 us per iteration but the
+// matvec kernel +13 us (every finishing CTA needs a system-scope fence before the block counter and they all finish
+// in the last microseconds of the kernel), net zero; one push CTA per peer needs `world` fences in total.
+struct P2PArgs {
+    double* w[Ctx::P2P_MAX];        // parity buffer of this matvec in every rank's window
+    unsigned* flags[Ctx::P2P_MAX];  // flags[p][rank] <- seq
+    unsigned seq;
+    int rank, row0, n_rows;
+};
+
+__global__ void __launch_bounds__(512) p2p_push_kernel(const double* __restrict__ y_local, const P2PArgs pp) {
+    const int p = blockIdx.x;
+    double* dst = pp.w[p] + pp.row0;
+    for (int i = threadIdx.x; i < pp.n_rows; i += 512) dst[i] = y_local[i];
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.flags[p] + pp.rank), "r"(pp.seq) : "memory");
+}
+
 // The CTA that finishes a 64-row block last (ticket counter per row block) adds the split partials in split order and
 // writes y = alpha * sum: the result does not depend on which CTA that is, and no second kernel is needed.
 __global__ void __launch_bounds__(GEMV_THREADS) gemv_n_partial_kernel(const double* __restrict__ A, int ld, int n_rows_pad,
@@ -554,6 +578,103 @@ __global__ void recip_kernel(const double* src, double* dst) { *dst = 1. / *src;
 // ---------------------------------------------------------------------------------------------------
 // Host-side drivers
 // ---------------------------------------------------------------------------------------------------
+// Consumer of the fused exchange: wait until every rank has raised its flag for matvec `seq` in this rank's window, then
+// copy the assembled vector out of the window (L2 loads: the window is written by peers, never cached in L1).
+__global__ void __launch_bounds__(256) p2p_wait_copy_kernel(const double* __restrict__ win_w, const unsigned* __restrict__ flags, unsigned seq,
+                                                             int world, int n, double* __restrict__ y_full) {
+    if (threadIdx.x < world) {
+        unsigned v;
+        do {
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + threadIdx.x) : "memory");
+        } while ((int)(v - seq) < 0);
+    }
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i < n) y_full[i] = __ldcg(win_w + i);
+}
+
+#ifdef ML_HAVE_NCCL
+// Map every rank's window into this process (CUDA IPC; one process per GPU on one node).  Collective: every rank calls
+// it with the same n.  On any failure on any rank all ranks fall back to ncclAllGather (p2p_ok = false).
+static void p2p_teardown(Ctx* c) {
+    for (int r = 0; r < Ctx::P2P_MAX; ++r) {
+        if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
+        c->peer_base[r] = nullptr;
+    }
+    if (c->win) cudaFree(c->win);
+    if (c->p2p_done) cudaFree(c->p2p_done);
+    c->win = nullptr;
+    c->p2p_done = nullptr;
+    c->win_n = 0;
+    c->p2p_ok = false;
+    cudaGetLastError();
+}
+
+void p2p_release(Ctx* c) { p2p_teardown(c); }
+
+static size_t p2p_window_bytes(size_t win_n) { return 2 * win_n * sizeof(double) + 2 * Ctx::P2P_MAX * sizeof(unsigned); }
+
+static ml_status p2p_setup(Ctx* c, int n) {
+    static const bool disabled = std::getenv("MACHLINE_NO_P2P") != nullptr;
+    if (c->world < 2 || c->world > Ctx::P2P_MAX || disabled) { c->p2p_ok = false; return ML_OK; }
+    const size_t need = ((size_t)n + 63) / 64 * 64;
+    if (c->p2p_ok && c->win_n >= need) return ML_OK;
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    p2p_teardown(c);
+    int ok = 1;
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof mine);
+    if (cudaMalloc((void**)&c->win, p2p_window_bytes(need)) != cudaSuccess || cudaMalloc((void**)&c->p2p_done, sizeof(unsigned)) != cudaSuccess ||
+        cudaMemset(c->win, 0, p2p_window_bytes(need)) != cudaSuccess || cudaMemset(c->p2p_done, 0, sizeof(unsigned)) != cudaSuccess ||
+        cudaIpcGetMemHandle(&mine, c->win) != cudaSuccess)
+        ok = 0;
+    cudaGetLastError();
+    // exchange the handles (and whether everyone got this far)
+    DevBuf<unsigned char> hs, ha;
+    DevBuf<int> dok;
+    ML_CUDA(c, hs.alloc(sizeof mine));
+    ML_CUDA(c, ha.alloc(sizeof mine * c->world));
+    ML_CUDA(c, dok.alloc(1));
+    std::vector<unsigned char> all(sizeof mine * c->world);
+    ML_CUDA(c, cudaMemcpyAsync(hs.p, &mine, sizeof mine, cudaMemcpyHostToDevice, c->stream));
+    ML_CUDA(c, cudaMemcpyAsync(dok.p, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (ncclAllGather(hs.p, ha.p, sizeof mine, ncclChar, c->comm, c->stream) != ncclSuccess ||
+        ncclAllReduce(dok.p, dok.p, 1, ncclInt, ncclMin, c->comm, c->stream) != ncclSuccess)
+        return c->fail(ML_NCCL_ERROR, "p2p_setup: handle exchange");
+    ML_CUDA(c, cudaMemcpyAsync(all.data(), ha.p, all.size(), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaMemcpyAsync(&ok, dok.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    if (ok) {
+        for (int r = 0; r < c->world && ok; ++r) {
+            if (r == c->rank) { c->peer_base[r] = c->win; continue; }
+            cudaIpcMemHandle_t hnd;
+            std::memcpy(&hnd, all.data() + (size_t)r * sizeof hnd, sizeof hnd);
+            if (cudaIpcOpenMemHandle(&c->peer_base[r], hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                c->peer_base[r] = nullptr;
+                ok = 0;
+            }
+        }
+        cudaGetLastError();
+    }
+    // everyone mapped everyone?
+    ML_CUDA(c, cudaMemcpyAsync(dok.p, &ok, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    if (ncclAllReduce(dok.p, dok.p, 1, ncclInt, ncclMin, c->comm, c->stream) != ncclSuccess) return c->fail(ML_NCCL_ERROR, "p2p_setup: agreement");
+    ML_CUDA(c, cudaMemcpyAsync(&ok, dok.p, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    hs.release();
+    ha.release();
+    dok.release();
+    if (!ok) {
+        p2p_teardown(c);
+        return ML_OK;
+    }
+    c->win_n = need;
+    c->p2p_seq = 0;
+    c->p2p_ok = true;
+    return ML_OK;
+}
+#endif
+
 // y_full[row0[r] + i] = gather[r * shard_pad + i], i < nrows[r]   (shards = row0[0..world), nrows[0..world))
 __global__ void compact_shards_kernel(const double* __restrict__ gather, int shard_pad, const int* __restrict__ shards, int world,
                                       double* __restrict__ y_full) {
@@ -584,6 +705,10 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
         ML_CUDA(c, tickets.alloc(row_blocks));
         ML_CUDA(c, cudaMemsetAsync(tickets.p, 0, (size_t)row_blocks * sizeof(unsigned), c->stream));
         if (c->world > 1) {
+#ifdef ML_HAVE_NCCL
+            ml_status ps = p2p_setup(c, N);
+            if (ps != ML_OK) return ps;
+#endif
             ML_CUDA(c, gather.alloc((size_t)shard_pad * c->world));
             ML_CUDA(c, d_shards.alloc(2 * c->world));
             std::vector<int> h(2 * c->world);
@@ -606,6 +731,7 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
             ML_CUDA(c, cudaEventCreate(&e1));
             ML_CUDA(c, cudaEventRecord(e0, c->stream));
         }
+        const bool p2p = c->world > 1 && c->p2p_ok;
         gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p, tickets.p,
                                                                      n_rows, alpha_dev, alpha, dst);
         if (c->profile) {
@@ -617,6 +743,35 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
         }
         c->launches += 1;
         ML_CUDA(c, cudaGetLastError());
+        if (p2p) {
+            c->p2p_seq += 1;
+            const unsigned par = c->p2p_seq & 1u;
+            P2PArgs pp;
+            for (int r = 0; r < Ctx::P2P_MAX; ++r) {
+                double* base = reinterpret_cast<double*>(c->peer_base[r < c->world ? r : c->rank]);
+                pp.w[r] = base + (size_t)par * c->win_n;
+                pp.flags[r] = reinterpret_cast<unsigned*>(base + 2 * c->win_n) + par * Ctx::P2P_MAX;
+            }
+            pp.seq = c->p2p_seq;
+            pp.rank = c->rank;
+            pp.row0 = row0;
+            pp.n_rows = n_rows;
+            p2p_push_kernel<<<c->world, 512, 0, c->stream>>>(dst, pp);
+            c->launches += 1;
+            const double* ww = c->win + (size_t)par * c->win_n;
+            const unsigned* fl = reinterpret_cast<const unsigned*>(c->win + 2 * c->win_n) + par * Ctx::P2P_MAX;
+            p2p_wait_copy_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(ww, fl, c->p2p_seq, c->world, N, y_full);
+            c->launches += 1;
+            if (c->profile) {
+                cudaEvent_t e2 = nullptr;
+                ML_CUDA(c, cudaEventCreate(&e2));
+                ML_CUDA(c, cudaEventRecord(e2, c->stream));
+                c->comm_ev.push_back(e1);
+                c->comm_ev.push_back(e2);
+            }
+            ML_CUDA(c, cudaGetLastError());
+            return ML_OK;
+        }
 #ifdef ML_HAVE_NCCL
         if (c->world > 1) {
             ncclResult_t r = ncclAllGather(gather.p + (size_t)c->rank * shard_pad, gather.p, shard_pad, ncclDouble, c->comm, c->stream);
@@ -625,6 +780,13 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
             compact_shards_kernel<<<dim3((shard_pad + 255) / 256, c->world), 256, 0, c->stream>>>(gather.p, shard_pad, d_shards.p, c->world,
                                                                                                    y_full);
             c->launches += 1;
+            if (c->profile) {   // exchange step = all-gather + compaction, timed from the end of the local matvec
+                cudaEvent_t e2 = nullptr;
+                ML_CUDA(c, cudaEventCreate(&e2));
+                ML_CUDA(c, cudaEventRecord(e2, c->stream));
+                c->comm_ev.push_back(e1);
+                c->comm_ev.push_back(e2);
+            }
         }
 #endif
         return ML_OK;

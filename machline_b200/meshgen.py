@@ -163,3 +163,45 @@ def sphere_input(mesh_file: str, matrix_solver: str = "GMRES") -> dict:
         "post_processing": {},
         "output": {"verbose": False},
     }
+
+
+def sears_haack(n_ax: int = 80, n_theta: int = 30, length: float = 0.6096, rmax_over_length: float = 0.037879):
+    """Closed Sears-Haack body of revolution along +x, r(x) = rmax (4 x/L (1 - x/L))^(3/4), pointed nose and tail
+    (BASELINE configs[2]/[4] family; the shape of the reference's studies/sears_haack/gen_SH_geometry.py, rebuilt
+    here with array operations): n_ax axial stations including both apexes, n_theta points per ring, triangle fans at
+    the ends and two triangles per quad in between, oriented outwards.  2 n_theta (n_ax - 2) panels."""
+    rmax = rmax_over_length * length
+    xs = np.linspace(0.0, length, n_ax)
+    r = rmax * (4.0 * (xs / length) * (1.0 - xs / length)) ** 0.75
+    th = 2.0 * np.pi * np.arange(n_theta) / n_theta
+    rings = np.stack([np.repeat(xs[1:-1, None], n_theta, axis=1),
+                      r[1:-1, None] * np.sin(th)[None, :],
+                      r[1:-1, None] * np.cos(th)[None, :]], axis=2).reshape(-1, 3)
+    pts = np.vstack([[0.0, 0.0, 0.0], rings, [length, 0.0, 0.0]])
+    n_rings = n_ax - 2
+    ring = lambda i: 1 + i * n_theta + np.arange(n_theta)      # noqa: E731  vertex ids of ring i
+    nxt = lambda a: np.roll(a, -1)                              # noqa: E731
+    tris = [np.stack([np.zeros(n_theta, dtype=np.int64), ring(0), nxt(ring(0))], axis=1)]
+    for i in range(n_rings - 1):
+        a, b = ring(i), ring(i + 1)
+        tris.append(np.stack([a, b, nxt(b)], axis=1))
+        tris.append(np.stack([a, nxt(b), nxt(a)], axis=1))
+    last = len(pts) - 1
+    tris.append(np.stack([ring(n_rings - 1), np.full(n_theta, last), nxt(ring(n_rings - 1))], axis=1))
+    tris = np.vstack(tris).astype(np.int32)
+    if check_outward(pts, tris) < 0:
+        tris = tris[:, ::-1].copy()
+    return pts, tris
+
+
+def sears_haack_input(mesh_file: str, mach: float = 2.0, matrix_solver: str = "GMRES") -> dict:
+    """Supersonic slender body, no wake, source-free formulation, the study's control-point offset
+    (studies/sears_haack/sears_haack_input.json); every pair goes through the domain-of-dependence test."""
+    return {
+        "flow": {"freestream_velocity": [1.0, 0.0, 0.0], "gamma": 1.4, "freestream_mach_number": mach},
+        "geometry": {"file": mesh_file, "spanwise_axis": "+y", "wake_model": {"wake_present": False},
+                     "reference": {"area": 1.675e-3}},
+        "solver": {"formulation": "dirichlet-source-free", "matrix_solver": matrix_solver, "control_point_offset": 1.1e-8},
+        "post_processing": {},
+        "output": {"verbose": False},
+    }

@@ -26,7 +26,9 @@ from machline_b200 import _abi, gpu, host, meshgen, shard  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--dims", default="226x112")
 ap.add_argument("--solvers", default="GMRES,LU")
-ap.add_argument("--mach", type=float, default=0.5)
+ap.add_argument("--mach", type=float, default=None)
+ap.add_argument("--case", default="wing", choices=["wing", "sears_haack"],
+                help="wing: mirrored half wing with wake, M = 0.5 (configs[1]/[4]); sears_haack: supersonic slender body, M = 2 (configs[2])")
 args = ap.parse_args()
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
 local = int(os.environ.get("LOCAL_RANK", rank))
@@ -36,9 +38,18 @@ if world > 1:
 nc, ns = (int(v) for v in args.dims.split("x"))
 tmp = tempfile.mkdtemp(prefix=f"machline_scale_r{rank}_")
 t0 = time.perf_counter()
-pts, tris = meshgen.swept_wing_half(nc, ns)
-meshgen.write_vtk(f"{tmp}/w.vtk", pts, tris)
-case = host.Case(meshgen.wing_input("w.vtk", mach=args.mach), base_dir=tmp)
+if args.case == "wing":
+    mach = 0.5 if args.mach is None else args.mach
+    pts, tris = meshgen.swept_wing_half(nc, ns)
+    meshgen.write_vtk(f"{tmp}/w.vtk", pts, tris)
+    case = host.Case(meshgen.wing_input("w.vtk", mach=mach), base_dir=tmp)
+    label = f"half wing {nc}x{ns}, M={mach}"
+else:
+    mach = 2.0 if args.mach is None else args.mach
+    pts, tris = meshgen.sears_haack(nc, ns)
+    meshgen.write_vtk(f"{tmp}/w.vtk", pts, tris)
+    case = host.Case(meshgen.sears_haack_input("w.vtk", mach=mach), base_dir=tmp)
+    label = f"Sears-Haack body {nc}x{ns}, M={mach}, source-free"
 host_s = time.perf_counter() - t0
 N = case.n_cp
 row0, nrows = shard.row_shard(N, rank, world)
@@ -80,7 +91,7 @@ for solver in args.solvers.split(","):
     if rank == 0:
         res = case.post(x)
         a_ms, s_ms, w_s = (float(v) for v in vals.cpu())
-        print(json.dumps({"case": f"half wing {nc}x{ns}, M={args.mach}", "n_gpus": world, "n_panels": case.info.n_body_panels,
+        print(json.dumps({"case": label, "n_gpus": world, "n_panels": case.info.n_body_panels,
                           "n_unknown": N, "A_bytes": 8.0 * N * N, "pairs": float(case.n_pairs), "matrix_solver": solver,
                           "host_setup_s": host_s, "assemble_ms": a_ms, "assemble_first_wall_s": asm_wall,
                           "pairs_per_s": case.n_pairs / (a_ms * 1e-3), "solve_ms": s_ms, "solve_wall_s": w_s,

@@ -112,3 +112,41 @@ def test_row_shard_assembles_the_same_rows(ctx):
     A_part = ctx.get_A()
     np.testing.assert_allclose(A_part, A_full[r0:r0 + nr], rtol=1e-13, atol=1e-18)
     case.close()
+
+
+def _synthetic_case(kind, tmp_path):
+    from machline_b200 import host, meshgen
+    if kind == "sears_haack":      # BASELINE configs[2]: supersonic slender body, every pair DoD-tested, source-free
+        pts, tris = meshgen.sears_haack(28, 14)
+        meshgen.write_vtk(tmp_path / "m.vtk", pts, tris)
+        return host.Case(meshgen.sears_haack_input("m.vtk", mach=2.0), base_dir=str(tmp_path))
+    if kind == "wing":             # BASELINE configs[1] family (the bench workload, small): mirrored, wake, M = 0.5
+        pts, tris = meshgen.swept_wing_half(20, 10)
+        meshgen.write_vtk(tmp_path / "m.vtk", pts, tris)
+        return host.Case(meshgen.wing_input("m.vtk", mach=0.5), base_dir=str(tmp_path))
+    pts, tris = meshgen.icosphere(2)   # BASELINE configs[0] family
+    meshgen.write_vtk(tmp_path / "m.vtk", pts, tris)
+    return host.Case(meshgen.sphere_input("m.vtk"), base_dir=str(tmp_path))
+
+
+@pytest.mark.parametrize("kind", ["sears_haack", "wing", "sphere"])
+def test_synthetic_bench_families_match_oracle(ctx, kind, tmp_path):
+    """The synthetic meshes bench.py / scripts/scale_run.py are run on, at sizes the oracle finishes in seconds: AIC entries,
+    I_known, GMRES iteration count and the solution against the oracle."""
+    case = _synthetic_case(kind, tmp_path)
+    ctx.set_case(case)
+    I_known = ctx.assemble()
+    A = ctx.get_A()
+    A_ref, I_ref, S = ob.assemble(case, with_scale=True)
+    assert ((A == 0) == (A_ref == 0)).all()
+    assert _rel_err(A, A_ref, S).max() < 2e-14
+    assert (np.abs(A - A_ref) / np.abs(A_ref).max(axis=1, keepdims=True)).max() < 1e-12
+    assert np.abs(I_known - I_ref).max() <= 1e-13 * max(1e-300, np.abs(I_ref).max())
+    x, info = ctx.solve(case.solver_opts(), case.BC)
+    x_ref, info_ref = ob.solve_system(A_ref, I_ref, case.BC, case.solver_opts())
+    assert abs(info.iterations - info_ref.iterations) <= 1
+    assert np.abs(x - x_ref).max() <= 1e-9 * np.abs(x_ref).max()
+    res, res_ref = case.post(x), case.post(x_ref)
+    assert abs(res.C_p_max - res_ref.C_p_max) < 1e-9 and abs(res.C_p_min - res_ref.C_p_min) < 1e-9
+    assert np.abs(np.array(res.C_F) - np.array(res_ref.C_F)).max() < 1e-9
+    case.close()
