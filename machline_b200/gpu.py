@@ -103,6 +103,38 @@ class Context:
         self._check(L.ml_set_row_shard(self._h, row0, nrows))
         self.row0, self.nrows = row0, nrows
 
+    def set_points(self, case, points: np.ndarray):
+        """Stage `case` with the rows of the system replaced by arbitrary field points (boundary condition "zero
+        potential", no sorting): ml_assemble then builds the influence matrix of every unknown on those points, which is
+        what the reference's off-body sweep evaluates (surface_mesh_get_induced_potentials_at_point,
+        src/surface_mesh.f90:2282-2385)."""
+        L = lib()
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        n = pts.shape[0]
+        bc = np.full(n, 1, dtype=np.int32)            # ML_BC_ZERO_POTENTIAL
+        rows = np.arange(n, dtype=np.int32)
+        m = _abi.MlSystemMap()
+        C.memmove(C.byref(m), C.byref(case.map), C.sizeof(m))
+        m.n_cp = n
+        self._check(L.ml_set_flow(self._h, C.byref(case.flow)))
+        wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
+        self._check(L.ml_set_panels(self._h, C.byref(case.body), wake))
+        self._check(L.ml_set_control_points(self._h, n, _dp(pts), bc.ctypes.data_as(_abi.c_int_p), None,
+                                            rows.ctypes.data_as(_abi.c_int_p)))
+        self._check(L.ml_set_system_map(self._h, C.byref(m)))
+        self._check(L.ml_set_row_shard(self._h, 0, n))
+        self.n_unknown, self.n_cp = case.n_unknown, n
+        self.row0, self.nrows = 0, n
+
+    def potentials_at(self, case, points: np.ndarray, x: np.ndarray):
+        """(phi_d, phi_s) induced at `points` by the solved strengths x (per unit freestream speed): phi_d = A_points x,
+        phi_s = the known-source sum the assembly returns as I_known.  Wake panels contribute to phi_d with their
+        (top - bottom) strengths, as in the AIC rows."""
+        self.set_points(case, points)
+        phi_s = self.assemble()
+        phi_d = self.get_A() @ np.asarray(x, dtype=np.float64)
+        return phi_d, phi_s
+
     def set_communicator(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(unique_id, len(unique_id))
         self._check(lib().ml_set_communicator(self._h, buf, rank, world))

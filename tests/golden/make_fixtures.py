@@ -9,6 +9,11 @@ Outputs (all under tests/golden/):
                                loader sees exactly the same vertex list and ordering.
   reference_goldens.json    -- the (C_p_max, C_p_min, Cx, Cy, Cz) tuples and tolerances asserted by
                                test/test_machline.py, with the input each test builds.
+  offbody_potentials.json   -- the reference's stored off-body results test/input_files/half_wing_{inc,supersonic}_offbody_points_correct.csv
+                               (400 field points in the root xz plane; written by panel_solver_export_off_body_points,
+                               src/panel_solver.f90:2771-2895, format e20.13): x, y, z, phi_d, phi_s and the inputs that the
+                               (commented-out) tests 22 / 23 of test/test_machline.py:636-730 build.  They pin the potential
+                               integrals at arbitrary field points.
   prototype_integrals.json  -- known-answer H(1,1,1) / hH(1,1,3) / F(1,1,1) values computed by
                                IMPORTING the reference's Python prototype dev/unit_tests/panel.py
                                (quadrilateral panels in local coordinates) at fixed points.
@@ -162,7 +167,27 @@ def make_prototype_integrals():
     print("prototype_integrals.json:", len(cases), "cases")
 
 
+def make_offbody():
+    """The two off-body golden tables and the inputs of the tests that produced them (test_machline.py:636-730)."""
+    out = {"source": "test/input_files/*_offbody_points_correct.csv, columns x,y,z,phi_d,phi_s (0,1,2,4,5 of 24), e20.13",
+           "cases": []}
+    for name, inp_file, csv_file, vel in [
+            ("half_wing_inc", "half_wing_input.json", "half_wing_inc_offbody_points_correct.csv", None),
+            ("half_wing_supersonic", "supersonic_half_wing_input.json", "half_wing_supersonic_offbody_points_correct.csv", [100.0, 5.0, 5.0])]:
+        inp = json.loads((REF / "test" / "input_files" / inp_file).read_text())
+        inp["solver"]["formulation"] = "dirichlet-morino"
+        if vel is not None:
+            inp["flow"]["freestream_velocity"] = vel
+        inp["output"] = {}
+        tab = np.genfromtxt(REF / "test" / "input_files" / csv_file, skip_header=1, delimiter=",")
+        out["cases"].append({"name": name, "input": inp, "points": tab[:, :3].tolist(), "phi_d": tab[:, 4].tolist(),
+                             "phi_s": tab[:, 5].tolist()})
+    (OUT / "offbody_potentials.json").write_text(json.dumps(out))
+    print("offbody_potentials.json:", [(c["name"], len(c["points"])) for c in out["cases"]])
+
+
 if __name__ == "__main__":
+    make_offbody()
     make_meshes()
     make_goldens()
     make_prototype_integrals()

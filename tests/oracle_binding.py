@@ -91,6 +91,23 @@ def assemble(case, row0: int = 0, nrows: int | None = None, n_threads: int = 0, 
     return A, I_known
 
 
+def assemble_at_points(case, points, with_wake: bool = True):
+    """Oracle influence matrix of every unknown on arbitrary field points (rows = points, zero-potential rows, unsorted):
+    phi_d(points) = A x, phi_s(points) = I_known.  with_wake=False leaves the wake panels out."""
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    n = pts.shape[0]
+    A = np.zeros((n, case.n_unknown), dtype=np.float64, order="F")
+    I_known = np.zeros(n, dtype=np.float64)
+    bc = np.full(n, 1, dtype=np.int32)
+    rows = np.arange(n, dtype=np.int32)
+    wake = C.byref(case.wake) if (with_wake and case.wake.n_panels > 0) else None
+    st = lib().orc_assemble(C.byref(case.flow), C.byref(case.body), wake, C.byref(case.map), n, _dp(pts),
+                            bc.ctypes.data_as(_abi.c_int_p), rows.ctypes.data_as(_abi.c_int_p), 0, n, _dp(A), n, _dp(I_known), 0, None)
+    if st != 0:
+        raise RuntimeError(f"orc_assemble status {st}")
+    return A, I_known
+
+
 def pair(case, table, j: int, img: int, P) -> OrcPairOut:
     out = OrcPairOut()
     Pa = np.ascontiguousarray(P, dtype=np.float64)
