@@ -23,8 +23,10 @@
 // __float128.  Superinclined panels are rejected by the reference at init (panel.f90:439-443), so
 // the *_supinc branches are not restated.
 //
-// Parity pinning: through the golden tuples of test/test_machline.py (tests/test_golden_cpu.py) and
-// through known-answer integrals generated from dev/unit_tests/panel.py (tests/golden/).
+// Parity pinning: through the golden tuples of test/test_machline.py (tests/test_oracle_golden.py), through the
+// reference's stored off-body potentials at 400 field points, sub- and supersonic (tests/test_oracle_offbody.py), and
+// through known-answer integrals generated from dev/unit_tests/panel.py (tests/test_oracle_integrals.py); fixtures and
+// the script that made them are under tests/golden/.
 #include <algorithm>
 #include <cmath>
 #include <cstring>
