@@ -317,11 +317,25 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 1) lu_panel_coop_kernel(cons
             s_l[r] = l;
         }
         __syncthreads();
-        const int ncr = nb - jj - 1;
-        for (int item = warp; item < ncr * nrb; item += T / 32) {
-            const int cc = item / nrb, r = ((item - cc * nrb) << 5) + lane;
-            const int c = jj + 1 + cc;
-            if (r < nr && r0 + r > j) el(r, c) = fma(-s_l[r], s_piv[c], el(r, c));
+        // items = (32-row block, group of 4 columns): four independent load / fma / store chains per thread (one element
+        // per item left the loop latency-bound: ~75 cycles per element and warp)
+        const int ncr = nb - jj - 1, ncg = (ncr + 3) >> 2;
+        for (int item = warp; item < ncg * nrb; item += T / 32) {
+            const int cg = item / nrb, r = ((item - cg * nrb) << 5) + lane;
+            const int c0 = jj + 1 + (cg << 2);
+            if (r < nr && r0 + r > j) {
+                const double ml = -s_l[r];
+                double v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + u < nb) v[u] = el(r, c0 + u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + u < nb) v[u] = fma(ml, s_piv[c0 + u], v[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (c0 + u < nb) el(r, c0 + u) = v[u];
+            }
         }
         __syncthreads();
     }
