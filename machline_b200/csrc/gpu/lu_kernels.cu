@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(256) lu_gemm_dmma_kernel(double* __restrict__ 
 // (bitwise the same result).
 constexpr int G2_THREADS = 256;
 constexpr int G2_BN = 32;                                   // columns per group tile
-constexpr size_t G2_SMEM = (size_t)(GM_K * GM_SA + 2 * 2 * G2_BN * GM_SB) * sizeof(double);
+constexpr size_t g2_smem(int nh) { return (size_t)(nh * GM_K * GM_SA + 2 * 2 * G2_BN * GM_SB) * sizeof(double); }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool pred) {
     const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
@@ -499,23 +499,27 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void group_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
 
+template <int NH>   // NH 64-wide halves of K: 1 = rank-64 update, 2 = rank-128 update (two panels applied in one pass over C)
 __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(const double* __restrict__ Lp, int ldl, const double* __restrict__ Up, int ldu,
                                                                  double* __restrict__ Cp, int ldc, int M, int Nc, int n_col_tiles,
                                                                  int tiles_per_cta, const unsigned char* __restrict__ row_block_active) {
-    // C (M x Nc, ldc) -= L (M x 64, ldl) * U (64 x Nc, ldu).  Single GPU: the three are windows of the same matrix; the
+    // C (M x Nc, ldc) -= L (M x 64 NH, ldl) * U (64 NH x Nc, ldu).  Single GPU: the three are windows of the same matrix; the
     // distributed factorisation passes the gathered multipliers of the local rows and the broadcast U12 block row, and
     // a byte per 128-row block that says whether any of its rows is still below the panel.
+    // NH = 2: L (128 x 128) stays resident; each C tile takes two steps, one per 64-row half of its U tile, through the
+    // same double buffer, and is read and written once - half the C traffic per flop of two rank-64 updates.
     extern __shared__ __align__(16) double smem[];
     if (row_block_active && !row_block_active[blockIdx.x]) return;
-    double* sA = smem;                  // [GM_K][GM_SA]   L21 (negated when the fragments are read)
+    constexpr int KT = GM_K * NH;
+    double* sA = smem;                  // [KT][GM_SA]   L21 (negated when the fragments are read)
     const int tid = threadIdx.x, grp = tid >> 7, gtid = tid & 127, warp = gtid >> 5, lane = tid & 31;
-    double* sB = smem + GM_K * GM_SA + grp * (2 * G2_BN * GM_SB);   // this group's [2][G2_BN][GM_SB] U12 tiles
+    double* sB = smem + KT * GM_SA + grp * (2 * G2_BN * GM_SB);   // this group's [2][G2_BN][GM_SB] U12 half tiles
     const int row0 = blockIdx.x * GM_BM;
     const int ct0 = blockIdx.y * tiles_per_cta + grp, ct1 = min((int)(blockIdx.y + 1) * tiles_per_cta, n_col_tiles);
     const int wm = warp * 32;
     const int g = lane >> 2, q = lane & 3;
 
-    for (int t = tid; t < GM_K * (GM_BM / 2); t += G2_THREADS) {
+    for (int t = tid; t < KT * (GM_BM / 2); t += G2_THREADS) {
         const int k = t / (GM_BM / 2), m2 = (t % (GM_BM / 2)) * 2;
         const int r = row0 + m2;
         cp_async16(sA + k * GM_SA + m2, Lp + (size_t)k * ldl + min(r, M - 1), r < M);
@@ -524,13 +528,13 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(const double* _
     cp_async_wait<0>();
     __syncthreads();
     if (ct0 >= ct1) return;
-    auto load_u = [&](int buf, int ct) {
+    auto load_u = [&](int buf, int ct, int half) {
         double* dst = sB + buf * (G2_BN * GM_SB);
         const int col0 = ct * G2_BN;
         for (int t = gtid; t < G2_BN * (GM_K / 2); t += 128) {
             const int nn = t / (GM_K / 2), k2 = (t % (GM_K / 2)) * 2;
             const int c = col0 + nn;
-            cp_async16(dst + nn * GM_SB + k2, Up + (size_t)min(c, Nc - 1) * ldu + k2, c < Nc);
+            cp_async16(dst + nn * GM_SB + k2, Up + (size_t)min(c, Nc - 1) * ldu + half * GM_K + k2, c < Nc);
         }
     };
     double cn[4][4][2];
@@ -546,12 +550,12 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(const double* _
                 cn[mt][nt][1] = (r < M && cc + 1 < Nc) ? __ldcs(Cp + r + (size_t)(cc + 1) * ldc) : 0.;
             }
     };
-    load_u(0, ct0);
+    load_u(0, ct0, 0);
     cp_async_commit();
     load_c(ct0);
     int buf = 0;
-    for (int ct = ct0; ct < ct1; ct += 2, buf ^= 1) {
-        double c[4][4][2];
+    double c[4][4][2];
+    for (int ct = ct0; ct < ct1; ct += 2) {
 #pragma unroll
         for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
@@ -559,55 +563,63 @@ __global__ void __launch_bounds__(G2_THREADS, 1) lu_gemm2_kernel(const double* _
                 c[mt][nt][0] = cn[mt][nt][0];
                 c[mt][nt][1] = cn[mt][nt][1];
             }
-        if (ct + 2 < ct1) {
-            load_u(buf ^ 1, ct + 2);
-            cp_async_commit();
-            load_c(ct + 2);
-            cp_async_wait<1>();
-        } else {
-            cp_async_wait<0>();
-        }
-        group_sync(1 + grp);
-        const double* sBb = sB + buf * (G2_BN * GM_SB);
-#pragma unroll 4
-        for (int ks = 0; ks < GM_K; ks += 4) {
-            double a[4], b[4];
 #pragma unroll
-            for (int mt = 0; mt < 4; ++mt) a[mt] = -sA[(ks + q) * GM_SA + wm + mt * 8 + g];
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) b[nt] = sBb[(nt * 8 + g) * GM_SB + ks + q];
-#pragma unroll
-            for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-                for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(c[mt][nt][0], c[mt][nt][1], a[mt], b[nt]);
-        }
-        const int col0 = ct * G2_BN;
-#pragma unroll
-        for (int mt = 0; mt < 4; ++mt)
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt) {
-                const int r = row0 + wm + mt * 8 + g;
-                const int cc = col0 + nt * 8 + 2 * q;
-                if (r < M && cc < Nc) Cp[r + (size_t)cc * ldc] = c[mt][nt][0];
-                if (r < M && cc + 1 < Nc) Cp[r + (size_t)(cc + 1) * ldc] = c[mt][nt][1];
+        for (int half = 0; half < NH; ++half, buf ^= 1) {
+            // fetch the next step's U half tile (and, on the last half, the next C tile) before computing this one
+            const bool last_half = (half == NH - 1);
+            const bool more = !last_half || (ct + 2 < ct1);
+            if (more) {
+                load_u(buf ^ 1, last_half ? ct + 2 : ct, last_half ? 0 : half + 1);
+                cp_async_commit();
+                if (last_half) load_c(ct + 2);
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
             }
-        group_sync(1 + grp);   // every warp of the group is done with sB[buf] before the next iteration refills it
+            group_sync(1 + grp);
+            const double* sBb = sB + buf * (G2_BN * GM_SB);
+            const double* sAh = sA + half * GM_K * GM_SA;
+#pragma unroll 4
+            for (int ks = 0; ks < GM_K; ks += 4) {
+                double a[4], b[4];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt) a[mt] = -sAh[(ks + q) * GM_SA + wm + mt * 8 + g];
+#pragma unroll
+                for (int nt = 0; nt < 4; ++nt) b[nt] = sBb[(nt * 8 + g) * GM_SB + ks + q];
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) dmma_m8n8k4(c[mt][nt][0], c[mt][nt][1], a[mt], b[nt]);
+            }
+            if (last_half) {
+                const int col0 = ct * G2_BN;
+#pragma unroll
+                for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+                    for (int nt = 0; nt < 4; ++nt) {
+                        const int r = row0 + wm + mt * 8 + g;
+                        const int cc = col0 + nt * 8 + 2 * q;
+                        if (r < M && cc < Nc) Cp[r + (size_t)cc * ldc] = c[mt][nt][0];
+                        if (r < M && cc + 1 < Nc) Cp[r + (size_t)(cc + 1) * ldc] = c[mt][nt][1];
+                    }
+            }
+            group_sync(1 + grp);   // every warp of the group is done with sB[buf] before the next step refills it
+        }
     }
 }
 
 // Grid shape of the trailing update: rb row blocks x `chunks` runs of 32-column tiles.  Picks the run length that
 // minimises (number of waves over the SMs) x (tiles per run + the cost of staging L21, ~3 tiles), so the last wave
 // is not mostly empty (82 row blocks x 4 runs = 2.2 waves wasted a quarter of the launch).
-static void lu_gemm2_shape(int rb, int ctiles, int num_sms, int max_per, int* per_out, int* chunks_out) {
+static void lu_gemm2_shape(int rb, int ctiles, int num_sms, int k_halves, int* per_out, int* chunks_out) {
     long long best = -1;
     int best_per = ctiles, best_chunks = 1;
     for (int chunks = 1; chunks <= ctiles; ++chunks) {
         int per = (ctiles + chunks - 1) / chunks;
         per = (per + 1) & ~1;   // both warp groups get the same number of tiles
-        if (per > max_per && per > 2) continue;   // short runs: CTAs retire often (look-ahead: the panel kernel waits for SMs)
         const int nch = (ctiles + per - 1) / per;
         const long long waves = ((long long)rb * nch + num_sms - 1) / num_sms;
-        const long long cost = waves * (per + 6);
+        const long long cost = waves * (per * k_halves + 6 * k_halves);
         if (best < 0 || cost < best) { best = cost; best_per = per; best_chunks = nch; }
         if (per <= 8) break;
     }
@@ -726,16 +738,20 @@ __global__ void __launch_bounds__(256) lu_bwd_step_kernel(const double* __restri
 
 // C (M x Nc) -= L (M x 64) * U (64 x Nc) on the FP64 tensor cores; all leading dimensions even, pointers 16-byte aligned
 void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ldu, double* Cp, int ldc, int M, int Nc,
-                     const unsigned char* row_block_active, int max_per = 1 << 30) {
+                     const unsigned char* row_block_active, int k_halves = 1) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(lu_gemm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
+        cudaFuncSetAttribute(lu_gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem(1));
+        cudaFuncSetAttribute(lu_gemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem(2));
         attr_set = true;
     }
     const int rb = (M + GM_BM - 1) / GM_BM, ct32 = (Nc + G2_BN - 1) / G2_BN;
     int per, chunks;
-    lu_gemm2_shape(rb, ct32, c->num_sms, max_per, &per, &chunks);
-    lu_gemm2_kernel<<<dim3(rb, chunks), G2_THREADS, G2_SMEM, c->stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
+    lu_gemm2_shape(rb, ct32, c->num_sms, k_halves, &per, &chunks);
+    if (k_halves == 2)
+        lu_gemm2_kernel<2><<<dim3(rb, chunks), G2_THREADS, g2_smem(2), c->stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
+    else
+        lu_gemm2_kernel<1><<<dim3(rb, chunks), G2_THREADS, g2_smem(1), c->stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
     c->launches += 1;
 }
 
@@ -837,64 +853,66 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     ml_status pst = PW.init(c);
     if (pst != ML_OK) return pst;
     static const bool old_gemm = getenv("MACHLINE_LU_GEMM_V1") != nullptr;
-    static const bool want_lookahead = getenv("MACHLINE_LU_LOOKAHEAD") != nullptr;
-    // Look-ahead (opt-in, MACHLINE_LU_LOOKAHEAD=1): once the update of panel k has reached the columns of panel k+1 (a
-    // 64-column strip, done first), panel k+1 is factored on a second, high-priority stream while the main stream
-    // applies panel k to the rest of the matrix; the two touch disjoint columns.  Measured on B200 (r01e): it does NOT
-    // pay yet - 108.6 vs 103.4 ms at N = 10.5k, 916 vs 841 ms at N = 29k - the cooperative panel grid only starts once
-    // all its CTAs fit, i.e. after the trailing update has drained, so nothing overlaps and the strip launches are pure
-    // overhead.  Kept for the next round (a non-cooperative panel kernel on a reserved set of SMs).
-    const bool lookahead = want_lookahead && !old_gemm && (ld & 1) == 0 && n > 4 * LU_NB && c->stream2 != nullptr;
-    cudaStream_t S0 = c->stream, S1 = lookahead ? c->stream2 : c->stream;
-    static const int la_max_per = getenv("MACHLINE_LU_LA_PER") ? atoi(getenv("MACHLINE_LU_LA_PER")) : 8;
-    auto laswp = [&](int c0, int c1, int k0, int k1) {
+    static const bool no_k128 = getenv("MACHLINE_LU_NO_K128") != nullptr;
+    const bool fast_gemm = !old_gemm && (ld & 1) == 0;
+    cudaStream_t S0 = c->stream;
+    auto laswp = [&](int c0, int c1, int k0, int k1) {   // interchanges of panel [k0, k1) applied to columns [c0, c1)
         if (c1 > c0) {
             lu_laswp_kernel<<<(c1 - c0 + 255) / 256, 256, 0, S0>>>(dA, ld, c0, c1, k0, k1, d_piv);
             c->launches += 1;
         }
     };
-    auto update = [&](int c0, int c1, int k0, int k1) {   // columns [c0, c1) right of panel [k0, k1): TRSM + rank-64 update
-        if (c1 <= c0) return;
-        lu_trsm_kernel<<<(c1 - c0 + 63) / 64, 64, 0, S0>>>(dA + k0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, c1 - c0);
-        c->launches += 1;
-        if (k1 >= n) return;
-        if (!old_gemm && (ld & 1) == 0) {
-            lu_gemm2_launch(c, dA + k1 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, dA + k1 + (size_t)c0 * ld, ld, n - k1, c1 - c0, nullptr,
-                            lookahead ? la_max_per : (1 << 30));
-        } else {
-            const size_t gemm_smem1 = (size_t)(GM_K * GM_SA + GM_BN * GM_SB) * sizeof(double);
-            dim3 grid((n - k1 + GM_BM - 1) / GM_BM, (n - k1 + GM_BN - 1) / GM_BN);
-            lu_gemm_dmma_kernel<<<grid, 256, gemm_smem1, S0>>>(dA, ld, n, k0, k1);   // whole trailing matrix (c0 == k1, c1 == n)
+    auto trsm = [&](int k0, int c0, int c1) {            // U(k0..k0+64, c0..c1) = L11^-1 A(k0..k0+64, c0..c1)
+        if (c1 > c0) {
+            lu_trsm_kernel<<<(c1 - c0 + 63) / 64, 64, 0, S0>>>(dA + k0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, c1 - c0);
+            c->launches += 1;
+        }
+    };
+    // A(r0..r1, c0..c1) -= A(r0..r1, k0..k0+64 kh) A(k0..k0+64 kh, c0..c1)
+    auto gemm = [&](int r0, int r1, int c0, int c1, int k0, int kh) {
+        if (r1 <= r0 || c1 <= c0) return;
+        if (fast_gemm) {
+            lu_gemm2_launch(c, dA + r0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, dA + r0 + (size_t)c0 * ld, ld, r1 - r0, c1 - c0, nullptr, kh);
+        } else {   // first-generation kernel: whole trailing matrix of one panel (r0 == c0 == k0 + 64, r1 == c1 == n)
+            dim3 grid((n - r0 + GM_BM - 1) / GM_BM, (n - r0 + GM_BN - 1) / GM_BN);
+            lu_gemm_dmma_kernel<<<grid, 256, gemm_smem, S0>>>(dA, ld, n, k0, k0 + LU_NB);
             c->launches += 1;
         }
     };
     pst = lu_panel_factor(c, PW, dA, ld, n, 0, std::min(LU_NB, n), d_vv, d_piv, d_perm, S0);
     if (pst != ML_OK) { PW.release(); return pst; }
-    for (int k0 = 0; k0 < n; k0 += LU_NB) {
+    for (int k0 = 0; k0 < n;) {   // invariant: panel [k0, k0 + 64) is factored, nothing to its right has seen it yet
         const int k1 = std::min(k0 + LU_NB, n), k2 = std::min(k1 + LU_NB, n);
-        if (lookahead && k0 > 0) ML_CUDA(c, cudaStreamWaitEvent(S0, c->ev_panel, 0));   // panel [k0, k1) is factored
-        if (k1 < n) {
-            if (lookahead) {
-                // the strip first, then panel k+1 goes to the second stream
-                laswp(k1, k2, k0, k1);
-                update(k1, k2, k0, k1);
-                ML_CUDA(c, cudaEventRecord(c->ev_strip, S0));
-                ML_CUDA(c, cudaStreamWaitEvent(S1, c->ev_strip, 0));
-                pst = lu_panel_factor(c, PW, dA, ld, n, k1, k2, d_vv, d_piv, d_perm, S1, true);
-                if (pst != ML_OK) { PW.release(); return pst; }
-                ML_CUDA(c, cudaEventRecord(c->ev_panel, S1));
-                laswp(0, k0, k0, k1);
-                laswp(k2, n, k0, k1);
-                update(k2, n, k0, k1);
-            } else {
-                laswp(0, k0, k0, k1);
-                laswp(k1, n, k0, k1);
-                update(k1, n, k0, k1);
+        if (fast_gemm && !no_k128 && k2 - k1 == LU_NB && k2 < n) {
+            // Two panels A = [k0, k1), B = [k1, k2) per pass over the trailing matrix: A is applied to B's 64 columns only,
+            // B is factored, then both reach the rest in ONE rank-128 update (C is read and written once for 256 flop per
+            // entry instead of twice for 128 each).
+            laswp(k1, k2, k0, k1);
+            trsm(k0, k1, k2);
+            gemm(k1, n, k1, k2, k0, 1);
+            pst = lu_panel_factor(c, PW, dA, ld, n, k1, k2, d_vv, d_piv, d_perm, S0);
+            if (pst != ML_OK) { PW.release(); return pst; }
+            laswp(0, k0, k0, k1);     // A's interchanges, left and right of the pair
+            laswp(k2, n, k0, k1);
+            laswp(0, k1, k1, k2);     // B's: the left part includes A's own columns (its multipliers move with the rows)
+            laswp(k2, n, k1, k2);
+            trsm(k0, k2, n);                  // U rows of A
+            gemm(k1, k2, k2, n, k0, 1);       // rows of B's diagonal block: minus L21_A U_A
+            trsm(k1, k2, n);                  // U rows of B
+            gemm(k2, n, k2, n, k0, 2);        // everything below: minus [L_A L_B] [U_A; U_B]
+            pst = lu_panel_factor(c, PW, dA, ld, n, k2, std::min(k2 + LU_NB, n), d_vv, d_piv, d_perm, S0);
+            if (pst != ML_OK) { PW.release(); return pst; }
+            k0 = k2;
+        } else {
+            laswp(0, k0, k0, k1);
+            laswp(k1, n, k0, k1);
+            if (k1 < n) {
+                trsm(k0, k1, n);
+                gemm(k1, n, k1, n, k0, 1);
                 pst = lu_panel_factor(c, PW, dA, ld, n, k1, k2, d_vv, d_piv, d_perm, S0);
                 if (pst != ML_OK) { PW.release(); return pst; }
             }
-        } else {
-            laswp(0, k0, k0, k1);
+            k0 = k1;
         }
         ML_CUDA(c, cudaGetLastError());
     }
@@ -1198,7 +1216,7 @@ ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int
             dist_gather_l_kernel<<<dim3((n_rows_pad + 255) / 256, LU_NB), 256, 0, c->stream>>>(Pbuf.p, NP, pos_of_lr.p, n_rows, n_rows_pad, k1,
                                                                                                Lloc.p, rb_active.p);
             c->launches += 1;
-            lu_gemm2_launch(c, Lloc.p, n_rows_pad, Ubuf.p, LU_NB, dAloc + (size_t)k1 * ld, ld, n_rows, W, rb_active.p);
+            lu_gemm2_launch(c, Lloc.p, n_rows_pad, Ubuf.p, LU_NB, dAloc + (size_t)k1 * ld, ld, n_rows, W, rb_active.p, 1);
         }
         DIST_CUDA(cudaGetLastError());
     }
