@@ -275,8 +275,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # rows of the permuted system per rank: contiguous blocks for the Krylov solvers; block-cyclic for the direct solver,
+    # where contiguous blocks would retire the ranks one after the other (DESIGN.md "Multi-GPU")
+    shard_kw = dict(row0=row0, nrows=nrows)
+    if world > 1 and args.matrix_solver == "LU":
+        shard_kw = dict(cyclic=(shard.CYCLIC_BLOCK, rank, world))
+
     # ---- resident-input steps (value): tables already on the device --------------------------------
-    ctx.set_case(case, row0=row0, nrows=nrows)
+    ctx.set_case(case, **shard_kw)
     ctx.assemble()                      # H2D of the tables + first assembly (untimed)
     x = None
     for _ in range(args.warmup):
@@ -313,7 +319,7 @@ def main():
     t0 = time.perf_counter()
     ev[2].record(ext)
     for _ in range(args.steps):
-        ctx.set_case(case, row0=row0, nrows=nrows)   # marks the device tables dirty -> H2D again in assemble()
+        ctx.set_case(case, **shard_kw)   # marks the device tables dirty -> H2D again in assemble()
         ctx.assemble()
         x, info_e = ctx.solve(opts, BC)
     ev[3].record(ext)
@@ -407,7 +413,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(case, dims), "n_panels": case.info.n_body_panels, "n_unknown": case.n_unknown,
-                       "pairs_per_step": pairs, "matrix_solver": args.matrix_solver, "parallelism": f"row-sharded x{world}",
+                       "pairs_per_step": pairs, "matrix_solver": args.matrix_solver, "parallelism": f"row-sharded x{world}" + (" (block-cyclic 128)" if "cyclic" in shard_kw else ""),
                        "l2": "inputs larger than L2: A (8*N^2 bytes) is rewritten by every assembly and streamed by every matvec"},
             "assemble": {"ms": a_ms, "pairs_per_s": pairs / (a_ms * 1e-3)},
             "solve": {"ms": s_ms, "iterations": int(info.iterations), "res_norm": info.res_norm, "res_max": info.res_max,

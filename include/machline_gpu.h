@@ -149,6 +149,12 @@ ml_status ml_set_system_map(ml_ctx *ctx, const ml_system_map *map);
 /* Multi-GPU: this context builds and owns rows [row0, row0+nrows) of the permuted system.
    Default: all rows. */
 ml_status ml_set_row_shard(ml_ctx *ctx, int row0, int nrows);
+/* Multi-GPU, block-cyclic alternative (load balance of the sharded LU): this context owns the blocks
+   b = rank (mod world) of block_rows consecutive rows.  ml_get_A / ml_set_A then address runs of rows that are
+   consecutive inside the context; ml_local_rows lists the global row of every local row (after ml_assemble; pass
+   rows_out = NULL to query the count). */
+ml_status ml_set_row_shard_cyclic(ml_ctx *ctx, int block_rows, int rank, int world_size);
+ml_status ml_local_rows(ml_ctx *ctx, int *rows_out, int *n_out);
 /* Multi-GPU: join an NCCL communicator (id = the 128-byte ncclUniqueId made by rank 0). */
 ml_status ml_set_communicator(ml_ctx *ctx, const void *nccl_unique_id, int rank, int world_size);
 

@@ -232,8 +232,27 @@ extern "C" ml_status ml_set_system_map(ml_ctx* c, const ml_system_map* m) {
     return ML_OK;
 }
 
+extern "C" ml_status ml_set_row_shard_cyclic(ml_ctx* c, int block_rows, int rank, int world) {
+    if (!c || block_rows <= 0 || world < 1 || rank < 0 || rank >= world) return ML_BAD_ARGUMENT;
+    c->cyc_block = block_rows;
+    c->cyc_rank = rank;
+    c->cyc_world = world;
+    c->dirty = true;
+    c->assembled = false;
+    return ML_OK;
+}
+
+extern "C" ml_status ml_local_rows(ml_ctx* c, int* rows_out, int* n_out) {
+    if (!c || !n_out) return ML_BAD_ARGUMENT;
+    if (!c->assembled) return c->fail(ML_NOT_READY, "ml_local_rows before ml_assemble");
+    *n_out = (int)c->local_rows.size();
+    if (rows_out) std::memcpy(rows_out, c->local_rows.data(), c->local_rows.size() * sizeof(int));
+    return ML_OK;
+}
+
 extern "C" ml_status ml_set_row_shard(ml_ctx* c, int row0, int nrows) {
     if (!c || row0 < 0 || nrows < 0) return ML_BAD_ARGUMENT;
+    c->cyc_block = 0;
     c->row0 = row0;
     c->nrows = nrows;
     c->dirty = true;
@@ -288,8 +307,19 @@ static ml_status prepare(ml_ctx* c) {
     const std::vector<int>& P = c->P;
 
     // ---- rows: this context's shard of the permuted system ----
-    const int nrows = (c->nrows < 0) ? c->n_cp - c->row0 : c->nrows;
-    if (c->row0 + nrows > c->n_cp) return c->fail(ML_BAD_ARGUMENT, "row shard out of range");
+    // local row -> global row, and its inverse for the rows this context owns
+    c->local_rows.clear();
+    if (c->cyc_block > 0) {
+        for (int b0 = c->cyc_rank * c->cyc_block; b0 < c->n_cp; b0 += c->cyc_world * c->cyc_block)
+            for (int r = b0; r < std::min(b0 + c->cyc_block, c->n_cp); ++r) c->local_rows.push_back(r);
+    } else {
+        const int nr = (c->nrows < 0) ? c->n_cp - c->row0 : c->nrows;
+        if (c->row0 + nr > c->n_cp) return c->fail(ML_BAD_ARGUMENT, "row shard out of range");
+        for (int r = 0; r < nr; ++r) c->local_rows.push_back(c->row0 + r);
+    }
+    const int nrows = (int)c->local_rows.size();
+    std::vector<int> local_of(c->n_cp, -1);
+    for (int lr = 0; lr < nrows; ++lr) local_of[c->local_rows[lr]] = lr;
     c->n_rows = nrows;
     c->n_rows_pad = ((nrows + 63) / 64) * 64;
     if (c->n_rows_pad == 0) c->n_rows_pad = 64;
@@ -436,8 +466,8 @@ static ml_status prepare(ml_ctx* c) {
     std::vector<unsigned char> active(c->n_rows_pad, 0);
     std::vector<int> sm_rows, sm_colp, sm_colm;
     for (int i = 0; i < c->n_cp; ++i) {
-        int row = c->cp_row[i] - c->row0;
-        if (row < 0 || row >= nrows) continue;
+        const int row = local_of[c->cp_row[i]];
+        if (row < 0) continue;
         xyz[row] = c->cp_loc[3 * (size_t)i];
         xyz[(size_t)c->n_rows_pad + row] = c->cp_loc[3 * (size_t)i + 1];
         xyz[(size_t)2 * c->n_rows_pad + row] = c->cp_loc[3 * (size_t)i + 2];
@@ -574,11 +604,21 @@ extern "C" ml_status ml_assemble_resident(ml_ctx* c, double* device_ms) {
     return ML_OK;
 }
 
+// local index of global row `row0` if rows row0 .. row0+nrows-1 are consecutive local rows of this context, else -1
+static int local_run(const ml_ctx* c, int row0, int nrows) {
+    auto it = std::lower_bound(c->local_rows.begin(), c->local_rows.end(), row0);
+    if (nrows == 0) return 0;
+    if (it == c->local_rows.end() || *it != row0) return -1;
+    const int lr = (int)(it - c->local_rows.begin());
+    if (lr + nrows > (int)c->local_rows.size() || c->local_rows[lr + nrows - 1] != row0 + nrows - 1) return -1;
+    return lr;
+}
+
 extern "C" ml_status ml_get_A(ml_ctx* c, int row0, int nrows, double* dst, int ld) {
     if (!c || !dst || nrows < 0 || ld < nrows) return ML_BAD_ARGUMENT;
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_get_A before ml_assemble");
-    int lr = row0 - c->row0;
-    if (lr < 0 || lr + nrows > c->n_rows) return c->fail(ML_BAD_ARGUMENT, "rows outside this context's shard");
+    const int lr = local_run(c, row0, nrows);
+    if (lr < 0) return c->fail(ML_BAD_ARGUMENT, "rows outside this context's shard (or not consecutive in it)");
     ML_CUDA(c, cudaSetDevice(c->device));
     ML_CUDA(c, cudaMemcpy2DAsync(dst, (size_t)ld * sizeof(double), c->d_A.p + lr, (size_t)c->ld * sizeof(double),
                                  (size_t)nrows * sizeof(double), c->n_cols, cudaMemcpyDeviceToHost, c->stream));
@@ -589,8 +629,8 @@ extern "C" ml_status ml_get_A(ml_ctx* c, int row0, int nrows, double* dst, int l
 extern "C" ml_status ml_set_A(ml_ctx* c, int row0, int nrows, const double* src, int ld) {
     if (!c || !src || nrows < 0 || ld < nrows) return ML_BAD_ARGUMENT;
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_set_A before ml_assemble");
-    int lr = row0 - c->row0;
-    if (lr < 0 || lr + nrows > c->n_rows) return c->fail(ML_BAD_ARGUMENT, "rows outside this context's shard");
+    const int lr = local_run(c, row0, nrows);
+    if (lr < 0) return c->fail(ML_BAD_ARGUMENT, "rows outside this context's shard (or not consecutive in it)");
     ML_CUDA(c, cudaSetDevice(c->device));
     ML_CUDA(c, cudaMemcpy2DAsync(c->d_A.p + lr, (size_t)c->ld * sizeof(double), src, (size_t)ld * sizeof(double),
                                  (size_t)nrows * sizeof(double), c->n_cols, cudaMemcpyHostToDevice, c->stream));

@@ -131,7 +131,9 @@ struct Ctx {
     std::vector<int> P, i_sigma_in_sys;
     std::vector<unsigned char> sigma_known;
     std::vector<double> sigma;
-    int row0 = 0, nrows = -1;   // shard (global permuted rows)
+    int row0 = 0, nrows = -1;   // shard (global permuted rows): contiguous block ...
+    int cyc_block = 0, cyc_rank = 0, cyc_world = 1;   // ... or, cyc_block > 0, blocks b = cyc_rank (mod cyc_world) of cyc_block rows
+    std::vector<int> local_rows;   // global row of every local row (ascending), set by ml_assemble
     bool dirty = true;          // device tables need rebuilding
 
     // ---- device tables ----
@@ -151,7 +153,10 @@ struct Ctx {
 #ifdef ML_HAVE_NCCL
     ncclComm_t comm = nullptr;
 #endif
-    std::vector<int> shard_row0, shard_nrows;  // per rank (equal split)
+    std::vector<int> shard_nrows;              // rows per rank
+    std::vector<int> g_of_slot, slot_of_g;     // slot = rank * shard_pad + local row  <->  global row (-1: padding)
+    int shard_pad = 0;
+    DevBuf<int> d_g_of_slot, d_slot_of_g;
     // Peer-memory exchange of the Krylov vector (solve_kernels.cu: p2p_setup): every rank maps every other rank's window
     // (CUDA IPC); after the matvec one CTA per peer stores this rank's rows of w straight into that peer's window over NVLink
     // and raises a flag there.

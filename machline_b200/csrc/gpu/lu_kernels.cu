@@ -985,15 +985,17 @@ ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, 
 // The right-hand side travels as column N of the local matrix, so forward elimination costs nothing extra and L is
 // never stored.  Back substitution walks the panels backwards: owners contribute their 64 y entries (allreduce), the
 // diagonal block (kept from step 2, replicated) is solved redundantly, and every rank updates its local y.
-__global__ void dist_init_perm_kernel(int* __restrict__ perm, int* __restrict__ pos_of_lr, int N, const int* __restrict__ row0,
-                                      const int* __restrict__ nrows, int world, int S, int rank) {
+__global__ void dist_init_perm_kernel(int* __restrict__ perm, int* __restrict__ pos_of_lr, int N, const int* __restrict__ slot_of_g, int S,
+                                      int rank, const double* __restrict__ b, double* __restrict__ ycol) {
+    // initially position = global row: perm[pos] = its slot; the owner notes the position of its local row and takes b
     const int pos = blockIdx.x * blockDim.x + threadIdx.x;
     if (pos >= N) return;
-    for (int r = 0; r < world; ++r)
-        if (pos >= row0[r] && pos < row0[r] + nrows[r]) {
-            perm[pos] = r * S + (pos - row0[r]);
-            if (r == rank) pos_of_lr[pos - row0[r]] = pos;
-        }
+    const int s = slot_of_g[pos];
+    perm[pos] = s;
+    if (s / S == rank) {
+        pos_of_lr[s - rank * S] = pos;
+        ycol[s - rank * S] = b[pos];
+    }
 }
 // vv(pos) = 1 / amax(slot at pos); a zero row flags the matrix singular
 __global__ void dist_vv_kernel(const double* __restrict__ amax_all, const int* __restrict__ perm, int N, double* __restrict__ vv,
@@ -1112,24 +1114,18 @@ __global__ void dist_copy_block_kernel(const double* __restrict__ Pbuf, int NP, 
 // d_b: the whole right-hand side on every rank; d_x: the whole solution on every rank.
 ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int n_rows_pad, int S, const double* d_b, double* d_x) {
     const int world = c->world, rank = c->rank;
-    if ((int)c->shard_row0.size() != world) return c->fail(ML_NOT_READY, "row shards unknown");
+    if ((int)c->shard_nrows.size() != world || c->d_slot_of_g.p == nullptr || c->shard_pad != S) return c->fail(ML_NOT_READY, "row shards unknown");
     if (ld & 1) return c->fail(ML_BAD_ARGUMENT, "leading dimension must be even");
     const int NP = ((N + 63) / 64) * 64;
     const int npan = (N + LU_NB - 1) / LU_NB;
-    const int row0 = c->shard_row0[rank];
     ml_status st = ML_OK;
-    DevBuf<int> perm, piv, pos_of_lr, d_shards, flag;
+    DevBuf<int> perm, piv, pos_of_lr, flag;
     DevBuf<double> vv, amax_loc, amax_all, Gsend, Gall, Pbuf, Usend, Ubuf, Dall, Lloc, yvec;
     DevBuf<unsigned char> rb_active;
     LuPanelWork PW;
     const int n_rb = (n_rows_pad + GM_BM - 1) / GM_BM;
     double* ycol = dAloc + (size_t)N * ld;
     int h_flag = 0;
-    std::vector<int> h_shards(2 * world);
-    for (int r = 0; r < world; ++r) {
-        h_shards[r] = c->shard_row0[r];
-        h_shards[world + r] = c->shard_nrows[r];
-    }
     auto allgather = [&](const double* send, double* recv, size_t count) -> bool {
         if (world == 1) return cudaMemcpyAsync(recv, send, count * sizeof(double), cudaMemcpyDeviceToDevice, c->stream) == cudaSuccess;
 #ifdef ML_HAVE_NCCL
@@ -1149,7 +1145,6 @@ ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int
     DIST_CUDA(perm.alloc(N));
     DIST_CUDA(piv.alloc(N));
     DIST_CUDA(pos_of_lr.alloc(std::max(1, S)));
-    DIST_CUDA(d_shards.alloc(2 * world));
     DIST_CUDA(flag.alloc(1));
     DIST_CUDA(vv.alloc(N));
     DIST_CUDA(amax_loc.alloc(S));
@@ -1165,13 +1160,11 @@ ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int
     DIST_CUDA(rb_active.alloc(n_rb));
     st = PW.init(c);
     if (st != ML_OK) goto done;
-    DIST_CUDA(cudaMemcpyAsync(d_shards.p, h_shards.data(), 2 * world * sizeof(int), cudaMemcpyHostToDevice, c->stream));
     DIST_CUDA(cudaMemsetAsync(flag.p, 0, sizeof(int), c->stream));
     DIST_CUDA(cudaMemsetAsync(Dall.p, 0, (size_t)LU_NB * LU_NB * npan * sizeof(double), c->stream));
     DIST_CUDA(cudaMemsetAsync(amax_loc.p, 0, (size_t)S * sizeof(double), c->stream));
-    // right-hand side as column N of the local rows
-    DIST_CUDA(cudaMemcpyAsync(ycol, d_b + row0, (size_t)n_rows * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-    dist_init_perm_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(perm.p, pos_of_lr.p, N, d_shards.p, d_shards.p + world, world, S, rank);
+    // perm = identity in slot terms; the right-hand side becomes column N of the local rows
+    dist_init_perm_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(perm.p, pos_of_lr.p, N, c->d_slot_of_g.p, S, rank, d_b, ycol);
     if (n_rows > 0)
         lu_row_amax_kernel<<<dim3((n_rows + 127) / 128, (N + RS_COLS - 1) / RS_COLS), 128, 0, c->stream>>>(dAloc, ld, n_rows, N,
                                                                                                             (unsigned long long*)amax_loc.p);
@@ -1233,7 +1226,7 @@ ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int
     DIST_CUDA(cudaStreamSynchronize(c->stream));
 done:
     PW.release();
-    perm.release(); piv.release(); pos_of_lr.release(); d_shards.release(); flag.release();
+    perm.release(); piv.release(); pos_of_lr.release(); flag.release();
     vv.release(); amax_loc.release(); amax_all.release(); Gsend.release(); Gall.release(); Pbuf.release();
     Usend.release(); Ubuf.release(); Dall.release(); Lloc.release(); yvec.release(); rb_active.release();
     return st;

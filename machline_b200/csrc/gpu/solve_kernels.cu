@@ -51,13 +51,14 @@ struct P2PArgs {
     double* w[Ctx::P2P_MAX];        // parity buffer of this matvec in every rank's window
     unsigned* flags[Ctx::P2P_MAX];  // flags[p][rank] <- seq
     unsigned seq;
-    int rank, row0, n_rows;
+    int rank, n_rows;
+    const int* g_of_local;          // global row of each local row of this rank
 };
 
 __global__ void __launch_bounds__(512) p2p_push_kernel(const double* __restrict__ y_local, const P2PArgs pp) {
     const int p = blockIdx.x;
-    double* dst = pp.w[p] + pp.row0;
-    for (int i = threadIdx.x; i < pp.n_rows; i += 512) dst[i] = y_local[i];
+    double* dst = pp.w[p];
+    for (int i = threadIdx.x; i < pp.n_rows; i += 512) dst[pp.g_of_local[i]] = y_local[i];
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pp.flags[p] + pp.rank), "r"(pp.seq) : "memory");
@@ -675,21 +676,21 @@ static ml_status p2p_setup(Ctx* c, int n) {
 }
 #endif
 
-// y_full[row0[r] + i] = gather[r * shard_pad + i], i < nrows[r]   (shards = row0[0..world), nrows[0..world))
-__global__ void compact_shards_kernel(const double* __restrict__ gather, int shard_pad, const int* __restrict__ shards, int world,
+// y_full[global row of slot s] = gather[s]   (slot = rank * shard_pad + local row; -1 marks padding)
+__global__ void compact_shards_kernel(const double* __restrict__ gather, const int* __restrict__ g_of_slot, int n_slots,
                                       double* __restrict__ y_full) {
-    const int r = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < shards[world + r]) y_full[shards[r] + i] = gather[(size_t)r * shard_pad + i];
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const int g = g_of_slot[s];
+    if (g >= 0) y_full[g] = gather[s];
 }
 
 struct Sys {            // the (possibly row-sharded) system seen by the solvers
     Ctx* c;
     const double* A;    // local rows, column-major
     int ld, n_rows, n_rows_pad, N;
-    int row0;           // first global row of this shard
     int shard_pad;      // rows per rank in the all-gather layout
     DevBuf<double> y_part, gather;
-    DevBuf<int> d_shards;       // row0[world], nrows[world] of the all-gather layout
     DevBuf<unsigned> tickets;   // per 64-row block: splits finished (gemv_n_partial_kernel)
     int n_split = 1, cols_per_split = 0;
 
@@ -710,14 +711,6 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
             if (ps != ML_OK) return ps;
 #endif
             ML_CUDA(c, gather.alloc((size_t)shard_pad * c->world));
-            ML_CUDA(c, d_shards.alloc(2 * c->world));
-            std::vector<int> h(2 * c->world);
-            for (int r = 0; r < c->world; ++r) {
-                h[r] = c->shard_row0[r];
-                h[c->world + r] = c->shard_nrows[r];
-            }
-            ML_CUDA(c, cudaMemcpyAsync(d_shards.p, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-            ML_CUDA(c, cudaStreamSynchronize(c->stream));
         }
         return ML_OK;
     }
@@ -754,8 +747,8 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
             }
             pp.seq = c->p2p_seq;
             pp.rank = c->rank;
-            pp.row0 = row0;
             pp.n_rows = n_rows;
+            pp.g_of_local = c->d_g_of_slot.p + (size_t)c->rank * shard_pad;
             p2p_push_kernel<<<c->world, 512, 0, c->stream>>>(dst, pp);
             c->launches += 1;
             const double* ww = c->win + (size_t)par * c->win_n;
@@ -777,8 +770,8 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
             ncclResult_t r = ncclAllGather(gather.p + (size_t)c->rank * shard_pad, gather.p, shard_pad, ncclDouble, c->comm, c->stream);
             if (r != ncclSuccess) return c->fail(ML_NCCL_ERROR, ncclGetErrorString(r));
             // compact the padded shards into the contiguous full vector: one launch (a memcpy per rank costs ~2.5 us each)
-            compact_shards_kernel<<<dim3((shard_pad + 255) / 256, c->world), 256, 0, c->stream>>>(gather.p, shard_pad, d_shards.p, c->world,
-                                                                                                   y_full);
+            compact_shards_kernel<<<(shard_pad * c->world + 255) / 256, 256, 0, c->stream>>>(gather.p, c->d_g_of_slot.p, shard_pad * c->world,
+                                                                                              y_full);
             c->launches += 1;
             if (c->profile) {   // exchange step = all-gather + compaction, timed from the end of the local matvec
                 cudaEvent_t e2 = nullptr;
@@ -794,7 +787,6 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
     void release() {
         y_part.release();
         gather.release();
-        d_shards.release();
         tickets.release();
     }
 };
@@ -1146,36 +1138,62 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     S.n_rows = c->n_rows;
     S.n_rows_pad = c->n_rows_pad;
     S.N = N;
-    S.row0 = c->row0;
-    // all-gather layout: every rank contributes shard_pad entries
-    if (c->world > 1) {
+    // Slot tables of the all-gather layout: slot = rank * shard_pad + local row <-> global row.  Every rank contributes the
+    // list of rows it assembled, so any dealing of rows to ranks (contiguous blocks, block-cyclic) works the same way.
+    {
+        c->shard_nrows.assign(c->world, c->n_rows);
+        int S_pad = c->n_rows_pad;
+        if (c->world > 1) {
 #ifdef ML_HAVE_NCCL
-        // exchange (row0, nrows) of every rank
-        std::vector<int> mine = {c->row0, c->n_rows}, all(2 * c->world);
-        DevBuf<int> dm, da;
-        ML_CUDA(c, dm.alloc(2));
-        ML_CUDA(c, da.alloc(2 * c->world));
-        ML_CUDA(c, cudaMemcpyAsync(dm.p, mine.data(), 2 * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-        if (ncclAllGather(dm.p, da.p, 2, ncclInt, c->comm, c->stream) != ncclSuccess) return c->fail(ML_NCCL_ERROR, "allgather shards");
-        ML_CUDA(c, cudaMemcpyAsync(all.data(), da.p, 2 * c->world * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
-        ML_CUDA(c, cudaStreamSynchronize(c->stream));
-        dm.release();
-        da.release();
-        c->shard_row0.resize(c->world);
-        c->shard_nrows.resize(c->world);
-        int mxr = 0;
-        for (int r = 0; r < c->world; ++r) {
-            c->shard_row0[r] = all[2 * r];
-            c->shard_nrows[r] = all[2 * r + 1];
-            mxr = std::max(mxr, all[2 * r + 1]);
-        }
-        S.shard_pad = ((mxr + 63) / 64) * 64;
+            std::vector<int> all(c->world);
+            DevBuf<int> dm, da;
+            ML_CUDA(c, dm.alloc(1));
+            ML_CUDA(c, da.alloc(c->world));
+            ML_CUDA(c, cudaMemcpyAsync(dm.p, &c->n_rows, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+            if (ncclAllGather(dm.p, da.p, 1, ncclInt, c->comm, c->stream) != ncclSuccess) return c->fail(ML_NCCL_ERROR, "allgather shard sizes");
+            ML_CUDA(c, cudaMemcpyAsync(all.data(), da.p, c->world * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+            ML_CUDA(c, cudaStreamSynchronize(c->stream));
+            dm.release();
+            da.release();
+            int mxr = 0;
+            for (int r = 0; r < c->world; ++r) {
+                c->shard_nrows[r] = all[r];
+                mxr = std::max(mxr, all[r]);
+            }
+            S_pad = ((mxr + 63) / 64) * 64;
 #else
-        return c->fail(ML_UNSUPPORTED, "library built without NCCL");
+            return c->fail(ML_UNSUPPORTED, "library built without NCCL");
 #endif
-    } else {
-        if (c->n_rows != N) return c->fail(ML_BAD_ARGUMENT, "row shard set but no communicator joined");
-        S.shard_pad = c->n_rows_pad;
+        } else if (c->n_rows != N) {
+            return c->fail(ML_BAD_ARGUMENT, "row shard set but no communicator joined");
+        }
+        c->shard_pad = S_pad;
+        const size_t n_slots = (size_t)S_pad * c->world;
+        std::vector<int> mine(S_pad, -1);
+        for (int i = 0; i < c->n_rows; ++i) mine[i] = c->local_rows[i];
+        c->g_of_slot.assign(n_slots, -1);
+        ML_CUDA(c, c->d_g_of_slot.alloc(n_slots));
+        ML_CUDA(c, c->d_slot_of_g.alloc(N));
+        ML_CUDA(c, cudaMemcpyAsync(c->d_g_of_slot.p + (size_t)c->rank * S_pad, mine.data(), (size_t)S_pad * sizeof(int), cudaMemcpyHostToDevice,
+                                   c->stream));
+#ifdef ML_HAVE_NCCL
+        if (c->world > 1 &&
+            ncclAllGather(c->d_g_of_slot.p + (size_t)c->rank * S_pad, c->d_g_of_slot.p, S_pad, ncclInt, c->comm, c->stream) != ncclSuccess)
+            return c->fail(ML_NCCL_ERROR, "allgather row lists");
+#endif
+        ML_CUDA(c, cudaMemcpyAsync(c->g_of_slot.data(), c->d_g_of_slot.p, n_slots * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+        ML_CUDA(c, cudaStreamSynchronize(c->stream));
+        c->slot_of_g.assign(N, -1);
+        for (size_t sl = 0; sl < n_slots; ++sl) {
+            const int g = c->g_of_slot[sl];
+            if (g < 0) continue;
+            if (g >= N || c->slot_of_g[g] != -1) return c->fail(ML_BAD_ARGUMENT, "row shards overlap or exceed the system");
+            c->slot_of_g[g] = (int)sl;
+        }
+        for (int g = 0; g < N; ++g)
+            if (c->slot_of_g[g] < 0) return c->fail(ML_BAD_ARGUMENT, "row shards do not cover the system");
+        ML_CUDA(c, cudaMemcpyAsync(c->d_slot_of_g.p, c->slot_of_g.data(), (size_t)N * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        S.shard_pad = S_pad;
     }
     ml_status st = S.init();
     if (st != ML_OK) return st;
@@ -1195,11 +1213,11 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
         ML_CUDA(c, cudaMemcpyAsync(tmp.data(), g.p, tmp.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         ML_CUDA(c, cudaStreamSynchronize(c->stream));
         g.release();
-        for (int r = 0; r < c->world; ++r)
-            for (int i = 0; i < c->shard_nrows[r]; ++i) Ik_full[c->shard_row0[r] + i] = tmp[(size_t)r * S.shard_pad + i];
+        for (size_t sl = 0; sl < tmp.size(); ++sl)
+            if (c->g_of_slot[sl] >= 0) Ik_full[c->g_of_slot[sl]] = tmp[sl];
 #endif
     } else {
-        for (int i = 0; i < N; ++i) Ik_full[i] = c->h_I_known[i];
+        for (int i = 0; i < N; ++i) Ik_full[c->local_rows[i]] = c->h_I_known[i];
     }
     for (int i = 0; i < N; ++i) b[i] = BC[i] - Ik_full[i];
     for (int i = 0; i < N; ++i)
@@ -1214,17 +1232,14 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     const double* scale_ptr = nullptr;
     if (opts->preconditioner == ML_PREC_DIAG) {
         // linalg.f90:1813-1816: A_ii_inv(:) = 1/A(N,N).  Row N-1 lives on the rank that owns it.
-        const int last = N - 1;
-        const bool mine = last >= c->row0 && last < c->row0 + c->n_rows;
-        if (mine) {
-            recip_kernel<<<1, 1, 0, c->stream>>>(c->d_A.p + (last - c->row0) + (size_t)last * c->ld, d_scale.p);
+        const int last_slot = c->slot_of_g[N - 1];
+        const int owner = last_slot / S.shard_pad, last_lr = last_slot % S.shard_pad;
+        if (owner == c->rank) {
+            recip_kernel<<<1, 1, 0, c->stream>>>(c->d_A.p + last_lr + (size_t)(N - 1) * c->ld, d_scale.p);
             c->launches += 1;
         }
 #ifdef ML_HAVE_NCCL
         if (c->world > 1) {
-            int owner = 0;
-            for (int r = 0; r < c->world; ++r)
-                if (last >= c->shard_row0[r] && last < c->shard_row0[r] + c->shard_nrows[r]) owner = r;
             if (ncclBroadcast(d_scale.p, d_scale.p, 1, ncclDouble, owner, c->comm, c->stream) != ncclSuccess)
                 return c->fail(ML_NCCL_ERROR, "broadcast scale");
         }
@@ -1238,10 +1253,6 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     static const bool force_sharded_lu = std::getenv("MACHLINE_LU_SHARDED") != nullptr;   // tests: the NCCL algorithm on one rank
     if (opts->matrix_solver == ML_SOLVER_LU && (c->world > 1 || force_sharded_lu)) {
         // row-sharded LU: the local rows (plus the right-hand side as column N) are factored in a scratch copy (A_p)
-        if (c->world == 1) {
-            c->shard_row0.assign(1, 0);
-            c->shard_nrows.assign(1, N);
-        }
         ML_CUDA(c, Acopy.alloc((size_t)c->ld * (N + 1)));
         ML_CUDA(c, cudaMemcpyAsync(Acopy.p, c->d_A.p, (size_t)c->ld * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
         st = lu_solve_sharded(c, N, Acopy.p, c->ld, c->n_rows, c->n_rows_pad, S.shard_pad, d_b.p, d_x.p);
@@ -1292,7 +1303,6 @@ ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_
     S.n_rows = N;
     S.n_rows_pad = ld;
     S.N = N;
-    S.row0 = 0;
     S.shard_pad = ld;
     int saved_world = c->world;
     c->world = 1;  // a host-supplied dense system is never sharded

@@ -41,6 +41,8 @@ def lib() -> C.CDLL:
         L.ml_set_control_points.argtypes = [vp, C.c_int, dp, ip, dp, ip]
         L.ml_set_system_map.argtypes = [vp, C.POINTER(_abi.MlSystemMap)]
         L.ml_set_row_shard.argtypes = [vp, C.c_int, C.c_int]
+        L.ml_set_row_shard_cyclic.argtypes = [vp, C.c_int, C.c_int, C.c_int]
+        L.ml_local_rows.argtypes = [vp, ip, ip]
         L.ml_set_communicator.argtypes = [vp, C.c_void_p, C.c_int, C.c_int]
         L.ml_assemble.argtypes = [vp, dp]
         L.ml_assemble_resident.argtypes = [vp, dp]
@@ -87,8 +89,10 @@ class Context:
             raise GpuError(st, lib().ml_last_error(self._h).decode())
 
     # ---- inputs ----------------------------------------------------------------------------------
-    def set_case(self, case, row0: int = 0, nrows: int | None = None):
-        """Stage the tables of a machline_b200.host.Case (host -> device happens in assemble())."""
+    def set_case(self, case, row0: int = 0, nrows: int | None = None, cyclic: tuple[int, int, int] | None = None):
+        """Stage the tables of a machline_b200.host.Case (host -> device happens in assemble()).  Rows of the permuted
+        system owned by this context: [row0, row0 + nrows), or with cyclic = (block, rank, world) the blocks
+        b = rank (mod world) of `block` rows."""
         L = lib()
         self._check(L.ml_set_flow(self._h, C.byref(case.flow)))
         wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
@@ -98,10 +102,18 @@ class Context:
         self._check(L.ml_set_system_map(self._h, C.byref(case.map)))
         self.n_unknown = case.n_unknown
         self.n_cp = case.n_cp
+        if cyclic is not None:
+            from . import shard
+            block, rank, world = cyclic
+            self._check(L.ml_set_row_shard_cyclic(self._h, block, rank, world))
+            self.local_rows = shard.cyclic_rows(case.n_cp, rank, world, block)
+            self.row0, self.nrows = (int(self.local_rows[0]) if len(self.local_rows) else 0), len(self.local_rows)
+            return
         if nrows is None:
             nrows = case.n_cp - row0
         self._check(L.ml_set_row_shard(self._h, row0, nrows))
         self.row0, self.nrows = row0, nrows
+        self.local_rows = np.arange(row0, row0 + nrows, dtype=np.int32)
 
     def set_points(self, case, points: np.ndarray):
         """Stage `case` with the rows of the system replaced by arbitrary field points (boundary condition "zero
@@ -152,7 +164,25 @@ class Context:
         self._check(lib().ml_assemble_resident(self._h, C.byref(ms)))
         return ms.value
 
+    @staticmethod
+    def _runs(rows):
+        """(start index, first row, length) of the maximal runs of consecutive global rows in `rows`."""
+        rows = np.asarray(rows)
+        if len(rows) == 0:
+            return []
+        cut = np.flatnonzero(np.diff(rows) != 1) + 1
+        starts = np.concatenate([[0], cut])
+        ends = np.concatenate([cut, [len(rows)]])
+        return [(int(s), int(rows[s]), int(e - s)) for s, e in zip(starts, ends)]
+
     def get_A(self, row0: int | None = None, nrows: int | None = None) -> np.ndarray:
+        if row0 is None and nrows is None:   # every local row, in local order (block-cyclic shards: run by run)
+            A = np.zeros((self.nrows, self.n_unknown), dtype=np.float64, order="F")
+            for s, r0, n in self._runs(self.local_rows):
+                part = np.zeros((n, self.n_unknown), dtype=np.float64, order="F")
+                self._check(lib().ml_get_A(self._h, r0, n, _dp(part), n))
+                A[s:s + n] = part
+            return A
         row0 = self.row0 if row0 is None else row0
         nrows = self.nrows if nrows is None else nrows
         A = np.zeros((nrows, self.n_unknown), dtype=np.float64, order="F")
@@ -161,8 +191,13 @@ class Context:
 
     def set_A(self, A_rows: np.ndarray, row0: int | None = None):
         """Overwrite rows [row0, row0 + len(A_rows)) of the resident system (ml_set_A)."""
-        row0 = self.row0 if row0 is None else row0
-        A_rows = np.asfortranarray(A_rows, dtype=np.float64)
+        A_rows = np.asarray(A_rows, dtype=np.float64)
+        if row0 is None:                      # one row per local row, in local order
+            for s, r0, n in self._runs(self.local_rows):
+                part = np.asfortranarray(A_rows[s:s + n])
+                self._check(lib().ml_set_A(self._h, r0, n, _dp(part), n))
+            return
+        A_rows = np.asfortranarray(A_rows)
         self._check(lib().ml_set_A(self._h, row0, A_rows.shape[0], _dp(A_rows), A_rows.shape[0]))
 
     @property

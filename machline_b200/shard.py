@@ -4,7 +4,12 @@ The AIC is assembled where it is used: rank r builds and keeps rows [row0, row0+
 (contiguous blocks, multiples of 64 rows so that every shard's leading dimension is aligned) and never ships them.
 The Krylov solvers exchange one vector per matvec: each rank contributes `shard_pad` entries to an all-gather
 (`ml_solve`, csrc/gpu/solve_kernels.cu: Sys::matvec) and the padded shards are compacted into the full vector.
-These helpers are the single statement of that layout on the host side (bench.py, tests)."""
+These helpers are the single statement of that layout on the host side (bench.py, tests).
+
+For the direct solver the rows can instead be dealt block-cyclically (`cyclic_rows`, `ml_set_row_shard_cyclic`): with
+contiguous blocks and a diagonally dominant matrix the ranks run out of rows below the pivot one after the other, so
+the last rank does N^3/P flops instead of 2/3 N^3/P.  The library learns any dealing from the row lists the ranks
+exchange (slot tables in ml_solve), so both layouts go through the same kernels."""
 from __future__ import annotations
 
 import numpy as np
@@ -43,3 +48,14 @@ def compact_gathered(gathered: np.ndarray, shards, pad: int) -> np.ndarray:
     for r, (r0, nr) in enumerate(shards):
         out[r0:r0 + nr] = gathered[r * pad:r * pad + nr]
     return out
+
+
+CYCLIC_BLOCK = 128   # the trailing update of the LU works on blocks of 128 local rows
+
+
+def cyclic_rows(n_rows: int, rank: int, world: int, block: int = CYCLIC_BLOCK) -> np.ndarray:
+    """Global rows of `rank` under block-cyclic dealing: blocks b = rank (mod world) of `block` rows, ascending."""
+    if not (0 <= rank < world) or block <= 0:
+        raise ValueError(f"rank {rank} outside world {world} or block {block} <= 0")
+    rows = [np.arange(b0, min(b0 + block, n_rows)) for b0 in range(rank * block, n_rows, world * block)]
+    return np.concatenate(rows).astype(np.int32) if rows else np.zeros(0, dtype=np.int32)

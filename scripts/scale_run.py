@@ -27,6 +27,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--dims", default="226x112")
 ap.add_argument("--solvers", default="GMRES,LU")
 ap.add_argument("--mach", type=float, default=None)
+ap.add_argument("--cyclic", type=int, default=0, help="deal rows block-cyclically in blocks of this many rows (LU load balance); 0 = contiguous")
 ap.add_argument("--case", default="wing", choices=["wing", "sears_haack"],
                 help="wing: mirrored half wing with wake, M = 0.5 (configs[1]/[4]); sears_haack: supersonic slender body, M = 2 (configs[2])")
 args = ap.parse_args()
@@ -68,7 +69,10 @@ def barrier():
         dist.barrier()
 
 
-ctx.set_case(case, row0=row0, nrows=nrows)
+if args.cyclic > 0:
+    ctx.set_case(case, cyclic=(args.cyclic, rank, world))
+else:
+    ctx.set_case(case, row0=row0, nrows=nrows)
 barrier()
 t0 = time.perf_counter()
 ctx.assemble()
@@ -92,7 +96,7 @@ for solver in args.solvers.split(","):
         res = case.post(x)
         a_ms, s_ms, w_s = (float(v) for v in vals.cpu())
         print(json.dumps({"case": label, "n_gpus": world, "n_panels": case.info.n_body_panels,
-                          "n_unknown": N, "A_bytes": 8.0 * N * N, "pairs": float(case.n_pairs), "matrix_solver": solver,
+                          "n_unknown": N, "A_bytes": 8.0 * N * N, "pairs": float(case.n_pairs), "matrix_solver": solver, "row_dealing": f"block-cyclic {args.cyclic}" if args.cyclic else "contiguous",
                           "host_setup_s": host_s, "assemble_ms": a_ms, "assemble_first_wall_s": asm_wall,
                           "pairs_per_s": case.n_pairs / (a_ms * 1e-3), "solve_ms": s_ms, "solve_wall_s": w_s,
                           "iterations": int(info.iterations), "res_norm": info.res_norm, "res_max": info.res_max,

@@ -41,7 +41,13 @@ if world > 1:
         uid.copy_(torch.frombuffer(bytearray(gpu.nccl_unique_id()), dtype=torch.uint8))
     dist.broadcast(uid, src=0)
     ctx.set_communicator(bytes(uid.cpu().numpy().tobytes()), rank, world)
-ctx.set_case(case, row0=row0, nrows=nrows)
+cyclic_block = int(os.environ.get("MACHLINE_TEST_CYCLIC", "0"))
+if cyclic_block > 0:
+    ctx.set_case(case, cyclic=(cyclic_block, rank, world))
+    my_rows = shard.cyclic_rows(N, rank, world, cyclic_block)
+else:
+    ctx.set_case(case, row0=row0, nrows=nrows)
+    my_rows = np.arange(row0, row0 + nrows)
 I_loc = ctx.assemble()
 opts = case.solver_opts()
 BC = np.array(case.BC)
@@ -59,19 +65,21 @@ assert info.res_norm < 1e-10, info.res_norm
 rng = np.random.default_rng(1234)
 A = np.asfortranarray(rng.standard_normal((N, N)))
 A[::5] *= 1e3
-ctx.set_A(A[row0:row0 + nrows])
+ctx.set_A(A[my_rows])
+I_full = np.zeros(N)
 if world > 1:
     parts = [None] * world
-    dist.all_gather_object(parts, I_loc)
-    I_full = np.concatenate(parts)
+    dist.all_gather_object(parts, (my_rows, I_loc))
+    for rows_r, I_r in parts:
+        I_full[rows_r] = I_r
 else:
-    I_full = I_loc
+    I_full[my_rows] = I_loc
 b = BC - I_full
 x2, info2 = ctx.solve(opts, BC)
 x_np = np.linalg.solve(A, b)
 err2 = np.abs(x2 - x_np).max() / np.abs(x_np).max()
 assert err2 < 1e-7, f"rank {rank}: random system, sharded LU vs numpy: {err2:.2e}"
-print(f"rank {rank}/{world}: N={N} rows [{row0},{row0 + nrows}) AIC err {err:.2e} random err {err2:.2e} res {info2.res_norm:.2e} "
+print(f"rank {rank}/{world}: N={N} {len(my_rows)} rows ({'cyclic ' + str(cyclic_block) if cyclic_block else 'contiguous'}) AIC err {err:.2e} random err {err2:.2e} res {info2.res_norm:.2e} "
       f"solve_ms {info.solve_ms:.1f}/{info2.solve_ms:.1f} OK", flush=True)
 ctx.close()
 if world > 1:

@@ -30,14 +30,22 @@ def test_sharded_lu_algorithm_on_one_rank(dims):
     assert "OK" in out
 
 
+@pytest.mark.parametrize("cyclic", ["0", "128", "64"])
 @pytest.mark.parametrize("dims", ["12x6", "40x20"])
-def test_sharded_lu_two_ranks_nccl(dims):
+def test_sharded_lu_two_ranks_nccl(dims, cyclic):
+    """Contiguous row blocks and block-cyclic dealing (MACHLINE_TEST_CYCLIC = block size) through the same kernels."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     out = _run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
-                "--master-port", "29533", WORKER, dims], {})
+                "--master-port", "29533", WORKER, dims], {"MACHLINE_TEST_CYCLIC": cyclic})
     assert out.count("OK") == 2
+
+
+def test_cyclic_shard_on_one_rank():
+    """world = 1 block-cyclic = all rows; exercises the row-list plumbing on the single-GPU test box."""
+    out = _run([sys.executable, WORKER, "12x6"], {"MACHLINE_LU_SHARDED": "1", "MACHLINE_TEST_CYCLIC": "64"})
+    assert "OK" in out
 
 
 @pytest.mark.parametrize("env", [{"MACHLINE_LU_PANEL_RPC": "512"}, {"MACHLINE_LU_PER_COLUMN": "1"}, {"MACHLINE_LU_GEMM_V1": "1"}])

@@ -43,6 +43,20 @@ def test_row_shards_cover_every_row_once():
         shard.row_shard(10, 2, 2)
 
 
+def test_cyclic_rows_cover_every_row_once():
+    from machline_b200 import shard
+    for n in [1, 63, 128, 129, 1202, 10513]:
+        for world in [1, 2, 3, 8]:
+            for block in [64, 128]:
+                rows = [shard.cyclic_rows(n, r, world, block) for r in range(world)]
+                allr = np.sort(np.concatenate(rows))
+                assert (allr == np.arange(n)).all()
+                assert all((np.diff(r) > 0).all() for r in rows)
+                assert max(len(r) for r in rows) - min(len(r) for r in rows) <= block
+                for r, rr in enumerate(rows):
+                    assert ((rr // block) % world == r).all()
+
+
 def _worker(rank: int, world: int, port: int, out_dir: str):
     import torch
     import torch.distributed as dist
