@@ -137,6 +137,7 @@ class Context:
         self._check(L.ml_set_row_shard(self._h, 0, n))
         self.n_unknown, self.n_cp = case.n_unknown, n
         self.row0, self.nrows = 0, n
+        self.local_rows = np.arange(n, dtype=np.int32)
 
     def potentials_at(self, case, points: np.ndarray, x: np.ndarray):
         """(phi_d, phi_s) induced at `points` by the solved strengths x (per unit freestream speed): phi_d = A_points x,
