@@ -328,10 +328,15 @@ static ml_status prepare(ml_ctx* c) {
     // Tile height: a CTA owns R rows for the whole record stream, so R trades per-chunk overhead against the
     // number of tiles available to the 2 x num_sms resident CTAs (dynamic scheduling wants several per CTA).
     {
+        // Measured on B200 (r01e): subsonic, R = 8 is fastest at every size tried (N = 10.5k: 12.6 / 13.7 / 16.9 ms for
+        // R = 8 / 16 / 32; N = 29k: 92.3 / 95.7 / 102.9 ms); supersonic, where a warp's DoD branches are uniform only if it
+        // holds one record, R = 32 wins once there are a few tiles per resident CTA (SH_320_120: 111.7 / 111.5 / 108.3 ms).
         const long long slots = 2LL * c->num_sms;
         int R = 8;
-        if (c->n_rows_pad / 32 >= 8 * slots) R = 32;
-        else if (c->n_rows_pad / 16 >= 6 * slots) R = 16;
+        if (sup) {
+            if (c->n_rows_pad / 32 >= 2 * slots) R = 32;
+            else if (c->n_rows_pad / 16 >= 2 * slots) R = 16;
+        }
         if (const char* e = std::getenv("MACHLINE_AIC_TILE_ROWS")) {
             int v = std::atoi(e);
             if (v == 8 || v == 16 || v == 32) R = v;
