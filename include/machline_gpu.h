@@ -120,7 +120,9 @@ typedef struct ml_solver_opts {     /* defaults: panel_solver.f90:173-209 */
     int max_iterations;        /* 1000                                                                  */
     int restart_iterations;    /* 20                                                                    */
     int block_size;            /* <= 0 -> N/5 (panel_solver.f90:1910-1912)                              */
-    const char *iteration_file;/* NULL or "none": no iteration history                                  */
+    const char *iteration_file;/* NULL or "none": no iteration history; else the file the reference's solver
+                                  writes (solver.iterative_solver_output): GMRES linalg.f90:1273-1280,1316;
+                                  RGMRES :1376-1383,1438; BJAC :659-666,717; BSSOR :514-520,587            */
 } ml_solver_opts;
 
 typedef struct ml_solve_info {

@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -1027,10 +1028,41 @@ __global__ void __launch_bounds__(1024) vec_norm_kernel(const double* __restrict
     }
 }
 
+// out = || a - b ||_2   (||dx|| of the iteration history, linalg.f90:714, 585)
+__global__ void __launch_bounds__(1024) vec_diff_norm_kernel(const double* __restrict__ a, const double* __restrict__ b, int n,
+                                                              double* __restrict__ out) {
+    __shared__ double s_part[32];
+    double acc = 0.;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        const double d = a[i] - b[i];
+        acc = fma(d, d, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.;
+        for (int k = 0; k < 32; ++k) t += s_part[k];
+        *out = sqrt(t);
+    }
+}
+
+// Iteration history of the block solvers as the reference writes it (linalg.f90:659-666, 717; 514-520, 587): rank 0 only.
+static FILE* open_block_history(Ctx* c, const char* path, const char* method, int N, bool with_n) {
+    if (!path || !*path || std::strcmp(path, "none") == 0 || c->rank != 0) return nullptr;
+    FILE* f = std::fopen(path, "w");
+    if (!f) return nullptr;
+    std::fprintf(f, " method\n %s\n", method);
+    if (with_n) std::fprintf(f, " N=%12d\n", N);
+    std::fprintf(f, " iteration,||dx||,||err||,relaxation\n");
+    return f;
+}
+
 // err_scale = |1/A(N,N)| when the reference's DIAG "preconditioner" scaled the system (the stopping test is on the
 // scaled residual, linalg.f90:712-716), else 1.
 ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
-                              int max_iter, int* iters, double* d_x, double err_scale) {
+                              int max_iter, int* iters, double* d_x, double err_scale, const char* iteration_file) {
     if (block_size <= 0 || block_size > N) return c->fail(ML_BAD_ARGUMENT, "block_size out of range");
     int N_blocks = N / block_size;
     if (N % block_size > 0) N_blocks += 1;
@@ -1049,7 +1081,8 @@ ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const dou
     ML_CUDA(c, flag.alloc(1));
     ML_CUDA(c, x_new.alloc(N));
     ML_CUDA(c, bi.alloc(N));
-    ML_CUDA(c, nrm.alloc(1));
+    ML_CUDA(c, nrm.alloc(2));
+    FILE* hist = open_block_history(c, iteration_file, "BJAC", N, true);
     ml_status st = ML_OK;
     for (int i = 0; i < N_blocks && st == ML_OK; ++i) {
         bs[i] = i * block_size;
@@ -1086,13 +1119,21 @@ ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const dou
         bj_rhs_kernel<<<(N + 31) / 32, 256, 0, c->stream>>>(dA, ld, N, 0, N, 0, 0, d_b, x_new.p, bi.p);
         vec_norm_kernel<<<1, 1024, 0, c->stream>>>(bi.p, N, nrm.p);
         c->launches += 3;
+        double dx = 0.;
+        if (hist) {   // dx = || x - x_new ||  (linalg.f90:714)
+            vec_diff_norm_kernel<<<1, 1024, 0, c->stream>>>(d_x, x_new.p, N, nrm.p + 1);
+            c->launches += 1;
+        }
         cudaError_t e = cudaMemcpyAsync(d_x, x_new.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
         if (e == cudaSuccess) e = cudaMemcpyAsync(&err, nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && hist) e = cudaMemcpyAsync(&dx, nrm.p + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { st = c->cuda_fail(e, "block_jacobi iteration"); break; }
         if (!(err == err)) { st = ML_NAN_RESIDUAL; break; }
         err *= err_scale;
+        if (hist) std::fprintf(hist, "%6d,%10.3E,%10.3E,%10.3E\n", iteration, dx, err, rel);
     }
+    if (hist) std::fclose(hist);
     *iters = iteration;
     cleanup();
     return st;
@@ -1109,7 +1150,7 @@ __global__ void bssor_relax_kernel(double rel, const double* __restrict__ xi, do
 }
 
 ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
-                            int max_iter, int* iters, double* d_x, double err_scale) {
+                            int max_iter, int* iters, double* d_x, double err_scale, const char* iteration_file) {
     if (block_size <= 0 || block_size > N) return c->fail(ML_BAD_ARGUMENT, "block_size out of range");
     int N_blocks = N / block_size;
     if (N % block_size > 0) N_blocks += 1;
@@ -1124,7 +1165,7 @@ ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const doubl
         vv.release(); flag.release(); xi.release(); bi.release(); nrm.release();
     };
     if (vv.alloc(block_size + 64) != cudaSuccess || flag.alloc(1) != cudaSuccess || xi.alloc(N) != cudaSuccess ||
-        bi.alloc(N) != cudaSuccess || nrm.alloc(1) != cudaSuccess) {
+        bi.alloc(N) != cudaSuccess || nrm.alloc(2) != cudaSuccess) {
         cleanup();
         return c->fail(ML_CUDA_ERROR, "block SSOR: out of device memory");
     }
@@ -1150,9 +1191,16 @@ ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const doubl
     }
     int iteration = 0, step = -1;
     double err = tol + 1.;
+    FILE* hist = open_block_history(c, iteration_file, "BSSOR", N, false);
+    DevBuf<double> x_prev;   // only for the ||dx|| column of the history
+    if (hist && x_prev.alloc(N) != cudaSuccess) {
+        std::fclose(hist);
+        hist = nullptr;
+    }
     while (st == ML_OK && err >= tol && iteration < max_iter) {
         iteration += 1;
         step = -step;   // first sweep runs forward (linalg.f90:516-527)
+        if (hist) cudaMemcpyAsync(x_prev.p, d_x, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
         for (int n = 0; n < N_blocks && st == ML_OK; ++n) {
             const int i = (step == 1) ? n : N_blocks - 1 - n;
             const int nb = be[i] - bs[i];
@@ -1167,12 +1215,21 @@ ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const doubl
         bj_rhs_kernel<<<(N + 31) / 32, 256, 0, c->stream>>>(dA, ld, N, 0, N, 0, 0, d_b, d_x, bi.p);
         vec_norm_kernel<<<1, 1024, 0, c->stream>>>(bi.p, N, nrm.p);
         c->launches += 2;
+        double dx = 0.;
+        if (hist) {
+            vec_diff_norm_kernel<<<1, 1024, 0, c->stream>>>(x_prev.p, d_x, N, nrm.p + 1);
+            c->launches += 1;
+        }
         cudaError_t e = cudaMemcpyAsync(&err, nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && hist) e = cudaMemcpyAsync(&dx, nrm.p + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { st = c->cuda_fail(e, "block_ssor iteration"); break; }
         if (!(err == err)) { st = ML_NAN_RESIDUAL; break; }
         err *= err_scale;
+        if (hist) std::fprintf(hist, "%6d,%10.3E,%10.3E,%10.3E\n", iteration, dx, err, rel);
     }
+    if (hist) std::fclose(hist);
+    x_prev.release();
     *iters = iteration;
     cleanup();
     return st;

@@ -808,10 +808,30 @@ struct GmresWork {  // device buffers of one gmres_device call (pool-allocated);
 }  // namespace
 
 // GMRES / restarted GMRES (linalg.f90:1235-1453) on the scaled system (scale*A) x = scale*b.
+// Iteration history as the reference writes it (linalg.f90:1273-1280, 1316; 1376-1383, 1438): list-directed header lines
+// (leading blank, default integer width 12), then '(i6, a, ES10.3)' rows.  nullptr / "none": no file.  Rank 0 only.
+static FILE* open_iteration_file(Ctx* c, const char* path, const char* method, int N, const char* columns) {
+    if (!path || !*path || std::strcmp(path, "none") == 0 || c->rank != 0) return nullptr;
+    FILE* f = std::fopen(path, "w");
+    if (!f) return nullptr;
+    std::fprintf(f, " method\n %s\n N=%12d\n %s\n", method, N, columns);
+    return f;
+}
+
+struct HistFile {   // closes on every return path
+    FILE* f;
+    ~HistFile() {
+        if (f) std::fclose(f);
+    }
+};
+
 static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, double tol, int max_iter, int restart_iter,
-                              bool restarted, bool use_mgs, double* d_x, int* total_iter_out) {
+                              bool restarted, bool use_mgs, double* d_x, int* total_iter_out, const char* iteration_file) {
     Ctx* c = S.c;
     const int N = S.N;
+    HistFile hist{open_iteration_file(c, iteration_file, "GMRES", N,
+                                      restarted ? "iteration,outer iteration,inner iteration,||err||" : "iteration,||err||")};
+    int outer_iter = 0;
     const int k_max = restarted ? std::min(restart_iter, N) : std::min(N, max_iter);
     if (k_max < 1) return c->fail(ML_BAD_ARGUMENT, "max_iterations < 1");
     const int hs = k_max + 2;  // stride of one Hessenberg-column slot
@@ -929,6 +949,7 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     bool first_cycle = true;
     while (err > tol && (restarted ? total_iter <= max_iter : first_cycle)) {
         first_cycle = false;
+        outer_iter += 1;
         std::fill(H.begin(), H.end(), 0.);
         std::fill(cs.begin(), cs.end(), 0.);
         std::fill(sn.begin(), sn.end(), 0.);
@@ -990,6 +1011,10 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
             E[kk + 1] = -sn[kk] * E[kk];
             E[kk] = cs[kk] * E[kk];
             err = beta * std::fabs(E[kk + 1]);
+            if (hist.f) {
+                if (restarted) std::fprintf(hist.f, "%6d,%6d,%6d,%10.3E\n", total_iter, outer_iter, k, err);
+                else std::fprintf(hist.f, "%6d,%10.3E\n", k, err);
+            }
             if (!restarted && err < tol) break;
         }
         if (st != ML_OK) break;
@@ -1027,9 +1052,9 @@ ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, 
 ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int n_rows_pad, int S, const double* d_b,
                            double* d_x);                                                      // lu_kernels.cu
 ml_status block_jacobi_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
-                              int max_iter, int* iters, double* d_x, double err_scale);      // lu_kernels.cu
+                              int max_iter, int* iters, double* d_x, double err_scale, const char* iteration_file);   // lu_kernels.cu
 ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
-                            int max_iter, int* iters, double* d_x, double err_scale);        // lu_kernels.cu
+                            int max_iter, int* iters, double* d_x, double err_scale, const char* iteration_file);     // lu_kernels.cu
 ml_status qrup_solve_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, const double* d_scale, bool fast,
                             double* d_x);                                                    // seq_solvers.cu
 ml_status purcell_solve_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, const double* d_scale,
@@ -1070,12 +1095,12 @@ static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_
         case ML_SOLVER_BJAC:
             if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "BJAC needs the full matrix on one device");
             st = block_jacobi_device(c, S.N, lu_matrix, lu_ld, d_b, block_size, opts->tol, opts->rel, opts->max_iterations, &iters, d_x,
-                                     err_scale);
+                                     err_scale, opts->iteration_file);
             break;
         case ML_SOLVER_BSSOR:
             if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "BSSOR needs the full matrix on one device");
             st = block_ssor_device(c, S.N, lu_matrix, lu_ld, d_b, block_size, opts->tol, opts->rel, opts->max_iterations, &iters, d_x,
-                                   err_scale);
+                                   err_scale, opts->iteration_file);
             break;
         case ML_SOLVER_QRUP:
         case ML_SOLVER_FQRUP:
@@ -1087,11 +1112,13 @@ static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_
             st = purcell_solve_device(c, S.N, lu_matrix, lu_ld, d_b, d_scale, d_x);
             break;
         case ML_SOLVER_RGMRES:
-            st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, true, use_mgs, d_x, &iters);
+            st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, true, use_mgs, d_x, &iters,
+                              opts->iteration_file);
             break;
         case ML_SOLVER_GMRES:
         default:  // invalid names fall back to GMRES (panel_solver.f90:1969-1973)
-            st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, false, use_mgs, d_x, &iters);
+            st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, false, use_mgs, d_x, &iters,
+                              opts->iteration_file);
             break;
     }
     if (st != ML_OK) return st;

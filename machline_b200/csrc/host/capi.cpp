@@ -253,7 +253,8 @@ extern "C" int mlh_case_solver_settings(const mlh_case* h, mlh_solver_settings* 
     o->opts.max_iterations = s.max_iterations;
     o->opts.restart_iterations = s.restart_iterations;
     o->opts.block_size = s.block_size;
-    o->opts.iteration_file = nullptr;
+    // solver.iterative_solver_output (panel_solver.f90:186); the string lives as long as the case
+    o->opts.iteration_file = (s.iteration_file.empty() || s.iteration_file == "none") ? nullptr : s.iteration_file.c_str();
     std::snprintf(o->matrix_solver_name, sizeof o->matrix_solver_name, "%s", s.matrix_solver.c_str());
     std::snprintf(o->formulation, sizeof o->formulation, "%s", s.formulation.c_str());
     o->sort_system = s.sort_system;
