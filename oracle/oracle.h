@@ -38,6 +38,7 @@ int orc_restarted_gmres(int N, const double *A, const double *b, double tol, int
                         int *total_iter, double *x);
 int orc_block_jacobi(int N, double *A, const double *b, int block_size, double tol, double rel, int max_iter,
                      int *total_iter, double *x);
+void orc_set_block_history(double *dx, double *err, int capacity);
 int orc_block_ssor(int N, double *A, const double *b, int block_size, double tol, double rel, int max_iter,
                    int *total_iter, double *x);
 int orc_qr_givens_up(int N, double *A, double *b, double *x);

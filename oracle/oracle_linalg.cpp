@@ -324,6 +324,24 @@ extern "C" int orc_restarted_gmres(int N, const double* A, const double* b, doub
     return 0;
 }
 
+// Optional per-iteration history of the block solvers (the columns ||dx||, ||err|| of the reference's iteration file,
+// linalg.f90:714-717, 585-587): orc_set_block_history(dx, err, capacity) arms it for the next block solve.
+static double* g_hist_dx = nullptr;
+static double* g_hist_err = nullptr;
+static int g_hist_cap = 0;
+extern "C" void orc_set_block_history(double* dx, double* err, int capacity) {
+    g_hist_dx = dx;
+    g_hist_err = err;
+    g_hist_cap = capacity;
+}
+static void record_block_history(int iteration, const double* x, const double* x_new, int N, double err) {
+    if (!g_hist_err || iteration > g_hist_cap) return;
+    std::vector<double> d(N);
+    for (int i = 0; i < N; ++i) d[i] = x[i] - x_new[i];
+    if (g_hist_dx) g_hist_dx[iteration - 1] = norm2_gf(d.data(), N);
+    g_hist_err[iteration - 1] = err;
+}
+
 // linalg.f90:601-728
 extern "C" int orc_block_jacobi(int N, double* A, const double* b, int block_size, double tol, double rel, int max_iter,
                                 int* total_iter, double* x) {
@@ -361,6 +379,7 @@ extern "C" int orc_block_jacobi(int N, double* A, const double* b, int block_siz
             dvec[i] = x[i] - x_new[i];
         }
         err = norm2_gf(rvec.data(), N);
+        record_block_history(iteration, x, x_new.data(), N, err);
         for (int i = 0; i < N; ++i) x[i] = x_new[i];
     }
     *total_iter = iteration;
@@ -410,6 +429,7 @@ extern "C" int orc_block_ssor(int N, double* A, const double* b, int block_size,
         std::vector<double> rvec(N);
         for (int i = 0; i < N; ++i) rvec[i] = vk[i] - b[i];
         err = norm2_gf(rvec.data(), N);
+        record_block_history(iteration, x, x_new.data(), N, err);
         for (int i = 0; i < N; ++i) x[i] = x_new[i];
     }
     *total_iter = iteration;

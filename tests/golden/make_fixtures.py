@@ -14,6 +14,12 @@ Outputs (all under tests/golden/):
                                src/panel_solver.f90:2771-2895, format e20.13): x, y, z, phi_d, phi_s and the inputs that the
                                (commented-out) tests 22 / 23 of test/test_machline.py:636-730 build.  They pin the potential
                                integrals at arbitrary field points.
+  solver_histories.json     -- the reference's stored per-iteration histories studies/matrix_solvers/iterations/*_prec_history.csv
+                               (written by its own GMRES / block_jacobi_solve / block_ssor_solve through
+                               solver.iterative_solver_output, '(i6, a, ES10.3)') for the cone (coarse, medium) and the
+                               diamond wing (coarse), preconditioner DIAG / none, sorted / unsorted, with the inputs of
+                               studies/matrix_solvers/matrix_solver_study.py:69-100, 246-252.  They pin assembly + sort +
+                               "preconditioner" + each iterative solver, iteration by iteration.
   prototype_integrals.json  -- known-answer H(1,1,1) / hH(1,1,3) / F(1,1,1) values computed by
                                IMPORTING the reference's Python prototype dev/unit_tests/panel.py
                                (quadrilateral panels in local coordinates) at fixed points.
@@ -69,6 +75,14 @@ def make_meshes():
         out[f"{name}.vtk:triangles"] = tris
     pts, txt = read_stl(REF / "test" / "meshes" / "diamond_full_wing.stl")
     out["diamond_full_wing.stl:facet_vertices"] = pts
+    # meshes of studies/matrix_solvers (the stored iteration histories below were produced on them)
+    study = REF / "studies" / "matrix_solvers" / "meshes"
+    for name in ["cone_10_deg_coarse", "cone_10_deg_medium"]:
+        pts, tris, txt = read_vtk_v3(study / f"{name}.vtk")
+        out[f"{name}.vtk:points"] = pts
+        out[f"{name}.vtk:triangles"] = tris
+    pts, txt = read_stl(study / "diamond_5_deg_full_coarse.stl")
+    out["diamond_5_deg_full_coarse.stl:facet_vertices"] = pts
     np.savez_compressed(OUT / "meshes.npz", **out)
     print("meshes.npz:", {k: v.shape for k, v in out.items()})
 
@@ -186,7 +200,40 @@ def make_offbody():
     print("offbody_potentials.json:", [(c["name"], len(c["points"])) for c in out["cases"]])
 
 
+def make_solver_histories():
+    """Iteration histories of studies/matrix_solvers (matrix_solver_study.py:246-252: cone V = (-1,0,0), M = 1.5, mirror xy;
+    diamond wing V = (1,0,0), M = 2, no mirror; formulation "morino" = today's dirichlet-morino, lower order)."""
+    it_dir = REF / "studies" / "matrix_solvers" / "iterations"
+    out = {"source": "studies/matrix_solvers/iterations/<mesh>_<solver>_<refinement>_<prec>_<sorted|unsorted>_prec_history.csv",
+           "cases": []}
+    for root, refinement, mesh, vel, mach, mirror in [
+            ("cone_10_deg_", "coarse", "cone_10_deg_coarse.vtk", [-1.0, 0.0, 0.0], 1.5, "xy"),
+            ("cone_10_deg_", "medium", "cone_10_deg_medium.vtk", [-1.0, 0.0, 0.0], 1.5, "xy"),
+            ("diamond_5_deg_full_", "coarse", "diamond_5_deg_full_coarse.stl", [1.0, 0.0, 0.0], 2.0, None)]:
+        for solver in ["GMRES", "BJAC", "BSSOR"]:
+            for prec in ["DIAG", "none"]:
+                for sort in [True, False]:
+                    f = it_dir / f"{root}{solver}_{refinement}_{prec}_{'sorted' if sort else 'unsorted'}_prec_history.csv"
+                    if not f.exists():
+                        continue
+                    rows = f.read_text().split("\n")
+                    i0 = next(i for i, r in enumerate(rows) if r.strip().startswith("iteration"))
+                    tab = [[float(v) for v in r.split(",")] for r in rows[i0 + 1:] if r.strip()]
+                    geom = {"file": f"test/meshes/{mesh}", "spanwise_axis": "+y", "singularity_order": "lower"}
+                    if mirror:
+                        geom["mirror_about"] = mirror
+                    inp = {"flow": {"freestream_velocity": vel, "freestream_mach_number": mach}, "geometry": geom,
+                           "solver": {"formulation": "dirichlet-morino", "matrix_solver": solver, "preconditioner": prec,
+                                      "sort_system": sort},
+                           "post_processing": {}, "output": {}}
+                    out["cases"].append({"name": f.stem.replace("_prec_history", ""), "input": inp, "header": rows[:i0 + 1],
+                                         "columns": rows[i0].strip().split(","), "rows": tab})
+    (OUT / "solver_histories.json").write_text(json.dumps(out))
+    print("solver_histories.json:", len(out["cases"]), "histories,", sum(len(c["rows"]) for c in out["cases"]), "rows")
+
+
 if __name__ == "__main__":
+    make_solver_histories()
     make_offbody()
     make_meshes()
     make_goldens()
