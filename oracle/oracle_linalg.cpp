@@ -13,6 +13,11 @@
 //   fast Givens, QR_fast_givens_solve_upper_pentagonal   linalg.f90:968-1165
 //   arnoldi_update, GMRES, restarted_GMRES    linalg.f90:1208-1453
 //   diagonal_preconditioner (with its bug)    linalg.f90:1798-1831
+// Parity pinning: GMRES, block_jacobi_solve and block_ssor_solve (and through the block solvers decompose_blocks,
+// lu_decomp, lu_back_sub, the DIAG scale and the N/5 block size) reproduce the reference's stored iteration histories
+// studies/matrix_solvers/iterations/*.csv row by row (tests/test_oracle_solver_histories.py); GMRES / BJAC / FQRUP also run
+// inside the golden tuples of test/test_machline.py (tests/test_oracle_golden.py).  restarted_GMRES and purcell_solve
+// have no reference data: parity unpinned for those two.
 // Matrices are column-major, A(i,j) = A[i + j*N], as in the reference.  Dense matvecs follow the
 // natural ascending-k order (libgfortran's matmul may use FMA variants at run time, so the
 // reference itself is only reproducible to rounding there).
