@@ -60,17 +60,6 @@ extern "C" ml_status ml_ctx_create(ml_ctx** out, int device_id) {
         delete c;
         return ML_CUDA_ERROR;
     }
-    {
-        int lo = 0, hi = 0;
-        cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        if (cudaStreamCreateWithPriority(&c->stream2, cudaStreamNonBlocking, hi) != cudaSuccess) c->stream2 = nullptr;
-        if (cudaEventCreateWithFlags(&c->ev_strip, cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming) != cudaSuccess) {
-            if (c->stream2) cudaStreamDestroy(c->stream2);
-            c->stream2 = nullptr;
-        }
-        cudaGetLastError();
-    }
     // solver temporaries come from the default stream-ordered pool and stay cached between solves (ctx.h: PoolScope)
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device_id) == cudaSuccess) {
@@ -85,9 +74,6 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
-    if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
-    if (c->ev_strip) cudaEventDestroy(c->ev_strip);
-    if (c->ev_panel) cudaEventDestroy(c->ev_panel);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     for (auto& e : c->slot_ev)
         if (e) cudaEventDestroy(e);

@@ -101,9 +101,7 @@ struct AicLaunch {            // arguments of the assembly kernel (aic_kernels.c
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t stream2 = nullptr;               // high priority: LU look-ahead (panel k+1 under the update of panel k)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    cudaEvent_t ev_strip = nullptr, ev_panel = nullptr;   // ordering between stream and stream2
     std::string err;
     int num_sms = 148;
     long long launches = 0;
@@ -164,7 +162,6 @@ struct Ctx {
     double* win = nullptr;              // this rank's window: [2][win_n] doubles, then [2][P2P_MAX] flags
     size_t win_n = 0;                   // doubles per parity buffer
     void* peer_base[P2P_MAX] = {};      // mapped windows (peer_base[rank] == win)
-    unsigned* p2p_done = nullptr;       // unused scratch counter (kept zero)
     unsigned p2p_seq = 0;               // matvecs exchanged so far (identical on every rank)
     bool p2p_ok = false;
 

@@ -603,9 +603,7 @@ static void p2p_teardown(Ctx* c) {
         c->peer_base[r] = nullptr;
     }
     if (c->win) cudaFree(c->win);
-    if (c->p2p_done) cudaFree(c->p2p_done);
     c->win = nullptr;
-    c->p2p_done = nullptr;
     c->win_n = 0;
     c->p2p_ok = false;
     cudaGetLastError();
@@ -625,8 +623,7 @@ static ml_status p2p_setup(Ctx* c, int n) {
     int ok = 1;
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof mine);
-    if (cudaMalloc((void**)&c->win, p2p_window_bytes(need)) != cudaSuccess || cudaMalloc((void**)&c->p2p_done, sizeof(unsigned)) != cudaSuccess ||
-        cudaMemset(c->win, 0, p2p_window_bytes(need)) != cudaSuccess || cudaMemset(c->p2p_done, 0, sizeof(unsigned)) != cudaSuccess ||
+    if (cudaMalloc((void**)&c->win, p2p_window_bytes(need)) != cudaSuccess || cudaMemset(c->win, 0, p2p_window_bytes(need)) != cudaSuccess ||
         cudaIpcGetMemHandle(&mine, c->win) != cudaSuccess)
         ok = 0;
     cudaGetLastError();

@@ -12,7 +12,7 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from . import _abi, gpu, host
+from . import _abi, gpu, host, vtk_out
 
 
 @dataclass
@@ -52,6 +52,9 @@ def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None
             report_file = case.input.get("output", {}).get("report_file")
         if report_file and report_file != "none":
             case.write_report(report_file, info, 0, total)
+        body_file = case.input.get("output", {}).get("body_file")
+        if body_file and body_file != "none":     # surface_mesh_output_results, src/surface_mesh.f90:2515-2517
+            vtk_out.write_body_vtk(body_file, case, res)
         return RunResult(res.C_p_max, res.C_p_min, res.C_F, res.C_M, res.mu, res.C_p, info.iterations,
                          info.res_max, info.res_norm, info.assemble_ms, info.solve_ms, ctx.pair_count,
                          ctx.launch_count, total)
