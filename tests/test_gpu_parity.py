@@ -185,3 +185,24 @@ def test_reference_offbody_potentials_through_gpu(ctx, c):
     if "supersonic" in c["name"]:
         assert np.abs(phi_d * U - gold_d).max() < 1e-10
     case.close()
+
+
+def test_run_case_writes_the_reference_outputs(tmp_path):
+    """solver.run_case = `machline.exe input.json`: report.json, the body results VTK and the iteration history appear where
+    the input asks for them, and the numbers in them are the solved ones."""
+    import json
+    from machline_b200 import solver
+    inp, expect, tol = fixtures.golden_input("test_08")
+    inp = json.loads(json.dumps(inp))
+    inp["solver"]["iterative_solver_output"] = str(tmp_path / "iterations.csv")
+    inp["output"] = {"report_file": str(tmp_path / "report.json"), "body_file": str(tmp_path / "results" / "body.vtk")}
+    res = solver.run_case(inp, base_dir=fixtures.mesh_root())
+    assert abs(res.C_p_max - expect[0]) < tol[0] and abs(res.C_p_min - expect[1]) < tol[1]
+    rep = json.loads((tmp_path / "report.json").read_text())
+    assert rep["solver_results"]["iterations"] == res.iterations
+    hist = (tmp_path / "iterations.csv").read_text().split("\n")
+    assert hist[1] == " GMRES" and len([ln for ln in hist[4:] if ln]) == res.iterations
+    vtk = (tmp_path / "results" / "body.vtk").read_text().split("\n")
+    i0 = vtk.index("SCALARS C_p_inc float 1") + 2
+    cp = np.array([float(v) for v in vtk[i0:i0 + len(res.C_p)]])
+    assert abs(cp.max() - res.C_p_max) < 1e-10 and abs(cp.min() - res.C_p_min) < 1e-10
