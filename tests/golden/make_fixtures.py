@@ -20,6 +20,9 @@ Outputs (all under tests/golden/):
                                diamond wing (coarse), preconditioner DIAG / none, sorted / unsorted, with the inputs of
                                studies/matrix_solvers/matrix_solver_study.py:69-100, 246-252.  They pin assembly + sort +
                                "preconditioner" + each iterative solver, iteration by iteration.
+  aic_singular_values.json  -- largest and smallest singular value of the reference's own AIC matrix (numpy SVD of the A_mat.txt
+                               it wrote with solver.write_A_and_b; studies/matrix_solvers/*_condition_data.csv,
+                               matrix_conditions.py:20-36) for the cone and diamond-wing study meshes: pins the matrix ENTRIES.
   prototype_integrals.json  -- known-answer H(1,1,1) / hH(1,1,3) / F(1,1,1) values computed by
                                IMPORTING the reference's Python prototype dev/unit_tests/panel.py
                                (quadrilateral panels in local coordinates) at fixed points.
@@ -232,9 +235,32 @@ def make_solver_histories():
     print("solver_histories.json:", len(out["cases"]), "histories,", sum(len(c["rows"]) for c in out["cases"]), "rows")
 
 
+def make_singular_values():
+    import csv
+    out = {"source": "studies/matrix_solvers/{cone_10_deg,diamond_5_deg_full}_condition_data.csv (S_max, S_min of A_mat.txt)", "cases": []}
+    for f, root, ext, vel, mach, mirror in [("cone_10_deg_condition_data.csv", "cone_10_deg_", ".vtk", [-1.0, 0.0, 0.0], 1.5, "xy"),
+                                            ("diamond_5_deg_full_condition_data.csv", "diamond_5_deg_full_", ".stl", [1.0, 0.0, 0.0], 2.0, None)]:
+        for r in csv.DictReader(open(REF / "studies" / "matrix_solvers" / f)):
+            mesh = f"{root}{r['Refinement']}{ext}"
+            if not (OUT / "meshes.npz").exists() or f"{mesh}:points" not in np.load(OUT / "meshes.npz").files and \
+                    f"{mesh}:facet_vertices" not in np.load(OUT / "meshes.npz").files:
+                continue
+            geom = {"file": f"test/meshes/{mesh}", "spanwise_axis": "+y"}
+            if mirror:
+                geom["mirror_about"] = mirror
+            inp = {"flow": {"freestream_velocity": vel, "freestream_mach_number": mach}, "geometry": geom,
+                   "solver": {"matrix_solver": "GMRES", "preconditioner": r["Preconditioner"], "sort_system": r["Sort System"] == "True"},
+                   "post_processing": {}, "output": {}}
+            out["cases"].append({"name": f"{root}{r['Refinement']}_{r['Preconditioner']}_{'sorted' if r['Sort System'] == 'True' else 'unsorted'}",
+                                 "input": inp, "S_max": float(r["S_max"]), "S_min": float(r["S_min"])})
+    (OUT / "aic_singular_values.json").write_text(json.dumps(out, indent=1))
+    print("aic_singular_values.json:", len(out["cases"]), "cases")
+
+
 if __name__ == "__main__":
     make_solver_histories()
     make_offbody()
     make_meshes()
     make_goldens()
     make_prototype_integrals()
+    make_singular_values()     # after make_meshes: only meshes that are in meshes.npz

@@ -206,3 +206,22 @@ def test_run_case_writes_the_reference_outputs(tmp_path):
     i0 = vtk.index("SCALARS C_p_inc float 1") + 2
     cp = np.array([float(v) for v in vtk[i0:i0 + len(res.C_p)]])
     assert abs(cp.max() - res.C_p_max) < 1e-10 and abs(cp.min() - res.C_p_min) < 1e-10
+
+
+def _sv_cases():
+    import json
+    from pathlib import Path
+    return json.loads((Path(__file__).resolve().parent / "golden" / "aic_singular_values.json").read_text())["cases"]
+
+
+@pytest.mark.parametrize("c", _sv_cases(), ids=lambda c: c["name"])
+def test_gpu_aic_has_the_reference_singular_values(ctx, c):
+    """Extreme singular values of the reference's own AIC matrix (tests/test_oracle_singular_values.py) from the matrix the
+    CUDA assembly builds: pins the entries of the GPU matrix against the reference directly, not through the oracle."""
+    from machline_b200 import host
+    case = host.Case(c["input"], base_dir=fixtures.mesh_root())
+    ctx.set_case(case)
+    ctx.assemble()
+    S = np.linalg.svd(ctx.get_A(), compute_uv=False)
+    assert abs(S[0] - c["S_max"]) < 3e-13 and abs(S[-1] - c["S_min"]) < 3e-13
+    case.close()
