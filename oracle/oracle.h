@@ -31,6 +31,7 @@ int orc_assemble(const ml_flow *fs, const ml_panel_soa *body, const ml_panel_soa
 
 /* common/linalg.f90 solvers on a host system; A is column-major N x N and is overwritten the way
    the reference overwrites A_p.  Returns ml_status. */
+int orc_lu_decomp(int N, double *A, int *indx);
 int orc_lu_solve(int N, double *A, const double *b, double *x);
 int orc_gmres(int N, const double *A, const double *b, double tol, int max_iter, int *total_iter, double *x,
               double *err_history /* NULL or [max_iter] */);

@@ -219,6 +219,9 @@ extern "C" int orc_lower_bandwidth(int N, const double* A) {  // linalg.f90:797-
     return B_l;
 }
 
+// lu_decomp alone (linalg.f90:166-280): A overwritten by its factors, indx = the 0-based pivot row of every column
+extern "C" int orc_lu_decomp(int N, double* A, int* indx) { return lu_decomp(A, N, N, indx); }
+
 extern "C" int orc_lu_solve(int N, double* A, const double* b, double* x) {  // linalg.f90:118-148
     std::vector<int> indx(N);
     if (lu_decomp(A, N, N, indx.data())) return ML_SINGULAR;

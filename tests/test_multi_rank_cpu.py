@@ -182,3 +182,138 @@ def test_bench_b200_arm_fails_loudly_without_gpu():
                          timeout=600, cwd=str(ROOT))
     assert res.returncode != 0
     assert not any(ln.startswith("{") for ln in res.stdout.splitlines())      # no number without the CUDA path
+
+
+# ---- row-sharded LU: the algorithm of csrc/gpu/lu_sharded.cu stated with numpy + gloo collectives --------------------
+def _sharded_lu_model(A_loc, my_rows, b, N, rank, world, dist, torch, nb=64):
+    """Every rank keeps its rows in place.  perm[position] = (owner, local row); per panel: all-gather the panel columns,
+    factor them redundantly (implicit scaling, LAST maximal row on ties, linalg.f90:242), sum the pivot rows' trailing
+    entries over the ranks (one non-zero contributor each), triangular solve, local rank-nb update of the rows still
+    below the panel; the right-hand side rides along as column N.  Returns (x, pivot positions)."""
+    S = max(int(v) for v in _all_gather_obj(dist, len(my_rows)))
+    n_loc = len(my_rows)
+    M = np.zeros((n_loc, N + 1))
+    M[:, :N] = A_loc
+    M[:, N] = b[my_rows]
+    rows_all = _all_gather_obj(dist, list(map(int, my_rows)))
+    slot_of_g = {}
+    for r, rows in enumerate(rows_all):
+        for i, g in enumerate(rows):
+            slot_of_g[g] = (r, i)
+    perm = [slot_of_g[g] for g in range(N)]                       # position -> (rank, local row)
+
+    def allgather_rows(x_loc, width):                              # [n_loc, width] -> dict (rank, i) -> row
+        buf = torch.zeros(S, width, dtype=torch.float64)
+        buf[:n_loc] = torch.from_numpy(np.ascontiguousarray(x_loc))
+        out = [torch.zeros(S, width, dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(out, buf)
+        return [o.numpy() for o in out]
+
+    amax = allgather_rows(np.abs(M[:, :N]).max(axis=1, keepdims=True), 1)
+    vv = np.array([1.0 / amax[r][i, 0] for r, i in perm])        # by position
+    piv_pos, D = [], {}
+    for k0 in range(0, N, nb):
+        k1 = min(k0 + nb, N)
+        w = k1 - k0
+        G = allgather_rows(M[:, k0:k1], w)
+        P = np.array([G[r][i] for r, i in perm])                   # panel in position order (rows < k0 unused)
+        for j in range(k0, k1):
+            cand = vv[j:] * np.abs(P[j:, j - k0])
+            p = j + int(np.flatnonzero(cand == cand.max())[-1])    # last maximal row
+            piv_pos.append(p)
+            if p != j:
+                P[[j, p]] = P[[p, j]]
+                perm[j], perm[p] = perm[p], perm[j]
+                vv[p] = vv[j]
+            P[j + 1:, j - k0] *= 1.0 / P[j, j - k0]
+            P[j + 1:, j - k0 + 1:] -= np.outer(P[j + 1:, j - k0], P[j, j - k0 + 1:])
+        D[k0] = P[k0:k1, :].copy()
+        # U rows: owners contribute, everyone sums
+        Wd = N + 1 - k1
+        U = torch.zeros(w, Wd, dtype=torch.float64)
+        for jj in range(w):
+            r, i = perm[k0 + jj]
+            if r == rank:
+                U[jj] = torch.from_numpy(M[i, k1:])
+        dist.all_reduce(U)
+        U = U.numpy()
+        Lk = np.tril(D[k0], -1) + np.eye(w)
+        U = np.linalg.solve(Lk, U) if w > 1 else U
+        for jj in range(w):
+            r, i = perm[k0 + jj]
+            if r == rank:
+                M[i, k1:] = U[jj]
+        pos_of = {perm[pos][1]: pos for pos in range(k1, N) if perm[pos][0] == rank}
+        for i, pos in pos_of.items():                               # local rows still below the panel
+            M[i, k1:] -= P[pos, :] @ U
+    x = np.zeros(N)
+    for k0 in reversed(range(0, N, nb)):
+        k1 = min(k0 + nb, N)
+        y = torch.zeros(k1 - k0, dtype=torch.float64)
+        for jj in range(k1 - k0):
+            r, i = perm[k0 + jj]
+            if r == rank:
+                y[jj] = M[i, N]
+        dist.all_reduce(y)
+        xk = np.linalg.solve(np.triu(D[k0]), y.numpy())
+        x[k0:k1] = xk
+        M[:, N] -= M[:, k0:k1] @ xk
+    return x, piv_pos
+
+
+def _all_gather_obj(dist, obj):
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def _lu_worker(rank: int, world: int, port: int, out_dir: str, cyclic: int):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    from machline_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        N = 300
+        rng = np.random.default_rng(7)
+        A = rng.standard_normal((N, N))
+        A[::5] *= 1e3
+        A[10] = A[11]                      # exact ties of vv * |a| in every column between two rows ...
+        A[11, 200] += 1.0                  # ... that are not copies of each other
+        b = rng.standard_normal(N)
+        if cyclic:
+            rows = shard.cyclic_rows(N, rank, world, cyclic)
+        else:
+            r0, nr = shard.row_shard(N, rank, world)
+            rows = np.arange(r0, r0 + nr)
+        x, piv = _sharded_lu_model(A[rows], rows, b, N, rank, world, dist, torch)
+        np.savez(Path(out_dir) / f"lu_rank{rank}.npz", x=x, piv=np.array(piv), A=A, b=b)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cyclic", [0, 64])
+def test_two_rank_sharded_lu_algorithm(tmp_path, cyclic):
+    """The sharded LU's bookkeeping (positions vs slots, replicated panel, exact U-row sums, right-hand side as a column,
+    distributed back substitution) on two gloo ranks: same pivot sequence as the oracle's lu_decomp and the same solution."""
+    import ctypes as C
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_lu_worker, args=(2, port, str(tmp_path), cyclic), nprocs=2, join=True)
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_binding as ob
+    from machline_b200 import _abi
+    r = [np.load(tmp_path / f"lu_rank{k}.npz") for k in range(2)]
+    A, b = r[0]["A"], r[0]["b"]
+    assert np.array_equal(r[0]["x"], r[1]["x"]) and np.array_equal(r[0]["piv"], r[1]["piv"])
+    x_or, _ = ob.solve_system(np.asfortranarray(A), np.zeros(len(b)), b, _abi.solver_opts("LU"))
+    assert np.abs(r[0]["x"] - x_or).max() <= 1e-9 * np.abs(x_or).max()
+    # pivot positions = the oracle's indx (0-based)
+    N = len(b)
+    Af = np.asfortranarray(A.copy())
+    indx = np.zeros(N, dtype=np.int32)
+    L = ob.lib()
+    if hasattr(L, "orc_lu_decomp"):
+        L.orc_lu_decomp.argtypes = [C.c_int, _abi.c_double_p, _abi.c_int_p]
+        assert L.orc_lu_decomp(N, Af.ctypes.data_as(_abi.c_double_p), indx.ctypes.data_as(_abi.c_int_p)) == 0
+        assert np.array_equal(indx, r[0]["piv"])
