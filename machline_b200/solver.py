@@ -41,10 +41,12 @@ def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None
     ctx = gpu.Context(device)
     try:
         ctx.set_case(case)
-        ctx.assemble()
+        I_known = ctx.assemble()
         opts = case.solver_opts()
         if matrix_solver is not None:
             opts.matrix_solver = _abi.SOLVERS.get(matrix_solver, _abi.SOLVERS["GMRES"])
+        if case.settings.write_A_and_b:           # panel_solver.f90:1834, before the solve; files in the working directory
+            vtk_out.write_system(ctx.get_A(), np.asarray(case.BC) - I_known)
         x, info = ctx.solve(opts, case.BC)
         res = case.post(x)
         total = time.perf_counter() - t0

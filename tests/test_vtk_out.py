@@ -49,3 +49,16 @@ def test_body_file_layout_and_read_back(tmp_path):
     assert case2.info.n_body_panels == nb and case2.info.n_body_verts == nv
     case2.close()
     case.close()
+
+
+def test_write_system_round_trips_like_the_reference_study_reads_it(tmp_path):
+    """A_mat.txt as studies/matrix_solvers/matrix_conditions.py:26 reads it (np.genfromtxt): 12 significant digits per entry."""
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((7, 7)) * 10.0 ** rng.integers(-8, 3, size=(7, 7))
+    b = rng.standard_normal(7)
+    vtk_out.write_system(A, b, tmp_path / "A_mat.txt", tmp_path / "b_vec.txt")
+    lines = (tmp_path / "A_mat.txt").read_text().split("\n")
+    assert len(lines[0]) == 7 * 20
+    A2 = np.array([[float(ln[20 * j:20 * j + 20]) for j in range(7)] for ln in lines[:7]])
+    assert np.abs(A2 - A).max() <= 5e-12 * np.abs(A).max() and (np.abs(A2 - A) <= 5e-12 * np.abs(A)).all()
+    assert np.array_equal(np.genfromtxt(tmp_path / "b_vec.txt"), b)
