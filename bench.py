@@ -427,7 +427,7 @@ def main():
             "result_check": {"C_p_max": res.C_p_max, "C_p_min": res.C_p_min, "Cx": float(res.C_F[0]), "Cz": float(res.C_F[2])},
             "e2e": {"value": pairs / (e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": prof.h2d_bytes / args.steps, "d2h_bytes_per_step": prof.d2h_bytes / args.steps,
-                    "path": "host tables -> ml_set_* -> ml_assemble -> ml_solve -> x on host (C ABI, pageable host buffers)"},
+                    "path": "host tables (caller buffers) -> ml_set_* -> packed into pinned staging -> async H2D -> ml_assemble -> ml_solve -> x on host (C ABI)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": dominant,

@@ -75,6 +75,7 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto& e : c->slot_ev)
         if (e) cudaEventDestroy(e);
 #ifdef ML_HAVE_NCCL
@@ -387,8 +388,29 @@ static ml_status prepare(ml_ctx* c) {
     const int n_body_chunks = (int)((body_recs.size() + C - 1) / C), n_wake_chunks = (int)((wake_recs.size() + C - 1) / C);
     const int n_chunks = n_body_chunks + n_wake_chunks;
     const int LB = aic_list_bytes(C), MAXI = 6 * C;
-    std::vector<double> recs((size_t)std::max(1, n_chunks) * C * STRIDE, 0.);
-    std::vector<unsigned char> lists((size_t)std::max(1, n_chunks) * LB, 0);
+    // packed straight into pinned host memory (kept by the context), so the two large H2D copies run at PCIe rate
+    const size_t n_recs = (size_t)std::max(1, n_chunks) * C * STRIDE, n_lists = (size_t)std::max(1, n_chunks) * LB;
+    const size_t recs_bytes = (n_recs * sizeof(double) + 255) / 256 * 256;
+    if (c->h_stage_bytes < recs_bytes + n_lists) {
+        if (c->h_stage) cudaFreeHost(c->h_stage);
+        c->h_stage = nullptr;
+        c->h_stage_bytes = 0;
+        ML_CUDA(c, cudaMallocHost(&c->h_stage, recs_bytes + n_lists));
+        c->h_stage_bytes = recs_bytes + n_lists;
+    }
+    std::memset(c->h_stage, 0, recs_bytes + n_lists);
+    struct RecsView {
+        double* p;
+        size_t n;
+        double* data() const { return p; }
+        size_t size() const { return n; }
+    } recs{reinterpret_cast<double*>(c->h_stage), n_recs};
+    struct ListsView {
+        unsigned char* p;
+        size_t n;
+        unsigned char* data() const { return p; }
+        size_t size() const { return n; }
+    } lists{reinterpret_cast<unsigned char*>(c->h_stage) + recs_bytes, n_lists};
     std::vector<unsigned char> col_seen(m.n_unknown, 0);
     std::vector<int> wcol_of(m.n_unknown, -1), wcols;      // compact wake column ids
     std::vector<unsigned char> wseen;

@@ -134,6 +134,10 @@ struct Ctx {
     std::vector<int> local_rows;   // global row of every local row (ascending), set by ml_assemble
     bool dirty = true;          // device tables need rebuilding
 
+    // pinned staging of the packed tables (records + scatter lists): packed in place, then one async H2D each
+    void* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+
     // ---- device tables ----
     DevBuf<double> d_recs, d_cp_xyz, d_A, d_I_known, d_work, d_W;
     DevBuf<unsigned char> d_row_active, d_lists;
