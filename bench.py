@@ -4,13 +4,15 @@
     python bench.py --gpus N --steps K --warmup W            # our CUDA path (one rank per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
 
-A "step" is one pass of the hot path over one synthetic case: ml_assemble (DoD + body + wake
-influences -> A resident in HBM) followed by ml_solve (the input's matrix_solver, GMRES by default
-as in the reference).  Workload at N=1: BASELINE.json configs[1] -- a mirrored, swept, tapered
-ONERA-M6-planform half wing with a rounded tip at M = 0.5 with an automatic wake, ~20k panels --
-generated deterministically by machline_b200.meshgen (the reference's own mesh lives in its
-studies/ tree, which does not travel).  At N GPUs the mesh is refined so that pairs/GPU stays ~constant (weak
-scaling) and the permuted system's rows are dealt to the ranks in contiguous blocks.
+A "step" is one pass of the hot path over one case: ml_assemble (DoD + body + wake influences -> A
+resident in HBM) followed by ml_solve (the input's matrix_solver, GMRES by default as in the
+reference).  Workload at N=1: BASELINE.json configs[1] on the reference's OWN mesh
+studies/subsonic_onera_m6_wing/meshes/M6_onera_fine.stl (committed in tests/golden/study_meshes.npz):
+ONERA M6, mirrored about xz, M = 0.5, alpha = 3.06 deg, automatic wake, 14 512 panels x 2 images.
+At N > 1 GPUs (weak scaling) the case must grow with N, which a fixed mesh cannot: the synthetic
+ONERA-M6-planform family of machline_b200.meshgen is used, refined so that pairs/GPU stays ~constant,
+and the line carries the same family's single-GPU value measured in the same run
+("scaling_reference") plus a parity block (sharded solve against a single-GPU solve of the same case).
 
 One JSON line is printed by rank 0 (see DESIGN.md "Measurement" for every key).
 """
@@ -42,18 +44,38 @@ def wing_dims(n_gpus: int):
     return int(round(96 * f)), int(round(52 * f))
 
 
-def build_case(n_gpus: int, tmpdir: str, matrix_solver: str, dims: str | None = None):
+STUDY_NPZ = ROOT / "tests" / "golden" / "study_meshes.npz"
+STUDY_MESH = {"onera_m6": "M6_onera_fine.stl", "cone": "cone_10_deg_fine.vtk", "sears_haack": "SH_160_60.tri",
+              "agard_b": "agard_b_fine.vtk"}
+
+
+def default_workload(n_gpus: int) -> str:
+    return "onera_m6" if n_gpus == 1 else "synthetic_wing"
+
+
+def build_case(n_gpus: int, tmpdir: str, matrix_solver: str, dims: str | None = None, workload: str | None = None):
+    """(host.Case, description dict).  workload: a study case of meshgen.study_input on the reference's own mesh, or
+    "synthetic_wing" (sized for n_gpus; `dims` = "NCxNS" overrides the size, tests only)."""
     from machline_b200 import host, meshgen
-    nc, ns = wing_dims(n_gpus)
-    if dims:   # tests only: a small mesh, e.g. "16x8"
-        nc, ns = (int(v) for v in dims.lower().split("x"))
-    pts, tris = meshgen.swept_wing_half(nc, ns)
-    name = f"wing_{nc}x{ns}.vtk"
-    meshgen.write_vtk(Path(tmpdir) / name, pts, tris)
-    inp = meshgen.wing_input(name, mach=0.5, alpha_deg=3.06, matrix_solver=matrix_solver)
+    workload = workload or (default_workload(n_gpus) if not dims else "synthetic_wing")
+    if workload == "synthetic_wing":
+        nc, ns = wing_dims(n_gpus)
+        if dims:
+            nc, ns = (int(v) for v in dims.lower().split("x"))
+        pts, tris = meshgen.swept_wing_half(nc, ns)
+        name = f"wing_{nc}x{ns}.vtk"
+        meshgen.write_vtk(Path(tmpdir) / name, pts, tris)
+        inp = meshgen.wing_input(name, mach=0.5, alpha_deg=3.06, matrix_solver=matrix_solver)
+        desc = dict(workload=workload, mesh=f"synthetic {nc}x{ns} (machline_b200.meshgen.swept_wing_half)", data="synthetic")
+    else:
+        meshgen.materialise_npz(STUDY_NPZ, tmpdir, only=[STUDY_MESH[workload]])
+        inp = meshgen.study_input(workload, matrix_solver=matrix_solver)
+        desc = dict(workload=workload, mesh=f"{STUDY_MESH[workload]} (the reference's study mesh, tests/golden/study_meshes.npz)",
+                    data="reference mesh, synthetic freestream per SURVEY 8(d)")
     t0 = time.perf_counter()
     case = host.Case(inp, base_dir=tmpdir)
-    return case, dict(n_chord=nc, n_span=ns, host_setup_s=time.perf_counter() - t0)
+    desc["host_setup_s"] = time.perf_counter() - t0
+    return case, desc
 
 
 class ClockSampler:
@@ -200,7 +222,7 @@ def run_reference(args):
     if rank != 0:
         return
     tmp = tempfile.mkdtemp(prefix="machline_bench_ref_")
-    case, dims = build_case(args.gpus, tmp, args.matrix_solver, args.dims)
+    case, dims = build_case(args.gpus, tmp, args.matrix_solver, args.dims, args.workload)
     n_steps = args.steps + args.warmup
     r = ReferenceRunner(case, budget_s=120.0, n_steps=n_steps)
     times, pairs = [], []
@@ -217,7 +239,7 @@ def run_reference(args):
     cores = r.cores
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64", "data": dims["data"],
             "config": {"workload": workload_name(case, dims), "n_panels": case.info.n_body_panels, "n_unknown": case.n_unknown,
                        "pairs_per_step": float(np.mean(pairs)), "pairs_full_case": case.n_pairs, "matrix_solver": args.matrix_solver},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": r.sample_text()},
@@ -227,9 +249,60 @@ def run_reference(args):
 
 def workload_name(case, dims):
     i = case.info
-    return (f"BASELINE configs[1] family: mirrored swept tapered half wing (ONERA-M6 planform, NACA0010-type section), "
-            f"M=0.5, alpha=3.06deg, automatic wake, dirichlet-morino lower-order; {i.n_body_panels} body panels x 2 images + "
-            f"{i.n_wake_panels} wake panels x 2, {case.n_unknown} unknowns (synthetic mesh {dims['n_chord']}x{dims['n_span']})")
+    img = case.body.n_images
+    head = {"onera_m6": "BASELINE configs[1]: ONERA M6 wing, mirrored about xz, M=0.5, alpha=3.06deg, automatic wake",
+            "synthetic_wing": "BASELINE configs[1] family (weak-scaling stand-in): mirrored swept tapered half wing, ONERA-M6 planform, "
+                              "M=0.5, alpha=3.06deg, automatic wake",
+            "cone": "BASELINE configs[2]: 10 deg cone, mirrored about xy, M=1.5", "sears_haack": "BASELINE configs[2]: Sears-Haack body, M=2, source-free",
+            "agard_b": "BASELINE configs[3]: AGARD-B wing-body, mirrored about yz, M=1.6, supersonic wake"}[dims["workload"]]
+    return (f"{head}; lower-order Dirichlet; {i.n_body_panels} body panels x {img} images + {i.n_wake_panels} wake panels, "
+            f"{case.n_unknown} unknowns; mesh: {dims['mesh']}")
+
+
+def supersonic_probe(local: int, fp64_peak: float, tmp: str):
+    """BASELINE configs[2] on the reference's SH_160_60.tri (M = 2, every pair DoD-tested): the supersonic instantiation of
+    the assembly kernel against the FP64 roofline in SURVEY 8(d)'s flop convention (30 per culled pair, 76 + 44 e per pair
+    evaluated with e edges in the domain of dependence; the class counts come from ml_dod_census), outside the timed region."""
+    from machline_b200 import gpu
+    case, desc = build_case(1, tmp, "GMRES", None, "sears_haack")
+    ctx = gpu.Context(local)
+    try:
+        ctx.set_case(case)
+        ctx.assemble()
+        ms = min(ctx.assemble_resident() for _ in range(3))
+        census = ctx.dod_census()
+        flops = 30.0 * census[0] + sum((76.0 + 44.0 * e) * census[e] for e in (1, 2, 3))
+        x, info = ctx.solve(case.solver_opts(), np.array(case.BC))
+        res = case.post(x)
+        pairs = ctx.pair_count
+        tfl = flops / (ms * 1e-3) / 1e12
+        return {"kernel": "aic_assemble_kernel<supersonic> (DoD test fused, culled pairs skipped)", "bound": "fp64",
+                "achieved": tfl, "peak": fp64_peak, "unit": "TFLOP/s", "frac": tfl / fp64_peak if fp64_peak else None, "traffic": None,
+                "workload": workload_name(case, desc), "avg_launch_ms": ms, "pairs": pairs, "pairs_per_s": pairs / (ms * 1e-3),
+                "pair_classes": {"culled": census[0], "edges_in_dod_1": census[1], "edges_in_dod_2": census[2], "edges_in_dod_3": census[3]},
+                "algorithmic_flops": flops, "solve": {"iterations": int(info.iterations), "ms": info.solve_ms, "res_norm": info.res_norm},
+                "result_check": {"C_p_max": res.C_p_max, "C_p_min": res.C_p_min, "Cx": float(res.C_F[0])}}
+    finally:
+        ctx.close()
+        case.close()
+
+
+def single_gpu_run(local: int, case, opts, BC, steps: int):
+    """One context, whole system on this GPU: (x, iterations, ms per step with resident tables, pairs)."""
+    from machline_b200 import gpu
+    ctx = gpu.Context(local)
+    try:
+        ctx.set_case(case)
+        ctx.assemble()
+        x, info = ctx.solve(opts, BC)
+        t = []
+        for _ in range(steps):
+            a = ctx.assemble_resident()
+            x, info = ctx.solve(opts, BC)
+            t.append(a + info.solve_ms)
+        return x, info, (float(np.mean(t)) if t else None), ctx.pair_count
+    finally:
+        ctx.close()
 
 
 def main():
@@ -241,7 +314,10 @@ def main():
     ap.add_argument("--matrix-solver", default="GMRES")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-lu-probe", action="store_true")
-    ap.add_argument("--dims", default=None, help="tests only: NCxNS mesh instead of the BASELINE-sized one")
+    ap.add_argument("--dims", default=None, help="tests only: NCxNS synthetic mesh instead of the BASELINE-sized one")
+    ap.add_argument("--workload", default=None, choices=["onera_m6", "synthetic_wing", "cone", "sears_haack", "agard_b"],
+                    help="default: onera_m6 (the reference's mesh) at N=1, synthetic_wing (refined with N) at N>1")
+    ap.add_argument("--no-extra-probes", action="store_true", help="skip the supersonic / scaling-reference / parity legs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -256,7 +332,7 @@ def main():
     if world != args.gpus and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     tmp = tempfile.mkdtemp(prefix=f"machline_bench_r{rank}_")
-    case, dims = build_case(world, tmp, args.matrix_solver, args.dims)
+    case, dims = build_case(world, tmp, args.matrix_solver, args.dims, args.workload)
     N = case.n_cp
     row0, nrows = shard.row_shard(N, rank, world)   # contiguous row blocks of the permuted system
     ctx = gpu.Context(local)
@@ -357,10 +433,34 @@ def main():
                     "peak": dmma_peak, "unit": "TFLOP/s", "frac": flops / (best * 1e-3) / 1e12 / dmma_peak,
                     "peak_source": "measured live: register-resident mma.sync.m8n8k4.f64 loop (ml_measure_dmma_peak)",
                     "res_norm": info_lu.res_norm, "max_abs_dx_vs_gmres": float(np.abs(x_lu - x).max()),
-                    "note": "N = 10.5k is latency-bound on the 165 panel launches; profiles/ holds N = 29k (52 %) and the "
+                    "note": "at this N the solve is latency-bound on the panel launches; profiles/ holds larger N and the "
                             "8-GPU N = 104k run"}
         ctx.assemble_resident()   # leave the resident system as the timed region left it
 
+    # ---- legs outside the timed region -------------------------------------------------------------------------------
+    extra = {}
+    if not args.no_extra_probes and not args.dims:
+        if world > 1:
+            barrier()
+            if rank == 0:
+                # (1) parity of the sharded path: the same case assembled and solved on ONE GPU
+                x1, info1, _, _ = single_gpu_run(local, case, opts, BC, 0)
+                r_sh, r_1 = case.post(x), case.post(x1)
+                extra["parity"] = {
+                    "what": f"row-sharded x{world} assemble + solve against a single-GPU assemble + solve of the same case",
+                    "max_abs_dx_over_max_abs_x": float(np.abs(x - x1).max() / np.abs(x1).max()),
+                    "iterations": [int(info.iterations), int(info1.iterations)],
+                    "res_norm": [float(info.res_norm), float(info1.res_norm)],
+                    "max_abs_dCp": float(np.abs(r_sh.C_p - r_1.C_p).max()),
+                    "max_abs_dCF": float(np.abs(np.array(r_sh.C_F) - np.array(r_1.C_F)).max())}
+                # (2) the weak-scaling baseline of THIS mesh family: its N = 1 member on one GPU, same run
+                case1, dims1 = build_case(1, tmp, args.matrix_solver, None, "synthetic_wing")
+                _, i1, ms1, pairs1 = single_gpu_run(local, case1, case1.solver_opts(), np.array(case1.BC), args.steps)
+                extra["scaling_reference"] = {"what": "same synthetic family at N = 1 (pairs per GPU ~equal), one GPU, resident tables",
+                                              "workload": workload_name(case1, dims1), "value": pairs1 / (ms1 * 1e-3), "unit": UNIT,
+                                              "ms_per_step": ms1, "iterations": int(i1.iterations)}
+                case1.close()
+            barrier()
     # ---- reduce over ranks: max time, sum of pairs ---------------------------------------------------
     vals = torch.tensor([step_ms_local, e2e_ms_local, float(np.mean(asm_ms)), float(np.mean(sol_ms)), step_wall_ms_local,
                          e2e_dev_ms_local, gp.gemv_ms, gp.comm_ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -396,22 +496,28 @@ def main():
         asm_tflops = ALG_FLOPS_PER_PAIR_SUBSONIC * local_pairs / (a_ms * 1e-3) / 1e12
         roof_gemv = {"kernel": "gemv_n_partial_kernel (GMRES matvec w = A q)", "bound": "hbm", "achieved": gemv_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": gemv_gbs / hbm_peak if hbm_peak else None,
-                     "traffic": traffic.get("gemv_n_partial_kernel"), "peak_source": hbm_src,
+                     "traffic": traffic.get("gemv_n_partial_kernel") if world == 1 else None,
+                     "traffic_source": (traffic.get("_source", {}).get("gemv") if world == 1 else "not profiled at this N"),
+                     "peak_source": hbm_src,
                      "algorithmic_bytes_per_launch": gemv_bytes, "avg_launch_ms": gemv_avg_ms,
                      "launches_per_step": int(gp.gemv_launches), "share_of_step": gemv_share}
         roof_asm = {"kernel": "aic_assemble_kernel<subsonic>", "bound": "fp64", "achieved": asm_tflops, "peak": fp64_peak,
                     "unit": "TFLOP/s", "frac": asm_tflops / fp64_peak if fp64_peak else None,
-                    "traffic": traffic.get("aic_assemble_kernel"),
-                    "ncu": traffic.get("_aic_ncu"),
+                    "traffic": traffic.get("aic_assemble_kernel") if world == 1 else None,
+                    "traffic_source": (traffic.get("_source", {}).get("aic") if world == 1 else "not profiled at this N"),
+                    "ncu": traffic.get("_aic_ncu") if world == 1 else None,
                     "peak_source": "measured live: register-resident DFMA loop on all SMs (ml_measure_peaks); "
                                    "MEASURED_PEAKS.json carries no FP64 figure",
                     "algorithmic_flops_per_pair": ALG_FLOPS_PER_PAIR_SUBSONIC, "avg_launch_ms": a_ms,
                     "share_of_step": a_ms / max(1e-9, (a_ms + s_ms))}
         dominant, other = (roof_gemv, roof_asm) if gemv_share >= roof_asm["share_of_step"] else (roof_asm, roof_gemv)
+        sup_probe = None
+        if world == 1 and not args.no_extra_probes and not args.dims:
+            sup_probe = supersonic_probe(local, fp64_peak, tmp)
         line = {
             "metric": METRIC, "value": pairs / (step_ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic",
+            "dtype": "f64", "data": dims["data"],
             "config": {"workload": workload_name(case, dims), "n_panels": case.info.n_body_panels, "n_unknown": case.n_unknown,
                        "pairs_per_step": pairs, "matrix_solver": args.matrix_solver, "parallelism": f"row-sharded x{world}" + (" (block-cyclic 128)" if "cyclic" in shard_kw else ""),
                        "l2": "inputs larger than L2: A (8*N^2 bytes) is rewritten by every assembly and streamed by every matvec"},
@@ -431,9 +537,14 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": dominant,
-            "roofline_other": [other] + ([lu_probe] if lu_probe else []),
+            "roofline_other": [other] + ([lu_probe] if lu_probe else []) + ([sup_probe] if sup_probe else []),
             "host_setup_s": dims["host_setup_s"],
+            # the `main`-equivalent wall time of SURVEY 8(d) M2: mesh / wake / control points / panel tables on the host, then
+            # tables -> device -> assembly -> solve -> x on the host (post-processing and file output excluded)
+            "main_equivalent_s": dims["host_setup_s"] + e2e_ms * 1e-3,
         }
+        if extra:
+            line.update(extra)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(case)
         else:

@@ -195,6 +195,11 @@ ml_status ml_device_system(ml_ctx *ctx, double **A_dev, int *ld, int *nrows_loca
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is enqueued on: lets a caller bracket a
    sequence of entry-point calls with its own CUDA events (bench.py times steps on the device this way). */
 ml_status ml_device_stream(ml_ctx *ctx, void **stream_out);
+/* Census of the pair classes of the assembled case (the algorithmic flop count of a supersonic assembly, SURVEY 8(d):
+   30 flop per culled pair, 76 + 44 e per evaluated pair with e edges in the domain of dependence): counts4[0] = pairs
+   outside the domain of dependence (panel_check_dod, src/panel.f90:1732-1901), counts4[e] = evaluated pairs with e = 1..3
+   edges inside.  Subsonic: everything in counts4[3]. */
+ml_status ml_dod_census(ml_ctx *ctx, long long *counts4);
 /* Re-run the assembly kernels only (inputs resident, no host transfers); returns device ms. */
 ml_status ml_assemble_resident(ml_ctx *ctx, double *device_ms);
 /* Roofline denominators measured on this device: FP64 vector pipe (register-resident DFMA loop,

@@ -96,6 +96,8 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     c->d_sm_rows.release();
     c->d_sm_colp.release();
     c->d_sm_colm.release();
+    c->d_g_of_slot.release();
+    c->d_slot_of_g.release();
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -161,6 +163,7 @@ extern "C" ml_status ml_set_flow(ml_ctx* c, const ml_flow* f) {
     c->flow = *f;
     c->have_flow = true;
     c->dirty = true;
+    c->assembled = false;   // a failed re-preparation must not leave the previous system looking valid
     return ML_OK;
 }
 
@@ -179,6 +182,7 @@ extern "C" ml_status ml_set_panels(ml_ctx* c, const ml_panel_soa* body, const ml
     }
     c->have_panels = true;
     c->dirty = true;
+    c->assembled = false;   // a failed re-preparation must not leave the previous system looking valid
     return ML_OK;
 }
 
@@ -198,6 +202,7 @@ extern "C" ml_status ml_set_control_points(ml_ctx* c, int n_cp, const double* lo
     }
     c->have_cps = true;
     c->dirty = true;
+    c->assembled = false;   // a failed re-preparation must not leave the previous system looking valid
     return ML_OK;
 }
 
@@ -216,6 +221,7 @@ extern "C" ml_status ml_set_system_map(ml_ctx* c, const ml_system_map* m) {
     c->map.sigma = nullptr;
     c->have_map = true;
     c->dirty = true;
+    c->assembled = false;   // a failed re-preparation must not leave the previous system looking valid
     return ML_OK;
 }
 
@@ -225,7 +231,7 @@ extern "C" ml_status ml_set_row_shard_cyclic(ml_ctx* c, int block_rows, int rank
     c->cyc_rank = rank;
     c->cyc_world = world;
     c->dirty = true;
-    c->assembled = false;
+    c->assembled = false;   // a failed re-preparation must not leave the previous system looking valid
     return ML_OK;
 }
 
@@ -243,6 +249,7 @@ extern "C" ml_status ml_set_row_shard(ml_ctx* c, int row0, int nrows) {
     c->row0 = row0;
     c->nrows = nrows;
     c->dirty = true;
+    c->assembled = false;   // a failed re-preparation must not leave the previous system looking valid
     return ML_OK;
 }
 
@@ -614,6 +621,27 @@ extern "C" ml_status ml_assemble_resident(ml_ctx* c, double* device_ms) {
     c->assemble_ms = ms;
     c->assembled = true;
     if (device_ms) *device_ms = ms;
+    return ML_OK;
+}
+
+extern "C" ml_status ml_dod_census(ml_ctx* c, long long* counts4) {
+    if (!c || !counts4) return ML_BAD_ARGUMENT;
+    if (!c->assembled) return c->fail(ML_NOT_READY, "ml_dod_census before ml_assemble");
+    ML_CUDA(c, cudaSetDevice(c->device));
+    if (!c->flow.supersonic) {   // subsonic: every pair is evaluated with all three edges
+        counts4[0] = counts4[1] = counts4[2] = 0;
+        counts4[3] = c->pair_count;
+        return ML_OK;
+    }
+    DevBuf<unsigned long long> d;
+    ML_CUDA(c, d.alloc(4));
+    ML_CUDA(c, cudaMemsetAsync(d.p, 0, 4 * sizeof(unsigned long long), c->stream));
+    ML_CUDA(c, launch_dod_census(c, c->d_recs.p, c->n_chunks * c->chunk_records, c->d_cp_xyz.p, c->d_row_active.p, c->n_rows, c->n_rows_pad,
+                                 make_flow_const(c->flow), d.p));
+    unsigned long long h[4];
+    ML_CUDA(c, cudaMemcpyAsync(h, d.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; ++k) counts4[k] = (long long)h[k];
     return ML_OK;
 }
 

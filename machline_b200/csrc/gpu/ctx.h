@@ -48,6 +48,10 @@ struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t pool_stream = nullptr;   // non-null: allocated with cudaMallocAsync on this stream
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;        // owning: every early return releases
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
     cudaError_t alloc(size_t count) {
         if (count <= n && p) return cudaSuccess;
         release();
@@ -105,6 +109,7 @@ struct Ctx {
     std::string err;
     int num_sms = 148;
     long long launches = 0;
+    unsigned attr_mask = 0;   // per-context (= per-device) record of the cudaFuncSetAttribute opt-ins already made (bit per call site)
     // accounting for bench.py (ml_get_profile)
     long long h2d_bytes = 0, d2h_bytes = 0;
     bool profile = false;
@@ -190,6 +195,8 @@ FlowConst make_flow_const(const ml_flow& f);
 cudaError_t launch_aic(Ctx* c, const AicLaunch& L, bool supersonic);
 cudaError_t launch_strength_rows(Ctx* c, double* A, int ld, const int* rows, const int* colp, const int* colm, int n);
 cudaError_t launch_zero_columns(Ctx* c, double* A, int ld, const int* cols, int n_cols);
+cudaError_t launch_dod_census(Ctx* c, const double* recs, int n_rec_slots, const double* cp_xyz, const unsigned char* row_active,
+                              int n_rows, int n_rows_pad, const FlowConst& fc, unsigned long long* d_counts);   // aic_sup.cu
 int aic_chunk_records(int tile_rows);
 int aic_record_stride(bool supersonic);
 int aic_list_bytes(int chunk_records);

@@ -738,11 +738,11 @@ __global__ void __launch_bounds__(256) lu_bwd_step_kernel(const double* __restri
 // C (M x Nc) -= L (M x 64) * U (64 x Nc) on the FP64 tensor cores; all leading dimensions even, pointers 16-byte aligned
 void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ldu, double* Cp, int ldc, int M, int Nc,
                      const unsigned char* row_block_active, int k_halves) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(lu_gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem(1));
-        cudaFuncSetAttribute(lu_gemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem(2));
-        attr_set = true;
+    if (!(c->attr_mask & 2u)) {   // per device: remembered per context
+        cudaError_t e1 = cudaFuncSetAttribute(lu_gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem(1));
+        cudaError_t e2 = cudaFuncSetAttribute(lu_gemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem(2));
+        if (e1 == cudaSuccess && e2 == cudaSuccess) c->attr_mask |= 2u;
+        else c->err = std::string("lu_gemm2 shared-memory opt-in: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2);   // the launch below then fails and is reported
     }
     const int rb = (M + GM_BM - 1) / GM_BM, ct32 = (Nc + G2_BN - 1) / G2_BN;
     int per, chunks;
@@ -760,13 +760,12 @@ static size_t lu_panel_smem(int rpc) {
 }
 
 ml_status LuPanelWork::init(Ctx* c) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    if (!(c->attr_mask & 4u)) {
         ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)lu_panel_smem(LUP_CAP)));
         ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)lu_panel_smem(LUP_RPC_MAX)));
-        attr_set = true;
+        c->attr_mask |= 4u;
     }
     gmax = c->num_sms;
     ML_CUDA(c, pscr.alloc((size_t)2 * gmax * (LUP_ROW + 1) + 2 * LUP_ROW));
@@ -837,11 +836,10 @@ ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int n, int
 // ---- host drivers ---------------------------------------------------------------------------------------
 // In-place LU of the n x n matrix at dA (leading dimension ld).  piv / vv are device work arrays of length n.
 static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double* d_vv, int* d_flag) {
-    static bool attr_set = false;
     const size_t gemm_smem = (size_t)(GM_K * GM_SA + GM_BN * GM_SB) * sizeof(double);
-    if (!attr_set) {
+    if (!(c->attr_mask & 8u)) {
         ML_CUDA(c, cudaFuncSetAttribute(lu_gemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
-        attr_set = true;
+        c->attr_mask |= 8u;
     }
     ML_CUDA(c, cudaMemsetAsync(d_flag, 0, sizeof(int), c->stream));
     int* d_perm = d_piv + n;   // d_piv holds 2 n ints: the interchanges, then the row permutation they compose to

@@ -862,11 +862,11 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     GM_CUDA(cudaMemsetAsync(W.Q.p, 0, (size_t)ldq * (k_max + 1) * sizeof(double), c->stream));
     GM_CUDA(cudaMemsetAsync(W.w.p, 0, (size_t)ldq * sizeof(double), c->stream));
     {
-        static bool attr_set = false;
-        if (!attr_set) {
+        // the opt-in is per device: remembered per context, not per process
+        if (!(c->attr_mask & 1u)) {
             GM_CUDA(cudaFuncSetAttribute(orth_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             GM_CUDA(cudaFuncSetAttribute(arnoldi_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
-            attr_set = true;
+            c->attr_mask |= 1u;
         }
     }
     GM_CUDA(W.ydev.alloc(k_max + 1));
@@ -1328,10 +1328,14 @@ ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_
     S.n_rows_pad = ld;
     S.N = N;
     S.shard_pad = ld;
-    int saved_world = c->world;
-    c->world = 1;  // a host-supplied dense system is never sharded
+    struct WorldGuard {   // a host-supplied dense system is never sharded; restored on every return path
+        Ctx* c;
+        int saved;
+        explicit WorldGuard(Ctx* c_) : c(c_), saved(c_->world) { c->world = 1; }
+        ~WorldGuard() { c->world = saved; }
+    } world_guard(c);
     ml_status st = S.init();
-    if (st != ML_OK) { c->world = saved_world; return st; }
+    if (st != ML_OK) return st;
     DevBuf<double> d_b, d_x, d_scale, Acopy;
     ML_CUDA(c, d_b.alloc(N));
     ML_CUDA(c, d_x.alloc(N));
@@ -1374,7 +1378,6 @@ ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_
     d_x.release();
     d_scale.release();
     S.release();
-    c->world = saved_world;
     return st;
 }
 

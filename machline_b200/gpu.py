@@ -55,6 +55,7 @@ def lib() -> C.CDLL:
         L.ml_solve.argtypes = [vp, C.POINTER(_abi.MlSolverOpts), dp, dp, C.POINTER(_abi.MlSolveInfo)]
         L.ml_solve_dense.argtypes = [vp, C.c_int, dp, dp, C.POINTER(_abi.MlSolverOpts), dp,
                                      C.POINTER(_abi.MlSolveInfo)]
+        L.ml_dod_census.argtypes = [vp, C.POINTER(C.c_longlong)]
         L.ml_device_system.argtypes = [vp, C.POINTER(dp), ip, ip, ip]
         L.ml_measure_peaks.argtypes = [vp, dp, dp]
         L.ml_measure_dmma_peak.argtypes = [vp, dp]
@@ -200,6 +201,12 @@ class Context:
             return
         A_rows = np.asfortranarray(A_rows)
         self._check(lib().ml_set_A(self._h, row0, A_rows.shape[0], _dp(A_rows), A_rows.shape[0]))
+
+    def dod_census(self) -> list[int]:
+        """[culled pairs, evaluated pairs with 1, 2, 3 edges in the domain of dependence] of the assembled case."""
+        out = (C.c_longlong * 4)()
+        self._check(lib().ml_dod_census(self._h, out))
+        return [int(v) for v in out]
 
     @property
     def pair_count(self) -> int:

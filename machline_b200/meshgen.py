@@ -205,3 +205,91 @@ def sears_haack_input(mesh_file: str, mach: float = 2.0, matrix_solver: str = "G
         "post_processing": {},
         "output": {"verbose": False},
     }
+
+
+# ---- committed reference meshes (tests/golden/*.npz) -> mesh files ----------------------------------------------------
+def materialise_npz(npz_path, out_dir, only=None) -> list[str]:
+    """Writes every mesh of an archive made by tests/golden/make_fixtures.py back out as the file type its name says
+    (ASCII VTK v3 / STL / Cart3D .tri) with 17 significant digits, so that the host loader parses exactly the doubles the
+    reference's own files hold, in the same vertex and panel order."""
+    out_dir = Path(out_dir)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    z = np.load(npz_path)
+    names = sorted({k.split(":")[0] for k in z.files})
+    if only is not None:
+        names = [n for n in names if n in set(only)]
+    for name in names:
+        path = out_dir / name
+        if name.endswith(".vtk"):
+            pts, tris = z[f"{name}:points"], z[f"{name}:triangles"]
+            with open(path, "w") as f:
+                f.write("# vtk DataFile Version 3.0\nfixture\nASCII\nDATASET POLYDATA\n")
+                f.write(f"POINTS {len(pts)} float\n")
+                f.write("\n".join(f"{float(p[0])!r} {float(p[1])!r} {float(p[2])!r}" for p in pts) + "\n")
+                f.write(f"POLYGONS {len(tris)} {4 * len(tris)}\n")
+                f.write("\n".join(f"3 {t[0]} {t[1]} {t[2]}" for t in tris) + "\n")
+        elif name.endswith(".tri"):
+            pts, tris = z[f"{name}:points"], z[f"{name}:triangles"]
+            with open(path, "w") as f:
+                f.write(f"{len(pts)} {len(tris)}\n")
+                f.write("\n".join(f"{float(p[0])!r} {float(p[1])!r} {float(p[2])!r}" for p in pts) + "\n")
+                f.write("\n".join(f"{t[0] + 1} {t[1] + 1} {t[2] + 1}" for t in tris) + "\n")
+        elif name.endswith(".stl"):
+            fv = z[f"{name}:facet_vertices"]
+            with open(path, "w") as f:
+                f.write("solid\n")
+                for k in range(0, len(fv), 3):
+                    f.write(" facet normal 0 0 0\n   outer loop\n")
+                    for p in fv[k:k + 3]:
+                        f.write(f"     vertex {float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n")
+                    f.write("   endloop\n endfacet\n")
+                f.write("endsolid\n")
+    return names
+
+
+def study_input(name: str, mesh_dir: str = "", matrix_solver: str = "GMRES", **over) -> dict:
+    """Inputs of BASELINE.json configs[1]-[3] on the reference's own study meshes (SURVEY 8(d) "Concrete inputs";
+    studies/subsonic_onera_m6_wing/M6_input.json, studies/supersonic_cone/cone_input.json,
+    studies/sears_haack/run_study.py:24-55, studies/supersonic_agard_b_wing_body/run_study.py:23-56).  The study scripts
+    say "morino" / "source-free"; today's reference spells them dirichlet-morino / dirichlet-source-free
+    (src/panel_solver.f90:135).  Lower-order singularities."""
+    pre = (mesh_dir.rstrip("/") + "/") if mesh_dir else ""
+    a = np.deg2rad(3.06)
+    cases = {
+        # configs[1]: ONERA M6, Prandtl-Glauert M = 0.5, alpha = 3.06 deg, mirrored about xz, automatic wake
+        "onera_m6": {"flow": {"freestream_velocity": [float(np.cos(a)), 0.0, float(np.sin(a))], "freestream_mach_number": 0.5},
+                     "geometry": {"file": pre + "M6_onera_fine.stl", "mirror_about": "xz", "spanwise_axis": "+y",
+                                  "reference": {"area": 0.7532}},
+                     "solver": {"formulation": "dirichlet-morino"}},
+        # configs[2]: 10 degree cone, M = 1.5, mirrored about xy, no wake
+        "cone": {"flow": {"freestream_velocity": [-1.0, 0.0, 0.0], "gamma": 1.4, "freestream_mach_number": 1.5},
+                 "geometry": {"file": pre + "cone_10_deg_fine.vtk", "spanwise_axis": "+z", "mirror_about": "xy",
+                              "max_continuity_angle": 45.0, "wake_model": {"append_wake": False}, "reference": {"area": 4.0}},
+                 "solver": {"formulation": "dirichlet-morino"}},
+        # configs[2]: Sears-Haack body, M = 2, source-free, no wake
+        "sears_haack": {"flow": {"freestream_velocity": [1.0, 0.0, 0.0], "gamma": 1.4, "freestream_mach_number": 2.0},
+                        "geometry": {"file": pre + "SH_160_60.tri", "spanwise_axis": "+y", "wake_model": {"wake_present": False},
+                                     "reference": {"area": 1.675e-3}},
+                        "solver": {"formulation": "dirichlet-source-free", "control_point_offset": 1.1e-8}},
+        # configs[3]: AGARD-B wing-body, M = 1.6, mirrored about yz, supersonic wake
+        "agard_b": {"flow": {"freestream_velocity": [0.0, 0.0, -1.0], "gamma": 1.4, "freestream_mach_number": 1.6},
+                    "geometry": {"file": pre + "agard_b_fine.vtk", "spanwise_axis": "+x", "mirror_about": "yz", "wake_model": {},
+                                 "reference": {"area": 1.0}},
+                    "solver": {"formulation": "dirichlet-morino"}},
+        "agard_b_coarse": {"flow": {"freestream_velocity": [0.0, 0.0, -1.0], "gamma": 1.4, "freestream_mach_number": 1.6},
+                           "geometry": {"file": pre + "agard_b_coarse.vtk", "spanwise_axis": "+x", "mirror_about": "yz",
+                                        "wake_model": {}, "reference": {"area": 1.0}},
+                           "solver": {"formulation": "dirichlet-morino"}},
+    }
+    inp = cases[name]
+    inp["geometry"]["singularity_order"] = "lower"
+    inp["solver"]["matrix_solver"] = matrix_solver
+    inp["post_processing"] = {"pressure_rules": {"isentropic": True}}
+    inp["output"] = {"verbose": False}
+    for key, val in over.items():
+        d = inp
+        ks = key.split(".")
+        for k in ks[:-1]:
+            d = d.setdefault(k, {})
+        d[ks[-1]] = val
+    return inp

@@ -15,35 +15,20 @@ GOLDEN = Path(__file__).resolve().parent / "golden"
 
 @lru_cache(maxsize=1)
 def _mesh_dir() -> str:
-    """Writes tests/golden/meshes.npz back out as ASCII VTK v3 / STL files (17 significant digits, so the
-    loader parses exactly the doubles the reference's files hold) under <tmp>/test/meshes/."""
+    """Writes tests/golden/meshes.npz and study_meshes.npz back out as mesh files (17 significant digits, so the loader
+    parses exactly the doubles the reference's files hold) under <tmp>/test/meshes/."""
+    from machline_b200 import meshgen
     root = Path(tempfile.mkdtemp(prefix="machline_fixture_"))
     mdir = root / "test" / "meshes"
-    mdir.mkdir(parents=True)
-    z = np.load(GOLDEN / "meshes.npz")
-    names = sorted({k.split(":")[0] for k in z.files})
-    for name in names:
-        if name.endswith(".vtk"):
-            pts, tris = z[f"{name}:points"], z[f"{name}:triangles"]
-            with open(mdir / name, "w") as f:
-                f.write("# vtk DataFile Version 3.0\nfixture\nASCII\nDATASET POLYDATA\n")
-                f.write(f"POINTS {len(pts)} float\n")
-                for p in pts:
-                    f.write(f"{float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n")
-                f.write(f"POLYGONS {len(tris)} {4 * len(tris)}\n")
-                for t in tris:
-                    f.write(f"3 {t[0]} {t[1]} {t[2]}\n")
-        elif name.endswith(".stl"):
-            fv = z[f"{name}:facet_vertices"]
-            with open(mdir / name, "w") as f:
-                f.write("solid\n")
-                for k in range(0, len(fv), 3):
-                    f.write(" facet normal 0 0 0\n   outer loop\n")
-                    for p in fv[k:k + 3]:
-                        f.write(f"     vertex {float(p[0])!r} {float(p[1])!r} {float(p[2])!r}\n")
-                    f.write("   endloop\n endfacet\n")
-                f.write("endsolid\n")
+    meshgen.materialise_npz(GOLDEN / "meshes.npz", mdir)
+    meshgen.materialise_npz(GOLDEN / "study_meshes.npz", mdir)
     return str(root)
+
+
+def study_case(name: str, **over):
+    """host.Case of one of the BASELINE configs[1]-[3] study inputs (meshgen.study_input) on the committed study mesh."""
+    from machline_b200 import host, meshgen
+    return host.Case(meshgen.study_input(name, mesh_dir="test/meshes", **over), base_dir=mesh_root())
 
 
 def mesh_root() -> str:

@@ -90,6 +90,49 @@ def make_meshes():
     print("meshes.npz:", {k: v.shape for k, v in out.items()})
 
 
+def read_vtk_v5(path: Path):
+    """ASCII VTK v5 POLYDATA (OFFSETS / CONNECTIVITY); triangles only.  As src/vtk.f90:560-640 reads it the panel count is
+    the POLYGONS count minus one (the count on that line is the number of offsets)."""
+    toks = path.read_text().split()
+    i = toks.index("POINTS")
+    n = int(toks[i + 1])
+    pts = np.array(toks[i + 3: i + 3 + 3 * n], dtype=np.float64).reshape(n, 3)
+    j = toks.index("POLYGONS") if "POLYGONS" in toks else toks.index("CELLS")   # UNSTRUCTURED_GRID files say CELLS
+    m = int(toks[j + 1]) - 1
+    k = toks.index("CONNECTIVITY", j)
+    tris = np.array(toks[k + 2: k + 2 + 3 * m], dtype=np.int64).reshape(m, 3)
+    offs = np.array(toks[toks.index("OFFSETS", j) + 2: toks.index("OFFSETS", j) + 3 + m], dtype=np.int64)
+    assert (np.diff(offs) == 3).all()
+    return pts, tris.astype(np.int32)
+
+
+def read_tri(path: Path):
+    toks = path.read_text().split()
+    n, m = int(toks[0]), int(toks[1])
+    pts = np.array(toks[2: 2 + 3 * n], dtype=np.float64).reshape(n, 3)
+    tris = np.array(toks[2 + 3 * n: 2 + 3 * n + 3 * m], dtype=np.int64).reshape(m, 3) - 1
+    return pts, tris.astype(np.int32)
+
+
+def make_study_meshes():
+    """The meshes of BASELINE.json configs[1]-[3] (SURVEY 8(d) "Concrete inputs"): ONERA M6 fine, cone fine, Sears-Haack
+    160x60, AGARD-B coarse / fine.  Kept in a second archive so that the small one stays small."""
+    S = REF / "studies"
+    out = {}
+    for name, path in [("agard_b_coarse.vtk", S / "supersonic_agard_b_wing_body/meshes/agard_b_coarse.vtk"),
+                       ("agard_b_fine.vtk", S / "supersonic_agard_b_wing_body/meshes/agard_b_fine.vtk")]:
+        pts, tris = read_vtk_v5(path)
+        out[f"{name}:points"], out[f"{name}:triangles"] = pts, tris
+    pts, tris, _ = read_vtk_v3(S / "supersonic_cone/meshes/cone_10_deg_fine.vtk")
+    out["cone_10_deg_fine.vtk:points"], out["cone_10_deg_fine.vtk:triangles"] = pts, tris
+    pts, tris = read_tri(S / "sears_haack/meshes/SH_160_60.tri")
+    out["SH_160_60.tri:points"], out["SH_160_60.tri:triangles"] = pts, tris
+    pts, _ = read_stl(S / "subsonic_onera_m6_wing/meshes/M6_onera_fine.stl")
+    out["M6_onera_fine.stl:facet_vertices"] = pts
+    np.savez_compressed(OUT / "study_meshes.npz", **out)
+    print("study_meshes.npz:", {k: v.shape for k, v in out.items()})
+
+
 # (C_p_max, C_p_min, Cx, Cy, Cz) and tolerances, transcribed from test/test_machline.py (line numbers
 # of the asserts).  "alter" is the list of (dotted key, value) edits the test applies to the base input.
 GOLDENS = [
@@ -261,6 +304,7 @@ if __name__ == "__main__":
     make_solver_histories()
     make_offbody()
     make_meshes()
+    make_study_meshes()
     make_goldens()
     make_prototype_integrals()
     make_singular_values()     # after make_meshes: only meshes that are in meshes.npz

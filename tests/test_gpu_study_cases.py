@@ -1,0 +1,94 @@
+"""GPU: BASELINE.json configs[1]-[3] on the reference's OWN study meshes (SURVEY 8(d) "Concrete inputs"; committed in
+tests/golden/study_meshes.npz): ONERA M6 fine (M = 0.5, mirrored, wake), the 10 degree cone fine (M = 1.5, mirrored),
+Sears-Haack 160x60 (M = 2, source-free) and AGARD-B coarse / fine (M = 1.6, mirrored, supersonic wake; GMRES and LU).
+Every case: AIC entries of the CUDA assembly against the oracle on the same tables (1e-12, metric of test_gpu_parity.py),
+then surface Cp and force coefficients of the CUDA solve against the oracle's solve of ITS matrix (1e-9, north star)."""
+import numpy as np
+import pytest
+
+import fixtures
+import oracle_binding as ob
+from test_gpu_parity import _rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from machline_b200 import gpu
+    c = gpu.Context(0)
+    yield c
+    c.close()
+
+
+def _check_rows(A, A_ref, S, I_known, I_ref):
+    assert ((A == 0) == (A_ref == 0)).all()                    # same domain of dependence, pair by pair
+    err = _rel_err(A, A_ref, S)
+    assert err.max() < 2e-14, f"max AIC error relative to its terms {err.max():.3e}"
+    assert (np.abs(A - A_ref) / np.abs(A_ref).max(axis=1, keepdims=True).clip(1e-300)).max() < 1e-12
+    sel = np.abs(A_ref) > 0.25 * S
+    assert (np.abs(A - A_ref)[sel] / np.abs(A_ref)[sel]).max() < 1e-12
+    assert np.abs(I_known - I_ref).max() <= 1e-13 * max(1e-300, np.abs(I_ref).max())
+
+
+def _check_post(case, x, x_ref):
+    res, ref = case.post(x), case.post(x_ref)
+    assert abs(res.C_p_max - ref.C_p_max) < 1e-9 and abs(res.C_p_min - ref.C_p_min) < 1e-9
+    assert np.abs(res.C_p - ref.C_p).max() < 1e-9
+    assert np.abs(np.array(res.C_F) - np.array(ref.C_F)).max() < 1e-9
+    return res
+
+
+@pytest.mark.parametrize("name", ["agard_b_coarse", "agard_b", "onera_m6", "sears_haack"])
+def test_study_case_matches_oracle(ctx, name):
+    case = fixtures.study_case(name)
+    ctx.set_case(case)
+    I_known = ctx.assemble()
+    A = ctx.get_A()
+    A_ref, I_ref, S = ob.assemble(case, with_scale=True)
+    _check_rows(A, A_ref, S, I_known, I_ref)
+    x, info = ctx.solve(case.solver_opts(), case.BC)
+    x_ref, info_ref = ob.solve_system(A_ref, I_ref, case.BC, case.solver_opts())
+    assert abs(info.iterations - info_ref.iterations) <= max(1, info_ref.iterations // 100)
+    assert info.res_norm < 1e-10
+    res = _check_post(case, x, x_ref)
+    print(f"{name}: N={case.n_unknown} pairs={case.n_pairs:.3g} iterations gpu/oracle {info.iterations}/{info_ref.iterations} "
+          f"C_p [{res.C_p_min:.6f}, {res.C_p_max:.6f}] C_F {np.array(res.C_F)}")
+    case.close()
+
+
+@pytest.mark.parametrize("name", ["agard_b_coarse", "agard_b"])
+def test_agard_b_direct_lu_matches_oracle_lu(ctx, name):
+    """configs[3] "GMRES vs direct LU": the CUDA blocked LU on the CUDA matrix against the oracle's lu_solve on the oracle's."""
+    from machline_b200 import _abi
+    case = fixtures.study_case(name, matrix_solver="LU")
+    opts = _abi.solver_opts("LU", preconditioner="DIAG")
+    ctx.set_case(case)
+    ctx.assemble()
+    x, info = ctx.solve(opts, case.BC)
+    A_ref, I_ref = ob.assemble(case)
+    x_ref, _ = ob.solve_system(A_ref, I_ref, case.BC, opts)
+    assert info.iterations == -1 and info.res_norm < 1e-10
+    # cond(A) = 3e7: the two factorizations agree to cond * eps in x, and to 1e-9 in everything derived from it
+    assert np.abs(x - x_ref).max() <= 1e-8 * np.abs(x_ref).max()
+    _check_post(case, x, x_ref)
+    case.close()
+
+
+def test_cone_fine_row_windows_match_oracle(ctx):
+    """configs[2], 12 121 unknowns x 47 800 panel images: three windows of rows of the CUDA matrix against the oracle, the
+    zone of silence (rows upstream of everything are exactly zero outside their own cone), and the solve by properties."""
+    case = fixtures.study_case("cone")
+    N = case.n_cp
+    ctx.set_case(case)
+    I_known = ctx.assemble()
+    for row0 in (0, N // 2 - 128, N - 256):
+        A_ref, I_ref, S = ob.assemble(case, row0=row0, nrows=256, with_scale=True)
+        A = ctx.get_A(row0, 256)
+        _check_rows(A, A_ref, S, I_known[row0:row0 + 256], I_ref)
+    x, info = ctx.solve(case.solver_opts(), case.BC)
+    assert info.res_norm < 1e-10 and 0 < info.iterations < 1000
+    res = case.post(x)
+    # axisymmetric body at zero incidence: no side force, no lift
+    assert abs(res.C_F[1]) < 1e-8 and abs(res.C_F[2]) < 1e-8 and res.C_F[0] < 0.   # V = (-1,0,0): drag along -x
+    case.close()
