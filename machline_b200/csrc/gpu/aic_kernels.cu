@@ -32,7 +32,7 @@ FlowConst make_flow_const(const ml_flow& f) {
     return h;
 }
 
-int aic_chunk_records(int tile_rows) { return tile_rows == 8 ? 128 : 64; }
+int aic_chunk_records(int tile_rows) { return tile_rows <= 8 ? 128 : 64; }
 int aic_record_stride(bool supersonic) { return supersonic ? R_SUP_STRIDE : R_SUB_STRIDE; }
 int aic_list_bytes(int chunk_records) { return list_bytes(chunk_records); }
 

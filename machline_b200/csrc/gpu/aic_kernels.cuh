@@ -79,7 +79,7 @@ struct AicSmem {
 };
 
 template <bool SUP, int R, int C>
-__global__ void __launch_bounds__(AIC_THREADS, 2) aic_assemble_kernel(const AicLaunch L) {
+__global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : 3) aic_assemble_kernel(const AicLaunch L) {
     using S = AicSmem<SUP, C>;
     constexpr int SUBS = AIC_THREADS / R;   // records evaluated concurrently by the CTA
     constexpr int CPW = 32 / R;             // columns one warp handles concurrently in phase 2
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(AIC_THREADS, 2) aic_assemble_kernel(const AicL
     double* const s_stage = reinterpret_cast<double*>(smem_raw + S::STAGE_OFF);
     __shared__ uint64_t full_bar[2];
     __shared__ int s_tile;
-    __shared__ double s_red[AIC_THREADS];
+    double* const s_red = s_stage;   // [AIC_THREADS] partial sums of I_known: the stage is free at the end of a tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int row_l = tid & (R - 1), sub0 = tid / R;

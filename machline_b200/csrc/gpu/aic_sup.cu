@@ -8,6 +8,7 @@ cudaError_t launch_aic_supersonic(Ctx* c, const AicLaunch& L) {
         case 32: return launch_aic_t<true, 32, 64>(c, L);
         case 16: return launch_aic_t<true, 16, 64>(c, L);
         case 8: return launch_aic_t<true, 8, 128>(c, L);
+        case 4: return launch_aic_t<true, 4, 128>(c, L);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -333,7 +333,7 @@ static ml_status prepare(ml_ctx* c) {
         }
         if (const char* e = std::getenv("MACHLINE_AIC_TILE_ROWS")) {
             int v = std::atoi(e);
-            if (v == 8 || v == 16 || v == 32) R = v;
+            if (v == 4 || v == 8 || v == 16 || v == 32) R = v;
         }
         c->tile_rows = R;
         c->chunk_records = aic_chunk_records(R);
