@@ -31,6 +31,9 @@
 
 namespace mlgpu {
 
+#ifndef ML_AIC_SUB_CTAS
+#define ML_AIC_SUB_CTAS 2
+#endif
 constexpr int AIC_THREADS = 256;
 constexpr int AIC_WARPS = AIC_THREADS / 32;
 
@@ -79,7 +82,7 @@ struct AicSmem {
 };
 
 template <bool SUP, int R, int C>
-__global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : 3) aic_assemble_kernel(const AicLaunch L) {
+__global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_assemble_kernel(const AicLaunch L) {
     using S = AicSmem<SUP, C>;
     constexpr int SUBS = AIC_THREADS / R;   // records evaluated concurrently by the CTA
     constexpr int CPW = 32 / R;             // columns one warp handles concurrently in phase 2
@@ -158,8 +161,9 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : 3) aic_assemble_kernel(
                 const bool wake = (lst[2] & LF_WAKE) != 0;
                 const unsigned* cols = reinterpret_cast<const unsigned*>(lst + 4);
                 const unsigned short* beg = reinterpret_cast<const unsigned short*>(lst + 4 + S::MAXI);
-                const unsigned short* item = beg + S::MAXI + 2;
+                const unsigned* item = reinterpret_cast<const unsigned*>(beg + S::MAXI + 2);
                 double* const base = (wake ? L.W : L.A) + (size_t)tile * R + (lane & (R - 1));
+                const char* const stage_lane = reinterpret_cast<const char*>(s_stage + (lane & (R - 1)));
                 for (int ci = warp * CPW + lane / R; ci < n_cols; ci += AIC_WARPS * CPW) {
                     const unsigned cw = cols[ci];
                     double* dst = base + (size_t)(cw & ~COL_FIRST) * ld;
@@ -168,9 +172,9 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : 3) aic_assemble_kernel(
                     double acc = (!SUP && (cw & COL_FIRST)) ? 0. : __ldcg(dst);
                     const int i1 = beg[ci + 1];
                     for (int it = beg[ci]; it < i1; ++it) {
-                        const unsigned u = item[it];
-                        const double v = s_stage[(size_t)(u & 0x7fffu) * R + (lane & (R - 1))];
-                        acc = (u & 0x8000u) ? acc - v : acc + v;
+                        const unsigned u = item[it];   // byte offset of the staged value | sign
+                        const double v = *reinterpret_cast<const double*>(stage_lane + (u & ~ITEM_NEG));
+                        acc = acc + __hiloint2double(__double2hiint(v) ^ (int)(u & ITEM_NEG), __double2loint(v));
                     }
                     __stcg(dst, acc);
                 }

@@ -427,11 +427,23 @@ static ml_status prepare(ml_ctx* c) {
         int* head = reinterpret_cast<int*>(lists.data() + (size_t)chunk * LB);
         unsigned* cols = reinterpret_cast<unsigned*>(head + 4);
         unsigned short* beg = reinterpret_cast<unsigned short*>(head + 4 + MAXI);
-        unsigned short* item = beg + MAXI + 2;
+        unsigned* item = reinterpret_cast<unsigned*>(beg + MAXI + 2);
+        const unsigned item_scale = (unsigned)c->tile_rows * 8u;   // bytes between consecutive staged values of one row
         std::vector<int> order;                       // columns in order of first appearance
-        std::vector<std::vector<unsigned short>> per; // items per column, in (record, slot) order
-        for (size_t r = 0; r < n_here; ++r) {
-            const HostRecord& hr = src[first + r];
+        std::vector<std::vector<unsigned>> per;       // items per column, in (record, slot) order
+        // Position of a record inside the chunk: images of the panel itself first, mirror images after them (each group in
+        // stream order), so that the records a warp evaluates together share the mirror flag (pair_influence.cuh).  The order
+        // of ADDITION is unaffected: it is the order of the items below, which follows the stream.
+        std::vector<int> pos(n_here);
+        {
+            int n0 = 0;
+            for (size_t r = 0; r < n_here; ++r) n0 += (src[first + r].img == 0);
+            int p0 = 0, p1 = n0;
+            for (size_t r = 0; r < n_here; ++r) pos[r] = (src[first + r].img == 0) ? p0++ : p1++;
+        }
+        for (size_t r0 = 0; r0 < n_here; ++r0) {
+            const HostRecord& hr = src[first + r0];
+            const size_t r = (size_t)pos[r0];
             pack_record(recs.data() + ((size_t)chunk * C + r) * STRIDE, STRIDE, sup, view_of(*hr.table), hr.j, hr.img, hr.sigma_val, hr.flags);
             for (int k = 0; k < hr.n_slots; ++k) {
                 const int col = hr.cols[k];
@@ -440,7 +452,7 @@ static ml_status prepare(ml_ctx* c) {
                     order.push_back(col);
                     per.emplace_back();
                 }
-                per[slot_of_col[col]].push_back((unsigned short)((r * 3 + (k % 3)) | (k >= 3 ? 0x8000u : 0u)));
+                per[slot_of_col[col]].push_back((unsigned)(r * 3 + (k % 3)) * item_scale | (k >= 3 ? ITEM_NEG : 0u));
             }
         }
         int n_items = 0;
@@ -464,7 +476,7 @@ static ml_status prepare(ml_ctx* c) {
             }
             cols[i] = target | (first_touch ? COL_FIRST : 0u);
             beg[i] = (unsigned short)n_items;
-            for (unsigned short u : per[i]) item[n_items++] = u;
+            for (unsigned u : per[i]) item[n_items++] = u;
             slot_of_col[col] = -1;
         }
         beg[order.size()] = (unsigned short)n_items;

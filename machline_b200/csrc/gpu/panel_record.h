@@ -1,8 +1,10 @@
 // Packed per-image panel record, the unit the assembly kernel stages in shared memory with a bulk
 // (TMA) copy.  One record per (panel, image); doubles first, then an int tail.
 // Source of every field: type(panel) members used at evaluation time (src/panel.f90:38-70).
-// The record stride is an ODD number of doubles (37 / 51): when the lanes of a warp read the same field of
-// 2, 4 or 8 different records (row tiles narrower than a warp) the 8-byte accesses fall in distinct banks.
+// The record stride is an EVEN number of doubles (38 / 52), so every record is 16-byte aligned and its fields are read
+// with 128-bit shared-memory loads (two doubles per LDS); the strides are 304 B and 416 B = 12 and 8 banks (mod 32), so
+// the 16-byte accesses of the 2, 4 or 8 different records a warp reads at once (row tiles narrower than a warp) fall
+// in distinct banks.
 #pragma once
 
 namespace mlgpu {
@@ -20,12 +22,12 @@ enum : int {
                     //         [1] subsonic: float bits of the near-edge threshold (0.05 * longest edge)^2
     R_AREA2 = 36,   // [1]   |(v2-v1) x (v3-v1)| in local scaled coordinates = twice the panel area there (subsonic only)
     R_SUB_DOUBLES = 37,  // subsonic payload
-    R_SUB_STRIDE = 37,   // subsonic record stride (296 B)
+    R_SUB_STRIDE = 38,   // subsonic record stride (304 B)
     R_B = 36,       // [3]   edge parameter b            (supersonic only from here on)
     R_SB = 39,      // [3]   sqrt|b|
     R_VG = 42,      // [9]   global vertex locations of this image (DoD tests)
     R_SUP_DOUBLES = 51,  // supersonic payload
-    R_SUP_STRIDE = 51    // supersonic record stride (408 B)
+    R_SUP_STRIDE = 52    // supersonic record stride (416 B)
 };
 
 enum : int { RF_EVAL = 1, RF_MIRROR = 2, RF_SOURCE = 4 };
@@ -37,9 +39,11 @@ enum : int { RF_EVAL = 1, RF_MIRROR = 2, RF_SOURCE = 4 };
 //   int  head[4]      : n_cols, n_items, flags (bit0: wake pass), spare
 //   int  col[6C]      : target column; bit 31 set = first chunk of the pass that touches it (start from 0)
 //   u16  beg[6C + 2]  : item range of column i = [beg[i], beg[i+1])
-//   u16  item[6C]     : (record_in_chunk * 3 + slot % 3) | (slot >= 3 ? 0x8000 : 0)   (0x8000 = subtract)
+//   u32  item[6C]     : byte offset of the staged value, (position_in_chunk * 3 + slot % 3) * R * 8 (R = tile rows), with
+//                       bit 31 set when the item is subtracted (slot >= 3: bottom side of a wake panel)
 constexpr int list_max_items(int C) { return 6 * C; }
-constexpr int list_bytes(int C) { return ((16 + 4 * list_max_items(C) + 2 * (list_max_items(C) + 2) + 2 * list_max_items(C)) + 15) / 16 * 16; }
+constexpr int list_bytes(int C) { return ((16 + 4 * list_max_items(C) + 2 * (list_max_items(C) + 2) + 4 * list_max_items(C)) + 15) / 16 * 16; }
+constexpr unsigned ITEM_NEG = 0x80000000u;
 enum : int { LF_WAKE = 1 };
 constexpr unsigned COL_FIRST = 0x80000000u;
 

@@ -24,7 +24,9 @@ _lib = None
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        path = build.GPU_LIB
+        import os
+        from pathlib import Path
+        path = Path(os.environ["MACHLINE_GPU_LIB"]) if os.environ.get("MACHLINE_GPU_LIB") else build.GPU_LIB   # kernel experiments: a variant build
         if not path.exists():
             raise ImportError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(the CUDA extension is the only compute path; there is no fallback)")
