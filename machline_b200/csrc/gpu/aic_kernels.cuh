@@ -77,8 +77,10 @@ struct AicSmem {
     static constexpr int REC_OFF = 0;
     static constexpr int LIST_OFF = (REC_BYTES + 127) / 128 * 128;
     static constexpr int STAGE_OFF = (LIST_OFF + 2 * LIST_BYTES + 127) / 128 * 128;
-    static constexpr int stage_bytes(int R) { return C * 3 * R * 8; }
-    static constexpr int total(int R) { return STAGE_OFF + stage_bytes(R); }
+    static constexpr int SLOTS = SUP ? 4 : 3;   // staged values per (record, row): three doublet coefficients (+ the source term)
+    static constexpr int stage_bytes(int R) { return C * SLOTS * R * 8; }
+    static constexpr int queue_bytes(int R) { return SUP ? R * C * 2 : 0; }   // per-row queues of in-DoD records (u16)
+    static constexpr int total(int R) { return STAGE_OFF + stage_bytes(R) + queue_bytes(R); }
 };
 
 template <bool SUP, int R, int C>
@@ -90,8 +92,10 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
     double* const s_rec = reinterpret_cast<double*>(smem_raw + S::REC_OFF);
     unsigned char* const s_list = smem_raw + S::LIST_OFF;
     double* const s_stage = reinterpret_cast<double*>(smem_raw + S::STAGE_OFF);
+    unsigned short* const s_q = reinterpret_cast<unsigned short*>(smem_raw + S::STAGE_OFF + C * S::SLOTS * R * 8);   // [R][C], SUP only
     __shared__ uint64_t full_bar[2];
     __shared__ int s_tile;
+    __shared__ int s_qn[R];          // SUP: entries in each row's queue
     double* const s_red = s_stage;   // [AIC_THREADS] partial sums of I_known: the stage is free at the end of a tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -101,6 +105,7 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
         mbar_init(&full_bar[1], 1);
         fence_mbar_init();
     }
+    if (tid < R) s_qn[tid] = 0;
     __syncthreads();
     uint32_t phase[2] = {0, 0};
     const FlowConst& fc = L.fc;   // kernel parameters live in the constant bank
@@ -128,28 +133,80 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
             const int b = t & 1;
             mbar_wait(&full_bar[b], phase[b]);
             phase[b] ^= 1;
-            // ---- phase 1: pair influences -> stage ----------------------------------------------------------
-            int any = 0;
+            int live;
+            if constexpr (!SUP) {
+                // ---- phase 1: pair influences -> stage ------------------------------------------------------
 #pragma unroll 1
-            for (int r = sub0; r < C; r += SUBS) {
-                const double* rec = s_rec + r * S::STRIDE;
-                const int flags = reinterpret_cast<const int*>(rec + R_FLAGS)[0];
-                double ps = 0., pd[3] = {0., 0., 0.};
-                bool ok = false;
-                if (active && (flags & RF_EVAL)) ok = pair_influence<SUP>(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, ps, pd);
-                if (ok) {
-                    if (flags & RF_SOURCE) Ik = Ik + ps * rec[R_SIGMA];   // panel_solver.f90:1245-1246
-                    any = 1;
-                } else {
-                    pd[0] = pd[1] = pd[2] = 0.;
+                for (int r = sub0; r < C; r += SUBS) {
+                    const double* rec = s_rec + r * S::STRIDE;
+                    const int flags = reinterpret_cast<const int*>(rec + R_FLAGS)[0];
+                    double ps = 0., pd[3] = {0., 0., 0.};
+                    if (active && (flags & RF_EVAL)) {
+                        pair_influence<false>(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, ps, pd);
+                        if (flags & RF_SOURCE) Ik = Ik + ps * rec[R_SIGMA];   // panel_solver.f90:1245-1246
+                    }
+                    double* st = s_stage + (size_t)(r * 3) * R + row_l;
+                    st[0] = pd[0];
+                    st[R] = pd[1];
+                    st[2 * R] = pd[2];
                 }
-                double* st = s_stage + (size_t)(r * 3) * R + row_l;
-                st[0] = pd[0];
-                st[R] = pd[1];
-                st[2 * R] = pd[2];
+                __syncthreads();
+                live = 1;
+            } else {
+                // ---- phase 1a: domain-of-dependence test of every (record, row) pair of the chunk; the pairs inside are
+                // compacted with a warp ballot into one queue per row, so that phase 1b runs the influence integrals on
+                // full warps whatever fraction of the chunk is culled (panel_check_dod, src/panel.f90:1732-1901) -----
+                const bool chunk_src = (reinterpret_cast<const int*>(s_list + b * S::LIST_BYTES)[2] & LF_SOURCES) != 0;
+                constexpr unsigned ROWMASK = R == 32 ? 0x1u : R == 16 ? 0x00010001u : R == 8 ? 0x01010101u : 0x11111111u;
+#pragma unroll 1
+                for (int r = sub0; r < C; r += SUBS) {
+                    const double* rec = s_rec + r * S::STRIDE;
+                    const int flags = reinterpret_cast<const int*>(rec + R_FLAGS)[0];
+                    bool e_in[3] = {false, false, false};
+                    bool in = false;
+                    if (active && (flags & RF_EVAL)) in = panel_check_dod(fc, rec, Px, Py, Pz, e_in);
+                    const unsigned mine = __ballot_sync(0xffffffffu, in) & (ROWMASK << (lane & (R - 1)));   // lanes of my row
+                    int base = 0;
+                    if (lane < R && mine) base = atomicAdd(&s_qn[row_l], __popc(mine));
+                    base = __shfl_sync(0xffffffffu, base, lane & (R - 1));
+                    if (in) {
+                        s_q[row_l * C + base + __popc(mine & ((1u << lane) - 1u))] =
+                            (unsigned short)(r | ((int)e_in[0] << 8) | ((int)e_in[1] << 9) | ((int)e_in[2] << 10));
+                    } else {
+                        double* st = s_stage + (size_t)(r * 4) * R + row_l;
+                        st[0] = 0.;
+                        st[R] = 0.;
+                        st[2 * R] = 0.;
+                        if (chunk_src) st[3 * R] = 0.;
+                    }
+                }
+                __syncthreads();
+                // ---- phase 1b: influence integrals of the queued pairs -> stage --------------------------------
+                const int qn = s_qn[row_l];
+#pragma unroll 1
+                for (int k = sub0; k < qn; k += SUBS) {
+                    const unsigned e = s_q[row_l * C + k];
+                    const int r = (int)(e & 0xffu);
+                    const double* rec = s_rec + r * S::STRIDE;
+                    const int flags = reinterpret_cast<const int*>(rec + R_FLAGS)[0];
+                    const bool e_in[3] = {(e & 0x100u) != 0, (e & 0x200u) != 0, (e & 0x400u) != 0};
+                    double ps = 0., pd[3] = {0., 0., 0.};
+                    pair_eval_supersonic(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, e_in, ps, pd);
+                    double* st = s_stage + (size_t)(r * 4) * R + row_l;
+                    st[0] = pd[0];
+                    st[R] = pd[1];
+                    st[2 * R] = pd[2];
+                    if (chunk_src) st[3 * R] = (flags & RF_SOURCE) ? ps * rec[R_SIGMA] : 0.;
+                }
+                // a chunk entirely outside every row's domain of dependence adds only zeros -> phase 2 is skipped
+                live = __syncthreads_or(qn > 0);
+                if (tid < R) s_qn[tid] = 0;   // next written after the barrier that ends phase 2
+                if (live && chunk_src) {
+                    // known-source terms of this chunk, in the fixed order (records sub0, sub0 + SUBS, ...) of the subsonic kernel
+#pragma unroll 1
+                    for (int r = sub0; r < C; r += SUBS) Ik = Ik + s_stage[(size_t)(r * 4 + 3) * R + row_l];   // panel_solver.f90:1245-1246
+                }
             }
-            // supersonic: a chunk entirely outside every row's domain of dependence adds only zeros -> skip phase 2
-            const int live = SUP ? __syncthreads_or(any) : (__syncthreads(), 1);
             if (tid == 0 && t + 1 < L.n_chunks) {
                 fence_proxy_async();
                 issue(t + 1);

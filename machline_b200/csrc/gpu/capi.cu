@@ -452,7 +452,7 @@ static ml_status prepare(ml_ctx* c) {
                     order.push_back(col);
                     per.emplace_back();
                 }
-                per[slot_of_col[col]].push_back((unsigned)(r * 3 + (k % 3)) * item_scale | (k >= 3 ? ITEM_NEG : 0u));
+                per[slot_of_col[col]].push_back((unsigned)(r * (sup ? 4 : 3) + (k % 3)) * item_scale | (k >= 3 ? ITEM_NEG : 0u));
             }
         }
         int n_items = 0;
@@ -482,7 +482,9 @@ static ml_status prepare(ml_ctx* c) {
         beg[order.size()] = (unsigned short)n_items;
         head[0] = (int)order.size();
         head[1] = n_items;
-        head[2] = wake ? LF_WAKE : 0;
+        bool any_src = false;
+        for (size_t r0 = 0; r0 < n_here; ++r0) any_src = any_src || (src[first + r0].flags & RF_SOURCE);
+        head[2] = (wake ? LF_WAKE : 0) | (any_src ? LF_SOURCES : 0);
         head[3] = (int)n_here;
     };
     for (int ch = 0; ch < n_body_chunks; ++ch) build_chunk(ch, body_recs, (size_t)ch * C, false);

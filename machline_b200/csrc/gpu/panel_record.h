@@ -39,12 +39,13 @@ enum : int { RF_EVAL = 1, RF_MIRROR = 2, RF_SOURCE = 4 };
 //   int  head[4]      : n_cols, n_items, flags (bit0: wake pass), spare
 //   int  col[6C]      : target column; bit 31 set = first chunk of the pass that touches it (start from 0)
 //   u16  beg[6C + 2]  : item range of column i = [beg[i], beg[i+1])
-//   u32  item[6C]     : byte offset of the staged value, (position_in_chunk * 3 + slot % 3) * R * 8 (R = tile rows), with
+//   u32  item[6C]     : byte offset of the staged value, (position_in_chunk * S + slot % 3) * R * 8 (R = tile rows, S = staged
+//                       values per record and row: 3 subsonic, 4 supersonic), with
 //                       bit 31 set when the item is subtracted (slot >= 3: bottom side of a wake panel)
 constexpr int list_max_items(int C) { return 6 * C; }
 constexpr int list_bytes(int C) { return ((16 + 4 * list_max_items(C) + 2 * (list_max_items(C) + 2) + 4 * list_max_items(C)) + 15) / 16 * 16; }
 constexpr unsigned ITEM_NEG = 0x80000000u;
-enum : int { LF_WAKE = 1 };
+enum : int { LF_WAKE = 1, LF_SOURCES = 2 };   // LF_SOURCES: some record of the chunk feeds a known source strength
 constexpr unsigned COL_FIRST = 0x80000000u;
 
 }  // namespace mlgpu
