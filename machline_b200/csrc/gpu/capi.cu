@@ -78,8 +78,8 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     if (c->h_stage) cudaFreeHost(c->h_stage);
     for (auto& e : c->slot_ev)
         if (e) cudaEventDestroy(e);
-#ifdef ML_HAVE_NCCL
     mlgpu::p2p_release(c);
+#ifdef ML_HAVE_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
     c->d_recs.release();

@@ -168,6 +168,8 @@ struct Ctx {
     // (CUDA IPC); after the matvec one CTA per peer stores this rank's rows of w straight into that peer's window over NVLink
     // and raises a flag there.
     static constexpr int P2P_MAX = 8;
+    static constexpr int P2P_KR = 2048;  // doubles per rank in a reduction slot of the sharded Arnoldi tail (k_max + 2 <= P2P_KR)
+    unsigned xseq = 0;                  // exchanges of the sharded Arnoldi tail so far (identical on every rank)
     double* win = nullptr;              // this rank's window: [2][win_n] doubles, then [2][P2P_MAX] flags
     size_t win_n = 0;                   // doubles per parity buffer
     void* peer_base[P2P_MAX] = {};      // mapped windows (peer_base[rank] == win)

@@ -594,9 +594,13 @@ __global__ void __launch_bounds__(256) p2p_wait_copy_kernel(const double* __rest
     if (i < n) y_full[i] = __ldcg(win_w + i);
 }
 
-#ifdef ML_HAVE_NCCL
-// Map every rank's window into this process (CUDA IPC; one process per GPU on one node).  Collective: every rank calls
-// it with the same n.  On any failure on any rank all ranks fall back to ncclAllGather (p2p_ok = false).
+// ---- peer-memory windows (CUDA IPC; one process per GPU on one node) ----------------------------------------------------
+// Layout of a window, in doubles (win_n = N rounded up to 64, KR = Ctx::P2P_KR):
+//   [0, 2 win_n)            vector, two parities       (Sys::exchange: p2p_push_kernel / p2p_wait_copy_kernel)
+//   8 doubles               flags of that exchange     ([2][P2P_MAX] u32)
+//   8 doubles               flags of the sharded Arnoldi tail ([2][P2P_MAX] u32, gmres_sharded.cuh)
+//   [.., + 2 win_n)         vector of the sharded Arnoldi tail, two parities
+//   [.., + 2 P2P_MAX KR)    reduction slots of the sharded Arnoldi tail, two parities
 static void p2p_teardown(Ctx* c) {
     for (int r = 0; r < Ctx::P2P_MAX; ++r) {
         if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
@@ -611,12 +615,29 @@ static void p2p_teardown(Ctx* c) {
 
 void p2p_release(Ctx* c) { p2p_teardown(c); }
 
-static size_t p2p_window_bytes(size_t win_n) { return 2 * win_n * sizeof(double) + 2 * Ctx::P2P_MAX * sizeof(unsigned); }
+static size_t p2p_window_doubles(size_t win_n) { return 4 * win_n + 16 + (size_t)2 * Ctx::P2P_MAX * Ctx::P2P_KR; }
+static size_t p2p_window_bytes(size_t win_n) { return p2p_window_doubles(win_n) * sizeof(double); }
 
-static ml_status p2p_setup(Ctx* c, int n) {
+// Collective: every rank calls it with the same n.  On any failure on any rank all ranks fall back to ncclAllGather
+// (p2p_ok = false).  local_only: one rank, the window is its own memory (the multi-rank kernels on the single-GPU test box).
+static ml_status p2p_setup(Ctx* c, int n, bool local_only) {
     static const bool disabled = std::getenv("MACHLINE_NO_P2P") != nullptr;
-    if (c->world < 2 || c->world > Ctx::P2P_MAX || disabled) { c->p2p_ok = false; return ML_OK; }
     const size_t need = ((size_t)n + 63) / 64 * 64;
+    if (local_only && c->world == 1) {
+        if (c->p2p_ok && c->win_n >= need) return ML_OK;
+        ML_CUDA(c, cudaStreamSynchronize(c->stream));
+        p2p_teardown(c);
+        ML_CUDA(c, cudaMalloc((void**)&c->win, p2p_window_bytes(need)));
+        ML_CUDA(c, cudaMemset(c->win, 0, p2p_window_bytes(need)));
+        c->peer_base[0] = c->win;
+        c->win_n = need;
+        c->p2p_seq = 0;
+        c->xseq = 0;
+        c->p2p_ok = !disabled;
+        return ML_OK;
+    }
+    if (c->world < 2 || c->world > Ctx::P2P_MAX || disabled) { c->p2p_ok = false; return ML_OK; }
+#ifdef ML_HAVE_NCCL
     if (c->p2p_ok && c->win_n >= need) return ML_OK;
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
     p2p_teardown(c);
@@ -668,10 +689,14 @@ static ml_status p2p_setup(Ctx* c, int n) {
     }
     c->win_n = need;
     c->p2p_seq = 0;
+    c->xseq = 0;
     c->p2p_ok = true;
     return ML_OK;
-}
+#else
+    c->p2p_ok = false;
+    return ML_OK;
 #endif
+}
 
 // y_full[global row of slot s] = gather[s]   (slot = rank * shard_pad + local row; -1 marks padding)
 __global__ void compact_shards_kernel(const double* __restrict__ gather, const int* __restrict__ g_of_slot, int n_slots,
@@ -690,6 +715,7 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
     DevBuf<double> y_part, gather;
     DevBuf<unsigned> tickets;   // per 64-row block: splits finished (gemv_n_partial_kernel)
     int n_split = 1, cols_per_split = 0;
+    bool force_shard = false;   // one rank running the multi-rank code paths (MACHLINE_GMRES_SHARDED=1: the single-GPU test box)
 
     ml_status init() {
         // enough CTAs for >= 4 per SM; splits of at least 256 columns
@@ -702,38 +728,41 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
         ML_CUDA(c, y_part.alloc((size_t)n_split * n_rows_pad));
         ML_CUDA(c, tickets.alloc(row_blocks));
         ML_CUDA(c, cudaMemsetAsync(tickets.p, 0, (size_t)row_blocks * sizeof(unsigned), c->stream));
-        if (c->world > 1) {
-#ifdef ML_HAVE_NCCL
-            ml_status ps = p2p_setup(c, N);
+        if (sharded()) {
+            ml_status ps = p2p_setup(c, N, force_shard);
             if (ps != ML_OK) return ps;
-#endif
             ML_CUDA(c, gather.alloc((size_t)shard_pad * c->world));
         }
         return ML_OK;
     }
-    // y_full[N] = alpha * (alpha_dev ? *alpha_dev : 1) * A x      (x, y_full replicated full-length vectors)
-    ml_status matvec(const double* x, double* y_full, double alpha, const double* alpha_dev) {
+    // dst_loc[local rows] = alpha * (alpha_dev ? *alpha_dev : 1) * A_loc x      (x: replicated full-length vector)
+    ml_status gemv_local(const double* x, double* dst_loc, double alpha, const double* alpha_dev, cudaEvent_t* end_event = nullptr) {
         dim3 grid(n_rows_pad / GEMV_ROWS, n_split);
-        double* dst = (c->world > 1) ? gather.p + (size_t)c->rank * shard_pad : y_full;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
         if (c->profile) {
             ML_CUDA(c, cudaEventCreate(&e0));
             ML_CUDA(c, cudaEventCreate(&e1));
             ML_CUDA(c, cudaEventRecord(e0, c->stream));
         }
-        const bool p2p = c->world > 1 && c->p2p_ok;
         gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p, tickets.p,
-                                                                     n_rows, alpha_dev, alpha, dst);
+                                                                     n_rows, alpha_dev, alpha, dst_loc);
         if (c->profile) {
             ML_CUDA(c, cudaEventRecord(e1, c->stream));
             c->gemv_ev.push_back(e0);
             c->gemv_ev.push_back(e1);
             c->gemv_launches += 1;
             c->gemv_bytes += (long long)8 * n_rows * N;
+            if (end_event) *end_event = e1;
         }
         c->launches += 1;
         ML_CUDA(c, cudaGetLastError());
-        if (p2p) {
+        return ML_OK;
+    }
+    // The exchange step: every rank's local rows (src_loc = gather.p + rank * shard_pad) -> the replicated full vector.
+    // Peer-memory push + wait (p2p), else ncclAllGather + compaction.  e1 = end of the producing kernel (profiling).
+    ml_status exchange(double* y_full, cudaEvent_t e1) {
+        double* src = gather.p + (size_t)c->rank * shard_pad;
+        if (sharded() && c->p2p_ok) {
             c->p2p_seq += 1;
             const unsigned par = c->p2p_seq & 1u;
             P2PArgs pp;
@@ -746,40 +775,42 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
             pp.rank = c->rank;
             pp.n_rows = n_rows;
             pp.g_of_local = c->d_g_of_slot.p + (size_t)c->rank * shard_pad;
-            p2p_push_kernel<<<c->world, 512, 0, c->stream>>>(dst, pp);
+            p2p_push_kernel<<<c->world, 512, 0, c->stream>>>(src, pp);
             c->launches += 1;
             const double* ww = c->win + (size_t)par * c->win_n;
             const unsigned* fl = reinterpret_cast<const unsigned*>(c->win + 2 * c->win_n) + par * Ctx::P2P_MAX;
             p2p_wait_copy_kernel<<<(N + 255) / 256, 256, 0, c->stream>>>(ww, fl, c->p2p_seq, c->world, N, y_full);
             c->launches += 1;
-            if (c->profile) {
-                cudaEvent_t e2 = nullptr;
-                ML_CUDA(c, cudaEventCreate(&e2));
-                ML_CUDA(c, cudaEventRecord(e2, c->stream));
-                c->comm_ev.push_back(e1);
-                c->comm_ev.push_back(e2);
-            }
-            ML_CUDA(c, cudaGetLastError());
-            return ML_OK;
-        }
+        } else {
 #ifdef ML_HAVE_NCCL
-        if (c->world > 1) {
-            ncclResult_t r = ncclAllGather(gather.p + (size_t)c->rank * shard_pad, gather.p, shard_pad, ncclDouble, c->comm, c->stream);
-            if (r != ncclSuccess) return c->fail(ML_NCCL_ERROR, ncclGetErrorString(r));
+            if (c->world > 1) {
+                ncclResult_t r = ncclAllGather(src, gather.p, shard_pad, ncclDouble, c->comm, c->stream);
+                if (r != ncclSuccess) return c->fail(ML_NCCL_ERROR, ncclGetErrorString(r));
+            }
+#endif
             // compact the padded shards into the contiguous full vector: one launch (a memcpy per rank costs ~2.5 us each)
             compact_shards_kernel<<<(shard_pad * c->world + 255) / 256, 256, 0, c->stream>>>(gather.p, c->d_g_of_slot.p, shard_pad * c->world,
                                                                                               y_full);
             c->launches += 1;
-            if (c->profile) {   // exchange step = all-gather + compaction, timed from the end of the local matvec
-                cudaEvent_t e2 = nullptr;
-                ML_CUDA(c, cudaEventCreate(&e2));
-                ML_CUDA(c, cudaEventRecord(e2, c->stream));
-                c->comm_ev.push_back(e1);
-                c->comm_ev.push_back(e2);
-            }
         }
-#endif
+        if (c->profile && e1) {   // exchange step timed from the end of the local kernel
+            cudaEvent_t e2 = nullptr;
+            ML_CUDA(c, cudaEventCreate(&e2));
+            ML_CUDA(c, cudaEventRecord(e2, c->stream));
+            c->comm_ev.push_back(e1);
+            c->comm_ev.push_back(e2);
+        }
+        ML_CUDA(c, cudaGetLastError());
         return ML_OK;
+    }
+    bool sharded() const { return c->world > 1 || force_shard; }
+    // y_full[N] = alpha * (alpha_dev ? *alpha_dev : 1) * A x      (x, y_full replicated full-length vectors)
+    ml_status matvec(const double* x, double* y_full, double alpha, const double* alpha_dev) {
+        if (!sharded()) return gemv_local(x, y_full, alpha, alpha_dev);
+        cudaEvent_t e1 = nullptr;
+        ml_status st = gemv_local(x, gather.p + (size_t)c->rank * shard_pad, alpha, alpha_dev, &e1);
+        if (st != ML_OK) return st;
+        return exchange(y_full, e1);
     }
     void release() {
         y_part.release();
@@ -1045,6 +1076,241 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     return st;
 }
 
+}  // namespace mlgpu
+#include "gmres_sharded.cuh"
+namespace mlgpu {
+
+// local rows of a replicated vector: dst[i] = src[g_of_local[i]]
+__global__ void gather_rows_kernel(const double* __restrict__ src, const int* __restrict__ g_of_local, int n_loc, double* __restrict__ dst) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_loc) dst[i] = src[g_of_local[i]];
+}
+
+// GMRES / restarted GMRES on a row-sharded system with the basis sharded by rows (gmres_sharded.cuh).  Same host pipeline as
+// gmres_device: the Hessenberg column of step k comes back through a pinned slot while later steps are already enqueued; every
+// rank receives bitwise identical columns, takes identical decisions and therefore launches the identical kernel sequence.
+static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d_scale, double tol, int max_iter, int restart_iter,
+                                      bool restarted, double* d_x, int* total_iter_out, const char* iteration_file) {
+    Ctx* c = S.c;
+    const int N = S.N, n_loc = S.n_rows;
+    HistFile hist{open_iteration_file(c, iteration_file, "GMRES", N,
+                                      restarted ? "iteration,outer iteration,inner iteration,||err||" : "iteration,||err||")};
+    int outer_iter = 0;
+    const int k_max = restarted ? std::min(restart_iter, N) : std::min(N, max_iter);
+    if (k_max < 1) return c->fail(ML_BAD_ARGUMENT, "max_iterations < 1");
+    const int hs = k_max + 3;   // slot stride: h[0..k], the error flag
+    const int ldq = S.n_rows_pad;
+    const int nfull = ((N + 63) / 64) * 64;
+    // one CTA per SM at most; every CTA owns a block of >= 32 local rows
+    int grid = std::max(1, std::min(c->num_sms, (n_loc + 31) / 32));
+    const int rows_per_cta = 32 * ((n_loc + 32 * grid - 1) / (32 * grid));
+    grid = std::max(1, (n_loc + rows_per_cta - 1) / rows_per_cta);
+    const int kpad = k_max + 4;
+    DevBuf<double> Q, w, r0, xfull, xloc, ydev, hdev, nrm, part, npart, h1;
+    DevBuf<unsigned> sync;   // [0] ticket, [1] ready
+    DevBuf<int> err;
+#define GS_CUDA(call)                                            \
+    do {                                                         \
+        cudaError_t e__ = (call);                                \
+        if (e__ != cudaSuccess) {                                \
+            cudaStreamSynchronize(c->stream);                    \
+            return c->cuda_fail(e__, #call);                     \
+        }                                                        \
+    } while (0)
+    GS_CUDA(Q.alloc((size_t)ldq * (k_max + 1)));
+    GS_CUDA(w.alloc(ldq));
+    GS_CUDA(r0.alloc(nfull));
+    GS_CUDA(xfull.alloc(nfull));
+    GS_CUDA(xloc.alloc((size_t)S.shard_pad * c->world));
+    GS_CUDA(part.alloc((size_t)grid * kpad));
+    GS_CUDA(npart.alloc(grid));
+    GS_CUDA(h1.alloc(kpad));
+    GS_CUDA(sync.alloc(2));
+    GS_CUDA(err.alloc(1));
+    GS_CUDA(ydev.alloc(k_max + 1));
+    GS_CUDA(nrm.alloc(2));
+    GS_CUDA(cudaMemsetAsync(sync.p, 0, 2 * sizeof(unsigned), c->stream));
+    GS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), c->stream));
+    GS_CUDA(cudaMemsetAsync(Q.p, 0, (size_t)ldq * (k_max + 1) * sizeof(double), c->stream));
+    GS_CUDA(cudaMemsetAsync(w.p, 0, (size_t)ldq * sizeof(double), c->stream));
+    GS_CUDA(cudaMemsetAsync(xloc.p, 0, (size_t)S.shard_pad * c->world * sizeof(double), c->stream));
+    if (!(c->attr_mask & 16u)) {
+        GS_CUDA(cudaFuncSetAttribute(arnoldi_tail_sharded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        c->attr_mask |= 16u;
+    }
+    int depth = 4;
+    if (const char* e = std::getenv("MACHLINE_GMRES_LOOKAHEAD")) depth = std::max(1, std::min(8, std::atoi(e)));
+    const int n_slots = depth + 1;
+    GS_CUDA(hdev.alloc((size_t)n_slots * hs));
+    if (c->h_pinned_n < (size_t)n_slots * hs) {
+        if (c->h_pinned) cudaFreeHost(c->h_pinned);
+        c->h_pinned = nullptr;
+        c->h_pinned_n = 0;
+        GS_CUDA(cudaHostAlloc((void**)&c->h_pinned, (size_t)n_slots * hs * sizeof(double), cudaHostAllocDefault));
+        c->h_pinned_n = (size_t)n_slots * hs;
+    }
+    for (int i = 0; i < n_slots; ++i)
+        if (!c->slot_ev[i]) GS_CUDA(cudaEventCreateWithFlags(&c->slot_ev[i], cudaEventDisableTiming));
+    const int* g_of_local = c->d_g_of_slot.p + (size_t)c->rank * S.shard_pad;
+
+    const int ldh = k_max + 1;
+    std::vector<double> H((size_t)ldh * k_max, 0.), cs(k_max, 0.), sn(k_max, 0.), E(std::max(N, k_max + 1) + 1, 0.);
+    GS_CUDA(cudaMemsetAsync(d_x, 0, (size_t)N * sizeof(double), c->stream));
+    int total_iter = 0;
+    double err_est = tol + 1;
+    const int nb256 = (N + 255) / 256;
+    ml_status st = ML_OK;
+    unsigned launches_done = 0;
+
+    auto enqueue = [&](int kk) -> ml_status {   // Arnoldi step kk (0-based): w_loc = A_loc q_kk, then the sharded tail
+        const int k = kk + 1, slot = kk % n_slots;
+        double* hfin = hdev.p + (size_t)slot * hs;
+        cudaEvent_t e1 = nullptr;
+        ml_status s = S.gemv_local(xfull.p, w.p, 1.0, d_scale, &e1);
+        if (s != ML_OK) return s;
+        ShTailArgs a{};
+        a.Q = Q.p; a.ldq = ldq; a.n_loc = n_loc; a.k = k;
+        a.w = w.p; a.partial = part.p; a.kpad = kpad; a.h1 = h1.p; a.hfin = hfin; a.npart = npart.p;
+        a.qnext = Q.p + (size_t)k * ldq; a.xfull = xfull.p; a.N = N; a.g_of_local = g_of_local;
+        a.P = c->world; a.rank = c->rank; a.kr = Ctx::P2P_KR; a.nv = (int)c->win_n;
+        for (int r = 0; r < Ctx::P2P_MAX; ++r) {
+            double* base = reinterpret_cast<double*>(c->peer_base[r < c->world ? r : c->rank]);
+            a.flags[r] = reinterpret_cast<unsigned*>(base + 2 * c->win_n + 8);
+            a.vec[r] = base + 2 * c->win_n + 16;
+            a.red[r] = base + 4 * c->win_n + 16;
+        }
+        a.seq = c->xseq + 1;
+        c->xseq += 3;
+        a.ticket = sync.p; a.ready = sync.p + 1; a.base = launches_done++;
+        a.err = err.p; a.rows_per_cta = rows_per_cta;
+        void* kargs[] = {(void*)&a};
+        const size_t smem = (size_t)(2 * ((k + 3) & ~1) + 1024) * sizeof(double);
+        cudaError_t e = cudaLaunchCooperativeKernel((const void*)arnoldi_tail_sharded_kernel, dim3(grid), dim3(SHT_THREADS), kargs, smem, c->stream);
+        if (e != cudaSuccess) return c->cuda_fail(e, "arnoldi_tail_sharded_kernel");
+        c->launches += 1;
+        if (c->profile && e1) {   // the exchanges live inside the tail: "exchange" = the whole tail, from the end of the local matvec
+            cudaEvent_t e2 = nullptr;
+            if (cudaEventCreate(&e2) == cudaSuccess && cudaEventRecord(e2, c->stream) == cudaSuccess) {
+                c->comm_ev.push_back(e1);
+                c->comm_ev.push_back(e2);
+            }
+        }
+        e = cudaMemcpyAsync(c->h_pinned + (size_t)slot * hs, hfin, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(c->slot_ev[slot], c->stream);
+        if (e != cudaSuccess) return c->cuda_fail(e, "gmres enqueue");
+        c->d2h_bytes += (long long)(k + 2) * sizeof(double);
+        return ML_OK;
+    };
+
+    bool first_cycle = true;
+    while (err_est > tol && (restarted ? total_iter <= max_iter : first_cycle)) {
+        first_cycle = false;
+        outer_iter += 1;
+        std::fill(H.begin(), H.end(), 0.);
+        std::fill(cs.begin(), cs.end(), 0.);
+        std::fill(sn.begin(), sn.end(), 0.);
+        std::fill(E.begin(), E.end(), 0.);
+        E[0] = 1.;
+        // r0 = scale*b - (scale*A) x on the replicated vectors (x = 0 in the first cycle)
+        scale_copy_kernel<<<nb256, 256, 0, c->stream>>>(d_b, 1.0, d_scale, r0.p, N);
+        c->launches += 1;
+        if (restarted && total_iter > 0) {
+            st = S.matvec(d_x, xfull.p, 1.0, d_scale);
+            if (st != ML_OK) break;
+            axpby_kernel<<<nb256, 256, 0, c->stream>>>(1.0, r0.p, -1.0, xfull.p, r0.p, N);
+            c->launches += 1;
+        }
+        norm_scale_kernel<<<1, 1024, 0, c->stream>>>(r0.p, N, nrm.p, xfull.p);  // beta, q_1 = r0/beta (replicated)
+        gather_rows_kernel<<<(n_loc + 255) / 256, 256, 0, c->stream>>>(xfull.p, g_of_local, n_loc, Q.p);
+        c->launches += 2;
+        double beta = 0.;
+        GS_CUDA(cudaMemcpyAsync(&beta, nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        GS_CUDA(cudaStreamSynchronize(c->stream));
+        if (!(beta == beta)) {
+            st = ML_NAN_IN_SYSTEM;
+            break;
+        }
+        int k = 0;
+        const int k_last = k_max - 1;
+        int next_enq = 0;
+        auto fill = [&](int upto) -> ml_status {
+            while (next_enq <= upto && next_enq < k_last) {
+                ml_status s = enqueue(next_enq);
+                if (s != ML_OK) return s;
+                ++next_enq;
+            }
+            return ML_OK;
+        };
+        if (err_est > tol) st = fill(depth - 1);
+        if (st != ML_OK) break;
+        while (err_est > tol && k < k_last && k < next_enq) {
+            k += 1;
+            total_iter += 1;
+            const int kk = k - 1, slot = kk % n_slots;
+            st = fill(kk + depth);
+            if (st != ML_OK) break;
+            GS_CUDA(cudaEventSynchronize(c->slot_ev[slot]));
+            const double* hcol = c->h_pinned + (size_t)slot * hs;
+            if (hcol[k + 1] != 0.) {
+                st = c->fail(ML_NCCL_ERROR, "sharded GMRES: a peer did not answer within the spin limit");
+                break;
+            }
+            for (int i = 0; i <= k; ++i) H[i + (size_t)kk * ldh] = hcol[i];
+            for (int i = 0; i < kk; ++i) {   // Givens updates, linalg.f90:1293-1313
+                double temp = cs[i] * H[i + (size_t)kk * ldh] + sn[i] * H[(i + 1) + (size_t)kk * ldh];
+                H[(i + 1) + (size_t)kk * ldh] = -sn[i] * H[i + (size_t)kk * ldh] + cs[i] * H[(i + 1) + (size_t)kk * ldh];
+                H[i + (size_t)kk * ldh] = temp;
+            }
+            const double hkk = H[kk + (size_t)kk * ldh], hk1 = H[(kk + 1) + (size_t)kk * ldh];
+            const double d = std::sqrt(hkk * hkk + hk1 * hk1);
+            cs[kk] = std::fabs(hkk) / d;
+            sn[kk] = fsign(1., hkk) * hk1 / d;
+            H[kk + (size_t)kk * ldh] = cs[kk] * hkk + sn[kk] * hk1;
+            H[(kk + 1) + (size_t)kk * ldh] = 0.;
+            E[kk + 1] = -sn[kk] * E[kk];
+            E[kk] = cs[kk] * E[kk];
+            err_est = beta * std::fabs(E[kk + 1]);
+            if (hist.f) {
+                if (restarted) std::fprintf(hist.f, "%6d,%6d,%6d,%10.3E\n", total_iter, outer_iter, k, err_est);
+                else std::fprintf(hist.f, "%6d,%10.3E\n", k, err_est);
+            }
+            if (!restarted && err_est < tol) break;
+        }
+        if (st != ML_OK) break;
+        GS_CUDA(cudaStreamSynchronize(c->stream));  // drain the speculative steps
+        if (k == 0) break;
+        std::vector<double> y(k);
+        bool singular = false;
+        for (int i = k - 1; i >= 0; --i) {   // linalg.f90:930-965
+            double v = beta * E[i];
+            for (int j = i + 1; j < k; ++j) v = v - H[i + (size_t)j * ldh] * y[j];
+            if (H[i + (size_t)i * ldh] == 0.) {
+                singular = true;
+                break;
+            }
+            y[i] = v / H[i + (size_t)i * ldh];
+        }
+        if (singular) {
+            st = c->fail(ML_SINGULAR, "Zero found on the diagonal of R (linalg.f90:956-961)");
+            break;
+        }
+        // x (+)= Q y: local rows, then the exchange of the local parts (xloc doubles as the gather buffer layout)
+        GS_CUDA(cudaMemcpyAsync(ydev.p, y.data(), (size_t)k * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        gemv_n_small_kernel<<<(n_loc + 63) / 64, 64, 0, c->stream>>>(Q.p, ldq, n_loc, k, ydev.p, S.gather.p + (size_t)c->rank * S.shard_pad, 0);
+        c->launches += 1;
+        st = S.exchange(xfull.p, nullptr);
+        if (st != ML_OK) break;
+        if (restarted) axpby_kernel<<<nb256, 256, 0, c->stream>>>(1.0, d_x, 1.0, xfull.p, d_x, N);
+        else axpby_kernel<<<nb256, 256, 0, c->stream>>>(1.0, xfull.p, 0.0, xfull.p, d_x, N);
+        c->launches += 1;
+        GS_CUDA(cudaStreamSynchronize(c->stream));
+    }
+    cudaStreamSynchronize(c->stream);
+    *total_iter_out = total_iter;
+#undef GS_CUDA
+    return st;
+}
+
 ml_status lu_solve_device(Ctx* c, int N, double* dA, int ld, const double* d_b, double* d_x);  // lu_kernels.cu
 ml_status lu_solve_sharded(Ctx* c, int N, double* dAloc, int ld, int n_rows, int n_rows_pad, int S, const double* d_b,
                            double* d_x);                                                      // lu_kernels.cu
@@ -1109,14 +1375,21 @@ static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_
             st = purcell_solve_device(c, S.N, lu_matrix, lu_ld, d_b, d_scale, d_x);
             break;
         case ML_SOLVER_RGMRES:
-            st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, true, use_mgs, d_x, &iters,
-                              opts->iteration_file);
-            break;
         case ML_SOLVER_GMRES:
-        default:  // invalid names fall back to GMRES (panel_solver.f90:1969-1973)
-            st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, false, use_mgs, d_x, &iters,
-                              opts->iteration_file);
+        default: {  // invalid names fall back to GMRES (panel_solver.f90:1969-1973)
+            const bool restarted = opts->matrix_solver == ML_SOLVER_RGMRES;
+            const int k_max = restarted ? std::min(opts->restart_iterations, S.N) : std::min(S.N, opts->max_iterations);
+            // row-sharded basis + peer-memory reductions when the windows are mapped; else the replicated basis (NCCL all-gather)
+            const bool shard_basis = S.sharded() && c->p2p_ok && !use_mgs && k_max + 3 <= Ctx::P2P_KR &&
+                                     std::getenv("MACHLINE_GMRES_REPLICATED") == nullptr;
+            if (shard_basis)
+                st = gmres_sharded_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, restarted, d_x, &iters,
+                                          opts->iteration_file);
+            else
+                st = gmres_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, restarted, use_mgs, d_x, &iters,
+                                  opts->iteration_file);
             break;
+        }
     }
     if (st != ML_OK) return st;
     if (info) info->iterations = iters;
@@ -1162,6 +1435,12 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
     S.n_rows = c->n_rows;
     S.n_rows_pad = c->n_rows_pad;
     S.N = N;
+    {   // one rank running the multi-rank Krylov code paths (peer-memory exchange, sharded basis): the single-GPU test box
+        const int ms = opts->matrix_solver;
+        const bool krylov = !(ms == ML_SOLVER_LU || ms == ML_SOLVER_BJAC || ms == ML_SOLVER_BSSOR || ms == ML_SOLVER_QRUP || ms == ML_SOLVER_FQRUP ||
+                              ms == ML_SOLVER_PURC);
+        S.force_shard = c->world == 1 && krylov && std::getenv("MACHLINE_GMRES_SHARDED") != nullptr;
+    }
     // Slot tables of the all-gather layout: slot = rank * shard_pad + local row <-> global row.  Every rank contributes the
     // list of rows it assembled, so any dealing of rows to ranks (contiguous blocks, block-cyclic) works the same way.
     {

@@ -1,0 +1,82 @@
+"""Worker of tests/test_gpu_sharded_gmres.py: GMRES and restarted GMRES through ml_solve on a row-sharded system, one rank per
+GPU (torchrun), or ONE rank with MACHLINE_GMRES_SHARDED=1 (the multi-rank kernels -- peer-memory exchange, row-sharded Krylov
+basis with the reductions fused into the Arnoldi tail -- with every "peer" being the rank itself).
+
+usage: mp_gmres_worker.py <NCxNS | study case name>
+env:   MACHLINE_TEST_CYCLIC=<block>   block-cyclic dealing of the rows instead of contiguous blocks
+       MACHLINE_NO_P2P=1              no peer windows: ncclAllGather + compaction, replicated basis
+       MACHLINE_GMRES_REPLICATED=1    peer-memory exchange of the Krylov vector, replicated basis
+Checked against the oracle on the same tables: x (1e-9 of max|x|), the iteration count (+-1), the residual."""
+import os
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import fixtures  # noqa: E402
+import oracle_binding as ob  # noqa: E402
+from machline_b200 import _abi, gpu, host, meshgen, shard  # noqa: E402
+
+rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+local = int(os.environ.get("LOCAL_RANK", rank))
+what = sys.argv[1] if len(sys.argv) > 1 else "24x12"
+if world > 1:
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+if "x" in what and what.split("x")[0].isdigit():
+    nc, ns = (int(v) for v in what.split("x"))
+    tmp = tempfile.mkdtemp(prefix=f"machline_gmres_r{rank}_")
+    pts, tris = meshgen.swept_wing_half(nc, ns)
+    meshgen.write_vtk(f"{tmp}/w.vtk", pts, tris)
+    case = host.Case(meshgen.wing_input("w.vtk", mach=0.5, matrix_solver="GMRES"), base_dir=tmp)
+else:
+    case = fixtures.study_case(what)
+N = case.n_cp
+ctx = gpu.Context(local)
+if world > 1:
+    uid = torch.zeros(128, dtype=torch.uint8, device=f"cuda:{local}")
+    if rank == 0:
+        uid.copy_(torch.frombuffer(bytearray(gpu.nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(uid, src=0)
+    ctx.set_communicator(bytes(uid.cpu().numpy().tobytes()), rank, world)
+cyclic_block = int(os.environ.get("MACHLINE_TEST_CYCLIC", "0"))
+if cyclic_block > 0:
+    ctx.set_case(case, cyclic=(cyclic_block, rank, world))
+else:
+    row0, nrows = shard.row_shard(N, rank, world)
+    ctx.set_case(case, row0=row0, nrows=nrows)
+ctx.assemble()
+BC = np.array(case.BC)
+A_ref, I_ref = ob.assemble(case)
+report = []
+for solver in ("GMRES", "RGMRES"):
+    opts = case.solver_opts()
+    opts.matrix_solver = _abi.SOLVERS[solver]
+    if solver == "RGMRES":
+        opts.max_iterations = 4000
+    x_ref, info_ref = ob.solve_system(A_ref, I_ref, BC, opts)
+    for rep in range(2):     # twice: the windows, sequence numbers and flags persist across solves
+        x, info = ctx.solve(opts, BC)
+        err = np.abs(x - x_ref).max() / np.abs(x_ref).max()
+        tol_it = 1 if solver == "GMRES" else max(2, info_ref.iterations // 20)   # restarts amplify a one-step difference
+        assert abs(info.iterations - info_ref.iterations) <= tol_it, f"rank {rank} {solver}: iterations {info.iterations} vs oracle {info_ref.iterations}"
+        assert err < 1e-9, f"rank {rank} {solver}: |dx|/|x| = {err:.2e}"
+        assert info.res_norm < 1e-10, info.res_norm
+    report.append(f"{solver} it {info.iterations}/{info_ref.iterations} err {err:.1e} {info.solve_ms:.1f} ms")
+if world > 1:   # every rank must hold the same x bit for bit (identical Hessenberg columns on every rank)
+    xs = [None] * world
+    dist.all_gather_object(xs, x.tobytes())
+    assert all(b == xs[0] for b in xs), "ranks disagree on x"
+print(f"rank {rank}/{world}: N={N} rows {ctx.nrows} ({'cyclic ' + str(cyclic_block) if cyclic_block else 'contiguous'}) " + "; ".join(report) + " OK", flush=True)
+ctx.close()
+if world > 1:
+    dist.barrier()
+    dist.destroy_process_group()
