@@ -92,15 +92,18 @@ def build_gpu(force: bool = False) -> Path:
     if force or _newer(GPU_LIB, deps):
         objdir = gdir / "build"
         objdir.mkdir(exist_ok=True)
-        objs = []
-        logs = []
-        for s in srcs:
-            o = objdir / (s.stem + ".o")
-            if force or _newer(o, deps):
-                extra = PER_FILE_FLAGS.get(s.name, [])
-                res = _run([NVCC, *gpu_compile_flags(), *extra, "-ccbin", GXX, "-c", s, "-o", o])
-                logs.append(f"== {s.name}\n{res.stderr}")
-            objs.append(o)
+        objs = [objdir / (s.stem + ".o") for s in srcs]
+        todo = [(s, o) for s, o in zip(srcs, objs) if force or _newer(o, deps)]
+
+        def compile_one(so):
+            s, o = so
+            extra = PER_FILE_FLAGS.get(s.name, [])
+            res = _run([NVCC, *gpu_compile_flags(), *extra, "-ccbin", GXX, "-c", s, "-o", o])
+            return f"== {s.name}\n{res.stderr}"
+
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(8, max(1, len(todo)))) as pool:   # one nvcc per translation unit
+            logs = list(pool.map(compile_one, todo))
         (objdir / "ptxas.log").write_text("\n".join(logs))
         link = [NVCC, *NVCC_ARCH, "-shared", "-ccbin", GXX, "-o", GPU_LIB, *objs, "-lcudart_static"]
         _, lib = _nccl_dirs()

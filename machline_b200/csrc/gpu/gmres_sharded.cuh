@@ -27,13 +27,14 @@ namespace mlgpu {
 constexpr int SHT_THREADS = 1024;
 constexpr int SHT_WARPS = SHT_THREADS / 32;
 constexpr long long SHT_SPIN_LIMIT = 8000000000LL;   // clock64 ticks (~4 s)
+constexpr int SHT_MAXCH = 4;                          // a CTA owns at most 32 * SHT_MAXCH rows
 
 struct ShTailArgs {
     const double* Q;        // local rows of the basis, column-major, leading dimension ldq
     int ldq, n_loc, k;      // k = basis vectors to orthogonalise against
     double* w;              // [ldq] local rows of A q (in), orthogonalised (out)
-    double* partial;        // [grid][kpad]
-    int kpad;
+    double* partial;        // [k][gpad]: partial[j * gpad + cta], so that the reducing warp reads one column's partials coalesced
+    int gpad;
     double* h1;             // [k] coefficients of the pass being applied (global scratch)
     double* hfin;           // [k + 2]: h1 + h2, the norm, and the error flag (as a double) for the host
     double* npart;          // [grid]
@@ -53,6 +54,7 @@ struct ShTailArgs {
     unsigned base;          // launches of this solve before this one
     int* err;               // raised when a spin loop gives up
     int rows_per_cta;       // multiple of 32
+    long long* dbg;         // nullptr, or [2][16] clock64 stamps (CTA 0 / the CTA that was last at stage 0) -- MACHLINE_SHT_DEBUG
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
@@ -78,57 +80,85 @@ __device__ __forceinline__ double ld_peer(const double* p) {
     return v;
 }
 
-// Partial dots of this CTA's rows: partial[blockIdx.x][j] = sum_{i in rows} Q[i, j] * w[i], fixed order.
-__device__ __forceinline__ void sht_dot_phase(const ShTailArgs& a, int row0, int nrows) {
+// Partial dots of this CTA's rows: partial[j][blockIdx.x] = sum_{i in rows} Q[i, j] * w[i], fixed order.  A warp takes four
+// columns per trip and issues all their loads before the first use (the phase is a chain of L2 round trips otherwise).
+template <int NCOL, int NCH>
+__device__ __forceinline__ void sht_dot_phase_t(const ShTailArgs& a, int row0, int nrows, const double* s_w) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double* out = a.partial + (size_t)blockIdx.x * a.kpad;
-    for (int j = warp; j < a.k; j += SHT_WARPS) {
-        const double* q = a.Q + (size_t)j * a.ldq + row0;
-        double acc = 0.;
-        for (int i = lane; i < nrows; i += 32) acc = fma(q[i], __ldcg(a.w + row0 + i), acc);
+    double* out = a.partial + blockIdx.x;
+    double wv[NCH];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) __stcg(out + j, acc);
+    for (int c = 0; c < NCH; ++c) wv[c] = (lane + 32 * c < nrows) ? s_w[lane + 32 * c] : 0.;
+    for (int j0 = warp * NCOL; j0 < a.k; j0 += SHT_WARPS * NCOL) {
+        double qv[NCOL][NCH];
+#pragma unroll
+        for (int u = 0; u < NCOL; ++u) {
+            const double* q = a.Q + (size_t)min(j0 + u, a.k - 1) * a.ldq + row0 + lane;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) qv[u][c] = (lane + 32 * c < nrows) ? q[32 * c] : 0.;
+        }
+#pragma unroll
+        for (int u = 0; u < NCOL; ++u) {
+            double acc = 0.;
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) acc = fma(qv[u][c], wv[c], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0 && j0 + u < a.k) __stcg(out + (size_t)(j0 + u) * a.gpad, acc);
+        }
     }
+}
+__device__ __forceinline__ void sht_dot_phase(const ShTailArgs& a, int row0, int nrows, const double* s_w) {
+    if (a.rows_per_cta <= 32) sht_dot_phase_t<8, 1>(a, row0, nrows, s_w);
+    else if (a.rows_per_cta <= 64) sht_dot_phase_t<8, 2>(a, row0, nrows, s_w);
+    else sht_dot_phase_t<4, SHT_MAXCH>(a, row0, nrows, s_w);
 }
 
 // w[rows] -= Q[rows, 0..k-1] h; returns the sum of squares of the new w over the CTA's rows (thread 0), fixed order.
+// The 32 warps split the columns; a lane owns rows lane, lane + 32, ... (at most SHT_MAXCH of them: rows_per_cta <= 32 SHT_MAXCH),
+// so all loads of a thread are independent and one shared-memory reduction over the warps finishes the block.
 __device__ __forceinline__ double sht_sub_phase(const ShTailArgs& a, int row0, int nrows, const double* s_h, double* s_acc,
-                                                bool want_norm) {
+                                                double* s_w, bool want_norm) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double sq_total = 0.;
-    for (int r0 = 0; r0 < nrows; r0 += 32) {              // 32 rows at a time, the 32 warps split the columns
-        const int i = r0 + lane;
-        double acc = 0.;
-        if (i < nrows) {
-            const double* q = a.Q + row0 + i;
-            double a0 = 0., a1 = 0.;
-            int j = warp;
-            for (; j + SHT_WARPS < a.k; j += 2 * SHT_WARPS) {
-                a0 = fma(q[(size_t)j * a.ldq], s_h[j], a0);
-                a1 = fma(q[(size_t)(j + SHT_WARPS) * a.ldq], s_h[j + SHT_WARPS], a1);
-            }
-            if (j < a.k) a0 = fma(q[(size_t)j * a.ldq], s_h[j], a0);
-            acc = a0 + a1;
-        }
-        s_acc[warp * 32 + lane] = acc;
-        __syncthreads();
-        if (warp == 0) {
-            double s = 0.;
-#pragma unroll 8
-            for (int c = 0; c < SHT_WARPS; ++c) s += s_acc[c * 32 + lane];
-            double v = 0.;
-            if (i < nrows) {
-                v = __ldcg(a.w + row0 + i) - s;
-                __stcg(a.w + row0 + i, v);
-            }
-            if (want_norm) {
-                double sq = v * v;
+    double acc[SHT_MAXCH];
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-                sq_total += sq;
-            }
+    for (int c = 0; c < SHT_MAXCH; ++c) acc[c] = 0.;
+    const double* q0 = a.Q + row0 + lane;
+    for (int j = warp; j < a.k; j += SHT_WARPS) {
+        const double hj = s_h[j];
+        const double* q = q0 + (size_t)j * a.ldq;
+#pragma unroll
+        for (int c = 0; c < SHT_MAXCH; ++c)
+            if (lane + 32 * c < nrows) acc[c] = fma(q[32 * c], hj, acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < SHT_MAXCH; ++c) s_acc[(c * SHT_WARPS + warp) * 32 + lane] = acc[c];
+    __syncthreads();
+    double sq = 0.;
+    if (warp < SHT_MAXCH) {                 // warp c finishes row chunk c
+        const int i = warp * 32 + lane;
+        double s = 0.;
+#pragma unroll 8
+        for (int w2 = 0; w2 < SHT_WARPS; ++w2) s += s_acc[(warp * SHT_WARPS + w2) * 32 + lane];
+        double v = 0.;
+        if (i < nrows) {
+            v = s_w[i] - s;
+            s_w[i] = v;
+            __stcg(a.w + row0 + i, v);
         }
+        if (want_norm) {
+            sq = v * v;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        }
+    }
+    __syncthreads();
+    double sq_total = 0.;
+    if (want_norm) {
+        if (warp < SHT_MAXCH && lane == 0) s_acc[warp] = sq;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            for (int c = 0; c < SHT_MAXCH; ++c) sq_total += s_acc[c];
         __syncthreads();
     }
     return sq_total;   // meaningful in thread 0
@@ -161,21 +191,22 @@ __device__ __forceinline__ void sht_wait_ready(const ShTailArgs& a, int stage) {
     __syncthreads();
 }
 __device__ __forceinline__ void sht_publish(const ShTailArgs& a, int stage) {
-    __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) st_release_gpu(a.ready, a.base * 3u + (unsigned)stage + 1u);
 }
 
 // LAST CTA: s_vals[0..n) (shared memory, this rank's contribution) -> the reduction slots of exchange `e` in every rank's
-// window; flags; wait for the P flags of the own window; sum over ranks in rank order -> s_out[0..n) (shared memory).
-__device__ __forceinline__ void sht_exchange(const ShTailArgs& a, unsigned e, const double* s_vals, int n, double* s_out) {
+// window; one system-scope fence (cumulative over the CTA's stores through the barrier before it); flags; wait for the P flags
+// of the own window.  Afterwards the P contributions sit in this rank's window: sht_rank_sum adds them in rank order.
+__device__ __forceinline__ void sht_exchange(const ShTailArgs& a, unsigned e, const double* s_vals, int n) {
     const size_t roff = (size_t)(e & 1u) * Ctx::P2P_MAX * a.kr, foff = (size_t)(e & 1u) * Ctx::P2P_MAX;
     for (int p = 0; p < a.P; ++p) {
         double* dst = a.red[p] + roff + (size_t)a.rank * a.kr;
         for (int j = threadIdx.x; j < n; j += SHT_THREADS) dst[j] = s_vals[j];
     }
-    __threadfence_system();
     __syncthreads();
+    // st.release.sys is cumulative over everything that happens-before it: the CTA's own stores through the barrier above, and
+    // the other CTAs' stores to the peers' vector windows through their arrival at the ticket (fence + atomic, gpu scope)
     if ((int)threadIdx.x < a.P) {
         st_release_sys(a.flags[threadIdx.x] + foff + a.rank, e);
         const unsigned* f = a.flags[a.rank] + foff + threadIdx.x;
@@ -188,10 +219,17 @@ __device__ __forceinline__ void sht_exchange(const ShTailArgs& a, unsigned e, co
         }
     }
     __syncthreads();
-    const double* mine = a.red[a.rank] + roff;
+}
+// s_out[j] = sum over ranks (rank order) of the contributions of exchange e, j = 0..n-1: identical bits on every rank and CTA
+__device__ __forceinline__ void sht_rank_sum(const ShTailArgs& a, unsigned e, int n, double* s_out) {
+    const double* mine = a.red[a.rank] + (size_t)(e & 1u) * Ctx::P2P_MAX * a.kr;
     for (int j = threadIdx.x; j < n; j += SHT_THREADS) {
+        double v[Ctx::P2P_MAX];
+#pragma unroll
+        for (int r = 0; r < Ctx::P2P_MAX; ++r) v[r] = (r < a.P) ? ld_peer(mine + (size_t)r * a.kr + j) : 0.;
         double s = 0.;
-        for (int r = 0; r < a.P; ++r) s += ld_peer(mine + (size_t)r * a.kr + j);
+#pragma unroll
+        for (int r = 0; r < Ctx::P2P_MAX; ++r) s += v[r];
         s_out[j] = s;
     }
     __syncthreads();
@@ -202,51 +240,85 @@ __global__ void __launch_bounds__(SHT_THREADS, 1) arnoldi_tail_sharded_kernel(co
     const int kk = (a.k + 3) & ~1;
     double* s_h = s_mem;                 // [kk] coefficients being applied / this rank's contribution
     double* s_out = s_mem + kk;          // [kk] reduced over ranks
-    double* s_acc = s_mem + 2 * kk;      // [1024]
+    double* s_acc = s_mem + 2 * kk;      // [SHT_MAXCH][32 warps][32 lanes]
+    double* s_w = s_acc + SHT_MAXCH * SHT_THREADS;   // [rows_per_cta] this CTA's rows of w
     __shared__ int s_flag;
     __shared__ double s_norm;
     const int row0 = blockIdx.x * a.rows_per_cta;
     const int nrows = max(0, min(a.rows_per_cta, a.n_loc - row0));
     const unsigned G = gridDim.x;
+    for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) s_w[i] = a.w[row0 + i];
+    __syncthreads();
+    int stamp_n = 0;
+    long long stamps[16];
+#define SHT_STAMP() do { if (a.dbg && stamp_n < 16) stamps[stamp_n++] = clock64(); } while (0)
+    SHT_STAMP();
+    bool was_last0 = false;
 
     for (int pass = 0; pass < 2; ++pass) {
         // ---- D: partial dots of this CTA's rows ----
-        sht_dot_phase(a, row0, nrows);
-        if (sht_arrive_is_last(a, pass, &s_flag)) {
-            // ---- R: this rank's coefficients = sum of the CTA partials in CTA order; exchange; sum over ranks ----
-            for (int j = threadIdx.x; j < a.k; j += SHT_THREADS) {
-                double s = 0.;
-                for (unsigned c = 0; c < G; ++c) s += __ldcg(a.partial + (size_t)c * a.kpad + j);
-                s_h[j] = s;
+        sht_dot_phase(a, row0, nrows, s_w);
+        SHT_STAMP();
+        const bool last = sht_arrive_is_last(a, pass, &s_flag);
+        SHT_STAMP();
+        if (pass == 0) was_last0 = last;
+        if (last) {
+            // ---- R: this rank's coefficients = sum of the CTA partials (a warp per column, lanes over the CTAs: lane l adds
+            // CTAs l, l + 32, ... in that order, then a fixed shuffle tree; four columns in flight per warp) ----
+            const int lane = threadIdx.x & 31;
+            for (int j0 = (threadIdx.x >> 5) * 4; j0 < a.k; j0 += SHT_WARPS * 4) {
+                double pv[4][5];   // grid <= 160 CTAs (one per SM): five per lane
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double* pj = a.partial + (size_t)min(j0 + u, a.k - 1) * a.gpad + lane;
+#pragma unroll
+                    for (int m = 0; m < 5; ++m) pv[u][m] = (lane + 32 * m < (int)G) ? __ldcg(pj + 32 * m) : 0.;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    double sv = 0.;
+#pragma unroll
+                    for (int m = 0; m < 5; ++m) sv += pv[u][m];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+                    if (lane == 0 && j0 + u < a.k) s_h[j0 + u] = sv;
+                }
             }
             __syncthreads();
-            sht_exchange(a, a.seq + (unsigned)pass, s_h, a.k, s_out);
-            for (int j = threadIdx.x; j < a.k; j += SHT_THREADS) {
-                const double h = s_out[j];
-                if (pass == 1) __stcg(a.hfin + j, __ldcg(a.h1 + j) + h);
-                __stcg(a.h1 + j, h);     // the coefficients the S phase of this pass applies
-            }
+            SHT_STAMP();
+            sht_exchange(a, a.seq + (unsigned)pass, s_h, a.k);
+            SHT_STAMP();
             sht_publish(a, pass);
         } else {
             sht_wait_ready(a, pass);
         }
+        SHT_STAMP();
+        // every CTA adds the P contributions itself (rank order): the coefficients this pass applies
+        sht_rank_sum(a, a.seq + (unsigned)pass, a.k, s_h);
+        if (last) {   // the Hessenberg column for the host, off the critical path of the other CTAs
+            for (int j = threadIdx.x; j < a.k; j += SHT_THREADS) {
+                if (pass == 0) __stcg(a.h1 + j, s_h[j]);
+                else __stcg(a.hfin + j, __ldcg(a.h1 + j) + s_h[j]);
+            }
+        }
+        SHT_STAMP();
         // ---- S: subtract on this CTA's rows ----
-        for (int j = threadIdx.x; j < a.k; j += SHT_THREADS) s_h[j] = __ldcg(a.h1 + j);
-        __syncthreads();
-        const double sq = sht_sub_phase(a, row0, nrows, s_h, s_acc, pass == 1);
+        const double sq = sht_sub_phase(a, row0, nrows, s_h, s_acc, s_w, pass == 1);
+        SHT_STAMP();
         if (pass == 1) {
             if (threadIdx.x == 0) __stcg(a.npart + blockIdx.x, sq);
             // the all-gather of the next Krylov vector, fused: this CTA's rows go to every rank's window at their global index
             const size_t voff = (size_t)((a.seq + 2u) & 1u) * a.nv;
             for (int p = 0; p < a.P; ++p) {
                 double* dst = a.vec[p] + voff;
-                for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) dst[a.g_of_local[row0 + i]] = __ldcg(a.w + row0 + i);
+                for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) dst[a.g_of_local[row0 + i]] = s_w[i];
             }
-            __threadfence_system();
+            // (made visible to the peers by the flag release of the last CTA: see sht_exchange)
         }
     }
     // ---- R3: the norm ----
-    if (sht_arrive_is_last(a, 2, &s_flag)) {
+    const bool last3 = sht_arrive_is_last(a, 2, &s_flag);
+    if (last3) {
         if (threadIdx.x < 32) {
             double t = 0.;
             for (unsigned c = threadIdx.x; c < G; c += 32) t += __ldcg(a.npart + c);
@@ -255,22 +327,31 @@ __global__ void __launch_bounds__(SHT_THREADS, 1) arnoldi_tail_sharded_kernel(co
             if (threadIdx.x == 0) s_h[0] = t;
         }
         __syncthreads();
-        sht_exchange(a, a.seq + 2u, s_h, 1, s_out);
-        if (threadIdx.x == 0) {
-            __stcg(a.hfin + a.k, sqrt(s_out[0]));
-            __stcg(a.hfin + a.k + 1, (double)(*reinterpret_cast<volatile int*>(a.err)));
-        }
+        sht_exchange(a, a.seq + 2u, s_h, 1);
         sht_publish(a, 2);
     } else {
         sht_wait_ready(a, 2);
     }
-    if (threadIdx.x == 0) s_norm = __ldcg(a.hfin + a.k);
+    sht_rank_sum(a, a.seq + 2u, 1, s_out);
+    if (threadIdx.x == 0) {
+        s_norm = sqrt(s_out[0]);
+        if (last3) {
+            __stcg(a.hfin + a.k, s_norm);
+            __stcg(a.hfin + a.k + 1, (double)(*reinterpret_cast<volatile int*>(a.err)));
+        }
+    }
     __syncthreads();
     const double nrm = s_norm;
     // ---- F: the new basis vector (local rows) and the operand of the next matvec (all rows, from the window) ----
-    for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) a.qnext[row0 + i] = __ldcg(a.w + row0 + i) / nrm;
+    for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) a.qnext[row0 + i] = s_w[i] / nrm;
     const double* mine = a.vec[a.rank] + (size_t)((a.seq + 2u) & 1u) * a.nv;
     for (int g = blockIdx.x * SHT_THREADS + threadIdx.x; g < a.N; g += G * SHT_THREADS) a.xfull[g] = ld_peer(mine + g) / nrm;
+    SHT_STAMP();
+    if (a.dbg && threadIdx.x == 0 && (blockIdx.x == 0 || was_last0)) {
+        long long* d = a.dbg + (was_last0 ? 16 : 0);
+        for (int i = 0; i < 16; ++i) d[i] = i < stamp_n ? stamps[i] - stamps[0] : -1;
+    }
+#undef SHT_STAMP
 }
 
 }  // namespace mlgpu

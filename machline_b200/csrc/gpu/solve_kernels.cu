@@ -1102,13 +1102,15 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
     const int ldq = S.n_rows_pad;
     const int nfull = ((N + 63) / 64) * 64;
     // one CTA per SM at most; every CTA owns a block of >= 32 local rows
-    int grid = std::max(1, std::min(c->num_sms, (n_loc + 31) / 32));
+    int grid = std::max(1, std::min(std::min(c->num_sms, 160), (n_loc + 31) / 32));
     const int rows_per_cta = 32 * ((n_loc + 32 * grid - 1) / (32 * grid));
     grid = std::max(1, (n_loc + rows_per_cta - 1) / rows_per_cta);
     const int kpad = k_max + 4;
     DevBuf<double> Q, w, r0, xfull, xloc, ydev, hdev, nrm, part, npart, h1;
     DevBuf<unsigned> sync;   // [0] ticket, [1] ready
     DevBuf<int> err;
+    DevBuf<long long> dbg;
+    const bool want_dbg = std::getenv("MACHLINE_SHT_DEBUG") != nullptr;
 #define GS_CUDA(call)                                            \
     do {                                                         \
         cudaError_t e__ = (call);                                \
@@ -1122,7 +1124,8 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
     GS_CUDA(r0.alloc(nfull));
     GS_CUDA(xfull.alloc(nfull));
     GS_CUDA(xloc.alloc((size_t)S.shard_pad * c->world));
-    GS_CUDA(part.alloc((size_t)grid * kpad));
+    const int gpad = ((grid + 31) / 32) * 32;
+    GS_CUDA(part.alloc((size_t)gpad * kpad));
     GS_CUDA(npart.alloc(grid));
     GS_CUDA(h1.alloc(kpad));
     GS_CUDA(sync.alloc(2));
@@ -1131,6 +1134,10 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
     GS_CUDA(nrm.alloc(2));
     GS_CUDA(cudaMemsetAsync(sync.p, 0, 2 * sizeof(unsigned), c->stream));
     GS_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), c->stream));
+    if (want_dbg) {
+        GS_CUDA(dbg.alloc(32));
+        GS_CUDA(cudaMemsetAsync(dbg.p, 0xff, 32 * sizeof(long long), c->stream));
+    }
     GS_CUDA(cudaMemsetAsync(Q.p, 0, (size_t)ldq * (k_max + 1) * sizeof(double), c->stream));
     GS_CUDA(cudaMemsetAsync(w.p, 0, (size_t)ldq * sizeof(double), c->stream));
     GS_CUDA(cudaMemsetAsync(xloc.p, 0, (size_t)S.shard_pad * c->world * sizeof(double), c->stream));
@@ -1170,7 +1177,7 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
         if (s != ML_OK) return s;
         ShTailArgs a{};
         a.Q = Q.p; a.ldq = ldq; a.n_loc = n_loc; a.k = k;
-        a.w = w.p; a.partial = part.p; a.kpad = kpad; a.h1 = h1.p; a.hfin = hfin; a.npart = npart.p;
+        a.w = w.p; a.partial = part.p; a.gpad = gpad; a.h1 = h1.p; a.hfin = hfin; a.npart = npart.p;
         a.qnext = Q.p + (size_t)k * ldq; a.xfull = xfull.p; a.N = N; a.g_of_local = g_of_local;
         a.P = c->world; a.rank = c->rank; a.kr = Ctx::P2P_KR; a.nv = (int)c->win_n;
         for (int r = 0; r < Ctx::P2P_MAX; ++r) {
@@ -1182,9 +1189,9 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
         a.seq = c->xseq + 1;
         c->xseq += 3;
         a.ticket = sync.p; a.ready = sync.p + 1; a.base = launches_done++;
-        a.err = err.p; a.rows_per_cta = rows_per_cta;
+        a.err = err.p; a.rows_per_cta = rows_per_cta; a.dbg = want_dbg ? dbg.p : nullptr;
         void* kargs[] = {(void*)&a};
-        const size_t smem = (size_t)(2 * ((k + 3) & ~1) + 1024) * sizeof(double);
+        const size_t smem = (size_t)(2 * ((k + 3) & ~1) + SHT_MAXCH * SHT_THREADS + rows_per_cta) * sizeof(double);
         cudaError_t e = cudaLaunchCooperativeKernel((const void*)arnoldi_tail_sharded_kernel, dim3(grid), dim3(SHT_THREADS), kargs, smem, c->stream);
         if (e != cudaSuccess) return c->cuda_fail(e, "arnoldi_tail_sharded_kernel");
         c->launches += 1;
@@ -1306,6 +1313,16 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
         GS_CUDA(cudaStreamSynchronize(c->stream));
     }
     cudaStreamSynchronize(c->stream);
+    if (want_dbg) {   // clock64 stamps of the last launch: CTA 0 and the CTA that was last at stage 0
+        long long hd[32];
+        if (cudaMemcpy(hd, dbg.p, sizeof hd, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            for (int r = 0; r < 2; ++r) {
+                std::fprintf(stderr, "sht stamps %s:", r ? "last-CTA" : "CTA0");
+                for (int i = 0; i < 16; ++i) std::fprintf(stderr, " %lld", hd[16 * r + i]);
+                std::fprintf(stderr, "\n");
+            }
+        }
+    }
     *total_iter_out = total_iter;
 #undef GS_CUDA
     return st;
@@ -1380,7 +1397,7 @@ static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_
             const bool restarted = opts->matrix_solver == ML_SOLVER_RGMRES;
             const int k_max = restarted ? std::min(opts->restart_iterations, S.N) : std::min(S.N, opts->max_iterations);
             // row-sharded basis + peer-memory reductions when the windows are mapped; else the replicated basis (NCCL all-gather)
-            const bool shard_basis = S.sharded() && c->p2p_ok && !use_mgs && k_max + 3 <= Ctx::P2P_KR &&
+            const bool shard_basis = S.sharded() && c->p2p_ok && !use_mgs && k_max + 3 <= Ctx::P2P_KR && S.n_rows <= c->num_sms * 32 * SHT_MAXCH &&
                                      std::getenv("MACHLINE_GMRES_REPLICATED") == nullptr;
             if (shard_basis)
                 st = gmres_sharded_device(S, d_b, d_scale, opts->tol, opts->max_iterations, opts->restart_iterations, restarted, d_x, &iters,

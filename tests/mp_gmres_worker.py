@@ -56,6 +56,9 @@ else:
 ctx.assemble()
 BC = np.array(case.BC)
 A_ref, I_ref = ob.assemble(case)
+# yardstick for x: GMRES stops on an absolute residual of 1e-12, so two conforming runs agree in x only to cond(A) * 1e-12;
+# how far that is on this system is measured -- the oracle's own GMRES against a direct solve of the oracle's matrix
+x_direct = np.linalg.solve(A_ref, BC - I_ref)
 report = []
 for solver in ("GMRES", "RGMRES"):
     opts = case.solver_opts()
@@ -66,10 +69,11 @@ for solver in ("GMRES", "RGMRES"):
     for rep in range(2):     # twice: the windows, sequence numbers and flags persist across solves
         x, info = ctx.solve(opts, BC)
         err = np.abs(x - x_ref).max() / np.abs(x_ref).max()
+        slack = np.abs(x_ref - x_direct).max() / np.abs(x_ref).max()
         tol_it = 1 if solver == "GMRES" else max(2, info_ref.iterations // 20)   # restarts amplify a one-step difference
         assert abs(info.iterations - info_ref.iterations) <= tol_it, f"rank {rank} {solver}: iterations {info.iterations} vs oracle {info_ref.iterations}"
-        assert err < 1e-9, f"rank {rank} {solver}: |dx|/|x| = {err:.2e}"
-        assert info.res_norm < 1e-10, info.res_norm
+        assert err < max(1e-9, 3 * slack), f"rank {rank} {solver}: |dx|/|x| = {err:.2e} (oracle GMRES vs direct solve: {slack:.2e})"
+        assert info.res_norm < max(1e-10, 10 * info_ref.res_norm), (info.res_norm, info_ref.res_norm)
     report.append(f"{solver} it {info.iterations}/{info_ref.iterations} err {err:.1e} {info.solve_ms:.1f} ms")
 if world > 1:   # every rank must hold the same x bit for bit (identical Hessenberg columns on every rank)
     xs = [None] * world
