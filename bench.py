@@ -321,6 +321,9 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if os.environ.get("MACHLINE_BENCH_WATCHDOG"):   # debugging aid: dump every thread's stack and exit if the run exceeds N seconds
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["MACHLINE_BENCH_WATCHDOG"]), exit=True)
     if args.impl == "reference":
         run_reference(args)
         return

@@ -18,7 +18,7 @@
 //       their GLOBAL index (the all-gather of the next Krylov vector, fused)        -> ticket
 //   R3  LAST CTA: sum of squares in CTA order -> exchanged like h -> norm = sqrt(sum over ranks), hfin[k] = norm
 //   F   Qloc(:, k) = w_loc / norm on the CTA's rows; x_full = window / norm (the operand of the next local matvec)
-// Three grid-wide waits and three NVLink round trips per iteration; spin loops give up after ~4 s and raise an error flag
+// Three grid-wide waits and three NVLink round trips per iteration; spin loops give up after ~20 s and raise an error flag
 // (a rank that died must not hang the others).
 #pragma once
 
@@ -26,7 +26,7 @@ namespace mlgpu {
 
 constexpr int SHT_THREADS = 1024;
 constexpr int SHT_WARPS = SHT_THREADS / 32;
-constexpr long long SHT_SPIN_LIMIT = 8000000000LL;   // clock64 ticks (~4 s)
+constexpr long long SHT_SPIN_LIMIT = 40000000000LL;  // clock64 ticks (~20 s)
 constexpr int SHT_MAXCH = 4;                          // a CTA owns at most 32 * SHT_MAXCH rows
 
 struct ShTailArgs {

