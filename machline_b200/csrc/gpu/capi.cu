@@ -98,6 +98,9 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     c->d_sm_colm.release();
     c->d_g_of_slot.release();
     c->d_slot_of_g.release();
+    if (c->stream_hi) cudaStreamDestroy(c->stream_hi);
+    for (auto& e : c->ev_la)
+        if (e) cudaEventDestroy(e);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->stream) cudaStreamDestroy(c->stream);

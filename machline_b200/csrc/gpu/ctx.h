@@ -106,6 +106,8 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t stream_hi = nullptr;        // higher-priority stream of the LU look-ahead (created on first use)
+    cudaEvent_t ev_la[2] = {nullptr, nullptr};
     std::string err;
     int num_sms = 148;
     long long launches = 0;

@@ -23,7 +23,7 @@ struct LuPanelWork {
 // Factor the panel (rows k0..n, columns k0..k1 of dA): pivots into d_piv[k0..k1), rows interchanged inside the panel,
 // perm updated (when W.all_coop stays true).
 ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int n, int k0, int k1, double* d_vv, int* d_piv, int* d_perm,
-                          cudaStream_t stream);
+                          cudaStream_t stream, int max_ctas = 0);
 // amax[i] = max_j |A(i, j)| over nr x nc (amax zeroed by the caller; bit pattern of a non-negative double)
 void lu_launch_row_amax(Ctx* c, const double* A, int ld, int nr, int nc, double* amax);
 // X (64 x ncols, ldx) <- L^-1 X with L the unit lower triangle of a 64 x 64 block
@@ -33,6 +33,6 @@ void lu_launch_trsv_diag(Ctx* c, const double* D, int ld, int nb, double* x, int
 // C (M x Nc) -= L (M x 64 k_halves) * U (64 k_halves x Nc) on the FP64 tensor cores; all leading dimensions even, pointers
 // 16-byte aligned; row_block_active: optional byte per LU_GEMM_BM rows of C (0 = skip)
 void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ldu, double* Cp, int ldc, int M, int Nc,
-                     const unsigned char* row_block_active, int k_halves = 1);
+                     const unsigned char* row_block_active, int k_halves = 1, cudaStream_t stream = nullptr);
 
 }  // namespace mlgpu

@@ -15,6 +15,8 @@
 #include <string>
 #include <vector>
 
+#include <cooperative_groups.h>
+
 #include "lu_internal.cuh"
 
 namespace mlgpu {
@@ -131,7 +133,10 @@ __global__ void __launch_bounds__(256) lu_panel_update_kernel(double* __restrict
 // a(i,c) = fma(-l, a(j,c), a(i,c)) with l = a(i,j) * (1/a(j,j)), identical to the per-column kernels.
 // 256 threads per CTA; 128 (<= 96 registers) when a CTA holds 128 rows, so that it fits on an SM next to a CTA of the
 // trailing update: the look-ahead factors panel k+1 under the update of panel k.
-constexpr int LUP_THREADS = 256;
+#ifndef ML_LUP_THREADS
+#define ML_LUP_THREADS 512
+#endif
+constexpr int LUP_THREADS = ML_LUP_THREADS;   // 16 warps: the per-column work of a CTA is a chain of shared-memory latencies
 constexpr int LUP_CAP = 384;   // rows a CTA can hold: 64 columns x 384 rows x 8 B = 192 KB
 constexpr int LUP_CAP_OVF = 320;   // shared-memory rows per CTA when the panel overflows (the rest stay in global memory)
 constexpr int LUP_RPC_MAX = 2048;  // rows per CTA the overflow variant supports (s_l, s_vv, s_perm are per row)
@@ -166,8 +171,14 @@ __device__ __forceinline__ void lup_grid_sync(unsigned* bar, unsigned target) {
 
 __device__ __forceinline__ bool lup_better(double v, int i, double best, int bi) { return v > best || (v == best && i > bi); }
 
-template <bool OVF, int T>
+// CL: the CTAs form ONE thread-block cluster (<= 16 CTAs): the candidate slots live in every CTA's shared memory and are written
+// by the peers through distributed shared memory, the per-column barrier is the hardware cluster barrier instead of an atomic
+// counter in global memory (three L2 round trips + a polling loop per column), and the kernel occupies at most 16 SMs, so it
+// runs NEXT TO the trailing update of the previous pair of panels (look-ahead).
+constexpr int LUP_CL_MAX = 16;   // CTAs of the cluster variant
+template <bool OVF, int T, bool CL = false>
 __global__ void __launch_bounds__(T, T == 128 ? 5 : 1) lu_panel_coop_kernel(const LuPanelArgs a) {
+    namespace cg = cooperative_groups;
     extern __shared__ __align__(16) double lup_smem[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int G = gridDim.x, bid = blockIdx.x;
@@ -188,10 +199,17 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 1) lu_panel_coop_kernel(cons
     double* s_oldj = s_piv + LUP_ROW;                  // [LUP_ROW] old row j (+ perm, vv)
     double* s_l = s_oldj + LUP_ROW;                    // [rpc]
     double* s_vv = s_l + a.rpc;                        // [rpc]
-    double* s_rv = s_vv + a.rpc;                       // [8]
-    int* s_ri = reinterpret_cast<int*>(s_rv + 8);      // [8] + s_ri[8] = winner
-    int* s_perm = s_ri + 16;                           // [rpc]
+    constexpr int NW = T / 32 < 8 ? 8 : T / 32;        // warp partials (at least the 8 slots the layout always had)
+    double* s_rv = s_vv + a.rpc;                       // [32]: warp partials, s_rv[NW] = the CTA's best value
+    int* s_ri = reinterpret_cast<int*>(s_rv + 32);     // [32] + s_ri[32] = winner
+    int* s_perm = s_ri + 34;                           // [rpc]
+    // CL: candidate slots of every CTA of the cluster, two parities (written by the peers through DSMEM)
+    double* cl_row = reinterpret_cast<double*>(s_perm + ((a.rpc + 1) & ~1));   // [2][LUP_CL_MAX][LUP_ROW]
+    double* cl_rowj = cl_row + 2 * LUP_CL_MAX * LUP_ROW;                        // [2][LUP_ROW]
+    double* cl_v = cl_rowj + 2 * LUP_ROW;                                       // [2][LUP_CL_MAX]
+    int* cl_i = reinterpret_cast<int*>(cl_v + 2 * LUP_CL_MAX);                  // [2][LUP_CL_MAX]
     const int nrb = (nr + 31) >> 5;
+    if constexpr (CL) cg::this_cluster().sync();       // every CTA of the cluster is running before the first remote store
 
     for (int item = warp; item < nb * nrb; item += T / 32) {
         const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
@@ -227,38 +245,73 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 1) lu_panel_coop_kernel(cons
             best = lane < T / 32 ? s_rv[lane] : -1.;
             bi = lane < T / 32 ? s_ri[lane] : -1;
 #pragma unroll
-            for (int o = 4; o > 0; o >>= 1) {
+            for (int o = NW / 2; o > 0; o >>= 1) {
                 const double ov = __shfl_xor_sync(0xffffffffu, best, o);
                 const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                 if (lup_better(ov, oi, best, bi)) { best = ov; bi = oi; }
             }
             if (lane == 0) {
-                s_ri[8] = bi;
-                __stcg(a.cand_v + par * G + bid, best);
-                __stcg(a.cand_i + par * G + bid, bi);
+                s_ri[32] = bi;
+                if constexpr (CL) {
+                    s_rv[NW] = best;
+                } else {
+                    __stcg(a.cand_v + par * G + bid, best);
+                    __stcg(a.cand_i + par * G + bid, bi);
+                }
             }
         }
         __syncthreads();
-        bi = s_ri[8];
-        if (bi >= 0) {
-            double* slot = a.cand_row + ((size_t)par * G + bid) * LUP_ROW;
-            if (tid < nb) __stcg(slot + tid, el(bi - r0, tid));
-            if (tid == LU_NB) __stcg(slot + LU_NB, (double)s_perm[bi - r0]);
-        }
+        bi = s_ri[32];
         const bool own_j = (j >= r0 && j < r0 + nr);
-        if (own_j) {
-            double* slot = a.rowj + par * LUP_ROW;
-            if (tid < nb) __stcg(slot + tid, el(j - r0, tid));
-            if (tid == LU_NB) __stcg(slot + LU_NB, (double)s_perm[j - r0]);
-            if (tid == LU_NB + 1) __stcg(slot + LU_NB + 1, s_vv[j - r0]);
+        if constexpr (CL) {
+            // this CTA's candidate (value, position, the row's panel entries, its perm entry) and -- from the CTA that holds
+            // it -- row j go into the slots of EVERY CTA of the cluster: thread t serves destination t / 80, word t % 80
+            cg::cluster_group cluster = cg::this_cluster();
+            for (int t = tid; t < G * 80; t += T) {
+                const int dst = t / 80, wd = t - dst * 80;
+                if (wd < LUP_ROW) {
+                    if (bi >= 0 && (wd < nb || wd == LU_NB)) {
+                        const double v = wd < nb ? el(bi - r0, wd) : (double)s_perm[bi - r0];
+                        cluster.map_shared_rank(cl_row, dst)[(par * LUP_CL_MAX + bid) * LUP_ROW + wd] = v;
+                    }
+                } else if (wd == LUP_ROW) {
+                    cluster.map_shared_rank(cl_v, dst)[par * LUP_CL_MAX + bid] = s_rv[NW];
+                } else if (wd == LUP_ROW + 1) {
+                    cluster.map_shared_rank(cl_i, dst)[par * LUP_CL_MAX + bid] = bi;
+                } else if (own_j && wd - (LUP_ROW + 2) < 12) {
+                    // 12 threads per destination copy row j: words 6 q .. 6 q + 5 of its 66-word slot (entries, perm, vv)
+                    const int q = wd - (LUP_ROW + 2);
+                    double* rj = cluster.map_shared_rank(cl_rowj, dst) + par * LUP_ROW;
+                    for (int u2 = 6 * q; u2 < 6 * q + 6 && u2 < LUP_ROW; ++u2) {
+                        double v = 0.;
+                        if (u2 < nb) v = el(j - r0, u2);
+                        else if (u2 == LU_NB) v = (double)s_perm[j - r0];
+                        else if (u2 == LU_NB + 1) v = s_vv[j - r0];
+                        rj[u2] = v;
+                    }
+                }
+            }
+            cluster.sync();
+        } else {
+            if (bi >= 0) {
+                double* slot = a.cand_row + ((size_t)par * G + bid) * LUP_ROW;
+                if (tid < nb) __stcg(slot + tid, el(bi - r0, tid));
+                if (tid == LU_NB) __stcg(slot + LU_NB, (double)s_perm[bi - r0]);
+            }
+            if (own_j) {
+                double* slot = a.rowj + par * LUP_ROW;
+                if (tid < nb) __stcg(slot + tid, el(j - r0, tid));
+                if (tid == LU_NB) __stcg(slot + LU_NB, (double)s_perm[j - r0]);
+                if (tid == LU_NB + 1) __stcg(slot + LU_NB + 1, s_vv[j - r0]);
+            }
+            lup_grid_sync(a.bar, a.bar_base + (unsigned)(jj + 1) * (unsigned)G);
         }
-        lup_grid_sync(a.bar, a.bar_base + (unsigned)(jj + 1) * (unsigned)G);
         // ---- global pivot: reduce the G candidates (every CTA, redundantly) ---------------------------------
         best = -1.;
         bi = -1;
         for (int g = tid; g < G; g += T) {
-            const double v = __ldcg(a.cand_v + par * G + g);
-            const int i = __ldcg(a.cand_i + par * G + g);
+            const double v = CL ? cl_v[par * LUP_CL_MAX + g] : __ldcg(a.cand_v + par * G + g);
+            const int i = CL ? cl_i[par * LUP_CL_MAX + g] : __ldcg(a.cand_i + par * G + g);
             if (i >= 0 && lup_better(v, i, best, bi)) { best = v; bi = i; }
         }
 #pragma unroll
@@ -274,23 +327,25 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 1) lu_panel_coop_kernel(cons
                 best = lane < T / 32 ? s_rv[lane] : -1.;
                 bi = lane < T / 32 ? s_ri[lane] : -1;
 #pragma unroll
-                for (int o = 4; o > 0; o >>= 1) {
+                for (int o = NW / 2; o > 0; o >>= 1) {
                     const double ov = __shfl_xor_sync(0xffffffffu, best, o);
                     const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
                     if (lup_better(ov, oi, best, bi)) { best = ov; bi = oi; }
                 }
-                if (lane == 0) s_ri[8] = bi;
+                if (lane == 0) s_ri[32] = bi;
             }
         } else if (tid == 0) {
-            s_ri[8] = bi;   // warp 0 saw every candidate
+            s_ri[32] = bi;   // warp 0 saw every candidate
         }
         __syncthreads();
-        int p = s_ri[8];
+        int p = s_ri[32];
         if (p < 0) p = j;   // a column of NaNs: keep the diagonal (the reference's imax stays at its previous value)
         const int w = (p - a.k0) / a.rpc;
         const bool own_p = (p >= r0 && p < r0 + nr);
-        if (tid < nb || tid == LU_NB) s_piv[tid] = __ldcg(a.cand_row + ((size_t)par * G + w) * LUP_ROW + tid);
-        if (p != j && own_p && (tid < nb || tid == LU_NB || tid == LU_NB + 1)) s_oldj[tid] = __ldcg(a.rowj + par * LUP_ROW + tid);
+        if (tid < nb || tid == LU_NB)
+            s_piv[tid] = CL ? cl_row[(par * LUP_CL_MAX + w) * LUP_ROW + tid] : __ldcg(a.cand_row + ((size_t)par * G + w) * LUP_ROW + tid);
+        if (p != j && own_p && (tid < nb || tid == LU_NB || tid == LU_NB + 1))
+            s_oldj[tid] = CL ? cl_rowj[par * LUP_ROW + tid] : __ldcg(a.rowj + par * LUP_ROW + tid);
         if (bid == 0 && tid == 0) a.piv[j] = p;
         __syncthreads();
         if (p != j) {   // whole-row interchange inside the panel (linalg.f90:254-263)
@@ -737,7 +792,8 @@ __global__ void __launch_bounds__(256) lu_bwd_step_kernel(const double* __restri
 
 // C (M x Nc) -= L (M x 64) * U (64 x Nc) on the FP64 tensor cores; all leading dimensions even, pointers 16-byte aligned
 void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ldu, double* Cp, int ldc, int M, int Nc,
-                     const unsigned char* row_block_active, int k_halves) {
+                     const unsigned char* row_block_active, int k_halves, cudaStream_t stream) {
+    if (!stream) stream = c->stream;
     if (!(c->attr_mask & 2u)) {   // per device: remembered per context
         cudaError_t e1 = cudaFuncSetAttribute(lu_gemm2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem(1));
         cudaError_t e2 = cudaFuncSetAttribute(lu_gemm2_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem(2));
@@ -748,22 +804,24 @@ void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ld
     int per, chunks;
     lu_gemm2_shape(rb, ct32, c->num_sms, k_halves, &per, &chunks);
     if (k_halves == 2)
-        lu_gemm2_kernel<2><<<dim3(rb, chunks), G2_THREADS, g2_smem(2), c->stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
+        lu_gemm2_kernel<2><<<dim3(rb, chunks), G2_THREADS, g2_smem(2), stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
     else
-        lu_gemm2_kernel<1><<<dim3(rb, chunks), G2_THREADS, g2_smem(1), c->stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
+        lu_gemm2_kernel<1><<<dim3(rb, chunks), G2_THREADS, g2_smem(1), stream>>>(Lp, ldl, Up, ldu, Cp, ldc, M, Nc, ct32, per, row_block_active);
     c->launches += 1;
 }
 
-static size_t lu_panel_smem(int rpc) {
+static size_t lu_panel_smem(int rpc, bool cluster = false) {
     const int cap = rpc <= LUP_CAP ? rpc : LUP_CAP_OVF;
-    return (size_t)(LU_NB * (cap | 1) + 2 * LUP_ROW + 2 * rpc + 8) * sizeof(double) + (size_t)(16 + rpc) * sizeof(int);
+    size_t b = (size_t)(LU_NB * (cap | 1) + 2 * LUP_ROW + 2 * rpc + 32) * sizeof(double) + (size_t)(34 + ((rpc + 1) & ~1)) * sizeof(int);
+    if (cluster) b += (size_t)(2 * LUP_CL_MAX * LUP_ROW + 2 * LUP_ROW + 2 * LUP_CL_MAX) * sizeof(double) + (size_t)2 * LUP_CL_MAX * sizeof(int);
+    return b;
 }
 
 ml_status LuPanelWork::init(Ctx* c) {
     if (!(c->attr_mask & 4u)) {
-        ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<false, LUP_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)lu_panel_smem(LUP_CAP)));
-        ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        ML_CUDA(c, cudaFuncSetAttribute(lu_panel_coop_kernel<true, LUP_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)lu_panel_smem(LUP_RPC_MAX)));
         c->attr_mask |= 4u;
     }
@@ -800,12 +858,55 @@ void lu_launch_trsv_diag(Ctx* c, const double* D, int ld, int nb, double* x, int
 // Factor the panel (rows k0..n, columns k0..k1 of dA): pivots into d_piv[k0..k1), rows interchanged inside the panel.
 // One cooperative launch when the panel's rows fit the CTAs' shared memory, else two launches per column.
 ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int n, int k0, int k1, double* d_vv, int* d_piv, int* d_perm,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, int max_ctas) {
     static const bool per_column = getenv("MACHLINE_LU_PER_COLUMN") != nullptr;   // the unfused path, kept for A/B timing
     const int m = n - k0;
-    int rpc = 128;
-    if ((long long)rpc * W.gmax < m) rpc = (((m + W.gmax - 1) / W.gmax) + 31) & ~31;
     static const char* rpc_env = getenv("MACHLINE_LU_PANEL_RPC");   // tests: force a rows-per-CTA value (e.g. the overflow variant)
+    // Cluster variant (one thread-block cluster of <= 16 CTAs, candidates through distributed shared memory, hardware cluster
+    // barrier per column): whenever the panel's rows fit 16 CTAs' shared memory.  MACHLINE_LU_NO_CLUSTER=1 disables it.
+    static const bool no_cluster = getenv("MACHLINE_LU_NO_CLUSTER") != nullptr;
+    if (!per_column && !no_cluster && !rpc_env && m <= LUP_CL_MAX * LUP_CAP) {
+        int G = 1;
+        while (G < LUP_CL_MAX && G * 128 < m) G *= 2;
+        while (G < LUP_CL_MAX && (m + G - 1) / G > LUP_CAP) G *= 2;
+        int rpc_c = (((m + G - 1) / G) + 31) & ~31;
+        while (G > 1 && (long long)rpc_c * (G - 1) >= m) {           // every CTA of the cluster owns at least one row
+            G /= 2;
+            rpc_c = (((m + G - 1) / G) + 31) & ~31;
+        }
+        if (rpc_c <= LUP_CAP) {
+            auto kern = lu_panel_coop_kernel<false, LUP_THREADS, true>;
+            const size_t smem = lu_panel_smem(rpc_c, true);
+            if (!(c->attr_mask & 32u)) {
+                ML_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel_smem(LUP_CAP, true)));
+                ML_CUDA(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                c->attr_mask |= 32u;
+            }
+            LuPanelArgs pa;
+            pa.A = dA; pa.ld = ld; pa.n = n; pa.k0 = k0; pa.k1 = k1; pa.rpc = rpc_c;
+            pa.vv = d_vv; pa.piv = d_piv; pa.perm = d_perm;
+            pa.cand_v = nullptr; pa.cand_row = nullptr; pa.rowj = nullptr; pa.cand_i = nullptr; pa.bar = nullptr; pa.bar_base = 0;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(LUP_THREADS);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = G;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            ML_CUDA(c, cudaLaunchKernelEx(&cfg, kern, pa));
+            c->launches += 1;
+            return ML_OK;
+        }
+    }
+    // max_ctas > 0 (look-ahead): the panel runs on a few SMs next to the trailing update of the previous pair
+    const int gcap = (max_ctas > 0) ? std::min(max_ctas, W.gmax) : W.gmax;
+    int rpc = 128;
+    if ((long long)rpc * gcap < m) rpc = (((m + gcap - 1) / gcap) + 31) & ~31;
     if (rpc_env && atoi(rpc_env) >= 128) rpc = std::max(rpc, (atoi(rpc_env) + 31) & ~31);
     if (!per_column && rpc <= LUP_RPC_MAX) {
         LuPanelArgs pa;
@@ -819,8 +920,12 @@ ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int n, int
         const int G = (m + rpc - 1) / rpc;
         W.bar_base += (unsigned)(k1 - k0) * (unsigned)G;
         void* kargs[] = {(void*)&pa};
-        const void* kern = rpc <= LUP_CAP ? (const void*)lu_panel_coop_kernel<false, 256> : (const void*)lu_panel_coop_kernel<true, 256>;
-        ML_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(G), dim3(LUP_THREADS), kargs, lu_panel_smem(rpc), stream));
+        const void* kern = rpc <= LUP_CAP ? (const void*)lu_panel_coop_kernel<false, LUP_THREADS> : (const void*)lu_panel_coop_kernel<true, LUP_THREADS>;
+        // A cooperative launch waits until the whole grid fits at once, i.e. until a concurrent trailing update has drained.
+        // With a capped grid an ordinary launch is enough: the CTAs spin on the panel's own barrier, the update's CTAs do not
+        // depend on them and retire, and the freed SMs go to this (higher-priority) kernel first: no deadlock.
+        if (max_ctas > 0) ML_CUDA(c, cudaLaunchKernel(kern, dim3(G), dim3(LUP_THREADS), kargs, lu_panel_smem(rpc), stream));
+        else ML_CUDA(c, cudaLaunchCooperativeKernel(kern, dim3(G), dim3(LUP_THREADS), kargs, lu_panel_smem(rpc), stream));
         c->launches += 1;
     } else {
         W.all_coop = false;
@@ -858,64 +963,110 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     static const bool no_k128 = getenv("MACHLINE_LU_NO_K128") != nullptr;
     const bool fast_gemm = !old_gemm && (ld & 1) == 0;
     cudaStream_t S0 = c->stream;
-    auto laswp = [&](int c0, int c1, int k0, int k1) {   // interchanges of panel [k0, k1) applied to columns [c0, c1)
+    // Look-ahead: the next pair of panels is factored on a second, higher-priority stream (on a few SMs) while the rank-128
+    // update of the current pair still runs on the rest of the matrix.  MACHLINE_LU_LOOKAHEAD=0 disables it, =<n> caps the panel
+    // kernel at n CTAs (default 32).
+    int la_ctas = 32;
+    if (const char* e = getenv("MACHLINE_LU_LOOKAHEAD")) la_ctas = atoi(e);
+    const bool lookahead = fast_gemm && !no_k128 && la_ctas > 0;
+    if (lookahead && !c->stream_hi) {
+        int lo = 0, hi = 0;
+        ML_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        ML_CUDA(c, cudaStreamCreateWithPriority(&c->stream_hi, cudaStreamNonBlocking, hi));
+        ML_CUDA(c, cudaEventCreateWithFlags(&c->ev_la[0], cudaEventDisableTiming));
+        ML_CUDA(c, cudaEventCreateWithFlags(&c->ev_la[1], cudaEventDisableTiming));
+    }
+    cudaStream_t S1 = lookahead ? c->stream_hi : S0;
+    auto laswp = [&](cudaStream_t st, int c0, int c1, int k0, int k1) {   // interchanges of panel [k0, k1) applied to columns [c0, c1)
         if (c1 > c0) {
-            lu_laswp_kernel<<<(c1 - c0 + 255) / 256, 256, 0, S0>>>(dA, ld, c0, c1, k0, k1, d_piv);
+            lu_laswp_kernel<<<(c1 - c0 + 255) / 256, 256, 0, st>>>(dA, ld, c0, c1, k0, k1, d_piv);
             c->launches += 1;
         }
     };
-    auto trsm = [&](int k0, int c0, int c1) {            // U(k0..k0+64, c0..c1) = L11^-1 A(k0..k0+64, c0..c1)
+    auto trsm = [&](cudaStream_t st, int k0, int c0, int c1) {            // U(k0..k0+64, c0..c1) = L11^-1 A(k0..k0+64, c0..c1)
         if (c1 > c0) {
-            lu_trsm_kernel<<<(c1 - c0 + 63) / 64, 64, 0, S0>>>(dA + k0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, c1 - c0);
+            lu_trsm_kernel<<<(c1 - c0 + 63) / 64, 64, 0, st>>>(dA + k0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, c1 - c0);
             c->launches += 1;
         }
     };
     // A(r0..r1, c0..c1) -= A(r0..r1, k0..k0+64 kh) A(k0..k0+64 kh, c0..c1)
-    auto gemm = [&](int r0, int r1, int c0, int c1, int k0, int kh) {
+    auto gemm = [&](cudaStream_t st, int r0, int r1, int c0, int c1, int k0, int kh) {
         if (r1 <= r0 || c1 <= c0) return;
         if (fast_gemm) {
-            lu_gemm2_launch(c, dA + r0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, dA + r0 + (size_t)c0 * ld, ld, r1 - r0, c1 - c0, nullptr, kh);
+            lu_gemm2_launch(c, dA + r0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, dA + r0 + (size_t)c0 * ld, ld, r1 - r0, c1 - c0, nullptr, kh,
+                            st);
         } else {   // first-generation kernel: whole trailing matrix of one panel (r0 == c0 == k0 + 64, r1 == c1 == n)
             dim3 grid((n - r0 + GM_BM - 1) / GM_BM, (n - r0 + GM_BN - 1) / GM_BN);
-            lu_gemm_dmma_kernel<<<grid, 256, gemm_smem, S0>>>(dA, ld, n, k0, k0 + LU_NB);
+            lu_gemm_dmma_kernel<<<grid, 256, gemm_smem, st>>>(dA, ld, n, k0, k0 + LU_NB);
             c->launches += 1;
         }
     };
-    pst = lu_panel_factor(c, PW, dA, ld, n, 0, std::min(LU_NB, n), d_vv, d_piv, d_perm, S0);
-    if (pst != ML_OK) { PW.release(); return pst; }
-    for (int k0 = 0; k0 < n;) {   // invariant: panel [k0, k0 + 64) is factored, nothing to its right has seen it yet
+    // Panels A = [a0, a0 + 64) and B = [a0 + 64, a0 + 128), whose columns have seen every earlier panel: factor A, apply it to B's
+    // 64 columns, factor B.  On `st` with at most `cap` CTAs per panel kernel (0: the whole grid, cooperative).
+    auto factor_pair = [&](cudaStream_t st, int a0, int cap) -> ml_status {
+        const int a1 = a0 + LU_NB, a2 = a1 + LU_NB;
+        ml_status ps = lu_panel_factor(c, PW, dA, ld, n, a0, a1, d_vv, d_piv, d_perm, st, cap);
+        if (ps != ML_OK) return ps;
+        laswp(st, a1, a2, a0, a1);
+        trsm(st, a0, a1, a2);
+        gemm(st, a1, n, a1, a2, a0, 1);
+        return lu_panel_factor(c, PW, dA, ld, n, a1, a2, d_vv, d_piv, d_perm, st, cap);
+    };
+    int k0 = 0;
+    bool have_panel = false;   // panel [k0, k0 + 64) is factored and nothing to its right has seen it yet
+    if (fast_gemm && !no_k128 && n > 2 * LU_NB) {
+        // ---- pairs of panels, one rank-128 update per pair (C is read and written once for 256 flop per entry) ----
+        pst = factor_pair(S0, 0, 0);
+        if (pst != ML_OK) { PW.release(); return pst; }
+        for (;;) {   // invariant: A = [k0, k1), B = [k1, k2) factored (B has seen A); k2 < n; nothing outside the pair has seen them
+            const int k1 = k0 + LU_NB, k2 = k1 + LU_NB;
+            laswp(S0, 0, k0, k0, k1);     // A's interchanges, left and right of the pair
+            laswp(S0, k2, n, k0, k1);
+            laswp(S0, 0, k1, k1, k2);     // B's: the left part includes A's own columns (its multipliers move with the rows)
+            laswp(S0, k2, n, k1, k2);
+            trsm(S0, k0, k2, n);                  // U rows of A
+            gemm(S0, k1, k2, k2, n, k0, 1);       // rows of B's diagonal block: minus L21_A U_A
+            trsm(S0, k1, k2, n);                  // U rows of B
+            const bool next_pair = (n - k2) > 2 * LU_NB;   // another complete pair with something after it
+            if (!next_pair) {
+                gemm(S0, k2, n, k2, n, k0, 2);    // everything below: minus [L_A L_B] [U_A; U_B]
+                k0 = k2;
+                break;
+            }
+            const int k4 = k2 + 2 * LU_NB;
+            gemm(S0, k2, n, k2, k4, k0, 2);       // the next pair's columns first ...
+            if (lookahead) {
+                ML_CUDA(c, cudaEventRecord(c->ev_la[0], S0));
+                ML_CUDA(c, cudaStreamWaitEvent(S1, c->ev_la[0], 0));
+            }
+            pst = factor_pair(S1, k2, lookahead ? la_ctas : 0);   // ... so that its panels are factored under the rest of the update
+            if (pst != ML_OK) { PW.release(); return pst; }
+            gemm(S0, k2, n, k4, n, k0, 2);
+            if (lookahead) {
+                ML_CUDA(c, cudaEventRecord(c->ev_la[1], S1));
+                ML_CUDA(c, cudaStreamWaitEvent(S0, c->ev_la[1], 0));
+            }
+            k0 = k2;
+            ML_CUDA(c, cudaGetLastError());
+        }
+    }
+    // ---- single panels: the remaining columns (or the whole matrix on the fallback paths) ----
+    if (k0 < n) {
+        pst = lu_panel_factor(c, PW, dA, ld, n, k0, std::min(k0 + LU_NB, n), d_vv, d_piv, d_perm, S0);
+        if (pst != ML_OK) { PW.release(); return pst; }
+        have_panel = true;
+    }
+    while (have_panel && k0 < n) {   // invariant: panel [k0, k0 + 64) is factored, nothing to its right has seen it yet
         const int k1 = std::min(k0 + LU_NB, n), k2 = std::min(k1 + LU_NB, n);
-        if (fast_gemm && !no_k128 && k2 - k1 == LU_NB && k2 < n) {
-            // Two panels A = [k0, k1), B = [k1, k2) per pass over the trailing matrix: A is applied to B's 64 columns only,
-            // B is factored, then both reach the rest in ONE rank-128 update (C is read and written once for 256 flop per
-            // entry instead of twice for 128 each).
-            laswp(k1, k2, k0, k1);
-            trsm(k0, k1, k2);
-            gemm(k1, n, k1, k2, k0, 1);
+        laswp(S0, 0, k0, k0, k1);
+        laswp(S0, k1, n, k0, k1);
+        if (k1 < n) {
+            trsm(S0, k0, k1, n);
+            gemm(S0, k1, n, k1, n, k0, 1);
             pst = lu_panel_factor(c, PW, dA, ld, n, k1, k2, d_vv, d_piv, d_perm, S0);
             if (pst != ML_OK) { PW.release(); return pst; }
-            laswp(0, k0, k0, k1);     // A's interchanges, left and right of the pair
-            laswp(k2, n, k0, k1);
-            laswp(0, k1, k1, k2);     // B's: the left part includes A's own columns (its multipliers move with the rows)
-            laswp(k2, n, k1, k2);
-            trsm(k0, k2, n);                  // U rows of A
-            gemm(k1, k2, k2, n, k0, 1);       // rows of B's diagonal block: minus L21_A U_A
-            trsm(k1, k2, n);                  // U rows of B
-            gemm(k2, n, k2, n, k0, 2);        // everything below: minus [L_A L_B] [U_A; U_B]
-            pst = lu_panel_factor(c, PW, dA, ld, n, k2, std::min(k2 + LU_NB, n), d_vv, d_piv, d_perm, S0);
-            if (pst != ML_OK) { PW.release(); return pst; }
-            k0 = k2;
-        } else {
-            laswp(0, k0, k0, k1);
-            laswp(k1, n, k0, k1);
-            if (k1 < n) {
-                trsm(k0, k1, n);
-                gemm(k1, n, k1, n, k0, 1);
-                pst = lu_panel_factor(c, PW, dA, ld, n, k1, k2, d_vv, d_piv, d_perm, S0);
-                if (pst != ML_OK) { PW.release(); return pst; }
-            }
-            k0 = k1;
         }
+        k0 = k1;
         ML_CUDA(c, cudaGetLastError());
     }
     if (!PW.all_coop) {
