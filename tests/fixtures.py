@@ -60,6 +60,30 @@ def golden_input(name: str):
     return inp, case["expect"], case["tol"]
 
 
+def comparison_names():
+    return [c["name"] for c in goldens().get("comparisons", [])]
+
+
+def comparison_cases(name: str):
+    """(host.Case A, host.Case B, tolerances) of a reference test that compares two runs with each other."""
+    from machline_b200 import host
+    doc = goldens()
+    cmp_ = next(c for c in doc["comparisons"] if c["name"] == name)
+    out = []
+    for nm in cmp_["inputs"]:
+        inp = copy.deepcopy(doc["inputs"][nm])
+        for key, val in cmp_["alter"]:
+            d = inp
+            ks = key.split(".")
+            for k in ks[:-1]:
+                d = d.setdefault(k, {})
+            d[ks[-1]] = val
+        inp.setdefault("output", {})["verbose"] = False
+        inp["output"] = {"verbose": False}
+        out.append(host.Case(inp, base_dir=mesh_root()))
+    return out[0], out[1], cmp_["tol"]
+
+
 def make_case(name: str):
     from machline_b200 import host
     inp, expect, tol = golden_input(name)

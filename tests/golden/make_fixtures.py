@@ -152,6 +152,10 @@ GOLDENS = [
          expect=[0.99114275830853, -1.23782791839695, 0.0, 0.0, 0.0], tol=[1e-12, 1e-12, 2e-5, 2e-5, 2e-5]),
     dict(name="test_08", lines="286-297", input="sphere_input.json", alter=[],
          expect=[0.991142758308531, -1.23782791839695, 0.0, 0.0, 0.0], tol=[1e-12, 1e-12, 1e-4, 1e-4, 1e-4]),
+    # test_09 writes an altered (neumann-mass-flux) input but RUNS the unaltered sphere_input.json (test_machline.py:304-310):
+    # what it pins is the default Morino sphere, with its own force tolerances
+    dict(name="test_09", lines="300-322", input="sphere_input.json", alter=[],
+         expect=[0.991142758308531, -1.23782791839695, 0.0, 0.0, 0.0], tol=[1e-12, 1e-12, 1e-4, 1e-4, 1e-4]),
     dict(name="test_12", lines="416-429", input="compressible_half_wing_input.json", alter=[],
          expect=[0.817285785213847, -1.09376107707523, -0.508549885785561, 0.0102005794126269, 26.2795099006351],
          tol=[1e-9, 1e-9, 1e-9, 1e-9, 1e-8]),
@@ -179,13 +183,25 @@ GOLDENS = [
 ]
 
 
+# Tests that compare two runs with each other instead of with stored numbers (test_machline.py:325-363): the full wing against
+# the mirrored half wing, lower-order Morino, V = (100, 0, 10); tolerances on |full - half| of (C_p_max, C_p_min, Cx, Cy, Cz).
+COMPARISONS = [
+    dict(name="test_10", lines="325-363", inputs=["full_wing_input.json", "half_wing_input.json"],
+         alter=[["flow.freestream_velocity", [100.0, 0.0, 10.0]], ["solver.formulation", "dirichlet-morino"]],
+         tol=[1e-3, 2e-3, 1e-3, 1e-3, 2e-2]),
+]
+
+
 def make_goldens():
     inputs = {}
+    for cmp_ in COMPARISONS:
+        for nm in cmp_["inputs"]:
+            inputs[nm] = json.loads((REF / "test" / "input_files" / nm).read_text())
     for g in GOLDENS:
         if g["input"] not in inputs:
             inputs[g["input"]] = json.loads((REF / "test" / "input_files" / g["input"]).read_text())
     doc = dict(source="usuaero/MachLine test/test_machline.py (golden tuples C_p_max, C_p_min, Cx, Cy, Cz)",
-               inputs=inputs, cases=GOLDENS)
+               inputs=inputs, cases=GOLDENS, comparisons=COMPARISONS)
     (OUT / "reference_goldens.json").write_text(json.dumps(doc, indent=1))
     print("reference_goldens.json:", len(GOLDENS), "cases")
 

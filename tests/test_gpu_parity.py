@@ -107,6 +107,22 @@ def test_reference_goldens_through_gpu(ctx, name):
     case.close()
 
 
+@pytest.mark.parametrize("name", fixtures.comparison_names())
+def test_reference_comparisons_through_gpu(ctx, name):
+    """Reference tests that compare two runs with each other (test 10: full wing vs mirrored half wing) through the CUDA path."""
+    a, b, tol = fixtures.comparison_cases(name)
+    tuples = []
+    for case in (a, b):
+        ctx.set_case(case)
+        ctx.assemble()
+        x, info = ctx.solve(case.solver_opts(), case.BC)
+        r = case.post(x)
+        tuples.append([r.C_p_max, r.C_p_min, *[float(v) for v in r.C_F]])
+        case.close()
+    for x, y, t in zip(tuples[0], tuples[1], tol):
+        assert abs(x - y) < t, tuples
+
+
 @pytest.mark.parametrize("name", ["test_08", "test_13", "test_05"])
 def test_gmres_iterations_and_solution_match_oracle(ctx, name):
     case, _, _ = fixtures.make_case(name)
