@@ -464,6 +464,28 @@ def main():
                                               "ms_per_step": ms1, "iterations": int(i1.iterations)}
                 case1.close()
             barrier()
+    # ---- sharded direct solve (N > 1): the row-sharded blocked LU on the same case, rows dealt block-cyclically -------------
+    lu_sharded = None
+    if world > 1 and not args.no_lu_probe and not args.no_extra_probes and not args.dims:
+        from machline_b200 import _abi
+        barrier()
+        ctx.set_case(case, cyclic=(shard.CYCLIC_BLOCK, rank, world))
+        ctx.assemble()
+        lu_opts = _abi.solver_opts("LU", preconditioner="DIAG" if opts.preconditioner else "none")
+        x_lu, info_lu = ctx.solve(lu_opts, BC)
+        t_lu = torch.tensor([info_lu.solve_ms], dtype=torch.float64, device=f"cuda:{local}")
+        dist.all_reduce(t_lu, op=dist.ReduceOp.MAX)
+        lu_ms = float(t_lu.cpu()[0])
+        if rank == 0:
+            dmma_peak = ctx.measure_dmma_peak()
+            flops = 2.0 / 3.0 * float(N) ** 3
+            lu_sharded = {"kernel": f"row-sharded blocked LU over {world} GPUs (lu_sharded.cu: gathered panel, replicated panel factorisation, "
+                                    "U-row exchange over NCCL, local DMMA update), whole solve, rows block-cyclic 128",
+                          "bound": "tensor(fp64)", "n": int(N), "solve_ms": lu_ms, "achieved": flops / (lu_ms * 1e-3) / 1e12,
+                          "peak": dmma_peak * world, "unit": "TFLOP/s", "frac": flops / (lu_ms * 1e-3) / 1e12 / (dmma_peak * world),
+                          "peak_source": f"{world} x the DMMA peak measured live on rank 0 (ml_measure_dmma_peak)",
+                          "res_norm": info_lu.res_norm, "max_abs_dx_vs_gmres": float(np.abs(x_lu - x).max())}
+        barrier()
     # ---- reduce over ranks: max time, sum of pairs ---------------------------------------------------
     vals = torch.tensor([step_ms_local, e2e_ms_local, float(np.mean(asm_ms)), float(np.mean(sol_ms)), step_wall_ms_local,
                          e2e_dev_ms_local, gp.gemv_ms, gp.comm_ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -540,7 +562,7 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": dominant,
-            "roofline_other": [other] + ([lu_probe] if lu_probe else []) + ([sup_probe] if sup_probe else []),
+            "roofline_other": [other] + ([lu_probe] if lu_probe else []) + ([sup_probe] if sup_probe else []) + ([lu_sharded] if lu_sharded else []),
             "host_setup_s": dims["host_setup_s"],
             # the `main`-equivalent wall time of SURVEY 8(d) M2: mesh / wake / control points / panel tables on the host, then
             # tables -> device -> assembly -> solve -> x on the host (post-processing and file output excluded)

@@ -65,6 +65,11 @@ int mlh_case_solver_settings(const mlh_case *c, mlh_solver_settings *out);
 /* x[n_unknown] in permuted order, as returned by ml_solve. Result pointers valid until the next
    mlh_case_post or destroy. */
 int mlh_case_post(mlh_case *c, const double *x, mlh_results *out);
+/* The same for the formulations without a prescribed inner flow (neumann-*): v_inner[n_points][3] = the induced velocity
+   (doublet + source, per unit freestream speed) at the points of mlh_case_inner_points -- just inside every panel, where
+   panel_solver_calc_cell_velocities evaluates it (src/panel_solver.f90:2063-2066, 2080-2083).  pts may be NULL to query the count. */
+int mlh_case_inner_points(mlh_case *c, double *pts, int *n_points);
+int mlh_case_post2(mlh_case *c, const double *x, const double *v_inner, mlh_results *out);
 /* Write report.json in the reference's layout (panel_solver.f90:2618-2746) */
 int mlh_case_write_report(mlh_case *c, const char *path, const ml_solve_info *info, int solver_stat,
                           double total_runtime);

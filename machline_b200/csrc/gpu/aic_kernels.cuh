@@ -83,7 +83,9 @@ struct AicSmem {
     static constexpr int total(int R) { return STAGE_OFF + stage_bytes(R) + queue_bytes(R); }
 };
 
-template <bool SUP, int R, int C>
+// VEL: Neumann rows (velocity influences projected on the row's direction, L.row_nB) -- a separate instantiation, so that the
+// Dirichlet kernel carries neither the extra registers nor the branch
+template <bool SUP, int R, int C, bool VEL = false>
 __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_assemble_kernel(const AicLaunch L) {
     using S = AicSmem<SUP, C>;
     constexpr int SUBS = AIC_THREADS / R;   // records evaluated concurrently by the CTA
@@ -126,6 +128,14 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
         const int row = tile * R + row_l;   // < n_rows_pad: the coordinate arrays are padded
         const bool active = (row < L.n_rows) && L.row_active[row];
         const double Px = L.cp_xyz[row], Py = L.cp_xyz[L.n_rows_pad + row], Pz = L.cp_xyz[2 * (size_t)L.n_rows_pad + row];
+        // Neumann rows: the direction of the velocity projection (kernel-uniform choice: all rows of a system are of one kind)
+        double nBv[3] = {0., 0., 0.};
+        if constexpr (VEL) {
+            nBv[0] = L.row_nB[row];
+            nBv[1] = L.row_nB[L.n_rows_pad + row];
+            nBv[2] = L.row_nB[2 * (size_t)L.n_rows_pad + row];
+        }
+        const double* const nB = VEL ? nBv : nullptr;
         if (tid == 0) issue(0);
         double Ik = 0.;
 
@@ -142,7 +152,7 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
                     const int flags = reinterpret_cast<const int*>(rec + R_FLAGS)[0];
                     double ps = 0., pd[3] = {0., 0., 0.};
                     if (active && (flags & RF_EVAL)) {
-                        pair_influence<false>(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, ps, pd);
+                        pair_influence<false>(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, ps, pd, nB);
                         if (flags & RF_SOURCE) Ik = Ik + ps * rec[R_SIGMA];   // panel_solver.f90:1245-1246
                     }
                     double* st = s_stage + (size_t)(r * 3) * R + row_l;
@@ -191,7 +201,7 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
                     const int flags = reinterpret_cast<const int*>(rec + R_FLAGS)[0];
                     const bool e_in[3] = {(e & 0x100u) != 0, (e & 0x200u) != 0, (e & 0x400u) != 0};
                     double ps = 0., pd[3] = {0., 0., 0.};
-                    pair_eval_supersonic(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, e_in, ps, pd);
+                    pair_eval_supersonic(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, e_in, ps, pd, nB);
                     double* st = s_stage + (size_t)(r * 4) * R + row_l;
                     st[0] = pd[0];
                     st[R] = pd[1];
@@ -261,11 +271,11 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
     }
 }
 
-template <bool SUP, int R, int C>
+template <bool SUP, int R, int C, bool VEL = false>
 static cudaError_t launch_aic_t(Ctx* c, const AicLaunch& L) {
     using S = AicSmem<SUP, C>;
     const size_t smem = S::total(R);
-    auto kern = aic_assemble_kernel<SUP, R, C>;
+    auto kern = aic_assemble_kernel<SUP, R, C, VEL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;

@@ -4,6 +4,15 @@
 namespace mlgpu {
 
 cudaError_t launch_aic_supersonic(Ctx* c, const AicLaunch& L) {
+    if (L.row_nB) {   // Neumann rows
+        switch (L.tile_rows) {
+            case 32: return launch_aic_t<true, 32, 64, true>(c, L);
+            case 16: return launch_aic_t<true, 16, 64, true>(c, L);
+            case 8: return launch_aic_t<true, 8, 128, true>(c, L);
+            case 4: return launch_aic_t<true, 4, 128, true>(c, L);
+            default: return cudaErrorInvalidValue;
+        }
+    }
     switch (L.tile_rows) {
         case 32: return launch_aic_t<true, 32, 64>(c, L);
         case 16: return launch_aic_t<true, 16, 64>(c, L);

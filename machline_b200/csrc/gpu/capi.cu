@@ -92,6 +92,7 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
     c->d_wcol.release();
     c->d_zero_cols.release();
     c->d_row_active.release();
+    c->d_row_nB.release();
     c->d_counter.release();
     c->d_sm_rows.release();
     c->d_sm_colp.release();
@@ -191,17 +192,24 @@ extern "C" ml_status ml_set_panels(ml_ctx* c, const ml_panel_soa* body, const ml
 
 extern "C" ml_status ml_set_control_points(ml_ctx* c, int n_cp, const double* loc, const int* bc, const double* n_g,
                                            const int* row_perm) {
-    (void)n_g;
     if (!c || n_cp <= 0 || !loc || !bc || !row_perm) return ML_BAD_ARGUMENT;
     c->n_cp = n_cp;
     c->cp_loc.assign(loc, loc + (size_t)3 * n_cp);
     c->cp_bc.assign(bc, bc + n_cp);
     c->cp_row.assign(row_perm, row_perm + n_cp);
+    c->cp_n_g.clear();
+    int n_neumann = 0;
     for (int i = 0; i < n_cp; ++i) {
         int b = bc[i];
-        if (b != ML_BC_ZERO_POTENTIAL && b != ML_BC_SF_POTENTIAL && b != ML_BC_STRENGTH_MATCHING)
-            return c->fail(ML_UNSUPPORTED, "only Dirichlet and strength-matching control points are supported");
+        if (b == ML_BC_ZERO_NORMAL_MF || b == ML_BC_ZERO_NORMAL_VEL) ++n_neumann;
+        else if (b != ML_BC_ZERO_POTENTIAL && b != ML_BC_SF_POTENTIAL && b != ML_BC_STRENGTH_MATCHING)
+            return c->fail(ML_UNSUPPORTED, "boundary condition not built (Dirichlet, strength matching, zero normal mass flux / velocity are)");
         if (row_perm[i] < 0 || row_perm[i] >= n_cp) return c->fail(ML_BAD_ARGUMENT, "row_perm out of range");
+    }
+    if (n_neumann) {   // Neumann rows (panel_solver.f90:1322-1440): every row needs its normal
+        if (!n_g) return c->fail(ML_BAD_ARGUMENT, "Neumann control points need n_g");
+        if (n_neumann != n_cp) return c->fail(ML_UNSUPPORTED, "Neumann and Dirichlet rows cannot be mixed in one system");
+        c->cp_n_g.assign(n_g, n_g + (size_t)3 * n_cp);
     }
     c->have_cps = true;
     c->dirty = true;
@@ -499,6 +507,10 @@ static ml_status prepare(ml_ctx* c) {
         if (!col_seen[col]) zero_cols.push_back(col);
     c->n_zero_cols = (int)zero_cols.size();
 
+    // Neumann rows: the direction the induced velocity is projected on, n_g (normal velocity) or B_mat_g^T n_g (normal mass flux:
+    // n . (B v) = (B^T n) . v; panel_solver.f90:1335-1336, 1409-1410)
+    const bool velocity_rows = !c->cp_n_g.empty();
+    std::vector<double> nB(velocity_rows ? (size_t)3 * c->n_rows_pad : 0, 0.);
     std::vector<double> xyz((size_t)3 * c->n_rows_pad, 0.);
     std::vector<unsigned char> active(c->n_rows_pad, 0);
     std::vector<int> sm_rows, sm_colp, sm_colm;
@@ -508,6 +520,15 @@ static ml_status prepare(ml_ctx* c) {
         xyz[row] = c->cp_loc[3 * (size_t)i];
         xyz[(size_t)c->n_rows_pad + row] = c->cp_loc[3 * (size_t)i + 1];
         xyz[(size_t)2 * c->n_rows_pad + row] = c->cp_loc[3 * (size_t)i + 2];
+        if (velocity_rows) {
+            const double* n = c->cp_n_g.data() + 3 * (size_t)i;
+            for (int k = 0; k < 3; ++k) {
+                double v = n[k];
+                if (c->cp_bc[i] == ML_BC_ZERO_NORMAL_MF)
+                    v = c->flow.B_mat_g[0 + k] * n[0] + c->flow.B_mat_g[3 + k] * n[1] + c->flow.B_mat_g[6 + k] * n[2];   // (B^T n)_k
+                nB[(size_t)k * c->n_rows_pad + row] = v;
+            }
+        }
         if (c->cp_bc[i] == ML_BC_STRENGTH_MATCHING) {
             int half = c->n_cp / 2;
             if (i - half < 0) return c->fail(ML_BAD_ARGUMENT, "strength-matching control point in the first half");
@@ -523,6 +544,8 @@ static ml_status prepare(ml_ctx* c) {
     ML_CUDA(c, c->d_recs.alloc(recs.size()));
     ML_CUDA(c, c->d_lists.alloc(lists.size()));
     ML_CUDA(c, c->d_cp_xyz.alloc(xyz.size()));
+    c->velocity_rows = velocity_rows;
+    if (velocity_rows) ML_CUDA(c, c->d_row_nB.alloc(nB.size()));
     ML_CUDA(c, c->d_row_active.alloc(active.size()));
     ML_CUDA(c, c->d_counter.alloc(4));
     ML_CUDA(c, c->d_I_known.alloc(c->n_rows_pad));
@@ -539,6 +562,7 @@ static ml_status prepare(ml_ctx* c) {
     ML_CUDA(c, h2d(c->d_recs.p, recs.data(), recs.size() * sizeof(double)));
     ML_CUDA(c, h2d(c->d_lists.p, lists.data(), lists.size()));
     ML_CUDA(c, h2d(c->d_cp_xyz.p, xyz.data(), xyz.size() * sizeof(double)));
+    if (velocity_rows) ML_CUDA(c, h2d(c->d_row_nB.p, nB.data(), nB.size() * sizeof(double)));
     ML_CUDA(c, h2d(c->d_row_active.p, active.data(), active.size()));
     ML_CUDA(c, h2d(c->d_sm_rows.p, sm_rows.data(), sm_rows.size() * sizeof(int)));
     ML_CUDA(c, h2d(c->d_sm_colp.p, sm_colp.data(), sm_rows.size() * sizeof(int)));
@@ -576,6 +600,7 @@ static ml_status run_assembly_kernels(ml_ctx* c) {
     L.tile_rows = c->tile_rows;
     L.cp_xyz = c->d_cp_xyz.p;
     L.row_active = c->d_row_active.p;
+    L.row_nB = c->velocity_rows ? c->d_row_nB.p : nullptr;
     L.n_rows = c->n_rows;
     L.n_rows_pad = c->n_rows_pad;
     L.A = c->d_A.p;

@@ -90,6 +90,7 @@ struct AicLaunch {            // arguments of the assembly kernel (aic_kernels.c
     int tile_rows;            // R: rows owned by one CTA (32, 16 or 8)
     const double* cp_xyz;     // [3][n_rows_pad] control-point coordinates by local row
     const unsigned char* row_active;  // [n_rows_pad] 1: row evaluates influences
+    const double* row_nB;     // nullptr (potential rows) or [3][n_rows_pad]: direction of the velocity projection of each row
     int n_rows, n_rows_pad;   // local rows, padded to 64
     double* A;                // column-major, ld rows
     int ld;
@@ -130,7 +131,8 @@ struct Ctx {
     ml_flow flow{};
     HostPanelTable body, wake;
     int n_cp = 0;
-    std::vector<double> cp_loc;
+    std::vector<double> cp_loc, cp_n_g;   // cp_n_g: empty, or the normals of Neumann rows
+    bool velocity_rows = false;
     std::vector<int> cp_bc, cp_row;
     ml_system_map map{};
     std::vector<int> P, i_sigma_in_sys;
@@ -146,7 +148,7 @@ struct Ctx {
     size_t h_stage_bytes = 0;
 
     // ---- device tables ----
-    DevBuf<double> d_recs, d_cp_xyz, d_A, d_I_known, d_work, d_W;
+    DevBuf<double> d_recs, d_cp_xyz, d_row_nB, d_A, d_I_known, d_work, d_W;
     DevBuf<unsigned char> d_row_active, d_lists;
     DevBuf<int> d_counter, d_sm_rows, d_sm_colp, d_sm_colm, d_wcol, d_zero_cols;
     int n_rec = 0, n_sm_rows = 0;

@@ -1440,10 +1440,143 @@ static ml_status residual(Sys& S, const double* d_x, const double* d_b, ml_solve
     return ML_OK;
 }
 
+// ---- overdetermined least squares (the Neumann formulations; panel_solver.f90:1842-1895) ---------------------------------------
+// C = A^T A for A (m x n, column-major, lda): CTA tile 64 x 64, 256 threads x (4 x 4) outputs, the rows of A walked in chunks of
+// 16 in ascending order (every C entry is summed in row order, as the reference's matmul(transpose(A), A) does).
+__global__ void __launch_bounds__(256) ata_kernel(const double* __restrict__ A, int lda, int m, int n, double* __restrict__ C, int ldc) {
+    __shared__ double sI[16][64 + 1], sJ[16][64 + 1];
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+    const int i0 = blockIdx.x * 64, j0 = blockIdx.y * 64;
+    double acc[4][4] = {};
+    for (int r0 = 0; r0 < m; r0 += 16) {
+        for (int t = threadIdx.x; t < 16 * 64; t += 256) {
+            const int rr = t & 15, cc = t >> 4;
+            const int r = r0 + rr;
+            sI[rr][cc] = (r < m && i0 + cc < n) ? A[r + (size_t)(i0 + cc) * lda] : 0.;
+            sJ[rr][cc] = (r < m && j0 + cc < n) ? A[r + (size_t)(j0 + cc) * lda] : 0.;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int rr = 0; rr < 16; ++rr) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                a[u] = sI[rr][tx + 16 * u];
+                b[u] = sJ[rr][ty + 16 * u];
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int i = i0 + tx + 16 * u, j = j0 + ty + 16 * v;
+            if (i < n && j < n) C[i + (size_t)j * ldc] = acc[u][v];
+        }
+}
+
+// x minimises ||A x - b|| through the normal equations A^T A x = A^T b with the input's preconditioner and solver; the residual
+// reported is that of the original system (panel_solver.f90:1992-1998).  Single GPU.
+static ml_status solve_least_squares(Ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info) {
+    const int N = c->n_cols, M = c->n_cp;
+    if (c->world > 1 || c->n_rows != M) return c->fail(ML_UNSUPPORTED, "least-squares formulations run on one GPU (row shards are not built for them)");
+    if (M < N) return c->fail(ML_UNSUPPORTED, "underdetermined least squares (neumann-doublet-source-mass-flux-ls) is not built");
+    ML_CUDA(c, cudaEventRecord(c->ev0, c->stream));
+    std::vector<double> b(M);
+    for (int i = 0; i < M; ++i) b[i] = BC[i] - c->h_I_known[i];
+    for (int i = 0; i < M; ++i)
+        if (!(b[i] == b[i])) return c->fail(ML_NAN_IN_SYSTEM, "NaN in b");
+    const int ldn = ((N + 63) / 64) * 64;
+    DevBuf<double> d_b, AtA, Atb, d_x, d_scale, Acopy, Ax;
+    ML_CUDA(c, d_b.alloc(c->n_rows_pad));
+    ML_CUDA(c, AtA.alloc((size_t)ldn * N));
+    ML_CUDA(c, Atb.alloc(ldn));
+    ML_CUDA(c, d_x.alloc(ldn));
+    ML_CUDA(c, d_scale.alloc(2));
+    ML_CUDA(c, cudaMemsetAsync(d_b.p, 0, (size_t)c->n_rows_pad * sizeof(double), c->stream));
+    ML_CUDA(c, cudaMemsetAsync(AtA.p, 0, (size_t)ldn * N * sizeof(double), c->stream));
+    ML_CUDA(c, cudaMemcpyAsync(d_b.p, b.data(), (size_t)M * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    c->h2d_bytes += (long long)M * sizeof(double);
+    ata_kernel<<<dim3((N + 63) / 64, (N + 63) / 64), 256, 0, c->stream>>>(c->d_A.p, c->ld, M, N, AtA.p, ldn);
+    gemv_t_kernel<<<N, 256, 0, c->stream>>>(c->d_A.p, c->ld, M, d_b.p, Atb.p);
+    c->launches += 2;
+    Sys S{};
+    S.c = c;
+    S.A = AtA.p;
+    S.ld = ldn;
+    S.n_rows = N;
+    S.n_rows_pad = ldn;
+    S.N = N;
+    S.shard_pad = ldn;
+    ml_status st = S.init();
+    if (st != ML_OK) return st;
+    const double* scale_ptr = nullptr;
+    if (opts->preconditioner == ML_PREC_DIAG) {   // diagonal_preconditioner on A^T A: 1 / (A^T A)(N, N)
+        recip_kernel<<<1, 1, 0, c->stream>>>(AtA.p + (N - 1) + (size_t)(N - 1) * ldn, d_scale.p);
+        c->launches += 1;
+        scale_ptr = d_scale.p;
+    }
+    double* lu_matrix = nullptr;
+    if (needs_whole_matrix(opts->matrix_solver)) {
+        lu_matrix = AtA.p;
+        if (opts->matrix_solver == ML_SOLVER_LU) {
+            ML_CUDA(c, Acopy.alloc((size_t)ldn * N));
+            ML_CUDA(c, cudaMemcpyAsync(Acopy.p, AtA.p, (size_t)ldn * N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+            lu_matrix = Acopy.p;
+        }
+    }
+    st = run_solver(S, opts, Atb.p, scale_ptr, d_x.p, info, lu_matrix, ldn);
+    S.release();
+    if (st != ML_OK) return st;
+    // R = A x - b with the original (rectangular) system
+    Sys R{};
+    R.c = c;
+    R.A = c->d_A.p;
+    R.ld = c->ld;
+    R.n_rows = M;
+    R.n_rows_pad = c->n_rows_pad;
+    R.N = N;
+    R.shard_pad = c->n_rows_pad;
+    st = R.init();
+    if (st != ML_OK) return st;
+    ML_CUDA(c, Ax.alloc(c->n_rows_pad));
+    st = R.gemv_local(d_x.p, Ax.p, 1.0, nullptr);
+    if (st != ML_OK) return st;
+    std::vector<double> hAx(M);
+    ML_CUDA(c, cudaMemcpyAsync(hAx.data(), Ax.p, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaMemcpyAsync(x_out, d_x.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->d2h_bytes += (long long)(M + N) * sizeof(double);
+    R.release();
+    double mx = 0., ss = 0.;
+    for (int i = 0; i < M; ++i) {
+        const double r = hAx[i] - b[i];
+        mx = std::max(mx, std::fabs(r));
+        ss += r * r;
+    }
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->solve_ms = ms;
+    if (info) {
+        info->res_max = mx;
+        info->res_norm = std::sqrt(ss);
+        info->assemble_ms = c->assemble_ms;
+        info->solve_ms = ms;
+    }
+    if (!(ss == ss)) return ML_NAN_RESIDUAL;
+    return ML_OK;
+}
+
 // Solve with the matrix the assembly left resident (possibly row-sharded).
 ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info) {
     const int N = c->n_cols;
-    if (c->n_cp != N) return c->fail(ML_UNSUPPORTED, "only square systems are supported (least-squares formulations are out of scope)");
+    if (c->n_cp != N) return solve_least_squares(c, opts, BC, x_out, info);
     ML_CUDA(c, cudaEventRecord(c->ev0, c->stream));
     Sys S{};
     S.c = c;

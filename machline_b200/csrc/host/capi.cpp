@@ -262,12 +262,27 @@ extern "C" int mlh_case_solver_settings(const mlh_case* h, mlh_solver_settings* 
     return 0;
 }
 
-extern "C" int mlh_case_post(mlh_case* h, const double* x, mlh_results* out) {
+extern "C" int mlh_case_inner_points(mlh_case* h, double* pts, int* n_points) {
+    if (!h || !n_points) return 1;
+    try {
+        std::vector<double> p = h->c.inner_points();
+        *n_points = (int)(p.size() / 3);
+        if (pts) std::memcpy(pts, p.data(), p.size() * sizeof(double));
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+extern "C" int mlh_case_post(mlh_case* h, const double* x, mlh_results* out) { return mlh_case_post2(h, x, nullptr, out); }
+
+extern "C" int mlh_case_post2(mlh_case* h, const double* x, const double* v_inner, mlh_results* out) {
     if (!h || !x || !out) return 1;
     try {
         const Case& c = h->c;
         std::vector<double> xv(x, x + c.N_unknown);
-        h->last = c.post(xv);
+        h->last = c.post(xv, v_inner);
         const Results& R = h->last;
         const std::vector<double>& rep = c.solver.incompressible_rule ? R.C_p_inc : R.C_p_ise;
         h->res_cp = rep;

@@ -210,7 +210,8 @@ struct Case {
         pre_solve();
     }
     // x -> mu, sigma; cell velocities, pressures, forces, moments (panel_solver.f90:2012-2615)
-    Results post(const std::vector<double>& x) const;
+    Results post(const std::vector<double>& x, const double* v_inner = nullptr) const;
+    std::vector<double> inner_points() const;
 
     // ---- pieces (public for tests) ----
     void load_mesh_file(const std::string& file);
@@ -223,6 +224,8 @@ struct Case {
     void clone_vertices();
     void init_wake();
     void place_internal_vertex_control_points(double offset, const std::string& offset_type);
+    void place_centroid_control_points(double offset);
+    void init_neumann();
     void set_permutation();
     bool is_convex_at_vertex(int i_vert) const;
     V3 get_clone_control_point_dir(int i_vert) const;

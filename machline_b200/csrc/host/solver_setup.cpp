@@ -244,6 +244,36 @@ void Case::place_internal_vertex_control_points(double offset, const std::string
     }
 }
 
+// surface_mesh_place_centroid_control_points (src/surface_mesh.f90:1895-1981): one control point per panel at its centroid,
+// moved by `offset` along the panel normal (0: on the surface, > 0: outside); mirrored copies for an asymmetric flow.
+void Case::place_centroid_control_points(double offset) {
+    if (asym_flow) {
+        for (int i = 0; i < N_verts; ++i)
+            if (vertices[i].on_mirror_plane && !vertices[i].mirrored_is_unique)
+                throw std::runtime_error("Neumann formulations on a mirrored mesh in an asymmetric flow with vertices on the mirror plane "
+                                         "(strength-matching control points) are not supported");
+    }
+    N_cp = asym_flow ? N_panels * 2 : N_panels;
+    cp.assign(N_cp, ControlPoint());
+    for (int i = 0; i < N_panels; ++i) {
+        cp[i].loc = panels[i].centr + panels[i].n_g * offset;      // get_cp_locs_centroid_based, :1772-1793
+        cp[i].cp_type = offset == 0. ? 2 : (offset > 0. ? 3 : 1);   // SURFACE / EXTERNAL / INTERNAL
+        cp[i].tied_to_type = TT_PANEL;
+        cp[i].tied_to_index = i;
+        cp[i].is_mirror = false;
+    }
+    if (asym_flow) {
+        for (int i = 0; i < N_panels; ++i) {
+            ControlPoint& m = cp[i + N_panels];
+            m.loc = mirror_across_plane(cp[i].loc, mirror_plane);
+            m.cp_type = cp[i].cp_type;
+            m.tied_to_type = TT_PANEL;
+            m.tied_to_index = i;
+            m.is_mirror = true;
+        }
+    }
+}
+
 // panel_solver.f90:778-1030
 void Case::set_permutation() {
     auto t0 = std::chrono::steady_clock::now();
@@ -309,9 +339,12 @@ void Case::init_solver() {
     const std::string& f = solver.formulation;
     if (f == "dirichlet-morino" || f == "dirichlet-source-free") {
         solver.dirichlet = true;
-    } else if (f == "neumann-mass-flux" || f == "neumann-velocity" || f == "neumann-doublet-source-mass-flux-ls" ||
-               f == "neumann-mass-flux-inner-flow" || f == "neumann-doublet-only-mass-flux") {
-        throw std::runtime_error("Neumann formulations are outside the round-1 hot-path scope (SURVEY 8f rank 3)");
+    } else if (f == "neumann-mass-flux" || f == "neumann-velocity") {
+        solver.dirichlet = false;
+        init_neumann();
+        return;
+    } else if (f == "neumann-doublet-source-mass-flux-ls" || f == "neumann-mass-flux-inner-flow" || f == "neumann-doublet-only-mass-flux") {
+        throw std::runtime_error("'" + f + "': only the least-squares Neumann formulations neumann-mass-flux and neumann-velocity are built");
     } else {
         throw std::runtime_error("'" + f + "' is not a valid formulation.");
     }
@@ -361,6 +394,29 @@ void Case::init_solver() {
             }
         }
         cp[i].bc = (f == "dirichlet-morino") ? BC_ZERO_POTENTIAL : BC_SF_POTENTIAL;
+    }
+    set_permutation();
+}
+
+// init_neumann (panel_solver.f90:367-420) for the two overdetermined least-squares formulations: control points at (above) the
+// panel centroids, no sources on subinclined panels (:436-440), one doublet unknown per vertex (:515-563), the panel normal as
+// the direction of the condition (:567-598), no sorting (:192-196).
+void Case::init_neumann() {
+    const std::string& f = solver.formulation;
+    place_centroid_control_points(f == "neumann-mass-flux" ? 0. : solver.control_point_offset);
+    for (auto& p : panels) p.has_sources = (p.r < 0);
+    N_sigma = asym_flow ? N_panels * 2 : N_panels;
+    N_d_unknown = asym_flow ? N_verts * 2 : N_verts;
+    sigma_known.assign(N_sigma, 1);
+    N_s_unknown = 0;
+    i_sigma_in_sys.assign(N_sigma, -1);
+    i_sys_sigma_in_body.clear();
+    N_unknown = N_d_unknown;
+    inner_flow = freestream.c_hat_g;
+    for (int i = 0; i < N_cp; ++i) {
+        cp[i].bc = (f == "neumann-velocity") ? BC_ZERO_NORMAL_VEL : BC_ZERO_NORMAL_MF;
+        const Panel& p = panels[cp[i].tied_to_index];
+        cp[i].n_g = cp[i].is_mirror ? p.n_g_mir : p.n_g;
     }
     set_permutation();
 }
@@ -427,8 +483,28 @@ V3 panel_get_velocity_jump(const Panel& p, const Case& c, const std::vector<doub
     return dv;
 }
 
+// The points just inside every panel (and its mirror image in an asymmetric flow) where calc_cell_velocities evaluates the
+// induced velocity for the non-Dirichlet formulations: P = centr - 1e-10 n_g (panel_solver.f90:2063, 2080)
+std::vector<double> Case::inner_points() const {
+    const int n_cells = asym_flow ? 2 * N_panels : N_panels;
+    std::vector<double> pts((size_t)3 * n_cells);
+    for (int i = 0; i < N_panels; ++i) {
+        V3 P = panels[i].centr - 1.e-10 * panels[i].n_g;
+        for (int k = 0; k < 3; ++k) pts[3 * (size_t)i + k] = P[k];
+        if (asym_flow) {
+            V3 Pm = mirror_across_plane(P, mirror_plane);
+            for (int k = 0; k < 3; ++k) pts[3 * (size_t)(i + N_panels) + k] = Pm[k];
+        }
+    }
+    return pts;
+}
+
 // panel_solver.f90:2012-2615 (lower-order path)
-Results Case::post(const std::vector<double>& x) const {
+Results Case::post(const std::vector<double>& x, const double* v_inner) const {
+    // v_inner: [N_cells][3] induced velocity (v_d + v_s, per unit freestream speed) just inside every panel, needed by the
+    // formulations without a prescribed inner flow (panel_solver.f90:2063-2066); nullptr for the Dirichlet formulations
+    if (!solver.dirichlet && !v_inner)
+        throw std::runtime_error("post-processing of a Neumann formulation needs the induced velocities at Case::inner_points()");
     Results R;
     R.mu.assign(asym_flow ? N_verts * 2 : N_verts, 0.);
     for (int i = 0; i < N_d_unknown; ++i) R.mu[i] = x[P[i]];
@@ -441,10 +517,15 @@ Results Case::post(const std::vector<double>& x) const {
     R.V_cells_inner.assign(R.N_cells, V3{});
     for (int i = 0; i < N_panels; ++i) {  // calc_cell_velocities :2030-2095
         R.V_cells_inner[i] = inner_flow * fs.U;
+        if (!solver.dirichlet) R.V_cells_inner[i] = fs.v_inf + fs.U * V3{v_inner[3 * i], v_inner[3 * i + 1], v_inner[3 * i + 2]};
         V3 dv = panel_get_velocity_jump(panels[i], *this, R.mu, R.sigma, false);
         R.V_cells[i] = fs.U * ((R.V_cells_inner[i] / fs.U) + dv);
         if (asym_flow) {
             R.V_cells_inner[i + N_panels] = inner_flow * fs.U;
+            if (!solver.dirichlet) {
+                const double* v = v_inner + 3 * (size_t)(i + N_panels);
+                R.V_cells_inner[i + N_panels] = fs.v_inf + fs.U * V3{v[0], v[1], v[2]};
+            }
             V3 dvm = panel_get_velocity_jump(panels[i], *this, R.mu, R.sigma, true);
             R.V_cells[i + N_panels] = fs.U * ((R.V_cells_inner[i + N_panels] / fs.U) + dvm);
         }

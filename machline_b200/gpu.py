@@ -118,7 +118,7 @@ class Context:
         self.row0, self.nrows = row0, nrows
         self.local_rows = np.arange(row0, row0 + nrows, dtype=np.int32)
 
-    def set_points(self, case, points: np.ndarray):
+    def set_points(self, case, points: np.ndarray, direction=None):
         """Stage `case` with the rows of the system replaced by arbitrary field points (boundary condition "zero
         potential", no sorting): ml_assemble then builds the influence matrix of every unknown on those points, which is
         what the reference's off-body sweep evaluates (surface_mesh_get_induced_potentials_at_point,
@@ -127,6 +127,10 @@ class Context:
         pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
         n = pts.shape[0]
         bc = np.full(n, 1, dtype=np.int32)            # ML_BC_ZERO_POTENTIAL
+        n_g = None
+        if direction is not None:                     # rows = the induced velocity along `direction` (ML_BC_ZERO_NORMAL_VEL)
+            bc[:] = 5
+            n_g = np.ascontiguousarray(np.tile(np.asarray(direction, dtype=np.float64), (n, 1)))
         rows = np.arange(n, dtype=np.int32)
         m = _abi.MlSystemMap()
         C.memmove(C.byref(m), C.byref(case.map), C.sizeof(m))
@@ -134,7 +138,7 @@ class Context:
         self._check(L.ml_set_flow(self._h, C.byref(case.flow)))
         wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
         self._check(L.ml_set_panels(self._h, C.byref(case.body), wake))
-        self._check(L.ml_set_control_points(self._h, n, _dp(pts), bc.ctypes.data_as(_abi.c_int_p), None,
+        self._check(L.ml_set_control_points(self._h, n, _dp(pts), bc.ctypes.data_as(_abi.c_int_p), _dp(n_g) if n_g is not None else None,
                                             rows.ctypes.data_as(_abi.c_int_p)))
         self._check(L.ml_set_system_map(self._h, C.byref(m)))
         self._check(L.ml_set_row_shard(self._h, 0, n))
@@ -150,6 +154,20 @@ class Context:
         phi_s = self.assemble()
         phi_d = self.get_A() @ np.asarray(x, dtype=np.float64)
         return phi_d, phi_s
+
+    def velocities_at(self, case, points: np.ndarray, x: np.ndarray) -> np.ndarray:
+        """Induced velocity v_d + v_s at `points` (per unit freestream speed) from the solved strengths x: three assemblies with
+        the field points as rows and the unit vectors as projection directions (the kernels of the Neumann rows), what
+        surface_mesh_get_induced_velocities_at_point sums panel by panel (src/surface_mesh.f90:2388-2500)."""
+        x = np.asarray(x, dtype=np.float64)
+        v = np.zeros((len(points), 3))
+        for k in range(3):
+            e = np.zeros(3)
+            e[k] = 1.0
+            self.set_points(case, points, direction=e)
+            v_s = self.assemble()
+            v[:, k] = self.get_A() @ x + v_s
+        return v
 
     def set_communicator(self, unique_id: bytes, rank: int, world: int):
         buf = C.create_string_buffer(unique_id, len(unique_id))

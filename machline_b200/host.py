@@ -40,6 +40,8 @@ def lib() -> C.CDLL:
                                       C.POINTER(_abi.MlhCpTable)]
         L.mlh_case_solver_settings.argtypes = [C.c_void_p, C.POINTER(_abi.MlhSolverSettings)]
         L.mlh_case_post.argtypes = [C.c_void_p, _abi.c_double_p, C.POINTER(_abi.MlhResults)]
+        L.mlh_case_post2.argtypes = [C.c_void_p, _abi.c_double_p, _abi.c_double_p, C.POINTER(_abi.MlhResults)]
+        L.mlh_case_inner_points.argtypes = [C.c_void_p, _abi.c_double_p, C.POINTER(C.c_int)]
         L.mlh_case_write_report.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_abi.MlSolveInfo), C.c_int,
                                             C.c_double]
         _lib = L
@@ -124,11 +126,31 @@ class Case:
         C.memmove(C.byref(o), C.byref(self.settings.opts), C.sizeof(o))
         return o
 
-    def post(self, x: np.ndarray) -> Results:
+    @property
+    def dirichlet(self) -> bool:
+        return str(self.input.get("solver", {}).get("formulation", "dirichlet-morino")).startswith("dirichlet")
+
+    def inner_points(self) -> np.ndarray:
+        """The points just inside every panel where the non-Dirichlet formulations evaluate the induced velocity
+        (panel_solver_calc_cell_velocities, src/panel_solver.f90:2063, 2080)."""
+        n = C.c_int()
+        lib().mlh_case_inner_points(self._h, None, C.byref(n))
+        pts = np.zeros((n.value, 3), dtype=np.float64)
+        if lib().mlh_case_inner_points(self._h, pts.ctypes.data_as(_abi.c_double_p), C.byref(n)) != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+        return pts
+
+    def post(self, x: np.ndarray, v_inner: np.ndarray | None = None) -> Results:
+        """Post-processing of the solved strengths x.  Neumann formulations need v_inner = the induced velocity (per unit
+        freestream speed) at inner_points() -- gpu.Context.velocities_at(case, case.inner_points(), x)."""
         x = np.ascontiguousarray(x, dtype=np.float64)
         assert x.shape == (self.n_unknown,)
         r = _abi.MlhResults()
-        rc = lib().mlh_case_post(self._h, x.ctypes.data_as(_abi.c_double_p), C.byref(r))
+        vp = None
+        if v_inner is not None:
+            v_inner = np.ascontiguousarray(v_inner, dtype=np.float64)
+            vp = v_inner.ctypes.data_as(_abi.c_double_p)
+        rc = lib().mlh_case_post2(self._h, x.ctypes.data_as(_abi.c_double_p), vp, C.byref(r))
         if rc != 0:
             raise MachLineError(lib().mlh_last_error().decode())
         return Results(

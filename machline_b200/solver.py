@@ -48,7 +48,8 @@ def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None
         if case.settings.write_A_and_b:           # panel_solver.f90:1834, before the solve; files in the working directory
             vtk_out.write_system(ctx.get_A(), np.asarray(case.BC) - I_known)
         x, info = ctx.solve(opts, case.BC)
-        res = case.post(x)
+        v_inner = None if case.dirichlet else ctx.velocities_at(case, case.inner_points(), x)   # panel_solver.f90:2063-2066
+        res = case.post(x, v_inner)
         total = time.perf_counter() - t0
         if report_file is None:
             report_file = case.input.get("output", {}).get("report_file")

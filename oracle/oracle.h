@@ -14,6 +14,9 @@ typedef struct orc_pair_out {
     double phi_s;      /* source influence (S space, S_dim = 1)      */
     double phi_d[3];   /* doublet influences (M space, M_dim = 3)    */
     double phi_d_abs[3]; /* sum of |terms| behind phi_d[c]: the scale of its rounding noise (tests only) */
+    double v_s[3];     /* source-induced velocity influence, global coordinates (S_dim = 1; panel.f90:3011-3075)   */
+    double v_d[9];     /* doublet-induced velocity influences, global coordinates, v_d[3 * i + c] = component i of */
+                       /* column c (M_dim = 3; panel.f90:3078-3170)                                                 */
 } orc_pair_out;
 
 /* tests only: log/atan2 through binary128, rounded once (noise-floor calibration) */
@@ -28,6 +31,12 @@ int orc_assemble(const ml_flow *fs, const ml_panel_soa *body, const ml_panel_soa
                  int n_cp, const double *cp_loc, const int *cp_bc, const int *row_perm, int row0, int nrows,
                  double *A_colmajor, int ld, double *I_known, int n_threads,
                  double *A_abs /* NULL or same layout: per entry, the sum of |panel contributions| */);
+
+/* The same with the Neumann rows of panel_solver.f90:1322-1440 / 1570-1650: cp_n_g[n_cp][3] are the control points' normals
+   (boundary conditions ML_BC_ZERO_NORMAL_MF: n . B v, ML_BC_ZERO_NORMAL_VEL: n . v). */
+int orc_assemble_n(const ml_flow *fs, const ml_panel_soa *body, const ml_panel_soa *wake, const ml_system_map *map,
+                   int n_cp, const double *cp_loc, const int *cp_bc, const double *cp_n_g, const int *row_perm, int row0,
+                   int nrows, double *A_colmajor, int ld, double *I_known, int n_threads, double *A_abs);
 
 /* common/linalg.f90 solvers on a host system; A is column-major N x N and is overwritten the way
    the reference overwrites A_p.  Returns ml_status. */
@@ -53,6 +62,12 @@ void orc_set_threads(int n);
    column-major) is not modified. */
 int orc_solve_system(int N, const double *A, const double *I_known, const double *BC, const ml_solver_opts *opts,
                      double *x, ml_solve_info *info);
+
+/* The overdetermined least-squares branch (panel_solver.f90:1842-1895: neumann-mass-flux / neumann-velocity): A is n_cp x N
+   column-major (leading dimension n_cp); the normal equations A^T A x = A^T b go through the same preconditioner and solvers;
+   the residual is that of the original system. */
+int orc_solve_system_ls(int n_cp, int N, const double *A, const double *I_known, const double *BC, const ml_solver_opts *opts,
+                        double *x, ml_solve_info *info);
 
 #ifdef __cplusplus
 }

@@ -400,6 +400,33 @@ extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int
         for (int k = 0; k < 3; ++k) acc = acc + m[k] * p.T[3 * k + c];
         out->phi_d[c] = I.s * fs->K_inv * acc;
     }
+    // assemble_v_s_S_space (order 1), panel.f90:3029-3072: local (r H213, s H123, -rs hH113), times -K_inv J, to global
+    {
+        double vl[3] = {I.r * I.H213, I.s * I.H123, -I.rs * I.hH113};
+        for (int k = 0; k < 3; ++k) vl[k] = has_src ? -vl[k] * fs->K_inv * p.J : 0.;
+        for (int i = 0; i < 3; ++i) {   // matmul(transpose(A_g_to_ls), v)
+            double acc = 0.;
+            for (int k = 0; k < 3; ++k) acc = acc + p.A[3 * k + i] * vl[k];
+            out->v_s[i] = acc;
+        }
+    }
+    // assemble_v_d_M_space (order 1), panel.f90:3118-3166
+    {
+        double vmu[9] = {0., I.hH113, 0., 0., 0., I.hH113, 0., I.H213, I.H123};   // row-major 3 x mu_dim
+        double vM[9];
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c) {
+                double acc = 0.;
+                for (int k = 0; k < 3; ++k) acc = acc + vmu[3 * i + k] * p.T[3 * k + c];
+                vM[3 * i + c] = I.s * fs->K_inv * acc;
+            }
+        for (int i = 0; i < 3; ++i)
+            for (int c = 0; c < 3; ++c) {
+                double acc = 0.;
+                for (int k = 0; k < 3; ++k) acc = acc + p.A[3 * k + i] * vM[3 * k + c];
+                out->v_d[3 * i + c] = acc;
+            }
+    }
     // magnitude of the terms that were summed into phi_d[c] (forward-error scale, tests only)
     double ma[3];
     double s2a = 0., s3a = 0.;
@@ -444,6 +471,30 @@ extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const m
                             const ml_system_map* map, int n_cp, const double* cp_loc, const int* cp_bc,
                             const int* row_perm, int row0, int nrows, double* A, int ld, double* I_known,
                             int n_threads, double* A_abs) {
+    return orc_assemble_n(fs, body, wake, map, n_cp, cp_loc, cp_bc, nullptr, row_perm, row0, nrows, A, ld, I_known, n_threads, A_abs);
+}
+
+// source_inf = matmul(n_g, matmul(B_mat_g, v_s)) / matmul(n_g, v_s)  (panel_solver.f90:1335-1336, 1409-1410)
+static double project_velocity(const ml_flow* fs, const double* n_g, const double* v, int stride, bool mass_flux) {
+    double w[3];
+    for (int i = 0; i < 3; ++i) {
+        if (mass_flux) {
+            double acc = 0.;
+            for (int k = 0; k < 3; ++k) acc = acc + fs->B_mat_g[3 * i + k] * v[k * stride];
+            w[i] = acc;
+        } else {
+            w[i] = v[i * stride];
+        }
+    }
+    double acc = 0.;
+    for (int i = 0; i < 3; ++i) acc = acc + n_g[i] * w[i];
+    return acc;
+}
+
+extern "C" int orc_assemble_n(const ml_flow* fs, const ml_panel_soa* body, const ml_panel_soa* wake,
+                              const ml_system_map* map, int n_cp, const double* cp_loc, const int* cp_bc, const double* cp_n_g,
+                              const int* row_perm, int row0, int nrows, double* A, int ld, double* I_known,
+                              int n_threads, double* A_abs) {
     const int N_unknown = map->n_unknown, N_panels = map->n_body_panels, N_verts = map->n_verts;
     const int* P = map->P;
     if (n_threads <= 0) n_threads = omp_get_max_threads();
@@ -486,18 +537,54 @@ extern "C" int orc_assemble(const ml_flow* fs, const ml_panel_soa* body, const m
                     }
                 }
             }
+        } else if ((cp_bc[i] == ML_BC_ZERO_NORMAL_MF || cp_bc[i] == ML_BC_ZERO_NORMAL_VEL) && cp_n_g) {
+            // Neumann rows, panel_solver.f90:1322-1440: normal mass flux n . B v or normal velocity n . v
+            const bool mf = cp_bc[i] == ML_BC_ZERO_NORMAL_MF;
+            const double* n_g = cp_n_g + 3 * (size_t)i;
+            for (int j = 0; j < N_panels; ++j) {
+                for (int img = 0; img < body->n_images; ++img) {
+                    orc_pair_out o;
+                    orc_pair_influence(fs, body, j, img, Pt, &o);
+                    if (!o.in_dod) continue;
+                    bool mirrored_panel = (img == 1) && map->asym_flow;
+                    if (body->has_sources[j]) {
+                        const double source_inf = project_velocity(fs, n_g, o.v_s, 1, mf);
+                        int ips = body->i_panel_s[j];
+                        int index;
+                        if (mirrored_panel) index = (ips >= N_panels) ? ips - N_panels : ips + N_panels;
+                        else index = (ips >= N_panels) ? ips - N_panels : ips;
+                        if (map->sigma_known[index]) I_known_i = I_known_i + source_inf * map->sigma[index];
+                        else A_i[P[map->i_sigma_in_sys[index]]] += source_inf;
+                    }
+                    for (int k = 0; k < 3; ++k) {
+                        const double doublet_inf = project_velocity(fs, n_g, o.v_d + k, 3, mf);
+                        int iv = body->i_vert_d[(size_t)j * body->n_cols + k];
+                        int index;
+                        if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
+                        else index = (iv >= N_verts) ? iv - N_verts : iv;
+                        A_i[P[index]] = A_i[P[index]] + doublet_inf;
+                        if (A_abs) S_i[P[index]] += std::fabs(doublet_inf);
+                    }
+                }
+            }
         } else {
 #pragma omp critical
             status = ML_UNSUPPORTED;
         }
         // wake pass (panel_solver.f90:1650-1697): a separate row accumulated from zero, then added
         if (wake && wake->n_panels > 0 && cp_bc[i] != ML_BC_STRENGTH_MATCHING) {
+            const bool neumann = (cp_bc[i] == ML_BC_ZERO_NORMAL_MF || cp_bc[i] == ML_BC_ZERO_NORMAL_VEL) && cp_n_g;
             std::vector<double> W_i(N_unknown, 0.);
             for (int l = 0; l < wake->n_panels; ++l) {
                 for (int img = 0; img < wake->n_images; ++img) {
                     if (img == 1 && !(wake->image_present && wake->image_present[l])) continue;
                     orc_pair_out o;
                     orc_pair_influence(fs, wake, l, img, Pt, &o);
+                    if (neumann) {   // panel_solver.f90:1530-1566, 1612-1650: the doublet velocity influences, projected
+                        for (int c = 0; c < 3; ++c)
+                            o.phi_d[c] = o.in_dod ? project_velocity(fs, cp_n_g + 3 * (size_t)i, o.v_d + c, 3, cp_bc[i] == ML_BC_ZERO_NORMAL_MF) : 0.;
+                        for (int c = 0; c < 3; ++c) o.phi_d_abs[c] = std::fabs(o.phi_d[c]);
+                    }
                     // in_dod = false leaves zeros (panel.f90:2959-2967), which are still "added"
                     for (int k = 0; k < 6; ++k) {
                         int iv = wake->i_vert_d[(size_t)l * wake->n_cols + k];

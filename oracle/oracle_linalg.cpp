@@ -626,3 +626,43 @@ extern "C" int orc_solve_system(int N, const double* A, const double* I_known, c
     if (std::isnan(std::sqrt(ss))) return ML_NAN_RESIDUAL;
     return 0;
 }
+
+// panel_solver.f90:1842-1895, overdetermined least squares: A_p = diagonal_preconditioner(matmul(transpose(A), A)),
+// b_p likewise from matmul(transpose(A), b); the residual is A x - b of the original system (:1992-1998)
+extern "C" int orc_solve_system_ls(int n_cp, int N, const double* A, const double* I_known, const double* BC, const ml_solver_opts* opts,
+                                   double* x, ml_solve_info* info) {
+    std::vector<double> b(n_cp), AtA((size_t)N * N), Atb(N);
+    for (int i = 0; i < n_cp; ++i) b[i] = BC[i] - (I_known ? I_known[i] : 0.);
+#pragma omp parallel for schedule(static)
+    for (int j = 0; j < N; ++j) {
+        const double* aj = A + (size_t)j * n_cp;
+        for (int i = 0; i < N; ++i) {
+            const double* ai = A + (size_t)i * n_cp;
+            double acc = 0.;
+            for (int r = 0; r < n_cp; ++r) acc = acc + ai[r] * aj[r];
+            AtA[i + (size_t)j * N] = acc;
+        }
+        double acc = 0.;
+        for (int r = 0; r < n_cp; ++r) acc = acc + aj[r] * b[r];
+        Atb[j] = acc;
+    }
+    ml_solve_info tmp{};
+    std::vector<double> zero(N, 0.);
+    int st = orc_solve_system(N, AtA.data(), zero.data(), Atb.data(), opts, x, &tmp);
+    if (st && st != ML_NAN_RESIDUAL) return st;
+    double mx = 0., ss = 0.;
+    for (int r = 0; r < n_cp; ++r) {
+        double acc = 0.;
+        for (int j = 0; j < N; ++j) acc = acc + A[r + (size_t)j * n_cp] * x[j];
+        const double R = acc - b[r];
+        mx = std::max(mx, std::fabs(R));
+        ss += R * R;
+    }
+    if (info) {
+        info->iterations = tmp.iterations;
+        info->res_max = mx;
+        info->res_norm = std::sqrt(ss);
+    }
+    if (std::isnan(std::sqrt(ss))) return ML_NAN_RESIDUAL;
+    return 0;
+}

@@ -177,6 +177,10 @@ GOLDENS = [
          tol=[1e-12, 1e-12, 1e-12, 1e-12, 1e-10]),
     dict(name="test_19", lines="612-625", input="fuselage_input.json", alter=[],
          expect=[0.955084903205978, -0.574040916470699, 0.0, 0.0, 0.0], tol=[1e-12, 1e-12, 2.1e-3, 2.1e-3, 2.1e-3]),
+    dict(name="test_21", lines="610-633", input="supersonic_full_wing_input.json",
+         alter=[["solver.formulation", "neumann-mass-flux"], ["solver.matrix_solver", "GMRES"]],
+         expect=[0.205581816085009, -0.265679125725778, 0.0721530311378978, 0.0, 0.431906841113295],
+         tol=[1e-9, 1e-9, 1e-9, 1e-11, 1e-9]),
     dict(name="test_20", lines="628-641", input="supersonic_full_wing_input.json", alter=[],
          expect=[0.194950351346633, -0.324945660429385, 0.0718540012154408, 0.0, 0.429236847680447],
          tol=[1e-12, 1e-12, 1e-12, 1e-11, 1e-12]),

@@ -26,7 +26,7 @@ class OrcPairOut(C.Structure):
     _fields_ = [("in_dod", C.c_int), ("edges_in_dod", C.c_int * 3), ("F111", C.c_double * 3),
                 ("hH113", C.c_double), ("H111", C.c_double), ("H213", C.c_double), ("H123", C.c_double),
                 ("h", C.c_double), ("phi_s", C.c_double), ("phi_d", C.c_double * 3),
-                ("phi_d_abs", C.c_double * 3)]
+                ("phi_d_abs", C.c_double * 3), ("v_s", C.c_double * 3), ("v_d", C.c_double * 9)]
 
 
 _lib = None
@@ -46,6 +46,10 @@ def lib() -> C.CDLL:
         L.orc_assemble.argtypes = [C.POINTER(_abi.MlFlow), C.POINTER(_abi.MlPanelSoa), C.POINTER(_abi.MlPanelSoa),
                                    C.POINTER(_abi.MlSystemMap), C.c_int, dp, ip, ip, C.c_int, C.c_int, dp, C.c_int,
                                    dp, C.c_int, dp]
+        L.orc_assemble_n.argtypes = [C.POINTER(_abi.MlFlow), C.POINTER(_abi.MlPanelSoa), C.POINTER(_abi.MlPanelSoa),
+                                     C.POINTER(_abi.MlSystemMap), C.c_int, dp, ip, dp, ip, C.c_int, C.c_int, dp, C.c_int,
+                                     dp, C.c_int, dp]
+        L.orc_solve_system_ls.argtypes = [C.c_int, C.c_int, dp, dp, dp, C.POINTER(_abi.MlSolverOpts), dp, C.POINTER(_abi.MlSolveInfo)]
         L.orc_lu_solve.argtypes = [C.c_int, dp, dp, dp]
         L.orc_gmres.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, ip, dp, dp]
         L.orc_restarted_gmres.argtypes = [C.c_int, dp, dp, C.c_double, C.c_int, C.c_int, ip, dp]
@@ -81,9 +85,9 @@ def assemble(case, row0: int = 0, nrows: int | None = None, n_threads: int = 0, 
     I_known = np.zeros(nrows, dtype=np.float64)
     wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
     S = np.zeros((nrows, n_u), dtype=np.float64, order="F") if with_scale else None
-    st = lib().orc_assemble(C.byref(case.flow), C.byref(case.body), wake, C.byref(case.map), n_cp, case.cps.loc,
-                            case.cps.bc, case.cps.row_perm, row0, nrows, _dp(A), max(1, nrows), _dp(I_known), n_threads,
-                            _dp(S) if with_scale else None)
+    st = lib().orc_assemble_n(C.byref(case.flow), C.byref(case.body), wake, C.byref(case.map), n_cp, case.cps.loc,
+                              case.cps.bc, case.cps.n_g, case.cps.row_perm, row0, nrows, _dp(A), max(1, nrows), _dp(I_known), n_threads,
+                              _dp(S) if with_scale else None)
     if st != 0:
         raise RuntimeError(f"orc_assemble status {st}")
     if with_scale:
@@ -108,6 +112,28 @@ def assemble_at_points(case, points, with_wake: bool = True):
     return A, I_known
 
 
+def velocities_at(case, points, x):
+    """Oracle: induced velocity v_d + v_s (per unit freestream speed) at field points from the solved strengths x."""
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    n = pts.shape[0]
+    bc = np.full(n, 5, dtype=np.int32)
+    rows = np.arange(n, dtype=np.int32)
+    wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
+    v = np.zeros((n, 3))
+    for k in range(3):
+        n_g = np.zeros((n, 3))
+        n_g[:, k] = 1.0
+        A = np.zeros((n, case.n_unknown), dtype=np.float64, order="F")
+        I_known = np.zeros(n, dtype=np.float64)
+        st = lib().orc_assemble_n(C.byref(case.flow), C.byref(case.body), wake, C.byref(case.map), n, _dp(pts),
+                                  bc.ctypes.data_as(_abi.c_int_p), _dp(n_g), rows.ctypes.data_as(_abi.c_int_p), 0, n, _dp(A), n,
+                                  _dp(I_known), 0, None)
+        if st != 0:
+            raise RuntimeError(f"orc_assemble_n status {st}")
+        v[:, k] = A @ np.asarray(x, dtype=np.float64) + I_known
+    return v
+
+
 def pair(case, table, j: int, img: int, P) -> OrcPairOut:
     out = OrcPairOut()
     Pa = np.ascontiguousarray(P, dtype=np.float64)
@@ -117,13 +143,16 @@ def pair(case, table, j: int, img: int, P) -> OrcPairOut:
 
 def solve_system(A, I_known, BC, opts):
     """panel_solver_solve_system on the CPU.  Returns (x, MlSolveInfo)."""
-    N = A.shape[0]
+    n_cp, N = A.shape
     A = np.asfortranarray(A, dtype=np.float64)
     x = np.zeros(N)
     info = _abi.MlSolveInfo()
     I_known = np.ascontiguousarray(I_known, dtype=np.float64)
     BC = np.ascontiguousarray(BC, dtype=np.float64)
-    st = lib().orc_solve_system(N, _dp(A), _dp(I_known), _dp(BC), C.byref(opts), _dp(x), C.byref(info))
+    if n_cp != N:    # overdetermined least squares (the Neumann formulations), panel_solver.f90:1842-1895
+        st = lib().orc_solve_system_ls(n_cp, N, _dp(A), _dp(I_known), _dp(BC), C.byref(opts), _dp(x), C.byref(info))
+    else:
+        st = lib().orc_solve_system(N, _dp(A), _dp(I_known), _dp(BC), C.byref(opts), _dp(x), C.byref(info))
     if st != 0:
         raise RuntimeError(f"orc_solve_system status {st}")
     return x, info
@@ -133,4 +162,5 @@ def run_case(case):
     """Full CPU pipeline: host setup (already done in `case`) -> oracle assemble -> oracle solve -> host post."""
     A, I_known = assemble(case)
     x, info = solve_system(A, I_known, case.BC, case.solver_opts())
-    return case.post(x), info, A
+    v_inner = None if case.dirichlet else velocities_at(case, case.inner_points(), x)
+    return case.post(x, v_inner), info, A

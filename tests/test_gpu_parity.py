@@ -101,7 +101,9 @@ def test_reference_goldens_through_gpu(ctx, name):
     ctx.set_case(case)
     ctx.assemble()
     x, info = ctx.solve(opts, case.BC)
-    res = case.post(x)
+    # Neumann formulations (test 21): the inner velocity of every panel comes from a sweep of velocity influences
+    v_inner = None if case.dirichlet else ctx.velocities_at(case, case.inner_points(), x)
+    res = case.post(x, v_inner)
     s_cp, s_f = ILL_CONDITIONED.get(name, (1., 1.))
     fixtures.check_tuple(res, expect, [tol[0] * s_cp, tol[1] * s_cp, tol[2] * s_f, tol[3] * s_f, tol[4] * s_f])
     case.close()
@@ -134,6 +136,32 @@ def test_gmres_iterations_and_solution_match_oracle(ctx, name):
     assert abs(info.iterations - info_ref.iterations) <= 1
     assert np.abs(x - x_ref).max() <= 1e-9 * np.abs(x_ref).max()
     assert info.res_norm < 1e-10
+    case.close()
+
+
+def test_neumann_rows_and_least_squares_match_oracle(ctx):
+    """Reference test 21 (neumann-mass-flux on the supersonic full wing: control points at the panel centroids, rows
+    n . B v of the doublet velocity influences, overdetermined least squares through A^T A): the CUDA matrix against the
+    oracle's entry by entry, the least-squares solution, and the velocity sweep that feeds the post-processing."""
+    case, _, _ = fixtures.make_case("test_21")
+    assert case.n_cp > case.n_unknown
+    ctx.set_case(case)
+    I_known = ctx.assemble()
+    A = ctx.get_A()
+    A_ref, I_ref, S = ob.assemble(case, with_scale=True)
+    assert A.shape == A_ref.shape == (case.n_cp, case.n_unknown)
+    assert ((A == 0) == (A_ref == 0)).all()
+    assert (np.abs(A - A_ref) / np.abs(A_ref).max(axis=1, keepdims=True)).max() < 1e-12
+    assert np.abs(I_known - I_ref).max() <= 1e-13 * max(1e-300, np.abs(I_ref).max())
+    x, info = ctx.solve(case.solver_opts(), case.BC)
+    x_ref, info_ref = ob.solve_system(A_ref, I_ref, case.BC, case.solver_opts())
+    assert abs(info.iterations - info_ref.iterations) <= max(2, info_ref.iterations // 50)
+    assert abs(info.res_norm - info_ref.res_norm) < 1e-9          # the least-squares residual itself (not zero)
+    assert np.abs(x - x_ref).max() <= 1e-7 * np.abs(x_ref).max()   # cond(A^T A) = cond(A)^2
+    pts = case.inner_points()
+    v = ctx.velocities_at(case, pts, x_ref)
+    v_ref = ob.velocities_at(case, pts, x_ref)
+    assert np.abs(v - v_ref).max() < 1e-12
     case.close()
 
 
