@@ -70,7 +70,8 @@ typedef struct ml_flow {
 typedef struct ml_panel_soa {
     int n_panels;
     int n_images;              /* 1, or 2 when mirrored twins are present                              */
-    int n_cols;                /* entries of i_vert_d per panel: M_dim (3) for body, 2*M_dim (6) wake  */
+    int n_cols;                /* entries of i_vert_d per panel: M_dim (3) for body, 2*M_dim (6) wake; 6
+                                  for a higher-order body table (order2 below)                         */
     int in_wake;               /* 1: wake table (doublet only, bottom = -top, panel.f90:2909-2912)     */
     const double *centr;       /* [n_rec][3]      centr / centr_mir                                    */
     const double *A_g_to_ls;   /* [n_rec][3][3]   A_g_to_ls / A_g_to_ls_mir                            */
@@ -88,6 +89,19 @@ typedef struct ml_panel_soa {
     const unsigned char *has_sources;   /* [n_panels]; body only                                       */
     const unsigned char *image_present; /* [n_panels] or NULL (= all): whether record r+n_panels is
                                            evaluated (wake_strip%mirrored, wake_strip.f90:49)          */
+    /* Higher-order distributions (geometry.singularity_order = "higher": quadratic doublets, linear sources;
+       panel.f90:544-969).  order2 = 0 (and the pointers below NULL) for a lower-order table.  With order2 = 1 the body
+       table has n_cols = 6: row j of i_vert_d holds the M_dim(j) doublet ids of panel j (its 3 vertices, then the vertex
+       opposite every continuous edge, panel.f90:605-665), -1 padded.  Wake tables are always lower order. */
+    int order2;
+    const unsigned char *order; /* [n_panels]      1 or 2 (panel.f90:556-565: 3 discontinuous edges -> 1)      */
+    const int    *M_dim;        /* [n_panels]      3..6                                                        */
+    const double *T_mu6;        /* [n_rec][6][6]   T_mu / T_mu_mir (mu_dim x M_dim), zero padded; order-1 panels
+                                                   carry their 3 x 3 in the upper left corner                  */
+    const int    *S_dim;        /* [n_panels]      1..4                                                        */
+    const int    *i_panel_s4;   /* [n_panels][4]   source panel ids (panel.f90:668-693), -1 padded             */
+    const double *T_sigma;      /* [n_rec][3][4]   T_sigma / T_sigma_mir (sigma_dim x S_dim), zero padded;
+                                                   order-1 panels: T_sigma(0,0) = 1                            */
 } ml_panel_soa;
 
 /* Unknown / index bookkeeping used by update_system_row (panel_solver.f90:1203-1287). */

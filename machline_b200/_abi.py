@@ -32,7 +32,9 @@ class MlPanelSoa(C.Structure):
                 ("n_hat_ls", c_double_p), ("b", c_double_p), ("sqrt_b", c_double_p), ("J", c_double_p),
                 ("r", c_int_p), ("area", c_double_p), ("vert_g", c_double_p), ("T_mu", c_double_p),
                 ("i_vert_d", c_int_p), ("i_panel_s", c_int_p), ("has_sources", c_ubyte_p),
-                ("image_present", c_ubyte_p)]
+                ("image_present", c_ubyte_p),
+                ("order2", C.c_int), ("order", c_ubyte_p), ("M_dim", c_int_p), ("T_mu6", c_double_p),
+                ("S_dim", c_int_p), ("i_panel_s4", c_int_p), ("T_sigma", c_double_p)]
 
 
 class MlSystemMap(C.Structure):

@@ -18,8 +18,22 @@ struct PanelTableStore {
     std::vector<int> r, i_vert_d, i_panel_s;
     std::vector<unsigned char> has_sources, image_present;
     int n_panels = 0, n_images = 1, n_cols = 3, in_wake = 0;
+    // higher-order tables (include/machline_gpu.h)
+    int order2 = 0;
+    std::vector<unsigned char> order;
+    std::vector<int> M_dim, S_dim, i_panel_s4;
+    std::vector<double> T_mu6, T_sigma;
 
-    void reserve_for(int np, int ni, int ncols, int wake) {
+    void reserve_for(int np, int ni, int ncols, int wake, int ho = 0) {
+        order2 = ho;
+        if (ho) {
+            order.assign(np, 1);
+            M_dim.assign(np, 3);
+            S_dim.assign(np, 1);
+            i_panel_s4.assign((size_t)np * 4, -1);
+            T_mu6.assign((size_t)np * ni * 36, 0.);
+            T_sigma.assign((size_t)np * ni * 12, 0.);
+        }
         n_panels = np;
         n_images = ni;
         n_cols = ncols;
@@ -64,7 +78,25 @@ struct PanelTableStore {
             J[rec] = m ? p.J_mir : p.J;
             r[rec] = m ? p.r_mir : p.r;
             const std::vector<double>& T = m ? p.T_mu_mir : p.T_mu;
-            for (int k = 0; k < 9 && k < (int)T.size(); ++k) T_mu[rec * 9 + k] = T[k];
+            if (p.order == 1)
+                for (int k = 0; k < 9 && k < (int)T.size(); ++k) T_mu[rec * 9 + k] = T[k];
+            if (order2) {
+                for (int a = 0; a < p.mu_dim; ++a)
+                    for (int bb = 0; bb < p.M_dim; ++bb) T_mu6[rec * 36 + 6 * a + bb] = T[(size_t)a * p.M_dim + bb];
+                const std::vector<double>& Ts = m ? p.T_sigma_mir : p.T_sigma;
+                if (p.order == 2 && !Ts.empty()) {
+                    for (int a = 0; a < 3; ++a)
+                        for (int bb = 0; bb < p.S_dim; ++bb) T_sigma[rec * 12 + 4 * a + bb] = Ts[(size_t)a * p.S_dim + bb];
+                } else {
+                    T_sigma[rec * 12] = 1.;
+                }
+            }
+        }
+        if (order2) {
+            order[j] = (unsigned char)p.order;
+            M_dim[j] = p.M_dim;
+            S_dim[j] = p.i_panel_s.empty() ? 0 : (int)p.i_panel_s.size();
+            for (int k = 0; k < 4 && k < (int)p.i_panel_s.size(); ++k) i_panel_s4[(size_t)j * 4 + k] = p.i_panel_s[k];
         }
         area[j] = p.A;
         for (int k = 0; k < n_cols && k < (int)p.i_vert_d.size(); ++k) i_vert_d[(size_t)j * n_cols + k] = p.i_vert_d[k];
@@ -92,6 +124,15 @@ struct PanelTableStore {
         out->i_panel_s = i_panel_s.data();
         out->has_sources = has_sources.data();
         out->image_present = image_present.data();
+        out->order2 = order2;
+        if (order2) {
+            out->order = order.data();
+            out->M_dim = M_dim.data();
+            out->T_mu6 = T_mu6.data();
+            out->S_dim = S_dim.data();
+            out->i_panel_s4 = i_panel_s4.data();
+            out->T_sigma = T_sigma.data();
+        }
     }
 };
 
@@ -150,7 +191,9 @@ extern "C" int mlh_case_info(const mlh_case* h, mlh_mesh_info* o) {
 
 static void build_tables(mlh_case* h) {
     Case& c = h->c;
-    h->body.reserve_for(c.N_panels, c.mirrored ? 2 : 1, 3, 0);
+    bool ho = false;
+    for (auto& p : c.panels) ho = ho || p.order == 2;
+    h->body.reserve_for(c.N_panels, c.mirrored ? 2 : 1, ho ? 6 : 3, 0, ho ? 1 : 0);
     for (int j = 0; j < c.N_panels; ++j) h->body.put(j, c.panels[j], c.vertices, c.mirrored, c.mirror_plane);
     // wake: strips flattened in (strip, panel) order, the order of panel_solver.f90:1656-1657
     int nw = c.wake.N_panels;

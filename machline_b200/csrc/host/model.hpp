@@ -115,6 +115,10 @@ struct Panel {
     bool edge_is_discontinuous[3] = {false, false, false};
     bool has_sources = true;
     int mu_dim = 3, M_dim = 3, sigma_dim = 1, S_dim = 1;
+    // order 2 only (panel.f90:736-743, 1116-1231): inverse of S_mu (6 x 6 row-major) and the C integrals C(0:3,0:3) that
+    // integrate a quadratic pressure distribution over the panel
+    std::vector<double> S_mu_inv, S_mu_inv_mir;
+    double C[4][4] = {}, C_mir[4][4] = {};
 };
 
 struct WakeStrip {  // src/wake_strip.f90:10-26
@@ -248,7 +252,7 @@ bool panel_line_passes_through(const Panel& p, const std::vector<Vertex>& verts,
 void panel_weighted_normal_at_corner(const Panel& p, const std::vector<Vertex>& verts, const V3& vert_loc, quad out[3]);
 int panel_get_opposite_vertex(const Panel& p, int i1, int i2);
 V3 panel_get_velocity_jump(const Panel& p, const Case& c, const std::vector<double>& mu, const std::vector<double>& sigma,
-                           bool mirrored);
+                           bool mirrored, const V3* point = nullptr);
 
 std::string read_text_file(const std::string& path);
 

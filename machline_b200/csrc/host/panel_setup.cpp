@@ -211,33 +211,215 @@ int panel_get_opposite_vertex(const Panel& p, int i1, int i2) {
     return i_opp;
 }
 
-// panel.f90:696-852, lower-order branch (T_mu = S_mu^-1); the quadratic branch is out of the
-// round-1 scope and reported as unsupported by Case::init_with_flow.
-static void calc_M_mu_transform(Panel& p, bool calc_mirror) {
-    double S_mu[9], S_inv[9];
+// Small dense products in the order gfortran's inlined MATMUL accumulates (ascending contracted index).
+// All matrices row-major: C(m x n) = A(m x k) B(k x n).
+static void mm(int m, int k, int n, const double* A, const double* B, double* C) {
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) {
+            double acc = 0.;
+            for (int l = 0; l < k; ++l) acc = acc + A[i * k + l] * B[l * n + j];
+            C[i * n + j] = acc;
+        }
+}
+static void transpose_mn(int m, int n, const double* A, double* At) {
+    for (int i = 0; i < m; ++i)
+        for (int j = 0; j < n; ++j) At[j * m + i] = A[i * n + j];
+}
+
+// panel.f90:696-852: transformation from the strengths that set the distribution ({M}: the panel's vertices and, for a
+// quadratic distribution, the vertices opposite its continuous edges) to the distribution parameters {mu}
+static void calc_M_mu_transform(Panel& p, const std::vector<Vertex>& body_verts, bool calc_mirror, int mirror_plane) {
+    const int md = p.mu_dim, Md = p.M_dim;
+    const int N_body_verts = (int)body_verts.size();
+    std::vector<double> S_mu((size_t)md * md, 0.), S_inv((size_t)md * md, 0.);
+    const double(*vls)[2] = calc_mirror ? p.vertices_ls_mir : p.vertices_ls;
+    for (int i = 0; i < md; ++i) S_mu[i * md + 0] = 1.;
     for (int i = 0; i < 3; ++i) {
-        S_mu[3 * i + 0] = 1.;
-        if (calc_mirror) {
-            S_mu[3 * i + 1] = p.vertices_ls_mir[i][0];
-            S_mu[3 * i + 2] = p.vertices_ls_mir[i][1];
-        } else {
-            S_mu[3 * i + 1] = p.vertices_ls[i][0];
-            S_mu[3 * i + 2] = p.vertices_ls[i][1];
+        S_mu[i * md + 1] = vls[i][0];
+        S_mu[i * md + 2] = vls[i][1];
+    }
+    if (p.order == 2) {
+        for (int i = 0; i < 3; ++i) {   // edge midpoints: 0.5*(x + cshift(x, 1))
+            const int n = (i + 1) % 3;
+            S_mu[(3 + i) * md + 1] = 0.5 * (S_mu[i * md + 1] + S_mu[n * md + 1]);
+            S_mu[(3 + i) * md + 2] = 0.5 * (S_mu[i * md + 2] + S_mu[n * md + 2]);
+        }
+        for (int i = 0; i < md; ++i) {
+            const double x = S_mu[i * md + 1], y = S_mu[i * md + 2];
+            S_mu[i * md + 3] = 0.5 * (x * x);
+            S_mu[i * md + 4] = x * y;
+            S_mu[i * md + 5] = 0.5 * (y * y);
         }
     }
-    matinv(3, S_mu, S_inv);
+    matinv(md, S_mu.data(), S_inv.data());
+    if (p.order == 2) (calc_mirror ? p.S_mu_inv_mir : p.S_mu_inv) = S_inv;
     std::vector<double>& T = calc_mirror ? p.T_mu_mir : p.T_mu;
-    T.assign(S_inv, S_inv + 9);
+    if (p.order == 1) {
+        T = S_inv;
+        return;
+    }
+    std::vector<double> M_mat((size_t)md * Md, 0.);
+    for (int i = 0; i < 3; ++i) M_mat[i * Md + i] = 1.;
+    double E[4 * 6] = {0.};
+    for (int i = 0; i < 3; ++i)
+        for (int k = 0; k < 6; ++k) E[i * 6 + k] = S_mu[i * md + k];
+    int j = 3;
+    for (int i = 0; i < 3; ++i) {
+        if (p.edge_is_discontinuous[i]) {
+            // the midpoint strength is the average of the endpoint strengths
+            M_mat[(i + 3) * Md + i] = 0.5;
+            M_mat[(i + 3) * Md + (i + 1) % 3] = 0.5;
+        } else {
+            // underdetermined least-squares fit through the three vertices and the vertex opposite the edge
+            const int iv = p.i_vert_d[j];
+            V3 P_g;
+            if (calc_mirror) {
+                if (iv >= N_body_verts) P_g = body_verts[iv - N_body_verts].loc;
+                else P_g = mirror_across_plane(body_verts[iv].loc, mirror_plane);
+            } else {
+                if (iv >= N_body_verts) P_g = mirror_across_plane(body_verts[iv - N_body_verts].loc, mirror_plane);
+                else P_g = body_verts[iv].loc;
+            }
+            const V3 P_ls = calc_mirror ? matvec(p.A_g_to_ls_mir, P_g - p.centr_mir) : matvec(p.A_g_to_ls, P_g - p.centr);
+            E[3 * 6 + 0] = 1.;
+            E[3 * 6 + 1] = P_ls[0];
+            E[3 * 6 + 2] = P_ls[1];
+            E[3 * 6 + 3] = 0.5 * (P_ls[0] * P_ls[0]);
+            E[3 * 6 + 4] = P_ls[0] * P_ls[1];
+            E[3 * 6 + 5] = 0.5 * (P_ls[1] * P_ls[1]);
+            double Et[6 * 4], EEt[16], EE_inv[16], EtEEinv[6 * 4], M_row[4];
+            transpose_mn(4, 6, E, Et);
+            mm(4, 6, 4, E, Et, EEt);
+            matinv(4, EEt, EE_inv);
+            mm(6, 4, 4, Et, EE_inv, EtEEinv);
+            mm(1, 6, 4, &S_mu[(i + 3) * md], EtEEinv, M_row);
+            for (int k = 0; k < 3; ++k) M_mat[(i + 3) * Md + k] = M_row[k];
+            M_mat[(i + 3) * Md + j] = M_row[3];
+            ++j;
+        }
+    }
+    T.assign((size_t)md * Md, 0.);
+    mm(md, md, Md, S_inv.data(), M_mat.data(), T.data());
+}
+
+// panel.f90:855-969: transformation from the source strengths of this panel and its neighbours across continuous edges ({S})
+// to the parameters of the linear source distribution {sigma}
+static void calc_S_sigma_transform(Panel& p, const std::vector<Panel>& body_panels, bool calc_mirror, int mirror_plane,
+                                   bool force_sigma_match) {
+    if (p.order != 2) return;
+    const int Sd = p.S_dim, N_panels = (int)body_panels.size();
+    std::vector<double> S((size_t)Sd * 3, 0.);
+    S[0] = 1.;
+    V3 P_ls{0., 0., 0.};
+    for (int i = 1; i < Sd; ++i) {
+        const int ip = p.i_panel_s[i];
+        V3 P_g;
+        if (calc_mirror) {
+            if (ip >= N_panels) P_g = body_panels[ip - N_panels].centr;
+            else P_g = body_panels[ip].centr_mir;
+            P_ls = matvec(p.A_g_to_ls_mir, P_g - p.centr_mir);
+        } else {
+            if (ip >= N_panels) P_g = mirror_across_plane(body_panels[ip - N_panels].centr, mirror_plane);
+            else P_g = body_panels[ip].centr;
+            P_ls = matvec(p.A_g_to_ls, P_g - p.centr);
+        }
+        S[i * 3 + 0] = 1.;
+        S[i * 3 + 1] = P_ls[0];
+        S[i * 3 + 2] = P_ls[1];
+    }
+    std::vector<double> T((size_t)3 * Sd, 0.);
+    if (Sd == 4) {
+        if (!force_sigma_match) {
+            double St[3 * 4], StS[9], SS_inv[9];
+            transpose_mn(4, 3, S.data(), St);
+            mm(3, 4, 3, St, S.data(), StS);
+            matinv(3, StS, SS_inv);
+            mm(3, 3, 4, SS_inv, St, T.data());
+        } else {
+            double Sub[3 * 2], Subt[2 * 3], StS[4], SS_inv[4], A_mat[3 * 4] = {0.}, StA[2 * 4], T23[2 * 4];
+            for (int i = 0; i < 3; ++i) {
+                Sub[i * 2 + 0] = S[(i + 1) * 3 + 1];
+                Sub[i * 2 + 1] = S[(i + 1) * 3 + 2];
+            }
+            transpose_mn(3, 2, Sub, Subt);
+            mm(2, 3, 2, Subt, Sub, StS);
+            matinv(2, StS, SS_inv);
+            for (int i = 0; i < 3; ++i) A_mat[i * 4 + 0] = -1.;
+            A_mat[0 * 4 + 1] = 1.;
+            A_mat[1 * 4 + 2] = 1.;
+            A_mat[2 * 4 + 3] = 1.;
+            mm(2, 3, 4, Subt, A_mat, StA);
+            mm(2, 2, 4, SS_inv, StA, T23);
+            T[0] = 1.;
+            for (int k = 0; k < 4; ++k) {
+                T[1 * 4 + k] = T23[k];
+                T[2 * 4 + k] = T23[4 + k];
+            }
+        }
+    } else if (Sd == 3) {
+        matinv(3, S.data(), T.data());
+    } else if (Sd == 2) {
+        double A_mat[3 * 2] = {0.}, SA[4], SA_inv[4];
+        A_mat[0] = 1.;
+        if (std::fabs(P_ls[0]) > std::fabs(P_ls[1])) {
+            A_mat[1 * 2 + 1] = 1.;
+            A_mat[2 * 2 + 1] = P_ls[1] / P_ls[0];
+        } else {
+            A_mat[1 * 2 + 1] = P_ls[0] / P_ls[1];
+            A_mat[2 * 2 + 1] = 1.;
+        }
+        mm(2, 3, 2, S.data(), A_mat, SA);
+        matinv(2, SA, SA_inv);
+        mm(3, 2, 2, A_mat, SA_inv, T.data());
+    }
+    (calc_mirror ? p.T_sigma_mir : p.T_sigma) = T;
+}
+
+// panel.f90:1116-1231: C(i,j) = integral of xi^i eta^j over the panel, from the edge recursions (H by eta, I by xi)
+static void calc_C_integrals(Panel& p, bool mir) {
+    const int Ni = 3, Nj = 3;
+    double d_eta[3], d_xi[3], xi[3], eta[3];
+    const double(*v)[2] = mir ? p.vertices_ls_mir : p.vertices_ls;
+    for (int k = 0; k < 3; ++k) {
+        const int kn = (k + 1) % 3;
+        xi[k] = v[k][0];
+        eta[k] = v[k][1];
+        if (!mir) {
+            d_xi[k] = v[kn][0] - v[k][0];
+            d_eta[k] = v[kn][1] - v[k][1];
+        } else {
+            d_xi[kn] = v[k][0] - v[kn][0];
+            d_eta[kn] = v[k][1] - v[kn][1];
+        }
+    }
+    static thread_local double II[Ni + 3][Nj + 1][Ni + 2][3];
+    for (int i = 0; i <= Ni + 2; ++i)
+        for (int e = 0; e < 3; ++e) II[i][0][0][e] = 1. / (i + 1.);
+    for (int j = 1; j <= Nj; ++j)
+        for (int i = 0; i <= Ni - j; ++i)
+            for (int e = 0; e < 3; ++e) II[i][j][0][e] = eta[e] * II[i][j - 1][0][e] + d_eta[e] * II[i + 1][j - 1][0][e];
+    for (int j = 0; j <= Nj; ++j)
+        for (int k = 1; k <= Ni - j; ++k)
+            for (int i = Ni - j; i >= k; --i)
+                for (int e = 0; e < 3; ++e) II[i][j][k][e] = xi[e] * II[i - 1][j][k - 1][e] + d_xi[e] * II[i][j][k - 1][e];
+    double(*C)[4] = mir ? p.C_mir : p.C;
+    for (int i = 0; i <= Ni; ++i)
+        for (int j = 0; j <= Nj; ++j) {
+            // the reference reads II(i+1, j, i+1, :) for every (i, j) of the 4 x 4 table, including entries its recursions
+            // never set (i + j > 2: allocated, not initialised there); only C(i,j) with i + j <= 3 and in fact <= 2 for the
+            // pressure average are used.  Entries outside the recursion's range are reported as zero here.
+            double acc = 0.;
+            const bool set = (i + 1 <= Ni - j);
+            if (set)
+                for (int e = 0; e < 3; ++e) acc = acc + d_eta[e] * II[i + 1][j][i + 1][e];
+            C[i][j] = set ? acc / (i + 1) : 0.;
+        }
 }
 
 // panel.f90:544-693
 void panel_set_distribution(Panel& p, int order, const std::vector<Panel>& body_panels,
                             const std::vector<Vertex>& body_verts, const std::vector<Vertex>& own_verts,
                             bool mirror_needed, int mirror_plane, bool force_sigma_match) {
-    (void)body_panels;
-    (void)body_verts;
-    (void)mirror_plane;
-    (void)force_sigma_match;
     if (p.in_wake) {
         p.order = 1;
         p.has_sources = false;
@@ -245,11 +427,18 @@ void panel_set_distribution(Panel& p, int order, const std::vector<Panel>& body_
         p.order = order;
     }
     if (p.N_discont_edges == 3 && p.order == 2) p.order = 1;
-    if (p.order != 1) throw std::runtime_error("higher-order singularity distributions are not built yet");
-    p.mu_dim = 3;
-    p.M_dim = 3;
-    p.sigma_dim = 1;
-    p.S_dim = 1;
+    if (p.order == 1) {
+        p.mu_dim = 3;
+        p.M_dim = 3;
+        p.sigma_dim = 1;
+        p.S_dim = 1;
+    } else {
+        p.mu_dim = 6;
+        p.M_dim = 6 - p.N_discont_edges;
+        p.sigma_dim = 3;
+        p.S_dim = 4 - p.N_discont_edges;
+    }
+    const int N_body_panels = (int)body_panels.size(), N_body_verts = (int)body_verts.size();
     // set_doublet_verts, panel.f90:605-665
     if (p.in_wake) {
         p.i_vert_d.assign(2 * p.M_dim, -1);
@@ -260,13 +449,39 @@ void panel_set_distribution(Panel& p, int order, const std::vector<Panel>& body_
     } else {
         p.i_vert_d.assign(p.M_dim, -1);
         for (int i = 0; i < 3; ++i) p.i_vert_d[i] = p.iv[i];
+        if (p.order == 2) {
+            int j = 3;
+            for (int i = 0; i < 3; ++i) {
+                if (p.edge_is_discontinuous[i]) continue;
+                const int i1 = p.iv[i], i2 = p.iv[(i + 1) % 3];
+                if (p.abutting_panels[i] >= N_body_panels) {   // the neighbour is this panel's own mirror image
+                    p.i_vert_d[j] = panel_get_opposite_vertex(p, i1, i2) + N_body_verts;
+                } else {
+                    p.i_vert_d[j] = panel_get_opposite_vertex(body_panels[p.abutting_panels[i]], i1, i2);
+                }
+                ++j;
+            }
+        }
     }
-    calc_M_mu_transform(p, false);
+    calc_M_mu_transform(p, body_verts, false, mirror_plane);
     if (p.has_sources) {
         p.i_panel_s.assign(p.S_dim, -1);  // set_source_panels, panel.f90:668-693
         p.i_panel_s[0] = p.index;
+        if (p.order == 2) {
+            int j = 1;
+            for (int i = 0; i < 3; ++i)
+                if (!p.edge_is_discontinuous[i]) p.i_panel_s[j++] = p.abutting_panels[i];
+        }
+        calc_S_sigma_transform(p, body_panels, false, mirror_plane, force_sigma_match);
     }
-    if (mirror_needed) calc_M_mu_transform(p, true);
+    if (mirror_needed) {
+        calc_M_mu_transform(p, body_verts, true, mirror_plane);
+        if (p.has_sources) calc_S_sigma_transform(p, body_panels, true, mirror_plane, force_sigma_match);
+    }
+    if (p.order == 2) {
+        calc_C_integrals(p, false);
+        if (mirror_needed) calc_C_integrals(p, true);
+    }
 }
 
 // panel.f90:1357-1401

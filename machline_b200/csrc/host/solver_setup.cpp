@@ -307,8 +307,22 @@ void Case::set_permutation() {
                 int i_vert = q.tied_to_index;
                 x[i] = huge;
                 for (int i_neighbor : vertices[i_vert].adjacent_vertices) x[i] = std::min(x[i], key(vertices[i_neighbor].loc));
-                // (higher-order abutting-panel extension, panel_solver.f90:859-894/931-966, applies to
-                //  order-2 panels only)
+                // higher-order distributions reach the vertex opposite each continuous edge as well
+                // (panel_solver.f90:859-894 / 931-966)
+                for (int i_panel : vertices[i_vert].panels_not_across_wake_edge) {
+                    const Panel& pp = panels[i_panel];
+                    if (pp.order != 2) continue;
+                    int k_v = -1;
+                    for (int k = 0; k < 3; ++k)
+                        if (pp.iv[k] == i_vert) k_v = k;   // get_opposite_edge, panel.f90:1656-1682
+                    if (k_v < 0) continue;
+                    const int i_opp_edge = pp.edges[(k_v + 1) % 3];
+                    const Edge& e = edges[i_opp_edge];
+                    if (e.discontinuous || e.on_mirror_plane) continue;
+                    const int i_panel_abutting = (e.panels[0] == i_panel) ? e.panels[1] : e.panels[0];
+                    const int i_neighbor = panel_get_opposite_vertex(panels[i_panel_abutting], e.top_verts[0], e.top_verts[1]);
+                    if (i_neighbor >= 0) x[i] = std::min(x[i], key(vertices[i_neighbor].loc));
+                }
             } else {
                 int i_panel = q.tied_to_index;
                 x[i] = huge;
@@ -444,12 +458,15 @@ void Case::pre_solve() {
     }
 }
 
-// panel.f90:3351-3512 (lower-order): velocity jump across a panel at its centroid
+// panel.f90:3351-3512: velocity jump across a panel at `point` (default: its centroid)
 V3 panel_get_velocity_jump(const Panel& p, const Case& c, const std::vector<double>& mu, const std::vector<double>& sigma,
-                           bool mirrored) {
+                           bool mirrored, const V3* point) {
+    V3 Q_ls{0., 0., 0.};
+    if (point) Q_ls = mirrored ? matvec(p.A_g_to_ls_mir, *point - p.centr_mir) : matvec(p.A_g_to_ls, *point - p.centr);
     // get_doublet_strengths, panel.f90:3351-3412 (body panels)
-    double mu_verts[3];
-    for (int i = 0; i < 3; ++i) {
+    const int Md = (int)p.i_vert_d.size(), md = p.mu_dim;
+    double mu_verts[6] = {0., 0., 0., 0., 0., 0.};
+    for (int i = 0; i < Md; ++i) {
         int iv = p.i_vert_d[i];
         int idx;
         if (c.asym_flow) {
@@ -461,26 +478,79 @@ V3 panel_get_velocity_jump(const Panel& p, const Case& c, const std::vector<doub
         mu_verts[i] = mu[idx];
     }
     const std::vector<double>& T = mirrored ? p.T_mu_mir : p.T_mu;
-    double mu_params[3];
-    for (int i = 0; i < 3; ++i) mu_params[i] = T[3 * i + 0] * mu_verts[0] + T[3 * i + 1] * mu_verts[1] + T[3 * i + 2] * mu_verts[2];
-    V3 dv{mu_params[1], mu_params[2], 0.};
+    double mu_params[6] = {0., 0., 0., 0., 0., 0.};
+    for (int i = 0; i < md; ++i) {
+        double acc = 0.;
+        for (int k = 0; k < Md; ++k) acc = acc + T[(size_t)i * Md + k] * mu_verts[k];
+        mu_params[i] = acc;
+    }
+    V3 dv;
+    if (p.order == 2) {
+        dv = {mu_params[1] + mu_params[3] * Q_ls[0] + mu_params[4] * Q_ls[1],
+              mu_params[2] + mu_params[4] * Q_ls[0] + mu_params[5] * Q_ls[1], 0.};
+    } else {
+        dv = {mu_params[1], mu_params[2], 0.};
+    }
     const M33& A = mirrored ? p.A_g_to_ls_mir : p.A_g_to_ls;
     dv = matvec(transpose(A), dv);
     if (p.has_sources) {
         V3 s_dir = mirrored ? p.n_g_mir / inner(p.nu_g_mir, p.n_g_mir) : p.n_g / inner(p.nu_g, p.n_g);
-        // get_source_strengths, panel.f90:3268-3313
-        int ip = p.i_panel_s[0];
-        int idx;
-        if (c.asym_flow) {
-            if (mirrored) idx = (ip >= c.N_panels) ? ip - c.N_panels : ip + c.N_panels;
-            else idx = ip;
-        } else {
-            idx = (ip >= c.N_panels) ? ip - c.N_panels : ip;
+        // get_source_strengths / get_source_parameters, panel.f90:3268-3348
+        const int Sd = (int)p.i_panel_s.size();
+        double sig[4] = {0., 0., 0., 0.};
+        for (int i = 0; i < Sd; ++i) {
+            int ip = p.i_panel_s[i];
+            int idx;
+            if (c.asym_flow) {
+                if (mirrored) idx = (ip >= c.N_panels) ? ip - c.N_panels : ip + c.N_panels;
+                else idx = ip;
+            } else {
+                idx = (ip >= c.N_panels) ? ip - c.N_panels : ip;
+            }
+            sig[i] = sigma[idx];
         }
-        double s = sigma[idx];
+        double s;
+        if (p.sigma_dim > 1) {
+            const std::vector<double>& Ts = mirrored ? p.T_sigma_mir : p.T_sigma;
+            double sp[3];
+            for (int i = 0; i < 3; ++i) {
+                double acc = 0.;
+                for (int k = 0; k < Sd; ++k) acc = acc + Ts[(size_t)i * Sd + k] * sig[k];
+                sp[i] = acc;
+            }
+            s = sp[0] + sp[1] * Q_ls[0] + sp[2] * Q_ls[1];
+        } else {
+            s = sig[0];
+        }
         dv = dv + s * s_dir;
     }
     return dv;
+}
+
+// panel.f90:3541-3606: parameters of the quadratic pressure distribution over an order-2 panel, from the pressure rule applied
+// to the velocity at its three vertices and three edge midpoints.  (For the mirrored image the reference evaluates the
+// "vertex" velocities at the un-mirrored vertex locations, :3570-3571; restated as it is.)
+static void quadratic_pressure_params(const Panel& p, const Case& c, const Results& R, bool mirrored, const V3& inner_flow,
+                                      const char* rule, double out[6]) {
+    const Flow& fs = c.freestream;
+    double C_P[6];
+    for (int i = 0; i < 3; ++i) {
+        const V3 pt = c.vloc(p, i);
+        const V3 dv = panel_get_velocity_jump(p, c, R.mu, R.sigma, mirrored, &pt);
+        C_P[i] = fs.get_C_P(fs.U * (inner_flow + dv), rule, c.solver.M_inf_corr);
+    }
+    for (int i = 0; i < 3; ++i) {
+        V3 pt = 0.5 * (c.vloc(p, i) + c.vloc(p, (i + 1) % 3));
+        if (mirrored) pt = mirror_across_plane(pt, c.mirror_plane);
+        const V3 dv = panel_get_velocity_jump(p, c, R.mu, R.sigma, mirrored, &pt);
+        C_P[i + 3] = fs.get_C_P(fs.U * (inner_flow + dv), rule, c.solver.M_inf_corr);
+    }
+    const std::vector<double>& Si = mirrored ? p.S_mu_inv_mir : p.S_mu_inv;
+    for (int i = 0; i < 6; ++i) {
+        double acc = 0.;
+        for (int k = 0; k < 6; ++k) acc = acc + Si[i * 6 + k] * C_P[k];
+        out[i] = acc;
+    }
 }
 
 // The points just inside every panel (and its mirror image in an asymmetric flow) where calc_cell_velocities evaluates the
@@ -499,7 +569,7 @@ std::vector<double> Case::inner_points() const {
     return pts;
 }
 
-// panel_solver.f90:2012-2615 (lower-order path)
+// panel_solver.f90:2012-2615
 Results Case::post(const std::vector<double>& x, const double* v_inner) const {
     // v_inner: [N_cells][3] induced velocity (v_d + v_s, per unit freestream speed) just inside every panel, needed by the
     // formulations without a prescribed inner flow (panel_solver.f90:2063-2066); nullptr for the Dirichlet formulations
@@ -532,9 +602,23 @@ Results Case::post(const std::vector<double>& x, const double* v_inner) const {
     }
     // calc_pressures :2218-2321; the lower-order average pressure is the rule applied to the
     // centroid velocity (panel.f90:3638-3649), i.e. to V_cells.
+    // get_avg_pressure_coef, panel.f90:3609-3675: order 2 integrates the quadratic pressure distribution over the panel
+    auto avg_pressure = [&](int i_panel, bool mir, const char* rule) {
+        const Panel& p = panels[i_panel];
+        const int cell = mir ? i_panel + N_panels : i_panel;
+        if (p.order == 1) return fs.get_C_P(R.V_cells[cell], rule, solver.M_inf_corr);
+        double q[6];
+        quadratic_pressure_params(p, *this, R, mir, R.V_cells_inner[cell] / fs.U, rule, q);
+        const double(*C)[4] = mir ? p.C_mir : p.C;
+        double avg = C[0][0] * q[0] + C[1][0] * q[1] + C[0][1] * q[2] + 0.5 * C[2][0] * q[3] + C[1][1] * q[4] + 0.5 * C[0][2] * q[5];
+        return (mir ? p.J_mir : p.J) * avg / p.A;
+    };
     auto fill = [&](std::vector<double>& dst, const char* rule) {
         dst.assign(R.N_cells, 0.);
-        for (int i = 0; i < R.N_cells; ++i) dst[i] = fs.get_C_P(R.V_cells[i], rule, solver.M_inf_corr);
+        for (int i = 0; i < N_panels; ++i) {
+            dst[i] = avg_pressure(i, false, rule);
+            if (asym_flow) dst[i + N_panels] = avg_pressure(i, true, rule);
+        }
     };
     if (solver.incompressible_rule) fill(R.C_p_inc, "incompressible");
     if (solver.isentropic_rule) fill(R.C_p_ise, "isentropic");
@@ -572,9 +656,22 @@ Results Case::post(const std::vector<double>& x, const double* v_inner) const {
     // calc_moments :2551-2615 (order 1: no pressure-variation term)
     V3 msum{0., 0., 0.};
     std::vector<V3> dC_m(R.N_cells, V3{});
+    // get_moment_about_centroid, panel.f90:3678-3740 (order 2 only; the reference passes the solver's inner_flow here)
+    auto moment_about_centroid = [&](const Panel& p, bool mir) {
+        double q[6];
+        quadratic_pressure_params(p, *this, R, mir, inner_flow, pf.c_str(), q);
+        const double(*C)[4] = mir ? p.C_mir : p.C;
+        V3 m{C[1][0] * q[0] + C[2][0] * q[1] + C[1][1] * q[2] + 0.5 * C[3][0] * q[3] + C[2][1] * q[4] + 0.5 * C[1][2] * q[5],
+             C[0][1] * q[0] + C[1][1] * q[1] + C[0][2] * q[2] + 0.5 * C[2][1] * q[3] + C[1][2] * q[4] + 0.5 * C[0][3] * q[5], 0.};
+        return mir ? p.J_mir * cross(p.n_g_mir, matvec(p.A_ls_to_g_mir, m)) : p.J * cross(p.n_g, matvec(p.A_ls_to_g, m));
+    };
     for (int i = 0; i < N_panels; ++i) {
         dC_m[i] = cross(panels[i].centr - CG, R.dC_f[i]);
-        if (asym_flow) dC_m[i + N_panels] = cross(panels[i].centr_mir - CG, R.dC_f[i]);  // sic (:2583)
+        if (panels[i].order == 2) dC_m[i] = dC_m[i] + moment_about_centroid(panels[i], false);
+        if (asym_flow) {
+            dC_m[i + N_panels] = cross(panels[i].centr_mir - CG, R.dC_f[i]);  // sic (:2583)
+            if (panels[i].order == 2) dC_m[i + N_panels] = dC_m[i + N_panels] + moment_about_centroid(panels[i], true);
+        }
     }
     for (int i = 0; i < R.N_cells; ++i) msum = msum + dC_m[i];
     R.C_M = msum / l_ref;

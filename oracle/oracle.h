@@ -17,6 +17,13 @@ typedef struct orc_pair_out {
     double v_s[3];     /* source-induced velocity influence, global coordinates (S_dim = 1; panel.f90:3011-3075)   */
     double v_d[9];     /* doublet-induced velocity influences, global coordinates, v_d[3 * i + c] = component i of */
                        /* column c (M_dim = 3; panel.f90:3078-3170)                                                 */
+    /* higher-order panels (table->order2): strength-space influences of panel.f90:2815-2914 with S_dim <= 4 and M_dim <= 6;
+       for an order-1 panel of such a table phi_s_S[0] = phi_s and phi_d_M[0..2] = phi_d */
+    double phi_s_S[4];
+    double phi_d_M[6];
+    double phi_d_M_abs[6];
+    double F121[3], F211[3];
+    double H211, H121, H313, H223, H133;
 } orc_pair_out;
 
 /* tests only: log/atan2 through binary128, rounded once (noise-floor calibration) */

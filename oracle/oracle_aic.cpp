@@ -2,8 +2,9 @@
 // (machline_b200/, include/): only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 // --impl reference legs may use it, and only as the checker.
 //
-// CPU restatement of MachLine's AIC assembly for lower-order (linear doublet / constant source)
-// Dirichlet formulations, following the reference statement by statement:
+// CPU restatement of MachLine's AIC assembly (lower-order linear doublet / constant source panels for the Dirichlet and
+// the least-squares Neumann formulations; higher-order quadratic doublet / linear source panels for the Dirichlet
+// formulations), following the reference statement by statement:
 //   flow_point_in_dod                         src/flow.f90:282-310
 //   panel_check_dod                           src/panel.f90:1732-1901
 //   panel_calc_basic_geom                     src/panel.f90:1904-1938
@@ -13,7 +14,7 @@
 //   panel_calc_basic_F_integrals_supersonic_subinc  src/panel.f90:2286-2407
 //   panel_calc_hH113_subsonic                 src/panel.f90:2472-2509
 //   panel_calc_hH113_supersonic_subinc        src/panel.f90:2512-2573   (binary128 F1,F2,b)
-//   panel_calc_remaining_integrals            src/panel.f90:2631-2683   (order 1 part)
+//   panel_calc_remaining_integrals            src/panel.f90:2631-2683   (order 1 and order 2 potential integrals)
 //   panel_assemble_phi_s_S_space / phi_d_M_space   src/panel.f90:2815-2914
 //   panel_calc_potential_influences           src/panel.f90:2917-2971
 //   panel_solver_update_system_row            src/panel_solver.f90:1203-1287
@@ -72,6 +73,9 @@ struct Rec {  // one panel image
     const double *centr, *A, *vls, *nh, *b, *sb, *vg, *T;
     double J;
     int r;
+    // higher-order tables
+    int order = 1, M_dim = 3, S_dim = 1;
+    const double *T6 = nullptr, *Ts = nullptr;
 };
 inline Rec get_rec(const ml_panel_soa* t, int j, int img) {
     size_t rec = (size_t)j + (size_t)img * t->n_panels;
@@ -86,6 +90,13 @@ inline Rec get_rec(const ml_panel_soa* t, int j, int img) {
     R.T = t->T_mu + 9 * rec;
     R.J = t->J[rec];
     R.r = t->r[rec];
+    if (t->order2) {
+        R.order = t->order[j];
+        R.M_dim = t->M_dim[j];
+        R.S_dim = t->S_dim[j];
+        R.T6 = t->T_mu6 + 36 * rec;
+        R.Ts = t->T_sigma + 12 * rec;
+    }
     return R;
 }
 
@@ -242,11 +253,13 @@ struct Integrals {
     int r, s, rs;
     double H111, hH113, H213, H123;
     double F111[3];
+    double F121[3] = {0., 0., 0.}, F211[3] = {0., 0., 0.};   // order 2 (panel.f90:2275-2279, 2325-2392)
+    double H211 = 0., H121 = 0., H313 = 0., H223 = 0., H133 = 0.;
     double hH113_abs = 0.;  // running-error scale of hH113: sum over edges of |term| + |cancelled products behind it|
                             // (not a reference quantity; tests only)
 };
 
-// panel.f90:2232-2283 (F121/F211 feed only the order-2 recursions and are not restated)
+// panel.f90:2232-2283
 void F_subsonic(const Geom& g, Integrals& I) {
     for (int i = 0; i < 3; ++i) {
         if (fsign(1., g.l1[i]) != fsign(1., g.l2[i])) {
@@ -255,15 +268,22 @@ void F_subsonic(const Geom& g, Integrals& I) {
             I.F111[i] = fsign(1., g.l1[i]) * o_log((g.R2[i] + std::fabs(g.l2[i])) / (g.R1[i] + std::fabs(g.l1[i])));
         }
     }
+    for (int i = 0; i < 3; ++i) {   // :2278-2279
+        I.F121[i] = g.a[i] * g.v_eta[i] * I.F111[i] + g.v_xi[i] * g.dR[i];
+        I.F211[i] = g.a[i] * g.v_xi[i] * I.F111[i] - g.v_eta[i] * g.dR[i];
+    }
 }
 
 // panel.f90:2286-2407
-void F_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integrals& I) {
+void F_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, bool mirror, Integrals& I) {
     for (int i = 0; i < 3; ++i) {
         if (!dod.e[i]) continue;
+        const int i_next = (i + 1) % 3;
         double b = p.b[i], s_b = p.sb[i];
         if (g.R1[i] == 0. && g.R2[i] == 0.) {
             I.F111[i] = pi / s_b;
+            I.F121[i] = -g.a[i] * g.v_eta[i] * I.F111[i] / b;
+            I.F211[i] = g.a[i] * g.v_xi[i] * I.F111[i] / b;
         } else {
             double F1, F2;
             if (b > 0.) {
@@ -278,12 +298,24 @@ void F_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integrals&
                 double eps2 = eps * eps;
                 double series = eps * eps2 * (1. / 3. - b * eps2 / 5. + (b * eps2) * (b * eps2) / 7.);
                 I.F111[i] = -eps + b * series;
+                // :2339-2351 (p.vls is the mirrored panel's own vertex array for a mirror image)
+                const double eta_a = mirror ? p.vls[2 * i_next + 1] : p.vls[2 * i + 1];
+                const double eta_b = mirror ? p.vls[2 * i + 1] : p.vls[2 * i_next + 1];
+                I.F121[i] = (-g.v_xi[i] * g.dR[i] * g.R1[i] * g.R2[i] + g.l2[i] * g.R1[i] * (eta_a - g.P_ls[1]) -
+                             g.l1[i] * g.R2[i] * (eta_b - g.P_ls[1])) /
+                                (g.g2[i] * F2) -
+                            g.a[i] * g.v_eta[i] * series;
+                I.F211[i] = -g.v_eta[i] * g.dR[i] + g.a[i] * g.v_xi[i] * I.F111[i] - 2. * g.v_xi[i] * g.v_eta[i] * I.F121[i];
             } else if (b > 0.) {
                 I.F111[i] = -o_atan2(s_b * F1, F2) / s_b;
+                I.F121[i] = -(g.v_xi[i] * g.dR[i] + g.a[i] * g.v_eta[i] * I.F111[i]) / b;
+                I.F211[i] = -g.v_eta[i] * g.dR[i] + g.a[i] * g.v_xi[i] * I.F111[i] - 2. * g.v_xi[i] * g.v_eta[i] * I.F121[i];
             } else {
                 F1 = s_b * g.R1[i] + std::fabs(g.l1[i]);
                 F2 = s_b * g.R2[i] + std::fabs(g.l2[i]);
                 if (F1 != 0. && F2 != 0.) I.F111[i] = -fsign(1., g.v_eta[i]) * o_log(F1 / F2) / s_b;
+                I.F121[i] = -(g.v_xi[i] * g.dR[i] + g.a[i] * g.v_eta[i] * I.F111[i]) / b;
+                I.F211[i] = -g.v_eta[i] * g.dR[i] + g.a[i] * g.v_xi[i] * I.F111[i] - 2. * g.v_xi[i] * g.v_eta[i] * I.F121[i];
             }
         }
     }
@@ -341,13 +373,13 @@ void hH113_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integr
 }
 
 // panel.f90:2766-2812 + 2631-2647
-void calc_integrals(const Rec& p, const Geom& g, const ml_flow* fs, const Dod& dod, Integrals& I) {
+void calc_integrals(const Rec& p, const Geom& g, const ml_flow* fs, const Dod& dod, bool mirror, bool has_sources, Integrals& I) {
     I.F111[0] = I.F111[1] = I.F111[2] = 0.;
     I.r = p.r;
     I.s = (int)fs->s;
     I.rs = I.r * I.s;
     if (fs->supersonic) {
-        F_supersonic_subinc(p, g, dod, I);
+        F_supersonic_subinc(p, g, dod, mirror, I);
         hH113_supersonic_subinc(p, g, dod, I);
     } else {
         F_subsonic(g, I);
@@ -360,6 +392,22 @@ void calc_integrals(const Rec& p, const Geom& g, const ml_flow* fs, const Dod& d
     I.H111 = s1 - I.rs * g.h * I.hH113;
     I.H213 = -I.r * s2;
     I.H123 = -I.s * s3;
+    if (p.order == 2) {   // panel.f90:2649-2662
+        if (has_sources) {
+            double sa211 = 0., sa121 = 0.;
+            for (int i = 0; i < 3; ++i) sa211 = sa211 + g.a[i] * I.F211[i];
+            for (int i = 0; i < 3; ++i) sa121 = sa121 + g.a[i] * I.F121[i];
+            I.H211 = 0.5 * (-I.rs * g.h2 * I.H213 + sa211);
+            I.H121 = 0.5 * (-I.rs * g.h2 * I.H123 + sa121);
+        }
+        double sx211 = 0., sx121 = 0., se121 = 0.;
+        for (int i = 0; i < 3; ++i) sx211 = sx211 + g.v_xi[i] * I.F211[i];
+        for (int i = 0; i < 3; ++i) sx121 = sx121 + g.v_xi[i] * I.F121[i];
+        for (int i = 0; i < 3; ++i) se121 = se121 + g.v_eta[i] * I.F121[i];
+        I.H313 = I.r * (I.H111 - sx211);
+        I.H223 = -I.r * sx121;
+        I.H133 = I.s * (I.H111 - se121);
+    }
 }
 
 }  // namespace
@@ -379,8 +427,9 @@ extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int
     Geom g;
     if (fs->supersonic) supersonic_subinc_geom(p, P, mirror, dod, g);
     else subsonic_geom(p, P, mirror, g);
+    bool has_src = !t->in_wake && t->has_sources && t->has_sources[j];
     Integrals I;
-    calc_integrals(p, g, fs, dod, I);
+    calc_integrals(p, g, fs, dod, mirror, has_src, I);
     for (int i = 0; i < 3; ++i) out->F111[i] = I.F111[i];
     out->hH113 = I.hH113;
     out->H111 = I.H111;
@@ -388,7 +437,6 @@ extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int
     out->H123 = I.H123;
     out->h = g.h;
     // assemble_phi_s_S_space (order 1), panel.f90:2852-2859
-    bool has_src = !t->in_wake && t->has_sources && t->has_sources[j];
     out->phi_s = has_src ? -p.J * fs->K_inv * I.H111 : 0.;
     // assemble_phi_d_M_space, panel.f90:2888-2907
     double m[3];
@@ -399,6 +447,64 @@ extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int
         double acc = 0.;
         for (int k = 0; k < 3; ++k) acc = acc + m[k] * p.T[3 * k + c];
         out->phi_d[c] = I.s * fs->K_inv * acc;
+    }
+    for (int i = 0; i < 3; ++i) {
+        out->F121[i] = I.F121[i];
+        out->F211[i] = I.F211[i];
+    }
+    out->H211 = I.H211;
+    out->H121 = I.H121;
+    out->H313 = I.H313;
+    out->H223 = I.H223;
+    out->H133 = I.H133;
+    if (t->order2) {
+        // assemble_phi_s_S_space, panel.f90:2815-2863
+        if (has_src) {
+            if (p.order == 2) {
+                const double sg[3] = {I.H111, I.H111 * g.P_ls[0] + I.H211, I.H111 * g.P_ls[1] + I.H121};
+                for (int c = 0; c < p.S_dim; ++c) {
+                    double acc = 0.;
+                    for (int k = 0; k < 3; ++k) acc = acc + sg[k] * p.Ts[4 * k + c];
+                    out->phi_s_S[c] = -p.J * fs->K_inv * acc;
+                }
+            } else {
+                out->phi_s_S[0] = out->phi_s;
+            }
+        }
+        // assemble_phi_d_M_space, panel.f90:2866-2914
+        double mu6[6] = {m[0], m[1], m[2], 0., 0., 0.};
+        double mu6a[6] = {0., 0., 0., 0., 0., 0.};
+        const int md = p.order == 2 ? 6 : 3;
+        if (p.order == 2) {
+            mu6[3] = 0.5 * I.hH113 * (g.P_ls[0] * g.P_ls[0]) + g.h * (g.P_ls[0] * I.H213 + 0.5 * I.H313);
+            mu6[4] = I.hH113 * g.P_ls[0] * g.P_ls[1] + g.h * (g.P_ls[1] * I.H213 + g.P_ls[0] * I.H123 + I.H223);
+            mu6[5] = 0.5 * I.hH113 * (g.P_ls[1] * g.P_ls[1]) + g.h * (g.P_ls[1] * I.H123 + 0.5 * I.H133);
+        }
+        {   // forward-error scale of the six parameters-space influences (tests only)
+            double s2a = 0., s3a = 0.;
+            for (int i = 0; i < 3; ++i) s2a += std::fabs(g.v_xi[i] * I.F111[i]);
+            for (int i = 0; i < 3; ++i) s3a += std::fabs(g.v_eta[i] * I.F111[i]);
+            const double x = std::fabs(g.P_ls[0]), y = std::fabs(g.P_ls[1]), ah = std::fabs(g.h);
+            double sx211 = 0., sx121 = 0., se121 = 0., h111a = 0.;
+            for (int i = 0; i < 3; ++i) sx211 += std::fabs(g.v_xi[i] * I.F211[i]);
+            for (int i = 0; i < 3; ++i) sx121 += std::fabs(g.v_xi[i] * I.F121[i]);
+            for (int i = 0; i < 3; ++i) se121 += std::fabs(g.v_eta[i] * I.F121[i]);
+            for (int i = 0; i < 3; ++i) h111a += std::fabs(g.a[i] * I.F111[i]);
+            h111a += ah * I.hH113_abs;
+            mu6a[0] = I.hH113_abs;
+            mu6a[1] = I.hH113_abs * x + ah * s2a;
+            mu6a[2] = I.hH113_abs * y + ah * s3a;
+            mu6a[3] = 0.5 * I.hH113_abs * x * x + ah * (x * s2a + 0.5 * (h111a + sx211));
+            mu6a[4] = I.hH113_abs * x * y + ah * (y * s2a + x * s3a + sx121);
+            mu6a[5] = 0.5 * I.hH113_abs * y * y + ah * (y * s3a + 0.5 * (h111a + se121));
+        }
+        for (int c = 0; c < p.M_dim; ++c) {
+            double acc = 0., acc_a = 0.;
+            for (int k = 0; k < md; ++k) acc = acc + mu6[k] * p.T6[6 * k + c];
+            for (int k = 0; k < md; ++k) acc_a += mu6a[k] * std::fabs(p.T6[6 * k + c]);
+            out->phi_d_M[c] = I.s * fs->K_inv * acc;
+            out->phi_d_M_abs[c] = fs->K_inv * acc_a;
+        }
     }
     // assemble_v_s_S_space (order 1), panel.f90:3029-3072: local (r H213, s H123, -rs hH113), times -K_inv J, to global
     {
@@ -518,6 +624,28 @@ extern "C" int orc_assemble_n(const ml_flow* fs, const ml_panel_soa* body, const
                     orc_pair_influence(fs, body, j, img, Pt, &o);
                     if (!o.in_dod) continue;  // panel_solver.f90:1448 / 1462
                     bool mirrored_panel = (img == 1) && map->asym_flow;  // :1470-1471
+                    if (body->order2) {
+                        // update_system_row, panel_solver.f90:1203-1287, with the panel's own S_dim / M_dim
+                        if (body->has_sources[j]) {
+                            for (int k = 0; k < body->S_dim[j]; ++k) {
+                                int ips = body->i_panel_s4[(size_t)j * 4 + k];
+                                int index;
+                                if (mirrored_panel) index = (ips >= N_panels) ? ips - N_panels : ips + N_panels;
+                                else index = (ips >= N_panels) ? ips - N_panels : ips;
+                                if (map->sigma_known[index]) I_known_i = I_known_i + o.phi_s_S[k] * map->sigma[index];
+                                else A_i[P[map->i_sigma_in_sys[index]]] += o.phi_s_S[k];
+                            }
+                        }
+                        for (int k = 0; k < body->M_dim[j]; ++k) {
+                            int iv = body->i_vert_d[(size_t)j * body->n_cols + k];
+                            int index;
+                            if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
+                            else index = (iv >= N_verts) ? iv - N_verts : iv;
+                            A_i[P[index]] = A_i[P[index]] + o.phi_d_M[k];
+                            if (A_abs) S_i[P[index]] += o.phi_d_M_abs[k];
+                        }
+                        continue;
+                    }
                     // update_system_row, panel_solver.f90:1203-1287 (S_dim = 1, M_dim = 3)
                     if (body->has_sources[j]) {
                         int ips = body->i_panel_s[j];

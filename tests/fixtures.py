@@ -60,6 +60,12 @@ def golden_input(name: str):
     return inp, case["expect"], case["tol"]
 
 
+def oracle_slack(name: str) -> float:
+    """Factor on the reference's tolerances for the oracle run of a case (1 unless the fixture documents why not)."""
+    case = next(c for c in goldens()["cases"] if c["name"] == name)
+    return float(case.get("oracle_slack", 1.0))
+
+
 def comparison_names():
     return [c["name"] for c in goldens().get("comparisons", [])]
 

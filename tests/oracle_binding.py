@@ -26,7 +26,10 @@ class OrcPairOut(C.Structure):
     _fields_ = [("in_dod", C.c_int), ("edges_in_dod", C.c_int * 3), ("F111", C.c_double * 3),
                 ("hH113", C.c_double), ("H111", C.c_double), ("H213", C.c_double), ("H123", C.c_double),
                 ("h", C.c_double), ("phi_s", C.c_double), ("phi_d", C.c_double * 3),
-                ("phi_d_abs", C.c_double * 3), ("v_s", C.c_double * 3), ("v_d", C.c_double * 9)]
+                ("phi_d_abs", C.c_double * 3), ("v_s", C.c_double * 3), ("v_d", C.c_double * 9),
+                ("phi_s_S", C.c_double * 4), ("phi_d_M", C.c_double * 6), ("phi_d_M_abs", C.c_double * 6),
+                ("F121", C.c_double * 3), ("F211", C.c_double * 3), ("H211", C.c_double), ("H121", C.c_double),
+                ("H313", C.c_double), ("H223", C.c_double), ("H133", C.c_double)]
 
 
 _lib = None
