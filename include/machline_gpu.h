@@ -187,6 +187,12 @@ ml_status ml_set_A(ml_ctx *ctx, int row0, int nrows, const double *src_colmajor,
 /* Pair count of the last ml_assemble on this context: local rows x (body records + wake records). */
 long long ml_pair_count(const ml_ctx *ctx);
 
+/* panel_solver_check_system (panel_solver.f90:1709-1764; run when solver.run_checks is set, :1828-1831) on the resident
+   system: ML_NAN_IN_SYSTEM when A or b = BC - I_known holds a NaN, else ML_UNINFLUENCED when a row of A (a control point
+   that nothing influences) or a column (a vertex that exerts no influence) is entirely zero, else ML_OK.  n_zero_rows /
+   n_zero_cols (either may be NULL) receive the counts.  With a communicator the verdict covers all shards. */
+ml_status ml_check_system(ml_ctx *ctx, const double *BC, int *n_zero_rows, int *n_zero_cols);
+
 /* ---- hot path 2: dense solve ------------------------------------------------------------------ */
 /* BC[n_cp] is the boundary-condition vector in row order (panel_solver.f90:1104-1159); the library
    forms b = BC - I_known (:1818), applies the reference's "preconditioner", dispatches on

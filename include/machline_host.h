@@ -34,6 +34,7 @@ typedef struct mlh_solver_settings {   /* solver.* keys after defaults (panel_so
     char formulation[48];
     int sort_system;
     int write_A_and_b;
+    int run_checks;         /* solver.run_checks (main.f90:66 / panel_solver.f90:1828): check_system before the solve */
 } mlh_solver_settings;
 
 typedef struct mlh_results {

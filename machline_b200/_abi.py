@@ -61,7 +61,7 @@ class MlhCpTable(C.Structure):
 
 class MlhSolverSettings(C.Structure):
     _fields_ = [("opts", MlSolverOpts), ("matrix_solver_name", C.c_char * 16), ("formulation", C.c_char * 48),
-                ("sort_system", C.c_int), ("write_A_and_b", C.c_int)]
+                ("sort_system", C.c_int), ("write_A_and_b", C.c_int), ("run_checks", C.c_int)]
 
 
 class MlhResults(C.Structure):

@@ -26,7 +26,7 @@ DRIVER_EXE = PKG / "machline_b200.exe"
 
 HOST_SOURCES = ["flow.cpp", "mesh_io.cpp", "panel_setup.cpp", "surface_mesh.cpp", "wake.cpp",
                 "solver_setup.cpp", "capi.cpp"]
-GPU_SOURCES = ["capi.cu", "aic_kernels.cu", "aic_sub.cu", "aic_sup.cu", "solve_kernels.cu", "lu_kernels.cu", "lu_sharded.cu", "seq_solvers.cu", "peaks.cu"]
+GPU_SOURCES = ["capi.cu", "aic_kernels.cu", "aic_sub.cu", "aic_sup.cu", "aic_sub_ho.cu", "aic_sup_ho.cu", "solve_kernels.cu", "lu_kernels.cu", "lu_sharded.cu", "seq_solvers.cu", "peaks.cu"]
 
 # The image exports CXX=/opt/gcc/bin/g++ (a wrapper without libgomp.spec); the system compiler on
 # PATH is the complete one.
@@ -36,7 +36,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # The supersonic assembly kernel evaluates the reference's predicates operation by operation: no FMA
 # contraction there (csrc/gpu/pair_influence.cuh).  The solver kernels use explicit fma().
-PER_FILE_FLAGS = {"aic_sup.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"aic_sup.cu": ["-fmad=false"], "aic_sup_ho.cu": ["-fmad=false"]}
 
 
 def _newer(target: Path, deps) -> bool:

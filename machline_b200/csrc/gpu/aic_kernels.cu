@@ -22,6 +22,36 @@ __global__ void zero_columns_kernel(double* A, int ld, const int* cols, int n_co
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ld; i += gridDim.x * blockDim.x) col[i] = 0.;
 }
 
+// check_system (panel_solver.f90:1709-1764): one CTA per column; row_nz[r] / col_nz[c] = 1 when the row / column holds a
+// non-zero, flags[0] = 1 when an entry is NaN.
+__global__ void check_system_kernel(const double* __restrict__ A, int ld, int n_rows, unsigned char* row_nz, unsigned char* col_nz,
+                                    int* flags) {
+    const double* col = A + (size_t)blockIdx.x * ld;
+    int any = 0, nan = 0;
+    for (int r = threadIdx.x; r < n_rows; r += blockDim.x) {
+        const double v = col[r];
+        if (v != v) nan = 1;
+        else if (v != 0.) {
+            any = 1;
+            row_nz[r] = 1;   // benign race: every writer stores the same value
+        }
+    }
+    any = __syncthreads_or(any);
+    nan = __syncthreads_or(nan);
+    if (threadIdx.x == 0) {
+        col_nz[blockIdx.x] = (unsigned char)any;
+        if (nan) atomicOr(flags, 1);
+    }
+}
+
+cudaError_t launch_check_system(Ctx* c, const double* A, int ld, int n_rows, int n_cols, unsigned char* row_nz, unsigned char* col_nz,
+                                int* flags) {
+    if (n_cols <= 0) return cudaSuccess;
+    check_system_kernel<<<n_cols, 256, 0, c->stream>>>(A, ld, n_rows, row_nz, col_nz, flags);
+    c->launches += 1;
+    return cudaGetLastError();
+}
+
 FlowConst make_flow_const(const ml_flow& f) {
     FlowConst h;
     for (int i = 0; i < 3; ++i) h.c_hat[i] = f.c_hat_g[i];
@@ -33,10 +63,11 @@ FlowConst make_flow_const(const ml_flow& f) {
 }
 
 int aic_chunk_records(int tile_rows) { return tile_rows <= 8 ? 128 : 64; }
-int aic_record_stride(bool supersonic) { return supersonic ? R_SUP_STRIDE : R_SUB_STRIDE; }
+int aic_record_stride(bool supersonic, bool ho) { return record_stride(supersonic, ho); }
 int aic_list_bytes(int chunk_records) { return list_bytes(chunk_records); }
 
 cudaError_t launch_aic(Ctx* c, const AicLaunch& L, bool supersonic) {
+    if (L.ho) return supersonic ? launch_aic_supersonic_ho(c, L) : launch_aic_subsonic_ho(c, L);
     return supersonic ? launch_aic_supersonic(c, L) : launch_aic_subsonic(c, L);
 }
 

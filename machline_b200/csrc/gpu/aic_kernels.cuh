@@ -68,16 +68,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // generic-proxy reads of a buffer must be ordered before the async proxy overwrites it
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <bool SUP, int C>
+template <bool SUP, int C, bool HO = false>
 struct AicSmem {
-    static constexpr int STRIDE = SUP ? R_SUP_STRIDE : R_SUB_STRIDE;
+    static constexpr int STRIDE = record_stride(SUP, HO);
+    static constexpr int ND = HO ? 6 : 3;       // doublet coefficients per pair (M_dim <= 6 for higher-order tables)
     static constexpr int REC_BYTES = C * STRIDE * 8;
     static constexpr int LIST_BYTES = list_bytes(C);
     static constexpr int MAXI = list_max_items(C);
     static constexpr int REC_OFF = 0;
     static constexpr int LIST_OFF = (REC_BYTES + 127) / 128 * 128;
     static constexpr int STAGE_OFF = (LIST_OFF + 2 * LIST_BYTES + 127) / 128 * 128;
-    static constexpr int SLOTS = SUP ? 4 : 3;   // staged values per (record, row): three doublet coefficients (+ the source term)
+    static constexpr int SLOTS = ND + (SUP ? 1 : 0);   // staged values per (record, row): the doublet coefficients (+ the source term)
     static constexpr int stage_bytes(int R) { return C * SLOTS * R * 8; }
     static constexpr int queue_bytes(int R) { return SUP ? R * C * 2 : 0; }   // per-row queues of in-DoD records (u16)
     static constexpr int total(int R) { return STAGE_OFF + stage_bytes(R) + queue_bytes(R); }
@@ -85,9 +86,12 @@ struct AicSmem {
 
 // VEL: Neumann rows (velocity influences projected on the row's direction, L.row_nB) -- a separate instantiation, so that the
 // Dirichlet kernel carries neither the extra registers nor the branch
-template <bool SUP, int R, int C, bool VEL = false>
+// HO: higher-order table (records with the extension of panel_record.h, six doublet coefficients per pair)
+template <bool SUP, int R, int C, bool VEL = false, bool HO = false>
 __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_assemble_kernel(const AicLaunch L) {
-    using S = AicSmem<SUP, C>;
+    using S = AicSmem<SUP, C, HO>;
+    constexpr int ND = S::ND;
+    static_assert(!(HO && VEL), "velocity influences of higher-order panels are not built");
     constexpr int SUBS = AIC_THREADS / R;   // records evaluated concurrently by the CTA
     constexpr int CPW = 32 / R;             // columns one warp handles concurrently in phase 2
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -150,15 +154,19 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
                 for (int r = sub0; r < C; r += SUBS) {
                     const double* rec = s_rec + r * S::STRIDE;
                     const int flags = reinterpret_cast<const int*>(rec + R_FLAGS)[0];
-                    double ps = 0., pd[3] = {0., 0., 0.};
+                    double ps = 0., pd[ND] = {};
                     if (active && (flags & RF_EVAL)) {
-                        pair_influence<false>(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, ps, pd, nB);
-                        if (flags & RF_SOURCE) Ik = Ik + ps * rec[R_SIGMA];   // panel_solver.f90:1245-1246
+                        if constexpr (HO) {
+                            pair_influence_subsonic_ho(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, ps, pd);
+                            if (flags & RF_SOURCE) Ik = Ik + ps;   // the known strengths are folded into the record
+                        } else {
+                            pair_influence<false>(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, ps, pd, nB);
+                            if (flags & RF_SOURCE) Ik = Ik + ps * rec[R_SIGMA];   // panel_solver.f90:1245-1246
+                        }
                     }
-                    double* st = s_stage + (size_t)(r * 3) * R + row_l;
-                    st[0] = pd[0];
-                    st[R] = pd[1];
-                    st[2 * R] = pd[2];
+                    double* st = s_stage + (size_t)(r * S::SLOTS) * R + row_l;
+#pragma unroll
+                    for (int k = 0; k < ND; ++k) st[k * R] = pd[k];
                 }
                 __syncthreads();
                 live = 1;
@@ -183,11 +191,10 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
                         s_q[row_l * C + base + __popc(mine & ((1u << lane) - 1u))] =
                             (unsigned short)(r | ((int)e_in[0] << 8) | ((int)e_in[1] << 9) | ((int)e_in[2] << 10));
                     } else {
-                        double* st = s_stage + (size_t)(r * 4) * R + row_l;
-                        st[0] = 0.;
-                        st[R] = 0.;
-                        st[2 * R] = 0.;
-                        if (chunk_src) st[3 * R] = 0.;
+                        double* st = s_stage + (size_t)(r * S::SLOTS) * R + row_l;
+#pragma unroll
+                        for (int k = 0; k < ND; ++k) st[k * R] = 0.;
+                        if (chunk_src) st[ND * R] = 0.;
                     }
                 }
                 __syncthreads();
@@ -200,13 +207,13 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
                     const double* rec = s_rec + r * S::STRIDE;
                     const int flags = reinterpret_cast<const int*>(rec + R_FLAGS)[0];
                     const bool e_in[3] = {(e & 0x100u) != 0, (e & 0x200u) != 0, (e & 0x400u) != 0};
-                    double ps = 0., pd[3] = {0., 0., 0.};
-                    pair_eval_supersonic(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, e_in, ps, pd, nB);
-                    double* st = s_stage + (size_t)(r * 4) * R + row_l;
-                    st[0] = pd[0];
-                    st[R] = pd[1];
-                    st[2 * R] = pd[2];
-                    if (chunk_src) st[3 * R] = (flags & RF_SOURCE) ? ps * rec[R_SIGMA] : 0.;
+                    double ps = 0., pd[ND] = {};
+                    if constexpr (HO) pair_eval_supersonic_ho(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, e_in, ps, pd);
+                    else pair_eval_supersonic(fc, rec, Px, Py, Pz, (flags & RF_MIRROR) != 0, e_in, ps, pd, nB);
+                    double* st = s_stage + (size_t)(r * S::SLOTS) * R + row_l;
+#pragma unroll
+                    for (int k = 0; k < ND; ++k) st[k * R] = pd[k];
+                    if (chunk_src) st[ND * R] = (flags & RF_SOURCE) ? (HO ? ps : ps * rec[R_SIGMA]) : 0.;
                 }
                 // a chunk entirely outside every row's domain of dependence adds only zeros -> phase 2 is skipped
                 live = __syncthreads_or(qn > 0);
@@ -214,7 +221,7 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
                 if (live && chunk_src) {
                     // known-source terms of this chunk, in the fixed order (records sub0, sub0 + SUBS, ...) of the subsonic kernel
 #pragma unroll 1
-                    for (int r = sub0; r < C; r += SUBS) Ik = Ik + s_stage[(size_t)(r * 4 + 3) * R + row_l];   // panel_solver.f90:1245-1246
+                    for (int r = sub0; r < C; r += SUBS) Ik = Ik + s_stage[(size_t)(r * S::SLOTS + ND) * R + row_l];   // panel_solver.f90:1245-1246
                 }
             }
             if (tid == 0 && t + 1 < L.n_chunks) {
@@ -271,11 +278,11 @@ __global__ void __launch_bounds__(AIC_THREADS, SUP ? 2 : ML_AIC_SUB_CTAS) aic_as
     }
 }
 
-template <bool SUP, int R, int C, bool VEL = false>
+template <bool SUP, int R, int C, bool VEL = false, bool HO = false>
 static cudaError_t launch_aic_t(Ctx* c, const AicLaunch& L) {
-    using S = AicSmem<SUP, C>;
+    using S = AicSmem<SUP, C, HO>;
     const size_t smem = S::total(R);
-    auto kern = aic_assemble_kernel<SUP, R, C, VEL>;
+    auto kern = aic_assemble_kernel<SUP, R, C, VEL, HO>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int occ = 1;

@@ -1,0 +1,12 @@
+// subsonic higher-order instantiation of the assembly kernel (quadratic doublets, linear sources; geometry.singularity_order =
+// "higher"); compiled with FMA contraction as aic_sub.cu (see pair_influence.cuh)
+#include "aic_kernels.cuh"
+
+namespace mlgpu {
+
+cudaError_t launch_aic_subsonic_ho(Ctx* c, const AicLaunch& L) {
+    if (L.row_nB || L.tile_rows != 8) return cudaErrorInvalidValue;   // Dirichlet rows, 8-row tiles (capi.cu: prepare)
+    return launch_aic_t<false, 8, 64, false, true>(c, L);
+}
+
+}  // namespace mlgpu

@@ -53,9 +53,9 @@ __global__ void __launch_bounds__(256) dod_census_kernel(const double* __restric
 }
 
 cudaError_t launch_dod_census(Ctx* c, const double* recs, int n_rec_slots, const double* cp_xyz, const unsigned char* row_active,
-                              int n_rows, int n_rows_pad, const FlowConst& fc, unsigned long long* d_counts) {
+                              int n_rows, int n_rows_pad, const FlowConst& fc, unsigned long long* d_counts, int stride) {
     dim3 grid((n_rows + 255) / 256, 64);
-    dod_census_kernel<<<grid, 256, 0, c->stream>>>(recs, n_rec_slots, R_SUP_STRIDE, cp_xyz, row_active, n_rows, n_rows_pad, fc, d_counts);
+    dod_census_kernel<<<grid, 256, 0, c->stream>>>(recs, n_rec_slots, stride, cp_xyz, row_active, n_rows, n_rows_pad, fc, d_counts);
     c->launches += 1;
     return cudaGetLastError();
 }

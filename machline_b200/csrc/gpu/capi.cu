@@ -39,6 +39,22 @@ void HostPanelTable::copy_from(const ml_panel_soa* t) {
     else has_sources.assign(np, 0);
     if (t->image_present) image_present.assign(t->image_present, t->image_present + np);
     else image_present.assign(np, n_images > 1 ? 1 : 0);
+    order2 = t->order2;
+    if (order2) {
+        order.assign(t->order, t->order + np);
+        M_dim.assign(t->M_dim, t->M_dim + np);
+        S_dim.assign(t->S_dim, t->S_dim + np);
+        i_panel_s4.assign(t->i_panel_s4, t->i_panel_s4 + np * 4);
+        T_mu6.assign(t->T_mu6, t->T_mu6 + nr * 36);
+        T_sigma.assign(t->T_sigma, t->T_sigma + nr * 12);
+    } else {
+        order.clear();
+        M_dim.clear();
+        S_dim.clear();
+        i_panel_s4.clear();
+        T_mu6.clear();
+        T_sigma.clear();
+    }
 }
 
 extern "C" int ml_abi_version(void) { return 1; }
@@ -173,13 +189,21 @@ extern "C" ml_status ml_set_flow(ml_ctx* c, const ml_flow* f) {
 
 extern "C" ml_status ml_set_panels(ml_ctx* c, const ml_panel_soa* body, const ml_panel_soa* wake) {
     if (!c || !body) return ML_BAD_ARGUMENT;
-    if (body->n_panels <= 0 || (body->n_images != 1 && body->n_images != 2) || body->n_cols != 3)
-        return c->fail(ML_UNSUPPORTED, "body table: only lower-order panels (M_dim = 3) are supported");
+    if (body->n_panels <= 0 || (body->n_images != 1 && body->n_images != 2)) return c->fail(ML_BAD_ARGUMENT, "body table: n_panels / n_images");
+    if (body->order2) {   // higher-order table: quadratic doublets / linear sources (panel.f90:544-969)
+        if (body->n_cols != 6 || !body->order || !body->M_dim || !body->S_dim || !body->i_panel_s4 || !body->T_mu6 || !body->T_sigma)
+            return c->fail(ML_BAD_ARGUMENT, "higher-order body table: n_cols must be 6 and order / M_dim / S_dim / i_panel_s4 / T_mu6 / T_sigma set");
+        for (int j = 0; j < body->n_panels; ++j)
+            if (body->M_dim[j] < 3 || body->M_dim[j] > 6 || body->S_dim[j] < 0 || body->S_dim[j] > 4)
+                return c->fail(ML_BAD_ARGUMENT, "higher-order body table: M_dim must be 3..6 and S_dim 0..4");
+    } else if (body->n_cols != 3) {
+        return c->fail(ML_BAD_ARGUMENT, "lower-order body table must carry 3 doublet ids per panel");
+    }
     for (size_t i = 0; i < (size_t)body->n_panels * body->n_images; ++i)
         if (body->r[i] != 1) return c->fail(ML_UNSUPPORTED, "superinclined panels are not allowed (panel.f90:439-443)");
     c->body.copy_from(body);
     if (wake && wake->n_panels > 0) {
-        if (wake->n_cols != 6) return c->fail(ML_BAD_ARGUMENT, "wake table must carry 6 doublet ids per panel");
+        if (wake->n_cols != 6 || wake->order2) return c->fail(ML_BAD_ARGUMENT, "wake table must be lower order with 6 doublet ids per panel");
         c->wake.copy_from(wake);
     } else {
         c->wake = HostPanelTable();
@@ -295,7 +319,9 @@ struct HostRecord {   // one evaluated (panel, image) in stream order, with its 
     const HostPanelTable* table;
     int j, img, flags, n_slots;
     double sigma_val;
-    int cols[6];      // body: permuted columns of slots 0..2; wake: permuted columns of slots 0..5 (3..5 subtract)
+    int cols[6];      // body: permuted columns of slots 0..2 (0..M_dim-1 in a higher-order table); wake: permuted columns of
+                      // slots 0..5 (3..5 subtract)
+    double w[3];      // higher-order table: T_sigma times the known strengths of the panel's source panels (panel_record.h)
 };
 }  // namespace
 
@@ -308,7 +334,11 @@ static ml_status prepare(ml_ctx* c) {
     const int N_verts = m.n_verts, N_panels = m.n_body_panels;
     if (N_panels != c->body.n_panels) return c->fail(ML_BAD_ARGUMENT, "n_body_panels mismatch");
     const bool sup = c->flow.supersonic != 0;
-    const int STRIDE = aic_record_stride(sup);
+    const bool ho = c->body.order2 != 0;
+    if (ho && !c->cp_n_g.empty())
+        return c->fail(ML_UNSUPPORTED, "velocity (Neumann) rows with higher-order panels are not built (panel.f90:2686-2763 recursions)");
+    c->ho = ho;
+    const int STRIDE = aic_record_stride(sup, ho);
     const std::vector<int>& P = c->P;
 
     // ---- rows: this context's shard of the permuted system ----
@@ -346,8 +376,9 @@ static ml_status prepare(ml_ctx* c) {
             int v = std::atoi(e);
             if (v == 4 || v == 8 || v == 16 || v == 32) R = v;
         }
+        if (ho) R = 8;   // one instantiation of the higher-order kernels (aic_sub_ho.cu / aic_sup_ho.cu): 8-row tiles, 64-record chunks
         c->tile_rows = R;
-        c->chunk_records = aic_chunk_records(R);
+        c->chunk_records = ho ? 64 : aic_chunk_records(R);
     }
     const int C = c->chunk_records;
 
@@ -362,16 +393,31 @@ static ml_status prepare(ml_ctx* c) {
             hr.table = &c->body;
             hr.j = j;
             hr.img = img;
-            hr.n_slots = 3;
-            for (int k = 0; k < 3; ++k) {
-                int iv = c->body.i_vert_d[(size_t)j * 3 + k], index;
+            hr.n_slots = ho ? c->body.M_dim[j] : 3;
+            for (int k = 0; k < hr.n_slots; ++k) {
+                int iv = c->body.i_vert_d[(size_t)j * c->body.n_cols + k], index;
                 if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
                 else index = (iv >= N_verts) ? iv - N_verts : iv;
                 if (index < 0 || index >= m.n_unknown) return c->fail(ML_BAD_ARGUMENT, "doublet index out of range");
                 hr.cols[k] = P[index];
             }
             hr.flags = RF_EVAL | (img == 1 ? RF_MIRROR : 0);
-            if (c->body.has_sources[j]) {
+            if (ho) {
+                // update_system_row over the panel's S_dim source panels (panel_solver.f90:1220-1253), the strengths folded
+                // with T_sigma into three weights on the parameter-space influences
+                hr.w[0] = hr.w[1] = hr.w[2] = 0.;
+                if (c->body.has_sources[j]) {
+                    const size_t rec = (size_t)j + (size_t)img * c->body.n_panels;
+                    for (int k = 0; k < c->body.S_dim[j]; ++k) {
+                        int ips = c->body.i_panel_s4[(size_t)j * 4 + k], index;
+                        if (mirrored_panel) index = (ips >= N_panels) ? ips - N_panels : ips + N_panels;
+                        else index = (ips >= N_panels) ? ips - N_panels : ips;
+                        if (index < 0 || index >= m.n_sigma) return c->fail(ML_BAD_ARGUMENT, "source index out of range");
+                        for (int a = 0; a < 3; ++a) hr.w[a] += c->body.T_sigma[rec * 12 + 4 * a + k] * c->sigma[index];
+                    }
+                    hr.flags |= RF_SOURCE;
+                }
+            } else if (c->body.has_sources[j]) {
                 int ips = c->body.i_panel_s[j], index;
                 if (mirrored_panel) index = (ips >= N_panels) ? ips - N_panels : ips + N_panels;
                 else index = (ips >= N_panels) ? ips - N_panels : ips;
@@ -455,7 +501,21 @@ static ml_status prepare(ml_ctx* c) {
         for (size_t r0 = 0; r0 < n_here; ++r0) {
             const HostRecord& hr = src[first + r0];
             const size_t r = (size_t)pos[r0];
-            pack_record(recs.data() + ((size_t)chunk * C + r) * STRIDE, STRIDE, sup, view_of(*hr.table), hr.j, hr.img, hr.sigma_val, hr.flags);
+            double* const rec_p = recs.data() + ((size_t)chunk * C + r) * STRIDE;
+            pack_record(rec_p, STRIDE, sup, view_of(*hr.table), hr.j, hr.img, hr.sigma_val, hr.flags);
+            if (ho) {
+                if (wake) {   // wake panels stay lower order: their 3 x 3 T_mu in the upper left corner, no sources
+                    double T6[36] = {0.};
+                    const double* T3 = hr.table->T_mu.data() + 9 * ((size_t)hr.j + (size_t)hr.img * hr.table->n_panels);
+                    for (int a = 0; a < 3; ++a)
+                        for (int bb = 0; bb < 3; ++bb) T6[6 * a + bb] = T3[3 * a + bb];
+                    const double w0[3] = {0., 0., 0.};
+                    pack_record_ho(rec_p, sup, T6, w0);
+                } else {
+                    pack_record_ho(rec_p, sup, hr.table->T_mu6.data() + 36 * ((size_t)hr.j + (size_t)hr.img * hr.table->n_panels), hr.w);
+                }
+            }
+            const int n_stage = (ho ? 6 : 3) + (sup ? 1 : 0);   // staged values per record and row (aic_kernels.cuh: SLOTS)
             for (int k = 0; k < hr.n_slots; ++k) {
                 const int col = hr.cols[k];
                 if (slot_of_col[col] < 0) {
@@ -463,7 +523,9 @@ static ml_status prepare(ml_ctx* c) {
                     order.push_back(col);
                     per.emplace_back();
                 }
-                per[slot_of_col[col]].push_back((unsigned)(r * (sup ? 4 : 3) + (k % 3)) * item_scale | (k >= 3 ? ITEM_NEG : 0u));
+                // a wake panel's items 3..5 (bottom side) read its slots 0..2 again, negated (panel.f90:2909-2912)
+                const int slot = wake ? k % 3 : k;
+                per[slot_of_col[col]].push_back((unsigned)(r * n_stage + slot) * item_scale | ((wake && k >= 3) ? ITEM_NEG : 0u));
             }
         }
         int n_items = 0;
@@ -598,6 +660,7 @@ static ml_status run_assembly_kernels(ml_ctx* c) {
     L.lists = c->d_lists.p;
     L.n_chunks = c->n_chunks;
     L.tile_rows = c->tile_rows;
+    L.ho = c->ho ? 1 : 0;
     L.cp_xyz = c->d_cp_xyz.p;
     L.row_active = c->d_row_active.p;
     L.row_nB = c->velocity_rows ? c->d_row_nB.p : nullptr;
@@ -679,7 +742,7 @@ extern "C" ml_status ml_dod_census(ml_ctx* c, long long* counts4) {
     ML_CUDA(c, d.alloc(4));
     ML_CUDA(c, cudaMemsetAsync(d.p, 0, 4 * sizeof(unsigned long long), c->stream));
     ML_CUDA(c, launch_dod_census(c, c->d_recs.p, c->n_chunks * c->chunk_records, c->d_cp_xyz.p, c->d_row_active.p, c->n_rows, c->n_rows_pad,
-                                 make_flow_const(c->flow), d.p));
+                                 make_flow_const(c->flow), d.p, aic_record_stride(true, c->ho)));
     unsigned long long h[4];
     ML_CUDA(c, cudaMemcpyAsync(h, d.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -718,6 +781,64 @@ extern "C" ml_status ml_set_A(ml_ctx* c, int row0, int nrows, const double* src,
     ML_CUDA(c, cudaMemcpy2DAsync(c->d_A.p + lr, (size_t)c->ld * sizeof(double), src, (size_t)ld * sizeof(double),
                                  (size_t)nrows * sizeof(double), c->n_cols, cudaMemcpyHostToDevice, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    return ML_OK;
+}
+
+extern "C" ml_status ml_check_system(ml_ctx* c, const double* BC, int* n_zero_rows, int* n_zero_cols) {
+    if (!c || !BC) return ML_BAD_ARGUMENT;
+    if (!c->assembled) return c->fail(ML_NOT_READY, "ml_check_system before ml_assemble");
+    ML_CUDA(c, cudaSetDevice(c->device));
+    if (n_zero_rows) *n_zero_rows = 0;
+    if (n_zero_cols) *n_zero_cols = 0;
+    // b = BC - I_known (panel_solver.f90:1818) on this context's rows
+    bool nan = false;
+    for (int i = 0; i < c->n_rows; ++i) {
+        const double b = BC[c->local_rows[i]] - c->h_I_known[i];
+        nan = nan || (b != b);
+    }
+    DevBuf<unsigned char> d_row, d_col;
+    DevBuf<int> d_flags;
+    ML_CUDA(c, d_row.alloc((size_t)c->n_rows + 1));
+    ML_CUDA(c, d_col.alloc((size_t)c->n_cols + 1));
+    ML_CUDA(c, d_flags.alloc(4));
+    ML_CUDA(c, cudaMemsetAsync(d_row.p, 0, (size_t)c->n_rows + 1, c->stream));
+    ML_CUDA(c, cudaMemsetAsync(d_col.p, 0, (size_t)c->n_cols + 1, c->stream));
+    ML_CUDA(c, cudaMemsetAsync(d_flags.p, 0, 4 * sizeof(int), c->stream));
+    ML_CUDA(c, launch_check_system(c, c->d_A.p, c->ld, c->n_rows, c->n_cols, d_row.p, d_col.p, d_flags.p));
+    std::vector<unsigned char> row_nz(c->n_rows), col_nz(c->n_cols);
+    int flags[4] = {0, 0, 0, 0};
+    // flags[1] = this shard's zero rows; summed over the ranks below.  Columns: a column is zero when it is zero on every shard.
+    ML_CUDA(c, cudaMemcpyAsync(row_nz.data(), d_row.p, c->n_rows, cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaMemcpyAsync(flags, d_flags.p, sizeof flags, cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    int zr = 0;
+    for (int i = 0; i < c->n_rows; ++i) zr += !row_nz[i];
+    int nan_flag = (flags[0] || nan) ? 1 : 0;
+#ifdef ML_HAVE_NCCL
+    if (c->world > 1) {
+        int h[2] = {nan_flag, zr};
+        ML_CUDA(c, cudaMemcpyAsync(d_flags.p, h, sizeof h, cudaMemcpyHostToDevice, c->stream));
+        if (ncclAllReduce(d_flags.p, d_flags.p, 2, ncclInt, ncclSum, c->comm, c->stream) != ncclSuccess ||
+            ncclAllReduce(d_col.p, d_col.p, c->n_cols, ncclUint8, ncclMax, c->comm, c->stream) != ncclSuccess)
+            return c->fail(ML_NCCL_ERROR, "allreduce of the system check");
+        ML_CUDA(c, cudaMemcpyAsync(h, d_flags.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+        ML_CUDA(c, cudaStreamSynchronize(c->stream));
+        nan_flag = h[0] != 0;
+        zr = h[1];
+    }
+#endif
+    ML_CUDA(c, cudaMemcpyAsync(col_nz.data(), d_col.p, c->n_cols, cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    int zc = 0;
+    for (int j = 0; j < c->n_cols; ++j) zc += !col_nz[j];
+    if (nan_flag) return c->fail(ML_NAN_IN_SYSTEM, "invalid value detected in A or b");
+    if (n_zero_rows) *n_zero_rows = zr;
+    if (n_zero_cols) *n_zero_cols = zc;
+    if (zr || zc) {
+        char msg[160];
+        std::snprintf(msg, sizeof msg, "%d control point(s) not influenced, %d unknown(s) exert no influence", zr, zc);
+        return c->fail(ML_UNINFLUENCED, msg);
+    }
     return ML_OK;
 }
 

@@ -19,6 +19,11 @@ struct HostPanelTable {  // deep copy of an ml_panel_soa
     std::vector<double> centr, A_g_to_ls, vertices_ls, n_hat_ls, b, sqrt_b, J, area, vert_g, T_mu;
     std::vector<int> r, i_vert_d, i_panel_s;
     std::vector<unsigned char> has_sources, image_present;
+    // higher-order tables (ml_panel_soa.order2)
+    int order2 = 0;
+    std::vector<unsigned char> order;
+    std::vector<int> M_dim, S_dim, i_panel_s4;
+    std::vector<double> T_mu6, T_sigma;
     void copy_from(const ml_panel_soa* t);
 };
 
@@ -88,6 +93,7 @@ struct AicLaunch {            // arguments of the assembly kernel (aic_kernels.c
     const unsigned char* lists;  // per-chunk scatter lists, n_chunks blocks of list_bytes(C)
     int n_chunks;             // body chunks, then wake chunks
     int tile_rows;            // R: rows owned by one CTA (32, 16 or 8)
+    int ho;                   // 1: higher-order table (records carry the extension of panel_record.h, six doublet slots per pair)
     const double* cp_xyz;     // [3][n_rows_pad] control-point coordinates by local row
     const unsigned char* row_active;  // [n_rows_pad] 1: row evaluates influences
     const double* row_nB;     // nullptr (potential rows) or [3][n_rows_pad]: direction of the velocity projection of each row
@@ -133,6 +139,7 @@ struct Ctx {
     int n_cp = 0;
     std::vector<double> cp_loc, cp_n_g;   // cp_n_g: empty, or the normals of Neumann rows
     bool velocity_rows = false;
+    bool ho = false;            // higher-order body table (ml_panel_soa.order2)
     std::vector<int> cp_bc, cp_row;
     ml_system_map map{};
     std::vector<int> P, i_sigma_in_sys;
@@ -201,10 +208,14 @@ FlowConst make_flow_const(const ml_flow& f);
 cudaError_t launch_aic(Ctx* c, const AicLaunch& L, bool supersonic);
 cudaError_t launch_strength_rows(Ctx* c, double* A, int ld, const int* rows, const int* colp, const int* colm, int n);
 cudaError_t launch_zero_columns(Ctx* c, double* A, int ld, const int* cols, int n_cols);
+cudaError_t launch_check_system(Ctx* c, const double* A, int ld, int n_rows, int n_cols, unsigned char* row_nz, unsigned char* col_nz,
+                                int* flags);
 cudaError_t launch_dod_census(Ctx* c, const double* recs, int n_rec_slots, const double* cp_xyz, const unsigned char* row_active,
-                              int n_rows, int n_rows_pad, const FlowConst& fc, unsigned long long* d_counts);   // aic_sup.cu
+                              int n_rows, int n_rows_pad, const FlowConst& fc, unsigned long long* d_counts, int stride);   // aic_sup.cu
 int aic_chunk_records(int tile_rows);
-int aic_record_stride(bool supersonic);
+int aic_record_stride(bool supersonic, bool ho = false);
+cudaError_t launch_aic_subsonic_ho(Ctx* c, const AicLaunch& L);     // aic_sub_ho.cu
+cudaError_t launch_aic_supersonic_ho(Ctx* c, const AicLaunch& L);   // aic_sup_ho.cu
 int aic_list_bytes(int chunk_records);
 
 // solve_kernels.cu / lu_kernels.cu

@@ -30,6 +30,18 @@ enum : int {
     R_SUP_STRIDE = 52    // supersonic record stride (416 B)
 };
 
+// Higher-order tables (quadratic doublets, linear sources; panel.f90:544-969): the record is the lower-order record followed
+// by an extension of R_HO_EXTRA doubles (so the strides stay even: 78 / 92 doubles).  Offsets relative to the extension:
+enum : int {
+    R_HO_T = 0,       // [36]  T_mu (6 x 6 row-major, mu_dim x M_dim zero padded; an order-1 panel carries its 3 x 3 upper left)
+    R_HO_W = 36,      // [3]   T_sigma (3 x S_dim) times the known strengths of the panel's S_dim source panels: the source
+                      //       influence of the pair on I_known is -J K_inv (phi_s_sigma_space . w)  (panel.f90:2838-2849 with
+                      //       panel_solver.f90:1245-1246 folded in); an order-1 panel has w = (sigma, 0, 0)
+    R_HO_EXTRA = 40
+};
+constexpr int record_stride(bool sup, bool ho) { return (sup ? R_SUP_STRIDE : R_SUB_STRIDE) + (ho ? R_HO_EXTRA : 0); }
+constexpr int record_ho_offset(bool sup) { return sup ? R_SUP_STRIDE : R_SUB_STRIDE; }
+
 enum : int { RF_EVAL = 1, RF_MIRROR = 2, RF_SOURCE = 4 };
 
 // ---- per-chunk scatter list (built on the host, staged next to the records) -------------------------------
@@ -39,9 +51,10 @@ enum : int { RF_EVAL = 1, RF_MIRROR = 2, RF_SOURCE = 4 };
 //   int  head[4]      : n_cols, n_items, flags (bit0: wake pass), spare
 //   int  col[6C]      : target column; bit 31 set = first chunk of the pass that touches it (start from 0)
 //   u16  beg[6C + 2]  : item range of column i = [beg[i], beg[i+1])
-//   u32  item[6C]     : byte offset of the staged value, (position_in_chunk * S + slot % 3) * R * 8 (R = tile rows, S = staged
-//                       values per record and row: 3 subsonic, 4 supersonic), with
-//                       bit 31 set when the item is subtracted (slot >= 3: bottom side of a wake panel)
+//   u32  item[6C]     : byte offset of the staged value, (position_in_chunk * S + slot) * R * 8 (R = tile rows, S = staged
+//                       values per record and row: 3 subsonic, 4 supersonic; 6 / 7 for higher-order tables), with
+//                       bit 31 set when the item is subtracted (the bottom side of a wake panel: its items 3..5 read the
+//                       slots 0..2 again)
 constexpr int list_max_items(int C) { return 6 * C; }
 constexpr int list_bytes(int C) { return ((16 + 4 * list_max_items(C) + 2 * (list_max_items(C) + 2) + 4 * list_max_items(C)) + 15) / 16 * 16; }
 constexpr unsigned ITEM_NEG = 0x80000000u;

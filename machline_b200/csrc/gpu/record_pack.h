@@ -43,4 +43,12 @@ inline void pack_record(double* rec, int stride, bool sup, const PanelView& t, i
     std::memcpy(rec + R_FLAGS, fl, sizeof fl);
 }
 
+// Higher-order extension of a record (panel_record.h): T6 = the image's 6 x 6 padded T_mu, w = its T_sigma applied to the
+// known strengths of the panel's source panels.
+inline void pack_record_ho(double* rec, bool sup, const double* T6, const double w[3]) {
+    double* ext = rec + record_ho_offset(sup);
+    for (int k = 0; k < 36; ++k) ext[R_HO_T + k] = T6[k];
+    for (int k = 0; k < 3; ++k) ext[R_HO_W + k] = w[k];
+}
+
 }  // namespace mlgpu

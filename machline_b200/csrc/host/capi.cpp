@@ -302,6 +302,7 @@ extern "C" int mlh_case_solver_settings(const mlh_case* h, mlh_solver_settings* 
     std::snprintf(o->formulation, sizeof o->formulation, "%s", s.formulation.c_str());
     o->sort_system = s.sort_system;
     o->write_A_and_b = s.write_A_and_b;
+    o->run_checks = h->c.run_checks;
     return 0;
 }
 

@@ -58,6 +58,7 @@ def lib() -> C.CDLL:
         L.ml_solve_dense.argtypes = [vp, C.c_int, dp, dp, C.POINTER(_abi.MlSolverOpts), dp,
                                      C.POINTER(_abi.MlSolveInfo)]
         L.ml_dod_census.argtypes = [vp, C.POINTER(C.c_longlong)]
+        L.ml_check_system.argtypes = [vp, dp, ip, ip]
         L.ml_device_system.argtypes = [vp, C.POINTER(dp), ip, ip, ip]
         L.ml_measure_peaks.argtypes = [vp, dp, dp]
         L.ml_measure_dmma_peak.argtypes = [vp, dp]
@@ -244,6 +245,16 @@ class Context:
         st = lib().ml_solve(self._h, C.byref(opts), _dp(BC), _dp(x), C.byref(info))
         self._check(st)
         return x, info
+
+    def check_system(self, BC: np.ndarray) -> tuple[int, int, int]:
+        """panel_solver_check_system (src/panel_solver.f90:1709-1764) on the resident system.  Returns (status, zero rows,
+        zero columns): status 0, 1 (NaN in A or b) or 2 (a control point not influenced / an unknown without influence)."""
+        BC = np.ascontiguousarray(BC, dtype=np.float64)
+        zr, zc = C.c_int(0), C.c_int(0)
+        st = lib().ml_check_system(self._h, _dp(BC), C.byref(zr), C.byref(zc))
+        if st not in (0, 1, 2):
+            self._check(st)
+        return st, zr.value, zc.value
 
     def solve_dense(self, A: np.ndarray, b: np.ndarray, opts: _abi.MlSolverOpts):
         A = np.asfortranarray(A, dtype=np.float64)

@@ -33,6 +33,15 @@ class RunResult:
     total_s: float
 
 
+class SolverStatus(RuntimeError):
+    """The solve ended with a non-zero solver_stat of the reference (1..4); report.json has been written with the code."""
+
+    def __init__(self, status: int, total_s: float):
+        super().__init__(f"solver status {status} ({_abi.ML_STATUS_NAMES.get(status, status)})")
+        self.status = status
+        self.total_s = total_s
+
+
 def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None,
              matrix_solver: str | None = None) -> RunResult:
     """`inp`: dict, JSON text or path of a MachLine input file."""
@@ -47,12 +56,29 @@ def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None
             opts.matrix_solver = _abi.SOLVERS.get(matrix_solver, _abi.SOLVERS["GMRES"])
         if case.settings.write_A_and_b:           # panel_solver.f90:1834, before the solve; files in the working directory
             vtk_out.write_system(ctx.get_A(), np.asarray(case.BC) - I_known)
-        x, info = ctx.solve(opts, case.BC)
+        if report_file is None:
+            report_file = case.input.get("output", {}).get("report_file")
+        # solver_stat of the reference (panel_solver.f90:1722-1761, 2006-2010; main.f90:140-176): 1 NaN in the system, 2 zero
+        # row / column (both from check_system, run when solver.run_checks is set), 3 singular (lu_decomp), 4 NaN residual.
+        # A non-zero status skips the post-processing and is written to the report, as the reference does.
+        solver_stat, info = 0, _abi.MlSolveInfo()
+        if case.settings.run_checks:
+            solver_stat = ctx.check_system(case.BC)[0]
+        if solver_stat == 0:
+            try:
+                x, info = ctx.solve(opts, case.BC)
+            except gpu.GpuError as e:
+                if e.status not in (1, 2, 3, 4):
+                    raise
+                solver_stat = e.status
+        if solver_stat != 0:
+            total = time.perf_counter() - t0
+            if report_file and report_file != "none":
+                case.write_report(report_file, info, solver_stat, total)
+            raise SolverStatus(solver_stat, total)
         v_inner = None if case.dirichlet else ctx.velocities_at(case, case.inner_points(), x)   # panel_solver.f90:2063-2066
         res = case.post(x, v_inner)
         total = time.perf_counter() - t0
-        if report_file is None:
-            report_file = case.input.get("output", {}).get("report_file")
         if report_file and report_file != "none":
             case.write_report(report_file, info, 0, total)
         body_file = case.input.get("output", {}).get("body_file")

@@ -34,6 +34,9 @@ void orc_pair_influence(const ml_flow *fs, const ml_panel_soa *t, int j, int img
 void orc_pair_batch(const ml_flow *fs, const ml_panel_soa *t, int n_pts, const double *pts, double *phi_d,
                     double *phi_d_abs, double *phi_s, unsigned char *in_dod);
 
+void orc_pair_batch_ho(const ml_flow *fs, const ml_panel_soa *t, int n_pts, const double *pts, double *phi_d6,
+                       double *phi_d6_abs, double *phi_s, unsigned char *in_dod);
+
 int orc_assemble(const ml_flow *fs, const ml_panel_soa *body, const ml_panel_soa *wake, const ml_system_map *map,
                  int n_cp, const double *cp_loc, const int *cp_bc, const int *row_perm, int row0, int nrows,
                  double *A_colmajor, int ld, double *I_known, int n_threads,

@@ -570,6 +570,31 @@ extern "C" void orc_pair_batch(const ml_flow* fs, const ml_panel_soa* t, int n_p
     }
 }
 
+// The same for a higher-order table: phi_d6[n_pts][n_rec][6] (the panel's M_dim strength-space influences, zero padded),
+// phi_d6_abs likewise, phi_s[n_pts][n_rec] = the sum of the panel's S_dim source influences.
+extern "C" void orc_pair_batch_ho(const ml_flow* fs, const ml_panel_soa* t, int n_pts, const double* pts, double* phi_d6,
+                                  double* phi_d6_abs, double* phi_s, unsigned char* in_dod) {
+    const int n_rec = t->n_panels * t->n_images;
+#pragma omp parallel for schedule(static)
+    for (int p = 0; p < n_pts; ++p) {
+        for (int r = 0; r < n_rec; ++r) {
+            orc_pair_out o;
+            const int j = r % t->n_panels;
+            orc_pair_influence(fs, t, j, r / t->n_panels, pts + 3 * (size_t)p, &o);
+            const size_t k = (size_t)p * n_rec + r;
+            const bool on = o.in_dod && t->area[j] > 0.;
+            in_dod[k] = on;
+            double s = 0.;
+            for (int c = 0; c < t->S_dim[j]; ++c) s += o.phi_s_S[c];
+            phi_s[k] = on ? s : 0.;
+            for (int c = 0; c < 6; ++c) {
+                phi_d6[6 * k + c] = (on && c < t->M_dim[j]) ? o.phi_d_M[c] : 0.;
+                phi_d6_abs[6 * k + c] = (on && c < t->M_dim[j]) ? o.phi_d_M_abs[c] : 0.;
+            }
+        }
+    }
+}
+
 // panel_solver.f90:1290-1501 + :1504-1706, Dirichlet / strength-matching rows.
 // Rows row0..row0+nrows-1 of the permuted system are computed; A is column-major nrows x n_unknown with
 // leading dimension ld, output row index = row - row0 (likewise I_known and A_abs).

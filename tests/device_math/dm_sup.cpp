@@ -5,3 +5,6 @@
 extern "C" void dm_batch_sup(const ml_flow* fs, const ml_panel_soa* t, int n_pts, const double* pts, double* d, double* s, unsigned char* in) {
     dm_batch_sup_impl(fs, t, n_pts, pts, d, s, in);
 }
+extern "C" void dm_batch_sup_ho(const ml_flow* fs, const ml_panel_soa* t, int n_pts, const double* pts, double* d, double* s, unsigned char* in) {
+    dm_batch_sup_impl_ho(fs, t, n_pts, pts, d, s, in);
+}

@@ -9,7 +9,9 @@ import oracle_binding as ob
 
 pytestmark = pytest.mark.gpu
 
-AIC_CASES = ["test_08", "test_13", "test_01", "test_15", "test_05", "test_20", "test_19"]
+AIC_CASES = ["test_08", "test_13", "test_01", "test_15", "test_05", "test_20", "test_19",
+             # higher-order panels (quadratic doublets, linear sources): subsonic Morino / source-free, supersonic, supersonic + wake
+             "test_04", "test_02", "test_16", "test_17"]
 
 
 def _rel_err(A, A_ref, S):
@@ -90,7 +92,9 @@ def test_aic_entries_match_oracle(ctx, name):
 # a 1e-12 tolerance, measured; 3.9e-7 with LU) is cond(A) times the 1e-16 libm difference in A itself.
 # Tests 15 and 18 (supersonic wake; cond 4e17 / 4e5 with a 1e-9 / 1e-10 force tolerance) sit at cond * eps as well.
 ILL_CONDITIONED = {"test_01": (20., 20.), "test_03": (20., 20.), "test_12": (20., 20.), "test_20": (1., 400.),
-                   "test_15": (1., 10.), "test_18": (1., 10.)}
+                   "test_15": (1., 10.), "test_18": (1., 10.),
+                   # the same meshes and flows with higher-order panels (test 02's matrix is singular: fixtures oracle_slack)
+                   "test_02": (20., 20.), "test_04": (20., 20.), "test_17": (1., 10.)}
 
 
 @pytest.mark.parametrize("name", fixtures.golden_case_names())
@@ -289,4 +293,30 @@ def test_gpu_aic_has_the_reference_singular_values(ctx, c):
     ctx.assemble()
     S = np.linalg.svd(ctx.get_A(), compute_uv=False)
     assert abs(S[0] - c["S_max"]) < 3e-13 and abs(S[-1] - c["S_min"]) < 3e-13
+    case.close()
+
+
+def test_check_system_statuses(ctx):
+    """ml_check_system = panel_solver_check_system (src/panel_solver.f90:1709-1764): status 0 on a healthy system, 2 when a row
+    (control point not influenced) or a column (unknown without influence) is entirely zero, 1 on a NaN in A or b."""
+    case, _, _ = fixtures.make_case("test_08")
+    ctx.set_case(case)
+    ctx.assemble()
+    assert ctx.check_system(case.BC) == (0, 0, 0)
+    A = ctx.get_A()
+    B = A.copy()
+    B[5, :] = 0.
+    B[11, :] = 0.
+    B[:, 7] = 0.
+    ctx.set_A(B)
+    assert ctx.check_system(case.BC) == (2, 2, 1)
+    B = A.copy()
+    B[3, 4] = np.nan
+    ctx.set_A(B)
+    assert ctx.check_system(case.BC)[0] == 1
+    ctx.set_A(A)
+    bc = np.array(case.BC, dtype=np.float64)
+    bc[2] = np.nan
+    assert ctx.check_system(bc)[0] == 1
+    assert ctx.check_system(case.BC) == (0, 0, 0)
     case.close()
