@@ -150,6 +150,18 @@ typedef struct ml_solve_info {
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 int  ml_abi_version(void);
 ml_status ml_ctx_create(ml_ctx **out, int device_id);
+/* Single-process multi-GPU context (the reference's main is one process, src/main.f90:133): ONE host thread
+   drives the two hot paths on n_dev devices through the same entry points as a single-device context -- ml_set_* take the
+   same tables, ml_assemble returns the whole I_known, ml_get_A / ml_set_A address any rows, ml_solve returns the whole x,
+   ml_check_system covers all shards.  Rows of the permuted system are dealt to the devices in contiguous blocks, or
+   block-cyclically (blocks of block_rows) after ml_multi_set_dealing (load balance of the sharded LU); on several devices
+   ml_solve supports the solvers of a row-sharded system (GMRES, RGMRES, LU).  Inside, one ordinary context per device,
+   NCCL + peer-memory windows between them (peer access inside the process instead of CUDA IPC), one worker thread per
+   device for the duration of a call.  ml_set_row_shard*, ml_set_communicator, ml_device_system and ml_device_stream do
+   not apply to such a handle. */
+ml_status ml_ctx_create_multi(ml_ctx **out, const int *device_ids, int n_dev);
+ml_status ml_multi_set_dealing(ml_ctx *ctx, int block_rows);   /* 0: contiguous blocks (default) */
+int ml_device_count(const ml_ctx *ctx);                        /* devices behind the handle (1 for ml_ctx_create) */
 void ml_ctx_destroy(ml_ctx *ctx);
 const char *ml_last_error(const ml_ctx *ctx);
 

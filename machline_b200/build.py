@@ -26,7 +26,7 @@ DRIVER_EXE = PKG / "machline_b200.exe"
 
 HOST_SOURCES = ["flow.cpp", "mesh_io.cpp", "panel_setup.cpp", "surface_mesh.cpp", "wake.cpp",
                 "solver_setup.cpp", "capi.cpp"]
-GPU_SOURCES = ["capi.cu", "aic_kernels.cu", "aic_sub.cu", "aic_sup.cu", "aic_sub_ho.cu", "aic_sup_ho.cu", "solve_kernels.cu", "lu_kernels.cu", "lu_sharded.cu", "seq_solvers.cu", "peaks.cu"]
+GPU_SOURCES = ["capi.cu", "aic_kernels.cu", "aic_sub.cu", "aic_sup.cu", "aic_sub_ho.cu", "aic_sup_ho.cu", "solve_kernels.cu", "lu_kernels.cu", "lu_sharded.cu", "seq_solvers.cu", "peaks.cu", "multi.cu"]
 
 # The image exports CXX=/opt/gcc/bin/g++ (a wrapper without libgomp.spec); the system compiler on
 # PATH is the complete one.

@@ -88,6 +88,11 @@ extern "C" ml_status ml_ctx_create(ml_ctx** out, int device_id) {
 
 extern "C" void ml_ctx_destroy(ml_ctx* c) {
     if (!c) return;
+    if (c->group) {   // facade of a multi-GPU context: it owns no device resources itself
+        mlgpu::multi_destroy(c);
+        delete c;
+        return;
+    }
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -126,11 +131,12 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
 }
 
 extern "C" const char* ml_last_error(const ml_ctx* c) { return c ? c->err.c_str() : "null context"; }
-extern "C" long long ml_launch_count(const ml_ctx* c) { return c ? c->launches : 0; }
-extern "C" long long ml_pair_count(const ml_ctx* c) { return c ? c->pair_count : 0; }
+extern "C" long long ml_launch_count(const ml_ctx* c) { return !c ? 0 : (c->group ? mlgpu::multi_sum_launches(c) : c->launches); }
+extern "C" long long ml_pair_count(const ml_ctx* c) { return !c ? 0 : (c->group ? mlgpu::multi_sum_pairs(c) : c->pair_count); }
 
 extern "C" ml_status ml_set_profiling(ml_ctx* c, int on) {
     if (!c) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_profile(c, 0, on, nullptr);
     c->profile = on != 0;
     return ML_OK;
 }
@@ -153,6 +159,7 @@ static void drain_gemv_events(ml_ctx* c) {
 
 extern "C" ml_status ml_get_profile(ml_ctx* c, ml_profile* out) {
     if (!c || !out) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_profile(c, 1, 0, out);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     drain_gemv_events(c);
@@ -168,6 +175,7 @@ extern "C" ml_status ml_get_profile(ml_ctx* c, ml_profile* out) {
 
 extern "C" ml_status ml_reset_profile(ml_ctx* c) {
     if (!c) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_profile(c, 2, 0, nullptr);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     drain_gemv_events(c);
@@ -180,6 +188,7 @@ extern "C" ml_status ml_reset_profile(ml_ctx* c) {
 
 extern "C" ml_status ml_set_flow(ml_ctx* c, const ml_flow* f) {
     if (!c || !f) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_set_flow(c, f);
     c->flow = *f;
     c->have_flow = true;
     c->dirty = true;
@@ -189,6 +198,7 @@ extern "C" ml_status ml_set_flow(ml_ctx* c, const ml_flow* f) {
 
 extern "C" ml_status ml_set_panels(ml_ctx* c, const ml_panel_soa* body, const ml_panel_soa* wake) {
     if (!c || !body) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_set_panels(c, body, wake);
     if (body->n_panels <= 0 || (body->n_images != 1 && body->n_images != 2)) return c->fail(ML_BAD_ARGUMENT, "body table: n_panels / n_images");
     if (body->order2) {   // higher-order table: quadratic doublets / linear sources (panel.f90:544-969)
         if (body->n_cols != 6 || !body->order || !body->M_dim || !body->S_dim || !body->i_panel_s4 || !body->T_mu6 || !body->T_sigma)
@@ -217,6 +227,7 @@ extern "C" ml_status ml_set_panels(ml_ctx* c, const ml_panel_soa* body, const ml
 extern "C" ml_status ml_set_control_points(ml_ctx* c, int n_cp, const double* loc, const int* bc, const double* n_g,
                                            const int* row_perm) {
     if (!c || n_cp <= 0 || !loc || !bc || !row_perm) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_set_control_points(c, n_cp, loc, bc, n_g, row_perm);
     c->n_cp = n_cp;
     c->cp_loc.assign(loc, loc + (size_t)3 * n_cp);
     c->cp_bc.assign(bc, bc + n_cp);
@@ -243,6 +254,7 @@ extern "C" ml_status ml_set_control_points(ml_ctx* c, int n_cp, const double* lo
 
 extern "C" ml_status ml_set_system_map(ml_ctx* c, const ml_system_map* m) {
     if (!c || !m || !m->P) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_set_system_map(c, m);
     c->map = *m;
     c->P.assign(m->P, m->P + m->n_unknown);
     c->sigma_known.assign(m->sigma_known, m->sigma_known + m->n_sigma);
@@ -262,6 +274,7 @@ extern "C" ml_status ml_set_system_map(ml_ctx* c, const ml_system_map* m) {
 
 extern "C" ml_status ml_set_row_shard_cyclic(ml_ctx* c, int block_rows, int rank, int world) {
     if (!c || block_rows <= 0 || world < 1 || rank < 0 || rank >= world) return ML_BAD_ARGUMENT;
+    if (c->group) return c->fail(ML_BAD_ARGUMENT, "a multi-GPU context deals its rows itself (ml_multi_set_dealing)");
     c->cyc_block = block_rows;
     c->cyc_rank = rank;
     c->cyc_world = world;
@@ -272,6 +285,7 @@ extern "C" ml_status ml_set_row_shard_cyclic(ml_ctx* c, int block_rows, int rank
 
 extern "C" ml_status ml_local_rows(ml_ctx* c, int* rows_out, int* n_out) {
     if (!c || !n_out) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_local_rows(c, rows_out, n_out);
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_local_rows before ml_assemble");
     *n_out = (int)c->local_rows.size();
     if (rows_out) std::memcpy(rows_out, c->local_rows.data(), c->local_rows.size() * sizeof(int));
@@ -280,6 +294,7 @@ extern "C" ml_status ml_local_rows(ml_ctx* c, int* rows_out, int* n_out) {
 
 extern "C" ml_status ml_set_row_shard(ml_ctx* c, int row0, int nrows) {
     if (!c || row0 < 0 || nrows < 0) return ML_BAD_ARGUMENT;
+    if (c->group) return c->fail(ML_BAD_ARGUMENT, "a multi-GPU context deals its rows itself (ml_multi_set_dealing)");
     c->cyc_block = 0;
     c->row0 = row0;
     c->nrows = nrows;
@@ -290,6 +305,7 @@ extern "C" ml_status ml_set_row_shard(ml_ctx* c, int row0, int nrows) {
 
 extern "C" ml_status ml_set_communicator(ml_ctx* c, const void* id, int rank, int world) {
     if (!c || !id || world < 1 || rank < 0 || rank >= world) return ML_BAD_ARGUMENT;
+    if (c->group) return c->fail(ML_BAD_ARGUMENT, "a multi-GPU context owns its communicator");
 #ifdef ML_HAVE_NCCL
     cudaSetDevice(c->device);
     ncclUniqueId uid;
@@ -687,6 +703,7 @@ static ml_status run_assembly_kernels(ml_ctx* c) {
 
 extern "C" ml_status ml_assemble(ml_ctx* c, double* I_known_out) {
     if (!c) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_assemble(c, I_known_out, false, nullptr);
     ML_CUDA(c, cudaSetDevice(c->device));
     if (c->dirty) {
         ml_status st = prepare(c);
@@ -711,6 +728,7 @@ extern "C" ml_status ml_assemble(ml_ctx* c, double* I_known_out) {
 
 extern "C" ml_status ml_assemble_resident(ml_ctx* c, double* device_ms) {
     if (!c) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_assemble(c, nullptr, true, device_ms);
     ML_CUDA(c, cudaSetDevice(c->device));
     if (c->dirty) {
         ml_status st = prepare(c);
@@ -731,6 +749,7 @@ extern "C" ml_status ml_assemble_resident(ml_ctx* c, double* device_ms) {
 
 extern "C" ml_status ml_dod_census(ml_ctx* c, long long* counts4) {
     if (!c || !counts4) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_dod_census(c, counts4);
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_dod_census before ml_assemble");
     ML_CUDA(c, cudaSetDevice(c->device));
     if (!c->flow.supersonic) {   // subsonic: every pair is evaluated with all three edges
@@ -762,6 +781,7 @@ static int local_run(const ml_ctx* c, int row0, int nrows) {
 
 extern "C" ml_status ml_get_A(ml_ctx* c, int row0, int nrows, double* dst, int ld) {
     if (!c || !dst || nrows < 0 || ld < nrows) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_get_A(c, row0, nrows, dst, ld);
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_get_A before ml_assemble");
     const int lr = local_run(c, row0, nrows);
     if (lr < 0) return c->fail(ML_BAD_ARGUMENT, "rows outside this context's shard (or not consecutive in it)");
@@ -774,6 +794,7 @@ extern "C" ml_status ml_get_A(ml_ctx* c, int row0, int nrows, double* dst, int l
 
 extern "C" ml_status ml_set_A(ml_ctx* c, int row0, int nrows, const double* src, int ld) {
     if (!c || !src || nrows < 0 || ld < nrows) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_set_A(c, row0, nrows, src, ld);
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_set_A before ml_assemble");
     const int lr = local_run(c, row0, nrows);
     if (lr < 0) return c->fail(ML_BAD_ARGUMENT, "rows outside this context's shard (or not consecutive in it)");
@@ -786,6 +807,7 @@ extern "C" ml_status ml_set_A(ml_ctx* c, int row0, int nrows, const double* src,
 
 extern "C" ml_status ml_check_system(ml_ctx* c, const double* BC, int* n_zero_rows, int* n_zero_cols) {
     if (!c || !BC) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_check_system(c, BC, n_zero_rows, n_zero_cols);
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_check_system before ml_assemble");
     ML_CUDA(c, cudaSetDevice(c->device));
     if (n_zero_rows) *n_zero_rows = 0;
@@ -844,6 +866,7 @@ extern "C" ml_status ml_check_system(ml_ctx* c, const double* BC, int* n_zero_ro
 
 extern "C" ml_status ml_device_system(ml_ctx* c, double** A_dev, int* ld, int* nrows_local, int* ncols) {
     if (!c) return ML_BAD_ARGUMENT;
+    if (c->group) return c->fail(ML_UNSUPPORTED, "ml_device_system: a multi-GPU context has one resident shard per device");
     if (!c->assembled) return c->fail(ML_NOT_READY, "system not assembled");
     if (A_dev) *A_dev = c->d_A.p;
     if (ld) *ld = c->ld;
@@ -854,12 +877,14 @@ extern "C" ml_status ml_device_system(ml_ctx* c, double** A_dev, int* ld, int* n
 
 extern "C" ml_status ml_device_stream(ml_ctx* c, void** stream_out) {
     if (!c || !stream_out) return ML_BAD_ARGUMENT;
+    if (c->group) return c->fail(ML_UNSUPPORTED, "ml_device_stream: a multi-GPU context has one stream per device");
     *stream_out = (void*)c->stream;
     return ML_OK;
 }
 
 extern "C" ml_status ml_solve(ml_ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info) {
     if (!c || !opts || !BC || !x_out) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_solve(c, opts, BC, x_out, info);
     if (!c->assembled) return c->fail(ML_NOT_READY, "ml_solve before ml_assemble");
     ML_CUDA(c, cudaSetDevice(c->device));
     PoolScope pool(c->stream);
@@ -869,6 +894,7 @@ extern "C" ml_status ml_solve(ml_ctx* c, const ml_solver_opts* opts, const doubl
 extern "C" ml_status ml_solve_dense(ml_ctx* c, int N, const double* A, const double* b, const ml_solver_opts* opts,
                                     double* x_out, ml_solve_info* info) {
     if (!c || N <= 0 || !A || !b || !opts || !x_out) return ML_BAD_ARGUMENT;
+    if (c->group) return ml_solve_dense(mlgpu::multi_member(c, 0), N, A, b, opts, x_out, info);   // a host system: one device
     ML_CUDA(c, cudaSetDevice(c->device));
     PoolScope pool(c->stream);
     DevBuf<double> dA;

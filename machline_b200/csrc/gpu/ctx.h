@@ -109,8 +109,11 @@ struct AicLaunch {            // arguments of the assembly kernel (aic_kernels.c
     FlowConst fc;             // freestream constants (kernel-parameter constant bank)
 };
 
+struct Group;   // multi.cu: the member contexts behind an ml_ctx_create_multi handle
+
 struct Ctx {
     int device = 0;
+    Group* group = nullptr;   // non-null: this handle is the facade of a single-process multi-GPU context (multi.cu)
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t stream_hi = nullptr;        // higher-priority stream of the LU look-ahead (created on first use)
@@ -184,6 +187,7 @@ struct Ctx {
     double* win = nullptr;              // this rank's window: [2][win_n] doubles, then [2][P2P_MAX] flags
     size_t win_n = 0;                   // doubles per parity buffer
     void* peer_base[P2P_MAX] = {};      // mapped windows (peer_base[rank] == win)
+    bool peer_ipc[P2P_MAX] = {};        // mapped through CUDA IPC (another process) rather than peer access inside this process
     unsigned p2p_seq = 0;               // matvecs exchanged so far (identical on every rank)
     bool p2p_ok = false;
 
@@ -227,3 +231,25 @@ ml_status solve_dense_device(Ctx* c, int N, double* dA, int ld, const double* h_
 }  // namespace mlgpu
 
 struct ml_ctx : public mlgpu::Ctx {};
+
+// multi.cu: fan-out of the entry points over the member contexts of an ml_ctx_create_multi handle
+namespace mlgpu {
+void multi_destroy(ml_ctx* c);
+ml_status multi_set_flow(ml_ctx* c, const ml_flow* f);
+ml_status multi_set_panels(ml_ctx* c, const ml_panel_soa* body, const ml_panel_soa* wake);
+ml_status multi_set_system_map(ml_ctx* c, const ml_system_map* m);
+ml_status multi_set_control_points(ml_ctx* c, int n_cp, const double* loc, const int* bc, const double* n_g, const int* row_perm);
+ml_status multi_assemble(ml_ctx* c, double* I_known_out, bool resident, double* device_ms);
+ml_status multi_get_A(ml_ctx* c, int row0, int nrows, double* dst, int ld);
+ml_status multi_set_A(ml_ctx* c, int row0, int nrows, const double* src, int ld);
+ml_status multi_local_rows(ml_ctx* c, int* rows_out, int* n_out);
+ml_status multi_solve(ml_ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info);
+ml_status multi_check_system(ml_ctx* c, const double* BC, int* n_zero_rows, int* n_zero_cols);
+ml_status multi_dod_census(ml_ctx* c, long long* counts4);
+long long multi_sum_launches(const ml_ctx* c);
+long long multi_sum_pairs(const ml_ctx* c);
+ml_ctx* multi_member(const ml_ctx* c, int i);
+int multi_size(const ml_ctx* c);
+ml_status multi_profile(ml_ctx* c, int what, int on, ml_profile* out);
+}  // namespace mlgpu
+

@@ -65,6 +65,7 @@ using namespace mlgpu;
 
 extern "C" ml_status ml_measure_dmma_peak(ml_ctx* c, double* tflops) {
     if (!c || !tflops) return ML_BAD_ARGUMENT;
+    if (c->group) return ml_measure_dmma_peak(mlgpu::multi_member(c, 0), tflops);
     ML_CUDA(c, cudaSetDevice(c->device));
     DevBuf<double> out;
     ML_CUDA(c, out.alloc(1024));
@@ -88,6 +89,7 @@ extern "C" ml_status ml_measure_dmma_peak(ml_ctx* c, double* tflops) {
 
 extern "C" ml_status ml_measure_peaks(ml_ctx* c, double* fp64_tflops, double* hbm_gbs) {
     if (!c) return ML_BAD_ARGUMENT;
+    if (c->group) return ml_measure_peaks(mlgpu::multi_member(c, 0), fp64_tflops, hbm_gbs);
     ML_CUDA(c, cudaSetDevice(c->device));
     DevBuf<double> out;
     ML_CUDA(c, out.alloc(1024));

@@ -19,6 +19,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <unistd.h>
 #include <vector>
 
 #include "ctx.h"
@@ -603,8 +604,9 @@ __global__ void __launch_bounds__(256) p2p_wait_copy_kernel(const double* __rest
 //   [.., + 2 P2P_MAX KR)    reduction slots of the sharded Arnoldi tail, two parities
 static void p2p_teardown(Ctx* c) {
     for (int r = 0; r < Ctx::P2P_MAX; ++r) {
-        if (c->peer_base[r] && r != c->rank) cudaIpcCloseMemHandle(c->peer_base[r]);
+        if (c->peer_base[r] && r != c->rank && c->peer_ipc[r]) cudaIpcCloseMemHandle(c->peer_base[r]);
         c->peer_base[r] = nullptr;
+        c->peer_ipc[r] = false;
     }
     if (c->win) cudaFree(c->win);
     c->win = nullptr;
@@ -642,11 +644,23 @@ static ml_status p2p_setup(Ctx* c, int n, bool local_only) {
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
     p2p_teardown(c);
     int ok = 1;
-    cudaIpcMemHandle_t mine;
+    // What a peer needs to reach this rank's window: the IPC handle (another process), or, for a rank driven by a thread of
+    // the SAME process (ml_ctx_create_multi), the pointer itself and the device to enable peer access to -- a process cannot
+    // open its own IPC handles.
+    struct WinInfo {
+        cudaIpcMemHandle_t handle;
+        long long pid;
+        void* ptr;
+        int device;
+        int pad;
+    } mine;
     std::memset(&mine, 0, sizeof mine);
     if (cudaMalloc((void**)&c->win, p2p_window_bytes(need)) != cudaSuccess || cudaMemset(c->win, 0, p2p_window_bytes(need)) != cudaSuccess ||
-        cudaIpcGetMemHandle(&mine, c->win) != cudaSuccess)
+        cudaIpcGetMemHandle(&mine.handle, c->win) != cudaSuccess)
         ok = 0;
+    mine.pid = (long long)getpid();
+    mine.ptr = c->win;
+    mine.device = c->device;
     cudaGetLastError();
     // exchange the handles (and whether everyone got this far)
     DevBuf<unsigned char> hs, ha;
@@ -666,9 +680,21 @@ static ml_status p2p_setup(Ctx* c, int n, bool local_only) {
     if (ok) {
         for (int r = 0; r < c->world && ok; ++r) {
             if (r == c->rank) { c->peer_base[r] = c->win; continue; }
-            cudaIpcMemHandle_t hnd;
-            std::memcpy(&hnd, all.data() + (size_t)r * sizeof hnd, sizeof hnd);
-            if (cudaIpcOpenMemHandle(&c->peer_base[r], hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            WinInfo peer;
+            std::memcpy(&peer, all.data() + (size_t)r * sizeof peer, sizeof peer);
+            if (peer.pid == mine.pid) {
+                int can = 0;
+                cudaError_t e = cudaDeviceCanAccessPeer(&can, c->device, peer.device);
+                if (e == cudaSuccess && can) {
+                    e = cudaDeviceEnablePeerAccess(peer.device, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) e = cudaSuccess;
+                }
+                cudaGetLastError();
+                if (e == cudaSuccess && can) c->peer_base[r] = peer.ptr;
+                else ok = 0;
+            } else if (cudaIpcOpenMemHandle(&c->peer_base[r], peer.handle, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess) {
+                c->peer_ipc[r] = true;
+            } else {
                 c->peer_base[r] = nullptr;
                 ok = 0;
             }

@@ -59,6 +59,10 @@ def lib() -> C.CDLL:
                                      C.POINTER(_abi.MlSolveInfo)]
         L.ml_dod_census.argtypes = [vp, C.POINTER(C.c_longlong)]
         L.ml_check_system.argtypes = [vp, dp, ip, ip]
+        L.ml_ctx_create_multi.argtypes = [C.POINTER(vp), ip, C.c_int]
+        L.ml_multi_set_dealing.argtypes = [vp, C.c_int]
+        L.ml_device_count.argtypes = [vp]
+        L.ml_device_count.restype = C.c_int
         L.ml_device_system.argtypes = [vp, C.POINTER(dp), ip, ip, ip]
         L.ml_measure_peaks.argtypes = [vp, dp, dp]
         L.ml_measure_dmma_peak.argtypes = [vp, dp]
@@ -76,13 +80,20 @@ def _dp(a: np.ndarray):
 
 
 class Context:
-    """One ml_ctx bound to one CUDA device."""
+    """One ml_ctx: bound to one CUDA device (device = id), or -- devices = [ids] -- the single-process multi-GPU context of
+    ml_ctx_create_multi, driven through the same methods from this one thread."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, devices: list[int] | None = None):
         self._h = C.c_void_p()
-        st = lib().ml_ctx_create(C.byref(self._h), device)
+        if devices is not None:
+            ids = (C.c_int * len(devices))(*devices)
+            st = lib().ml_ctx_create_multi(C.byref(self._h), ids, len(devices))
+            device = devices[0]
+        else:
+            st = lib().ml_ctx_create(C.byref(self._h), device)
         if st != 0:
             raise GpuError(st, "ml_ctx_create failed (no CUDA device visible?)")
+        self.multi = devices is not None
         self.device = device
         self.row0 = 0
         self.nrows = None
@@ -106,6 +117,12 @@ class Context:
         self._check(L.ml_set_system_map(self._h, C.byref(case.map)))
         self.n_unknown = case.n_unknown
         self.n_cp = case.n_cp
+        if self.multi:      # the library deals the rows to its devices; `cyclic` = (block, ...) selects block-cyclic dealing
+            assert row0 == 0 and nrows is None
+            self._check(L.ml_multi_set_dealing(self._h, cyclic[0] if cyclic is not None else 0))
+            self.row0, self.nrows = 0, case.n_cp
+            self.local_rows = np.arange(case.n_cp, dtype=np.int32)
+            return
         if cyclic is not None:
             from . import shard
             block, rank, world = cyclic

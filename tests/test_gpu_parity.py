@@ -77,7 +77,9 @@ def test_aic_entries_match_oracle(ctx, name):
         # binary64: ~1e-16 ABSOLUTE per edge angle, inside the metric above (2e-14 of the summed terms) but visible in
         # plain-relative terms wherever the three O(1) angles cancel.  Measured 0.15-0.18 of the entries (13x the
         # one-ulp model); bounded here so that a regression shows.
-        assert frac_gpu <= 0.25
+        # Higher-order entries (tests 16, 17) cancel more: the one-ulp model itself rises from 0.013 to 0.08 there and the
+        # device sits at 0.30 (3.8x the model).
+        assert frac_gpu <= max(0.25, 5.0 * frac_noise)
     case.close()
 
 
