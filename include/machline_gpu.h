@@ -205,6 +205,10 @@ long long ml_pair_count(const ml_ctx *ctx);
    n_zero_cols (either may be NULL) receive the counts.  With a communicator the verdict covers all shards. */
 ml_status ml_check_system(ml_ctx *ctx, const double *BC, int *n_zero_rows, int *n_zero_cols);
 
+/* R_cp = A x - b on this context's rows, b = BC - I_known (panel_solver.f90:1992; the point data "residual" of
+   output.control_point_file): r_out is indexed like I_known_out of ml_assemble. */
+ml_status ml_residual(ml_ctx *ctx, const double *BC, const double *x, double *r_out);
+
 /* ---- hot path 2: dense solve ------------------------------------------------------------------ */
 /* BC[n_cp] is the boundary-condition vector in row order (panel_solver.f90:1104-1159); the library
    forms b = BC - I_known (:1818), applies the reference's "preconditioner", dispatches on

@@ -75,6 +75,15 @@ int mlh_case_post2(mlh_case *c, const double *x, const double *v_inner, mlh_resu
 int mlh_case_write_report(mlh_case *c, const char *path, const ml_solve_info *info, int solver_stat,
                           double total_runtime);
 
+/* Result files of the last mlh_case_post / mlh_case_post2 in the reference's legacy-VTK layout (src/vtk.f90:42-431):
+   output.body_file / output.mirrored_body_file (surface_mesh_write_body / write_body_mirror, src/surface_mesh.f90:2547-2735;
+   mirrored != 0 needs an asymmetric mirrored flow), output.wake_file (wake_mesh_write_strips, src/wake_mesh.f90:148-222;
+   *exported = 0 and no file when there is no wake) and output.control_point_file (surface_mesh_write_control_points,
+   src/surface_mesh.f90:2738-2777; residual[n_cp] = A x - b in row order as ml_residual returns it, or NULL). */
+int mlh_case_write_body(mlh_case *c, const char *path, int mirrored);
+int mlh_case_write_wake(mlh_case *c, const char *path, int *exported);
+int mlh_case_write_control_points(mlh_case *c, const char *path, const double *residual);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,7 +25,7 @@ GPU_LIB = PKG / "libmachline_gpu.so"
 DRIVER_EXE = PKG / "machline_b200.exe"
 
 HOST_SOURCES = ["flow.cpp", "mesh_io.cpp", "panel_setup.cpp", "surface_mesh.cpp", "wake.cpp",
-                "solver_setup.cpp", "capi.cpp"]
+                "solver_setup.cpp", "outputs.cpp", "capi.cpp"]
 GPU_SOURCES = ["capi.cu", "aic_kernels.cu", "aic_sub.cu", "aic_sup.cu", "aic_sub_ho.cu", "aic_sup_ho.cu", "solve_kernels.cu", "lu_kernels.cu", "lu_sharded.cu", "seq_solvers.cu", "peaks.cu", "multi.cu"]
 
 # The image exports CXX=/opt/gcc/bin/g++ (a wrapper without libgomp.spec); the system compiler on

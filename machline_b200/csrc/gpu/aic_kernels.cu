@@ -52,6 +52,37 @@ cudaError_t launch_check_system(Ctx* c, const double* A, int ld, int n_rows, int
     return cudaGetLastError();
 }
 
+// r = A x - b on the local rows (panel_solver.f90:1992): blockIdx.y splits the columns, partial[chunk][row]; the second kernel
+// adds the chunks in order (deterministic)
+__global__ void residual_partial_kernel(const double* __restrict__ A, int ld, int n_rows, int n_cols, const double* __restrict__ x,
+                                        double* __restrict__ partial, int cols_per_chunk) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    const int c0 = blockIdx.y * cols_per_chunk, c1 = min(n_cols, c0 + cols_per_chunk);
+    double acc = 0.;
+    for (int j = c0; j < c1; ++j) acc = fma(A[row + (size_t)j * ld], x[j], acc);
+    partial[(size_t)blockIdx.y * n_rows + row] = acc;
+}
+__global__ void residual_finish_kernel(const double* __restrict__ partial, int n_rows, int n_chunks, const double* __restrict__ b,
+                                       double* __restrict__ r) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double acc = 0.;
+    for (int k = 0; k < n_chunks; ++k) acc += partial[(size_t)k * n_rows + row];
+    r[row] = acc - b[row];
+}
+
+cudaError_t launch_residual(Ctx* c, const double* A, int ld, int n_rows, int n_cols, const double* x, const double* b, double* partial,
+                            int n_chunks, double* r) {
+    if (n_rows <= 0) return cudaSuccess;
+    const int cols_per_chunk = (n_cols + n_chunks - 1) / n_chunks;
+    dim3 grid((n_rows + 127) / 128, n_chunks);
+    residual_partial_kernel<<<grid, 128, 0, c->stream>>>(A, ld, n_rows, n_cols, x, partial, cols_per_chunk);
+    residual_finish_kernel<<<(n_rows + 127) / 128, 128, 0, c->stream>>>(partial, n_rows, n_chunks, b, r);
+    c->launches += 2;
+    return cudaGetLastError();
+}
+
 FlowConst make_flow_const(const ml_flow& f) {
     FlowConst h;
     for (int i = 0; i < 3; ++i) h.c_hat[i] = f.c_hat_g[i];

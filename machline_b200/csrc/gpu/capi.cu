@@ -864,6 +864,29 @@ extern "C" ml_status ml_check_system(ml_ctx* c, const double* BC, int* n_zero_ro
     return ML_OK;
 }
 
+extern "C" ml_status ml_residual(ml_ctx* c, const double* BC, const double* x, double* r_out) {
+    if (!c || !BC || !x || !r_out) return ML_BAD_ARGUMENT;
+    if (c->group) return mlgpu::multi_residual(c, BC, x, r_out);
+    if (!c->assembled) return c->fail(ML_NOT_READY, "ml_residual before ml_assemble");
+    ML_CUDA(c, cudaSetDevice(c->device));
+    const int n_chunks = 16;
+    std::vector<double> b(c->n_rows);
+    for (int i = 0; i < c->n_rows; ++i) b[i] = BC[c->local_rows[i]] - c->h_I_known[i];   // panel_solver.f90:1818
+    DevBuf<double> d_x, d_b, d_part, d_r;
+    ML_CUDA(c, d_x.alloc(c->n_cols));
+    ML_CUDA(c, d_b.alloc(c->n_rows + 1));
+    ML_CUDA(c, d_part.alloc((size_t)n_chunks * c->n_rows + 1));
+    ML_CUDA(c, d_r.alloc(c->n_rows + 1));
+    ML_CUDA(c, cudaMemcpyAsync(d_x.p, x, sizeof(double) * c->n_cols, cudaMemcpyHostToDevice, c->stream));
+    ML_CUDA(c, cudaMemcpyAsync(d_b.p, b.data(), sizeof(double) * c->n_rows, cudaMemcpyHostToDevice, c->stream));
+    ML_CUDA(c, launch_residual(c, c->d_A.p, c->ld, c->n_rows, c->n_cols, d_x.p, d_b.p, d_part.p, n_chunks, d_r.p));
+    ML_CUDA(c, cudaMemcpyAsync(r_out, d_r.p, sizeof(double) * c->n_rows, cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, cudaStreamSynchronize(c->stream));
+    c->h2d_bytes += (long long)sizeof(double) * (c->n_cols + c->n_rows);
+    c->d2h_bytes += (long long)sizeof(double) * c->n_rows;
+    return ML_OK;
+}
+
 extern "C" ml_status ml_device_system(ml_ctx* c, double** A_dev, int* ld, int* nrows_local, int* ncols) {
     if (!c) return ML_BAD_ARGUMENT;
     if (c->group) return c->fail(ML_UNSUPPORTED, "ml_device_system: a multi-GPU context has one resident shard per device");

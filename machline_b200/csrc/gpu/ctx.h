@@ -212,6 +212,8 @@ FlowConst make_flow_const(const ml_flow& f);
 cudaError_t launch_aic(Ctx* c, const AicLaunch& L, bool supersonic);
 cudaError_t launch_strength_rows(Ctx* c, double* A, int ld, const int* rows, const int* colp, const int* colm, int n);
 cudaError_t launch_zero_columns(Ctx* c, double* A, int ld, const int* cols, int n_cols);
+cudaError_t launch_residual(Ctx* c, const double* A, int ld, int n_rows, int n_cols, const double* x, const double* b, double* partial,
+                            int n_chunks, double* r);
 cudaError_t launch_check_system(Ctx* c, const double* A, int ld, int n_rows, int n_cols, unsigned char* row_nz, unsigned char* col_nz,
                                 int* flags);
 cudaError_t launch_dod_census(Ctx* c, const double* recs, int n_rec_slots, const double* cp_xyz, const unsigned char* row_active,
@@ -245,6 +247,7 @@ ml_status multi_set_A(ml_ctx* c, int row0, int nrows, const double* src, int ld)
 ml_status multi_local_rows(ml_ctx* c, int* rows_out, int* n_out);
 ml_status multi_solve(ml_ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info);
 ml_status multi_check_system(ml_ctx* c, const double* BC, int* n_zero_rows, int* n_zero_cols);
+ml_status multi_residual(ml_ctx* c, const double* BC, const double* x, double* r_out);
 ml_status multi_dod_census(ml_ctx* c, long long* counts4);
 long long multi_sum_launches(const ml_ctx* c);
 long long multi_sum_pairs(const ml_ctx* c);

@@ -206,6 +206,20 @@ ml_status multi_check_system(ml_ctx* c, const double* BC, int* n_zero_rows, int*
     return ML_OK;
 }
 
+ml_status multi_residual(ml_ctx* c, const double* BC, const double* x, double* r_out) {
+    Group* g = c->group;
+    if (!c->assembled) return c->fail(ML_NOT_READY, "ml_residual before ml_assemble");
+    std::vector<std::vector<double>> r(g->m.size());
+    ml_status st = for_all(c, [&](int i) {
+        r[i].assign(g->m[i]->local_rows.size() + 1, 0.);
+        return ml_residual(g->m[i], BC, x, r[i].data());
+    });
+    if (st != ML_OK) return st;
+    for (size_t i = 0; i < g->m.size(); ++i)
+        for (size_t k = 0; k < g->m[i]->local_rows.size(); ++k) r_out[g->m[i]->local_rows[k]] = r[i][k];
+    return ML_OK;
+}
+
 ml_status multi_dod_census(ml_ctx* c, long long* counts4) {
     Group* g = c->group;
     std::vector<std::array<long long, 4>> cnt(g->m.size());

@@ -351,6 +351,43 @@ extern "C" int mlh_case_post2(mlh_case* h, const double* x, const double* v_inne
     }
 }
 
+// Result files (outputs.cpp) of the last mlh_case_post / mlh_case_post2
+extern "C" int mlh_case_write_body(mlh_case* h, const char* path, int mirrored) {
+    if (!h || !path) return 1;
+    try {
+        if (h->last.N_cells == 0) throw std::runtime_error("no results yet: call mlh_case_post first");
+        write_body_file(h->c, h->last, path, mirrored != 0);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+extern "C" int mlh_case_write_wake(mlh_case* h, const char* path, int* exported) {
+    if (!h || !path) return 1;
+    try {
+        if (h->last.N_cells == 0) throw std::runtime_error("no results yet: call mlh_case_post first");
+        const bool ok = write_wake_file(h->c, h->last, path);
+        if (exported) *exported = ok ? 1 : 0;
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+extern "C" int mlh_case_write_control_points(mlh_case* h, const char* path, const double* residual) {
+    if (!h || !path) return 1;
+    try {
+        write_control_point_file(h->c, path, residual);
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
 static void add_minmax(FILE* f, const char* label, const std::vector<double>& v, bool& first) {
     if (v.empty()) return;
     double mx = v[0], mn = v[0];

@@ -152,7 +152,7 @@ struct SolverSettings {  // src/panel_solver.f90:164-310
 };
 
 struct Results {
-    std::vector<double> mu, sigma;
+    std::vector<double> mu, sigma, Phi_u;   // Phi_u: total outer surface potential at the vertices (panel_solver.f90:2098-2133)
     std::vector<V3> V_cells, V_cells_inner, dC_f;
     std::vector<double> C_p_inc, C_p_ise, C_p_2nd, C_p_sln, C_p_lin, C_p_pg, C_p_kt, C_p_lai;
     V3 C_F{}, C_M{};
@@ -255,5 +255,10 @@ V3 panel_get_velocity_jump(const Panel& p, const Case& c, const std::vector<doub
                            bool mirrored, const V3* point = nullptr);
 
 std::string read_text_file(const std::string& path);
+
+// outputs.cpp: result files in the reference's legacy-VTK layout
+void write_body_file(const Case& c, const Results& R, const std::string& path, bool mirror);
+bool write_wake_file(const Case& c, const Results& R, const std::string& path);
+void write_control_point_file(const Case& c, const std::string& path, const double* residual);
 
 }  // namespace mlh

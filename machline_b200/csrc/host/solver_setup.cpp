@@ -582,6 +582,13 @@ Results Case::post(const std::vector<double>& x, const double* v_inner) const {
     for (int i = 0; i < N_s_unknown; ++i) R.sigma[i_sys_sigma_in_body[i]] = x[P[N_d_unknown + i]];
 
     const Flow& fs = freestream;
+    // calc_surface_potentials, panel_solver.f90:2098-2133
+    R.Phi_u = R.mu;
+    for (int i = 0; i < N_verts; ++i) {
+        R.Phi_u[i] = R.Phi_u[i] + inner(inner_flow, vertices[i].loc);
+        if (asym_flow) R.Phi_u[i + N_verts] = R.Phi_u[i + N_verts] + inner(inner_flow, mirror_across_plane(vertices[i].loc, mirror_plane));
+    }
+    for (double& v : R.Phi_u) v = v * fs.U;
     R.N_cells = asym_flow ? 2 * N_panels : N_panels;
     R.V_cells.assign(R.N_cells, V3{});
     R.V_cells_inner.assign(R.N_cells, V3{});

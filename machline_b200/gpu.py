@@ -59,6 +59,7 @@ def lib() -> C.CDLL:
                                      C.POINTER(_abi.MlSolveInfo)]
         L.ml_dod_census.argtypes = [vp, C.POINTER(C.c_longlong)]
         L.ml_check_system.argtypes = [vp, dp, ip, ip]
+        L.ml_residual.argtypes = [vp, dp, dp, dp]
         L.ml_ctx_create_multi.argtypes = [C.POINTER(vp), ip, C.c_int]
         L.ml_multi_set_dealing.argtypes = [vp, C.c_int]
         L.ml_device_count.argtypes = [vp]
@@ -136,7 +137,7 @@ class Context:
         self.row0, self.nrows = row0, nrows
         self.local_rows = np.arange(row0, row0 + nrows, dtype=np.int32)
 
-    def set_points(self, case, points: np.ndarray, direction=None):
+    def set_points(self, case, points: np.ndarray, direction=None, with_wake: bool = True):
         """Stage `case` with the rows of the system replaced by arbitrary field points (boundary condition "zero
         potential", no sorting): ml_assemble then builds the influence matrix of every unknown on those points, which is
         what the reference's off-body sweep evaluates (surface_mesh_get_induced_potentials_at_point,
@@ -154,7 +155,7 @@ class Context:
         C.memmove(C.byref(m), C.byref(case.map), C.sizeof(m))
         m.n_cp = n
         self._check(L.ml_set_flow(self._h, C.byref(case.flow)))
-        wake = C.byref(case.wake) if case.wake.n_panels > 0 else None
+        wake = C.byref(case.wake) if (with_wake and case.wake.n_panels > 0) else None
         self._check(L.ml_set_panels(self._h, C.byref(case.body), wake))
         self._check(L.ml_set_control_points(self._h, n, _dp(pts), bc.ctypes.data_as(_abi.c_int_p), _dp(n_g) if n_g is not None else None,
                                             rows.ctypes.data_as(_abi.c_int_p)))
@@ -164,14 +165,27 @@ class Context:
         self.row0, self.nrows = 0, n
         self.local_rows = np.arange(n, dtype=np.int32)
 
-    def potentials_at(self, case, points: np.ndarray, x: np.ndarray):
+    def potentials_at(self, case, points: np.ndarray, x: np.ndarray, with_wake: bool = True):
         """(phi_d, phi_s) induced at `points` by the solved strengths x (per unit freestream speed): phi_d = A_points x,
         phi_s = the known-source sum the assembly returns as I_known.  Wake panels contribute to phi_d with their
-        (top - bottom) strengths, as in the AIC rows."""
-        self.set_points(case, points)
+        (top - bottom) strengths, as in the AIC rows (with_wake=False leaves them out)."""
+        self.set_points(case, points, with_wake=with_wake)
         phi_s = self.assemble()
         phi_d = self.get_A() @ np.asarray(x, dtype=np.float64)
         return phi_d, phi_s
+
+    def velocity_parts_at(self, case, points: np.ndarray, x: np.ndarray, with_wake: bool = True):
+        """(v_d, v_s) induced at `points` (per unit freestream speed), separately: the doublet part A_points x and the known-source
+        part, for each of the three global directions."""
+        x = np.asarray(x, dtype=np.float64)
+        v_d, v_s = np.zeros((len(points), 3)), np.zeros((len(points), 3))
+        for k in range(3):
+            e = np.zeros(3)
+            e[k] = 1.0
+            self.set_points(case, points, direction=e, with_wake=with_wake)
+            v_s[:, k] = self.assemble()
+            v_d[:, k] = self.get_A() @ x
+        return v_d, v_s
 
     def velocities_at(self, case, points: np.ndarray, x: np.ndarray) -> np.ndarray:
         """Induced velocity v_d + v_s at `points` (per unit freestream speed) from the solved strengths x: three assemblies with
@@ -272,6 +286,14 @@ class Context:
         if st not in (0, 1, 2):
             self._check(st)
         return st, zr.value, zc.value
+
+    def residual(self, BC: np.ndarray, x: np.ndarray) -> np.ndarray:
+        """R_cp = A x - (BC - I_known) on this context's rows (panel_solver.f90:1992)."""
+        BC = np.ascontiguousarray(BC, dtype=np.float64)
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        r = np.zeros(self.nrows, dtype=np.float64)
+        self._check(lib().ml_residual(self._h, _dp(BC), _dp(x), _dp(r)))
+        return r
 
     def solve_dense(self, A: np.ndarray, b: np.ndarray, opts: _abi.MlSolverOpts):
         A = np.asfortranarray(A, dtype=np.float64)

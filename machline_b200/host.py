@@ -44,6 +44,9 @@ def lib() -> C.CDLL:
         L.mlh_case_inner_points.argtypes = [C.c_void_p, _abi.c_double_p, C.POINTER(C.c_int)]
         L.mlh_case_write_report.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(_abi.MlSolveInfo), C.c_int,
                                             C.c_double]
+        L.mlh_case_write_body.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        L.mlh_case_write_wake.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
+        L.mlh_case_write_control_points.argtypes = [C.c_void_p, C.c_char_p, _abi.c_double_p]
         _lib = L
     return _lib
 
@@ -163,6 +166,32 @@ class Case:
         Path(path).parent.mkdir(parents=True, exist_ok=True)
         rc = lib().mlh_case_write_report(self._h, str(path).encode(), C.byref(info), solver_stat, runtime)
         if rc != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+
+    # -- result files of the last post(), in the reference's legacy-VTK layout (csrc/host/outputs.cpp) ------------------
+    def write_body(self, path, mirrored: bool = False):
+        """output.body_file / output.mirrored_body_file (surface_mesh_write_body / write_body_mirror)."""
+        Path(path).parent.mkdir(parents=True, exist_ok=True)
+        if lib().mlh_case_write_body(self._h, str(path).encode(), int(mirrored)) != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+
+    def write_wake(self, path) -> bool:
+        """output.wake_file (wake_mesh_write_strips); False (and no file) when there is no wake to export."""
+        Path(path).parent.mkdir(parents=True, exist_ok=True)
+        exported = C.c_int(0)
+        if lib().mlh_case_write_wake(self._h, str(path).encode(), C.byref(exported)) != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+        return bool(exported.value)
+
+    def write_control_points(self, path, residual: np.ndarray | None = None):
+        """output.control_point_file (surface_mesh_write_control_points); residual = gpu.Context.residual(BC, x)."""
+        Path(path).parent.mkdir(parents=True, exist_ok=True)
+        rp = None
+        if residual is not None:
+            residual = np.ascontiguousarray(residual, dtype=np.float64)
+            assert residual.shape == (self.n_cp,)
+            rp = residual.ctypes.data_as(_abi.c_double_p)
+        if lib().mlh_case_write_control_points(self._h, str(path).encode(), rp) != 0:
             raise MachLineError(lib().mlh_last_error().decode())
 
     def close(self):

@@ -81,9 +81,20 @@ def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None
         total = time.perf_counter() - t0
         if report_file and report_file != "none":
             case.write_report(report_file, info, 0, total)
-        body_file = case.input.get("output", {}).get("body_file")
-        if body_file and body_file != "none":     # surface_mesh_output_results, src/surface_mesh.f90:2515-2517
-            vtk_out.write_body_vtk(body_file, case, res)
+        # surface_mesh_output_results (src/surface_mesh.f90:2503-2544) and the off-body sweep (main.f90:118-119, 170)
+        out = case.input.get("output", {})
+        wanted = lambda key: out.get(key) if out.get(key) and out.get(key) != "none" else None
+        if wanted("body_file"):
+            case.write_body(wanted("body_file"))
+        if wanted("mirrored_body_file") and case.info.asym_flow:
+            case.write_body(wanted("mirrored_body_file"), mirrored=True)
+        if wanted("wake_file"):
+            case.write_wake(wanted("wake_file"))
+        if wanted("control_point_file"):
+            case.write_control_points(wanted("control_point_file"), ctx.residual(case.BC, x))
+        off = out.get("offbody_points", {}) or {}
+        if off.get("points_file", "none") != "none" and off.get("output_file", "none") != "none":
+            vtk_out.export_off_body_points(case, ctx, x, off["points_file"], off["output_file"])
         return RunResult(res.C_p_max, res.C_p_min, res.C_F, res.C_M, res.mu, res.C_p, info.iterations,
                          info.res_max, info.res_norm, info.assemble_ms, info.solve_ms, ctx.pair_count,
                          ctx.launch_count, total)

@@ -1,9 +1,6 @@
-"""Body results file in the reference's legacy-VTK layout (src/vtk.f90:42-431, src/surface_mesh.f90:2547-2641).
-
-Same sections, labels, order and number formats (`e20.12`, `i20`) as `surface_mesh_write_body(solved=.true.)`, for the
-quantities this implementation holds: points, panels, normals, inclination, distribution_order, centroid, the pressure
-coefficient of the rule in force (C_p_inc for M = 0, else C_p_ise), sigma, v, mu.  Not written (not computed here):
-N_discontinuous_edges, v_inner, dC_f, Phi_u, convex, the other pressure rules."""
+"""Text outputs written from Python: the linear system (solver.write_A_and_b) and the off-body CSV (output.offbody_points), with
+the reference's Fortran edit descriptors.  The VTK result files (body, mirrored body, wake, control points) are written by the
+host library (csrc/host/outputs.cpp; host.Case.write_body / write_wake / write_control_points)."""
 from __future__ import annotations
 
 from pathlib import Path
@@ -27,44 +24,34 @@ def fortran_e(v: float, width: int = 20, digits: int = 12) -> str:
     return s.rjust(width)
 
 
-def _vec_lines(a) -> str:
-    return "".join(fortran_e(x) + fortran_e(y) + fortran_e(z) + "\n" for x, y, z in a)
-
-
-def _scalar_lines(a) -> str:
-    return "".join(fortran_e(x) + "\n" for x in a)
-
-
-def write_body_vtk(path, case, results) -> None:
-    """case: machline_b200.host.Case; results: the Results of case.post(x)."""
-    nb, nv = case.info.n_body_panels, case.info.n_body_verts
-    body = case.body
-    vert_g = np.ctypeslib.as_array(body.vert_g, shape=(nb * body.n_images, 3, 3))[:nb]
-    ivd = np.ctypeslib.as_array(body.i_vert_d, shape=(nb, 3))
-    centr = np.ctypeslib.as_array(body.centr, shape=(nb * body.n_images, 3))[:nb]
-    r_inc = np.ctypeslib.as_array(body.r, shape=(nb * body.n_images,))[:nb]
-    verts = np.zeros((nv, 3))
-    verts[ivd.reshape(-1)] = vert_g.reshape(-1, 3)
-    n = np.cross(vert_g[:, 1] - vert_g[:, 0], vert_g[:, 2] - vert_g[:, 1])
-    n /= np.linalg.norm(n, axis=1, keepdims=True)
-    sigma = np.ctypeslib.as_array(case.map.sigma, shape=(case.map.n_sigma,))[:nb]
-    mach = case.flow.M_inf
-    out = ["# vtk DataFile Version 3.0\n", "MachLine results file. Generated by MachLine, USU AeroLab (c) 2023.\n", "ASCII\n",
-           "DATASET POLYDATA\n", "POINTS%20d float\n" % nv, _vec_lines(verts), "POLYGONS%20d%20d\n" % (nb, 4 * nb)]
-    out.append("".join("3" + "".join("%20d" % i for i in tri) + "\n" for tri in ivd))
-    out.append("CELL_DATA%20d\n" % nb)
-    out.append("NORMALS normals float\n" + _vec_lines(n))
-    for label, data in (("inclination", r_inc.astype(float)), ("distribution_order", np.ones(nb))):
-        out.append(f"SCALARS {label} float 1\nLOOKUP_TABLE default\n" + _scalar_lines(data))
-    out.append("VECTORS centroid float\n" + _vec_lines(centr))
-    cp_label = "C_p_inc" if mach == 0.0 else "C_p_ise"
-    out.append(f"SCALARS {cp_label} float 1\nLOOKUP_TABLE default\n" + _scalar_lines(np.asarray(results.C_p)[:nb]))
-    out.append("SCALARS sigma float 1\nLOOKUP_TABLE default\n" + _scalar_lines(sigma))
-    out.append("VECTORS v float\n" + _vec_lines(np.asarray(results.V_cells)[:nb]))
-    out.append("POINT_DATA%20d\n" % nv)
-    out.append("SCALARS mu float 1\nLOOKUP_TABLE default\n" + _scalar_lines(np.asarray(results.mu)[:nv]))
-    Path(path).parent.mkdir(parents=True, exist_ok=True)
-    Path(path).write_text("".join(out))
+def export_off_body_points(case, ctx, x, points_file, output_file) -> int:
+    """output.offbody_points (panel_solver_export_off_body_points, src/panel_solver.f90:2771-2895): potentials and velocities
+    induced at the points of `points_file` (a header line, then x,y,z per line) by the solved strengths x, written as the
+    reference's 24-column CSV (e20.13).  The influences are evaluated on the GPU (ctx: gpu.Context; ml_assemble with the field
+    points as rows).  As in the reference's sum, a wake panel's top and bottom halves cancel (src/panel.f90:3002-3003, 3257):
+    the wake contributes nothing to phi_d / v_d here.  Returns the number of points."""
+    pts = np.atleast_2d(np.genfromtxt(points_file, delimiter=",", skip_header=1))[:, :3]
+    pts = np.ascontiguousarray(pts, dtype=np.float64)
+    fs = case.flow
+    v_inf = np.array(case.input["flow"]["freestream_velocity"], dtype=np.float64)
+    U = float(np.sqrt((v_inf * v_inf).sum()))
+    c_hat = np.array(fs.c_hat_g[:])
+    phi_d, phi_s = ctx.potentials_at(case, pts, x, with_wake=False)
+    v_d, v_s = ctx.velocity_parts_at(case, pts, x, with_wake=False)
+    phi_d, phi_s, v_d, v_s = phi_d * U, phi_s * U, v_d * U, v_s * U
+    e = lambda v: fortran_e(v, 20, 13)
+    Path(output_file).parent.mkdir(parents=True, exist_ok=True)
+    with open(output_file, "w") as f:
+        f.write(" x,y,z,phi_inf,phi_d,phi_s,phi,Phi,v_inf_x,v_inf_y,v_inf_z,v_d_x,v_d_y,v_d_z,v_s_x,v_s_y,v_s_z,v_x,v_y,v_z,V_x,V_y,V_z,V\n")
+        for i in range(len(pts)):
+            phi_inf = U * float(pts[i] @ c_hat)
+            v = v_d[i] + v_s[i]
+            V = v_inf + v
+            cols = [pts[i, 0], pts[i, 1], pts[i, 2], phi_inf, phi_d[i], phi_s[i], phi_d[i] + phi_s[i], phi_inf + phi_d[i] + phi_s[i],
+                    v_inf[0], v_inf[1], v_inf[2], v_d[i, 0], v_d[i, 1], v_d[i, 2], v_s[i, 0], v_s[i, 1], v_s[i, 2], v[0], v[1], v[2],
+                    V[0], V[1], V[2], float(np.sqrt((V * V).sum()))]
+            f.write(",".join(e(c) for c in cols) + "\n")
+    return len(pts)
 
 
 def write_system(A, b, a_path="A_mat.txt", b_path="b_vec.txt") -> None:

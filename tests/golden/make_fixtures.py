@@ -280,7 +280,7 @@ def make_prototype_integrals():
 
 def make_offbody():
     """The two off-body golden tables and the inputs of the tests that produced them (test_machline.py:636-730)."""
-    out = {"source": "test/input_files/*_offbody_points_correct.csv, columns x,y,z,phi_d,phi_s (0,1,2,4,5 of 24), e20.13",
+    out = {"source": "test/input_files/*_offbody_points_correct.csv, columns x,y,z,phi_d,phi_s,v_d,v_s (0,1,2,4,5,11-13,14-16 of 24), e20.13",
            "cases": []}
     for name, inp_file, csv_file, vel in [
             ("half_wing_inc", "half_wing_input.json", "half_wing_inc_offbody_points_correct.csv", None),
@@ -291,8 +291,9 @@ def make_offbody():
             inp["flow"]["freestream_velocity"] = vel
         inp["output"] = {}
         tab = np.genfromtxt(REF / "test" / "input_files" / csv_file, skip_header=1, delimiter=",")
+        # columns: x,y,z,phi_inf,phi_d,phi_s,phi,Phi,v_inf(3),v_d(3),v_s(3),v(3),V(3),|V|  (panel_solver.f90:2862-2863)
         out["cases"].append({"name": name, "input": inp, "points": tab[:, :3].tolist(), "phi_d": tab[:, 4].tolist(),
-                             "phi_s": tab[:, 5].tolist()})
+                             "phi_s": tab[:, 5].tolist(), "v_d": tab[:, 11:14].tolist(), "v_s": tab[:, 14:17].tolist()})
     (OUT / "offbody_potentials.json").write_text(json.dumps(out))
     print("offbody_potentials.json:", [(c["name"], len(c["points"])) for c in out["cases"]])
 

@@ -137,6 +137,29 @@ def velocities_at(case, points, x):
     return v
 
 
+def velocity_influences_at(case, points, with_wake: bool = True):
+    """Oracle velocity influence rows at field points: (V [3][n x n_unknown], v_s [n x 3]) with v_d = V[k] @ x."""
+    pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+    n = pts.shape[0]
+    bc = np.full(n, 5, dtype=np.int32)
+    rows = np.arange(n, dtype=np.int32)
+    wake = C.byref(case.wake) if (with_wake and case.wake.n_panels > 0) else None
+    V, v_s = [], np.zeros((n, 3))
+    for k in range(3):
+        n_g = np.zeros((n, 3))
+        n_g[:, k] = 1.0
+        A = np.zeros((n, case.n_unknown), dtype=np.float64, order="F")
+        I_known = np.zeros(n, dtype=np.float64)
+        st = lib().orc_assemble_n(C.byref(case.flow), C.byref(case.body), wake, C.byref(case.map), n, _dp(pts),
+                                  bc.ctypes.data_as(_abi.c_int_p), _dp(n_g), rows.ctypes.data_as(_abi.c_int_p), 0, n, _dp(A), n,
+                                  _dp(I_known), 0, None)
+        if st != 0:
+            raise RuntimeError(f"orc_assemble_n status {st}")
+        V.append(A)
+        v_s[:, k] = I_known
+    return V, v_s
+
+
 def pair(case, table, j: int, img: int, P) -> OrcPairOut:
     out = OrcPairOut()
     Pa = np.ascontiguousarray(P, dtype=np.float64)

@@ -258,6 +258,45 @@ def test_reference_offbody_potentials_through_gpu(ctx, c):
     case.close()
 
 
+@pytest.mark.parametrize("c", _offbody_cases(), ids=lambda c: c["name"])
+def test_offbody_export_reproduces_the_reference_table(ctx, c, tmp_path):
+    """output.offbody_points through the CUDA path (vtk_out.export_off_body_points = panel_solver_export_off_body_points,
+    src/panel_solver.f90:2771-2895): the 24-column CSV against the table the reference itself wrote for the same input --
+    phi_s and the three v_s columns at print precision, phi_d / v_d as far as the case's singular system allows
+    (tests/test_oracle_offbody.py), and the velocity-influence rows entry by entry against the oracle."""
+    from machline_b200 import host, vtk_out
+    case = host.Case(c["input"], base_dir=fixtures.mesh_root())
+    ctx.set_case(case)
+    ctx.assemble()
+    x, info = ctx.solve(case.solver_opts(), case.BC)
+    pts = np.array(c["points"])
+    pfile, ofile = tmp_path / "points.csv", tmp_path / "out" / "offbody.csv"
+    pfile.write_text("x,y,z\n" + "".join("%.17g,%.17g,%.17g\n" % tuple(p) for p in pts))
+    assert vtk_out.export_off_body_points(case, ctx, x, pfile, ofile) == len(pts)
+    lines = ofile.read_text().split("\n")
+    assert lines[0].strip().startswith("x,y,z,phi_inf,phi_d,phi_s,phi,Phi,v_inf_x") and len(lines[1]) == 24 * 20 + 23
+    tab = np.genfromtxt(ofile, delimiter=",", skip_header=1)
+    assert tab.shape == (len(pts), 24)
+    supersonic = "supersonic" in c["name"]
+    assert np.abs(tab[:, 5] - np.array(c["phi_s"])).max() < 2e-11
+    gold_vs, gold_vd = np.array(c["v_s"]), np.array(c["v_d"])
+    assert np.abs(tab[:, 14:17] - gold_vs).max() < 1e-10 * max(1.0, np.abs(gold_vs).max())
+    if supersonic:
+        assert np.abs(tab[:, 4] - np.array(c["phi_d"])).max() < 1e-10
+        assert np.abs(tab[:, 12] - gold_vd[:, 1]).max() < 1e-9
+        assert np.abs(tab[:, 11:14] - gold_vd).max() < 1e-4 * np.abs(gold_vd).max()
+    # internal consistency of the derived columns
+    assert np.abs(tab[:, 6] - (tab[:, 4] + tab[:, 5])).max() < 1e-11 * max(1.0, np.abs(tab[:, 6]).max())
+    assert np.abs(tab[:, 23] - np.linalg.norm(tab[:, 20:23], axis=1)).max() < 1e-10 * np.abs(tab[:, 23]).max()
+    # velocity-influence rows against the oracle's
+    V_ref, vs_ref = ob.velocity_influences_at(case, pts, with_wake=False)
+    v_d, v_s = ctx.velocity_parts_at(case, pts, x, with_wake=False)
+    vd_ref = np.stack([V_ref[k] @ x for k in range(3)], axis=1)
+    assert np.abs(v_s - vs_ref).max() < 1e-12 * max(1.0, np.abs(vs_ref).max())
+    assert np.abs(v_d - vd_ref).max() < 1e-9 * max(1.0, np.abs(vd_ref).max())
+    case.close()
+
+
 def test_run_case_writes_the_reference_outputs(tmp_path):
     """solver.run_case = `machline.exe input.json`: report.json, the body results VTK and the iteration history appear where
     the input asks for them, and the numbers in them are the solved ones."""
@@ -266,8 +305,17 @@ def test_run_case_writes_the_reference_outputs(tmp_path):
     inp, expect, tol = fixtures.golden_input("test_08")
     inp = json.loads(json.dumps(inp))
     inp["solver"]["iterative_solver_output"] = str(tmp_path / "iterations.csv")
-    inp["output"] = {"report_file": str(tmp_path / "report.json"), "body_file": str(tmp_path / "results" / "body.vtk")}
+    inp["output"] = {"report_file": str(tmp_path / "report.json"), "body_file": str(tmp_path / "results" / "body.vtk"),
+                     "wake_file": str(tmp_path / "results" / "wake.vtk"), "control_point_file": str(tmp_path / "results" / "cp.vtk"),
+                     "mirrored_body_file": str(tmp_path / "results" / "mirror.vtk"),
+                     "offbody_points": {"points_file": str(tmp_path / "pts.csv"), "output_file": str(tmp_path / "results" / "off.csv")}}
+    (tmp_path / "pts.csv").write_text("x,y,z\n2.0,0.0,0.0\n0.0,3.0,0.5\n")
     res = solver.run_case(inp, base_dir=fixtures.mesh_root())
+    assert (tmp_path / "results" / "cp.vtk").exists() and len((tmp_path / "results" / "off.csv").read_text().split("\n")) == 4
+    assert not (tmp_path / "results" / "wake.vtk").exists() and not (tmp_path / "results" / "mirror.vtk").exists()   # sphere: neither
+    cpl = (tmp_path / "results" / "cp.vtk").read_text().split("\n")
+    i0 = cpl.index("SCALARS residual float 1") + 2
+    assert max(abs(float(v)) for v in cpl[i0:i0 + 10]) < 1e-11
     assert abs(res.C_p_max - expect[0]) < tol[0] and abs(res.C_p_min - expect[1]) < tol[1]
     rep = json.loads((tmp_path / "report.json").read_text())
     assert rep["solver_results"]["iterations"] == res.iterations
