@@ -35,4 +35,18 @@ void lu_launch_trsv_diag(Ctx* c, const double* D, int ld, int nb, double* x, int
 void lu_gemm2_launch(Ctx* c, const double* Lp, int ldl, const double* Up, int ldu, double* Cp, int ldc, int M, int Nc,
                      const unsigned char* row_block_active, int k_halves = 1, cudaStream_t stream = nullptr);
 
+// What the block solvers need from a row-sharded system (solve_kernels.cu: Sys): the local rows, their global indices, the
+// slot a rank writes its local results to and the exchange that turns the slots of all ranks into the replicated vector.
+struct RowShardOps {
+    const double* A;          // local rows, column-major
+    int ld, n_rows, N;
+    const int* g_of_local;    // device: global row of each local row
+    double* slot;             // device: this rank's part of the exchange buffer (n_rows doubles)
+    void* sys;                // opaque: the Sys behind `exchange`
+    ml_status (*exchange)(void* sys, double* y_full);
+};
+// block_jacobi_solve (common/linalg.f90:601-728) on a row-sharded system: SURVEY 8(e) row 2
+ml_status block_jacobi_sharded(Ctx* c, const RowShardOps& R, const double* d_b, int block_size, double tol, double rel, int max_iter,
+                               int* iters, double* d_x, double err_scale, const char* iteration_file);
+
 }  // namespace mlgpu

@@ -1298,6 +1298,149 @@ __global__ void bssor_relax_kernel(double rel, const double* __restrict__ xi, do
     if (i < n) x_new[i] = (1. - rel) * x_new[i] + rel * xi[i];  // linalg.f90:577
 }
 
+// ---- block Jacobi on a row-sharded system (block_jacobi_solve, common/linalg.f90:601-728) ----------------
+// Rows never move.  The diagonal blocks (N_blocks = 5 by default: 20 % of the matrix) are assembled on every rank -- each rank
+// stores its rows of a block into a zero-filled copy, one all-reduce per block adds the copies (one non-zero contributor per
+// entry: exact) -- and factored redundantly, so the block solves of an iteration need no communication.  Per iteration: the
+// right-hand sides b_i - sum_{j outside block} A x of the local rows (one kernel over all local rows, summation order of the
+// single-GPU kernel), exchanged into the replicated vector; the block solves and the relaxation on every rank; the residual
+// || A x_new - b || of the local rows, exchanged again.  All ranks hold identical vectors, hence take identical decisions.
+__global__ void __launch_bounds__(256) bjs_pack_block_kernel(const double* __restrict__ A, int ld, int n_rows, const int* __restrict__ g_of_local,
+                                                              int bs, int nb, double* __restrict__ dst, int ldd) {
+    const int r = blockIdx.x * 256 + threadIdx.x;
+    if (r >= n_rows) return;
+    const int g = g_of_local[r];
+    if (g >= bs && g < bs + nb) dst[(g - bs) + (size_t)blockIdx.y * ldd] = A[r + (size_t)(bs + blockIdx.y) * ld];
+}
+__global__ void bjs_init_kernel(const double* __restrict__ A, int ld, int n_rows, const int* __restrict__ g_of_local,
+                                const double* __restrict__ b, double* __restrict__ out) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < n_rows) {
+        const int g = g_of_local[r];
+        out[r] = b[g] / A[r + (size_t)g * ld];   // linalg.f90:645-647
+    }
+}
+// out[r] = b[g] - sum_{c outside the block of g} A[r, c] x[c] over the local rows (exclude = 0: the residual b - A x);
+// warps split the columns and lanes the rows exactly as bj_rhs_kernel does
+__global__ void __launch_bounds__(256) bjs_rhs_kernel(const double* __restrict__ A, int ld, int n, int n_rows, const int* __restrict__ g_of_local,
+                                                       int block_size, int exclude, const double* __restrict__ b,
+                                                       const double* __restrict__ x, double* __restrict__ out) {
+    __shared__ double s_part[8][33];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int r = blockIdx.x * 32 + lane;
+    double acc = 0.;
+    int g = 0;
+    if (r < n_rows) {
+        g = g_of_local[r];
+        int xs = 0, xe = 0;
+        if (exclude) {
+            xs = (g / block_size) * block_size;
+            xe = min(n, xs + block_size);
+        }
+        for (int c = warp; c < n; c += 8)
+            if (c < xs || c >= xe) acc = fma(A[r + (size_t)c * ld], __ldg(x + c), acc);
+    }
+    s_part[warp][lane] = acc;
+    __syncthreads();
+    if (warp == 0 && r < n_rows) {
+        double t = 0.;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += s_part[k][lane];
+        out[r] = b[g] - t;
+    }
+}
+
+ml_status block_jacobi_sharded(Ctx* c, const RowShardOps& R, const double* d_b, int block_size, double tol, double rel, int max_iter,
+                               int* iters, double* d_x, double err_scale, const char* iteration_file) {
+    const int N = R.N;
+    if (block_size <= 0 || block_size > N) return c->fail(ML_BAD_ARGUMENT, "block_size out of range");
+    int N_blocks = N / block_size;
+    if (N % block_size > 0) N_blocks += 1;
+    std::vector<DevBuf<double>> blocks(N_blocks);
+    std::vector<DevBuf<int>> pivs(N_blocks);
+    std::vector<int> bs(N_blocks), be(N_blocks), bld(N_blocks);
+    DevBuf<double> vv, x_new, bi, nrm;
+    DevBuf<int> flag;
+    auto cleanup = [&]() {
+        for (auto& b : blocks) b.release();
+        for (auto& p : pivs) p.release();
+        vv.release(); flag.release(); x_new.release(); bi.release(); nrm.release();
+    };
+    ML_CUDA(c, vv.alloc(block_size + 64));
+    ML_CUDA(c, flag.alloc(1));
+    ML_CUDA(c, x_new.alloc(N));
+    ML_CUDA(c, bi.alloc(N));
+    ML_CUDA(c, nrm.alloc(2));
+    FILE* hist = open_block_history(c, iteration_file, "BJAC", N, true);
+    ml_status st = ML_OK;
+    for (int i = 0; i < N_blocks && st == ML_OK; ++i) {
+        bs[i] = i * block_size;
+        be[i] = (i == N_blocks - 1) ? N : (i + 1) * block_size;
+        const int nb = be[i] - bs[i];
+        bld[i] = ((nb + 63) / 64) * 64;
+        if (blocks[i].alloc((size_t)bld[i] * nb) != cudaSuccess || pivs[i].alloc(2 * (size_t)nb) != cudaSuccess || vv.alloc(nb) != cudaSuccess) {
+            cleanup();
+            return c->fail(ML_CUDA_ERROR, "block Jacobi: out of device memory");
+        }
+        cudaError_t e = cudaMemsetAsync(blocks[i].p, 0, (size_t)bld[i] * nb * sizeof(double), c->stream);
+        if (e != cudaSuccess) { cleanup(); return c->cuda_fail(e, "block Jacobi: memset"); }
+        if (R.n_rows > 0) {
+            dim3 grid((R.n_rows + 255) / 256, nb);
+            bjs_pack_block_kernel<<<grid, 256, 0, c->stream>>>(R.A, R.ld, R.n_rows, R.g_of_local, bs[i], nb, blocks[i].p, bld[i]);
+            c->launches += 1;
+        }
+#ifdef ML_HAVE_NCCL
+        if (c->world > 1 &&
+            ncclAllReduce(blocks[i].p, blocks[i].p, (size_t)bld[i] * nb, ncclDouble, ncclSum, c->comm, c->stream) != ncclSuccess) {
+            cleanup();
+            return c->fail(ML_NCCL_ERROR, "block Jacobi: all-reduce of a diagonal block");
+        }
+#endif
+        st = lu_factor(c, blocks[i].p, bld[i], nb, pivs[i].p, vv.p, flag.p);
+    }
+    const int nbk = (N + 255) / 256, lbk = (R.n_rows + 31) / 32;
+    int iteration = 0;
+    double err = tol + 1.;
+    if (st == ML_OK) {
+        if (R.n_rows > 0) bjs_init_kernel<<<(R.n_rows + 255) / 256, 256, 0, c->stream>>>(R.A, R.ld, R.n_rows, R.g_of_local, d_b, R.slot);
+        c->launches += 1;
+        st = R.exchange(R.sys, d_x);
+    }
+    while (st == ML_OK && err >= tol && iteration < max_iter) {
+        iteration += 1;
+        if (R.n_rows > 0) bjs_rhs_kernel<<<lbk, 256, 0, c->stream>>>(R.A, R.ld, N, R.n_rows, R.g_of_local, block_size, 1, d_b, d_x, R.slot);
+        c->launches += 1;
+        st = R.exchange(R.sys, bi.p);
+        for (int i = 0; i < N_blocks && st == ML_OK; ++i)
+            st = lu_substitute(c, blocks[i].p, bld[i], be[i] - bs[i], pivs[i].p, bi.p + bs[i], x_new.p + bs[i]);
+        if (st != ML_OK) break;
+        bj_relax_kernel<<<nbk, 256, 0, c->stream>>>(rel, d_x, x_new.p, N);
+        if (R.n_rows > 0) bjs_rhs_kernel<<<lbk, 256, 0, c->stream>>>(R.A, R.ld, N, R.n_rows, R.g_of_local, block_size, 0, d_b, x_new.p, R.slot);
+        c->launches += 2;
+        st = R.exchange(R.sys, bi.p);
+        if (st != ML_OK) break;
+        vec_norm_kernel<<<1, 1024, 0, c->stream>>>(bi.p, N, nrm.p);
+        c->launches += 1;
+        double dx = 0.;
+        if (hist) {
+            vec_diff_norm_kernel<<<1, 1024, 0, c->stream>>>(d_x, x_new.p, N, nrm.p + 1);
+            c->launches += 1;
+        }
+        cudaError_t e = cudaMemcpyAsync(d_x, x_new.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(&err, nrm.p, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess && hist) e = cudaMemcpyAsync(&dx, nrm.p + 1, sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { st = c->cuda_fail(e, "block_jacobi iteration"); break; }
+        if (!(err == err)) { st = ML_NAN_RESIDUAL; break; }
+        err *= err_scale;
+        if (hist) std::fprintf(hist, "%6d,%10.3E,%10.3E,%10.3E\n", iteration, dx, err, rel);
+    }
+    if (hist) std::fclose(hist);
+    *iters = iteration;
+    cleanup();
+    return st;
+}
+
 ml_status block_ssor_device(Ctx* c, int N, const double* dA, int ld, const double* d_b, int block_size, double tol, double rel,
                             int max_iter, int* iters, double* d_x, double err_scale, const char* iteration_file) {
     if (block_size <= 0 || block_size > N) return c->fail(ML_BAD_ARGUMENT, "block_size out of range");

@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "ctx.h"
+#include "lu_internal.cuh"
 
 namespace mlgpu {
 
@@ -1399,6 +1400,14 @@ static ml_status run_solver(Sys& S, const ml_solver_opts* opts, const double* d_
             st = lu_solve_device(c, S.N, lu_matrix, lu_ld, d_b, d_x);
             break;
         case ML_SOLVER_BJAC:
+            if (S.sharded()) {   // rows stay where they were assembled (lu_kernels.cu: block_jacobi_sharded)
+                RowShardOps R{S.A, S.ld, S.n_rows, S.N, c->d_g_of_slot.p + (size_t)c->rank * S.shard_pad,
+                              S.gather.p + (size_t)c->rank * S.shard_pad, &S,
+                              [](void* sys, double* y_full) { return static_cast<Sys*>(sys)->exchange(y_full, nullptr); }};
+                st = block_jacobi_sharded(c, R, d_b, block_size, opts->tol, opts->rel, opts->max_iterations, &iters, d_x, err_scale,
+                                          opts->iteration_file);
+                break;
+            }
             if (!lu_matrix) return c->fail(ML_UNSUPPORTED, "BJAC needs the full matrix on one device");
             st = block_jacobi_device(c, S.N, lu_matrix, lu_ld, d_b, block_size, opts->tol, opts->rel, opts->max_iterations, &iters, d_x,
                                      err_scale, opts->iteration_file);
@@ -1615,7 +1624,8 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
         const int ms = opts->matrix_solver;
         const bool krylov = !(ms == ML_SOLVER_LU || ms == ML_SOLVER_BJAC || ms == ML_SOLVER_BSSOR || ms == ML_SOLVER_QRUP || ms == ML_SOLVER_FQRUP ||
                               ms == ML_SOLVER_PURC);
-        S.force_shard = c->world == 1 && krylov && std::getenv("MACHLINE_GMRES_SHARDED") != nullptr;
+        S.force_shard = c->world == 1 && ((krylov && std::getenv("MACHLINE_GMRES_SHARDED") != nullptr) ||
+                                          (ms == ML_SOLVER_BJAC && std::getenv("MACHLINE_BJAC_SHARDED") != nullptr));
     }
     // Slot tables of the all-gather layout: slot = rank * shard_pad + local row <-> global row.  Every rank contributes the
     // list of rows it assembled, so any dealing of rows to ranks (contiguous blocks, block-cyclic) works the same way.
@@ -1737,9 +1747,11 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
         st = lu_solve_sharded(c, N, Acopy.p, c->ld, c->n_rows, c->n_rows_pad, S.shard_pad, d_b.p, d_x.p);
         Acopy.release();
         if (st == ML_OK && info) info->iterations = -1;
+    } else if (opts->matrix_solver == ML_SOLVER_BJAC && S.sharded()) {
+        // block Jacobi on the row shards: no full copy (run_solver)
     } else if (needs_whole_matrix(opts->matrix_solver)) {
         if (c->world > 1)
-            return c->fail(ML_UNSUPPORTED, "BJAC/BSSOR/QRUP/FQRUP/PURC on a row-sharded system are not built (SURVEY 8(e)): use LU/GMRES/RGMRES");
+            return c->fail(ML_UNSUPPORTED, "BSSOR/QRUP/FQRUP/PURC are sequential sweeps (\"replicas only\", SURVEY 8(e)): on a row-sharded system use LU/GMRES/RGMRES/BJAC");
         lu_matrix = c->d_A.p;
         if (opts->matrix_solver == ML_SOLVER_LU) {   // factored in place: work on the reference's A_p copy
             ML_CUDA(c, Acopy.alloc((size_t)c->ld * N));

@@ -29,7 +29,8 @@ def _run(ctx, case, opts, cyclic=None):
 
 @pytest.mark.parametrize("n_dev", [1, 2, 4])
 @pytest.mark.parametrize("name,solver,cyclic", [("test_08", "GMRES", None), ("test_13", "GMRES", None), ("test_13", "RGMRES", None),
-                                                ("test_08", "LU", (128, 0, 0)), ("test_13", "LU", None), ("test_16", "GMRES", None)])
+                                                ("test_08", "LU", (128, 0, 0)), ("test_13", "LU", None), ("test_16", "GMRES", None),
+                                                ("test_08", "BJAC", None), ("test_13", "BJAC", (64, 0, 0))])
 def test_multi_context_matches_single_device(n_dev, name, solver, cyclic):
     if _n_devices() < n_dev:
         pytest.skip(f"needs {n_dev} GPUs")
@@ -52,6 +53,9 @@ def test_multi_context_matches_single_device(n_dev, name, solver, cyclic):
     scale = np.abs(x1).max()
     if solver == "LU":
         assert np.abs(x - x1).max() <= 1e-10 * scale
+    elif solver == "BJAC":   # block Jacobi on the shards repeats the single-device arithmetic row by row
+        assert info.iterations == info1.iterations
+        assert np.abs(x - x1).max() <= 1e-12 * scale
     else:
         assert abs(info.iterations - info1.iterations) <= 2
         assert np.abs(x - x1).max() <= 1e-8 * scale
@@ -81,3 +85,28 @@ def test_multi_context_rejects_per_device_calls():
     ids = (C.c_int * 2)(0, 0)
     assert L.ml_ctx_create_multi(C.byref(bad), ids, 2) == 10  # the same device twice
     multi.close()
+
+
+@pytest.mark.parametrize("name", ["test_08", "test_13", "test_19"])
+def test_block_jacobi_sharded_kernels_on_one_rank(name):
+    """MACHLINE_BJAC_SHARDED=1: block_jacobi_sharded (diagonal blocks packed from the row shard, right-hand sides and residuals
+    through the exchange) on one rank against the single-device block Jacobi and the oracle: what the 1-GPU box executes."""
+    import os
+    from machline_b200 import _abi, gpu
+    case, _, _ = fixtures.make_case(name)
+    opts = case.solver_opts()
+    opts.matrix_solver = _abi.SOLVERS["BJAC"]
+    ctx = gpu.Context(0)
+    A1, I1, x1, info1 = _run(ctx, case, opts)
+    os.environ["MACHLINE_BJAC_SHARDED"] = "1"
+    try:
+        x, info = ctx.solve(opts, case.BC)
+    finally:
+        del os.environ["MACHLINE_BJAC_SHARDED"]
+    assert info.iterations == info1.iterations and info.iterations > 3
+    assert np.abs(x - x1).max() <= 1e-13 * np.abs(x1).max()
+    x_ref, info_ref = ob.solve_system(*ob.assemble(case), case.BC, opts)
+    assert abs(info.iterations - info_ref.iterations) <= 1
+    assert np.abs(x - x_ref).max() <= 1e-9 * np.abs(x_ref).max()
+    ctx.close()
+    case.close()
