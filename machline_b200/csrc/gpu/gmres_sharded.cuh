@@ -52,6 +52,7 @@ struct ShTailArgs {
     unsigned* ticket;       // grid arrival counter (monotonic over the launches of one solve)
     unsigned* ready;        // published stage counter (monotonic)
     unsigned base;          // launches of this solve before this one
+    unsigned stages;        // grid-wide sync points per launch (3: arnoldi_tail_sharded_kernel, 4: arnoldi_tail_sharded2_kernel)
     int* err;               // raised when a spin loop gives up
     int rows_per_cta;       // multiple of 32
     long long* dbg;         // nullptr, or [2][16] clock64 stamps (CTA 0 / the CTA that was last at stage 0) -- MACHLINE_SHT_DEBUG
@@ -171,7 +172,7 @@ __device__ __forceinline__ bool sht_arrive_is_last(const ShTailArgs& a, int stag
     if (threadIdx.x == 0) {
         __threadfence();
         const unsigned t = atomicAdd(a.ticket, 1u);
-        const unsigned target = (a.base * 3u + (unsigned)stage + 1u) * gridDim.x - 1u;
+        const unsigned target = (a.base * a.stages + (unsigned)stage + 1u) * gridDim.x - 1u;
         *s_flag = (t == target);
     }
     __syncthreads();
@@ -179,7 +180,7 @@ __device__ __forceinline__ bool sht_arrive_is_last(const ShTailArgs& a, int stag
 }
 __device__ __forceinline__ void sht_wait_ready(const ShTailArgs& a, int stage) {
     if (threadIdx.x == 0) {
-        const unsigned target = a.base * 3u + (unsigned)stage + 1u;
+        const unsigned target = a.base * a.stages + (unsigned)stage + 1u;
         const long long t0 = clock64();
         while ((int)(ld_acquire_gpu(a.ready) - target) < 0) {
             if (clock64() - t0 > SHT_SPIN_LIMIT) {
@@ -192,7 +193,7 @@ __device__ __forceinline__ void sht_wait_ready(const ShTailArgs& a, int stage) {
 }
 __device__ __forceinline__ void sht_publish(const ShTailArgs& a, int stage) {
     __syncthreads();
-    if (threadIdx.x == 0) st_release_gpu(a.ready, a.base * 3u + (unsigned)stage + 1u);
+    if (threadIdx.x == 0) st_release_gpu(a.ready, a.base * a.stages + (unsigned)stage + 1u);
 }
 
 // LAST CTA: s_vals[0..n) (shared memory, this rank's contribution) -> the reduction slots of exchange `e` in every rank's
@@ -343,6 +344,176 @@ __global__ void __launch_bounds__(SHT_THREADS, 1) arnoldi_tail_sharded_kernel(co
     __syncthreads();
     const double nrm = s_norm;
     // ---- F: the new basis vector (local rows) and the operand of the next matvec (all rows, from the window) ----
+    for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) a.qnext[row0 + i] = s_w[i] / nrm;
+    const double* mine = a.vec[a.rank] + (size_t)((a.seq + 2u) & 1u) * a.nv;
+    for (int g = blockIdx.x * SHT_THREADS + threadIdx.x; g < a.N; g += G * SHT_THREADS) a.xfull[g] = ld_peer(mine + g) / nrm;
+    SHT_STAMP();
+    if (a.dbg && threadIdx.x == 0 && (blockIdx.x == 0 || was_last0)) {
+        long long* d = a.dbg + (was_last0 ? 16 : 0);
+        for (int i = 0; i < 16; ++i) d[i] = i < stamp_n ? stamps[i] - stamps[0] : -1;
+    }
+#undef SHT_STAMP
+}
+
+// ---- version 2: COLUMN-owned dot products --------------------------------------------------------------------------------
+// In the kernel above a Gram-Schmidt pass costs (measured at n_loc = 7376, k = 535: MACHLINE_SHT_DEBUG) 7 us of row-owned
+// partial dots, then 7 us in which ONE CTA adds the 148 x k partials while the others wait, then the exchange.  Here a CTA
+// owns whole COLUMNS for the dot products: it reads its ceil(k / grid) columns of Qloc and w_loc once, reduces them inside
+// the CTA (fixed order) and stores the finished coefficients straight into every rank's window -- no partial array, no
+// serial reduction; the last CTA to arrive only raises and awaits the flags.  The subtraction stays ROW-owned (a CTA keeps
+// its rows of w in shared memory), so a pass needs one more grid-wide wait (w complete before the second pass' dots):
+//   D1 (columns) | flags | h1 = sum over ranks | S1 (rows) | wait | D2 (columns) | flags | h2 | S2 (rows) + all-gather
+//   of the new vector | norm exchange | scale
+constexpr int SHT2_NC = 4;   // columns a CTA reduces per trip (1024 threads x 4 rows x 4 columns of loads in flight)
+
+// this rank's dot products of columns [c0, c0 + nc) with w_loc -> slot `rank` of exchange e in every rank's window
+__device__ __forceinline__ void sht2_dots(const ShTailArgs& a, unsigned e, int c0, int nc, double* s_red) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double acc[SHT2_NC];
+#pragma unroll
+    for (int c = 0; c < SHT2_NC; ++c) acc[c] = 0.;
+    const double* q0 = a.Q + (size_t)c0 * a.ldq;
+    for (int i0 = threadIdx.x; i0 < a.n_loc; i0 += 4 * SHT_THREADS) {
+        double wv[4], qv[4][SHT2_NC];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int r = i0 + u * SHT_THREADS;
+            const bool on = r < a.n_loc;
+            wv[u] = on ? __ldcg(a.w + r) : 0.;
+#pragma unroll
+            for (int c = 0; c < SHT2_NC; ++c) qv[u][c] = (on && c < nc) ? q0[(size_t)c * a.ldq + r] : 0.;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < SHT2_NC; ++c) acc[c] = fma(qv[u][c], wv[u], acc[c]);
+    }
+#pragma unroll
+    for (int c = 0; c < SHT2_NC; ++c) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+        if (lane == 0) s_red[warp * SHT2_NC + c] = acc[c];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < nc * a.P) {   // thread (column, destination rank): warp order, then one peer store
+        const int c = threadIdx.x / a.P, p = threadIdx.x % a.P;
+        double v = 0.;
+#pragma unroll 8
+        for (int w2 = 0; w2 < SHT_WARPS; ++w2) v += s_red[w2 * SHT2_NC + c];
+        a.red[p][(size_t)(e & 1u) * Ctx::P2P_MAX * a.kr + (size_t)a.rank * a.kr + c0 + c] = v;
+    }
+    __syncthreads();
+}
+
+// LAST CTA: raise this rank's flag of exchange e in every window (system-scope release: cumulative over the coefficient stores
+// of all CTAs, which reached this CTA through their ticket arrival), then wait for the P flags of the own window
+__device__ __forceinline__ void sht2_flags(const ShTailArgs& a, unsigned e) {
+    const size_t foff = (size_t)(e & 1u) * Ctx::P2P_MAX;
+    if ((int)threadIdx.x < a.P) {
+        st_release_sys(a.flags[threadIdx.x] + foff + a.rank, e);
+        const unsigned* f = a.flags[a.rank] + foff + threadIdx.x;
+        const long long t0 = clock64();
+        while ((int)(ld_acquire_sys(f) - e) < 0) {
+            if (clock64() - t0 > SHT_SPIN_LIMIT) {
+                *a.err = 1;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(SHT_THREADS, 1) arnoldi_tail_sharded2_kernel(const ShTailArgs a) {
+    extern __shared__ double s_mem[];
+    const int kk = (a.k + 3) & ~1;
+    double* s_h = s_mem;                 // [kk] coefficients being applied
+    double* s_out = s_mem + kk;          // [kk] scratch of the norm exchange
+    double* s_acc = s_mem + 2 * kk;      // [SHT_MAXCH][32 warps][32 lanes]; the dot phase keeps its warp sums here as well
+    double* s_w = s_acc + SHT_MAXCH * SHT_THREADS;   // [rows_per_cta] this CTA's rows of w
+    __shared__ int s_flag;
+    __shared__ double s_norm;
+    const int row0 = blockIdx.x * a.rows_per_cta;
+    const int nrows = max(0, min(a.rows_per_cta, a.n_loc - row0));
+    const unsigned G = gridDim.x;
+    const int npc = (a.k + (int)G - 1) / (int)G;                    // columns per CTA
+    const int col_lo = min(a.k, (int)blockIdx.x * npc), col_hi = min(a.k, col_lo + npc);
+    int stamp_n = 0;
+    long long stamps[16];
+#define SHT_STAMP() do { if (a.dbg && stamp_n < 16) stamps[stamp_n++] = clock64(); } while (0)
+    SHT_STAMP();
+    bool was_last0 = false;
+
+    for (int pass = 0; pass < 2; ++pass) {
+        const unsigned e = a.seq + (unsigned)pass;
+        // ---- D: dot products of this CTA's columns with all local rows of w ----
+        for (int c0 = col_lo; c0 < col_hi; c0 += SHT2_NC) sht2_dots(a, e, c0, min(SHT2_NC, col_hi - c0), s_acc);
+        SHT_STAMP();
+        const bool last = sht_arrive_is_last(a, 2 * pass, &s_flag);
+        if (pass == 0) was_last0 = last;
+        if (last) {
+            sht2_flags(a, e);
+            sht_publish(a, 2 * pass);
+        } else {
+            sht_wait_ready(a, 2 * pass);
+        }
+        SHT_STAMP();
+        sht_rank_sum(a, e, a.k, s_h);   // the P contributions in rank order: identical bits on every rank and CTA
+        if (blockIdx.x == 0) {          // the Hessenberg column for the host
+            for (int j = threadIdx.x; j < a.k; j += SHT_THREADS) {
+                if (pass == 0) __stcg(a.h1 + j, s_h[j]);
+                else __stcg(a.hfin + j, __ldcg(a.h1 + j) + s_h[j]);
+            }
+        }
+        SHT_STAMP();
+        // ---- S: subtract on this CTA's rows ----
+        if (pass == 0) {
+            for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) s_w[i] = __ldcg(a.w + row0 + i);
+            __syncthreads();
+        }
+        const double sq = sht_sub_phase(a, row0, nrows, s_h, s_acc, s_w, pass == 1);
+        SHT_STAMP();
+        if (pass == 0) {
+            // w must be complete before the second pass' column dots read all of its rows
+            const bool lastb = sht_arrive_is_last(a, 1, &s_flag);
+            if (lastb) sht_publish(a, 1);
+            else sht_wait_ready(a, 1);
+            SHT_STAMP();
+        } else {
+            if (threadIdx.x == 0) __stcg(a.npart + blockIdx.x, sq);
+            // the all-gather of the next Krylov vector, fused: this CTA's rows go to every rank's window at their global index
+            const size_t voff = (size_t)((a.seq + 2u) & 1u) * a.nv;
+            for (int p = 0; p < a.P; ++p) {
+                double* dst = a.vec[p] + voff;
+                for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) dst[a.g_of_local[row0 + i]] = s_w[i];
+            }
+        }
+    }
+    // ---- the norm ----
+    const bool last3 = sht_arrive_is_last(a, 3, &s_flag);
+    if (last3) {
+        if (threadIdx.x < 32) {
+            double t = 0.;
+            for (unsigned c = threadIdx.x; c < G; c += 32) t += __ldcg(a.npart + c);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (threadIdx.x == 0) s_h[0] = t;
+        }
+        __syncthreads();
+        sht_exchange(a, a.seq + 2u, s_h, 1);
+        sht_publish(a, 3);
+    } else {
+        sht_wait_ready(a, 3);
+    }
+    sht_rank_sum(a, a.seq + 2u, 1, s_out);
+    if (threadIdx.x == 0) {
+        s_norm = sqrt(s_out[0]);
+        if (last3) {
+            __stcg(a.hfin + a.k, s_norm);
+            __stcg(a.hfin + a.k + 1, (double)(*reinterpret_cast<volatile int*>(a.err)));
+        }
+    }
+    __syncthreads();
+    const double nrm = s_norm;
     for (int i = threadIdx.x; i < nrows; i += SHT_THREADS) a.qnext[row0 + i] = s_w[i] / nrm;
     const double* mine = a.vec[a.rank] + (size_t)((a.seq + 2u) & 1u) * a.nv;
     for (int g = blockIdx.x * SHT_THREADS + threadIdx.x; g < a.N; g += G * SHT_THREADS) a.xfull[g] = ld_peer(mine + g) / nrm;

@@ -1170,8 +1170,11 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
     GS_CUDA(cudaMemsetAsync(xloc.p, 0, (size_t)S.shard_pad * c->world * sizeof(double), c->stream));
     if (!(c->attr_mask & 16u)) {
         GS_CUDA(cudaFuncSetAttribute(arnoldi_tail_sharded_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        GS_CUDA(cudaFuncSetAttribute(arnoldi_tail_sharded2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         c->attr_mask |= 16u;
     }
+    // column-owned dot products (gmres_sharded.cuh, version 2) unless MACHLINE_SHT_V1 asks for the row-owned first version
+    const bool tail_v2 = std::getenv("MACHLINE_SHT_V1") == nullptr;
     int depth = 4;
     if (const char* e = std::getenv("MACHLINE_GMRES_LOOKAHEAD")) depth = std::max(1, std::min(8, std::atoi(e)));
     const int n_slots = depth + 1;
@@ -1216,10 +1219,12 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
         a.seq = c->xseq + 1;
         c->xseq += 3;
         a.ticket = sync.p; a.ready = sync.p + 1; a.base = launches_done++;
+        a.stages = tail_v2 ? 4u : 3u;
         a.err = err.p; a.rows_per_cta = rows_per_cta; a.dbg = want_dbg ? dbg.p : nullptr;
         void* kargs[] = {(void*)&a};
         const size_t smem = (size_t)(2 * ((k + 3) & ~1) + SHT_MAXCH * SHT_THREADS + rows_per_cta) * sizeof(double);
-        cudaError_t e = cudaLaunchCooperativeKernel((const void*)arnoldi_tail_sharded_kernel, dim3(grid), dim3(SHT_THREADS), kargs, smem, c->stream);
+        cudaError_t e = cudaLaunchCooperativeKernel(tail_v2 ? (const void*)arnoldi_tail_sharded2_kernel : (const void*)arnoldi_tail_sharded_kernel,
+                                                    dim3(grid), dim3(SHT_THREADS), kargs, smem, c->stream);
         if (e != cudaSuccess) return c->cuda_fail(e, "arnoldi_tail_sharded_kernel");
         c->launches += 1;
         if (c->profile && e1) {   // the exchanges live inside the tail: "exchange" = the whole tail, from the end of the local matvec
