@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "ctx.h"
 #include "record_pack.h"
@@ -478,7 +479,6 @@ static ml_status prepare(ml_ctx* c) {
         ML_CUDA(c, cudaMallocHost(&c->h_stage, recs_bytes + n_lists));
         c->h_stage_bytes = recs_bytes + n_lists;
     }
-    std::memset(c->h_stage, 0, recs_bytes + n_lists);
     struct RecsView {
         double* p;
         size_t n;
@@ -491,33 +491,33 @@ static ml_status prepare(ml_ctx* c) {
         unsigned char* data() const { return p; }
         size_t size() const { return n; }
     } lists{reinterpret_cast<unsigned char*>(c->h_stage) + recs_bytes, n_lists};
-    std::vector<unsigned char> col_seen(m.n_unknown, 0);
-    std::vector<int> wcol_of(m.n_unknown, -1), wcols;      // compact wake column ids
-    std::vector<unsigned char> wseen;
-    std::vector<int> slot_of_col(m.n_unknown, -1);           // scratch: column -> position in the current chunk's list
-    auto build_chunk = [&](int chunk, const std::vector<HostRecord>& src, size_t first, bool wake) {
+    if (n_chunks == 0) std::memset(c->h_stage, 0, recs_bytes + n_lists);
+    // Phase 1 (parallel over chunks: they are independent): pack the records, group the chunk's (record, slot) items by
+    // target column in order of first appearance.  cols[] holds the raw column here; phase 2 turns it into the final word.
+    auto build_chunk = [&](int chunk, const std::vector<HostRecord>& src, size_t first, bool wake, int* slot_of_col) {
         const size_t n_here = std::min((size_t)C, src.size() - first);
-        int* head = reinterpret_cast<int*>(lists.data() + (size_t)chunk * LB);
+        unsigned char* const lb = lists.data() + (size_t)chunk * LB;
+        std::memset(lb, 0, LB);
+        int* head = reinterpret_cast<int*>(lb);
         unsigned* cols = reinterpret_cast<unsigned*>(head + 4);
         unsigned short* beg = reinterpret_cast<unsigned short*>(head + 4 + MAXI);
         unsigned* item = reinterpret_cast<unsigned*>(beg + MAXI + 2);
         const unsigned item_scale = (unsigned)c->tile_rows * 8u;   // bytes between consecutive staged values of one row
-        std::vector<int> order;                       // columns in order of first appearance
-        std::vector<std::vector<unsigned>> per;       // items per column, in (record, slot) order
+        const int n_stage = (ho ? 6 : 3) + (sup ? 1 : 0);          // staged values per record and row (aic_kernels.cuh: SLOTS)
         // Position of a record inside the chunk: images of the panel itself first, mirror images after them (each group in
         // stream order), so that the records a warp evaluates together share the mirror flag (pair_influence.cuh).  The order
         // of ADDITION is unaffected: it is the order of the items below, which follows the stream.
-        std::vector<int> pos(n_here);
+        int pos[128];
         {
             int n0 = 0;
             for (size_t r = 0; r < n_here; ++r) n0 += (src[first + r].img == 0);
             int p0 = 0, p1 = n0;
             for (size_t r = 0; r < n_here; ++r) pos[r] = (src[first + r].img == 0) ? p0++ : p1++;
         }
+        int order[6 * 128], count[6 * 128], n_order = 0;   // columns in order of first appearance, items per column
         for (size_t r0 = 0; r0 < n_here; ++r0) {
             const HostRecord& hr = src[first + r0];
-            const size_t r = (size_t)pos[r0];
-            double* const rec_p = recs.data() + ((size_t)chunk * C + r) * STRIDE;
+            double* const rec_p = recs.data() + ((size_t)chunk * C + pos[r0]) * STRIDE;
             pack_record(rec_p, STRIDE, sup, view_of(*hr.table), hr.j, hr.img, hr.sigma_val, hr.flags);
             if (ho) {
                 if (wake) {   // wake panels stay lower order: their 3 x 3 T_mu in the upper left corner, no sources
@@ -531,22 +531,68 @@ static ml_status prepare(ml_ctx* c) {
                     pack_record_ho(rec_p, sup, hr.table->T_mu6.data() + 36 * ((size_t)hr.j + (size_t)hr.img * hr.table->n_panels), hr.w);
                 }
             }
-            const int n_stage = (ho ? 6 : 3) + (sup ? 1 : 0);   // staged values per record and row (aic_kernels.cuh: SLOTS)
             for (int k = 0; k < hr.n_slots; ++k) {
                 const int col = hr.cols[k];
                 if (slot_of_col[col] < 0) {
-                    slot_of_col[col] = (int)order.size();
-                    order.push_back(col);
-                    per.emplace_back();
+                    slot_of_col[col] = n_order;
+                    order[n_order] = col;
+                    count[n_order] = 0;
+                    ++n_order;
                 }
-                // a wake panel's items 3..5 (bottom side) read its slots 0..2 again, negated (panel.f90:2909-2912)
-                const int slot = wake ? k % 3 : k;
-                per[slot_of_col[col]].push_back((unsigned)(r * n_stage + slot) * item_scale | ((wake && k >= 3) ? ITEM_NEG : 0u));
+                count[slot_of_col[col]] += 1;
             }
         }
+        for (size_t r = n_here; r < (size_t)C; ++r) std::memset(recs.data() + ((size_t)chunk * C + r) * STRIDE, 0, sizeof(double) * STRIDE);
         int n_items = 0;
-        for (size_t i = 0; i < order.size(); ++i) {
-            const int col = order[i];
+        for (int i = 0; i < n_order; ++i) {
+            cols[i] = (unsigned)order[i];
+            beg[i] = (unsigned short)n_items;
+            n_items += count[i];
+            count[i] = beg[i];   // fill cursor
+        }
+        beg[n_order] = (unsigned short)n_items;
+        bool any_src = false;
+        for (size_t r0 = 0; r0 < n_here; ++r0) {
+            const HostRecord& hr = src[first + r0];
+            any_src = any_src || (hr.flags & RF_SOURCE);
+            for (int k = 0; k < hr.n_slots; ++k) {
+                // a wake panel's items 3..5 (bottom side) read its slots 0..2 again, negated (panel.f90:2909-2912)
+                const int slot = wake ? k % 3 : k;
+                item[count[slot_of_col[hr.cols[k]]]++] =
+                    (unsigned)(pos[r0] * n_stage + slot) * item_scale | ((wake && k >= 3) ? ITEM_NEG : 0u);
+            }
+        }
+        for (int i = 0; i < n_order; ++i) slot_of_col[order[i]] = -1;
+        head[0] = n_order;
+        head[1] = n_items;
+        head[2] = (wake ? LF_WAKE : 0) | (any_src ? LF_SOURCES : 0);
+        head[3] = (int)n_here;
+    };
+    {
+        const int n_thr = std::max(1, std::min({(int)std::thread::hardware_concurrency(), 8, n_chunks / 8 + 1}));
+        auto worker = [&](int t) {
+            std::vector<int> slot_of_col(m.n_unknown, -1);   // scratch: column -> position in the current chunk's list
+            for (int ch = t; ch < n_chunks; ch += n_thr) {
+                if (ch < n_body_chunks) build_chunk(ch, body_recs, (size_t)ch * C, false, slot_of_col.data());
+                else build_chunk(ch, wake_recs, (size_t)(ch - n_body_chunks) * C, true, slot_of_col.data());
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < n_thr; ++t) pool.emplace_back(worker, t);
+        worker(0);
+        for (auto& th : pool) th.join();
+    }
+    // Phase 2 (sequential, cheap): the first chunk of a pass that touches a column starts its sum from zero; wake columns get
+    // compact ids in order of first appearance.
+    std::vector<unsigned char> col_seen(m.n_unknown, 0);
+    std::vector<int> wcol_of(m.n_unknown, -1), wcols;      // compact wake column ids
+    std::vector<unsigned char> wseen;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+        int* head = reinterpret_cast<int*>(lists.data() + (size_t)ch * LB);
+        unsigned* cols = reinterpret_cast<unsigned*>(head + 4);
+        const bool wake = ch >= n_body_chunks;
+        for (int i = 0; i < head[0]; ++i) {
+            const int col = (int)cols[i];
             unsigned target;
             bool first_touch;
             if (wake) {
@@ -564,20 +610,8 @@ static ml_status prepare(ml_ctx* c) {
                 col_seen[col] = 1;
             }
             cols[i] = target | (first_touch ? COL_FIRST : 0u);
-            beg[i] = (unsigned short)n_items;
-            for (unsigned u : per[i]) item[n_items++] = u;
-            slot_of_col[col] = -1;
         }
-        beg[order.size()] = (unsigned short)n_items;
-        head[0] = (int)order.size();
-        head[1] = n_items;
-        bool any_src = false;
-        for (size_t r0 = 0; r0 < n_here; ++r0) any_src = any_src || (src[first + r0].flags & RF_SOURCE);
-        head[2] = (wake ? LF_WAKE : 0) | (any_src ? LF_SOURCES : 0);
-        head[3] = (int)n_here;
-    };
-    for (int ch = 0; ch < n_body_chunks; ++ch) build_chunk(ch, body_recs, (size_t)ch * C, false);
-    for (int ch = 0; ch < n_wake_chunks; ++ch) build_chunk(n_body_chunks + ch, wake_recs, (size_t)ch * C, true);
+    }
     c->n_chunks = n_chunks;
     c->n_wcols = (int)wcols.size();
     std::vector<int> zero_cols;
