@@ -1,7 +1,9 @@
 // C ABI of the host setup library (include/machline_host.h): flattens the Case object into the
 // plain tables that the GPU library takes (ml_flow / ml_panel_soa / ml_system_map), mirroring what
 // a Fortran bind(C) shim would do with type(panel) (src/panel.f90:38-70).
+#include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -137,6 +139,25 @@ struct PanelTableStore {
 };
 
 }  // namespace
+
+void mlh::Case::setup() {
+    const bool timing = std::getenv("MLH_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "mlh setup: %-16s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
+    init_mesh();
+    lap("init_mesh");
+    init_with_flow();
+    lap("init_with_flow");
+    init_solver();
+    lap("init_solver");
+    pre_solve();
+    lap("pre_solve");
+}
 
 struct mlh_case {
     Case c;

@@ -207,12 +207,7 @@ struct Case {
     void init_with_flow();  // surface_mesh_init_with_flow           surface_mesh.f90:683-756
     void init_solver();     // panel_solver_init minus the DoD pass  panel_solver.f90:115-161
     void pre_solve();       // calc_source_strengths + assemble_BC_vector  panel_solver.f90:1069,1078
-    void setup() {
-        init_mesh();
-        init_with_flow();
-        init_solver();
-        pre_solve();
-    }
+    void setup();   // init_mesh, init_with_flow, init_solver, pre_solve (capi.cpp; MLH_TIMING=1 prints the phases)
     // x -> mu, sigma; cell velocities, pressures, forces, moments (panel_solver.f90:2012-2615)
     Results post(const std::vector<double>& x, const double* v_inner = nullptr) const;
     std::vector<double> inner_points() const;
