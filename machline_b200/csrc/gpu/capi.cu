@@ -21,17 +21,30 @@ void HostPanelTable::copy_from(const ml_panel_soa* t) {
     n_cols = t->n_cols;
     in_wake = t->in_wake;
     const size_t nr = (size_t)n_panels * n_images, np = (size_t)n_panels;
-    auto cp = [](std::vector<double>& d, const double* s, size_t n) { d.assign(s, s + n); };
-    cp(centr, t->centr, nr * 3);
+    // the copies are memory-bound (13 MB at 40k records): large tables are copied by a few threads, one array each
+    std::vector<std::thread> pool;
+    const bool par = nr >= 8192 && std::thread::hardware_concurrency() > 2;
+    auto cp = [&](std::vector<double>& d, const double* s, size_t n) {
+        d.resize(n);
+        if (par && n >= 3 * nr) pool.emplace_back([&d, s, n] { std::memcpy(d.data(), s, n * sizeof(double)); });
+        else std::memcpy(d.data(), s, n * sizeof(double));
+    };
     cp(A_g_to_ls, t->A_g_to_ls, nr * 9);
+    cp(vert_g, t->vert_g, nr * 9);
+    cp(T_mu, t->T_mu, nr * 9);
     cp(vertices_ls, t->vertices_ls, nr * 6);
     cp(n_hat_ls, t->n_hat_ls, nr * 6);
+    cp(centr, t->centr, nr * 3);
     cp(b, t->b, nr * 3);
     cp(sqrt_b, t->sqrt_b, nr * 3);
     cp(J, t->J, nr);
     cp(area, t->area, np);
-    cp(vert_g, t->vert_g, nr * 9);
-    cp(T_mu, t->T_mu, nr * 9);
+    struct Join {
+        std::vector<std::thread>& p;
+        ~Join() {
+            for (auto& th : p) th.join();
+        }
+    } join{pool};
     r.assign(t->r, t->r + nr);
     i_vert_d.assign(t->i_vert_d, t->i_vert_d + np * n_cols);
     if (t->i_panel_s) i_panel_s.assign(t->i_panel_s, t->i_panel_s + np);
