@@ -160,7 +160,9 @@ ml_status ml_ctx_create(ml_ctx **out, int device_id);
    device for the duration of a call.  ml_set_row_shard*, ml_set_communicator, ml_device_system and ml_device_stream do
    not apply to such a handle. */
 ml_status ml_ctx_create_multi(ml_ctx **out, const int *device_ids, int n_dev);
-ml_status ml_multi_set_dealing(ml_ctx *ctx, int block_rows);   /* 0: contiguous blocks (default) */
+ml_status ml_multi_set_dealing(ml_ctx *ctx, int block_rows);   /* 0: contiguous blocks; > 0: block-cyclic; -1 (default): contiguous
+                                                                  for subsonic flows, block-cyclic 128 for supersonic ones (the rows
+                                                                  of a sorted supersonic system cost more the further downstream) */
 int ml_device_count(const ml_ctx *ctx);                        /* devices behind the handle (1 for ml_ctx_create) */
 void ml_ctx_destroy(ml_ctx *ctx);
 const char *ml_last_error(const ml_ctx *ctx);

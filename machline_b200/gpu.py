@@ -120,7 +120,7 @@ class Context:
         self.n_cp = case.n_cp
         if self.multi:      # the library deals the rows to its devices; `cyclic` = (block, ...) selects block-cyclic dealing
             assert row0 == 0 and nrows is None
-            self._check(L.ml_multi_set_dealing(self._h, cyclic[0] if cyclic is not None else 0))
+            self._check(L.ml_multi_set_dealing(self._h, cyclic[0] if cyclic is not None else -1))
             self.row0, self.nrows = 0, case.n_cp
             self.local_rows = np.arange(case.n_cp, dtype=np.int32)
             return

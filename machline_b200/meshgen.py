@@ -247,6 +247,29 @@ def materialise_npz(npz_path, out_dir, only=None) -> list[str]:
     return names
 
 
+def subdivide(pts: np.ndarray, tris: np.ndarray, levels: int = 1):
+    """Uniform 1:4 refinement of a triangle mesh (edge midpoints, flat: the geometry is not smoothed), `levels` times.  Keeps
+    the orientation of every panel and produces one shared vertex per edge, so sharp edges (wake-shedding trailing edges) and
+    vertices on a mirror plane stay what they were.  Used to grow the reference's study meshes to the 50k-100k panel class of
+    BASELINE configs[4]."""
+    pts = np.asarray(pts, dtype=np.float64)
+    tris = np.asarray(tris, dtype=np.int64)
+    for _ in range(levels):
+        n = len(pts)
+        e = np.sort(np.concatenate([tris[:, [0, 1]], tris[:, [1, 2]], tris[:, [2, 0]]]), axis=1)
+        key = e[:, 0] * n + e[:, 1]
+        uniq, inv = np.unique(key, return_inverse=True)
+        a, b = uniq // n, uniq % n
+        mid = 0.5 * (pts[a] + pts[b])
+        m = n + inv.reshape(3, -1).T                     # midpoint vertex of edges (01, 12, 20) of every triangle
+        t0, t1, t2 = tris[:, 0], tris[:, 1], tris[:, 2]
+        m01, m12, m20 = m[:, 0], m[:, 1], m[:, 2]
+        tris = np.concatenate([np.stack([t0, m01, m20], 1), np.stack([m01, t1, m12], 1), np.stack([m20, m12, t2], 1),
+                               np.stack([m01, m12, m20], 1)])
+        pts = np.concatenate([pts, mid])
+    return pts, tris.astype(np.int32)
+
+
 def study_input(name: str, mesh_dir: str = "", matrix_solver: str = "GMRES", **over) -> dict:
     """Inputs of BASELINE.json configs[1]-[3] on the reference's own study meshes (SURVEY 8(d) "Concrete inputs";
     studies/subsonic_onera_m6_wing/M6_input.json, studies/supersonic_cone/cone_input.json,
