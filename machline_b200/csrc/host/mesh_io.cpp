@@ -7,6 +7,7 @@
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
+#include <cstring>
 #include <unordered_map>
 
 #include "model.hpp"
@@ -89,73 +90,104 @@ std::vector<std::string> split_ws(const std::string& line) {
 }
 
 void load_vtk(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {
-    std::istringstream in(text);
-    std::string line;
-    std::getline(in, line);
+    // Legacy ASCII VTK (vtk.f90:440-640).  The numbers are scanned in place with strtod / strtol (same conversions as a
+    // stream would apply, no per-token strings); the few header lines go through a line reader.
+    const char* p = text.c_str();
+    const char* const end = p + text.size();
+    auto next_line = [&]() -> std::string {
+        const char* b = p;
+        while (p < end && *p != '\n') ++p;
+        std::string l(b, p);
+        if (p < end) ++p;
+        return l;
+    };
+    std::string line = next_line();
     size_t ind = line.find("Version");
     if (ind == std::string::npos) throw std::runtime_error("VTK header has no Version");
     int ver = line[ind + 8] - '0';
     if (ver != 3 && ver != 5) throw std::runtime_error("VTK file version not recognized");
-    for (int k = 0; k < 3; ++k) std::getline(in, line);  // 3 more header lines
-    std::string tok;
-    int N_verts = 0;
-    in >> tok >> N_verts >> tok;  // POINTS n float
+    for (int k = 0; k < 3; ++k) next_line();  // 3 more header lines
+    line = next_line();                       // POINTS n float
+    auto w = split_ws(line);
+    if (w.size() < 2) throw std::runtime_error("VTK: POINTS line not found");
+    const int N_verts = std::atoi(w[1].c_str());
     std::vector<V3> locs(N_verts);
-    for (int i = 0; i < N_verts; ++i) {
-        std::string a, b, c;
-        in >> a >> b >> c;
-        locs[i] = {std::strtod(a.c_str(), nullptr), std::strtod(b.c_str(), nullptr), std::strtod(c.c_str(), nullptr)};
-    }
+    for (int i = 0; i < N_verts; ++i)
+        for (int k = 0; k < 3; ++k) {
+            char* q = nullptr;
+            locs[i][k] = std::strtod(p, &q);
+            if (q == p) throw std::runtime_error("VTK: truncated POINTS section");
+            p = q;
+        }
     std::vector<int> new_ind;
     collapse_duplicate_vertices(locs, vertices, new_ind);
-    std::getline(in, line);  // rest of last coordinate line
+    next_line();  // rest of last coordinate line
+    auto next_int = [&]() -> long {
+        char* q = nullptr;
+        const long v = std::strtol(p, &q, 10);
+        if (q == p) throw std::runtime_error("VTK: truncated connectivity");
+        p = q;
+        return v;
+    };
+    auto index = [&](long i) -> int {
+        if (i < 0 || i >= N_verts) throw std::runtime_error("VTK: vertex index out of range");
+        return new_ind[i];
+    };
     if (ver == 3) {
         do {
-            if (!std::getline(in, line)) throw std::runtime_error("VTK: POLYGONS not found");
+            if (p >= end) throw std::runtime_error("VTK: POLYGONS not found");
+            line = next_line();
         } while (line.find("POLYGONS") == std::string::npos);
-        auto w = split_ws(line);
+        w = split_ws(line);
         int N_panels = std::atoi(w.at(1).c_str());
         panels.assign(N_panels, Panel());
         for (int i = 0; i < N_panels; ++i) {
-            std::getline(in, line);
-            auto p = split_ws(line);
-            if (p.size() < 4 || p[0] != "3") throw std::runtime_error("MachLine supports only triangular panels.");
-            int i1 = std::atoi(p[1].c_str()), i2 = std::atoi(p[2].c_str()), i3 = std::atoi(p[3].c_str());
-            panel_init(panels[i], vertices, new_ind[i1], new_ind[i2], new_ind[i3], i, false);
+            if (next_int() != 3) throw std::runtime_error("MachLine supports only triangular panels.");
+            const int i1 = index(next_int()), i2 = index(next_int()), i3 = index(next_int());
+            panel_init(panels[i], vertices, i1, i2, i3, i, false);
         }
     } else {
         do {
-            if (!std::getline(in, line)) throw std::runtime_error("VTK: POLYGONS/CELLS not found");
+            if (p >= end) throw std::runtime_error("VTK: POLYGONS/CELLS not found");
+            line = next_line();
         } while (line.find("POLYGONS") == std::string::npos && line.find("CELLS") == std::string::npos);
-        auto w = split_ws(line);
+        w = split_ws(line);
         int N_panels = std::atoi(w.at(1).c_str()) - 1;
         panels.assign(N_panels, Panel());
         do {
-            if (!std::getline(in, line)) throw std::runtime_error("VTK: CONNECTIVITY not found");
+            if (p >= end) throw std::runtime_error("VTK: CONNECTIVITY not found");
+            line = next_line();
         } while (line.find("CONNECTIVITY") == std::string::npos);
-        int idx = 0;
-        while (idx < N_panels) {
-            if (!std::getline(in, line)) throw std::runtime_error("VTK: truncated connectivity");
-            auto p = split_ws(line);
-            for (size_t k = 0; k + 2 < p.size() && k < 9 && idx < N_panels; k += 3) {
-                int i1 = std::atoi(p[k].c_str()), i2 = std::atoi(p[k + 1].c_str()), i3 = std::atoi(p[k + 2].c_str());
-                panel_init(panels[idx], vertices, new_ind[i1], new_ind[i2], new_ind[i3], idx, false);
-                ++idx;
-            }
+        for (int idx = 0; idx < N_panels; ++idx) {
+            const int i1 = index(next_int()), i2 = index(next_int()), i3 = index(next_int());
+            panel_init(panels[idx], vertices, i1, i2, i3, idx, false);
         }
     }
 }
 
 void load_stl(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {
-    std::istringstream in(text);
-    std::string line;
-    std::getline(in, line);  // header
+    // ASCII STL (stl.f90:14-117): every line whose first word is "vertex" carries one corner.  Scanned in place (the
+    // coordinates go through the same strtod as before: identical doubles), without a stream or a token vector per line.
+    const char* p = text.c_str();
+    const char* const end = p + text.size();
+    while (p < end && *p != '\n') ++p;   // header line
     std::vector<V3> locs;
-    while (std::getline(in, line)) {
-        auto w = split_ws(line);
-        if (w.size() >= 4 && w[0] == "vertex")
-            locs.push_back({std::strtod(w[1].c_str(), nullptr), std::strtod(w[2].c_str(), nullptr),
-                            std::strtod(w[3].c_str(), nullptr)});
+    locs.reserve(text.size() / 60);
+    while (p < end) {
+        while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
+        if (end - p > 6 && std::memcmp(p, "vertex", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
+            p += 6;
+            char* q = nullptr;
+            V3 v;
+            v[0] = std::strtod(p, &q);
+            p = q;
+            v[1] = std::strtod(p, &q);
+            p = q;
+            v[2] = std::strtod(p, &q);
+            p = q;
+            locs.push_back(v);
+        }
+        while (p < end && *p != '\n') ++p;
     }
     int N_panels = (int)locs.size() / 3;
     std::vector<int> new_ind;

@@ -4,7 +4,10 @@
 // by a vertex->panel lookup that visits the same candidate pairs in the same (i asc, j asc) order
 // (SURVEY F10 / App. A.18).
 #include <algorithm>
+#include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <stdexcept>
 
 #include "model.hpp"
@@ -43,7 +46,16 @@ void Case::init_mesh() {
     C_max_cont_angle = std::cos(PI * discont_angle / 180.);
     force_sigma_match = g->get("force_sigma_match", true);
 
+    const bool timing = std::getenv("MLH_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "mlh init_mesh: %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     load_mesh_file(mesh_file);
+    lap("load_mesh_file");
 
     // parse_mirror_settings
     std::string mp = g->get("mirror_about", "none");
@@ -76,7 +88,9 @@ void Case::init_mesh() {
 
     if (mirrored) find_vertices_on_mirror();
     locate_adjacent_panels();
+    lap("locate_adjacent_panels");
     calc_vertex_geometry();
+    lap("calc_vertex_geometry");
 }
 
 // surface_mesh.f90:329-343, base_geom.f90:217-234
