@@ -906,6 +906,18 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     // fused Arnoldi tail (one cooperative launch per iteration); MACHLINE_GMRES_TAIL=0 selects the five-kernel sequence
     bool fused_tail = !use_mgs;
     if (const char* e = std::getenv("MACHLINE_GMRES_TAIL")) fused_tail = fused_tail && std::atoi(e) != 0;
+    // the Gram-Schmidt kernels keep the k coefficients of a pass in shared memory: 200 KB opt-in for the fused tail (k_max <= 24.5k),
+    // 64 KB for the five-kernel sequence (k_max <= 7.6k); a Krylov space beyond that is refused, not mis-launched
+    constexpr size_t TAIL_SMEM_MAX = 200 * 1024, SUB_SMEM_MAX = 64 * 1024;
+    if (!use_mgs) {
+        const size_t need_fused = (size_t)(((k_max + 1) & ~1) + 1024) * sizeof(double);
+        const size_t need_split = (size_t)(((k_max + 1) & ~1) + 8 * 64 + 2) * sizeof(double);
+        if (fused_tail && need_fused > TAIL_SMEM_MAX) fused_tail = false;
+        if (!fused_tail && need_split > SUB_SMEM_MAX) {
+            if (need_fused <= TAIL_SMEM_MAX) fused_tail = true;
+            else return c->fail(ML_UNSUPPORTED, "GMRES: max_iterations (the Krylov dimension) is limited to 24 000 on the device; use RGMRES");
+        }
+    }
     const int tail_grid = c->num_sms;
     const int tail_rows = 32 * ((N + 32 * tail_grid - 1) / (32 * tail_grid));
     const int n_rb = fused_tail ? (N + TAIL_RB - 1) / TAIL_RB : (N + ORTH_RB - 1) / ORTH_RB;
@@ -923,7 +935,7 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         // the opt-in is per device: remembered per context, not per process
         if (!(c->attr_mask & 1u)) {
             GM_CUDA(cudaFuncSetAttribute(orth_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-            GM_CUDA(cudaFuncSetAttribute(arnoldi_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+            GM_CUDA(cudaFuncSetAttribute(arnoldi_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX));
             c->attr_mask |= 1u;
         }
     }
