@@ -317,3 +317,83 @@ def test_two_rank_sharded_lu_algorithm(tmp_path, cyclic):
         L.orc_lu_decomp.argtypes = [C.c_int, _abi.c_double_p, _abi.c_int_p]
         assert L.orc_lu_decomp(N, Af.ctypes.data_as(_abi.c_double_p), indx.ctypes.data_as(_abi.c_int_p)) == 0
         assert np.array_equal(indx, r[0]["piv"])
+
+
+def _bjac_worker(rank: int, world: int, port: int, out_dir: str, cyclic: int):
+    """The algorithm of block_jacobi_sharded (csrc/gpu/lu_kernels.cu) on gloo ranks: every rank keeps its rows; the diagonal
+    blocks are assembled with one all-reduce each (one non-zero contributor per entry) and solved on every rank; the block
+    right-hand sides and the residual of the local rows travel through an all-gather of the padded local parts."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, str(ROOT))
+    from machline_b200 import shard
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    try:
+        N, bs, rel, tol = 203, 41, 0.9, 1e-12
+        rng = np.random.default_rng(3)
+        A = rng.standard_normal((N, N)) * 0.05 + np.diag(2.0 + rng.random(N))      # diagonally dominant: block Jacobi converges
+        b = rng.standard_normal(N)
+        if cyclic:
+            rows = shard.cyclic_rows(N, rank, world, cyclic)
+        else:
+            r0, nr = shard.row_shard(N, rank, world)
+            rows = np.arange(r0, r0 + nr)
+        A_loc = A[rows]
+        n_blocks = (N + bs - 1) // bs
+        blocks = []
+        for i in range(n_blocks):
+            s, e = i * bs, min(N, (i + 1) * bs)
+            Bi = torch.zeros((e - s, e - s), dtype=torch.float64)
+            mine = (rows >= s) & (rows < e)
+            Bi[torch.from_numpy(rows[mine] - s)] = torch.from_numpy(A_loc[mine][:, s:e])
+            dist.all_reduce(Bi)                                   # exact: one contributor per entry
+            blocks.append(np.linalg.inv(Bi.numpy()))
+
+        def exchange(v_loc):                                      # local parts -> the replicated vector
+            pad = int(max(_all_gather_obj(dist, len(rows))))
+            buf = torch.zeros(pad, dtype=torch.float64)
+            buf[:len(rows)] = torch.from_numpy(np.ascontiguousarray(v_loc))
+            out = [torch.zeros(pad, dtype=torch.float64) for _ in range(world)]
+            dist.all_gather(out, buf)
+            all_rows = _all_gather_obj(dist, rows)
+            full = np.zeros(N)
+            for r in range(world):
+                full[all_rows[r]] = out[r].numpy()[:len(all_rows[r])]
+            return full
+
+        blk = rows // bs
+        x = exchange(b[rows] / A_loc[np.arange(len(rows)), rows])  # linalg.f90:645-647
+        it, err = 0, 1.0
+        while err >= tol and it < 500:
+            it += 1
+            rhs_loc = np.empty(len(rows))
+            for k, g in enumerate(rows):                          # b_i - sum over the columns outside the row's block
+                s, e = blk[k] * bs, min(N, (blk[k] + 1) * bs)
+                rhs_loc[k] = b[g] - (A_loc[k] @ x - A_loc[k, s:e] @ x[s:e])
+            rhs = exchange(rhs_loc)
+            x_new = np.concatenate([blocks[i] @ rhs[i * bs:min(N, (i + 1) * bs)] for i in range(n_blocks)])
+            x_new = (1. - rel) * x + rel * x_new
+            err = float(np.linalg.norm(exchange(b[rows] - A_loc @ x_new)))
+            x = x_new
+        np.savez(Path(out_dir) / f"bjac_rank{rank}.npz", x=x, it=it, A=A, b=b, bs=bs, rel=rel)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("cyclic", [0, 64])
+def test_two_rank_sharded_block_jacobi_algorithm(tmp_path, cyclic):
+    """block_jacobi_solve (common/linalg.f90:601-728) on a row-sharded system, two gloo ranks: both ranks hold the same x bit for
+    bit, the same iteration count as the oracle's block Jacobi on the whole matrix, the same solution."""
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_bjac_worker, args=(2, port, str(tmp_path), cyclic), nprocs=2, join=True)
+    sys.path.insert(0, str(ROOT / "tests"))
+    import oracle_binding as ob
+    from machline_b200 import _abi
+    r = [np.load(tmp_path / f"bjac_rank{k}.npz") for k in range(2)]
+    assert np.array_equal(r[0]["x"], r[1]["x"]) and int(r[0]["it"]) == int(r[1]["it"])
+    A, b = r[0]["A"], r[0]["b"]
+    opts = _abi.solver_opts("BJAC", preconditioner="none", rel=float(r[0]["rel"]), block_size=int(r[0]["bs"]))
+    x_or, info = ob.solve_system(np.asfortranarray(A), np.zeros(len(b)), b, opts)
+    assert abs(int(r[0]["it"]) - info.iterations) <= 1
+    assert np.abs(r[0]["x"] - x_or).max() <= 1e-10 * np.abs(x_or).max()
