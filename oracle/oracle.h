@@ -24,6 +24,12 @@ typedef struct orc_pair_out {
     double phi_d_M_abs[6];
     double F121[3], F211[3];
     double H211, H121, H313, H223, H133;
+    /* velocity influences of a higher-order table (panel.f90:3011-3170 with S_dim <= 4, M_dim <= 6), global coordinates:
+       v_s_S[4 * i + c] / v_d_M[6 * i + c] = component i of column c; for an order-1 panel the first column / three columns */
+    double v_s_S[12];
+    double v_d_M[18];
+    double F113[3], F123[3], F133[3];
+    double h3H115, H125, hH135, H145, H215, H225, H235, hH315, H325, H415, H113_3rsh2H115;
 } orc_pair_out;
 
 /* tests only: log/atan2 through binary128, rounded once (noise-floor calibration) */

@@ -255,6 +255,10 @@ struct Integrals {
     double F111[3];
     double F121[3] = {0., 0., 0.}, F211[3] = {0., 0., 0.};   // order 2 (panel.f90:2275-2279, 2325-2392)
     double H211 = 0., H121 = 0., H313 = 0., H223 = 0., H133 = 0.;
+    // velocity integrals (panel.f90:2686-2763)
+    double F113[3] = {0., 0., 0.}, F123[3] = {0., 0., 0.}, F133[3] = {0., 0., 0.};
+    double h3H115 = 0., H125 = 0., hH135 = 0., H145 = 0., H215 = 0., H225 = 0., H235 = 0., hH315 = 0., H325 = 0., H415 = 0.,
+           H113_3rsh2H115 = 0.;
     double hH113_abs = 0.;  // running-error scale of hH113: sum over edges of |term| + |cancelled products behind it|
                             // (not a reference quantity; tests only)
 };
@@ -370,6 +374,55 @@ void hH113_supersonic_subinc(const Rec& p, const Geom& g, const Dod& dod, Integr
             }
         }
     }
+}
+
+// panel.f90:2181-2229: E(M,N,K) of every edge; integer powers as Fortran evaluates them (x**0 = 1, x**1 = x, x**2 = x*x)
+inline double ipow(double x, int n) { return n == 0 ? 1. : (n == 1 ? x : x * x); }
+void EMNK(const Geom& g, int M, int N, int K, bool mirror, double E[3]) {
+    for (int i = 0; i < 3; ++i) {
+        const int n = (i + 1) % 3;
+        double E1, E2;
+        if (g.R1[i] == 0.) E1 = 0.0;
+        else if (mirror) E1 = ipow(g.d_ls[n][0], M - 1) * ipow(g.d_ls[n][1], N - 1) / ipow(g.R1[i], K);
+        else E1 = ipow(g.d_ls[i][0], M - 1) * ipow(g.d_ls[i][1], N - 1) / ipow(g.R1[i], K);
+        if (g.R2[i] == 0.) E2 = 0.0;
+        else if (mirror) E2 = ipow(g.d_ls[i][0], M - 1) * ipow(g.d_ls[i][1], N - 1) / ipow(g.R2[i], K);
+        else E2 = ipow(g.d_ls[n][0], M - 1) * ipow(g.d_ls[n][1], N - 1) / ipow(g.R2[i], K);
+        E[i] = E2 - E1;
+    }
+}
+
+// panel.f90:2686-2763: the F and H integrals of the velocity influences (the reference notes that its H recursions are
+// "ONLY SUBSONIC RIGHT NOW", :2740; restated as they are)
+void velocity_recursions(const Geom& g, const Dod& dod, bool mirror, Integrals& I) {
+    double E211[3], E121[3], E131[3], E221[3];
+    EMNK(g, 2, 1, 1, mirror, E211);
+    EMNK(g, 1, 2, 1, mirror, E121);
+    EMNK(g, 1, 3, 1, mirror, E131);
+    EMNK(g, 2, 2, 1, mirror, E221);
+    const double s = I.s, r = I.r, rs = I.rs;
+    for (int i = 0; i < 3; ++i) {
+        if (!dod.e[i]) {
+            I.F113[i] = I.F123[i] = I.F133[i] = 0.;
+            continue;
+        }
+        const double vx = g.v_xi[i], ve = g.v_eta[i];
+        I.F113[i] = (-s * ve * E211[i] + r * vx * E121[i]) / g.g2[i];
+        I.F123[i] = (-r * (vx * vx) * I.F121[i] + r * vx * E131[i] - s * ve * E221[i] + s * ve * vx * I.F211[i]) / g.g2[i];
+        I.F133[i] = (r * ve * g.a[i] * I.F123[i] + (vx * vx) * I.F111[i] - vx * E121[i]) / (s * (vx * vx) + r * (ve * ve));
+    }
+    auto sum3 = [](const double* u, const double* v) { return (u[0] * v[0] + u[1] * v[1]) + u[2] * v[2]; };
+    I.h3H115 = rs * (I.hH113 + g.h * sum3(g.a, I.F113)) / 3;
+    I.H125 = -s * sum3(g.v_eta, I.F113) / 3.;
+    I.hH135 = s * (I.hH113 - g.h * sum3(g.v_eta, I.F123)) / 3.;
+    I.H145 = s * (2. * I.H123 - sum3(g.v_eta, I.F133)) / 3.;
+    I.H215 = -r * sum3(g.v_xi, I.F113) / 3.;
+    I.H225 = -r * sum3(g.v_xi, I.F123) / 3.;
+    I.H235 = -r * sum3(g.v_xi, I.F133) / 3.;
+    I.hH315 = -rs * I.hH135 - s * I.h3H115 + r * I.hH113;
+    I.H325 = -rs * I.H145 - s * g.h2 * I.H125 + r * I.H123;
+    I.H415 = -rs * I.H235 - s * g.h2 * I.H215 + r * I.H223;   // sic (:2760): R^2 = xi^2 + eta^2 + h^2 gives H213 here; see tests/test_oracle_identities.py
+    I.H113_3rsh2H115 = -sum3(g.a, I.F113);
 }
 
 // panel.f90:2766-2812 + 2631-2647
@@ -532,6 +585,89 @@ extern "C" void orc_pair_influence(const ml_flow* fs, const ml_panel_soa* t, int
                 for (int k = 0; k < 3; ++k) acc = acc + p.A[3 * k + i] * vM[3 * k + c];
                 out->v_d[3 * i + c] = acc;
             }
+    }
+    // the same for a higher-order table (panel.f90:3011-3170): S_dim / M_dim columns
+    if (t->order2) {
+        for (int i = 0; i < 3; ++i) {
+            out->F113[i] = 0.;
+            out->F123[i] = 0.;
+            out->F133[i] = 0.;
+        }
+        if (p.order == 2) {
+            velocity_recursions(g, dod, mirror, I);
+            for (int i = 0; i < 3; ++i) {
+                out->F113[i] = I.F113[i];
+                out->F123[i] = I.F123[i];
+                out->F133[i] = I.F133[i];
+            }
+            out->h3H115 = I.h3H115; out->H125 = I.H125; out->hH135 = I.hH135; out->H145 = I.H145; out->H215 = I.H215;
+            out->H225 = I.H225; out->H235 = I.H235; out->hH315 = I.hH315; out->H325 = I.H325; out->H415 = I.H415;
+            out->H113_3rsh2H115 = I.H113_3rsh2H115;
+            const double r = I.r, sg = I.s, rs = I.rs, x = g.P_ls[0], y = g.P_ls[1], h = g.h, h2 = g.h2;
+            // assemble_v_s_S_space, panel.f90:3029-3072
+            if (has_src) {
+                double vs[3][3];   // [component][sigma parameter]
+                vs[0][0] = r * I.H213;
+                vs[1][0] = sg * I.H123;
+                vs[2][0] = -rs * I.hH113;
+                vs[0][1] = r * (I.H213 * x + I.H313);
+                vs[0][2] = r * (I.H213 * y + I.H223);
+                vs[1][1] = sg * (I.H123 * x + I.H223);
+                vs[1][2] = sg * (I.H123 * y + I.H133);
+                vs[2][1] = -rs * (I.hH113 * x + h * I.H213);
+                vs[2][2] = -rs * (I.hH113 * y + h * I.H123);
+                double vS[3][4] = {};
+                for (int i = 0; i < 3; ++i)
+                    for (int c = 0; c < p.S_dim; ++c) {
+                        double acc = 0.;
+                        for (int k = 0; k < 3; ++k) acc = acc + vs[i][k] * p.Ts[4 * k + c];
+                        vS[i][c] = -acc * fs->K_inv * p.J;
+                    }
+                for (int i = 0; i < 3; ++i)
+                    for (int c = 0; c < p.S_dim; ++c) {
+                        double acc = 0.;
+                        for (int k = 0; k < 3; ++k) acc = acc + p.A[3 * k + i] * vS[k][c];
+                        out->v_s_S[4 * i + c] = acc;
+                    }
+            }
+            // assemble_v_d_M_space, panel.f90:3118-3166
+            double vd[3][6] = {};
+            vd[0][1] = I.hH113;
+            vd[1][2] = I.hH113;
+            vd[2][1] = I.H213;
+            vd[2][2] = I.H123;
+            vd[0][3] = 3. * r * (0.5 * I.H215 * (x * x) * h + I.hH315 * x + 0.5 * I.H415 * h);
+            vd[0][4] = 3. * r * (I.H215 * h * x * y + I.hH315 * y + I.H225 * h * x + I.H325 * h);
+            vd[0][5] = 3. * r * (0.5 * I.H215 * (y * y) * h + I.H225 * h * y + 0.5 * I.H235 * h);
+            vd[1][3] = 3. * sg * (0.5 * I.H125 * (x * x) * h + I.H225 * h * x + 0.5 * I.H325 * h);
+            vd[1][4] = 3. * sg * (I.H125 * h * x * y + I.hH135 * x + I.H225 * h * y + I.H235 * h);
+            vd[1][5] = 3. * sg * (0.5 * I.H125 * (y * y) * h + I.hH135 * y + 0.5 * I.H145 * h);
+            vd[2][3] = 0.5 * (x * x) * I.H113_3rsh2H115 + x * (I.H213 - 3. * rs * h2 * I.H215) + 0.5 * (I.H313 - 3. * rs * h * I.hH315);
+            vd[2][4] = x * y * (I.H113_3rsh2H115) + y * (I.H213 - 3. * rs * h2 * I.H215) + x * (I.H123 - 3. * rs * h2 * I.H125) + I.H223 -
+                       3. * rs * h2 * I.H225;
+            vd[2][5] = 0.5 * (y * y) * I.H113_3rsh2H115 + y * (I.H123 - 3. * rs * h2 * I.H125) + 0.5 * (I.H133 - 3. * rs * h * I.hH135);
+            double vM[3][6] = {};
+            for (int i = 0; i < 3; ++i)
+                for (int c = 0; c < p.M_dim; ++c) {
+                    double acc = 0.;
+                    for (int k = 0; k < 6; ++k) acc = acc + vd[i][k] * p.T6[6 * k + c];
+                    vM[i][c] = I.s * fs->K_inv * acc;
+                }
+            for (int i = 0; i < 3; ++i)
+                for (int c = 0; c < p.M_dim; ++c) {
+                    double acc = 0.;
+                    for (int k = 0; k < 3; ++k) acc = acc + p.A[3 * k + i] * vM[k][c];
+                    out->v_d_M[6 * i + c] = acc;
+                }
+        } else {   // an order-1 panel of the table
+            for (int i = 0; i < 3; ++i) {
+                out->v_s_S[4 * i] = out->v_s[i];
+                for (int c = 0; c < 3; ++c) out->v_d_M[6 * i + c] = 0.;
+            }
+            // its T_mu lives in the upper left corner of T6 (p.T is filled as well for order 1)
+            for (int i = 0; i < 3; ++i)
+                for (int c = 0; c < 3; ++c) out->v_d_M[6 * i + c] = out->v_d[3 * i + c];
+        }
     }
     // magnitude of the terms that were summed into phi_d[c] (forward-error scale, tests only)
     double ma[3];
@@ -700,6 +836,29 @@ extern "C" int orc_assemble_n(const ml_flow* fs, const ml_panel_soa* body, const
                     orc_pair_influence(fs, body, j, img, Pt, &o);
                     if (!o.in_dod) continue;
                     bool mirrored_panel = (img == 1) && map->asym_flow;
+                    if (body->order2) {   // S_dim / M_dim columns of a higher-order table
+                        if (body->has_sources[j]) {
+                            for (int k = 0; k < body->S_dim[j]; ++k) {
+                                const double source_inf = project_velocity(fs, n_g, o.v_s_S + k, 4, mf);
+                                int ips = body->i_panel_s4[(size_t)j * 4 + k];
+                                int index;
+                                if (mirrored_panel) index = (ips >= N_panels) ? ips - N_panels : ips + N_panels;
+                                else index = (ips >= N_panels) ? ips - N_panels : ips;
+                                if (map->sigma_known[index]) I_known_i = I_known_i + source_inf * map->sigma[index];
+                                else A_i[P[map->i_sigma_in_sys[index]]] += source_inf;
+                            }
+                        }
+                        for (int k = 0; k < body->M_dim[j]; ++k) {
+                            const double doublet_inf = project_velocity(fs, n_g, o.v_d_M + k, 6, mf);
+                            int iv = body->i_vert_d[(size_t)j * body->n_cols + k];
+                            int index;
+                            if (mirrored_panel) index = (iv >= N_verts) ? iv - N_verts : iv + N_verts;
+                            else index = (iv >= N_verts) ? iv - N_verts : iv;
+                            A_i[P[index]] = A_i[P[index]] + doublet_inf;
+                            if (A_abs) S_i[P[index]] += std::fabs(doublet_inf);
+                        }
+                        continue;
+                    }
                     if (body->has_sources[j]) {
                         const double source_inf = project_velocity(fs, n_g, o.v_s, 1, mf);
                         int ips = body->i_panel_s[j];

@@ -29,7 +29,11 @@ class OrcPairOut(C.Structure):
                 ("phi_d_abs", C.c_double * 3), ("v_s", C.c_double * 3), ("v_d", C.c_double * 9),
                 ("phi_s_S", C.c_double * 4), ("phi_d_M", C.c_double * 6), ("phi_d_M_abs", C.c_double * 6),
                 ("F121", C.c_double * 3), ("F211", C.c_double * 3), ("H211", C.c_double), ("H121", C.c_double),
-                ("H313", C.c_double), ("H223", C.c_double), ("H133", C.c_double)]
+                ("H313", C.c_double), ("H223", C.c_double), ("H133", C.c_double),
+                ("v_s_S", C.c_double * 12), ("v_d_M", C.c_double * 18), ("F113", C.c_double * 3), ("F123", C.c_double * 3),
+                ("F133", C.c_double * 3), ("h3H115", C.c_double), ("H125", C.c_double), ("hH135", C.c_double), ("H145", C.c_double),
+                ("H215", C.c_double), ("H225", C.c_double), ("H235", C.c_double), ("hH315", C.c_double), ("H325", C.c_double),
+                ("H415", C.c_double), ("H113_3rsh2H115", C.c_double)]
 
 
 _lib = None
