@@ -37,6 +37,7 @@ struct ShTailArgs {
     int gpad;
     double* h1;             // [k] coefficients of the pass being applied (global scratch)
     double* hfin;           // [k + 2]: h1 + h2, the norm, and the error flag (as a double) for the host
+    double* hhost;          // version 2: the same k + 2 numbers stored straight into the host's pinned slot (mapped), or nullptr
     double* npart;          // [grid]
     double* qnext;          // Qloc(:, k)
     double* xfull;          // [N] next Krylov vector, replicated (operand of the next matvec)
@@ -461,7 +462,11 @@ __global__ void __launch_bounds__(SHT_THREADS, 1) arnoldi_tail_sharded2_kernel(c
         if (blockIdx.x == 0) {          // the Hessenberg column for the host
             for (int j = threadIdx.x; j < a.k; j += SHT_THREADS) {
                 if (pass == 0) __stcg(a.h1 + j, s_h[j]);
-                else __stcg(a.hfin + j, __ldcg(a.h1 + j) + s_h[j]);
+                else {
+                    const double hj = __ldcg(a.h1 + j) + s_h[j];
+                    __stcg(a.hfin + j, hj);
+                    if (a.hhost) a.hhost[j] = hj;
+                }
             }
         }
         SHT_STAMP();
@@ -508,8 +513,13 @@ __global__ void __launch_bounds__(SHT_THREADS, 1) arnoldi_tail_sharded2_kernel(c
     if (threadIdx.x == 0) {
         s_norm = sqrt(s_out[0]);
         if (last3) {
+            const double errd = (double)(*reinterpret_cast<volatile int*>(a.err));
             __stcg(a.hfin + a.k, s_norm);
-            __stcg(a.hfin + a.k + 1, (double)(*reinterpret_cast<volatile int*>(a.err)));
+            __stcg(a.hfin + a.k + 1, errd);
+            if (a.hhost) {
+                a.hhost[a.k] = s_norm;
+                a.hhost[a.k + 1] = errd;
+            }
         }
     }
     __syncthreads();

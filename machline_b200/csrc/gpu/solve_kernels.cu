@@ -34,10 +34,18 @@ namespace mlgpu {
 constexpr int GEMV_THREADS = 256;
 constexpr int GEMV_ROWS = 64;
 constexpr int GEMV_UNROLL = 8;
+constexpr double GEMV_L2_PIN_MB_DEFAULT = 0.;   // MACHLINE_GEMV_L2_PIN_MB overrides
 
 __device__ __forceinline__ double2 ld_stream_d2(const double* p) {
     double2 v;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+// the same load with an L2 eviction policy (createpolicy): the matvec keeps a fixed slice of A resident in L2 across the
+// iterations of a Krylov solve (evict_last) and streams the rest past it (evict_first)
+__device__ __forceinline__ double2 ld_stream_d2_hint(const double* p, unsigned long long pol) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(pol));
     return v;
 }
 
@@ -68,12 +76,19 @@ __global__ void __launch_bounds__(512) p2p_push_kernel(const double* __restrict_
 
 // The CTA that finishes a 64-row block last (ticket counter per row block) adds the split partials in split order and
 // writes y = alpha * sum: the result does not depend on which CTA that is, and no second kernel is needed.
+//
+// L2 residency (pin_cols > 0): the same A is streamed once per Krylov iteration and is larger than L2, so a plain stream
+// gets nothing from the 126 MB cache.  A fixed slice of the columns (pin_cols, see below) is loaded with an evict_last policy
+// and the others with evict_first: after the first iteration that slice (sized by the host to fit beside the Krylov basis)
+// is served from L2 in every later matvec of the solve.  The kept columns are spread over the trips of the column loop,
+// not put first: a block of hits followed by a block of misses runs at L2 speed and then at DRAM speed (measured: 40 % of
+// the ideal gain), interleaved the two overlap.  The order of the additions does not change.
 __global__ void __launch_bounds__(GEMV_THREADS) gemv_n_partial_kernel(const double* __restrict__ A, int ld, int n_rows_pad,
                                                                        int n_cols, int cols_per_split,
                                                                        const double* __restrict__ x,
                                                                        double* __restrict__ y_part, unsigned* __restrict__ tickets,
                                                                        int n_rows, const double* __restrict__ alpha_dev,
-                                                                       double alpha, double* __restrict__ y) {
+                                                                       double alpha, double* __restrict__ y, int pin_cols) {
     __shared__ double2 s_acc[GEMV_THREADS / 32][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * GEMV_ROWS + 2 * lane;
@@ -83,6 +98,31 @@ __global__ void __launch_bounds__(GEMV_THREADS) gemv_n_partial_kernel(const doub
     double2 acc = make_double2(0., 0.);
     const double* Ap = A + row;
     int c = c0 + warp;
+    if (pin_cols > 0) {
+        // pin_cols = 256 * base + f: in every trip of 64 columns the first `base` of the 8 loads of a thread are kept, and one
+        // more in f of every 256 trips (evenly spread), so that L2 hits and DRAM reads are in flight together all the time
+        unsigned long long pol_keep, pol_stream;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
+        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_stream));
+        const int base = pin_cols >> 8, f256 = pin_cols & 255;
+        int trip_no = 0;
+        for (; c + (GEMV_UNROLL - 1) * NW < c1; c += GEMV_UNROLL * NW) {
+            double2 v[GEMV_UNROLL];
+            double xv[GEMV_UNROLL];
+            const int npin = base + ((((trip_no + 1) * f256) >> 8) != ((trip_no * f256) >> 8) ? 1 : 0);
+            ++trip_no;
+#pragma unroll
+            for (int u = 0; u < GEMV_UNROLL; ++u)
+                v[u] = ld_stream_d2_hint(Ap + (size_t)(c + u * NW) * ld, u < npin ? pol_keep : pol_stream);
+#pragma unroll
+            for (int u = 0; u < GEMV_UNROLL; ++u) xv[u] = __ldg(x + c + u * NW);
+#pragma unroll
+            for (int u = 0; u < GEMV_UNROLL; ++u) {
+                acc.x = fma(v[u].x, xv[u], acc.x);
+                acc.y = fma(v[u].y, xv[u], acc.y);
+            }
+        }
+    }
     // main loop: GEMV_UNROLL independent 16-byte loads in flight per thread
     for (; c + (GEMV_UNROLL - 1) * NW < c1; c += GEMV_UNROLL * NW) {
         double2 v[GEMV_UNROLL];
@@ -482,6 +522,222 @@ __global__ void __launch_bounds__(TAIL_THREADS, 1) arnoldi_tail_kernel(const Tai
     }
 }
 
+// ---- fused Arnoldi tail, version 3 (default): column-owned dot products ------------------------------------------------
+// The first version's dot phase left an [N / 256] x k array of partial sums that every CTA of the subtraction phase then
+// added up again, column by column, with dependent L2 loads (29 per column at N = 7376; 7 us of a 19 us pass at k = 535).
+// Here a CTA owns whole COLUMNS of Q in the dot phases (groups of CG columns, all 1024 threads over the rows, one fixed
+// reduction tree: the finished coefficient is stored once) and ROWS in the subtraction phases (the coefficients are read
+// straight from that array, eight independent loads in flight per thread).  Same arithmetic sequence as classical
+// Gram-Schmidt with one re-orthogonalisation pass; the sums are deterministic and independent of the grid size.
+// CTA 0 finally writes the Hessenberg column into the host's pinned slot (mapped memory): no copy-engine operation
+// between the kernels of consecutive iterations.
+struct Tail3Args {
+    const double* Q;
+    int ldq, n, k;
+    double* w;
+    double* h1;             // first-pass coefficients
+    double* h2;             // second-pass corrections
+    double* hfin;           // hfin[0..k-1] = h1 + h2, hfin[k] = ||w||
+    double* hhost;          // the same k + 1 numbers in mapped pinned host memory (nullptr: none)
+    double* npart;          // [gridDim.x]
+    double* qnext;          // Q(:, k)
+    unsigned* bar;
+    unsigned bar_base;
+    int rows_per_cta;       // multiple of 32
+    long long* dbg;         // MACHLINE_TAIL_DEBUG: [16] accumulated clock64 deltas of CTA 0 per phase boundary, [16] = launches
+};
+
+template <int CG>
+__device__ __forceinline__ void tail3_dot_phase(const Tail3Args& a, double* s_red, bool second) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ngroups = (a.k + CG - 1) / CG;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int col0 = g * CG;
+        const double* q[CG];
+#pragma unroll
+        for (int c = 0; c < CG; ++c) q[c] = a.Q + (size_t)min(col0 + c, a.k - 1) * a.ldq;
+        double acc[CG];
+#pragma unroll
+        for (int c = 0; c < CG; ++c) acc[c] = 0.;
+        int r = threadIdx.x;
+        for (; r + 3 * TAIL_THREADS < a.n; r += 4 * TAIL_THREADS) {
+            double wv[4], qv[CG][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wv[u] = __ldcg(a.w + r + u * TAIL_THREADS);
+#pragma unroll
+            for (int c = 0; c < CG; ++c)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) qv[c][u] = __ldcg(q[c] + r + u * TAIL_THREADS);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int c = 0; c < CG; ++c) acc[c] = fma(qv[c][u], wv[u], acc[c]);
+        }
+        {   // the last (partial) trip, guarded: still all loads in flight together
+            double wv[4], qv[CG][4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) wv[u] = (r + u * TAIL_THREADS < a.n) ? __ldcg(a.w + r + u * TAIL_THREADS) : 0.;
+#pragma unroll
+            for (int c = 0; c < CG; ++c)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) qv[c][u] = (r + u * TAIL_THREADS < a.n) ? __ldcg(q[c] + r + u * TAIL_THREADS) : 0.;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int c = 0; c < CG; ++c) acc[c] = fma(qv[c][u], wv[u], acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < CG; ++c) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+            if (lane == 0) s_red[c * TAIL_WARPS + warp] = acc[c];
+        }
+        __syncthreads();
+        if (warp < CG && col0 + warp < a.k) {
+            double t = s_red[warp * TAIL_WARPS + lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            if (lane == 0) {
+                const int j = col0 + warp;
+                if (second) {
+                    __stcg(a.h2 + j, t);
+                    __stcg(a.hfin + j, __ldcg(a.h1 + j) + t);
+                } else {
+                    __stcg(a.h1 + j, t);
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// w -= Q h over this CTA's rows (h = the k coefficients of this pass); returns the CTA's sum of squares of the new w (thread 0)
+__device__ __forceinline__ double tail3_sub_phase(const Tail3Args& a, const double* h, double* s_h, double* s_acc, bool second) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int j = threadIdx.x; j < a.k; j += TAIL_THREADS) s_h[j] = __ldcg(h + j);
+    __syncthreads();
+    const int n_rg = a.rows_per_cta >> 5;                 // 32-row groups of this CTA
+    const int n_cs = TAIL_WARPS / n_rg > 0 ? TAIL_WARPS / n_rg : 1;   // column splits
+    const int cta_row0 = blockIdx.x * a.rows_per_cta;
+    double sq_total = 0.;
+    for (int rg0 = 0; rg0 < n_rg; rg0 += TAIL_WARPS) {     // one trip unless a CTA owns more than 1024 rows
+        const int rg = rg0 + (n_cs > 1 ? warp % n_rg : warp), cs = (n_cs > 1) ? warp / n_rg : 0;
+        const bool busy = rg < n_rg && cs < n_cs;
+        const int row = cta_row0 + rg * 32 + lane;
+        double acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = 0.;
+        if (busy && row < a.n) {
+            const double* q = a.Q + row;
+            int j = cs;
+            for (; j + 7 * n_cs < a.k; j += 8 * n_cs) {
+                double qv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) qv[u] = __ldcg(q + (size_t)(j + u * n_cs) * a.ldq);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] = fma(qv[u], s_h[j + u * n_cs], acc[u]);
+            }
+            {
+                double qv[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) qv[u] = (j + u * n_cs < a.k) ? __ldcg(q + (size_t)(j + u * n_cs) * a.ldq) : 0.;
+#pragma unroll
+                for (int u = 0; u < 8; ++u) acc[u] = fma(qv[u], (j + u * n_cs < a.k) ? s_h[j + u * n_cs] : 0., acc[u]);
+            }
+        }
+        if (busy) s_acc[cs * a.rows_per_cta + (rg - rg0) * 32 + lane] =
+            ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+        __syncthreads();
+        const int rows_here = min(TAIL_WARPS, n_rg - rg0) * 32;
+        double sq = 0.;
+        if ((int)threadIdx.x < rows_here) {
+            double s = 0.;
+            for (int c = 0; c < n_cs; ++c) s += s_acc[c * a.rows_per_cta + threadIdx.x];
+            const int r = cta_row0 + rg0 * 32 + threadIdx.x;
+            if (r < a.n) {
+                const double v = __ldcg(a.w + r) - s;
+                __stcg(a.w + r, v);
+                sq = v * v;
+            }
+        }
+        if (second) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            __syncthreads();
+            if (lane == 0) s_acc[warp] = sq;
+            __syncthreads();
+            if (threadIdx.x == 0)
+                for (int k2 = 0; k2 < TAIL_WARPS; ++k2) sq_total += s_acc[k2];
+        }
+        __syncthreads();
+    }
+    return sq_total;   // meaningful in thread 0
+}
+
+__global__ void __launch_bounds__(TAIL_THREADS, 1) arnoldi_tail3_kernel(const Tail3Args a) {
+    extern __shared__ double s_mem[];
+    double* s_h = s_mem;                                   // [k rounded up to even]
+    double* s_acc = s_mem + ((a.k + 1) & ~1);              // [1024]
+    __shared__ double s_red[4 * TAIL_WARPS];
+    __shared__ double s_norm;
+    const unsigned G = gridDim.x;
+    const bool wide = a.k > 2 * (int)G;                    // four columns per group once two no longer give every CTA one trip
+    long long t_prev = 0;
+    int stamp_n = 0;
+    const bool stamping = a.dbg != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+#define TAIL3_STAMP()                                                    \
+    do {                                                                 \
+        if (stamping) {                                                  \
+            const long long t_now = clock64();                           \
+            if (stamp_n > 0) a.dbg[stamp_n - 1] += t_now - t_prev;       \
+            t_prev = t_now;                                              \
+            ++stamp_n;                                                   \
+        }                                                                \
+    } while (0)
+    TAIL3_STAMP();
+    if (wide) tail3_dot_phase<4>(a, s_red, false); else tail3_dot_phase<2>(a, s_red, false);
+    TAIL3_STAMP();
+    tail_grid_sync(a.bar, a.bar_base + G);
+    TAIL3_STAMP();
+    tail3_sub_phase(a, a.h1, s_h, s_acc, false);
+    TAIL3_STAMP();
+    tail_grid_sync(a.bar, a.bar_base + 2 * G);
+    TAIL3_STAMP();
+    if (wide) tail3_dot_phase<4>(a, s_red, true); else tail3_dot_phase<2>(a, s_red, true);
+    TAIL3_STAMP();
+    tail_grid_sync(a.bar, a.bar_base + 3 * G);
+    TAIL3_STAMP();
+    const double sq = tail3_sub_phase(a, a.h2, s_h, s_acc, true);
+    if (threadIdx.x == 0) __stcg(a.npart + blockIdx.x, sq);
+    TAIL3_STAMP();
+    tail_grid_sync(a.bar, a.bar_base + 4 * G);
+    TAIL3_STAMP();
+    if (threadIdx.x < 32) {
+        double t = 0.;
+        for (unsigned c = threadIdx.x; c < G; c += 32) t += __ldcg(a.npart + c);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+        if (threadIdx.x == 0) {
+            s_norm = sqrt(t);
+            if (blockIdx.x == 0) a.hfin[a.k] = s_norm;
+        }
+    }
+    __syncthreads();
+    const double nrm = s_norm;
+    const int cta_row0 = blockIdx.x * a.rows_per_cta;
+    for (int t = threadIdx.x; t < a.rows_per_cta; t += TAIL_THREADS) {
+        const int r = cta_row0 + t;
+        if (r < a.n) a.qnext[r] = __ldcg(a.w + r) / nrm;
+    }
+    if (blockIdx.x == gridDim.x - 1 && a.hhost) {          // the CTA with the fewest rows (often none) reports to the host
+        for (int j = threadIdx.x; j <= a.k; j += TAIL_THREADS) a.hhost[j] = j < a.k ? __ldcg(a.hfin + j) : nrm;
+    }
+    __syncthreads();
+    TAIL3_STAMP();
+    if (stamping) a.dbg[16] += 1;
+#undef TAIL3_STAMP
+}
+
 // norm = sqrt(sum of the per-CTA partials) (fixed order); q = w / norm; CTA 0 also stores the norm
 __global__ void __launch_bounds__(1024) norm_scale2_kernel(const double* __restrict__ w, int n, const double* __restrict__ norm_partial,
                                                             int n_part, double* __restrict__ norm_out, double* __restrict__ q) {
@@ -742,6 +998,7 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
     DevBuf<double> y_part, gather;
     DevBuf<unsigned> tickets;   // per 64-row block: splits finished (gemv_n_partial_kernel)
     int n_split = 1, cols_per_split = 0;
+    int pin_cols = 0;           // columns of every split kept in L2 across matvecs (gemv_n_partial_kernel)
     bool force_shard = false;   // one rank running the multi-rank code paths (MACHLINE_GMRES_SHARDED=1: the single-GPU test box)
 
     ml_status init() {
@@ -752,6 +1009,19 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
         n_split = std::max(1, std::min((want + row_blocks - 1) / row_blocks, std::max(1, N / 256)));
         cols_per_split = (N + n_split - 1) / n_split;
         n_split = (N + cols_per_split - 1) / cols_per_split;
+        {   // L2-resident slice of A: GEMV_L2_PIN_MB of the local matrix when it is larger than the cache
+            double pin_mb = GEMV_L2_PIN_MB_DEFAULT;
+            if (const char* e = std::getenv("MACHLINE_GEMV_L2_PIN_MB")) pin_mb = std::atof(e);
+            const double a_bytes = 8.0 * n_rows_pad * N, col_bytes = 8.0 * n_rows_pad * n_split;
+            pin_cols = 0;
+            if (pin_mb > 0 && a_bytes > 100e6) {
+                // eighths of a trip's loads: `base` whole eighths in every trip + one more in a fraction of the trips
+                const double frac8 = std::min(7.0, 8.0 * pin_mb * 1e6 / a_bytes);
+                const int base = (int)frac8;
+                pin_cols = 256 * base + std::min(255, (int)((frac8 - base) * 256));
+                (void)col_bytes;
+            }
+        }
         ML_CUDA(c, y_part.alloc((size_t)n_split * n_rows_pad));
         ML_CUDA(c, tickets.alloc(row_blocks));
         ML_CUDA(c, cudaMemsetAsync(tickets.p, 0, (size_t)row_blocks * sizeof(unsigned), c->stream));
@@ -772,7 +1042,7 @@ struct Sys {            // the (possibly row-sharded) system seen by the solvers
             ML_CUDA(c, cudaEventRecord(e0, c->stream));
         }
         gemv_n_partial_kernel<<<grid, GEMV_THREADS, 0, c->stream>>>(A, ld, n_rows_pad, N, cols_per_split, x, y_part.p, tickets.p,
-                                                                     n_rows, alpha_dev, alpha, dst_loc);
+                                                                     n_rows, alpha_dev, alpha, dst_loc, pin_cols);
         if (c->profile) {
             ML_CUDA(c, cudaEventRecord(e1, c->stream));
             c->gemv_ev.push_back(e0);
@@ -905,7 +1175,11 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
     const int n_row64 = ldq / 64, kpad = k_max + 4;
     // fused Arnoldi tail (one cooperative launch per iteration); MACHLINE_GMRES_TAIL=0 selects the five-kernel sequence
     bool fused_tail = !use_mgs;
-    if (const char* e = std::getenv("MACHLINE_GMRES_TAIL")) fused_tail = fused_tail && std::atoi(e) != 0;
+    int tail_version = 3;   // 3: column-owned dots + Hessenberg column stored to mapped host memory; 1: the first fused kernel
+    if (const char* e = std::getenv("MACHLINE_GMRES_TAIL")) {
+        fused_tail = fused_tail && std::atoi(e) != 0;
+        if (std::atoi(e) == 1) tail_version = 1;
+    }
     // the Gram-Schmidt kernels keep the k coefficients of a pass in shared memory: 200 KB opt-in for the fused tail (k_max <= 24.5k),
     // 64 KB for the five-kernel sequence (k_max <= 7.6k); a Krylov space beyond that is refused, not mis-launched
     constexpr size_t TAIL_SMEM_MAX = 200 * 1024, SUB_SMEM_MAX = 64 * 1024;
@@ -936,6 +1210,7 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         if (!(c->attr_mask & 1u)) {
             GM_CUDA(cudaFuncSetAttribute(orth_sub_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             GM_CUDA(cudaFuncSetAttribute(arnoldi_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX));
+            GM_CUDA(cudaFuncSetAttribute(arnoldi_tail3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM_MAX));
             c->attr_mask |= 1u;
         }
     }
@@ -952,10 +1227,20 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         if (c->h_pinned) cudaFreeHost(c->h_pinned);
         c->h_pinned = nullptr;
         c->h_pinned_n = 0;
-        GM_CUDA(cudaHostAlloc((void**)&c->h_pinned, (size_t)n_slots * hs * sizeof(double), cudaHostAllocDefault));
+        GM_CUDA(cudaHostAlloc((void**)&c->h_pinned, (size_t)n_slots * hs * sizeof(double), cudaHostAllocMapped));
         c->h_pinned_n = (size_t)n_slots * hs;
     }
     W.h_pinned = c->h_pinned;
+    DevBuf<long long> tail_dbg;
+    if (std::getenv("MACHLINE_TAIL_DEBUG")) {
+        GM_CUDA(tail_dbg.alloc(17));
+        GM_CUDA(cudaMemsetAsync(tail_dbg.p, 0, 17 * sizeof(long long), c->stream));
+    }
+    double* h_pinned_dev = nullptr;   // the device's address of the pinned slots (tail version 3 stores the Hessenberg column there)
+    if (fused_tail && tail_version == 3 && std::getenv("MACHLINE_GMRES_D2H_COPY") == nullptr && cudaHostGetDevicePointer((void**)&h_pinned_dev, c->h_pinned, 0) != cudaSuccess) {
+        cudaGetLastError();
+        h_pinned_dev = nullptr;
+    }
     for (int i = 0; i < n_slots; ++i)
         if (!c->slot_ev[i]) GM_CUDA(cudaEventCreateWithFlags(&c->slot_ev[i], cudaEventDisableTiming));
     W.ev = c->slot_ev;
@@ -980,6 +1265,26 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
             mgs_kernel<<<1, 1024, 0, c->stream>>>(W.Q.p, ldq, N, k, W.w.p, hfin);
             norm_scale_kernel<<<1, 1024, 0, c->stream>>>(W.w.p, N, hfin + k, W.Q.p + (size_t)k * ldq);
             c->launches += 2;
+        } else if (fused_tail && tail_version == 3) {
+            Tail3Args ta;
+            ta.Q = W.Q.p; ta.ldq = ldq; ta.n = N; ta.k = k;
+            ta.w = W.w.p; ta.h1 = h1; ta.h2 = h2; ta.hfin = hfin;
+            ta.hhost = h_pinned_dev ? h_pinned_dev + (size_t)slot * hs : nullptr;
+            ta.npart = W.npart.p; ta.qnext = W.Q.p + (size_t)k * ldq;
+            ta.bar = W.bar.p; ta.bar_base = bar_base; ta.rows_per_cta = tail_rows; ta.dbg = tail_dbg.p;
+            bar_base += 4u * (unsigned)tail_grid;
+            void* kargs[] = {(void*)&ta};
+            const size_t smem = (size_t)(((k + 1) & ~1) + 1024) * sizeof(double);
+            cudaError_t e = cudaLaunchCooperativeKernel((const void*)arnoldi_tail3_kernel, dim3(tail_grid), dim3(TAIL_THREADS), kargs, smem,
+                                                        c->stream);
+            if (e != cudaSuccess) return c->cuda_fail(e, "arnoldi_tail3_kernel");
+            c->launches += 1;
+            if (h_pinned_dev) {   // the column is already on its way to the host: only the event follows
+                e = cudaEventRecord(W.ev[slot], c->stream);
+                if (e != cudaSuccess) return c->cuda_fail(e, "gmres enqueue");
+                c->d2h_bytes += (long long)(k + 1) * sizeof(double);
+                return ML_OK;
+            }
         } else if (fused_tail) {
             // classical Gram-Schmidt with one re-orthogonalisation pass (same Krylov subspace and Hessenberg matrix as
             // the reference's modified Gram-Schmidt up to rounding), norm and normalisation: one cooperative launch
@@ -1109,6 +1414,15 @@ static ml_status gmres_device(Sys& S, const double* d_b, const double* d_scale, 
         GM_CUDA(cudaStreamSynchronize(c->stream));
     }
     cudaStreamSynchronize(c->stream);
+    if (tail_dbg.p) {
+        long long d[17];
+        if (cudaMemcpy(d, tail_dbg.p, sizeof(d), cudaMemcpyDeviceToHost) == cudaSuccess && d[16] > 0) {
+            static const char* names[] = {"dot1", "bar1", "sub1", "bar2", "dot2", "bar3", "sub2", "bar4", "norm+scale"};
+            std::fprintf(stderr, "[tail3] %lld launches, cycles per launch (CTA 0):", d[16]);
+            for (int i = 0; i < 9; ++i) std::fprintf(stderr, " %s %.0f", names[i], (double)d[i] / (double)d[16]);
+            std::fprintf(stderr, "\n");
+        }
+    }
     *total_iter_out = total_iter;
     W.release();
 #undef GM_CUDA
@@ -1195,8 +1509,14 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
         if (c->h_pinned) cudaFreeHost(c->h_pinned);
         c->h_pinned = nullptr;
         c->h_pinned_n = 0;
-        GS_CUDA(cudaHostAlloc((void**)&c->h_pinned, (size_t)n_slots * hs * sizeof(double), cudaHostAllocDefault));
+        GS_CUDA(cudaHostAlloc((void**)&c->h_pinned, (size_t)n_slots * hs * sizeof(double), cudaHostAllocMapped));
         c->h_pinned_n = (size_t)n_slots * hs;
+    }
+    double* h_pinned_dev = nullptr;   // the device's address of the pinned slots
+    if (std::getenv("MACHLINE_GMRES_D2H_COPY") == nullptr &&
+        cudaHostGetDevicePointer((void**)&h_pinned_dev, c->h_pinned, 0) != cudaSuccess) {
+        cudaGetLastError();
+        h_pinned_dev = nullptr;
     }
     for (int i = 0; i < n_slots; ++i)
         if (!c->slot_ev[i]) GS_CUDA(cudaEventCreateWithFlags(&c->slot_ev[i], cudaEventDisableTiming));
@@ -1233,6 +1553,7 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
         a.ticket = sync.p; a.ready = sync.p + 1; a.base = launches_done++;
         a.stages = tail_v2 ? 4u : 3u;
         a.err = err.p; a.rows_per_cta = rows_per_cta; a.dbg = want_dbg ? dbg.p : nullptr;
+        a.hhost = (tail_v2 && h_pinned_dev) ? h_pinned_dev + (size_t)slot * hs : nullptr;
         void* kargs[] = {(void*)&a};
         const size_t smem = (size_t)(2 * ((k + 3) & ~1) + SHT_MAXCH * SHT_THREADS + rows_per_cta) * sizeof(double);
         cudaError_t e = cudaLaunchCooperativeKernel(tail_v2 ? (const void*)arnoldi_tail_sharded2_kernel : (const void*)arnoldi_tail_sharded_kernel,
@@ -1246,7 +1567,8 @@ static ml_status gmres_sharded_device(Sys& S, const double* d_b, const double* d
                 c->comm_ev.push_back(e2);
             }
         }
-        e = cudaMemcpyAsync(c->h_pinned + (size_t)slot * hs, hfin, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+        e = a.hhost ? cudaSuccess   // version 2 stored the column into the mapped slot itself: no copy-engine operation between kernels
+                    : cudaMemcpyAsync(c->h_pinned + (size_t)slot * hs, hfin, (size_t)(k + 2) * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaEventRecord(c->slot_ev[slot], c->stream);
         if (e != cudaSuccess) return c->cuda_fail(e, "gmres enqueue");
         c->d2h_bytes += (long long)(k + 2) * sizeof(double);
