@@ -431,7 +431,7 @@ def main():
             best = info_lu.solve_ms if best is None else min(best, info_lu.solve_ms)
         dmma_peak = ctx.measure_dmma_peak()
         flops = 2.0 / 3.0 * float(N) ** 3
-        lu_probe = {"kernel": "blocked LU (lu_panel_coop_kernel + lu_trsm_kernel + lu_gemm2_kernel DMMA), whole solve",
+        lu_probe = {"kernel": "blocked LU (lu_panel_cl2_kernel / lu_panel_coop_kernel + lu_trsm_kernel + lu_gemm2_kernel DMMA), whole solve",
                     "bound": "tensor(fp64)", "n": int(N), "solve_ms": best, "achieved": flops / (best * 1e-3) / 1e12,
                     "peak": dmma_peak, "unit": "TFLOP/s", "frac": flops / (best * 1e-3) / 1e12 / dmma_peak,
                     "peak_source": "measured live: register-resident mma.sync.m8n8k4.f64 loop (ml_measure_dmma_peak)",

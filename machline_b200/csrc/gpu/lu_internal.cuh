@@ -16,6 +16,7 @@ struct LuPanelWork {
     unsigned bar_base = 0;
     bool all_coop = true;   // every panel so far went through the cooperative kernel (which maintains perm)
     int gmax = 0;
+    long long* dbg = nullptr;   // MACHLINE_LU_PANEL_DBG: phase stamps of lu_panel_cl2_kernel
     ml_status init(Ctx* c);
     void release();
 };

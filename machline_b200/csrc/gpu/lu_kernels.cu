@@ -403,6 +403,266 @@ __global__ void __launch_bounds__(T, T == 128 ? 5 : 1) lu_panel_coop_kernel(cons
     }
 }
 
+// ---- cluster panel, second generation ---------------------------------------------------------------------
+// Same factorisation, same arithmetic per element (a(i,c) = fma(-l, a(j,c), a(i,c)) for the panel's columns j in ascending order,
+// l = a(i,j) * (1/a(j,j)), the reference's pivot rule), organised for latency: lu_panel_coop_kernel<.., CL> spends ~8400 cycles per
+// column whatever the panel's height (ncu: 645 warp instructions per warp and column, nine block barriers, 32 % of the stall
+// samples in the cluster barrier), and the panel is the critical path of the factorisation below N ~ 15k.
+//   * thread = row: a CTA holds up to 512 rows, thread t owns row t (its scale vv and permutation entry live in registers), so
+//     the multiplier, the update and the next column's candidate of a row never leave the thread: no s_l array, no barrier
+//     between them;
+//   * delayed update: columns are grouped in blocks of LUP2_IB = 8.  A column step updates only the (<= 7) columns left in its
+//     block; the columns right of the block receive the block's eight rank-1 updates at the block's end in one pass (each
+//     element read and written once instead of eight times, eight dependent FMAs in the order of the column steps: bit-identical
+//     values).  The pivot rows of a block arrive stale in those columns; every CTA rebuilds them (redundantly, <= 7 FMAs per
+//     column: s_U) from the pulled row and the row's own multipliers;
+//   * pull, not push: a CTA parks its candidate row (and the CTA that holds position j parks row j) in a slot of its OWN shared
+//     memory, double-buffered by column parity; only (value, position) -- 12 bytes -- go to the peers before the cluster
+//     barrier.  After it every CTA reads the winner's row from the winner's slot through distributed shared memory (one round
+//     trip) instead of every CTA storing 528 bytes into 16 peers per column.  (Pulling the 12 bytes as well makes the barrier
+//     cheaper, 1200 -> 880 cycles with no remote store to release, but the second dependent round trip costs more: r5e.)
+//   * arg max by three REDUX (lup2_warp_argmax); both reductions (CTA candidate, cluster pivot) are finished redundantly by
+//     every warp: one block barrier each.
+// Block barriers per column: three (+ one with an interchange inside the CTA, + one per block end); one cluster barrier.
+// OVF: rows beyond the shared-memory capacity of a CTA stay in global memory (touched by their owner thread and, for an
+// interchange, by the CTA's column threads: L2 loads / stores ordered by the block barriers).
+constexpr int LUP2_IB = 8;
+constexpr int LUP2_T = 512;     // most threads of a CTA = the most rows a CTA can own
+constexpr int LUP2_CAP = 416;   // rows of a CTA held in shared memory: 64 columns x 417 x 8 B = 213.5 KB
+
+// arg max of (v, position) over a warp with the reference's tie rule (largest v, ties -> LAST position), three REDUX
+// instead of a five-step shuffle tree on 96-bit items.  key = bit pattern of v (v >= +0: ordered like the values), idx >= 0;
+// "no candidate" = (0, -1), which loses against every real candidate (a real v = 0 has idx >= 0 > -1).
+__device__ __forceinline__ void lup2_warp_argmax(unsigned long long& key, int& idx) {
+    const unsigned hi = (unsigned)(key >> 32), lo = (unsigned)key;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+    idx = __reduce_max_sync(0xffffffffu, (hi == mh && lo == ml) ? idx : -1);
+    key = ((unsigned long long)mh << 32) | ml;
+}
+// (Tried, r5e: one REDUX on the high word + ballot + two shuffles when a single lane holds the maximum -- not faster.)
+
+template <bool OVF>
+__global__ void __launch_bounds__(LUP2_T, 1) lu_panel_cl2_kernel(const LuPanelArgs a) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    extern __shared__ __align__(16) double lup_smem[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int nb = a.k1 - a.k0;
+    const int r0 = a.k0 + bid * a.rpc;                 // first row position of this CTA
+    const int nr = min(a.rpc, a.n - r0);               // > 0 by grid sizing; <= blockDim.x
+    const int cap = OVF ? LUP2_CAP : a.rpc;
+    const int S = cap | 1;                             // odd column stride: gathers of a row are conflict-free
+    double* const sP = lup_smem;                       // [LU_NB][S]
+    double* const s_U = sP + LU_NB * S;                // [LUP2_IB][LU_NB]  pivot rows of the current block, delayed columns
+    double* const s_piv = s_U + LUP2_IB * LU_NB;       // [LUP_ROW] pivot row as pulled (+ its perm entry, 1 / pivot)
+    double* const s_oldj = s_piv + LUP_ROW;            // [LUP_ROW] row j as pulled (+ perm, vv)
+    double* const st_cand = s_oldj + LUP_ROW;          // [2][LUP_ROW] this CTA's candidate row, read by the peers
+    double* const st_rowj = st_cand + 2 * LUP_ROW;     // [2][LUP_ROW] row j (+ perm, vv), read by the CTA that holds the pivot
+    unsigned long long* const cl_k = reinterpret_cast<unsigned long long*>(st_rowj + 2 * LUP_ROW);   // [2][LUP_CL_MAX] candidate keys of every CTA (written by the peers)
+    unsigned long long* const s_rk = cl_k + 2 * LUP_CL_MAX;   // [16] warp partials
+    int* const cl_i = reinterpret_cast<int*>(s_rk + 16);      // [2][LUP_CL_MAX]
+    int* const s_ri = cl_i + 2 * LUP_CL_MAX;           // [16]
+    double* const gA = a.A + (size_t)a.k0 * a.ld + r0; // this CTA's rows of the panel in global memory
+    auto ld_el = [&](int r, int c) -> double {
+        if (OVF && r >= cap) return __ldcg(gA + (size_t)c * a.ld + r);
+        return sP[c * S + r];
+    };
+    auto st_el = [&](int r, int c, double v) {
+        if (OVF && r >= cap) __stcg(gA + (size_t)c * a.ld + r, v);
+        else sP[c * S + r] = v;
+    };
+    // MACHLINE_LU_PANEL_DBG: cycles per phase of a column step, summed by thread 0 of CTA 0 (development aid)
+    long long* const dbg = reinterpret_cast<long long*>(a.cand_row);
+    const bool stamping = dbg != nullptr && bid == 0 && tid == 0;
+    long long t_prev = 0;
+    __shared__ long long s_dbg[8];
+    if (stamping)
+        for (int k = 0; k < 8; ++k) s_dbg[k] = 0;
+#define LUP2_STAMP(slot)                                     \
+    do {                                                     \
+        if (stamping) {                                      \
+            const long long t_now = clock64();               \
+            s_dbg[slot] += t_now - t_prev;                   \
+            t_prev = t_now;                                  \
+        }                                                    \
+    } while (0)
+    const int nrb = (min(nr, cap) + 31) >> 5;
+    for (int item = warp; item < nb * nrb; item += nwarps) {
+        const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
+        if (r < nr && r < cap) sP[c * S + r] = __ldcg(a.A + (size_t)(a.k0 + c) * a.ld + r0 + r);
+    }
+    const bool has_row = tid < nr;
+    double vv_r = has_row ? __ldcg(a.vv + r0 + tid) : 0.;
+    int perm_r = has_row ? __ldcg(a.perm + r0 + tid) : 0;
+    cluster.sync();   // the panel is in shared memory; every CTA of the cluster is running before the first remote access
+    if (stamping) t_prev = clock64();
+
+    for (int jj = 0; jj < nb; ++jj) {
+        const int j = a.k0 + jj, par = jj & 1;
+        const int blk0 = jj & ~(LUP2_IB - 1), blkend = min(blk0 + LUP2_IB, nb);
+        // ---- this CTA's candidate for column j (largest vv*|a|, ties -> last position, linalg.f90:242) -------------
+        unsigned long long key = 0ull;
+        int bi = -1;
+        if (has_row && r0 + tid >= j) {
+            const double v = vv_r * fabs(ld_el(tid, jj));
+            if (v > -1.) { key = (unsigned long long)__double_as_longlong(v); bi = r0 + tid; }   // a NaN is never a candidate
+        }
+        lup2_warp_argmax(key, bi);
+        if (lane == 0) { s_rk[warp] = key; s_ri[warp] = bi; }
+        __syncthreads();
+        key = lane < nwarps ? s_rk[lane] : 0ull;
+        bi = lane < nwarps ? s_ri[lane] : -1;
+        lup2_warp_argmax(key, bi);                         // every warp finishes the reduction: no second barrier
+        LUP2_STAMP(0);
+        // ---- park the candidate row and row j in this CTA's slots; (value, position) to every CTA of the cluster ----
+        const bool own_j = (j >= r0 && j < r0 + nr);
+        const int ci = bi >= 0 ? bi : (own_j ? j : -1);    // a column of NaNs: row j stands in (the pivot stays on the diagonal)
+        if (ci >= 0) {
+            if (tid < nb) st_cand[par * LUP_ROW + tid] = ld_el(ci - r0, tid);
+            if (tid == ci - r0) st_cand[par * LUP_ROW + LU_NB] = (double)perm_r;
+            // 1 / pivot of this candidate, under the cluster barrier's own latency instead of after it
+            if (tid == LU_NB + 1) st_cand[par * LUP_ROW + LU_NB + 1] = 1.0 / ld_el(ci - r0, jj);
+        }
+        if (own_j) {
+            if (tid < nb) st_rowj[par * LUP_ROW + tid] = ld_el(j - r0, tid);
+            if (tid == j - r0) {
+                st_rowj[par * LUP_ROW + LU_NB] = (double)perm_r;
+                st_rowj[par * LUP_ROW + LU_NB + 1] = vv_r;
+            }
+        }
+        if (tid < G) {
+            cluster.map_shared_rank(cl_k, tid)[par * LUP_CL_MAX + bid] = key;
+            cluster.map_shared_rank(cl_i, tid)[par * LUP_CL_MAX + bid] = bi;
+        }
+        LUP2_STAMP(1);
+        cluster.sync();
+        LUP2_STAMP(2);
+        // ---- global pivot (every warp, redundantly), then the winner's row from the winner's slot -------------------
+        key = lane < G ? cl_k[par * LUP_CL_MAX + lane] : 0ull;
+        bi = lane < G ? cl_i[par * LUP_CL_MAX + lane] : -1;
+        lup2_warp_argmax(key, bi);
+        const int p = bi < 0 ? j : bi;   // a column of NaNs: keep the diagonal (the reference's imax stays at its previous value)
+        const int w = (p - a.k0) / a.rpc, wj = (j - a.k0) / a.rpc;
+        const bool own_p = (p >= r0 && p < r0 + nr);
+        double pulled = 0.;
+        if (tid < nb || tid == LU_NB || tid == LU_NB + 1) {
+            pulled = cluster.map_shared_rank(st_cand, w)[par * LUP_ROW + tid];
+            s_piv[tid] = pulled;
+        }
+        if (p != j && own_p && (tid < nb || tid == LU_NB || tid == LU_NB + 1))
+            s_oldj[tid] = cluster.map_shared_rank(st_rowj, wj)[par * LUP_ROW + tid];
+        if (bid == 0 && tid == 0) a.piv[j] = p;
+        __syncthreads();
+        LUP2_STAMP(3);
+        // the pivot row in the delayed columns: it has seen the blocks before this one, not this block's columns (< j) yet
+        if (tid >= blkend && tid < nb) {
+            double u = pulled;
+            for (int b = 0; b < jj - blk0; ++b) u = fma(-s_piv[blk0 + b], s_U[b * LU_NB + tid], u);
+            s_U[(jj - blk0) * LU_NB + tid] = u;
+        }
+        if (p != j && (own_j || own_p)) {   // whole-row interchange inside the panel (linalg.f90:254-263)
+            if (own_j) {
+                if (tid < nb) st_el(j - r0, tid, s_piv[tid]);
+                if (tid == j - r0) perm_r = (int)s_piv[LU_NB];
+            }
+            if (own_p) {
+                if (tid < nb) st_el(p - r0, tid, s_oldj[tid]);
+                if (tid == p - r0) {
+                    perm_r = (int)s_oldj[LU_NB];
+                    vv_r = s_oldj[LU_NB + 1];
+                }
+            }
+            __syncthreads();
+        }
+        LUP2_STAMP(4);
+        // ---- eliminate column j from this thread's row: the multiplier and the columns left in the block -------------
+        const double inv = s_piv[LU_NB + 1];   // 1.0 / s_piv[jj], computed by the pivot's CTA
+        if (has_row && r0 + tid > j) {
+            // loads first, then the FMAs, then the stores: written as a loop of load / fma / store the compiler has to keep the
+            // shared-memory accesses in order (it cannot tell sP from s_piv) and the <= 7 columns go one after the other
+            const int ncol = blkend - jj - 1;
+            double v[LUP2_IB - 1], u[LUP2_IB - 1];
+            const double e = ld_el(tid, jj);
+#pragma unroll
+            for (int k = 0; k < LUP2_IB - 1; ++k) {
+                if (k < ncol) {
+                    v[k] = ld_el(tid, jj + 1 + k);
+                    u[k] = s_piv[jj + 1 + k];
+                }
+            }
+            const double l = e * inv;
+            st_el(tid, jj, l);
+            const double ml = -l;
+#pragma unroll
+            for (int k = 0; k < LUP2_IB - 1; ++k)
+                if (k < ncol) st_el(tid, jj + 1 + k, fma(ml, u[k], v[k]));
+        }
+        LUP2_STAMP(5);
+        // ---- end of a block: its eight updates of the columns to its right, in the order of the column steps ---------
+        if (jj + 1 == blkend && blkend < nb) {   // blkend < nb: the block is complete (LUP2_IB columns)
+            __syncthreads();                     // s_U is complete
+            if (tid >= blkend && tid < nb) {     // the block's pivot rows take their final values in the delayed columns
+#pragma unroll
+                for (int b = 0; b < LUP2_IB; ++b) {
+                    const int pos = a.k0 + blk0 + b;
+                    if (pos >= r0 && pos < r0 + nr) st_el(pos - r0, tid, s_U[b * LU_NB + tid]);
+                }
+            }
+            if (has_row && r0 + tid >= a.k0 + blkend) {
+                double ml[LUP2_IB];
+#pragma unroll
+                for (int b = 0; b < LUP2_IB; ++b) ml[b] = -ld_el(tid, blk0 + b);
+                int c = blkend;
+                for (; c + 4 <= nb; c += 4) {
+                    double v0 = ld_el(tid, c), v1 = ld_el(tid, c + 1), v2 = ld_el(tid, c + 2), v3 = ld_el(tid, c + 3);
+#pragma unroll
+                    for (int b = 0; b < LUP2_IB; ++b) {
+                        const double2 u01 = *reinterpret_cast<const double2*>(s_U + b * LU_NB + c);
+                        const double2 u23 = *reinterpret_cast<const double2*>(s_U + b * LU_NB + c + 2);
+                        v0 = fma(ml[b], u01.x, v0);
+                        v1 = fma(ml[b], u01.y, v1);
+                        v2 = fma(ml[b], u23.x, v2);
+                        v3 = fma(ml[b], u23.y, v3);
+                    }
+                    st_el(tid, c, v0);
+                    st_el(tid, c + 1, v1);
+                    st_el(tid, c + 2, v2);
+                    st_el(tid, c + 3, v3);
+                }
+                for (; c < nb; ++c) {
+                    double v = ld_el(tid, c);
+#pragma unroll
+                    for (int b = 0; b < LUP2_IB; ++b) v = fma(ml[b], s_U[b * LU_NB + c], v);
+                    st_el(tid, c, v);
+                }
+            }
+            LUP2_STAMP(6);
+        }
+    }
+#undef LUP2_STAMP
+    if (stamping) {
+        for (int k = 0; k < 7; ++k) dbg[k] += s_dbg[k];
+        dbg[7] += nb;
+    }
+    cluster.sync();   // no CTA leaves while a peer may still read its slots
+    for (int item = warp; item < nb * nrb; item += nwarps) {
+        const int c = item / nrb, r = ((item - c * nrb) << 5) + lane;
+        if (r < nr && r < cap) a.A[(size_t)(a.k0 + c) * a.ld + r0 + r] = sP[c * S + r];
+    }
+    if (has_row) {
+        a.vv[r0 + tid] = vv_r;
+        a.perm[r0 + tid] = perm_r;
+    }
+}
+
+static size_t lu_panel2_smem(int rpc) {
+    const int cap = rpc <= LUP2_CAP ? rpc : LUP2_CAP;
+    return (size_t)(LU_NB * (cap | 1) + LUP2_IB * LU_NB + 6 * LUP_ROW + 2 * LUP_CL_MAX + 16) * sizeof(double) +
+           (size_t)(2 * LUP_CL_MAX + 16) * sizeof(int);
+}
+
 // the per-column fallback keeps only the interchanges: compose them (sequentially) into the row permutation
 __global__ void lu_perm_from_piv_kernel(const int* __restrict__ piv, int n, int* __restrict__ perm) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -434,35 +694,60 @@ __global__ void __launch_bounds__(256) lu_laswp_kernel(double* __restrict__ A, i
     }
 }
 
-// U12 = L11^{-1} A12 : one thread per column right of the panel, L11 (unit lower, 64 x 64) in shared memory.
-// Only full panels reach this kernel (a short last panel has nothing to its right).  Both loops are unrolled so the
-// column lives in registers; the column-oriented order (x[r] -= L[r][k] x[k] for all r > k) exposes 63..1 independent
-// FMAs per step, and every L[r][k] is a shared-memory broadcast.
-__global__ void __launch_bounds__(64) lu_trsm_kernel(const double* __restrict__ L, int ldl, double* __restrict__ X, int ldx, int ncols) {
+// U12 = L11^{-1} A12, L11 (unit lower, 64 x 64) in shared memory.  Only full panels reach this kernel (a short last panel has
+// nothing to its right).  Column-oriented substitution, x[r] = fma(-L[r][k], x[k], x[r]) for k ascending: per element the
+// reference's order.  A warp carries TRSM_CW columns at once, lane = rows (lane, lane + 32) of each: step k broadcasts x[k]
+// from its owner lane by shuffle, every lane updates its two rows of every column.  (The first version ran one thread per
+// column with the whole column in registers: 2016 dependent shared-memory broadcasts per thread on two warps per SM, 19 us
+// per call whatever the width, and three calls per pair of panels sit on the critical path of the factorisation.)
+constexpr int TRSM_CW = 4;
+constexpr int TRSM_THREADS = 256;
+constexpr int TRSM_COLS_PER_CTA = TRSM_THREADS / 32 * TRSM_CW;
+__global__ void __launch_bounds__(TRSM_THREADS) lu_trsm_kernel(const double* __restrict__ L, int ldl, double* __restrict__ X, int ldx, int ncols) {
     // L: the 64 x 64 diagonal block (unit lower part used); X: 64 x ncols right-hand sides, overwritten by L^{-1} X
-    __shared__ double sL[LU_NB * LU_NB];   // sL[k * LU_NB + r] = L(r, k): column-major, conflict-free fill
-    for (int t = threadIdx.x; t < LU_NB * LU_NB; t += 64) {
+    __shared__ double sL[LU_NB * LU_NB];   // sL[k * LU_NB + r] = L(r, k): column-major, conflict-free fill and reads
+    for (int t = threadIdx.x; t < LU_NB * LU_NB; t += TRSM_THREADS) {
         const int r = t % LU_NB, k = t / LU_NB;
         sL[t] = L[r + (size_t)k * ldl];
     }
     __syncthreads();
-    const int c = blockIdx.x * 64 + threadIdx.x;
-    if (c >= ncols) return;
-    double* col = X + (size_t)c * ldx;
-    double x[LU_NB];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int c0 = (blockIdx.x * (TRSM_THREADS / 32) + warp) * TRSM_CW;
+    if (c0 >= ncols) return;
+    double x0[TRSM_CW], x1[TRSM_CW];
 #pragma unroll
-    for (int r = 0; r < LU_NB; r += 2) {
-        const double2 v = *reinterpret_cast<const double2*>(col + r);
-        x[r] = v.x;
-        x[r + 1] = v.y;
+    for (int c = 0; c < TRSM_CW; ++c) {
+        const double* col = X + (size_t)min(c0 + c, ncols - 1) * ldx;   // a short last group repeats its last column (not stored)
+        x0[c] = col[lane];
+        x1[c] = col[lane + 32];
+    }
+#pragma unroll 4
+    for (int k = 0; k < 32; ++k) {          // x[k] lives in x0 of lane k
+        const double l0 = -sL[k * LU_NB + lane], l1 = -sL[k * LU_NB + lane + 32];
+#pragma unroll
+        for (int c = 0; c < TRSM_CW; ++c) {
+            const double xk = __shfl_sync(0xffffffffu, x0[c], k);
+            if (lane > k) x0[c] = fma(l0, xk, x0[c]);
+            x1[c] = fma(l1, xk, x1[c]);
+        }
+    }
+#pragma unroll 4
+    for (int k = 32; k < LU_NB - 1; ++k) {  // x[k] lives in x1 of lane k - 32
+        const double l1 = -sL[k * LU_NB + lane + 32];
+#pragma unroll
+        for (int c = 0; c < TRSM_CW; ++c) {
+            const double xk = __shfl_sync(0xffffffffu, x1[c], k - 32);
+            if (lane + 32 > k) x1[c] = fma(l1, xk, x1[c]);
+        }
     }
 #pragma unroll
-    for (int k = 0; k < LU_NB - 1; ++k) {
-#pragma unroll
-        for (int r = k + 1; r < LU_NB; ++r) x[r] = fma(-sL[k * LU_NB + r], x[k], x[r]);
+    for (int c = 0; c < TRSM_CW; ++c) {
+        if (c0 + c < ncols) {
+            double* col = X + (size_t)(c0 + c) * ldx;
+            col[lane] = x0[c];
+            col[lane + 32] = x1[c];
+        }
     }
-#pragma unroll
-    for (int r = 0; r < LU_NB; r += 2) *reinterpret_cast<double2*>(col + r) = make_double2(x[r], x[r + 1]);
 }
 
 // ---- trailing update on the FP64 tensor cores ---------------------------------------------------------
@@ -711,6 +996,29 @@ __global__ void lu_permute_kernel(const double* __restrict__ b, const int* __res
     if (i < n) x[i] = b[perm[i]];
 }
 
+// sum_c a[c * ld] * sx[c] in the order c = 0, 1, ... (one FMA chain, as before), with a full 64-column strip requested
+// together: the entries come from HBM (the factors are larger than L2), and a rolled loop kept only a few of them in flight
+// (~10 us of exposed latency per step, 2 N / 64 steps per solve).
+// The whole strip of a row is requested from HBM at once (prefetch to L2: no registers held), BEFORE the block barrier that
+// precedes lu_strip_dot: ptxas keeps a window of only ~10 loads of the FMA chain in flight whatever the source says (and sinks
+// prefetches into the chain when they are issued next to it); after the barrier the loads find their lines in L2.
+__device__ __forceinline__ void lu_strip_prefetch(const double* __restrict__ a, int ld, int nb) {
+    if (nb == LU_NB) {
+#pragma unroll
+        for (int c = 0; c < LU_NB; ++c) asm volatile("prefetch.global.L2 [%0];" ::"l"(a + (size_t)c * ld));
+    }
+}
+__device__ __forceinline__ double lu_strip_dot(const double* __restrict__ a, int ld, int nb, const double* __restrict__ sx) {
+    double acc = 0.;
+    if (nb == LU_NB) {
+#pragma unroll
+        for (int c = 0; c < LU_NB; ++c) acc = fma(__ldg(a + (size_t)c * ld), sx[c], acc);
+    } else {
+        for (int c = 0; c < nb; ++c) acc = fma(a[(size_t)c * ld], sx[c], acc);
+    }
+    return acc;
+}
+
 // One step of the blocked forward substitution in ONE launch: x[k0..k1) is final; every row below gets
 // x[r] -= L(r, k0..k1) . x[k0..k1), and the CTA that holds the next diagonal block solves it straight away (unit lower
 // triangular, one warp, column order), so a step costs one launch instead of two.  Same operation order per element
@@ -721,33 +1029,42 @@ __global__ void __launch_bounds__(256) lu_fwd_step_kernel(const double* __restri
     __shared__ double sL[LU_NB * LU_NB];
     const int nb = k1 - k0, tid = threadIdx.x;
     if (tid < nb) sx[tid] = x[k0 + tid];
-    __syncthreads();
-    const int r = k1 + blockIdx.x * 256 + tid;
-    double xr = 0.;
-    if (r < n) {
-        double acc = 0.;
-        for (int c = 0; c < nb; ++c) acc = fma(A[r + (size_t)(k0 + c) * ld], sx[c], acc);
-        xr = x[r] - acc;
-        if (blockIdx.x != 0 || tid >= LU_NB) x[r] = xr;
-    }
-    if (blockIdx.x != 0) return;
     const int nb2 = min(LU_NB, n - k1);
-    if (tid < nb2) sy[tid] = xr;
-    for (int t = tid; t < nb2 * nb2; t += 256) {
-        const int rr = t % nb2, cc = t / nb2;
-        sL[cc * LU_NB + rr] = A[(k1 + rr) + (size_t)(k1 + cc) * ld];
-    }
-    __syncthreads();
-    if (tid < 32) {
-        for (int c = 0; c < nb2; ++c) {
-            const double xc = sy[c];
-            if (tid > c && tid < nb2) sy[tid] = fma(-sL[c * LU_NB + tid], xc, sy[tid]);
-            if (tid + 32 > c && tid + 32 < nb2) sy[tid + 32] = fma(-sL[c * LU_NB + tid + 32], xc, sy[tid + 32]);
-            __syncwarp();
+    if (blockIdx.x == 0) {   // the next diagonal block does not depend on x: in flight together with the strip
+        for (int t = tid; t < nb2 * nb2; t += 256) {
+            const int rr = t % nb2, cc = t / nb2;
+            sL[cc * LU_NB + rr] = A[(k1 + rr) + (size_t)(k1 + cc) * ld];
         }
     }
+    const int r = k1 + blockIdx.x * 256 + tid;
+    if (r < n) lu_strip_prefetch(A + r + (size_t)k0 * ld, ld, nb);
     __syncthreads();
-    if (tid < nb2) x[k1 + tid] = sy[tid];
+    double xr = 0.;
+    if (r < n) xr = x[r] - lu_strip_dot(A + r + (size_t)k0 * ld, ld, nb, sx);
+    if (r < n && (blockIdx.x != 0 || tid >= LU_NB)) x[r] = xr;
+    if (blockIdx.x != 0) return;
+    if (tid < nb2) sy[tid] = xr;
+    __syncthreads();
+    if (tid < 32) {
+        // one warp, rows (lane, lane + 32) in registers, x[c] broadcast by shuffle: same order per row as the column loop over
+        // shared memory it replaces (a shared-memory round trip and two warp barriers per column)
+        const int lane = tid;
+        double y0 = lane < nb2 ? sy[lane] : 0., y1 = lane + 32 < nb2 ? sy[lane + 32] : 0.;
+        const int n_lo = min(32, nb2);
+#pragma unroll 4
+        for (int c = 0; c < n_lo; ++c) {
+            const double xc = __shfl_sync(0xffffffffu, y0, c);
+            if (lane > c && lane < nb2) y0 = fma(-sL[c * LU_NB + lane], xc, y0);
+            if (lane + 32 < nb2) y1 = fma(-sL[c * LU_NB + lane + 32], xc, y1);
+        }
+#pragma unroll 4
+        for (int c = 32; c < nb2; ++c) {
+            const double xc = __shfl_sync(0xffffffffu, y1, c - 32);
+            if (lane + 32 > c && lane + 32 < nb2) y1 = fma(-sL[c * LU_NB + lane + 32], xc, y1);
+        }
+        if (lane < nb2) x[k1 + lane] = y0;
+        if (lane + 32 < nb2) x[k1 + lane + 32] = y1;
+    }
 }
 
 // One step of the blocked back substitution: x[k0..k1) is final; rows above get x[r] -= U(r, k0..k1) . x[k0..k1), and the
@@ -758,36 +1075,43 @@ __global__ void __launch_bounds__(256) lu_bwd_step_kernel(const double* __restri
     __shared__ double sU[LU_NB * LU_NB];
     const int nb = k1 - k0, tid = threadIdx.x;
     if (tid < nb) sx[tid] = x[k0 + tid];
-    __syncthreads();
-    // CTA 0 covers rows [k0-256, k0) with its first 64 threads on the block just above the solved one
-    const int r = k0 - 1 - (blockIdx.x * 256 + tid);
-    double xr = 0.;
-    if (r >= 0) {
-        double acc = 0.;
-        for (int c = 0; c < nb; ++c) acc = fma(A[r + (size_t)(k0 + c) * ld], sx[c], acc);
-        xr = x[r] - acc;
-        if (blockIdx.x != 0 || tid >= LU_NB) x[r] = xr;
-    }
-    if (blockIdx.x != 0) return;
     const int b0 = k0 - LU_NB;   // k0 is a multiple of LU_NB and > 0
-    if (tid < LU_NB) sy[LU_NB - 1 - tid] = xr;   // thread t holds row k0-1-t
-    for (int t = tid; t < LU_NB * LU_NB; t += 256) {
-        const int rr = t % LU_NB, cc = t / LU_NB;
-        sU[cc * LU_NB + rr] = A[(b0 + rr) + (size_t)(b0 + cc) * ld];
-    }
-    __syncthreads();
-    if (tid < 32) {
-        for (int c = LU_NB - 1; c >= 0; --c) {
-            if (tid == (c & 31)) sy[c] = sy[c] / sU[c * LU_NB + c];
-            __syncwarp();
-            const double xc = sy[c];
-            if (tid < c) sy[tid] = fma(-sU[c * LU_NB + tid], xc, sy[tid]);
-            if (tid + 32 < c) sy[tid + 32] = fma(-sU[c * LU_NB + tid + 32], xc, sy[tid + 32]);
-            __syncwarp();
+    if (blockIdx.x == 0) {       // the diagonal block just above does not depend on x: in flight together with the strip
+        for (int t = tid; t < LU_NB * LU_NB; t += 256) {
+            const int rr = t % LU_NB, cc = t / LU_NB;
+            sU[cc * LU_NB + rr] = A[(b0 + rr) + (size_t)(b0 + cc) * ld];
         }
     }
+    // CTA 0 covers rows [k0-256, k0) with its first 64 threads on the block just above the solved one
+    const int r = k0 - 1 - (blockIdx.x * 256 + tid);
+    if (r >= 0) lu_strip_prefetch(A + r + (size_t)k0 * ld, ld, nb);
     __syncthreads();
-    if (tid < LU_NB) x[b0 + tid] = sy[tid];
+    double xr = 0.;
+    if (r >= 0) xr = x[r] - lu_strip_dot(A + r + (size_t)k0 * ld, ld, nb, sx);
+    if (r >= 0 && (blockIdx.x != 0 || tid >= LU_NB)) x[r] = xr;
+    if (blockIdx.x != 0) return;
+    if (tid < LU_NB) sy[LU_NB - 1 - tid] = xr;   // thread t holds row k0-1-t
+    __syncthreads();
+    if (tid < 32) {
+        // one warp, rows (lane, lane + 32) in registers, x[c] = y[c] / U(c, c) broadcast by shuffle (see lu_fwd_step_kernel)
+        const int lane = tid;
+        double y0 = sy[lane], y1 = sy[lane + 32];
+#pragma unroll 4
+        for (int c = LU_NB - 1; c >= 32; --c) {
+            if (lane == c - 32) y1 = y1 / sU[c * LU_NB + c];
+            const double xc = __shfl_sync(0xffffffffu, y1, c - 32);
+            y0 = fma(-sU[c * LU_NB + lane], xc, y0);
+            if (lane + 32 < c) y1 = fma(-sU[c * LU_NB + lane + 32], xc, y1);
+        }
+#pragma unroll 4
+        for (int c = 31; c >= 0; --c) {
+            if (lane == c) y0 = y0 / sU[c * LU_NB + c];
+            const double xc = __shfl_sync(0xffffffffu, y0, c);
+            if (lane < c) y0 = fma(-sU[c * LU_NB + lane], xc, y0);
+        }
+        x[b0 + lane] = y0;
+        x[b0 + lane + 32] = y1;
+    }
 }
 
 // C (M x Nc) -= L (M x 64) * U (64 x Nc) on the FP64 tensor cores; all leading dimensions even, pointers 16-byte aligned
@@ -832,9 +1156,24 @@ ml_status LuPanelWork::init(Ctx* c) {
     ML_CUDA(c, cudaMemsetAsync(pbar.p, 0, sizeof(unsigned), c->stream));
     bar_base = 0;
     all_coop = true;
+    if (getenv("MACHLINE_LU_PANEL_DBG")) {
+        ML_CUDA(c, cudaMalloc(&dbg, 8 * sizeof(long long)));
+        ML_CUDA(c, cudaMemset(dbg, 0, 8 * sizeof(long long)));
+    }
     return ML_OK;
 }
 void LuPanelWork::release() {
+    if (dbg) {   // cycles per phase of the cluster panel kernel, per column (thread 0 of CTA 0)
+        long long h[8];
+        cudaDeviceSynchronize();
+        cudaMemcpy(h, dbg, sizeof(h), cudaMemcpyDeviceToHost);
+        const double nc = h[7] > 0 ? (double)h[7] : 1.;
+        fprintf(stderr, "lu_panel_cl2 cycles per column over %lld columns: candidate %.0f | park+push %.0f | cluster barrier %.0f | pivot+pull %.0f | "
+                        "interchange %.0f | eliminate %.0f | block update %.0f\n",
+                h[7], h[0] / nc, h[1] / nc, h[2] / nc, h[3] / nc, h[4] / nc, h[5] / nc, h[6] / nc);
+        cudaFree(dbg);
+        dbg = nullptr;
+    }
     pscr.release();
     pidx.release();
     pbar.release();
@@ -847,7 +1186,7 @@ void lu_launch_row_amax(Ctx* c, const double* A, int ld, int nr, int nc, double*
 }
 void lu_launch_trsm(Ctx* c, const double* L, int ldl, double* X, int ldx, int ncols) {
     if (ncols <= 0) return;
-    lu_trsm_kernel<<<(ncols + 63) / 64, 64, 0, c->stream>>>(L, ldl, X, ldx, ncols);
+    lu_trsm_kernel<<<(ncols + TRSM_COLS_PER_CTA - 1) / TRSM_COLS_PER_CTA, TRSM_THREADS, 0, c->stream>>>(L, ldl, X, ldx, ncols);
     c->launches += 1;
 }
 void lu_launch_trsv_diag(Ctx* c, const double* D, int ld, int nb, double* x, int upper) {
@@ -865,6 +1204,45 @@ ml_status lu_panel_factor(Ctx* c, LuPanelWork& W, double* dA, int ld, int n, int
     // Cluster variant (one thread-block cluster of <= 16 CTAs, candidates through distributed shared memory, hardware cluster
     // barrier per column): whenever the panel's rows fit 16 CTAs' shared memory.  MACHLINE_LU_NO_CLUSTER=1 disables it.
     static const bool no_cluster = getenv("MACHLINE_LU_NO_CLUSTER") != nullptr;
+    // Second-generation cluster kernel (thread = row, delayed updates, pulled pivot rows): panels of up to 16 x 512 rows.
+    // MACHLINE_LU_PANEL_V1=1 keeps the first cluster kernel (A/B timing, bitwise comparison of the factors).
+    static const bool panel_v1 = getenv("MACHLINE_LU_PANEL_V1") != nullptr;
+    if (!per_column && !no_cluster && !rpc_env && !panel_v1 && m <= LUP_CL_MAX * LUP2_T) {
+        int G = 1;
+        while (G < LUP_CL_MAX && G * 64 < m) G *= 2;
+        // rows per CTA: exactly ceil(m / G) (nothing in the kernel needs a multiple of 32), so the last CTA always owns rows
+        const int rpc_c = (m + G - 1) / G;
+        if (rpc_c <= LUP2_T && (long long)rpc_c * (G - 1) < m) {
+            if (!(c->attr_mask & 64u)) {
+                ML_CUDA(c, cudaFuncSetAttribute(lu_panel_cl2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel2_smem(LUP2_CAP)));
+                ML_CUDA(c, cudaFuncSetAttribute(lu_panel_cl2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lu_panel2_smem(LUP2_T)));
+                ML_CUDA(c, cudaFuncSetAttribute(lu_panel_cl2_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                ML_CUDA(c, cudaFuncSetAttribute(lu_panel_cl2_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+                c->attr_mask |= 64u;
+            }
+            LuPanelArgs pa;
+            pa.A = dA; pa.ld = ld; pa.n = n; pa.k0 = k0; pa.k1 = k1; pa.rpc = rpc_c;
+            pa.vv = d_vv; pa.piv = d_piv; pa.perm = d_perm;
+            pa.cand_v = nullptr; pa.rowj = nullptr; pa.cand_i = nullptr; pa.bar = nullptr; pa.bar_base = 0;
+            pa.cand_row = reinterpret_cast<double*>(W.dbg);   // phase stamps (MACHLINE_LU_PANEL_DBG), else null
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(std::max(128, (rpc_c + 31) & ~31));   // thread = row; at least the 66 threads of the row slots
+            cfg.dynamicSmemBytes = lu_panel2_smem(rpc_c);
+            cfg.stream = stream;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = G;
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            if (rpc_c > LUP2_CAP) ML_CUDA(c, cudaLaunchKernelEx(&cfg, lu_panel_cl2_kernel<true>, pa));
+            else ML_CUDA(c, cudaLaunchKernelEx(&cfg, lu_panel_cl2_kernel<false>, pa));
+            c->launches += 1;
+            return ML_OK;
+        }
+    }
     if (!per_column && !no_cluster && !rpc_env && m <= LUP_CL_MAX * LUP_CAP) {
         int G = 1;
         while (G < LUP_CL_MAX && G * 128 < m) G *= 2;
@@ -985,7 +1363,8 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     };
     auto trsm = [&](cudaStream_t st, int k0, int c0, int c1) {            // U(k0..k0+64, c0..c1) = L11^-1 A(k0..k0+64, c0..c1)
         if (c1 > c0) {
-            lu_trsm_kernel<<<(c1 - c0 + 63) / 64, 64, 0, st>>>(dA + k0 + (size_t)k0 * ld, ld, dA + k0 + (size_t)c0 * ld, ld, c1 - c0);
+            lu_trsm_kernel<<<(c1 - c0 + TRSM_COLS_PER_CTA - 1) / TRSM_COLS_PER_CTA, TRSM_THREADS, 0, st>>>(dA + k0 + (size_t)k0 * ld, ld,
+                                                                                                        dA + k0 + (size_t)c0 * ld, ld, c1 - c0);
             c->launches += 1;
         }
     };
@@ -1020,6 +1399,8 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
         if (pst != ML_OK) { PW.release(); return pst; }
         for (;;) {   // invariant: A = [k0, k1), B = [k1, k2) factored (B has seen A); k2 < n; nothing outside the pair has seen them
             const int k1 = k0 + LU_NB, k2 = k1 + LU_NB;
+            // (one fused launch for the four was tried, r5d / r5e: 0.7 ms less at N = 7.4k without interchanges, 9-13 ms more with
+            // an interchange in every column)
             laswp(S0, 0, k0, k0, k1);     // A's interchanges, left and right of the pair
             laswp(S0, k2, n, k0, k1);
             laswp(S0, 0, k1, k1, k2);     // B's: the left part includes A's own columns (its multipliers move with the rows)

@@ -53,10 +53,11 @@ def test_lu_needs_pivoting(ctx):
     assert np.abs(A @ x - b).max() < 1e-10
 
 
-@pytest.mark.parametrize("n", [1500, 4500, 5000])
+@pytest.mark.parametrize("n", [1500, 4500, 5000, 7100])
 def test_lu_heavy_pivoting_across_ctas(ctx, n):
-    """No diagonal dominance: (almost) every column interchanges two rows held by different CTAs of the cooperative
-    panel kernel (n = 4500 / 5000: more than 32 CTAs, the two-level candidate reduction; 5000 is not a multiple of 64)."""
+    """No diagonal dominance: (almost) every column interchanges two rows held by different CTAs of the panel kernels
+    (n = 4500 / 5000: more than 32 CTAs for the grid-wide kernel, the two-level candidate reduction; 5000 is not a multiple of
+    64; n = 7100: the first panels of the cluster kernel keep their last rows in global memory)."""
     rng = np.random.default_rng(n)
     A = np.asfortranarray(rng.standard_normal((n, n)))
     A[::5] *= 1e3          # implicit scaling matters: vv differs by row
