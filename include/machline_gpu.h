@@ -224,6 +224,59 @@ ml_status ml_solve(ml_ctx *ctx, const ml_solver_opts *opts, const double *BC, do
 ml_status ml_solve_dense(ml_ctx *ctx, int N, const double *A_colmajor, const double *b,
                          const ml_solver_opts *opts, double *x_out, ml_solve_info *info);
 
+/* ---- post-processing on the device ---------------------------------------------------------
+ * panel_solver_calc_cell_velocities, calc_pressures, calc_forces and calc_moments (src/panel_solver.f90:2030-2095,
+ * 2218-2321, 2440-2528, 2551-2615) with panel_get_velocity_jump (src/panel.f90:3415-3512) and the pressure rules
+ * (src/flow.f90:313-585) for LOWER-ORDER panels: one thread per cell (= panel image), reading the solution that the
+ * last ml_solve left on the device, so that x only has to leave the GPU as results.  Higher-order panels (quadratic
+ * pressure distributions, src/panel.f90:3541-3740) are post-processed by the host library (mlh_case_post). */
+typedef struct ml_post_tables {
+    int n_cells;                /* N_panels, or 2 N_panels in an asymmetric mirrored flow (panel_solver.f90:2040-2047)   */
+    const int *mu_index;        /* [n_cells][3] position in x of each vertex's doublet strength (mu(i) = x(P(i)),
+                                   panel_solver.f90:2018-2020, with the mirror shift of panel.f90:3380-3400); -1: zero  */
+    const double *T_mu;         /* [n_cells][9] row-major T_mu of the cell's image (rows 2 and 3 give the gradient)      */
+    const double *A_g_to_ls;    /* [n_cells][9] row-major                                                               */
+    const double *s_dir;        /* [n_cells][3] n_g / (nu_g . n_g) (panel.f90:3489-3493); zeros: panel without sources   */
+    const int *sigma_index;     /* [n_cells] position in x of an unknown source strength, -1: use sigma_known            */
+    const double *sigma_known;  /* [n_cells]                                                                             */
+    const double *v_inner;      /* [n_cells][3] velocity just inside the cell per unit U: the prescribed inner flow of the
+                                   Dirichlet formulations, v_inf / U + induced velocity for the Neumann ones (:2063-2066) */
+    const double *n_g;          /* [n_cells][3] normal of the cell's image                                               */
+    const double *area;         /* [n_cells]                                                                             */
+    const double *centr;        /* [n_cells][3] centroid of the cell's image                                             */
+    const int *force_cell;      /* [n_cells] the cell whose force enters this cell's moment: the reference uses the
+                                   un-mirrored panel's force for the mirrored cell (panel_solver.f90:2583)               */
+} ml_post_tables;
+
+enum { ML_RULE_INCOMPRESSIBLE = 0, ML_RULE_ISENTROPIC, ML_RULE_SECOND_ORDER, ML_RULE_SLENDER_BODY, ML_RULE_LINEAR,
+       ML_RULE_PRANDTL_GLAUERT, ML_RULE_KARMAN_TSIEN, ML_RULE_LAITONE, ML_RULE_COUNT };
+
+typedef struct ml_post_flow {
+    double U, U_inv, M_inf, gamma;                          /* flow.f90:58-147                                          */
+    double a_ise, b_ise, c_ise, C_P_vac, C_P_stag;          /* constants of the isentropic rule and the limits          */
+    double M_inf_corr;                                      /* Mach number of the subsonic corrections                  */
+    double v_inf[3], A_g_to_c[9];
+    double CG[3], S_ref, l_ref;                             /* references of the force / moment coefficients            */
+    int rules;                                              /* bit ML_RULE_*: which pressure coefficients to compute    */
+    int force_rule;                                         /* ML_RULE_* of solver.pressure_for_forces                  */
+    int mirrored_symmetric;                                 /* mirrored mesh in a symmetric flow: C_F, C_M doubled /
+                                                               zeroed as panel_solver.f90:2513-2521, 2600-2612          */
+    int mirror_plane;                                       /* 1..3                                                     */
+} ml_post_flow;
+
+typedef struct ml_post_out {        /* host buffers; any array may be NULL                                               */
+    double *V_cells;                /* [n_cells][3]                                                                      */
+    double *C_p[ML_RULE_COUNT];     /* [n_cells] each, for the rules selected in ml_post_flow::rules                     */
+    double *dC_f;                   /* [n_cells][3]                                                                      */
+    double C_F[3], C_M[3];
+    double C_p_max, C_p_min;        /* of the rule test/test_machline.py:62-66 reads: incompressible if computed, else isentropic */
+} ml_post_out;
+
+/* Needs a successful ml_solve on this context (ML_BAD_ARGUMENT otherwise).  x_override (host, n_unknown) replaces the device
+   solution when non-NULL (tests). */
+ml_status ml_post_process(ml_ctx *ctx, const ml_post_tables *tables, const ml_post_flow *flow, const double *x_override,
+                          ml_post_out *out);
+
 /* ---- introspection for tests / benches --------------------------------------------------------- */
 /* Number of kernel launches issued by this context since creation (bench.py "gpu_launches"). */
 long long ml_launch_count(const ml_ctx *ctx);

@@ -71,6 +71,13 @@ int mlh_case_post(mlh_case *c, const double *x, mlh_results *out);
    panel_solver_calc_cell_velocities evaluates it (src/panel_solver.f90:2063-2066, 2080-2083).  pts may be NULL to query the count. */
 int mlh_case_inner_points(mlh_case *c, double *pts, int *n_points);
 int mlh_case_post2(mlh_case *c, const double *x, const double *v_inner, mlh_results *out);
+/* Per-rule arrays of the last mlh_case_post / mlh_case_post2: rule = ML_RULE_* (pressure coefficients, [n_cells]) or -1 (the
+   cells' force contributions dC_f, [n_cells][3]).  dst may be NULL to query the length; *n = 0 when the rule was not computed. */
+int mlh_case_result_array(mlh_case *c, int rule, double *dst, int *n);
+/* Tables and constants of ml_post_process (include/machline_gpu.h: the lower-order post-processing on the device,
+   panel_solver.f90:2030-2615), prepared with the operations of mlh_case_post.  v_inner as in mlh_case_post2 (NULL for the
+   Dirichlet formulations).  Pointers stay valid until the next call or mlh_case_destroy. */
+int mlh_case_post_tables(mlh_case *c, const double *v_inner, ml_post_tables *tables, ml_post_flow *flow);
 /* Write report.json in the reference's layout (panel_solver.f90:2618-2746) */
 int mlh_case_write_report(mlh_case *c, const char *path, const ml_solve_info *info, int solver_stat,
                           double total_runtime);

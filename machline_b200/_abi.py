@@ -70,6 +70,28 @@ class MlhResults(C.Structure):
                 ("mu", c_double_p), ("C_p", c_double_p), ("V_cells", c_double_p)]
 
 
+RULES = ["incompressible", "isentropic", "second-order", "slender-body", "linear", "prandtl-glauert", "karman-tsien", "laitone"]
+
+
+class MlPostTables(C.Structure):
+    _fields_ = [("n_cells", C.c_int), ("mu_index", c_int_p), ("T_mu", c_double_p), ("A_g_to_ls", c_double_p),
+                ("s_dir", c_double_p), ("sigma_index", c_int_p), ("sigma_known", c_double_p), ("v_inner", c_double_p),
+                ("n_g", c_double_p), ("area", c_double_p), ("centr", c_double_p), ("force_cell", c_int_p)]
+
+
+class MlPostFlow(C.Structure):
+    _fields_ = [("U", C.c_double), ("U_inv", C.c_double), ("M_inf", C.c_double), ("gamma", C.c_double),
+                ("a_ise", C.c_double), ("b_ise", C.c_double), ("c_ise", C.c_double), ("C_P_vac", C.c_double),
+                ("C_P_stag", C.c_double), ("M_inf_corr", C.c_double), ("v_inf", C.c_double * 3),
+                ("A_g_to_c", C.c_double * 9), ("CG", C.c_double * 3), ("S_ref", C.c_double), ("l_ref", C.c_double),
+                ("rules", C.c_int), ("force_rule", C.c_int), ("mirrored_symmetric", C.c_int), ("mirror_plane", C.c_int)]
+
+
+class MlPostOut(C.Structure):
+    _fields_ = [("V_cells", c_double_p), ("C_p", c_double_p * 8), ("dC_f", c_double_p), ("C_F", C.c_double * 3),
+                ("C_M", C.c_double * 3), ("C_p_max", C.c_double), ("C_p_min", C.c_double)]
+
+
 class MlhMeshInfo(C.Structure):
     _fields_ = [("n_body_panels", C.c_int), ("n_body_verts", C.c_int), ("n_wake_panels", C.c_int),
                 ("n_wake_strips", C.c_int), ("n_edges", C.c_int), ("n_cp", C.c_int), ("n_unknown", C.c_int),

@@ -26,7 +26,7 @@ DRIVER_EXE = PKG / "machline_b200.exe"
 
 HOST_SOURCES = ["flow.cpp", "mesh_io.cpp", "panel_setup.cpp", "surface_mesh.cpp", "wake.cpp",
                 "solver_setup.cpp", "outputs.cpp", "capi.cpp"]
-GPU_SOURCES = ["capi.cu", "aic_kernels.cu", "aic_sub.cu", "aic_sup.cu", "aic_sub_ho.cu", "aic_sup_ho.cu", "solve_kernels.cu", "lu_kernels.cu", "lu_sharded.cu", "seq_solvers.cu", "peaks.cu", "multi.cu"]
+GPU_SOURCES = ["capi.cu", "aic_kernels.cu", "aic_sub.cu", "aic_sup.cu", "aic_sub_ho.cu", "aic_sup_ho.cu", "solve_kernels.cu", "lu_kernels.cu", "lu_sharded.cu", "seq_solvers.cu", "peaks.cu", "multi.cu", "post.cu"]
 
 # The image exports CXX=/opt/gcc/bin/g++ (a wrapper without libgomp.spec); the system compiler on
 # PATH is the complete one.
@@ -36,7 +36,7 @@ NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
 NVCC_ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # The supersonic assembly kernel evaluates the reference's predicates operation by operation: no FMA
 # contraction there (csrc/gpu/pair_influence.cuh).  The solver kernels use explicit fma().
-PER_FILE_FLAGS = {"aic_sup.cu": ["-fmad=false"], "aic_sup_ho.cu": ["-fmad=false"]}
+PER_FILE_FLAGS = {"aic_sup.cu": ["-fmad=false"], "aic_sup_ho.cu": ["-fmad=false"], "post.cu": ["-fmad=false"]}
 
 
 def _newer(target: Path, deps) -> bool:
@@ -88,7 +88,7 @@ def gpu_compile_flags():
 def build_gpu(force: bool = False) -> Path:
     gdir = CSRC / "gpu"
     srcs = [gdir / s for s in GPU_SOURCES if (gdir / s).exists()]
-    deps = srcs + list(gdir.glob("*.cuh")) + list(gdir.glob("*.h")) + list(INCLUDE.glob("*.h"))
+    deps = srcs + list(gdir.glob("*.cuh")) + list(gdir.glob("*.h")) + list(INCLUDE.glob("*.h")) + [CSRC / "host" / "pressure_rules.hpp"]
     if force or _newer(GPU_LIB, deps):
         objdir = gdir / "build"
         objdir.mkdir(exist_ok=True)

@@ -117,6 +117,7 @@ extern "C" void ml_ctx_destroy(ml_ctx* c) {
 #ifdef ML_HAVE_NCCL
     if (c->comm) ncclCommDestroy(c->comm);
 #endif
+    c->d_x_last.release();
     c->d_recs.release();
     c->d_cp_xyz.release();
     c->d_A.release();

@@ -165,6 +165,8 @@ struct Ctx {
     int tile_rows = 32, chunk_records = 64, n_chunks = 0, n_wcols = 0, n_zero_cols = 0;
     int n_rows = 0, n_rows_pad = 0, ld = 0, n_cols = 0;
     bool assembled = false;
+    DevBuf<double> d_x_last;        // the solution of the last ml_solve, kept on the device for ml_post_process (post.cu)
+    int n_x_last = 0;
     std::vector<double> h_I_known;  // local rows
     long long pair_count = 0;
     double assemble_ms = 0, solve_ms = 0;
@@ -207,6 +209,9 @@ struct Ctx {
         if (e__ != cudaSuccess) return (ctx)->cuda_fail(e__, #call);  \
     } while (0)
 
+// post.cu
+ml_status post_process(Ctx* c, const ml_post_tables* t, const ml_post_flow* f, const double* x_override, ml_post_out* out);
+
 // aic_kernels.cu
 FlowConst make_flow_const(const ml_flow& f);
 cudaError_t launch_aic(Ctx* c, const AicLaunch& L, bool supersonic);
@@ -237,6 +242,7 @@ struct ml_ctx : public mlgpu::Ctx {};
 // multi.cu: fan-out of the entry points over the member contexts of an ml_ctx_create_multi handle
 namespace mlgpu {
 void multi_destroy(ml_ctx* c);
+ml_status multi_post_process(ml_ctx* c, const ml_post_tables* t, const ml_post_flow* f, const double* x_override, ml_post_out* out);
 ml_status multi_set_flow(ml_ctx* c, const ml_flow* f);
 ml_status multi_set_panels(ml_ctx* c, const ml_panel_soa* body, const ml_panel_soa* wake);
 ml_status multi_set_system_map(ml_ctx* c, const ml_system_map* m);

@@ -97,6 +97,14 @@ void multi_destroy(ml_ctx* c) {
     c->group = nullptr;
 }
 
+// every member holds the replicated solution after a solve: the first one post-processes it
+ml_status multi_post_process(ml_ctx* c, const ml_post_tables* t, const ml_post_flow* f, const double* x_override, ml_post_out* out) {
+    ml_ctx* m0 = c->group->m[0];
+    ml_status st = ml_post_process(m0, t, f, x_override, out);
+    if (st != ML_OK) c->err = m0->err;
+    return st;
+}
+
 ml_status multi_set_flow(ml_ctx* c, const ml_flow* f) {
     ml_status st = for_each_seq(c, [&](int i) { return ml_set_flow(c->group->m[i], f); });
     if (st != ML_OK) return st;

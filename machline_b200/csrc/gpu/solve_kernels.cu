@@ -1856,6 +1856,20 @@ __global__ void __launch_bounds__(256) ata_kernel(const double* __restrict__ A, 
 
 // x minimises ||A x - b|| through the normal equations A^T A x = A^T b with the input's preconditioner and solver; the residual
 // reported is that of the original system (panel_solver.f90:1992-1998).  Single GPU.
+// The solution stays on the device for ml_post_process (post.cu): a device-to-device copy of N doubles on the solve's stream.
+// The buffer outlives the solve, so it does not come from the stream-ordered pool of the solver temporaries.
+static cudaError_t keep_solution(Ctx* c, const double* d_x, int N) {
+    c->n_x_last = 0;
+    cudaStream_t pool = tl_pool_stream;
+    tl_pool_stream = nullptr;
+    cudaError_t e = c->d_x_last.alloc((size_t)N);
+    tl_pool_stream = pool;
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(c->d_x_last.p, d_x, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    if (e == cudaSuccess) c->n_x_last = N;
+    return e;
+}
+
 static ml_status solve_least_squares(Ctx* c, const ml_solver_opts* opts, const double* BC, double* x_out, ml_solve_info* info) {
     const int N = c->n_cols, M = c->n_cp;
     if (c->world > 1 || c->n_rows != M) return c->fail(ML_UNSUPPORTED, "least-squares formulations run on one GPU (row shards are not built for them)");
@@ -1924,6 +1938,7 @@ static ml_status solve_least_squares(Ctx* c, const ml_solver_opts* opts, const d
     std::vector<double> hAx(M);
     ML_CUDA(c, cudaMemcpyAsync(hAx.data(), Ax.p, (size_t)M * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     ML_CUDA(c, cudaMemcpyAsync(x_out, d_x.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    ML_CUDA(c, keep_solution(c, d_x.p, N));
     ML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
     c->d2h_bytes += (long long)(M + N) * sizeof(double);
@@ -2106,6 +2121,7 @@ ml_status solve_resident(Ctx* c, const ml_solver_opts* opts, const double* BC, d
         ML_CUDA(c, cudaMemcpyAsync(x_out, d_x.p, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
         c->d2h_bytes += (long long)N * sizeof(double);
     }
+    if (st == ML_OK) ML_CUDA(c, keep_solution(c, d_x.p, N));
     ML_CUDA(c, cudaEventRecord(c->ev1, c->stream));
     ML_CUDA(c, cudaStreamSynchronize(c->stream));
     float ms = 0.f;

@@ -159,6 +159,12 @@ void mlh::Case::setup() {
     lap("pre_solve");
 }
 
+// tables of ml_post_process (include/machline_gpu.h), one entry per cell
+struct PostTableStore {
+    std::vector<int> mu_index, sigma_index, force_cell;
+    std::vector<double> T_mu, A_g_to_ls, s_dir, sigma_known, v_inner, n_g, area, centr;
+};
+
 struct mlh_case {
     Case c;
     PanelTableStore body, wake;
@@ -167,6 +173,7 @@ struct mlh_case {
     bool tables_built = false;
     Results last;
     std::vector<double> res_cp, res_v;
+    PostTableStore post;
 };
 
 static thread_local std::string g_err;
@@ -365,6 +372,154 @@ extern "C" int mlh_case_post2(mlh_case* h, const double* x, const double* v_inne
         out->mu = R.mu.data();
         out->C_p = h->res_cp.data();
         out->V_cells = h->res_v.data();
+        return 0;
+    } catch (const std::exception& e) {
+        g_err = e.what();
+        return 1;
+    }
+}
+
+// Per-rule arrays of the last mlh_case_post / mlh_case_post2: rule = ML_RULE_* (pressure coefficients, [n_cells]) or -1 (the cells'
+// force contributions dC_f, [n_cells][3]).  dst may be NULL to query the length; *n = 0 when the rule was not computed.
+extern "C" int mlh_case_result_array(mlh_case* h, int rule, double* dst, int* n) {
+    if (!h || !n) return 1;
+    const Results& R = h->last;
+    if (rule == -1) {
+        *n = (int)R.dC_f.size() * 3;
+        if (dst)
+            for (size_t i = 0; i < R.dC_f.size(); ++i)
+                for (int k = 0; k < 3; ++k) dst[3 * i + k] = R.dC_f[i][k];
+        return 0;
+    }
+    const std::vector<double>* arrs[ML_RULE_COUNT] = {&R.C_p_inc, &R.C_p_ise, &R.C_p_2nd, &R.C_p_sln, &R.C_p_lin, &R.C_p_pg, &R.C_p_kt, &R.C_p_lai};
+    if (rule < 0 || rule >= ML_RULE_COUNT) {
+        g_err = "unknown rule";
+        return 1;
+    }
+    *n = (int)arrs[rule]->size();
+    if (dst) std::memcpy(dst, arrs[rule]->data(), arrs[rule]->size() * sizeof(double));
+    return 0;
+}
+
+// The tables and constants ml_post_process takes (lower-order panels only).  v_inner as in mlh_case_post2 (NULL for the Dirichlet
+// formulations).  Everything the device kernel reads is prepared with the operations of Case::post, so that both evaluate the same
+// arithmetic: mu(i) = x(P(i)) (panel_solver.f90:2018-2020), the mirror shifts of panel_get_velocity_jump (panel.f90:3380-3400,
+// 3300-3320), V_inner / U (panel_solver.f90:2070).  Pointers stay valid until the next call or mlh_case_destroy.
+extern "C" int mlh_case_post_tables(mlh_case* h, const double* v_inner, ml_post_tables* t, ml_post_flow* f) {
+    if (!h || !t || !f) return 1;
+    try {
+        const Case& c = h->c;
+        if (!c.solver.dirichlet && !v_inner)
+            throw std::runtime_error("post-processing of a Neumann formulation needs the induced velocities at mlh_case_inner_points");
+        for (const Panel& p : c.panels)
+            if (p.order != 1) throw std::runtime_error("ml_post_process covers lower-order panels; use mlh_case_post for higher-order distributions");
+        const Flow& fs = c.freestream;
+        const int Np = c.N_panels, n = c.asym_flow ? 2 * Np : Np;
+        PostTableStore& T = h->post;
+        T.mu_index.assign((size_t)3 * n, -1);
+        T.sigma_index.assign(n, -1);
+        T.force_cell.assign(n, 0);
+        T.T_mu.assign((size_t)9 * n, 0.);
+        T.A_g_to_ls.assign((size_t)9 * n, 0.);
+        T.s_dir.assign((size_t)3 * n, 0.);
+        T.sigma_known.assign(n, 0.);
+        T.v_inner.assign((size_t)3 * n, 0.);
+        T.n_g.assign((size_t)3 * n, 0.);
+        T.area.assign(n, 0.);
+        T.centr.assign((size_t)3 * n, 0.);
+        // position in x of body source strength i (unknown sources only): sigma(i_sys_sigma_in_body(k)) = x(P(N_d_unknown + k))
+        std::vector<int> sigma_pos(c.sigma.size(), -1);
+        for (int k = 0; k < c.N_s_unknown; ++k) sigma_pos[c.i_sys_sigma_in_body[k]] = c.P[c.N_d_unknown + k];
+        const int n_mu = c.asym_flow ? 2 * c.N_verts : c.N_verts;
+        for (int img = 0; img < (c.asym_flow ? 2 : 1); ++img) {
+            const bool mir = img == 1;
+            for (int i = 0; i < Np; ++i) {
+                const Panel& p = c.panels[i];
+                const size_t cell = (size_t)i + (size_t)img * Np;
+                if ((int)p.i_vert_d.size() != 3 || p.mu_dim != 3)
+                    throw std::runtime_error("ml_post_process: a lower-order panel with other than three doublet vertices");
+                for (int k = 0; k < 3; ++k) {
+                    const int iv = p.i_vert_d[k];
+                    int idx;
+                    if (c.asym_flow) idx = mir ? ((iv >= c.N_verts) ? iv - c.N_verts : iv + c.N_verts) : iv;
+                    else idx = (iv >= c.N_verts) ? iv - c.N_verts : iv;
+                    if (idx < 0 || idx >= n_mu) throw std::runtime_error("ml_post_process: vertex index out of range");
+                    T.mu_index[3 * cell + k] = idx < c.N_d_unknown ? c.P[idx] : -1;   // mu beyond the unknowns stays zero (Case::post)
+                }
+                const std::vector<double>& Tm = mir ? p.T_mu_mir : p.T_mu;
+                for (int k = 0; k < 9; ++k) T.T_mu[9 * cell + k] = Tm[k];
+                const M33& A = mir ? p.A_g_to_ls_mir : p.A_g_to_ls;
+                for (int a = 0; a < 3; ++a)
+                    for (int b = 0; b < 3; ++b) T.A_g_to_ls[9 * cell + 3 * a + b] = A[a][b];
+                if (p.has_sources) {
+                    const V3 s_dir = mir ? p.n_g_mir / inner(p.nu_g_mir, p.n_g_mir) : p.n_g / inner(p.nu_g, p.n_g);
+                    for (int k = 0; k < 3; ++k) T.s_dir[3 * cell + k] = s_dir[k];
+                    if (p.sigma_dim > 1 || p.i_panel_s.size() != 1) throw std::runtime_error("ml_post_process: linear source distribution on a lower-order panel");
+                    const int ip = p.i_panel_s[0];
+                    int idx;
+                    if (c.asym_flow) idx = mir ? ((ip >= Np) ? ip - Np : ip + Np) : ip;
+                    else idx = (ip >= Np) ? ip - Np : ip;
+                    if (idx < 0 || idx >= (int)c.sigma.size()) throw std::runtime_error("ml_post_process: source index out of range");
+                    T.sigma_index[cell] = sigma_pos[idx];
+                    T.sigma_known[cell] = c.sigma[idx];
+                }
+                // V_cells_inner / U as Case::post forms it (panel_solver.f90:2063-2073)
+                V3 V_in = c.inner_flow * fs.U;
+                if (!c.solver.dirichlet) {
+                    const double* v = v_inner + 3 * cell;
+                    V_in = fs.v_inf + fs.U * V3{v[0], v[1], v[2]};
+                }
+                const V3 vin = V_in / fs.U;
+                const V3& ng = mir ? p.n_g_mir : p.n_g;
+                const V3& ce = mir ? p.centr_mir : p.centr;
+                for (int k = 0; k < 3; ++k) {
+                    T.v_inner[3 * cell + k] = vin[k];
+                    T.n_g[3 * cell + k] = ng[k];
+                    T.centr[3 * cell + k] = ce[k];
+                }
+                T.area[cell] = p.A;
+                T.force_cell[cell] = i;   // the mirrored cell's moment uses the un-mirrored panel's force (panel_solver.f90:2583)
+            }
+        }
+        t->n_cells = n;
+        t->mu_index = T.mu_index.data();
+        t->T_mu = T.T_mu.data();
+        t->A_g_to_ls = T.A_g_to_ls.data();
+        t->s_dir = T.s_dir.data();
+        t->sigma_index = T.sigma_index.data();
+        t->sigma_known = T.sigma_known.data();
+        t->v_inner = T.v_inner.data();
+        t->n_g = T.n_g.data();
+        t->area = T.area.data();
+        t->centr = T.centr.data();
+        t->force_cell = T.force_cell.data();
+        std::memset(f, 0, sizeof *f);
+        f->U = fs.U;
+        f->U_inv = fs.U_inv;
+        f->M_inf = fs.M_inf;
+        f->gamma = fs.gamma;
+        f->a_ise = fs.a_ise;
+        f->b_ise = fs.b_ise;
+        f->c_ise = fs.c_ise;
+        f->C_P_vac = fs.C_P_vac;
+        f->C_P_stag = fs.C_P_stag;
+        f->M_inf_corr = c.solver.M_inf_corr;
+        for (int k = 0; k < 3; ++k) {
+            f->v_inf[k] = fs.v_inf[k];
+            f->CG[k] = c.CG[k];
+            for (int b = 0; b < 3; ++b) f->A_g_to_c[3 * k + b] = fs.A_g_to_c[k][b];
+        }
+        f->S_ref = c.S_ref;
+        f->l_ref = c.l_ref;
+        const SolverSettings& s = c.solver;
+        f->rules = (s.incompressible_rule ? 1 << ML_RULE_INCOMPRESSIBLE : 0) | (s.isentropic_rule ? 1 << ML_RULE_ISENTROPIC : 0) |
+                   (s.second_order_rule ? 1 << ML_RULE_SECOND_ORDER : 0) | (s.slender_rule ? 1 << ML_RULE_SLENDER_BODY : 0) |
+                   (s.linear_rule ? 1 << ML_RULE_LINEAR : 0) | (s.prandtl_glauert ? 1 << ML_RULE_PRANDTL_GLAUERT : 0) |
+                   (s.karman_tsien ? 1 << ML_RULE_KARMAN_TSIEN : 0) | (s.laitone ? 1 << ML_RULE_LAITONE : 0);
+        f->force_rule = pressure_rule_id(s.pressure_for_forces);
+        if (f->force_rule < 0 || !(f->rules & (1 << f->force_rule))) throw std::runtime_error(s.pressure_for_forces + " pressure for forces is not available.");
+        f->mirrored_symmetric = (c.mirrored && !c.asym_flow) ? 1 : 0;
+        f->mirror_plane = c.mirror_plane;
         return 0;
     } catch (const std::exception& e) {
         g_err = e.what();

@@ -150,43 +150,54 @@ bool Flow::point_in_dod(const V3& Q, const V3& P) const {
     return false;
 }
 
-double Flow::get_C_P_inc(const V3& v) const { return 1. - inner(v, v) * U_inv * U_inv; }
-
+// The rules themselves live in pressure_rules.hpp (shared with the device post-processing kernel)
+mlpr::FlowConst Flow::pressure_const() const {
+    mlpr::FlowConst f;
+    f.U_inv = U_inv;
+    f.M_inf = M_inf;
+    f.gamma = gamma;
+    f.a_ise = a_ise;
+    f.b_ise = b_ise;
+    f.c_ise = c_ise;
+    f.C_P_vac = C_P_vac;
+    f.C_P_stag = C_P_stag;
+    for (int i = 0; i < 3; ++i) {
+        f.v_inf[i] = v_inf[i];
+        for (int k = 0; k < 3; ++k) f.A_g_to_c[3 * i + k] = A_g_to_c[i][k];
+    }
+    return f;
+}
+static inline void v3_arr(const V3& v, double a[3]) {
+    a[0] = v[0];
+    a[1] = v[1];
+    a[2] = v[2];
+}
+double Flow::get_C_P_inc(const V3& v) const {
+    double a[3];
+    v3_arr(v, a);
+    return mlpr::C_P_inc(pressure_const(), a);
+}
 double Flow::get_C_P_ise(const V3& v) const {
-    double C = get_C_P_inc(v);
-    C = a_ise * (std::pow(1. + b_ise * C, c_ise) - 1.);
-    if (std::isnan(C)) C = C_P_vac;
-    return C;
+    double a[3];
+    v3_arr(v, a);
+    return mlpr::C_P_ise(pressure_const(), a);
 }
-
 V3 Flow::get_v_pert_c(const V3& v) const { return matvec(A_g_to_c, v - v_inf); }
-
-void Flow::restrict_pressure(double& C_P) const {
-    if (C_P > C_P_stag) C_P = C_P_stag;
-    else if (C_P < C_P_vac) C_P = C_P_vac;
-}
-
+void Flow::restrict_pressure(double& C_P) const { C_P = mlpr::restrict_pressure(pressure_const(), C_P); }
 double Flow::get_C_P_lin(const V3& v) const {
-    V3 vp = get_v_pert_c(v);
-    double C = -2. * vp[0] * U_inv;
-    restrict_pressure(C);
-    return C;
+    double a[3];
+    v3_arr(v, a);
+    return mlpr::C_P_lin(pressure_const(), a);
 }
-
 double Flow::get_C_P_sln(const V3& v) const {
-    double C_lin = get_C_P_lin(v);
-    V3 vp = get_v_pert_c(v);
-    double C = C_lin - (vp[1] * vp[1] + vp[2] * vp[2]) * (U_inv * U_inv);
-    restrict_pressure(C);
-    return C;
+    double a[3];
+    v3_arr(v, a);
+    return mlpr::C_P_sln(pressure_const(), a);
 }
-
 double Flow::get_C_P_2nd(const V3& v) const {
-    double C_sln = get_C_P_sln(v);
-    V3 vp = get_v_pert_c(v);
-    double C = C_sln - (1. - M_inf * M_inf) * (vp[0] * vp[0]) * (U_inv * U_inv);
-    restrict_pressure(C);
-    return C;
+    double a[3];
+    v3_arr(v, a);
+    return mlpr::C_P_2nd(pressure_const(), a);
 }
 
 double Flow::get_C_P_crit(double M) const {
@@ -197,30 +208,21 @@ double Flow::get_C_P_crit(double M) const {
     return 2. / (gamma * M2) * (std::pow(n / d, gamma / (gamma - 1.)) - 1.);
 }
 
+int pressure_rule_id(const std::string& rule) {
+    static const char* names[mlpr::RULE_COUNT] = {"incompressible", "isentropic", "second-order", "slender-body", "linear",
+                                                  "prandtl-glauert", "karman-tsien", "laitone"};
+    for (int i = 0; i < mlpr::RULE_COUNT; ++i)
+        if (rule == names[i]) return i;
+    return -1;
+}
+
 // flow.f90:528-585
 double Flow::get_C_P(const V3& v, const std::string& rule, double M_corr) const {
-    if (rule == "incompressible") return get_C_P_inc(v);
-    if (rule == "isentropic") return get_C_P_ise(v);
-    if (rule == "second-order") return get_C_P_2nd(v);
-    if (rule == "slender-body") return get_C_P_sln(v);
-    if (rule == "linear") return get_C_P_lin(v);
-    if (rule == "prandtl-glauert") {  // flow.f90:453-466
-        double C = get_C_P_inc(v);
-        return C / std::sqrt(1. - M_corr * M_corr);
-    }
-    if (rule == "karman-tsien") {  // flow.f90:469-487
-        double C = get_C_P_inc(v);
-        double M2 = M_corr * M_corr, sM2 = std::sqrt(1. - M2);
-        double x = M2 / (1. + sM2);
-        return C / (sM2 + 0.5 * x * C);
-    }
-    if (rule == "laitone") {  // flow.f90:490-508
-        double C = get_C_P_inc(v);
-        double M2 = M_corr * M_corr, sM2 = std::sqrt(1. - M2);
-        double x = M2 * (1. + (0.5 * (gamma - 1.) * M2)) / (2 * sM2);
-        return C / (sM2 + (x * C));
-    }
-    throw std::runtime_error("unknown pressure rule " + rule);
+    const int id = pressure_rule_id(rule);
+    if (id < 0) throw std::runtime_error("unknown pressure rule " + rule);
+    double a[3];
+    v3_arr(v, a);
+    return mlpr::C_P(pressure_const(), a, id, M_corr);
 }
 
 }  // namespace mlh

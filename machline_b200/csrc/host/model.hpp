@@ -9,6 +9,7 @@
 
 #include "geom.hpp"
 #include "json_min.hpp"
+#include "pressure_rules.hpp"
 
 namespace mlh {
 
@@ -35,7 +36,9 @@ struct Flow {
     double get_C_P_crit(double M) const;
     void restrict_pressure(double& C_P) const;
     double get_C_P(const V3& v, const std::string& rule, double M_corr) const;
+    mlpr::FlowConst pressure_const() const;   // the constants of the rules as pressure_rules.hpp takes them
 };
+int pressure_rule_id(const std::string& rule);   // mlpr::Rule of a rule name, -1 if unknown
 
 // ---- src/base_geom.f90:26-61 --------------------------------------------------------------------
 struct Vertex {

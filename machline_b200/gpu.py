@@ -72,6 +72,7 @@ def lib() -> C.CDLL:
         L.ml_set_profiling.argtypes = [vp, C.c_int]
         L.ml_get_profile.argtypes = [vp, C.POINTER(_abi.MlProfile)]
         L.ml_reset_profile.argtypes = [vp]
+        L.ml_post_process.argtypes = [vp, C.POINTER(_abi.MlPostTables), C.POINTER(_abi.MlPostFlow), dp, C.POINTER(_abi.MlPostOut)]
         _lib = L
     return _lib
 
@@ -304,6 +305,28 @@ class Context:
         info = _abi.MlSolveInfo()
         self._check(lib().ml_solve_dense(self._h, N, _dp(A), _dp(b), C.byref(opts), _dp(x), C.byref(info)))
         return x, info
+
+    def post_process(self, case, v_inner: np.ndarray | None = None, x: np.ndarray | None = None) -> dict:
+        """Lower-order post-processing on the device (ml_post_process) from the solution the last solve() left there (or from x):
+        {"V_cells", "C_p": {rule: array}, "dC_f", "C_F", "C_M", "C_p_max", "C_p_min"}.  Neumann formulations need v_inner as
+        host.Case.post does."""
+        t, f = case.post_tables(v_inner)
+        n = t.n_cells
+        out = _abi.MlPostOut()
+        V, dCf = np.zeros((n, 3)), np.zeros((n, 3))
+        out.V_cells, out.dC_f = _dp(V), _dp(dCf)
+        cps = {}
+        for r, name in enumerate(_abi.RULES):
+            if f.rules & (1 << r):
+                cps[name] = np.zeros(n)
+                out.C_p[r] = _dp(cps[name])
+        xp = None
+        if x is not None:
+            x = np.ascontiguousarray(x, dtype=np.float64)
+            xp = _dp(x)
+        self._check(lib().ml_post_process(self._h, C.byref(t), C.byref(f), xp, C.byref(out)))
+        return {"V_cells": V, "C_p": cps, "dC_f": dCf, "C_F": np.array(out.C_F[:]), "C_M": np.array(out.C_M[:]),
+                "C_p_max": out.C_p_max, "C_p_min": out.C_p_min}
 
     def set_profiling(self, on: bool):
         self._check(lib().ml_set_profiling(self._h, int(on)))

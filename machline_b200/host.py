@@ -47,6 +47,8 @@ def lib() -> C.CDLL:
         L.mlh_case_write_body.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
         L.mlh_case_write_wake.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_int)]
         L.mlh_case_write_control_points.argtypes = [C.c_void_p, C.c_char_p, _abi.c_double_p]
+        L.mlh_case_result_array.argtypes = [C.c_void_p, C.c_int, _abi.c_double_p, C.POINTER(C.c_int)]
+        L.mlh_case_post_tables.argtypes = [C.c_void_p, _abi.c_double_p, C.POINTER(_abi.MlPostTables), C.POINTER(_abi.MlPostFlow)]
         _lib = L
     return _lib
 
@@ -161,6 +163,29 @@ class Case:
             mu=np.ctypeslib.as_array(r.mu, shape=(r.n_mu,)).copy(),
             C_p=np.ctypeslib.as_array(r.C_p, shape=(r.n_cells,)).copy(),
             V_cells=np.ctypeslib.as_array(r.V_cells, shape=(r.n_cells, 3)).copy())
+
+    def result_array(self, rule) -> np.ndarray:
+        """Per-rule array of the last post(): rule = a name of _abi.RULES (pressure coefficients per cell) or "dC_f"."""
+        rid = -1 if rule == "dC_f" else _abi.RULES.index(rule)
+        n = C.c_int(0)
+        if lib().mlh_case_result_array(self._h, rid, None, C.byref(n)) != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+        out = np.zeros(n.value)
+        if n.value:
+            lib().mlh_case_result_array(self._h, rid, out.ctypes.data_as(_abi.c_double_p), C.byref(n))
+        return out.reshape(-1, 3) if rule == "dC_f" else out
+
+    def post_tables(self, v_inner: np.ndarray | None = None):
+        """(MlPostTables, MlPostFlow) for gpu.Context.post_process: the lower-order post-processing on the device.  The tables
+        live in the case handle until the next call."""
+        t, f = _abi.MlPostTables(), _abi.MlPostFlow()
+        vp = None
+        if v_inner is not None:
+            self._v_inner_keep = np.ascontiguousarray(v_inner, dtype=np.float64)
+            vp = self._v_inner_keep.ctypes.data_as(_abi.c_double_p)
+        if lib().mlh_case_post_tables(self._h, vp, C.byref(t), C.byref(f)) != 0:
+            raise MachLineError(lib().mlh_last_error().decode())
+        return t, f
 
     def write_report(self, path, info: _abi.MlSolveInfo, solver_stat: int = 0, runtime: float = 0.0):
         Path(path).parent.mkdir(parents=True, exist_ok=True)

@@ -31,6 +31,7 @@ class RunResult:
     n_pairs: int
     gpu_launches: int
     total_s: float
+    device_post: dict | None = None   # run_case(device_post=True): ml_post_process on the device-resident solution
 
 
 class SolverStatus(RuntimeError):
@@ -43,8 +44,9 @@ class SolverStatus(RuntimeError):
 
 
 def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None,
-             matrix_solver: str | None = None) -> RunResult:
-    """`inp`: dict, JSON text or path of a MachLine input file."""
+             matrix_solver: str | None = None, device_post: bool = False) -> RunResult:
+    """`inp`: dict, JSON text or path of a MachLine input file.  device_post: also run the lower-order post-processing on the
+    device from the solution ml_solve left there (gpu.Context.post_process; velocities, pressure rules, forces, moments)."""
     t0 = time.perf_counter()
     case = host.Case(inp, base_dir=base_dir)
     ctx = gpu.Context(device)
@@ -77,6 +79,8 @@ def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None
                 case.write_report(report_file, info, solver_stat, total)
             raise SolverStatus(solver_stat, total)
         v_inner = None if case.dirichlet else ctx.velocities_at(case, case.inner_points(), x)   # panel_solver.f90:2063-2066
+        # device-resident results first: a velocity sweep (Neumann) does not touch the solution kept by the solve
+        dev = ctx.post_process(case, v_inner) if device_post else None
         res = case.post(x, v_inner)
         total = time.perf_counter() - t0
         if report_file and report_file != "none":
@@ -97,7 +101,7 @@ def run_case(inp, base_dir=None, device: int = 0, report_file: str | None = None
             vtk_out.export_off_body_points(case, ctx, x, off["points_file"], off["output_file"])
         return RunResult(res.C_p_max, res.C_p_min, res.C_F, res.C_M, res.mu, res.C_p, info.iterations,
                          info.res_max, info.res_norm, info.assemble_ms, info.solve_ms, ctx.pair_count,
-                         ctx.launch_count, total)
+                         ctx.launch_count, total, dev)
     finally:
         ctx.close()
         case.close()

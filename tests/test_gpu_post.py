@@ -1,0 +1,158 @@
+"""Post-processing on the device (ml_post_process, csrc/gpu/post.cu): cell velocities, pressure rules, forces
+and moments of lower-order panels (src/panel_solver.f90:2030-2615, src/panel.f90:3415-3512, src/flow.f90:313-585).
+
+CPU part: the tables the host library prepares for the kernel (mlh_case_post_tables) carry everything Case::post uses -- a numpy
+model of the kernel on those tables reproduces the host post-processing for a random x.  GPU part: the kernel against the host
+library per cell and per rule, and -- through the whole CUDA path, x never leaving the device between solve and post -- against
+the reference's golden tuples."""
+import numpy as np
+import pytest
+
+import fixtures
+from machline_b200 import _abi
+
+HIGHER_ORDER = {"test_02", "test_04", "test_06", "test_11", "test_16", "test_17"}
+LOWER_ORDER_CASES = [n for n in fixtures.golden_case_names() if n not in HIGHER_ORDER]
+
+
+def _arr(ptr, shape, dtype=np.float64):
+    return np.ctypeslib.as_array(ptr, shape=shape).astype(dtype, copy=True)
+
+
+def _model(t, f, x):
+    """The arithmetic of post_cells_kernel / post_moments_sums_kernel in numpy (inc and isentropic rules only)."""
+    n = t.n_cells
+    mi = _arr(t.mu_index, (n, 3), np.int64)
+    T = _arr(t.T_mu, (n, 3, 3))
+    A = _arr(t.A_g_to_ls, (n, 3, 3))
+    s_dir = _arr(t.s_dir, (n, 3))
+    si = _arr(t.sigma_index, (n,), np.int64)
+    sk = _arr(t.sigma_known, (n,))
+    vin = _arr(t.v_inner, (n, 3))
+    ng = _arr(t.n_g, (n, 3))
+    area = _arr(t.area, (n,))
+    ce = _arr(t.centr, (n, 3))
+    fc = _arr(t.force_cell, (n,), np.int64)
+    mu_v = np.where(mi >= 0, x[np.maximum(mi, 0)], 0.)
+    mu_p = np.einsum("nrk,nk->nr", T, mu_v)
+    dv = A[:, 0, :] * mu_p[:, 1:2] + A[:, 1, :] * mu_p[:, 2:3]
+    sg = np.where(si >= 0, x[np.maximum(si, 0)], sk)
+    dv = dv + sg[:, None] * s_dir
+    V = f.U * (vin + dv)
+    cp_inc = 1. - (V * V).sum(axis=1) * f.U_inv * f.U_inv
+    cps = {"incompressible": cp_inc}
+    if f.rules & 2:
+        c = f.a_ise * (np.power(1. + f.b_ise * cp_inc, f.c_ise) - 1.)
+        cps["isentropic"] = np.where(np.isnan(c), f.C_P_vac, c)
+    cpf = cps[_abi.RULES[f.force_rule]]
+    dCf = (-cpf * area)[:, None] * ng
+    CF = dCf.sum(axis=0) / f.S_ref
+    CM = np.cross(ce - np.array(f.CG[:]), dCf[fc]).sum(axis=0) / f.l_ref
+    if f.mirrored_symmetric:
+        k = f.mirror_plane - 1
+        CF = 2. * CF
+        CF[k] = 0.
+        CM = np.array([2. * CM[i] if i == k else 0. for i in range(3)])
+    return V, cps, dCf, CF, CM
+
+
+@pytest.mark.parametrize("name", ["test_07", "test_01", "test_13", "test_05", "test_19"])
+def test_post_tables_reproduce_host_post(name):
+    case, _, _ = fixtures.make_case(name)
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal(case.n_unknown) * 0.1
+    res = case.post(x)
+    t, f = case.post_tables()
+    if _abi.RULES[f.force_rule] not in ("incompressible", "isentropic"):
+        pytest.skip("the numpy model covers the incompressible and isentropic rules")
+    V, cps, dCf, CF, CM = _model(t, f, x)
+    sc = max(1., np.abs(res.V_cells).max())
+    assert np.abs(V - res.V_cells).max() < 1e-13 * sc
+    rep = "incompressible" if f.rules & 1 else "isentropic"
+    ref_cp = case.result_array(rep)
+    ok = np.isfinite(ref_cp) & (np.abs(ref_cp) < 1e6)
+    assert np.abs(cps[rep] - ref_cp)[ok].max() < 1e-11 * max(1., np.abs(ref_cp[ok]).max())
+    assert np.abs(dCf - case.result_array("dC_f")).max() < 1e-11 * max(1., np.abs(dCf).max())
+    assert np.abs(CF - res.C_F).max() < 1e-11 * max(1., np.abs(res.C_F).max())
+    assert np.abs(CM - res.C_M).max() < 1e-11 * max(1., np.abs(res.C_M).max())
+    case.close()
+
+
+def test_post_tables_refuse_higher_order():
+    from machline_b200 import host
+    case, _, _ = fixtures.make_case("test_06")
+    with pytest.raises(host.MachLineError, match="lower-order"):
+        case.post_tables()
+    case.close()
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from machline_b200 import gpu
+    c = gpu.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", LOWER_ORDER_CASES)
+def test_device_post_matches_host_and_reference_goldens(ctx, name):
+    """host setup -> ml_assemble -> ml_solve -> ml_post_process (x stays on the device) == host post-processing per cell and per
+    rule, and == the reference's golden tuple at the tolerance of tests/test_gpu_parity.py."""
+    from test_gpu_parity import ILL_CONDITIONED
+    case, expect, tol = fixtures.make_case(name)
+    ctx.set_case(case)
+    ctx.assemble()
+    x, info = ctx.solve(case.solver_opts(), case.BC)
+    # Neumann formulations: the velocity sweep replaces the resident tables but not the solution the solve left on the device
+    v_inner = None if case.dirichlet else ctx.velocities_at(case, case.inner_points(), x)
+    dev = ctx.post_process(case, v_inner)
+    res = case.post(x, v_inner)
+    sc = max(1., np.abs(res.V_cells).max())
+    assert np.abs(dev["V_cells"] - res.V_cells).max() <= 1e-14 * sc
+    for rule, got in dev["C_p"].items():
+        ref = case.result_array(rule)
+        assert ref.shape == got.shape, rule
+        fin = np.isfinite(ref)
+        assert (np.isfinite(got) == fin).all(), rule
+        # identical operations except pow (isentropic) and the order of nothing: 1e-13 of the scale
+        assert np.abs(got - ref)[fin].max() <= 1e-13 * max(1., np.abs(ref[fin]).max()), rule
+    assert np.abs(dev["dC_f"] - case.result_array("dC_f")).max() <= 1e-13 * max(1e-300, np.abs(dev["dC_f"]).max())
+    # the sums run in another order (strided partial sums + one tree against the host's sequential loop): a few ulp of the
+    # sum of the absolute contributions (the sphere of tests 07-09 has radius 60 with S_ref = l_ref = 1: contributions of 1e6
+    # cancel to coefficients of 1e-3)
+    t, f = case.post_tables(v_inner)
+    n = t.n_cells
+    ce = np.ctypeslib.as_array(t.centr, shape=(n, 3))
+    fc = np.ctypeslib.as_array(t.force_cell, shape=(n,))
+    dCf = case.result_array("dC_f")
+    mult = 2. if f.mirrored_symmetric else 1.
+    scale_F = mult * np.abs(dCf).sum(axis=0).max() / f.S_ref
+    scale_M = mult * np.abs(np.cross(ce - np.array(f.CG[:]), dCf[fc])).sum(axis=0).max() / f.l_ref
+    assert np.abs(dev["C_F"] - res.C_F).max() <= 1e-14 * max(scale_F, 1e-300)
+    assert np.abs(dev["C_M"] - res.C_M).max() <= 1e-14 * max(scale_M, 1e-300)
+    assert abs(dev["C_p_max"] - res.C_p_max) <= 1e-13 * max(1., abs(res.C_p_max))
+    assert abs(dev["C_p_min"] - res.C_p_min) <= 1e-13 * max(1., abs(res.C_p_min))
+    # the reference's golden tuple from the device results alone
+    s_cp, s_f = ILL_CONDITIONED.get(name, (1., 1.))
+    got = [dev["C_p_max"], dev["C_p_min"], *[float(v) for v in dev["C_F"]]]
+    # (force columns: the reference's tolerance, or the summation-order bound above where that is larger -- the sphere)
+    floor = [0., 0., 1e-14 * scale_F, 1e-14 * scale_F, 1e-14 * scale_F]
+    for g, e, tl, sl, fl, lab in zip(got, expect, tol, [s_cp, s_cp, s_f, s_f, s_f], floor, ["C_p_max", "C_p_min", "Cx", "Cy", "Cz"]):
+        assert abs(g - e) < max(tl * sl, fl), f"{lab}: got {g!r}, reference {e!r}"
+    case.close()
+
+
+@pytest.mark.gpu
+def test_device_post_needs_a_solution_and_checks_its_tables(ctx):
+    from machline_b200 import gpu
+    case, _, _ = fixtures.make_case("test_07")
+    fresh = gpu.Context(0)
+    with pytest.raises(gpu.GpuError) as e:
+        fresh.post_process(case)
+    assert e.value.status == 10   # ML_BAD_ARGUMENT: no solution on the device
+    x = np.zeros(case.n_unknown)
+    out = fresh.post_process(case, x=x)   # zero strengths: the cell velocity is the inner flow + sigma s_dir
+    assert np.isfinite(out["V_cells"]).all()
+    fresh.close()
+    case.close()
