@@ -499,9 +499,11 @@ __global__ void __launch_bounds__(LUP2_T, 1) lu_panel_cl2_kernel(const LuPanelAr
     cluster.sync();   // the panel is in shared memory; every CTA of the cluster is running before the first remote access
     if (stamping) t_prev = clock64();
 
+    int wj = 0;
     for (int jj = 0; jj < nb; ++jj) {
         const int j = a.k0 + jj, par = jj & 1;
         const int blk0 = jj & ~(LUP2_IB - 1), blkend = min(blk0 + LUP2_IB, nb);
+        if (jj >= (wj + 1) * a.rpc) ++wj;   // the CTA that holds position j
         // ---- this CTA's candidate for column j (largest vv*|a|, ties -> last position, linalg.f90:242) -------------
         unsigned long long key = 0ull;
         int bi = -1;
@@ -516,7 +518,13 @@ __global__ void __launch_bounds__(LUP2_T, 1) lu_panel_cl2_kernel(const LuPanelAr
         bi = lane < nwarps ? s_ri[lane] : -1;
         lup2_warp_argmax(key, bi);                         // every warp finishes the reduction: no second barrier
         LUP2_STAMP(0);
-        // ---- park the candidate row and row j in this CTA's slots; (value, position) to every CTA of the cluster ----
+        // ---- (value, position) to every CTA of the cluster FIRST: the remote stores' round trips (which the barrier's release
+        // waits for) run under the parking of the candidate row and the division below; then park the candidate row and row j
+        // in this CTA's slots ----
+        if (tid < G) {
+            cluster.map_shared_rank(cl_k, tid)[par * LUP_CL_MAX + bid] = key;
+            cluster.map_shared_rank(cl_i, tid)[par * LUP_CL_MAX + bid] = bi;
+        }
         const bool own_j = (j >= r0 && j < r0 + nr);
         const int ci = bi >= 0 ? bi : (own_j ? j : -1);    // a column of NaNs: row j stands in (the pivot stays on the diagonal)
         if (ci >= 0) {
@@ -532,19 +540,18 @@ __global__ void __launch_bounds__(LUP2_T, 1) lu_panel_cl2_kernel(const LuPanelAr
                 st_rowj[par * LUP_ROW + LU_NB + 1] = vv_r;
             }
         }
-        if (tid < G) {
-            cluster.map_shared_rank(cl_k, tid)[par * LUP_CL_MAX + bid] = key;
-            cluster.map_shared_rank(cl_i, tid)[par * LUP_CL_MAX + bid] = bi;
-        }
         LUP2_STAMP(1);
         cluster.sync();
         LUP2_STAMP(2);
         // ---- global pivot (every warp, redundantly), then the winner's row from the winner's slot -------------------
         key = lane < G ? cl_k[par * LUP_CL_MAX + lane] : 0ull;
         bi = lane < G ? cl_i[par * LUP_CL_MAX + lane] : -1;
+        const int my_i = bi;
         lup2_warp_argmax(key, bi);
         const int p = bi < 0 ? j : bi;   // a column of NaNs: keep the diagonal (the reference's imax stays at its previous value)
-        const int w = (p - a.k0) / a.rpc, wj = (j - a.k0) / a.rpc;
+        // the CTA that holds the pivot = the lane whose candidate won (positions are unique); no integer division per column
+        const unsigned holder = __ballot_sync(0xffffffffu, lane < G && my_i == bi);
+        const int w = bi < 0 ? wj : __ffs((int)holder) - 1;
         const bool own_p = (p >= r0 && p < r0 + nr);
         double pulled = 0.;
         if (tid < nb || tid == LU_NB || tid == LU_NB + 1) {
@@ -558,9 +565,21 @@ __global__ void __launch_bounds__(LUP2_T, 1) lu_panel_cl2_kernel(const LuPanelAr
         LUP2_STAMP(3);
         // the pivot row in the delayed columns: it has seen the blocks before this one, not this block's columns (< j) yet
         if (tid >= blkend && tid < nb) {
+            // all loads, then the chain of FMAs (the two warps that do this are the last to reach the next block barrier)
+            const int jb = jj - blk0;
+            double lb[LUP2_IB - 1], ub[LUP2_IB - 1];
+#pragma unroll
+            for (int b = 0; b < LUP2_IB - 1; ++b) {
+                if (b < jb) {
+                    lb[b] = s_piv[blk0 + b];
+                    ub[b] = s_U[b * LU_NB + tid];
+                }
+            }
             double u = pulled;
-            for (int b = 0; b < jj - blk0; ++b) u = fma(-s_piv[blk0 + b], s_U[b * LU_NB + tid], u);
-            s_U[(jj - blk0) * LU_NB + tid] = u;
+#pragma unroll
+            for (int b = 0; b < LUP2_IB - 1; ++b)
+                if (b < jb) u = fma(-lb[b], ub[b], u);
+            s_U[jb * LU_NB + tid] = u;
         }
         if (p != j && (own_j || own_p)) {   // whole-row interchange inside the panel (linalg.f90:254-263)
             if (own_j) {
@@ -679,10 +698,12 @@ __global__ void lu_perm_from_piv_kernel(const int* __restrict__ piv, int n, int*
 }
 
 // apply the panel's row interchanges to columns [c0, c1)
-__global__ void __launch_bounds__(256) lu_laswp_kernel(double* __restrict__ A, int ld, int c0, int c1, int k0, int k1,
+// columns [c0, c1) and [c2, c3) (the second range may be empty): left and right of a pair of panels in one launch
+__global__ void __launch_bounds__(256) lu_laswp_kernel(double* __restrict__ A, int ld, int c0, int c1, int c2, int c3, int k0, int k1,
                                                         const int* __restrict__ piv) {
-    const int c = c0 + blockIdx.x * 256 + threadIdx.x;
-    if (c >= c1) return;
+    const int idx = blockIdx.x * 256 + threadIdx.x, n1 = c1 - c0;   // c1 >= c0, c3 >= c2
+    const int c = idx < n1 ? c0 + idx : c2 + (idx - n1);
+    if (idx >= n1 && c >= c3) return;
     double* col = A + (size_t)c * ld;
     for (int j = k0; j < k1; ++j) {
         int p = piv[j];
@@ -1355,12 +1376,15 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
         ML_CUDA(c, cudaEventCreateWithFlags(&c->ev_la[1], cudaEventDisableTiming));
     }
     cudaStream_t S1 = lookahead ? c->stream_hi : S0;
-    auto laswp = [&](cudaStream_t st, int c0, int c1, int k0, int k1) {   // interchanges of panel [k0, k1) applied to columns [c0, c1)
-        if (c1 > c0) {
-            lu_laswp_kernel<<<(c1 - c0 + 255) / 256, 256, 0, st>>>(dA, ld, c0, c1, k0, k1, d_piv);
+    // interchanges of panel [k0, k1) applied to columns [c0, c1) and [c2, c3)
+    auto laswp2 = [&](cudaStream_t st, int c0, int c1, int c2, int c3, int k0, int k1) {
+        const int nc = std::max(0, c1 - c0) + std::max(0, c3 - c2);
+        if (nc > 0) {
+            lu_laswp_kernel<<<(nc + 255) / 256, 256, 0, st>>>(dA, ld, c0, std::max(c0, c1), c2, std::max(c2, c3), k0, k1, d_piv);
             c->launches += 1;
         }
     };
+    auto laswp = [&](cudaStream_t st, int c0, int c1, int k0, int k1) { laswp2(st, c0, c1, c1, c1, k0, k1); };
     auto trsm = [&](cudaStream_t st, int k0, int c0, int c1) {            // U(k0..k0+64, c0..c1) = L11^-1 A(k0..k0+64, c0..c1)
         if (c1 > c0) {
             lu_trsm_kernel<<<(c1 - c0 + TRSM_COLS_PER_CTA - 1) / TRSM_COLS_PER_CTA, TRSM_THREADS, 0, st>>>(dA + k0 + (size_t)k0 * ld, ld,
@@ -1401,10 +1425,8 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
             const int k1 = k0 + LU_NB, k2 = k1 + LU_NB;
             // (one fused launch for the four was tried, r5d / r5e: 0.7 ms less at N = 7.4k without interchanges, 9-13 ms more with
             // an interchange in every column)
-            laswp(S0, 0, k0, k0, k1);     // A's interchanges, left and right of the pair
-            laswp(S0, k2, n, k0, k1);
-            laswp(S0, 0, k1, k1, k2);     // B's: the left part includes A's own columns (its multipliers move with the rows)
-            laswp(S0, k2, n, k1, k2);
+            laswp2(S0, 0, k0, k2, n, k0, k1);     // A's interchanges, left and right of the pair in one launch
+            laswp2(S0, 0, k1, k2, n, k1, k2);     // B's: the left part includes A's own columns (its multipliers move with the rows)
             trsm(S0, k0, k2, n);                  // U rows of A
             gemm(S0, k1, k2, k2, n, k0, 1);       // rows of B's diagonal block: minus L21_A U_A
             trsm(S0, k1, k2, n);                  // U rows of B
@@ -1439,8 +1461,7 @@ static ml_status lu_factor(Ctx* c, double* dA, int ld, int n, int* d_piv, double
     }
     while (have_panel && k0 < n) {   // invariant: panel [k0, k0 + 64) is factored, nothing to its right has seen it yet
         const int k1 = std::min(k0 + LU_NB, n), k2 = std::min(k1 + LU_NB, n);
-        laswp(S0, 0, k0, k0, k1);
-        laswp(S0, k1, n, k0, k1);
+        laswp2(S0, 0, k0, k1, n, k0, k1);
         if (k1 < n) {
             trsm(S0, k0, k1, n);
             gemm(S0, k1, n, k1, n, k0, 1);
