@@ -71,7 +71,7 @@ def build_host(force: bool = False) -> Path:
     srcs = [CSRC / "host" / s for s in HOST_SOURCES]
     deps = srcs + list((CSRC / "host").glob("*.hpp")) + list(INCLUDE.glob("*.h"))
     if force or _newer(HOST_LIB, deps):
-        _run([GXX, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-Wall", "-Wextra",
+        _run([GXX, "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-Wall", "-Wextra",
               "-o", HOST_LIB, *srcs, "-lquadmath"])
     return HOST_LIB
 

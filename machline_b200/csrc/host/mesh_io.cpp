@@ -2,8 +2,12 @@
 // Cart3D-style .tri (src/tri.f90:13-102), with the reference's duplicate-vertex collapse
 // (src/stl.f90:120-236).  The all-pairs duplicate search is replaced by a spatial hash that
 // returns the same answer (first unique vertex within 1e-12 in file order) in O(N).
+#include <charconv>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
@@ -11,15 +15,25 @@
 #include <unordered_map>
 
 #include "model.hpp"
+#include "parallel.hpp"
 
 namespace mlh {
 
 std::string read_text_file(const std::string& path) {
-    std::ifstream f(path, std::ios::binary);
+    std::FILE* f = std::fopen(path.c_str(), "rb");
     if (!f) throw std::runtime_error("cannot open file " + path);
-    std::stringstream ss;
-    ss << f.rdbuf();
-    return ss.str();
+    std::string text;
+    if (std::fseek(f, 0, SEEK_END) == 0) {
+        const long sz = std::ftell(f);
+        std::rewind(f);
+        if (sz > 0) {
+            text.resize((size_t)sz);
+            const size_t got = std::fread(&text[0], 1, (size_t)sz, f);
+            text.resize(got);
+        }
+    }
+    std::fclose(f);
+    return text;
 }
 
 namespace {
@@ -38,32 +52,65 @@ struct CellHash {
 };
 
 // stl.f90:120-236.  vertex_locs in file order -> unique vertices + new_ind (0-based).
+// The reference compares every vertex with every earlier unique one (O(N^2)): a vertex is a duplicate of the FIRST earlier
+// unique vertex within 1e-12.  Here the unique vertices sit in a spatial hash of cell size 1e-6 (flat open addressing, one chain
+// per cell); a vertex within 1e-12 of another lies in the same cell or, only if it is within 1e-12 of a cell face, in the
+// neighbour across that face -- so one cell is searched as a rule (27 in the first version of this routine).
 void collapse_duplicate_vertices(const std::vector<V3>& vertex_locs, std::vector<Vertex>& vertices,
                                  std::vector<int>& new_ind) {
     const int N = (int)vertex_locs.size();
     std::vector<char> is_duplicate(N, 0);
     std::vector<int> duplicate_of(N);
-    const double h = 1e-6;  // cell size >> tolerance; neighbours cover straddling
-    std::unordered_map<CellKey, std::vector<int>, CellHash> grid;
-    grid.reserve((size_t)N * 2);
+    const double h = 1e-6, tol = 1.e-12;
+    size_t cap = 16;
+    while (cap < (size_t)N * 2 + 16) cap <<= 1;
+    std::vector<int> head(cap, -1);           // slot -> first unique vertex of the cell stored there
+    std::vector<CellKey> slot_key(cap);
+    std::vector<int> next(N, -1);             // chain of the unique vertices of one cell
+    CellHash hasher;
+    auto find_slot = [&](const CellKey& k, bool insert) -> long {
+        size_t s = hasher(k) & (cap - 1);
+        for (;;) {
+            if (head[s] < 0) {
+                if (!insert) return -1;
+                slot_key[s] = k;
+                return (long)s;
+            }
+            if (slot_key[s] == k) return (long)s;
+            s = (s + 1) & (cap - 1);
+        }
+    };
     for (int j = 0; j < N; ++j) {
         duplicate_of[j] = j;
         const V3& p = vertex_locs[j];
-        CellKey c{(int64_t)std::floor(p[0] / h), (int64_t)std::floor(p[1] / h), (int64_t)std::floor(p[2] / h)};
+        const double q[3] = {p[0] / h, p[1] / h, p[2] / h};
+        const double fl[3] = {std::floor(q[0]), std::floor(q[1]), std::floor(q[2])};
+        const CellKey c{(int64_t)fl[0], (int64_t)fl[1], (int64_t)fl[2]};
+        // which neighbours can hold a point within tol: only across a face the vertex (almost) touches; the margin is a
+        // generous multiple of tol / h so that rounding of p / h cannot hide a neighbour
+        int64_t lo[3], hi[3];
+        for (int d = 0; d < 3; ++d) {
+            const double fr = q[d] - fl[d], margin = 1e-3;   // tol / h = 1e-6
+            lo[d] = fr < margin ? -1 : 0;
+            hi[d] = fr > 1. - margin ? 1 : 0;
+        }
         int best = -1;
-        for (int64_t dx = -1; dx <= 1; ++dx)
-            for (int64_t dy = -1; dy <= 1; ++dy)
-                for (int64_t dz = -1; dz <= 1; ++dz) {
-                    auto it = grid.find(CellKey{c.x + dx, c.y + dy, c.z + dz});
-                    if (it == grid.end()) continue;
-                    for (int i : it->second)
-                        if (dist(vertex_locs[i], p) < 1.e-12 && (best < 0 || i < best)) best = i;
+        for (int64_t dx = lo[0]; dx <= hi[0]; ++dx)
+            for (int64_t dy = lo[1]; dy <= hi[1]; ++dy)
+                for (int64_t dz = lo[2]; dz <= hi[2]; ++dz) {
+                    const long s = find_slot(CellKey{c.x + dx, c.y + dy, c.z + dz}, false);
+                    if (s < 0) continue;
+                    for (int i = head[s]; i >= 0; i = next[i])
+                        if (dist(vertex_locs[i], p) < tol && (best < 0 || i < best)) best = i;
                 }
         if (best >= 0) {
             is_duplicate[j] = 1;
             duplicate_of[j] = best;
         } else {
-            grid[c].push_back(j);  // only unique vertices are candidates (stl.f90:146,152)
+            // only unique vertices are candidates (stl.f90:146,152); appended at the head of its cell's chain
+            const long s = find_slot(c, true);
+            next[j] = head[s];
+            head[s] = j;
         }
     }
     new_ind.assign(N, 0);
@@ -165,36 +212,82 @@ void load_vtk(const std::string& text, std::vector<Vertex>& vertices, std::vecto
     }
 }
 
-void load_stl(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {
-    // ASCII STL (stl.f90:14-117): every line whose first word is "vertex" carries one corner.  Scanned in place (the
-    // coordinates go through the same strtod as before: identical doubles), without a stream or a token vector per line.
-    const char* p = text.c_str();
-    const char* const end = p + text.size();
-    while (p < end && *p != '\n') ++p;   // header line
-    std::vector<V3> locs;
-    locs.reserve(text.size() / 60);
-    while (p < end) {
-        while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
-        if (end - p > 6 && std::memcmp(p, "vertex", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
-            p += 6;
-            char* q = nullptr;
-            V3 v;
-            v[0] = std::strtod(p, &q);
-            p = q;
-            v[1] = std::strtod(p, &q);
-            p = q;
-            v[2] = std::strtod(p, &q);
-            p = q;
-            locs.push_back(v);
-        }
-        while (p < end && *p != '\n') ++p;
+// One decimal number at p (leading blanks skipped): std::from_chars is correctly rounded like strtod -- the same double for the
+// same text -- at a fifth of the time; anything it does not take (a leading '+', "inf", ...) goes through strtod.
+static inline double scan_double(const char*& p, const char* end) {
+    while (p < end && (*p == ' ' || *p == '\t')) ++p;
+    double x = 0.;
+    const auto r = std::from_chars(p, end, x);
+    if (r.ec == std::errc() && r.ptr != p) {
+        p = r.ptr;
+        return x;
     }
+    char* q = nullptr;
+    x = std::strtod(p, &q);
+    p = q;
+    return x;
+}
+
+void load_stl(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {
+    // ASCII STL (stl.f90:14-117): every line whose first word is "vertex" carries one corner.  Scanned in place, in chunks of
+    // whole lines on the host threads (parallel.hpp); the chunks' corners are concatenated in file order.
+    const char* const begin = text.c_str();
+    const char* const end = begin + text.size();
+    const char* p0 = begin;
+    while (p0 < end && *p0 != '\n') ++p0;   // header line
+    const int nt = std::max(1, std::min(host_threads(), (int)((end - p0) / (256 * 1024)) + 1));
+    std::vector<const char*> cut(nt + 1);
+    cut[0] = p0;
+    cut[nt] = end;
+    for (int t = 1; t < nt; ++t) {
+        const char* c = p0 + (size_t)(end - p0) * t / nt;
+        if (c < cut[t - 1]) c = cut[t - 1];
+        while (c < end && *c != '\n') ++c;   // a chunk starts at the end of a line
+        cut[t] = c;
+    }
+    std::vector<std::vector<V3>> part(nt);
+    parallel_for(nt, [&](int t) {
+        const char* p = cut[t];
+        const char* const stop = cut[t + 1];
+        std::vector<V3>& locs = part[t];
+        locs.reserve((size_t)(stop - p) / 60 + 16);
+        while (p < stop) {
+            while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
+            if (p >= stop) break;   // the line starting here belongs to the next chunk
+            if (end - p > 6 && std::memcmp(p, "vertex", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
+                p += 6;
+                V3 v;
+                v[0] = scan_double(p, end);
+                v[1] = scan_double(p, end);
+                v[2] = scan_double(p, end);
+                locs.push_back(v);
+            }
+            while (p < end && *p != '\n') ++p;
+        }
+    }, 1);
+    const bool timing = std::getenv("MLH_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "mlh load_stl: %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
+    std::vector<V3> locs;
+    size_t total = 0;
+    for (const auto& v : part) total += v.size();
+    locs.reserve(total);
+    for (const auto& v : part) locs.insert(locs.end(), v.begin(), v.end());
     int N_panels = (int)locs.size() / 3;
     std::vector<int> new_ind;
+    lap("concatenate");
     collapse_duplicate_vertices(locs, vertices, new_ind);
+    lap("collapse_duplicates");
     panels.assign(N_panels, Panel());
-    for (int i = 0; i < N_panels; ++i)
+    lap("panels.assign");
+    for (int i = 0; i < N_panels; ++i)   // serial: a panel registers itself with its vertices, in panel order
         panel_init(panels[i], vertices, new_ind[3 * i], new_ind[3 * i + 1], new_ind[3 * i + 2], i, false);
+    lap("panel_init");
 }
 
 void load_tri(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {

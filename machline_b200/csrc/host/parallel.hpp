@@ -1,0 +1,53 @@
+// Host-side parallel loops of the setup (the per-panel and per-vertex precompute is embarrassingly
+// parallel; every iteration writes only its own panel / vertex, so the results do not depend on the thread count).
+// Plain std::thread: the host library links nothing but libstdc++ / libquadmath.  MLH_THREADS overrides the thread count
+// (1 = serial, as before).
+#pragma once
+#include <algorithm>
+#include <cstdlib>
+#include <exception>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+namespace mlh {
+
+inline int host_threads() {
+    static const int n = [] {
+        if (const char* e = std::getenv("MLH_THREADS")) return std::max(1, std::atoi(e));
+        const unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::min(16u, std::max(1u, hw));
+    }();
+    return n;
+}
+
+// f(i) for i in [0, n), in contiguous chunks; the first exception thrown by any chunk is rethrown on the caller
+template <class F>
+void parallel_for(int n, F f, int min_per_thread = 128) {
+    int nt = std::min(host_threads(), n / std::max(1, min_per_thread));
+    if (nt <= 1) {
+        for (int i = 0; i < n; ++i) f(i);
+        return;
+    }
+    const int chunk = (n + nt - 1) / nt;
+    std::exception_ptr err;
+    std::mutex m;
+    std::vector<std::thread> th;
+    th.reserve(nt);
+    for (int t = 0; t < nt; ++t) {
+        const int a = t * chunk, b = std::min(n, a + chunk);
+        if (a >= b) break;
+        th.emplace_back([&, a, b] {
+            try {
+                for (int i = a; i < b; ++i) f(i);
+            } catch (...) {
+                std::lock_guard<std::mutex> g(m);
+                if (!err) err = std::current_exception();
+            }
+        });
+    }
+    for (auto& x : th) x.join();
+    if (err) std::rethrow_exception(err);
+}
+
+}  // namespace mlh

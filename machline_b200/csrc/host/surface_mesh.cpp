@@ -11,6 +11,7 @@
 #include <stdexcept>
 
 #include "model.hpp"
+#include "parallel.hpp"
 
 namespace mlh {
 
@@ -253,7 +254,7 @@ void Case::locate_adjacent_panels() {
 
 // surface_mesh.f90:610-659, base_geom.f90:163-214
 void Case::calc_vertex_geometry() {
-    for (int i = 0; i < N_verts; ++i) {
+    parallel_for(N_verts, [&](int i) {   // binary128 sums per vertex (the reference's real(16)); every vertex writes only itself
         Vertex& v = vertices[i];
         quad n_avg[3] = {0, 0, 0};
         for (int j_panel : v.panels) {
@@ -282,12 +283,12 @@ void Case::calc_vertex_geometry() {
         }
         if (N > 0) v.l_avg = v.l_avg / N;
         else v.l_avg = 1.;
-    }
+    });
 }
 
 // surface_mesh.f90:759-801
 void Case::init_panels_with_flow() {
-    for (auto& p : panels) panel_init_with_flow(p, vertices, freestream, mirrored, mirror_plane);
+    parallel_for((int)panels.size(), [&](int i) { panel_init_with_flow(panels[i], vertices, freestream, mirrored, mirror_plane); });
     N_subinc = N_supinc = 0;
     for (auto& p : panels) {
         if (p.r > 0) ++N_subinc; else ++N_supinc;
@@ -540,20 +541,36 @@ void Case::init_with_flow() {
 
     asym_flow = false;
     if (mirrored && !freestream.sym_about[mirror_plane - 1]) asym_flow = true;
+    const bool timing = std::getenv("MLH_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "mlh init_with_flow: %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     init_panels_with_flow();
+    lap("init_panels_with_flow");
     characterize_edges();
+    lap("characterize_edges");
     if (wake_present) {
         set_needed_vertex_clones();
         clone_vertices();
     }
+    lap("clone_vertices");
     if (!found_wake_edges) {
         vertex_ordering.resize(N_verts);
         for (int i = 0; i < N_verts; ++i) vertex_ordering[i] = i;
     }
     for (int i = 0; i < N_verts; ++i) vertices[i].convex = is_convex_at_vertex(i);
+    lap("is_convex_at_vertex");
     init_wake();
-    for (auto& p : panels)
-        panel_set_distribution(p, initial_panel_order, panels, vertices, vertices, mirrored, mirror_plane, force_sigma_match);
+    lap("init_wake");
+    // reads the neighbours' vertex indices (fixed by now), writes the panel itself
+    parallel_for((int)panels.size(), [&](int i) {
+        panel_set_distribution(panels[i], initial_panel_order, panels, vertices, vertices, mirrored, mirror_plane, force_sigma_match);
+    });
+    lap("panel_set_distribution");
 }
 
 }  // namespace mlh
