@@ -10,6 +10,7 @@
 
 #include "../../../include/machline_host.h"
 #include "model.hpp"
+#include "parallel.hpp"
 
 using namespace mlh;
 
@@ -41,17 +42,27 @@ struct PanelTableStore {
         n_cols = ncols;
         in_wake = wake;
         size_t n_rec = (size_t)np * ni;
-        centr.assign(n_rec * 3, 0.);
-        A_g_to_ls.assign(n_rec * 9, 0.);
-        vertices_ls.assign(n_rec * 6, 0.);
-        n_hat_ls.assign(n_rec * 6, 0.);
-        b.assign(n_rec * 3, 0.);
-        sqrt_b.assign(n_rec * 3, 0.);
-        J.assign(n_rec, 0.);
+        // zero-filled tables; the fresh pages of the large ones (220 MB at 280k panels x 2 images) are first touched on the host
+        // threads (as mesh_io.cpp: fresh_panels), the fill itself then runs on mapped memory
+        auto zeros = [](std::vector<double>& v, size_t n) {
+            v.clear();
+            v.reserve(n);
+            char* const raw = reinterpret_cast<char*>(v.data());
+            const size_t page = 4096, n_pages = (n * sizeof(double) + page - 1) / page;
+            if (raw && n_pages > 64) parallel_for((int)n_pages, [&](int k) { raw[(size_t)k * page] = 0; }, 2048);
+            v.assign(n, 0.);
+        };
+        zeros(centr, n_rec * 3);
+        zeros(A_g_to_ls, n_rec * 9);
+        zeros(vertices_ls, n_rec * 6);
+        zeros(n_hat_ls, n_rec * 6);
+        zeros(b, n_rec * 3);
+        zeros(sqrt_b, n_rec * 3);
+        zeros(J, n_rec);
         r.assign(n_rec, 1);
-        area.assign(np, 0.);
-        vert_g.assign(n_rec * 9, 0.);
-        T_mu.assign(n_rec * 9, 0.);
+        zeros(area, np);
+        zeros(vert_g, n_rec * 9);
+        zeros(T_mu, n_rec * 9);
         i_vert_d.assign((size_t)np * ncols, -1);
         i_panel_s.assign(np, -1);
         has_sources.assign(np, 0);
@@ -222,7 +233,7 @@ static void build_tables(mlh_case* h) {
     bool ho = false;
     for (auto& p : c.panels) ho = ho || p.order == 2;
     h->body.reserve_for(c.N_panels, c.mirrored ? 2 : 1, ho ? 6 : 3, 0, ho ? 1 : 0);
-    for (int j = 0; j < c.N_panels; ++j) h->body.put(j, c.panels[j], c.vertices, c.mirrored, c.mirror_plane);
+    parallel_for(c.N_panels, [&](int j) { h->body.put(j, c.panels[j], c.vertices, c.mirrored, c.mirror_plane); });   // record j only
     // wake: strips flattened in (strip, panel) order, the order of panel_solver.f90:1656-1657
     int nw = c.wake.N_panels;
     bool any_mir = false;

@@ -136,80 +136,48 @@ std::vector<std::string> split_ws(const std::string& line) {
     return out;
 }
 
-void load_vtk(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {
-    // Legacy ASCII VTK (vtk.f90:440-640).  The numbers are scanned in place with strtod / strtol (same conversions as a
-    // stream would apply, no per-token strings); the few header lines go through a line reader.
-    const char* p = text.c_str();
-    const char* const end = p + text.size();
-    auto next_line = [&]() -> std::string {
-        const char* b = p;
-        while (p < end && *p != '\n') ++p;
-        std::string l(b, p);
-        if (p < end) ++p;
-        return l;
-    };
-    std::string line = next_line();
-    size_t ind = line.find("Version");
-    if (ind == std::string::npos) throw std::runtime_error("VTK header has no Version");
-    int ver = line[ind + 8] - '0';
-    if (ver != 3 && ver != 5) throw std::runtime_error("VTK file version not recognized");
-    for (int k = 0; k < 3; ++k) next_line();  // 3 more header lines
-    line = next_line();                       // POINTS n float
-    auto w = split_ws(line);
-    if (w.size() < 2) throw std::runtime_error("VTK: POINTS line not found");
-    const int N_verts = std::atoi(w[1].c_str());
-    std::vector<V3> locs(N_verts);
-    for (int i = 0; i < N_verts; ++i)
-        for (int k = 0; k < 3; ++k) {
-            char* q = nullptr;
-            locs[i][k] = std::strtod(p, &q);
-            if (q == p) throw std::runtime_error("VTK: truncated POINTS section");
-            p = q;
-        }
-    std::vector<int> new_ind;
-    collapse_duplicate_vertices(locs, vertices, new_ind);
-    next_line();  // rest of last coordinate line
-    auto next_int = [&]() -> long {
-        char* q = nullptr;
-        const long v = std::strtol(p, &q, 10);
-        if (q == p) throw std::runtime_error("VTK: truncated connectivity");
-        p = q;
-        return v;
-    };
-    auto index = [&](long i) -> int {
-        if (i < 0 || i >= N_verts) throw std::runtime_error("VTK: vertex index out of range");
-        return new_ind[i];
-    };
-    if (ver == 3) {
-        do {
-            if (p >= end) throw std::runtime_error("VTK: POLYGONS not found");
-            line = next_line();
-        } while (line.find("POLYGONS") == std::string::npos);
-        w = split_ws(line);
-        int N_panels = std::atoi(w.at(1).c_str());
-        panels.assign(N_panels, Panel());
-        for (int i = 0; i < N_panels; ++i) {
-            if (next_int() != 3) throw std::runtime_error("MachLine supports only triangular panels.");
-            const int i1 = index(next_int()), i2 = index(next_int()), i3 = index(next_int());
-            panel_init(panels[i], vertices, i1, i2, i3, i, false);
-        }
-    } else {
-        do {
-            if (p >= end) throw std::runtime_error("VTK: POLYGONS/CELLS not found");
-            line = next_line();
-        } while (line.find("POLYGONS") == std::string::npos && line.find("CELLS") == std::string::npos);
-        w = split_ws(line);
-        int N_panels = std::atoi(w.at(1).c_str()) - 1;
-        panels.assign(N_panels, Panel());
-        do {
-            if (p >= end) throw std::runtime_error("VTK: CONNECTIVITY not found");
-            line = next_line();
-        } while (line.find("CONNECTIVITY") == std::string::npos);
-        for (int idx = 0; idx < N_panels; ++idx) {
-            const int i1 = index(next_int()), i2 = index(next_int()), i3 = index(next_int());
-            panel_init(panels[idx], vertices, i1, i2, i3, idx, false);
-        }
-    }
+// N default-constructed panels.  A Panel is 1.4 KB: at 280k panels the storage is 400 MB of fresh pages, and their first touch
+// (one page fault per 4 KB, in the kernel) costs more than the construction itself -- so the pages are touched on the host threads
+// first (writes of zero into the reserved, not yet constructed storage), then the panels are constructed in place, serially, on
+// memory that is already mapped.  The vertices' panel lists get room for the usual valence at the same time.
+static void fresh_panels(std::vector<Panel>& panels, int N_panels, std::vector<Vertex>& vertices) {
+    panels.clear();
+    panels.reserve((size_t)N_panels);
+    char* const raw = reinterpret_cast<char*>(panels.data());
+    const size_t bytes = (size_t)N_panels * sizeof(Panel), page = 4096;
+    const int n_pages = (int)((bytes + page - 1) / page);
+    if (raw) parallel_for(n_pages, [&](int k) { raw[(size_t)k * page] = 0; }, 2048);
+    panels.resize((size_t)N_panels);
+    (void)vertices;
+}
+
+// What panel_init does for the triangles tri[3 i .. 3 i + 2] (unique-vertex indices), i = 0 .. N - 1, on freshly constructed panels:
+// every panel gets its vertex indices and its geometry (host threads: a panel writes itself), and every vertex the list of the
+// panels that use it -- in panel order, as the push_backs of a serial loop over the panels leave it -- built by a counting
+// sort over the incidences (streaming passes instead of 3 N appends to N_verts little heap arrays).
+static void register_triangles(std::vector<Panel>& panels, std::vector<Vertex>& vertices, const std::vector<int>& tri) {
+    const int N = (int)panels.size(), V = (int)vertices.size();
+    parallel_for(N, [&](int i) {
+        Panel& p = panels[i];
+        p.N = 3;
+        p.iv[0] = tri[3 * (size_t)i];
+        p.iv[1] = tri[3 * (size_t)i + 1];
+        p.iv[2] = tri[3 * (size_t)i + 2];
+        p.index = i;
+        p.in_wake = false;
+        p.has_sources = true;
+        panel_calc_derived_geom(p, vertices);
+    });
+    std::vector<int> start((size_t)V + 1, 0);
+    for (size_t k = 0; k < tri.size(); ++k) ++start[(size_t)tri[k] + 1];
+    for (int v = 0; v < V; ++v) start[v + 1] += start[v];
+    std::vector<int> fill(start.begin(), start.end() - 1), inc(tri.size());
+    for (int i = 0; i < N; ++i)
+        for (int m = 0; m < 3; ++m) inc[fill[tri[3 * (size_t)i + m]]++] = i;
+    parallel_for(V, [&](int v) {
+        vertices[v].panels.assign(inc.begin() + start[v], inc.begin() + start[v + 1]);
+        vertices[v].panels_not_across_wake_edge = vertices[v].panels;
+    }, 2048);
 }
 
 // One decimal number at p (leading blanks skipped): std::from_chars is correctly rounded like strtod -- the same double for the
@@ -226,6 +194,97 @@ static inline double scan_double(const char*& p, const char* end) {
     x = std::strtod(p, &q);
     p = q;
     return x;
+}
+
+void load_vtk(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {
+    // Legacy ASCII VTK (vtk.f90:440-640).  The numbers are scanned in place with strtod / strtol (same conversions as a
+    // stream would apply, no per-token strings); the few header lines go through a line reader.
+    const char* p = text.c_str();
+    const char* const end = p + text.size();
+    auto next_line = [&]() -> std::string {
+        const char* b = p;
+        while (p < end && *p != '\n') ++p;
+        std::string l(b, p);
+        if (p < end) ++p;
+        return l;
+    };
+    const bool timing = std::getenv("MLH_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "mlh load_vtk: %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
+    std::string line = next_line();
+    size_t ind = line.find("Version");
+    if (ind == std::string::npos) throw std::runtime_error("VTK header has no Version");
+    int ver = line[ind + 8] - '0';
+    if (ver != 3 && ver != 5) throw std::runtime_error("VTK file version not recognized");
+    for (int k = 0; k < 3; ++k) next_line();  // 3 more header lines
+    line = next_line();                       // POINTS n float
+    auto w = split_ws(line);
+    if (w.size() < 2) throw std::runtime_error("VTK: POINTS line not found");
+    const int N_verts = std::atoi(w[1].c_str());
+    std::vector<V3> locs(N_verts);
+    for (int i = 0; i < N_verts; ++i)
+        for (int k = 0; k < 3; ++k) {
+            while (p < end && (*p == ' ' || *p == '\t' || *p == '\r' || *p == '\n')) ++p;
+            const char* const before = p;
+            locs[i][k] = scan_double(p, end);
+            if (p == before) throw std::runtime_error("VTK: truncated POINTS section");
+        }
+    lap("points");
+    std::vector<int> new_ind;
+    collapse_duplicate_vertices(locs, vertices, new_ind);
+    lap("collapse_duplicates");
+    next_line();  // rest of last coordinate line
+    auto next_int = [&]() -> long {
+        char* q = nullptr;
+        const long v = std::strtol(p, &q, 10);
+        if (q == p) throw std::runtime_error("VTK: truncated connectivity");
+        p = q;
+        return v;
+    };
+    auto index = [&](long i) -> int {
+        if (i < 0 || i >= N_verts) throw std::runtime_error("VTK: vertex index out of range");
+        return new_ind[i];
+    };
+    std::vector<int> tri;
+    if (ver == 3) {
+        do {
+            if (p >= end) throw std::runtime_error("VTK: POLYGONS not found");
+            line = next_line();
+        } while (line.find("POLYGONS") == std::string::npos);
+        w = split_ws(line);
+        int N_panels = std::atoi(w.at(1).c_str());
+        fresh_panels(panels, N_panels, vertices);
+        lap("fresh_panels");
+        tri.resize((size_t)3 * N_panels);
+        for (int i = 0; i < N_panels; ++i) {
+            if (next_int() != 3) throw std::runtime_error("MachLine supports only triangular panels.");
+            for (int m = 0; m < 3; ++m) tri[3 * (size_t)i + m] = index(next_int());
+        }
+    } else {
+        do {
+            if (p >= end) throw std::runtime_error("VTK: POLYGONS/CELLS not found");
+            line = next_line();
+        } while (line.find("POLYGONS") == std::string::npos && line.find("CELLS") == std::string::npos);
+        w = split_ws(line);
+        int N_panels = std::atoi(w.at(1).c_str()) - 1;
+        fresh_panels(panels, N_panels, vertices);
+        lap("panels.assign");
+        do {
+            if (p >= end) throw std::runtime_error("VTK: CONNECTIVITY not found");
+            line = next_line();
+        } while (line.find("CONNECTIVITY") == std::string::npos);
+        tri.resize((size_t)3 * N_panels);
+        for (int idx = 0; idx < N_panels; ++idx)
+            for (int m = 0; m < 3; ++m) tri[3 * (size_t)idx + m] = index(next_int());
+    }
+    lap("connectivity");
+    register_triangles(panels, vertices, tri);
+    lap("register_triangles");
 }
 
 void load_stl(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {
@@ -283,11 +342,11 @@ void load_stl(const std::string& text, std::vector<Vertex>& vertices, std::vecto
     lap("concatenate");
     collapse_duplicate_vertices(locs, vertices, new_ind);
     lap("collapse_duplicates");
-    panels.assign(N_panels, Panel());
+    fresh_panels(panels, N_panels, vertices);
     lap("panels.assign");
-    for (int i = 0; i < N_panels; ++i)   // serial: a panel registers itself with its vertices, in panel order
-        panel_init(panels[i], vertices, new_ind[3 * i], new_ind[3 * i + 1], new_ind[3 * i + 2], i, false);
-    lap("panel_init");
+    new_ind.resize((size_t)3 * N_panels);   // corner k of facet i is file vertex 3 i + k
+    register_triangles(panels, vertices, new_ind);
+    lap("register_triangles");
 }
 
 void load_tri(const std::string& text, std::vector<Vertex>& vertices, std::vector<Panel>& panels) {
@@ -306,7 +365,7 @@ void load_tri(const std::string& text, std::vector<Vertex>& vertices, std::vecto
     }
     std::vector<int> new_ind;
     collapse_duplicate_vertices(locs, vertices, new_ind);
-    panels.assign(N_panels, Panel());
+    fresh_panels(panels, N_panels, vertices);
     for (int i = 0; i < N_panels; ++i) {
         int i1, i2, i3;
         in >> i1 >> i2 >> i3;

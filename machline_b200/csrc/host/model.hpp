@@ -238,6 +238,7 @@ struct Case {
 
 // panel-level procedures (src/panel.f90); `verts` is the vertex array the panel indexes into.
 void panel_init(Panel& p, std::vector<Vertex>& verts, int i1, int i2, int i3, int index, bool in_wake);
+void panel_init_topology(Panel& p, std::vector<Vertex>& verts, int i1, int i2, int i3, int index, bool in_wake, bool reset);   // panel_init without the geometry
 void panel_calc_derived_geom(Panel& p, const std::vector<Vertex>& verts);
 void panel_init_with_flow(Panel& p, const std::vector<Vertex>& verts, const Flow& fs, bool mirrored, int mirror_plane);
 void panel_set_distribution(Panel& p, int order, const std::vector<Panel>& body_panels,

@@ -40,8 +40,9 @@ void panel_calc_derived_geom(Panel& p, const std::vector<Vertex>& verts) {
 }
 
 // panel.f90:188-237
-void panel_init(Panel& p, std::vector<Vertex>& verts, int i1, int i2, int i3, int index, bool in_wake) {
-    p = Panel();
+// the part of panel_init that touches shared state: the panel registers itself with its vertices (in panel order: serial)
+void panel_init_topology(Panel& p, std::vector<Vertex>& verts, int i1, int i2, int i3, int index, bool in_wake, bool reset) {
+    if (reset) p = Panel();   // false: a freshly constructed panel (the mesh loaders: 1.4 KB per panel not written twice)
     p.N = 3;
     p.iv[0] = i1;
     p.iv[1] = i2;
@@ -53,6 +54,10 @@ void panel_init(Panel& p, std::vector<Vertex>& verts, int i1, int i2, int i3, in
     }
     p.in_wake = in_wake;
     p.has_sources = !in_wake;
+}
+
+void panel_init(Panel& p, std::vector<Vertex>& verts, int i1, int i2, int i3, int index, bool in_wake) {
+    panel_init_topology(p, verts, i1, i2, i3, index, in_wake, true);
     panel_calc_derived_geom(p, verts);
 }
 

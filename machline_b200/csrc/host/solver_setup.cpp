@@ -12,6 +12,7 @@
 #include <stdexcept>
 
 #include "model.hpp"
+#include "parallel.hpp"
 
 namespace mlh {
 
@@ -204,7 +205,7 @@ bool Case::control_point_outside_mesh(const V3& cp_loc, int i_vert) const {
 void Case::place_internal_vertex_control_points(double offset, const std::string& offset_type) {
     N_cp = asym_flow ? N_verts * 2 : N_verts;
     cp.assign(N_cp, ControlPoint());
-    for (int i = 0; i < N_verts; ++i) {
+    parallel_for(N_verts, [&](int i) {   // reads the mesh, writes cp[i]
         const Vertex& v = vertices[i];
         V3 dir = v.clone ? get_clone_control_point_dir(i) : -v.n_g;
         double this_offset = (offset_type == "local") ? offset * v.l_avg : offset;
@@ -231,7 +232,7 @@ void Case::place_internal_vertex_control_points(double offset, const std::string
         cp[i].tied_to_type = TT_VERTEX;
         cp[i].tied_to_index = i;
         cp[i].is_mirror = false;
-    }
+    });
     if (asym_flow) {
         for (int i = 0; i < N_cp / 2; ++i) {
             ControlPoint& m = cp[i + N_cp / 2];

@@ -189,10 +189,17 @@ void Case::locate_adjacent_panels() {
     auto all_found = [&](const Panel& p) {
         return p.abutting_panels[0] != -1 && p.abutting_panels[1] != -1 && p.abutting_panels[2] != -1;
     };
-    std::vector<int> cand;
-    for (int i = 0; i < N_panels; ++i) {
-        // candidates j > i sharing at least two vertex indices with i, ascending
+    // Pass 1 (host threads; reads only): for every panel the panels j > i that share at least two vertex indices with it,
+    // ascending -- up to NB_MAX of them in a flat table (a manifold triangle has at most three neighbours; a panel with more
+    // candidates, e.g. at a non-manifold edge, is flagged and searched again in pass 2).
+    // Pass 2 (serial, in panel order as the reference's loop, surface_mesh.f90:346-496): the adjacency checks, which write both
+    // panels and number the edges in the order of discovery.
+    constexpr int NB_MAX = 4;
+    std::vector<int> nb((size_t)N_panels * NB_MAX);
+    std::vector<unsigned char> nb_n(N_panels, 0);
+    auto candidates_of = [&](int i, std::vector<int>& cand, std::vector<int>& out) {
         cand.clear();
+        out.clear();
         for (int m = 0; m < 3; ++m)
             for (int j : vertices[panels[i].iv[m]].panels)
                 if (j > i) cand.push_back(j);
@@ -200,10 +207,42 @@ void Case::locate_adjacent_panels() {
         for (size_t c = 0; c < cand.size();) {
             size_t e = c;
             while (e < cand.size() && cand[e] == cand[c]) ++e;
-            int j = cand[c];
-            size_t shared = e - c;
+            if (e - c >= 2) out.push_back(cand[c]);
             c = e;
-            if (shared < 2) continue;
+        }
+    };
+    {
+        const int nt = std::max(1, host_threads());
+        std::vector<std::vector<int>> scratch_a(nt), scratch_b(nt);
+        const int chunk = (N_panels + nt - 1) / nt;
+        parallel_for(nt, [&](int t) {
+            std::vector<int>&cand = scratch_a[t], &out = scratch_b[t];
+            for (int i = t * chunk; i < std::min(N_panels, (t + 1) * chunk); ++i) {
+                candidates_of(i, cand, out);
+                if ((int)out.size() > NB_MAX) {
+                    nb_n[i] = 255;
+                } else {
+                    nb_n[i] = (unsigned char)out.size();
+                    for (size_t k = 0; k < out.size(); ++k) nb[(size_t)i * NB_MAX + k] = out[k];
+                }
+            }
+        }, 1);
+        parallel_for(N_verts, [&](int i) {   // room for the usual valence: the lists below grow by push_back
+            vertices[i].adjacent_vertices.reserve(8);
+            vertices[i].adjacent_edges.reserve(8);
+        }, 2048);
+    }
+    std::vector<int> cand, over;
+    for (int i = 0; i < N_panels; ++i) {
+        const int* list = nb.data() + (size_t)i * NB_MAX;
+        int n_list = nb_n[i];
+        if (n_list == 255) {
+            candidates_of(i, cand, over);
+            list = over.data();
+            n_list = (int)over.size();
+        }
+        for (int k = 0; k < n_list; ++k) {
+            const int j = list[k];
             if (all_found(panels[i])) break;  // surface_mesh.f90:373
             int ep[2], ei, ej;
             if (check_panels_adjacent(panels, i, j, ep, ei, ej)) {
@@ -562,7 +601,7 @@ void Case::init_with_flow() {
         vertex_ordering.resize(N_verts);
         for (int i = 0; i < N_verts; ++i) vertex_ordering[i] = i;
     }
-    for (int i = 0; i < N_verts; ++i) vertices[i].convex = is_convex_at_vertex(i);
+    parallel_for(N_verts, [&](int i) { vertices[i].convex = is_convex_at_vertex(i); });   // const test, own flag
     lap("is_convex_at_vertex");
     init_wake();
     lap("init_wake");
