@@ -593,7 +593,7 @@ Results Case::post(const std::vector<double>& x, const double* v_inner) const {
     R.N_cells = asym_flow ? 2 * N_panels : N_panels;
     R.V_cells.assign(R.N_cells, V3{});
     R.V_cells_inner.assign(R.N_cells, V3{});
-    for (int i = 0; i < N_panels; ++i) {  // calc_cell_velocities :2030-2095
+    parallel_for(N_panels, [&](int i) {  // calc_cell_velocities :2030-2095 (a panel writes its own cells)
         R.V_cells_inner[i] = inner_flow * fs.U;
         if (!solver.dirichlet) R.V_cells_inner[i] = fs.v_inf + fs.U * V3{v_inner[3 * i], v_inner[3 * i + 1], v_inner[3 * i + 2]};
         V3 dv = panel_get_velocity_jump(panels[i], *this, R.mu, R.sigma, false);
@@ -607,7 +607,7 @@ Results Case::post(const std::vector<double>& x, const double* v_inner) const {
             V3 dvm = panel_get_velocity_jump(panels[i], *this, R.mu, R.sigma, true);
             R.V_cells[i + N_panels] = fs.U * ((R.V_cells_inner[i + N_panels] / fs.U) + dvm);
         }
-    }
+    }, 1024);
     // calc_pressures :2218-2321; the lower-order average pressure is the rule applied to the
     // centroid velocity (panel.f90:3638-3649), i.e. to V_cells.
     // get_avg_pressure_coef, panel.f90:3609-3675: order 2 integrates the quadratic pressure distribution over the panel
@@ -623,10 +623,10 @@ Results Case::post(const std::vector<double>& x, const double* v_inner) const {
     };
     auto fill = [&](std::vector<double>& dst, const char* rule) {
         dst.assign(R.N_cells, 0.);
-        for (int i = 0; i < N_panels; ++i) {
+        parallel_for(N_panels, [&](int i) {
             dst[i] = avg_pressure(i, false, rule);
             if (asym_flow) dst[i + N_panels] = avg_pressure(i, true, rule);
-        }
+        }, 1024);
     };
     if (solver.incompressible_rule) fill(R.C_p_inc, "incompressible");
     if (solver.isentropic_rule) fill(R.C_p_ise, "isentropic");
@@ -650,10 +650,10 @@ Results Case::post(const std::vector<double>& x, const double* v_inner) const {
     else if (pf == "laitone") pr = &R.C_p_lai;
     if (!pr || pr->empty()) throw std::runtime_error(pf + " pressure for forces is not available.");
     R.dC_f.assign(R.N_cells, V3{});
-    for (int i = 0; i < N_panels; ++i) {
+    parallel_for(N_panels, [&](int i) {
         R.dC_f[i] = (-(*pr)[i] * panels[i].A) * panels[i].n_g;
         if (asym_flow) R.dC_f[i + N_panels] = (-(*pr)[i + N_panels] * panels[i].A) * panels[i].n_g_mir;
-    }
+    }, 1024);
     V3 sum{0., 0., 0.};
     for (int i = 0; i < R.N_cells; ++i) sum = sum + R.dC_f[i];
     R.C_F = sum / S_ref;
@@ -673,14 +673,14 @@ Results Case::post(const std::vector<double>& x, const double* v_inner) const {
              C[0][1] * q[0] + C[1][1] * q[1] + C[0][2] * q[2] + 0.5 * C[2][1] * q[3] + C[1][2] * q[4] + 0.5 * C[0][3] * q[5], 0.};
         return mir ? p.J_mir * cross(p.n_g_mir, matvec(p.A_ls_to_g_mir, m)) : p.J * cross(p.n_g, matvec(p.A_ls_to_g, m));
     };
-    for (int i = 0; i < N_panels; ++i) {
+    parallel_for(N_panels, [&](int i) {
         dC_m[i] = cross(panels[i].centr - CG, R.dC_f[i]);
         if (panels[i].order == 2) dC_m[i] = dC_m[i] + moment_about_centroid(panels[i], false);
         if (asym_flow) {
             dC_m[i + N_panels] = cross(panels[i].centr_mir - CG, R.dC_f[i]);  // sic (:2583)
             if (panels[i].order == 2) dC_m[i + N_panels] = dC_m[i + N_panels] + moment_about_centroid(panels[i], true);
         }
-    }
+    }, 1024);
     for (int i = 0; i < R.N_cells; ++i) msum = msum + dC_m[i];
     R.C_M = msum / l_ref;
     if (mirrored && !asym_flow) {
