@@ -15,8 +15,15 @@ namespace mlh {
 inline int host_threads() {
     static const int n = [] {
         if (const char* e = std::getenv("MLH_THREADS")) return std::max(1, std::atoi(e));
-        const unsigned hw = std::thread::hardware_concurrency();
-        return (int)std::min(16u, std::max(1u, hw));
+        unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        // one process per GPU (torchrun / mpirun): every rank runs the same setup, so the cores are shared between the ranks
+        for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE"})
+            if (const char* e = std::getenv(name)) {
+                const int ranks = std::atoi(e);
+                if (ranks > 1) hw = std::max(2u, hw / (unsigned)ranks);
+                break;
+            }
+        return (int)std::min(16u, hw);
     }();
     return n;
 }
