@@ -156,3 +156,62 @@ def test_device_post_needs_a_solution_and_checks_its_tables(ctx):
     assert np.isfinite(out["V_cells"]).all()
     fresh.close()
     case.close()
+
+
+@pytest.mark.parametrize("compressible", [True, False])
+def test_every_pressure_rule_against_the_reference_formulas(compressible):
+    """The rules no reference golden exercises (second-order, slender-body, linear) and the three subsonic corrections, evaluated by
+    the host library (pressure_rules.hpp, the header the device kernel compiles too) against an independent numpy statement of
+    src/flow.f90:313-508 on the cell velocities: a compressible subsonic case with the five rules, and an incompressible one with
+    the corrections (which the reference allows at freestream_mach_number = 0 only)."""
+    import copy
+    from machline_b200 import host
+    inp, _, _ = fixtures.golden_input("test_05")
+    inp = copy.deepcopy(inp)
+    pp = inp.setdefault("post_processing", {})
+    if compressible:
+        inp["flow"]["freestream_mach_number"] = 0.5
+        pp["pressure_rules"] = {"incompressible": True, "isentropic": True, "second-order": True, "slender-body": True, "linear": True}
+        pp["pressure_for_forces"] = "second-order"
+        expect_rules = {1, 2, 3, 4}   # the reference drops the incompressible rule in a compressible flow
+    else:
+        pp["pressure_rules"] = {"incompressible": True, "second-order": True, "slender-body": True, "linear": True}
+        pp["subsonic_pressure_correction"] = {"correction_mach_number": 0.4, "prandtl-glauert": True, "karman-tsien": True, "laitone": True}
+        pp["pressure_for_forces"] = "karman-tsien"
+        expect_rules = {0, 2, 3, 4, 5, 6, 7}
+    case = host.Case(inp, base_dir=fixtures.mesh_root())
+    x = np.random.default_rng(11).standard_normal(case.n_unknown) * 0.05
+    res = case.post(x)
+    t, f = case.post_tables()
+    assert {r for r in range(8) if f.rules & (1 << r)} == expect_rules
+    V = res.V_cells
+    U_inv, M, g, Mc = f.U_inv, f.M_inf, f.gamma, f.M_inf_corr
+    A = np.array(f.A_g_to_c[:]).reshape(3, 3)
+    vp = (V - np.array(f.v_inf[:])) @ A.T                                  # flow_get_v_pert_c :345-356
+    clip = lambda c: np.minimum(np.maximum(c, f.C_P_vac), f.C_P_stag)      # restrict_pressure
+    inc = 1. - (V * V).sum(axis=1) * U_inv * U_inv                         # :313-324
+    with np.errstate(invalid="ignore", divide="ignore"):
+        ise = f.a_ise * (np.power(1. + f.b_ise * inc, f.c_ise) - 1.)       # :327-342
+        ise = np.where(np.isnan(ise), f.C_P_vac, ise)
+        lin = clip(-2. * vp[:, 0] * U_inv)                                 # :416-432
+        sln = clip(lin - (vp[:, 1] ** 2 + vp[:, 2] ** 2) * U_inv ** 2)     # :397-413
+        snd = clip(sln - (1. - M * M) * vp[:, 0] ** 2 * U_inv ** 2)        # :359-394
+        s = np.sqrt(1. - Mc * Mc)
+        pg = inc / s                                                       # :453-466
+        kt = inc / (s + 0.5 * (Mc * Mc / (1. + s)) * inc)                  # :469-487
+        lai = inc / (s + (Mc * Mc * (1. + 0.5 * (g - 1.) * Mc * Mc) / (2. * s)) * inc)   # :490-508
+    want = {"incompressible": inc, "isentropic": ise, "second-order": snd, "slender-body": sln, "linear": lin,
+            "prandtl-glauert": pg, "karman-tsien": kt, "laitone": lai}
+    for r, (rule, ref) in enumerate(want.items()):
+        assert _abi.RULES[r] == rule
+        if r not in expect_rules:
+            continue
+        got = case.result_array(rule)
+        assert got.shape == ref.shape, rule
+        assert np.abs(got - ref).max() <= 1e-13 * max(1., np.abs(ref).max()), rule
+    n = t.n_cells
+    ng = np.ctypeslib.as_array(t.n_g, shape=(n, 3))
+    area = np.ctypeslib.as_array(t.area, shape=(n,))
+    dCf = (-(snd if compressible else kt) * area)[:, None] * ng
+    assert np.abs(dCf - case.result_array("dC_f")).max() <= 1e-13 * np.abs(dCf).max()
+    case.close()
