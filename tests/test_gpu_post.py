@@ -215,3 +215,18 @@ def test_every_pressure_rule_against_the_reference_formulas(compressible):
     dCf = (-(snd if compressible else kt) * area)[:, None] * ng
     assert np.abs(dCf - case.result_array("dC_f")).max() <= 1e-13 * np.abs(dCf).max()
     case.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["test_07", "test_13", "test_21"])
+def test_run_case_device_post(name):
+    """solver.run_case(device_post=True): the public entry point with the device-resident post-processing next to the host's."""
+    from machline_b200 import solver
+    inp, _, _ = fixtures.golden_input(name)
+    r = solver.run_case(inp, base_dir=fixtures.mesh_root(), device_post=True)
+    d = r.device_post
+    assert d is not None and len(d["C_p"]) >= 1
+    assert abs(d["C_p_max"] - r.C_p_max) <= 1e-13 * max(1., abs(r.C_p_max))
+    assert abs(d["C_p_min"] - r.C_p_min) <= 1e-13 * max(1., abs(r.C_p_min))
+    rep = "incompressible" if "incompressible" in d["C_p"] else "isentropic"
+    assert np.abs(d["C_p"][rep] - r.C_p).max() <= 1e-13 * max(1., np.abs(r.C_p).max())
