@@ -107,93 +107,94 @@ struct EdgeRec {
 };
 }  // namespace
 
-// surface_mesh.f90:523-607
-static bool check_panels_adjacent(std::vector<Panel>& panels, int i, int j, int i_endpoints[2], int& edge_index_i,
-                                  int& edge_index_j) {
-    bool already_found_shared = false;
-    int m1 = -1, n1 = -1;
-    Panel& pi = panels[i];
-    Panel& pj = panels[j];
-    for (int m = 0; m < 3; ++m) {
-        for (int n = 0; n < 3; ++n) {
-            if (pi.iv[m] == pj.iv[n]) {
-                if (already_found_shared) {
-                    i_endpoints[1] = pi.iv[m];
-                    if (m1 == 0 && m == 2) std::swap(i_endpoints[0], i_endpoints[1]);
-                    if ((n1 == 0 && n == 2) || (n == 0 && n1 == 2)) {
-                        pj.abutting_panels[2] = i;
-                        edge_index_j = 2;
-                    } else {
-                        n1 = std::min(n, n1);
-                        pj.abutting_panels[n1] = i;
-                        edge_index_j = n1;
-                    }
-                    if (m1 == 0 && m == 2) {
-                        pi.abutting_panels[m] = j;
-                        edge_index_i = m;
-                    } else {
-                        pi.abutting_panels[m1] = j;
-                        edge_index_i = m1;
-                    }
-                    return true;
-                } else {
-                    already_found_shared = true;
-                    i_endpoints[0] = pi.iv[m];
-                    m1 = m;
-                    n1 = n;
-                }
-            }
-        }
-    }
-    return false;
-}
-
-// panel.f90:1293-1354
-static bool check_abutting_mirror_plane(Panel& p, const std::vector<Vertex>& verts, int N_panels, int i_endpoints[2],
-                                        int& edge_index) {
-    bool already_found = false;
-    int m1 = -1;
-    for (int m = 0; m < 3; ++m) {
-        if (verts[p.iv[m]].on_mirror_plane) {
-            if (already_found) {
-                i_endpoints[1] = p.iv[m];
-                if (m1 == 0 && m == 2) std::swap(i_endpoints[0], i_endpoints[1]);
-                if (m - m1 == 1) {
-                    p.abutting_panels[m1] = p.index + N_panels;
-                    edge_index = m1;
-                } else {
-                    p.abutting_panels[m] = p.index + N_panels;
-                    edge_index = m;
-                }
-                return true;
-            } else {
-                already_found = true;
-                i_endpoints[0] = p.iv[m];
-                m1 = m;
-            }
-        }
-    }
-    return false;
-}
-
 // surface_mesh.f90:346-520
+// The reference loops over all pairs of panels (O(N^2)); the outcome -- which panels abut across which edge, and the numbering of
+// the edges in the order of discovery -- is reproduced in three steps:
+//   1 (host threads; reads only): for every panel the panels j > i that share at least two vertex indices with it, ascending -- up
+//     to NB_MAX of them in a flat table (a manifold triangle has at most three neighbours; a panel with more candidates, e.g. at
+//     a non-manifold edge, is flagged and searched again in step 2);
+//   2 (serial, in panel order as the reference's loop, :346-496): the adjacency checks on compact arrays (vertex indices and
+//     abutting panels of all panels, 12 bytes per panel each: the 1.4 KB Panel objects and the vertices' little heap arrays are not
+//     touched), which number the edges;
+//   3 (host threads): the results go into the panels, the edges and the vertices' adjacency lists; the lists are built from the
+//     edge records by a counting sort, in edge order, as the appends of a serial loop leave them (base_geom.f90:163-214).
 void Case::locate_adjacent_panels() {
     std::vector<EdgeRec> recs;
     recs.reserve((size_t)N_panels * 3 / 2 + 16);
-    auto store_adjacent_vertices = [&](const int ep[2], int i_edge) {
-        if (!contains(vertices[ep[0]].adjacent_vertices, ep[1])) vertices[ep[0]].adjacent_vertices.push_back(ep[1]);
-        if (!contains(vertices[ep[1]].adjacent_vertices, ep[0])) vertices[ep[1]].adjacent_vertices.push_back(ep[0]);
-        vertices[ep[0]].adjacent_edges.push_back(i_edge);
-        vertices[ep[1]].adjacent_edges.push_back(i_edge);
+    std::vector<int> ivs((size_t)N_panels * 3), abut((size_t)N_panels * 3, -1);
+    parallel_for(N_panels, [&](int i) {
+        for (int m = 0; m < 3; ++m) ivs[3 * (size_t)i + m] = panels[i].iv[m];
+    }, 4096);
+    std::vector<char> on_mirror(N_verts, 0);
+    for (int v = 0; v < N_verts; ++v) on_mirror[v] = vertices[v].on_mirror_plane ? 1 : 0;
+    auto all_found = [&](int i) { return abut[3 * (size_t)i] != -1 && abut[3 * (size_t)i + 1] != -1 && abut[3 * (size_t)i + 2] != -1; };
+    // panel_check_abutting_panel? no: surface_mesh.f90:523-607 (check_panels_adjacent) on the compact arrays
+    auto check_adjacent = [&](int i, int j, int ep[2], int& edge_index_i, int& edge_index_j) {
+        bool already_found_shared = false;
+        int m1 = -1, n1 = -1;
+        const int* pi = &ivs[3 * (size_t)i];
+        const int* pj = &ivs[3 * (size_t)j];
+        for (int m = 0; m < 3; ++m) {
+            for (int n = 0; n < 3; ++n) {
+                if (pi[m] == pj[n]) {
+                    if (already_found_shared) {
+                        ep[1] = pi[m];
+                        if (m1 == 0 && m == 2) std::swap(ep[0], ep[1]);
+                        if ((n1 == 0 && n == 2) || (n == 0 && n1 == 2)) {
+                            abut[3 * (size_t)j + 2] = i;
+                            edge_index_j = 2;
+                        } else {
+                            n1 = std::min(n, n1);
+                            abut[3 * (size_t)j + n1] = i;
+                            edge_index_j = n1;
+                        }
+                        if (m1 == 0 && m == 2) {
+                            abut[3 * (size_t)i + m] = j;
+                            edge_index_i = m;
+                        } else {
+                            abut[3 * (size_t)i + m1] = j;
+                            edge_index_i = m1;
+                        }
+                        return true;
+                    } else {
+                        already_found_shared = true;
+                        ep[0] = pi[m];
+                        m1 = m;
+                        n1 = n;
+                    }
+                }
+            }
+        }
+        return false;
     };
-    auto all_found = [&](const Panel& p) {
-        return p.abutting_panels[0] != -1 && p.abutting_panels[1] != -1 && p.abutting_panels[2] != -1;
+    // panel.f90:1293-1354 (check_abutting_mirror_plane) on the compact arrays
+    auto check_mirror = [&](int i, int ep[2], int& edge_index) {
+        bool already_found = false;
+        int m1 = -1;
+        const int* pi = &ivs[3 * (size_t)i];
+        for (int m = 0; m < 3; ++m) {
+            if (on_mirror[pi[m]]) {
+                if (already_found) {
+                    ep[1] = pi[m];
+                    if (m1 == 0 && m == 2) std::swap(ep[0], ep[1]);
+                    if (m - m1 == 1) {
+                        abut[3 * (size_t)i + m1] = panels[i].index + N_panels;
+                        edge_index = m1;
+                    } else {
+                        abut[3 * (size_t)i + m] = panels[i].index + N_panels;
+                        edge_index = m;
+                    }
+                    return true;
+                } else {
+                    already_found = true;
+                    ep[0] = pi[m];
+                    m1 = m;
+                }
+            }
+        }
+        return false;
     };
-    // Pass 1 (host threads; reads only): for every panel the panels j > i that share at least two vertex indices with it,
-    // ascending -- up to NB_MAX of them in a flat table (a manifold triangle has at most three neighbours; a panel with more
-    // candidates, e.g. at a non-manifold edge, is flagged and searched again in pass 2).
-    // Pass 2 (serial, in panel order as the reference's loop, surface_mesh.f90:346-496): the adjacency checks, which write both
-    // panels and number the edges in the order of discovery.
+    // ---- step 1 ----
     constexpr int NB_MAX = 4;
     std::vector<int> nb((size_t)N_panels * NB_MAX);
     std::vector<unsigned char> nb_n(N_panels, 0);
@@ -201,7 +202,7 @@ void Case::locate_adjacent_panels() {
         cand.clear();
         out.clear();
         for (int m = 0; m < 3; ++m)
-            for (int j : vertices[panels[i].iv[m]].panels)
+            for (int j : vertices[ivs[3 * (size_t)i + m]].panels)
                 if (j > i) cand.push_back(j);
         std::sort(cand.begin(), cand.end());
         for (size_t c = 0; c < cand.size();) {
@@ -227,11 +228,8 @@ void Case::locate_adjacent_panels() {
                 }
             }
         }, 1);
-        parallel_for(N_verts, [&](int i) {   // room for the usual valence: the lists below grow by push_back
-            vertices[i].adjacent_vertices.reserve(8);
-            vertices[i].adjacent_edges.reserve(8);
-        }, 2048);
     }
+    // ---- step 2 ----
     std::vector<int> cand, over;
     for (int i = 0; i < N_panels; ++i) {
         const int* list = nb.data() + (size_t)i * NB_MAX;
@@ -243,39 +241,38 @@ void Case::locate_adjacent_panels() {
         }
         for (int k = 0; k < n_list; ++k) {
             const int j = list[k];
-            if (all_found(panels[i])) break;  // surface_mesh.f90:373
+            if (all_found(i)) break;  // surface_mesh.f90:373
             int ep[2], ei, ej;
-            if (check_panels_adjacent(panels, i, j, ep, ei, ej)) {
-                int i_edge = (int)recs.size();
-                store_adjacent_vertices(ep, i_edge);
-                recs.push_back({i, j, ep[0], ep[1], ei, ej, false});
-            }
+            if (check_adjacent(i, j, ep, ei, ej)) recs.push_back({i, j, ep[0], ep[1], ei, ej, false});
         }
     }
     if (mirrored) {
         for (int i = 0; i < N_panels; ++i) {
-            if (all_found(panels[i])) continue;
+            if (all_found(i)) continue;
             int ep[2], ei;
-            if (check_abutting_mirror_plane(panels[i], vertices, N_panels, ep, ei)) {
-                int i_edge = (int)recs.size();
-                store_adjacent_vertices(ep, i_edge);
-                recs.push_back({i, i + N_panels, ep[0], ep[1], ei, -1, true});
-            }
+            if (check_mirror(i, ep, ei)) recs.push_back({i, i + N_panels, ep[0], ep[1], ei, -1, true});
         }
     }
     for (int i = 0; i < N_panels; ++i) {
         for (int j = 0; j < 3; ++j) {
-            if (panels[i].abutting_panels[j] == -1) {
-                int ep[2] = {panels[i].iv[j], panels[i].iv[(j + 1) % 3]};
-                int i_edge = (int)recs.size();
-                recs.push_back({i, -1, ep[0], ep[1], j, -1, false});
-                store_adjacent_vertices(ep, i_edge);
-            }
+            if (abut[3 * (size_t)i + j] == -1) recs.push_back({i, -1, ivs[3 * (size_t)i + j], ivs[3 * (size_t)i + (j + 1) % 3], j, -1, false});
         }
     }
+    // ---- step 3 ----
     N_edges = (int)recs.size();
-    edges.assign(N_edges, Edge());
+    std::vector<int> pedge((size_t)N_panels * 3, -1);   // the edge of every panel side (a later edge overwrites, as in a serial loop)
     for (int i = 0; i < N_edges; ++i) {
+        pedge[3 * (size_t)recs[i].panel1 + recs[i].edge_index1] = i;
+        if (recs[i].panel2 < N_panels && recs[i].panel2 >= 0) pedge[3 * (size_t)recs[i].panel2 + recs[i].edge_index2] = i;
+    }
+    parallel_for(N_panels, [&](int i) {
+        for (int m = 0; m < 3; ++m) {
+            panels[i].abutting_panels[m] = abut[3 * (size_t)i + m];
+            if (pedge[3 * (size_t)i + m] >= 0) panels[i].edges[m] = pedge[3 * (size_t)i + m];
+        }
+    }, 4096);
+    edges.assign(N_edges, Edge());
+    parallel_for(N_edges, [&](int i) {
         Edge& e = edges[i];
         e.top_verts[0] = recs[i].vertex1;
         e.top_verts[1] = recs[i].vertex2;
@@ -286,9 +283,29 @@ void Case::locate_adjacent_panels() {
         e.on_mirror_plane = recs[i].on_mirror_plane;
         e.edge_index_for_panel[0] = recs[i].edge_index1;
         e.edge_index_for_panel[1] = recs[i].edge_index2;
-        panels[recs[i].panel1].edges[e.edge_index_for_panel[0]] = i;
-        if (recs[i].panel2 < N_panels && recs[i].panel2 >= 0) panels[recs[i].panel2].edges[e.edge_index_for_panel[1]] = i;
+    }, 4096);
+    // vertex adjacency: the incidences (edge, other endpoint) of every vertex in edge order
+    std::vector<int> start((size_t)N_verts + 1, 0);
+    for (int i = 0; i < N_edges; ++i) {
+        ++start[(size_t)recs[i].vertex1 + 1];
+        ++start[(size_t)recs[i].vertex2 + 1];
     }
+    for (int v = 0; v < N_verts; ++v) start[v + 1] += start[v];
+    std::vector<int> fill(start.begin(), start.end() - 1), inc_edge((size_t)2 * N_edges), inc_other((size_t)2 * N_edges);
+    for (int i = 0; i < N_edges; ++i) {
+        const int a = recs[i].vertex1, b = recs[i].vertex2;
+        inc_edge[fill[a]] = i;
+        inc_other[fill[a]++] = b;
+        inc_edge[fill[b]] = i;
+        inc_other[fill[b]++] = a;
+    }
+    parallel_for(N_verts, [&](int v) {
+        Vertex& vx = vertices[v];
+        vx.adjacent_edges.assign(inc_edge.begin() + start[v], inc_edge.begin() + start[v + 1]);
+        vx.adjacent_vertices.clear();
+        for (int k = start[v]; k < start[v + 1]; ++k)
+            if (!contains(vx.adjacent_vertices, inc_other[k])) vx.adjacent_vertices.push_back(inc_other[k]);
+    }, 2048);
 }
 
 // surface_mesh.f90:610-659, base_geom.f90:163-214
