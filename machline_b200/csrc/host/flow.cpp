@@ -13,8 +13,20 @@ quad sqrt_quad(quad x) { return sqrtq(x); }
 
 // linalg.f90:9-115
 void matinv(int n, const double* a, double* ai) {
-    std::vector<double> d((size_t)n * 2 * n, 0.0);
-    std::vector<int> io(n);
+    // n <= 6 everywhere in the setup (3 x 3 panel frames, 4 x 4 and 6 x 6 fits of the higher-order distributions): work arrays on
+    // the stack -- this runs several times per panel on the host threads, where heap allocations contend
+    double d_small[72];
+    int io_small[6];
+    std::vector<double> d_big;
+    std::vector<int> io_big;
+    double* d = d_small;
+    int* io = io_small;
+    if (n > 6) {
+        d_big.assign((size_t)n * 2 * n, 0.0);
+        io_big.assign(n, 0);
+        d = d_big.data();
+        io = io_big.data();
+    }
     auto D = [&](int i, int k) -> double& { return d[(size_t)i * 2 * n + k]; };
     for (int i = 0; i < n; ++i) io[i] = i;
     for (int i = 0; i < n; ++i)

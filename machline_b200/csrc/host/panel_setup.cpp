@@ -236,7 +236,7 @@ static void transpose_mn(int m, int n, const double* A, double* At) {
 static void calc_M_mu_transform(Panel& p, const std::vector<Vertex>& body_verts, bool calc_mirror, int mirror_plane) {
     const int md = p.mu_dim, Md = p.M_dim;
     const int N_body_verts = (int)body_verts.size();
-    std::vector<double> S_mu((size_t)md * md, 0.), S_inv((size_t)md * md, 0.);
+    double S_mu[36] = {0.}, S_inv[36] = {0.};   // md <= 6: on the stack (this runs once or twice per panel, on the host threads)
     const double(*vls)[2] = calc_mirror ? p.vertices_ls_mir : p.vertices_ls;
     for (int i = 0; i < md; ++i) S_mu[i * md + 0] = 1.;
     for (int i = 0; i < 3; ++i) {
@@ -256,11 +256,11 @@ static void calc_M_mu_transform(Panel& p, const std::vector<Vertex>& body_verts,
             S_mu[i * md + 5] = 0.5 * (y * y);
         }
     }
-    matinv(md, S_mu.data(), S_inv.data());
-    if (p.order == 2) (calc_mirror ? p.S_mu_inv_mir : p.S_mu_inv) = S_inv;
+    matinv(md, S_mu, S_inv);
+    if (p.order == 2) (calc_mirror ? p.S_mu_inv_mir : p.S_mu_inv).assign(S_inv, S_inv + (size_t)md * md);
     std::vector<double>& T = calc_mirror ? p.T_mu_mir : p.T_mu;
     if (p.order == 1) {
-        T = S_inv;
+        T.assign(S_inv, S_inv + (size_t)md * md);
         return;
     }
     std::vector<double> M_mat((size_t)md * Md, 0.);
@@ -304,7 +304,7 @@ static void calc_M_mu_transform(Panel& p, const std::vector<Vertex>& body_verts,
         }
     }
     T.assign((size_t)md * Md, 0.);
-    mm(md, md, Md, S_inv.data(), M_mat.data(), T.data());
+    mm(md, md, Md, S_inv, M_mat.data(), T.data());
 }
 
 // panel.f90:855-969: transformation from the source strengths of this panel and its neighbours across continuous edges ({S})
