@@ -124,8 +124,9 @@ void collapse_duplicate_vertices(const std::vector<V3>& vertex_locs, std::vector
         }
     }
     vertices.assign(N - N_duplicates, Vertex());
-    for (int i = 0; i < N; ++i)
+    parallel_for(N, [&](int i) {   // a unique vertex initialises its own slot
         if (!is_duplicate[i]) vertices[new_ind[i]].init(vertex_locs[i], new_ind[i]);
+    }, 4096);
 }
 
 std::vector<std::string> split_ws(const std::string& line) {

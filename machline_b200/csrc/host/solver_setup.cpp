@@ -292,12 +292,20 @@ void Case::set_permutation() {
             x[i] = -inner(freestream.c_hat_g, loc);
         }
         // insertion_arg_sort (sort.f90:359-388) is a stable ascending sort
-        std::vector<int> P_inv_1(N_unknown);
-        std::iota(P_inv_1.begin(), P_inv_1.end(), 0);
-        std::stable_sort(P_inv_1.begin(), P_inv_1.end(), [&](int a, int b) { return x[a] < x[b]; });
+        // (keys and indices sorted together: the same order as a stable sort of the indices by x[index], without the scattered
+        // reads of the comparator)
+        auto stable_arg_sort = [](const std::vector<double>& key, std::vector<int>& order) {
+            std::vector<std::pair<double, int>> kv(key.size());
+            for (size_t i = 0; i < key.size(); ++i) kv[i] = {key[i], (int)i};
+            std::stable_sort(kv.begin(), kv.end(), [](const std::pair<double, int>& a, const std::pair<double, int>& b) { return a.first < b.first; });
+            order.resize(key.size());
+            for (size_t i = 0; i < key.size(); ++i) order[i] = kv[i].second;
+        };
+        std::vector<int> P_inv_1;
+        stable_arg_sort(x, P_inv_1);
 
         const double huge = std::numeric_limits<double>::max();
-        for (int i = 0; i < (int)P_inv_1.size(); ++i) {
+        parallel_for((int)P_inv_1.size(), [&](int i) {   // reads the mesh, writes x[i]
             int i_cp = P_inv_1[i];
             const ControlPoint& q = cp[i_cp];
             const bool mir = q.is_mirror;
@@ -329,10 +337,9 @@ void Case::set_permutation() {
                 x[i] = huge;
                 for (int j = 0; j < 3; ++j) x[i] = std::min(x[i], key(vertices[panels[i_panel].iv[j]].loc));
             }
-        }
-        std::vector<int> P_inv_2(N_unknown);
-        std::iota(P_inv_2.begin(), P_inv_2.end(), 0);
-        std::stable_sort(P_inv_2.begin(), P_inv_2.end(), [&](int a, int b) { return x[a] < x[b]; });
+        }, 2048);
+        std::vector<int> P_inv_2;
+        stable_arg_sort(x, P_inv_2);
         P.assign(N_cp, -1);
         for (int i = 0; i < N_cp; ++i) P[P_inv_1[P_inv_2[i]]] = i;
     } else {
@@ -363,8 +370,17 @@ void Case::init_solver() {
     } else {
         throw std::runtime_error("'" + f + "' is not a valid formulation.");
     }
+    const bool timing = std::getenv("MLH_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        auto t1 = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "mlh init_solver: %-24s %8.2f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    };
     // init_dirichlet, panel_solver.f90:313-364
     place_internal_vertex_control_points(solver.control_point_offset, solver.control_point_offset_type);
+    lap("control points");
     // set_panel_sources :423-444
     for (auto& p : panels) p.has_sources = (f == "dirichlet-morino") ? true : (p.r < 0);
     // determine_dirichlet_unknowns :447-512
@@ -410,7 +426,9 @@ void Case::init_solver() {
         }
         cp[i].bc = (f == "dirichlet-morino") ? BC_ZERO_POTENTIAL : BC_SF_POTENTIAL;
     }
+    lap("unknowns + conditions");
     set_permutation();
+    lap("set_permutation");
 }
 
 // init_neumann (panel_solver.f90:367-420) for the two overdetermined least-squares formulations: control points at (above) the
