@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <exception>
 #include <mutex>
+#include <system_error>
 #include <thread>
 #include <vector>
 
@@ -41,17 +42,22 @@ void parallel_for(int n, F f, int min_per_thread = 128) {
     std::mutex m;
     std::vector<std::thread> th;
     th.reserve(nt);
+    auto run = [&](int a, int b) {
+        try {
+            for (int i = a; i < b; ++i) f(i);
+        } catch (...) {
+            std::lock_guard<std::mutex> g(m);
+            if (!err) err = std::current_exception();
+        }
+    };
     for (int t = 0; t < nt; ++t) {
         const int a = t * chunk, b = std::min(n, a + chunk);
         if (a >= b) break;
-        th.emplace_back([&, a, b] {
-            try {
-                for (int i = a; i < b; ++i) f(i);
-            } catch (...) {
-                std::lock_guard<std::mutex> g(m);
-                if (!err) err = std::current_exception();
-            }
-        });
+        try {
+            th.emplace_back(run, a, b);
+        } catch (const std::system_error&) {
+            run(a, b);   // no more threads to be had (a process limit): this chunk runs on the caller
+        }
     }
     for (auto& x : th) x.join();
     if (err) std::rethrow_exception(err);
