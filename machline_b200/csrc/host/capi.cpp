@@ -4,6 +4,7 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <new>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -16,8 +17,31 @@ using namespace mlh;
 
 namespace {
 
+// Zero-filled table storage from calloc: for the sizes that matter (220 MB at 280k panels x 2 images) the allocator hands out
+// fresh zero pages, so "zero-filling" costs nothing up front and the first touch happens where the records are written -- on
+// the host threads (put).  A std::vector would write every byte once serially before that.
+template <class T>
+struct ZeroBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    ZeroBuf() = default;
+    ZeroBuf(const ZeroBuf&) = delete;
+    ZeroBuf& operator=(const ZeroBuf&) = delete;
+    ~ZeroBuf() { std::free(p); }
+    void assign_zero(size_t count) {
+        std::free(p);
+        p = static_cast<T*>(std::calloc(count ? count : 1, sizeof(T)));
+        if (!p) throw std::bad_alloc();
+        n = count;
+    }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
 struct PanelTableStore {
-    std::vector<double> centr, A_g_to_ls, vertices_ls, n_hat_ls, b, sqrt_b, J, area, vert_g, T_mu;
+    ZeroBuf<double> centr, A_g_to_ls, vertices_ls, n_hat_ls, b, sqrt_b, J, area, vert_g, T_mu;
     std::vector<int> r, i_vert_d, i_panel_s;
     std::vector<unsigned char> has_sources, image_present;
     int n_panels = 0, n_images = 1, n_cols = 3, in_wake = 0;
@@ -42,27 +66,17 @@ struct PanelTableStore {
         n_cols = ncols;
         in_wake = wake;
         size_t n_rec = (size_t)np * ni;
-        // zero-filled tables; the fresh pages of the large ones (220 MB at 280k panels x 2 images) are first touched on the host
-        // threads (as mesh_io.cpp: fresh_panels), the fill itself then runs on mapped memory
-        auto zeros = [](std::vector<double>& v, size_t n) {
-            v.clear();
-            v.reserve(n);
-            char* const raw = reinterpret_cast<char*>(v.data());
-            const size_t page = 4096, n_pages = (n * sizeof(double) + page - 1) / page;
-            if (raw && n_pages > 64) parallel_for((int)n_pages, [&](int k) { raw[(size_t)k * page] = 0; }, 2048);
-            v.assign(n, 0.);
-        };
-        zeros(centr, n_rec * 3);
-        zeros(A_g_to_ls, n_rec * 9);
-        zeros(vertices_ls, n_rec * 6);
-        zeros(n_hat_ls, n_rec * 6);
-        zeros(b, n_rec * 3);
-        zeros(sqrt_b, n_rec * 3);
-        zeros(J, n_rec);
+        centr.assign_zero(n_rec * 3);
+        A_g_to_ls.assign_zero(n_rec * 9);
+        vertices_ls.assign_zero(n_rec * 6);
+        n_hat_ls.assign_zero(n_rec * 6);
+        b.assign_zero(n_rec * 3);
+        sqrt_b.assign_zero(n_rec * 3);
+        J.assign_zero(n_rec);
         r.assign(n_rec, 1);
-        zeros(area, np);
-        zeros(vert_g, n_rec * 9);
-        zeros(T_mu, n_rec * 9);
+        area.assign_zero(np);
+        vert_g.assign_zero(n_rec * 9);
+        T_mu.assign_zero(n_rec * 9);
         i_vert_d.assign((size_t)np * ncols, -1);
         i_panel_s.assign(np, -1);
         has_sources.assign(np, 0);
